@@ -1,0 +1,21 @@
+"""dynaml_b200 -- a B200-native (sm_100a) drop-in for DynaML's Gaussian-process hot path.
+
+Layout: csrc/ (CUDA kernels + the C ABI of include/dgp_b200.h), _capi (ctypes binding),
+kernels / models / optimization (host-side mirror of the dynaml-core classes on the path).
+Importing the package never touches the GPU; the first Context() does, and raises if the CUDA
+library or an sm_100 device is missing (there is no CPU fallback).
+"""
+from . import _capi
+from ._capi import Context, DgpError, NotPositiveDefinite, default_context
+from .kernels import (AdditiveCovariance, DiracKernel, GenericMaternKernel, LocalScalarKernel, MahalanobisKernel,
+                      PeriodicKernel, RBFKernel, SEKernel, SVMKernelMatrix)
+from .models import AbstractGPRegressionModel, CudaGPRegression, GPRegression, MultGaussianPRV
+from .optimization import CoupledSimulatedAnnealing, GradBasedGlobalOptimizer, GridSearch, ModelTuner
+
+__all__ = [
+    "Context", "DgpError", "NotPositiveDefinite", "default_context",
+    "LocalScalarKernel", "SEKernel", "RBFKernel", "MahalanobisKernel", "GenericMaternKernel", "PeriodicKernel",
+    "DiracKernel", "AdditiveCovariance", "SVMKernelMatrix",
+    "GPRegression", "CudaGPRegression", "AbstractGPRegressionModel", "MultGaussianPRV",
+    "GridSearch", "CoupledSimulatedAnnealing", "GradBasedGlobalOptimizer", "ModelTuner",
+]

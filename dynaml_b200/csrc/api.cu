@@ -1,0 +1,864 @@
+// api.cu -- the C ABI of libdgp_b200.so (include/dgp_b200.h): context, resident training data,
+// energy / gradEnergy / batched energies, fit + predict, kernel-matrix export, and the
+// measurement / building-block hooks used by tests and bench.py.
+#include <math.h>
+#include <stdarg.h>
+
+#include "assemble.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "grad.cuh"
+#include "potrf.cuh"
+#include "solve.cuh"
+
+namespace dgp {
+
+int32_t measure_peaks(Ctx *ctx, double *out, int n);  // peaks.cu
+void dist_destroy(Ctx *ctx);                          // dist.cu
+
+// ------------------------------------------------------------------------------------------------
+int32_t Ctx::fail(int32_t code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  err = buf;
+  return code;
+}
+
+void *Ctx::buf(const char *name, size_t bytes) {
+  auto it = arena.find(name);
+  if (it != arena.end() && it->second.second >= bytes) return it->second.first;
+  if (it != arena.end()) {
+    cudaStreamSynchronize(stream);
+    cudaStreamSynchronize(panel);
+    cudaFree(it->second.first);
+    arena.erase(it);
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    fail(DGP_ERR_OOM, "cudaMalloc(%zu bytes) for '%s' failed: %s", bytes, name, cudaGetErrorString(e));
+    return nullptr;
+  }
+  arena[name] = {p, bytes};
+  return p;
+}
+
+void Ctx::release(const char *name) {
+  auto it = arena.find(name);
+  if (it == arena.end()) return;
+  cudaStreamSynchronize(stream);
+  cudaStreamSynchronize(panel);
+  cudaFree(it->second.first);
+  arena.erase(it);
+}
+
+void Ctx::release_all() {
+  cudaStreamSynchronize(stream);
+  cudaStreamSynchronize(panel);
+  for (auto &kv : arena) cudaFree(kv.second.first);
+  arena.clear();
+}
+
+#define DGP_BUF(var, type, ctx, name, bytes)             \
+  type *var = (type *)(ctx)->buf(name, bytes);           \
+  if (!var) return DGP_ERR_OOM
+
+int32_t parse_spec(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
+  if (!in || !in->hyp) return ctx->fail(DGP_ERR_ARG, "kernel spec / hyp is NULL");
+  int want = -1;
+  switch (in->kind) {
+    case DGP_KERNEL_SE: want = 2; break;
+    case DGP_KERNEL_RBF: want = 1; break;
+    case DGP_KERNEL_ARD_SE: want = d + 1; break;
+    case DGP_KERNEL_MATERN: want = 2; break;
+    case DGP_KERNEL_PERIODIC: want = 3; break;
+    case DGP_KERNEL_DIRAC: want = 1; break;
+    default: return ctx->fail(DGP_ERR_UNSUPPORTED_KERNEL, "unsupported kernel kind %d", in->kind);
+  }
+  if (in->n_hyp != want || want > DGP_MAX_HYP)
+    return ctx->fail(DGP_ERR_ARG, "kernel kind %d with d=%d needs %d hyper-parameters, got %d", in->kind, d, want,
+                     in->n_hyp);
+  out->kind = in->kind;
+  out->n_hyp = in->n_hyp;
+  out->grad_mode = in->grad_mode;
+  out->noise = in->noise;
+  for (int i = 0; i < in->n_hyp; ++i) out->hyp[i] = in->hyp[i];
+  if (in->kind == DGP_KERNEL_MATERN) {
+    int p = (int)floor(fabs(in->hyp[0]));
+    if (p > MAX_MATERN_P) return ctx->fail(DGP_ERR_UNSUPPORTED_KERNEL, "Matern order p=%d > %d", p, MAX_MATERN_P);
+  }
+  return DGP_OK;
+}
+
+namespace {
+
+// Repack host points (either layout) into row-major n_p x dp with zero padding.
+void pack_points(const double *X, int64_t n, int d, int layout, int64_t np, int dp, std::vector<double> &out) {
+  out.assign((size_t)np * dp, 0.0);
+  if (layout == DGP_ROW_MAJOR) {
+    for (int64_t i = 0; i < n; ++i)
+      for (int c = 0; c < d; ++c) out[(size_t)i * dp + c] = X[(size_t)i * d + c];
+  } else {
+    for (int c = 0; c < d; ++c)
+      for (int64_t i = 0; i < n; ++i) out[(size_t)i * dp + c] = X[(size_t)c * n + i];
+  }
+}
+
+struct ScaleVec {
+  double v[128];
+};
+
+__global__ void scale_points_byval_kernel(const double *X, double *Xs, ScaleVec s, int64_t total, int dp) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) Xs[i] = X[i] * s.v[i % dp];
+}
+
+// ARD-SE: Xs = X * diag(1/b).  No-op (returns X) for the other kinds.
+int32_t scaled_points(Ctx *ctx, cudaStream_t st, const Spec &sp, const double *X, int64_t np, int dp, int d,
+                      const char *bufname, const double **out) {
+  if (sp.kind != DGP_KERNEL_ARD_SE) {
+    *out = X;
+    return DGP_OK;
+  }
+  if (dp > 128) return ctx->fail(DGP_ERR_SHAPE, "ARD-SE supports at most 128 features");
+  DGP_BUF(Xs, double, ctx, bufname, (size_t)np * dp * sizeof(double));
+  ScaleVec s;
+  for (int c = 0; c < 128; ++c) s.v[c] = (c < d) ? 1.0 / sp.hyp[1 + c] : 0.0;
+  int64_t total = np * dp;
+  scale_points_byval_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, Xs, s, total, dp);
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  *out = Xs;
+  return DGP_OK;
+}
+
+__global__ void pad_identity_kernel(double *A, int64_t ld, int64_t n, int64_t np) {
+  // rows/cols >= n of the np x np matrix: identity
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= np * np) return;
+  int64_t r = idx % np, c = idx / np;
+  if (r >= n || c >= n) A[r + c * ld] = (r == c) ? 1.0 : 0.0;
+}
+
+void tick(Ctx *ctx, int i) {
+  if (ctx->timing) cudaEventRecord(ctx->tev[i], ctx->stream);
+}
+
+// Enqueue one energy (and optionally gradient-moment) evaluation.  Results land in
+// d_scal[0] = r' K^-1 r, d_scal[1] = sum log L_ii, d_scal[2..] = gradient moments; *d_info != 0 on
+// a failed pivot.  Nothing here synchronises with the host.
+int32_t enqueue_eval(Ctx *ctx, const Data *D, const Spec &sp, bool want_grad, double *d_scal, int *d_info,
+                     int *ns_out) {
+  cudaStream_t S = ctx->stream;
+  const int64_t np = D->Np;
+  DGP_BUF(K, double, ctx, "K", (size_t)np * np * sizeof(double));
+  DGP_BUF(inv, double, ctx, "inv", (size_t)np * TILE * sizeof(double));
+  DGP_BUF(x, double, ctx, "x", (size_t)np * sizeof(double));
+  const double *Xk = nullptr;
+  DGP_TRY(scaled_points(ctx, S, sp, D->X, np, D->dp, D->d, "Xs", &Xk));
+  CovParams cp = make_cov_params(sp, true);
+
+  tick(ctx, 0);
+  AssembleArgs a;
+  a.X1 = Xk;  a.X2 = Xk;  a.dp = D->dp;
+  a.rows = D->N;  a.cols = D->N;  a.rows_p = np;  a.cols_p = np;
+  a.out = K;  a.ld = np;
+  a.symmetric = 1;  a.lower_only = 1;
+  DGP_TRY(assemble(ctx, S, cp, a));
+  tick(ctx, 1);
+  DGP_CUDA_OK(ctx, cudaMemsetAsync(d_info, 0, sizeof(int), S));
+  DGP_TRY(potrf_blocked(ctx, K, np, np, inv, d_info));
+  tick(ctx, 2);
+  DGP_CUDA_OK(ctx, cudaMemcpyAsync(x, D->r, (size_t)np * sizeof(double), cudaMemcpyDeviceToDevice, S));
+  DGP_TRY(trsv_lower_fwd(ctx, S, K, np, inv, np, x));
+  DGP_TRY(trsv_lower_bwd(ctx, S, K, np, inv, np, x));
+  DGP_TRY(dot(ctx, S, D->r, x, np, d_scal + 0));
+  DGP_TRY(diag_log_sum(ctx, S, K, np, np, d_scal + 1));
+  tick(ctx, 3);
+  if (want_grad) {
+    DGP_BUF(W, double, ctx, "W", (size_t)np * np * sizeof(double));
+    DGP_BUF(Kinv, double, ctx, "Kinv", (size_t)np * np * sizeof(double));
+    DGP_TRY(trtri_lower(ctx, K, np, inv, np, W, np, Kinv, np));
+    DGP_TRY(lauum_lower(ctx, W, np, np, Kinv, np));
+    tick(ctx, 4);
+    const int64_t mt = np / TILE, tiles = mt * (mt + 1) / 2;
+    const int nsmax = grad_partials_per_tile(cp, D->dp);
+    DGP_BUF(partials, double, ctx, "partials", (size_t)tiles * nsmax * sizeof(double));
+    GradArgs g;
+    g.X = D->X;  g.Xs = Xk;  g.alpha = x;  g.Kinv = Kinv;  g.ld = np;
+    g.n = D->N;  g.np = np;  g.dp = D->dp;
+    g.partials = partials;  g.sums = d_scal + 2;
+    DGP_TRY(grad_trace(ctx, S, cp, g, ns_out));
+    tick(ctx, 5);
+  }
+  return DGP_OK;
+}
+
+double energy_from(const Data *D, double quad, double logsum) {
+  // AbstractGPRegressionModel.scala:527-529: 0.5*(d + btrace(blog(Lmat)) + rows*log(2*Pi))
+  return 0.5 * (quad + logsum + (double)D->N * log(2.0 * M_PI));
+}
+
+void collect_timings(Ctx *ctx, bool grad) {
+  for (int i = 0; i < 16; ++i) ctx->timings[i] = 0.0;
+  if (!ctx->timing) return;
+  float ms;
+  auto el = [&](int a, int b) { cudaEventElapsedTime(&ms, ctx->tev[a], ctx->tev[b]); return (double)ms; };
+  ctx->timings[0] = el(0, 1);
+  ctx->timings[1] = el(1, 2);
+  ctx->timings[2] = el(2, 3);
+  if (grad) {
+    ctx->timings[3] = el(3, 4);
+    ctx->timings[4] = el(4, 5);
+    ctx->timings[8] = el(0, 5);
+  } else {
+    ctx->timings[8] = el(0, 3);
+  }
+}
+
+}  // namespace
+
+struct Model {
+  Spec spec;
+  int64_t N = 0, Np = 0;
+  int d = 0, dp = 0;
+  double *X = nullptr;    // own copy of the (unscaled) padded training points
+  double *Xk = nullptr;   // points the kernel consumes (ARD: scaled copy, else == X)
+  double *L = nullptr;    // Np x Np
+  double *inv = nullptr;  // Np x 128
+  double *alpha = nullptr;
+  double energy = 0.0;
+};
+
+}  // namespace dgp
+
+struct dgp_model : dgp::Model {};
+
+using namespace dgp;
+
+extern "C" {
+
+const char *dgp_version(void) { return "dgp-b200 0.1 (sm_100a, FP64 DMMA)"; }
+
+int32_t dgp_ctx_create(int32_t device, dgp_ctx **out) {
+  if (!out) return DGP_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return DGP_ERR_CUDA;  // no CPU fallback
+  if (device < 0 || device >= count) return DGP_ERR_ARG;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DGP_ERR_CUDA;
+  if (prop.major < 10) return DGP_ERR_CUDA;  // built for sm_100a only
+  if (cudaSetDevice(device) != cudaSuccess) return DGP_ERR_CUDA;
+  dgp_ctx *ctx = new dgp_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  bool ok = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, lo) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&ctx->panel, cudaStreamNonBlocking, hi) == cudaSuccess &&
+            cudaEventCreate(&ctx->ev_a) == cudaSuccess && cudaEventCreate(&ctx->ev_b) == cudaSuccess;
+  for (int i = 0; i < 16 && ok; ++i) ok = cudaEventCreate(&ctx->tev[i]) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_info, 4096 * sizeof(int)) == cudaSuccess &&
+       cudaMallocHost(&ctx->h_info, 4096 * sizeof(int)) == cudaSuccess &&
+       cudaMallocHost(&ctx->h_scal, 4096 * 160 * sizeof(double)) == cudaSuccess;
+  if (ok) ok = gemm_init(ctx) == DGP_OK && potrf_init(ctx) == DGP_OK;
+  if (!ok) {
+    delete ctx;
+    return DGP_ERR_CUDA;
+  }
+  for (int i = 0; i < 16; ++i) ctx->timings[i] = 0.0;
+  *out = ctx;
+  return DGP_OK;
+}
+
+int32_t dgp_ctx_destroy(dgp_ctx *ctx) {
+  if (!ctx) return DGP_OK;
+  cudaSetDevice(ctx->device);
+  dist_destroy(ctx);
+  ctx->release_all();
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+  for (int i = 0; i < 16; ++i) cudaEventDestroy(ctx->tev[i]);
+  cudaEventDestroy(ctx->ev_a);
+  cudaEventDestroy(ctx->ev_b);
+  cudaFree(ctx->d_info);
+  cudaFreeHost(ctx->h_info);
+  cudaFreeHost(ctx->h_scal);
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->panel);
+  delete ctx;
+  return DGP_OK;
+}
+
+const char *dgp_last_error(const dgp_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
+  if (!ctx || !key) return DGP_ERR_ARG;
+  if (!strcmp(key, "nb")) {
+    if (value < TILE || value % TILE) return ctx->fail(DGP_ERR_ARG, "nb must be a positive multiple of 128");
+    ctx->nb = value;
+  } else if (!strcmp(key, "lookahead")) {
+    ctx->lookahead = value != 0;
+  } else if (!strcmp(key, "timing")) {
+    ctx->timing = value != 0;
+  } else {
+    return ctx->fail(DGP_ERR_ARG, "unknown option '%s'", key);
+  }
+  return DGP_OK;
+}
+
+int32_t dgp_get_timings(const dgp_ctx *ctx, double *ms, int32_t n) {
+  if (!ctx || !ms) return DGP_ERR_ARG;
+  for (int i = 0; i < n; ++i) ms[i] = i < 16 ? ctx->timings[i] : 0.0;
+  return DGP_OK;
+}
+
+// ---- data ------------------------------------------------------------------------------------
+int32_t dgp_data_create(dgp_ctx *ctx, const double *X, int64_t N, int32_t d, int32_t x_layout, const double *y,
+                        const double *mean, dgp_data **out) {
+  if (!ctx || !X || !y || !out) return DGP_ERR_ARG;
+  if (N <= 0 || d <= 0) return ctx->fail(DGP_ERR_SHAPE, "data: N=%lld d=%d", (long long)N, d);
+  cudaSetDevice(ctx->device);
+  dgp_data *D = new dgp_data();
+  D->N = N;
+  D->Np = round_up(N, TILE);
+  D->d = d;
+  D->dp = (int)round_up(d, 4);
+  std::vector<double> hx, hr((size_t)D->Np, 0.0);
+  pack_points(X, N, d, x_layout, D->Np, D->dp, hx);
+  for (int64_t i = 0; i < N; ++i) hr[i] = y[i] - (mean ? mean[i] : 0.0);
+  cudaError_t e1 = cudaMalloc(&D->X, hx.size() * sizeof(double));
+  cudaError_t e2 = cudaMalloc(&D->r, hr.size() * sizeof(double));
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    cudaFree(D->X);
+    cudaFree(D->r);
+    delete D;
+    cudaGetLastError();
+    return ctx->fail(DGP_ERR_OOM, "data: device allocation failed");
+  }
+  cudaMemcpyAsync(D->X, hx.data(), hx.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(D->r, hr.data(), hr.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  DGP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = D;
+  return DGP_OK;
+}
+
+int32_t dgp_data_destroy(dgp_ctx *ctx, dgp_data *D) {
+  if (!D) return DGP_OK;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(D->X);
+  cudaFree(D->r);
+  delete D;
+  return DGP_OK;
+}
+
+// ---- energy / gradient -------------------------------------------------------------------------
+static int32_t energy_impl(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *spec, double *e, double *g) {
+  if (!ctx || !D || !spec) return DGP_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  Spec sp;
+  DGP_TRY(parse_spec(ctx, spec, D->d, &sp));
+  DGP_BUF(d_scal, double, ctx, "scal", 4096 * 160 * sizeof(double));
+  const bool want_grad = g != nullptr;
+  int ns = 0;
+  int32_t st = enqueue_eval(ctx, D, sp, want_grad, d_scal, ctx->d_info, &ns);
+  if (st != DGP_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    return st;
+  }
+  DGP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scal, d_scal, 160 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DGP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  DGP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  collect_timings(ctx, want_grad);
+  if (ctx->h_info[0] != 0) {
+    if (e) *e = INFINITY;
+    if (g)
+      for (int i = 0; i <= sp.n_hyp; ++i) g[i] = nan("");
+    return ctx->fail(DGP_ERR_NOT_PD, "Cholesky failed: pivot %d is not positive", ctx->h_info[0] - 1);
+  }
+  if (e) *e = energy_from(D, ctx->h_scal[0], ctx->h_scal[1]);
+  if (g) grad_finish(sp, D->d, ctx->h_scal + 2, ns, g);
+  return DGP_OK;
+}
+
+int32_t dgp_energy(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec, double *e) {
+  if (!e) return DGP_ERR_ARG;
+  return energy_impl(ctx, data, spec, e, nullptr);
+}
+
+int32_t dgp_energy_grad(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec, double *e, double *g) {
+  if (!g) return DGP_ERR_ARG;
+  return energy_impl(ctx, data, spec, e, g);
+}
+
+int32_t dgp_energy_batch(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *specs, int32_t n, double *e,
+                         int32_t *status) {
+  if (!ctx || !D || !specs || !e || !status || n < 0) return DGP_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  DGP_BUF(d_scal, double, ctx, "scal", 4096 * 160 * sizeof(double));
+  // Candidates are enqueued back to back on the same streams in chunks of 4096; the workspace is
+  // reused in stream order, so the GPU never waits for the host between candidates.
+  for (int32_t base = 0; base < n; base += 4096) {
+    const int32_t cnt = (n - base < 4096) ? n - base : 4096;
+    std::vector<int32_t> pre(cnt, DGP_OK);
+    for (int32_t i = 0; i < cnt; ++i) {
+      Spec sp;
+      int ns = 0;
+      int32_t st = parse_spec(ctx, &specs[base + i], D->d, &sp);
+      if (st == DGP_OK) st = enqueue_eval(ctx, D, sp, false, d_scal + (size_t)i * 160, ctx->d_info + i, &ns);
+      pre[i] = st;
+      if (st == DGP_ERR_CUDA || st == DGP_ERR_OOM) {
+        cudaStreamSynchronize(ctx->stream);
+        return st;
+      }
+    }
+    DGP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scal, d_scal, (size_t)cnt * 160 * sizeof(double), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    DGP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    DGP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int32_t i = 0; i < cnt; ++i) {
+      if (pre[i] != DGP_OK) {
+        status[base + i] = pre[i];
+        e[base + i] = nan("");
+      } else if (ctx->h_info[i] != 0) {
+        status[base + i] = DGP_ERR_NOT_PD;
+        e[base + i] = INFINITY;
+      } else {
+        status[base + i] = DGP_OK;
+        e[base + i] = energy_from(D, ctx->h_scal[(size_t)i * 160], ctx->h_scal[(size_t)i * 160 + 1]);
+      }
+    }
+  }
+  collect_timings(ctx, false);
+  return DGP_OK;
+}
+
+// ---- fit / predict ------------------------------------------------------------------------------
+int32_t dgp_model_destroy(dgp_ctx *ctx, dgp_model *m) {
+  if (!m) return DGP_OK;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  if (m->Xk != m->X) cudaFree(m->Xk);
+  cudaFree(m->X);
+  cudaFree(m->L);
+  cudaFree(m->inv);
+  cudaFree(m->alpha);
+  delete m;
+  return DGP_OK;
+}
+
+int32_t dgp_fit(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *spec, dgp_model **out) {
+  if (!ctx || !D || !spec || !out) return DGP_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  *out = nullptr;
+  Spec sp;
+  DGP_TRY(parse_spec(ctx, spec, D->d, &sp));
+  cudaStream_t S = ctx->stream;
+  const int64_t np = D->Np;
+  dgp_model *m = new dgp_model();
+  m->spec = sp;
+  m->N = D->N;  m->Np = np;  m->d = D->d;  m->dp = D->dp;
+  bool ok = cudaMalloc(&m->X, (size_t)np * D->dp * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&m->L, (size_t)np * np * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&m->inv, (size_t)np * TILE * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&m->alpha, (size_t)np * sizeof(double)) == cudaSuccess;
+  if (ok && sp.kind == DGP_KERNEL_ARD_SE) ok = cudaMalloc(&m->Xk, (size_t)np * D->dp * sizeof(double)) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    dgp_model_destroy(ctx, m);
+    return ctx->fail(DGP_ERR_OOM, "fit: device allocation failed for N=%lld", (long long)D->N);
+  }
+  auto bail = [&](int32_t st) {
+    cudaStreamSynchronize(S);
+    dgp_model_destroy(ctx, m);
+    return st;
+  };
+  cudaMemcpyAsync(m->X, D->X, (size_t)np * D->dp * sizeof(double), cudaMemcpyDeviceToDevice, S);
+  if (sp.kind == DGP_KERNEL_ARD_SE) {
+    ScaleVec s;
+    for (int c = 0; c < 128; ++c) s.v[c] = (c < D->d) ? 1.0 / sp.hyp[1 + c] : 0.0;
+    int64_t total = np * D->dp;
+    scale_points_byval_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S>>>(m->X, m->Xk, s, total, D->dp);
+  } else {
+    m->Xk = m->X;
+  }
+  CovParams cp = make_cov_params(sp, true);
+  DGP_BUF(d_scal, double, ctx, "scal", 4096 * 160 * sizeof(double));
+  tick(ctx, 0);
+  AssembleArgs a;
+  a.X1 = m->Xk;  a.X2 = m->Xk;  a.dp = D->dp;
+  a.rows = D->N;  a.cols = D->N;  a.rows_p = np;  a.cols_p = np;
+  a.out = m->L;  a.ld = np;  a.symmetric = 1;  a.lower_only = 1;
+  int32_t st = assemble(ctx, S, cp, a);
+  if (st != DGP_OK) return bail(st);
+  tick(ctx, 1);
+  cudaMemsetAsync(ctx->d_info, 0, sizeof(int), S);
+  st = potrf_blocked(ctx, m->L, np, np, m->inv, ctx->d_info);
+  if (st != DGP_OK) return bail(st);
+  tick(ctx, 2);
+  cudaMemcpyAsync(m->alpha, D->r, (size_t)np * sizeof(double), cudaMemcpyDeviceToDevice, S);
+  st = trsv_lower_fwd(ctx, S, m->L, np, m->inv, np, m->alpha);
+  if (st == DGP_OK) st = trsv_lower_bwd(ctx, S, m->L, np, m->inv, np, m->alpha);
+  if (st == DGP_OK) st = dot(ctx, S, D->r, m->alpha, np, d_scal);
+  if (st == DGP_OK) st = diag_log_sum(ctx, S, m->L, np, np, d_scal + 1);
+  if (st != DGP_OK) return bail(st);
+  tick(ctx, 3);
+  cudaMemcpyAsync(ctx->h_scal, d_scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, S);
+  cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, S);
+  cudaError_t ce = cudaStreamSynchronize(S);
+  if (ce != cudaSuccess) return bail(ctx->fail(DGP_ERR_CUDA, "fit: %s", cudaGetErrorString(ce)));
+  collect_timings(ctx, false);
+  if (ctx->h_info[0] != 0)
+    return bail(ctx->fail(DGP_ERR_NOT_PD, "Cholesky failed: pivot %d is not positive", ctx->h_info[0] - 1));
+  m->energy = energy_from(D, ctx->h_scal[0], ctx->h_scal[1]);
+  *out = m;
+  return DGP_OK;
+}
+
+int32_t dgp_model_energy(dgp_ctx *ctx, const dgp_model *m, double *e) {
+  if (!ctx || !m || !e) return DGP_ERR_ARG;
+  *e = m->energy;
+  return DGP_OK;
+}
+
+int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t M, int32_t x_layout,
+                    const double *mean_s, double *mean, double *cov, int64_t ldcov, double *lo, double *hi,
+                    double sigma) {
+  if (!ctx || !m || !Xs || !mean || M <= 0) return DGP_ERR_ARG;
+  if (cov && ldcov < M) return ctx->fail(DGP_ERR_SHAPE, "predict: ldcov < M");
+  if ((lo == nullptr) != (hi == nullptr)) return ctx->fail(DGP_ERR_ARG, "predict: lo and hi go together");
+  cudaSetDevice(ctx->device);
+  cudaStream_t S = ctx->stream;
+  const int64_t np = m->Np, mp = round_up(M, TILE);
+  const int dp = m->dp;
+  const bool need_cov = cov != nullptr || lo != nullptr;
+
+  std::vector<double> hx;
+  pack_points(Xs, M, m->d, x_layout, mp, dp, hx);
+  DGP_BUF(Xt, double, ctx, "Xt", (size_t)mp * dp * sizeof(double));
+  DGP_BUF(Ks, double, ctx, "Ks", (size_t)np * mp * sizeof(double));
+  DGP_BUF(dmean, double, ctx, "pmean", (size_t)mp * 3 * sizeof(double));
+  double *dbase = dmean + mp, *dbar = dmean + 2 * mp;
+  std::vector<double> hbase((size_t)mp, 0.0);
+  if (mean_s)
+    for (int64_t i = 0; i < M; ++i) hbase[i] = mean_s[i];
+  DGP_CUDA_OK(ctx, cudaMemcpyAsync(Xt, hx.data(), hx.size() * sizeof(double), cudaMemcpyHostToDevice, S));
+  DGP_CUDA_OK(ctx, cudaMemcpyAsync(dbase, hbase.data(), (size_t)mp * sizeof(double), cudaMemcpyHostToDevice, S));
+  const double *Xtk = nullptr;
+  DGP_TRY(scaled_points(ctx, S, m->spec, Xt, mp, dp, m->d, "Xts", &Xtk));
+
+  // K* = k(X, X*) : no noise (AbstractGPRegressionModel.scala:279-286)
+  CovParams cpx = make_cov_params(m->spec, false);
+  tick(ctx, 0);
+  {
+    AssembleArgs a;
+    a.X1 = m->Xk;  a.X2 = Xtk;  a.dp = dp;
+    a.rows = m->N;  a.cols = M;  a.rows_p = np;  a.cols_p = mp;
+    a.out = Ks;  a.ld = np;
+    DGP_TRY(assemble(ctx, S, cpx, a));
+  }
+  tick(ctx, 1);
+  // mean = m(X*) + K*' alpha   (:463)
+  DGP_TRY(gemv_t(ctx, S, Ks, np, np, mp, m->alpha, dbase, dmean));
+  tick(ctx, 2);
+  double *C = nullptr;
+  if (need_cov) {
+    C = (double *)ctx->buf("pcov", (size_t)mp * mp * sizeof(double));
+    if (!C) return DGP_ERR_OOM;
+    // K** = k(X*, X*), no noise (:288-295); padding = identity
+    AssembleArgs a;
+    a.X1 = Xtk;  a.X2 = Xtk;  a.dp = dp;
+    a.rows = M;  a.cols = M;  a.rows_p = mp;  a.cols_p = mp;
+    a.out = C;  a.ld = mp;  a.symmetric = 1;  a.lower_only = 1;
+    DGP_TRY(assemble(ctx, S, cpx, a));
+    // V = L^-1 K*  (blocked forward substitution on tensor cores, in place in Ks)
+    const int64_t nblk = np / TILE;
+    for (int64_t b = 0; b < nblk; ++b) {
+      GemmArgs d;  // V_b = inv(L_bb) * B_b, in place: a CTA reads exactly the tile it writes
+      d.A = m->inv + b * TILE * TILE;  d.lda = TILE;  d.a_kmajor = 0;
+      d.B = Ks + b * TILE;  d.ldb = np;  d.b_kmajor = 1;
+      d.C = Ks + b * TILE;  d.ldc = np;
+      d.M = TILE;  d.N = (int)mp;  d.K = TILE;
+      DGP_TRY(gemm(ctx, S, d));
+      const int64_t rb = (b + 1) * TILE;
+      if (rb >= np) break;
+      GemmArgs u;  // B[rb:] -= L[rb:, b] * V_b
+      u.A = m->L + rb + b * TILE * np;  u.lda = np;  u.a_kmajor = 0;
+      u.B = Ks + b * TILE;  u.ldb = np;  u.b_kmajor = 1;
+      u.C = Ks + rb;  u.ldc = np;
+      u.M = (int)(np - rb);  u.N = (int)mp;  u.K = TILE;
+      u.alpha = -1.0;  u.beta = 1.0;
+      DGP_TRY(gemm(ctx, S, u));
+    }
+    tick(ctx, 3);
+    GemmArgs s;  // Sigma* = K** - V' V  (lower tiles)   (:452-461)
+    s.A = Ks;  s.lda = np;  s.a_kmajor = 1;
+    s.B = Ks;  s.ldb = np;  s.b_kmajor = 1;
+    s.C = C;  s.ldc = mp;
+    s.M = (int)mp;  s.N = (int)mp;  s.K = (int)np;
+    s.alpha = -1.0;  s.beta = 1.0;  s.lower_only = 1;
+    DGP_TRY(gemm(ctx, S, s));
+    DGP_TRY(mirror_lower(ctx, S, C, mp, mp));
+    tick(ctx, 4);
+  }
+  DGP_CUDA_OK(ctx, cudaMemcpyAsync(mean, dmean, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, S));
+  if (cov)
+    DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(cov, ldcov * sizeof(double), C, mp * sizeof(double), M * sizeof(double), M,
+                                       cudaMemcpyDeviceToHost, S));
+  int32_t ret = DGP_OK;
+  if (lo) {
+    // error bars: mean -/+ |sigma| * chol(Sigma*) . 1   (BlockedMultiVariateGaussian.scala:58-68)
+    DGP_BUF(Lp, double, ctx, "plpost", (size_t)mp * mp * sizeof(double));
+    DGP_BUF(pinv, double, ctx, "pinv", (size_t)mp * TILE * sizeof(double));
+    DGP_TRY(copy_block(ctx, S, C, mp, Lp, mp, mp, mp));
+    DGP_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_info, 0, sizeof(int), S));
+    DGP_TRY(potrf_blocked(ctx, Lp, mp, mp, pinv, ctx->d_info));
+    DGP_TRY(lower_row_sums(ctx, S, Lp, mp, mp, dbar));
+    std::vector<double> hbar((size_t)M);
+    DGP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, S));
+    DGP_CUDA_OK(ctx, cudaMemcpyAsync(hbar.data(), dbar, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, S));
+    DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
+    if (ctx->h_info[0] != 0) {
+      for (int64_t i = 0; i < M; ++i) lo[i] = hi[i] = nan("");
+      ret = ctx->fail(DGP_ERR_NOT_PD, "posterior covariance is not positive definite (pivot %d)", ctx->h_info[0] - 1);
+    } else {
+      const double mult = fabs(sigma);
+      for (int64_t i = 0; i < M; ++i) {
+        lo[i] = mean[i] - hbar[i] * mult;
+        hi[i] = mean[i] + hbar[i] * mult;
+      }
+    }
+  }
+  DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
+  for (int i = 0; i < 16; ++i) ctx->timings[i] = 0.0;
+  if (ctx->timing) {
+    float ms;
+    cudaEventElapsedTime(&ms, ctx->tev[0], ctx->tev[1]);  ctx->timings[5] = ms;
+    if (need_cov) {
+      cudaEventElapsedTime(&ms, ctx->tev[2], ctx->tev[3]);  ctx->timings[6] = ms;
+      cudaEventElapsedTime(&ms, ctx->tev[3], ctx->tev[4]);  ctx->timings[7] = ms;
+      cudaEventElapsedTime(&ms, ctx->tev[0], ctx->tev[4]);  ctx->timings[8] = ms;
+    }
+  }
+  return ret;
+}
+
+// ---- kernel-matrix export ------------------------------------------------------------------------
+int32_t dgp_kernel_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec, const double *X1, int64_t N1, const double *X2,
+                          int64_t N2, int32_t d, int32_t x_layout, double *out, int64_t ld, int32_t add_noise) {
+  if (!ctx || !spec || !X1 || !out || N1 <= 0 || d <= 0) return DGP_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const bool sym = X2 == nullptr;
+  if (sym) N2 = N1;
+  if (N2 <= 0 || ld < N1) return ctx->fail(DGP_ERR_SHAPE, "kernel_matrix: bad N2 / ld");
+  Spec sp;
+  DGP_TRY(parse_spec(ctx, spec, d, &sp));
+  cudaStream_t S = ctx->stream;
+  const int64_t n1p = round_up(N1, TILE), n2p = round_up(N2, TILE);
+  const int dp = (int)round_up(d, 4);
+  std::vector<double> h1, h2;
+  pack_points(X1, N1, d, x_layout, n1p, dp, h1);
+  DGP_BUF(A1, double, ctx, "km_x1", h1.size() * sizeof(double));
+  DGP_CUDA_OK(ctx, cudaMemcpyAsync(A1, h1.data(), h1.size() * sizeof(double), cudaMemcpyHostToDevice, S));
+  double *A2 = A1;
+  if (!sym) {
+    pack_points(X2, N2, d, x_layout, n2p, dp, h2);
+    A2 = (double *)ctx->buf("km_x2", h2.size() * sizeof(double));
+    if (!A2) return DGP_ERR_OOM;
+    DGP_CUDA_OK(ctx, cudaMemcpyAsync(A2, h2.data(), h2.size() * sizeof(double), cudaMemcpyHostToDevice, S));
+  }
+  const double *B1 = nullptr, *B2 = nullptr;
+  DGP_TRY(scaled_points(ctx, S, sp, A1, n1p, dp, d, "km_x1s", &B1));
+  if (sym) B2 = B1;
+  else DGP_TRY(scaled_points(ctx, S, sp, A2, n2p, dp, d, "km_x2s", &B2));
+  DGP_BUF(Kd, double, ctx, "km_out", (size_t)n1p * n2p * sizeof(double));
+  CovParams cp = make_cov_params(sp, sym && add_noise);
+  AssembleArgs a;
+  a.X1 = B1;  a.X2 = B2;  a.dp = dp;
+  a.rows = N1;  a.cols = N2;  a.rows_p = n1p;  a.cols_p = n2p;
+  a.out = Kd;  a.ld = n1p;
+  a.symmetric = sym ? 1 : 0;
+  tick(ctx, 0);
+  DGP_TRY(assemble(ctx, S, cp, a));
+  tick(ctx, 1);
+  DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(out, ld * sizeof(double), Kd, n1p * sizeof(double), N1 * sizeof(double), N2,
+                                     cudaMemcpyDeviceToHost, S));
+  DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
+  for (int i = 0; i < 16; ++i) ctx->timings[i] = 0.0;
+  if (ctx->timing) {
+    float ms;
+    cudaEventElapsedTime(&ms, ctx->tev[0], ctx->tev[1]);
+    ctx->timings[0] = ms;
+  }
+  return DGP_OK;
+}
+
+// ---- measurement hooks ---------------------------------------------------------------------------
+int32_t dgp_measure_peaks(dgp_ctx *ctx, double *out, int32_t n) {
+  if (!ctx || !out) return DGP_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  return measure_peaks(ctx, out, n);
+}
+
+int32_t dgp_time_phase(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *spec, int32_t phase, int32_t reps,
+                       double *avg_ms) {
+  if (!ctx || !D || !spec || !avg_ms || reps <= 0) return DGP_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  Spec sp;
+  DGP_TRY(parse_spec(ctx, spec, D->d, &sp));
+  cudaStream_t S = ctx->stream;
+  const int64_t np = D->Np;
+  DGP_BUF(K, double, ctx, "K", (size_t)np * np * sizeof(double));
+  DGP_BUF(inv, double, ctx, "inv", (size_t)np * TILE * sizeof(double));
+  const double *Xk = nullptr;
+  DGP_TRY(scaled_points(ctx, S, sp, D->X, np, D->dp, D->d, "Xs", &Xk));
+  CovParams cp = make_cov_params(sp, true);
+  AssembleArgs a;
+  a.X1 = Xk;  a.X2 = Xk;  a.dp = D->dp;
+  a.rows = D->N;  a.cols = D->N;  a.rows_p = np;  a.cols_p = np;
+  a.out = K;  a.ld = np;  a.symmetric = 1;  a.lower_only = 1;
+  double total = 0.0;
+  for (int r = 0; r < reps; ++r) {
+    float ms = 0.f;
+    if (phase == 0) {
+      DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_a, S));
+      DGP_TRY(assemble(ctx, S, cp, a));
+      DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_b, S));
+    } else if (phase == 1) {
+      DGP_TRY(assemble(ctx, S, cp, a));
+      DGP_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_info, 0, sizeof(int), S));
+      DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_a, S));
+      DGP_TRY(potrf_blocked(ctx, K, np, np, inv, ctx->d_info));
+      DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_b, S));
+    } else if (phase == 2) {
+      // the dominant kernel in isolation: one full-size trailing update C -= P P^T with K = nb
+      const int64_t w = ctx->nb < np ? ctx->nb : np;
+      if (r == 0) DGP_TRY(assemble(ctx, S, cp, a));
+      GemmArgs g;
+      g.A = K + w;  g.lda = np;  g.B = K + w;  g.ldb = np;
+      g.C = K + w + w * np;  g.ldc = np;
+      g.M = (int)(np - w);  g.N = (int)(np - w);  g.K = (int)w;
+      g.alpha = -1e-9;  g.beta = 1.0;  g.lower_only = 1;
+      DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_a, S));
+      DGP_TRY(gemm(ctx, S, g));
+      DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_b, S));
+    } else {
+      return ctx->fail(DGP_ERR_ARG, "time_phase: unknown phase %d", phase);
+    }
+    DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
+    DGP_CUDA_OK(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    total += ms;
+  }
+  *avg_ms = total / reps;
+  return DGP_OK;
+}
+
+int32_t dgp_test_gemm(dgp_ctx *ctx, int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K, double alpha,
+                      const double *A, int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc,
+                      int32_t lower_only, double *ms_out) {
+  if (!ctx || !A || !B || !C || M <= 0 || N <= 0 || K <= 0) return DGP_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStream_t S = ctx->stream;
+  const int64_t mp = round_up(M, TILE), npd = round_up(N, TILE), kp = round_up(K, TILE);
+  // padded device copies, zero filled
+  const int64_t a_rows = transA ? kp : mp, a_cols = transA ? mp : kp;
+  const int64_t b_rows = transB ? npd : kp, b_cols = transB ? kp : npd;
+  DGP_BUF(dA, double, ctx, "tg_a", (size_t)a_rows * a_cols * sizeof(double));
+  DGP_BUF(dB, double, ctx, "tg_b", (size_t)b_rows * b_cols * sizeof(double));
+  DGP_BUF(dC, double, ctx, "tg_c", (size_t)mp * npd * sizeof(double));
+  DGP_CUDA_OK(ctx, cudaMemsetAsync(dA, 0, (size_t)a_rows * a_cols * sizeof(double), S));
+  DGP_CUDA_OK(ctx, cudaMemsetAsync(dB, 0, (size_t)b_rows * b_cols * sizeof(double), S));
+  DGP_CUDA_OK(ctx, cudaMemsetAsync(dC, 0, (size_t)mp * npd * sizeof(double), S));
+  const int64_t ar = transA ? K : M, ac = transA ? M : K;
+  const int64_t br = transB ? N : K, bc = transB ? K : N;
+  DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(dA, a_rows * sizeof(double), A, lda * sizeof(double), ar * sizeof(double), ac,
+                                     cudaMemcpyHostToDevice, S));
+  DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(dB, b_rows * sizeof(double), B, ldb * sizeof(double), br * sizeof(double), bc,
+                                     cudaMemcpyHostToDevice, S));
+  DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(dC, mp * sizeof(double), C, ldc * sizeof(double), M * sizeof(double), N,
+                                     cudaMemcpyHostToDevice, S));
+  GemmArgs g;
+  g.A = dA;  g.lda = a_rows;  g.a_kmajor = transA ? 1 : 0;
+  g.B = dB;  g.ldb = b_rows;  g.b_kmajor = transB ? 0 : 1;
+  g.C = dC;  g.ldc = mp;
+  g.M = (int)mp;  g.N = (int)npd;  g.K = (int)kp;
+  g.alpha = alpha;  g.beta = beta;
+  g.lower_only = lower_only && mp == npd;
+  DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_a, S));
+  DGP_TRY(gemm(ctx, S, g));
+  DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_b, S));
+  DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(C, ldc * sizeof(double), dC, mp * sizeof(double), M * sizeof(double), N,
+                                     cudaMemcpyDeviceToHost, S));
+  DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+  if (ms_out) *ms_out = ms;
+  return DGP_OK;
+}
+
+int32_t dgp_test_potrf(dgp_ctx *ctx, int64_t n, double *A, int64_t lda, double *Linv, double *Ainv,
+                       double *logdet_half, double *ms_out) {
+  if (!ctx || !A || n <= 0 || lda < n) return DGP_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStream_t S = ctx->stream;
+  const int64_t np = round_up(n, TILE);
+  DGP_BUF(dA, double, ctx, "tp_a", (size_t)np * np * sizeof(double));
+  DGP_BUF(inv, double, ctx, "tp_inv", (size_t)np * TILE * sizeof(double));
+  DGP_BUF(d_scal, double, ctx, "scal", 4096 * 160 * sizeof(double));
+  DGP_CUDA_OK(ctx, cudaMemsetAsync(dA, 0, (size_t)np * np * sizeof(double), S));
+  DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(dA, np * sizeof(double), A, lda * sizeof(double), n * sizeof(double), n,
+                                     cudaMemcpyHostToDevice, S));
+  pad_identity_kernel<<<(unsigned)((np * np + 255) / 256), 256, 0, S>>>(dA, np, n, np);
+  DGP_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_info, 0, sizeof(int), S));
+  DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_a, S));
+  DGP_TRY(potrf_blocked(ctx, dA, np, np, inv, ctx->d_info));
+  DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_b, S));
+  DGP_TRY(diag_log_sum(ctx, S, dA, np, np, d_scal));
+  double *dW = nullptr, *dKi = nullptr;
+  if (Linv || Ainv) {
+    dW = (double *)ctx->buf("tp_w", (size_t)np * np * sizeof(double));
+    dKi = (double *)ctx->buf("tp_ki", (size_t)np * np * sizeof(double));
+    if (!dW || !dKi) return DGP_ERR_OOM;
+    DGP_CUDA_OK(ctx, cudaMemsetAsync(dW, 0, (size_t)np * np * sizeof(double), S));
+    DGP_TRY(trtri_lower(ctx, dA, np, inv, np, dW, np, dKi, np));
+    if (Ainv) {
+      DGP_TRY(lauum_lower(ctx, dW, np, np, dKi, np));
+      DGP_TRY(mirror_lower(ctx, S, dKi, np, np));
+    }
+  }
+  DGP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scal, d_scal, sizeof(double), cudaMemcpyDeviceToHost, S));
+  DGP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, S));
+  DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+  if (ms_out) *ms_out = ms;
+  if (ctx->h_info[0] != 0)
+    return ctx->fail(DGP_ERR_NOT_PD, "Cholesky failed: pivot %d is not positive", ctx->h_info[0] - 1);
+  // L: the strictly-upper tiles were never touched (they still hold the input); zero them on the host side
+  DGP_CUDA_OK(ctx, cudaMemcpy2D(A, lda * sizeof(double), dA, np * sizeof(double), n * sizeof(double), n,
+                                cudaMemcpyDeviceToHost));
+  for (int64_t c = 0; c < n; ++c)
+    for (int64_t r = 0; r < c; ++r) A[r + c * lda] = 0.0;
+  if (Linv) {
+    DGP_CUDA_OK(ctx, cudaMemcpy2D(Linv, n * sizeof(double), dW, np * sizeof(double), n * sizeof(double), n,
+                                  cudaMemcpyDeviceToHost));
+    for (int64_t c = 0; c < n; ++c)
+      for (int64_t r = 0; r < c; ++r) Linv[r + c * n] = 0.0;
+  }
+  if (Ainv)
+    DGP_CUDA_OK(ctx, cudaMemcpy2D(Ainv, n * sizeof(double), dKi, np * sizeof(double), n * sizeof(double), n,
+                                  cudaMemcpyDeviceToHost));
+  if (logdet_half) *logdet_half = ctx->h_scal[0];
+  return DGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,29 @@
+// assemble.cuh -- kernel-matrix assembly interface.
+#pragma once
+#include "common.cuh"
+#include "covfn.cuh"
+
+namespace dgp {
+
+struct AssembleArgs {
+  // out(i - row_off, j - col_off) = k(X1[i], X2[j]) for the tile grid covering
+  // [row_off, row_off + rows_p) x [col_off, col_off + cols_p); point sets are row-major n x dp on
+  // the device (dp a multiple of 4, zero padded) and long enough for the padded ranges.
+  const double *X1 = nullptr;
+  const double *X2 = nullptr;
+  int dp = 0;
+  int64_t rows = 0, cols = 0;       // real extents (global indices >= these are padding)
+  int64_t rows_p = 0, cols_p = 0;   // extents of the produced block, multiples of 128
+  int64_t row_off = 0, col_off = 0;
+  double *out = nullptr;
+  int64_t ld = 0;
+  int symmetric = 0;   // X1 == X2 as point sets: padding becomes the identity, noise applies
+  int lower_only = 0;  // only tiles on/below the diagonal (requires rows_p == cols_p, offsets equal)
+};
+
+int32_t assemble(Ctx *ctx, cudaStream_t st, const CovParams &cp, const AssembleArgs &a);
+// Xs[i][c] = X[i][c] * inv_b[c]  (ARD-SE: MahalanobisKernel.scala:122-132 folded into the inputs)
+int32_t scale_points(Ctx *ctx, cudaStream_t st, const double *X, double *Xs, const double *d_inv_b, int64_t n,
+                     int dp);
+
+}  // namespace dgp

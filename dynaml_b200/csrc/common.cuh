@@ -1,0 +1,92 @@
+// common.cuh -- context, workspace arena and small helpers shared by every translation unit of
+// libdgp_b200.so.  Host-side plumbing only; the kernels live in the other files.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dgp_b200.h"
+
+namespace dgp {
+
+constexpr int TILE = 128;  // edge of the leaf blocks / GEMM CTA tiles; every padded dimension is a multiple
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------------------------
+// Context: one GPU, two streams (main + high-priority panel stream for look-ahead), a grow-only
+// arena of named device buffers so that repeated energy evaluations never call cudaMalloc.
+// ---------------------------------------------------------------------------------------------
+struct DistState;  // dist.cu
+
+struct Ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;  // main stream (trailing updates, assembly, solves)
+  cudaStream_t panel = nullptr;   // high-priority stream (leaf factorisations, panels) for look-ahead
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  std::vector<cudaEvent_t> ev_pool;  // look-ahead fork/join events
+  cudaEvent_t tev[16];               // phase timing events
+  std::string err;
+  std::map<std::string, std::pair<void *, size_t>> arena;
+  int64_t nb = 256;   // outer Cholesky block
+  int lookahead = 1;
+  int timing = 1;     // record per-phase events
+  double timings[16];
+  int *d_info = nullptr;  // device-side status word(s): [0] = first failing pivot index + 1, 0 = ok
+  int *h_info = nullptr;  // pinned mirror
+  double *h_scal = nullptr;  // pinned scratch for scalar read-back (64 doubles)
+  DistState *dist = nullptr;
+
+  int32_t fail(int32_t code, const char *fmt, ...);
+  // Named grow-only buffer.  Returns nullptr (and sets err) on OOM.
+  void *buf(const char *name, size_t bytes);
+  void release(const char *name);
+  void release_all();
+};
+
+#define DGP_CUDA_OK(ctx, expr)                                                               \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return (ctx)->fail(_e == cudaErrorMemoryAllocation ? DGP_ERR_OOM : DGP_ERR_CUDA,       \
+                         "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define DGP_TRY(expr)                \
+  do {                               \
+    int32_t _s = (expr);             \
+    if (_s != DGP_OK) return _s;     \
+  } while (0)
+
+// Device-resident, padded training set.
+struct Data {
+  int64_t N = 0;    // real points
+  int64_t Np = 0;   // padded to a multiple of the outer block
+  int d = 0;        // real feature count
+  int dp = 0;       // padded to a multiple of 4 (zero columns; exact for every distance used here)
+  double *X = nullptr;  // Np x dp, row-major (point i at X + i*dp), pad rows zero
+  double *r = nullptr;  // y - m(X), length Np, pad entries zero
+};
+
+// Host copy of a kernel spec with derived constants.
+struct Spec {
+  int kind = 0;
+  int n_hyp = 0;
+  int grad_mode = 0;
+  double hyp[DGP_MAX_HYP];
+  double noise = 0.0;
+};
+
+int32_t parse_spec(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out);
+
+}  // namespace dgp
+
+struct dgp_ctx : dgp::Ctx {};
+struct dgp_data : dgp::Data {};

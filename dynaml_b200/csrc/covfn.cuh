@@ -1,0 +1,108 @@
+// covfn.cuh -- device-side covariance functions and their hyper-parameter derivatives.
+// Each formula restates the reference's scalar closure (file:line in the comments); the
+// host-side CovParams::make() folds the hyper-parameters into the constants used here.
+#pragma once
+#include <math.h>
+#include "common.cuh"
+
+namespace dgp {
+
+constexpr int MAX_MATERN_P = 8;
+constexpr int MAX_SUMS = 132;  // gradient moment accumulators (ARD exact mode: 1 + d, + noise)
+
+struct CovParams {
+  int kind = 0;
+  int p = 0;           // Matern order
+  int grad_mode = 0;
+  int l1 = 0;          // 1: the kernel consumes |x-y|_1 (periodic), else |x-y|_2^2
+  double a2 = 1.0;     // SE/ARD: amplitude^2, periodic: sigma^2, Dirac: |s|, else 1
+  double c1 = 0.0;     // SE/RBF: 1/(2 l^2); ARD: 0.5 (inputs pre-scaled by 1/b_i); Matern: sqrt(2nu)/l;
+                       // periodic: pi*frequency
+  double c2 = 0.0;     // Matern: sqrt(8nu)/l; periodic: 2/l^2
+  double c3 = 0.0;     // Matern: l; periodic: pi*frequency/l^2 (the reference's gradient "k" factor)
+  double coef[MAX_MATERN_P + 1];  // Matern: Gamma(p+1)/Gamma(2p+1) * (p+i)!/(i!(p-i)!), i = 0..p
+  double noise_abs = 0.0;         // |noiseLevel| of the Dirac noise model, added where |x-y|_2 == 0
+};
+
+// Value of the covariance from the pair distance (`dist` = |x-y|^2, or |x-y|_1 when cp.l1).
+template <int KIND>
+__device__ __forceinline__ double cov_value(const CovParams &cp, double dist) {
+  if (KIND == DGP_KERNEL_SE || KIND == DGP_KERNEL_RBF || KIND == DGP_KERNEL_ARD_SE) {
+    // RBFKernel.scala:42-43, 79-80, 131-132:  a^2 exp(-|x-y|^2 / (2 l^2))
+    return cp.a2 * exp(-dist * cp.c1);
+  } else if (KIND == DGP_KERNEL_MATERN) {
+    // GenericMaternKernel.scala:55-68
+    double r = sqrt(dist);
+    double u = cp.c2 * r;
+    double s = cp.coef[0];
+    for (int i = 1; i <= cp.p; ++i) s = s * u + cp.coef[i];
+    return exp(-cp.c1 * r) * s;
+  } else if (KIND == DGP_KERNEL_PERIODIC) {
+    // PeriodicKernel.scala:34-46:  sigma^2 exp(-2 sin^2(pi f |x-y|_1) / l^2)
+    double sn = sin(dist * cp.c1);
+    return cp.a2 * exp(-cp.c2 * sn * sn);
+  } else {
+    // DiracKernel.scala:43-47
+    return dist == 0.0 ? cp.a2 : 0.0;
+  }
+}
+
+// Runtime-dispatched variant for the cold paths.
+__device__ __forceinline__ double cov_value_rt(const CovParams &cp, double dist) {
+  switch (cp.kind) {
+    case DGP_KERNEL_SE:
+    case DGP_KERNEL_RBF:
+    case DGP_KERNEL_ARD_SE: return cov_value<DGP_KERNEL_SE>(cp, dist);
+    case DGP_KERNEL_MATERN: return cov_value<DGP_KERNEL_MATERN>(cp, dist);
+    case DGP_KERNEL_PERIODIC: return cov_value<DGP_KERNEL_PERIODIC>(cp, dist);
+    default: return cov_value<DGP_KERNEL_DIRAC>(cp, dist);
+  }
+}
+
+// Host: fold a Spec into CovParams.  `noise` < 0 is legal (the reference takes abs()).
+inline CovParams make_cov_params(const Spec &s, bool with_noise) {
+  CovParams cp;
+  cp.kind = s.kind;
+  cp.grad_mode = s.grad_mode;
+  cp.noise_abs = with_noise ? fabs(s.noise) : 0.0;
+  for (int i = 0; i <= MAX_MATERN_P; ++i) cp.coef[i] = 0.0;
+  switch (s.kind) {
+    case DGP_KERNEL_SE:
+      cp.a2 = s.hyp[1] * s.hyp[1];
+      cp.c1 = 1.0 / (2.0 * s.hyp[0] * s.hyp[0]);
+      break;
+    case DGP_KERNEL_RBF:
+      cp.a2 = 1.0;
+      cp.c1 = 1.0 / (2.0 * s.hyp[0] * s.hyp[0]);
+      break;
+    case DGP_KERNEL_ARD_SE:
+      cp.a2 = s.hyp[0] * s.hyp[0];
+      cp.c1 = 0.5;
+      break;
+    case DGP_KERNEL_MATERN: {
+      int p = (int)floor(fabs(s.hyp[0]));  // setHyperParameters floors |p| (GenericMaternKernel.scala:48-53)
+      double nu = p + 0.5, l = s.hyp[1];
+      cp.p = p;
+      cp.c1 = sqrt(2.0 * nu) / l;
+      cp.c2 = sqrt(8.0 * nu) / l;
+      cp.c3 = l;
+      double lead = exp(lgamma((double)p + 1.0) - lgamma(2.0 * p + 1.0));
+      auto fact = [](int n) { double f = 1.0; for (int i = 2; i <= n; ++i) f *= i; return f; };
+      for (int i = 0; i <= p; ++i) cp.coef[i] = lead * (fact(p + i) / (fact(i) * fact(p - i)));
+      break;
+    }
+    case DGP_KERNEL_PERIODIC:
+      cp.l1 = 1;
+      cp.a2 = s.hyp[0] * s.hyp[0];
+      cp.c1 = M_PI * s.hyp[2];
+      cp.c2 = 2.0 / (s.hyp[1] * s.hyp[1]);
+      cp.c3 = M_PI * s.hyp[2] / (s.hyp[1] * s.hyp[1]);
+      break;
+    case DGP_KERNEL_DIRAC:
+      cp.a2 = fabs(s.hyp[0]);
+      break;
+  }
+  return cp;
+}
+
+}  // namespace dgp

@@ -1,0 +1,42 @@
+// gemm.cuh -- interface of the FP64 tensor-core (DMMA) GEMM that carries every O(N^3) step of the
+// path: Cholesky panel and trailing updates, the triangular inverse, L^-T L^-1, and the
+// prediction TRSM/SYRK.
+#pragma once
+#include "common.cuh"
+
+namespace dgp {
+
+// Per-tile restriction of the contraction range, used to skip the structurally-zero half of a
+// triangular operand.  (m0, n0) is the origin of the 128x128 output tile.
+enum KMode {
+  K_FULL = 0,
+  K_GE_COL = 1,      // k in [n0, K)        : op(B) is lower triangular  (B[k][n] = 0 for k < n)
+  K_LT_ROWEND = 2,   // k in [0, m0 + 128)  : op(A) is lower triangular  (A[m][k] = 0 for k > m)
+  K_GE_ROW = 3       // k in [m0, K)        : op(A) is upper triangular  (A[m][k] = 0 for k < m), lower output
+};
+
+struct GemmArgs {
+  // C[M x N] = alpha * op(A)[M x K] * op(B)[K x N] + beta * C, everything column-major.
+  //   a_kmajor == 0: op(A)(m,k) = A[m + k*lda]   (A stored M x K)
+  //   a_kmajor == 1: op(A)(m,k) = A[k + m*lda]   (A stored K x M, i.e. op(A) = A^T)
+  //   b_kmajor == 0: op(B)(k,n) = B[n + k*ldb]   (B stored N x K, i.e. op(B) = B^T)
+  //   b_kmajor == 1: op(B)(k,n) = B[k + n*ldb]   (B stored K x N)
+  const double *A = nullptr;
+  const double *B = nullptr;
+  double *C = nullptr;
+  int64_t lda = 0, ldb = 0, ldc = 0;
+  int M = 0, N = 0, K = 0;  // multiples of 128, 128, 16
+  double alpha = 1.0, beta = 0.0;
+  int a_kmajor = 0, b_kmajor = 0;
+  int lower_only = 0;  // square C: only tiles with m0 >= n0
+  int kmode = K_FULL;
+  int reverse = 0;     // launch heavy tiles first when the k-range grows with the tile index
+  int batch = 1;
+  int64_t strideA = 0, strideB = 0, strideC = 0;
+};
+
+// Enqueue on `stream`.  Returns DGP_OK or a CUDA error recorded on ctx.
+int32_t gemm(Ctx *ctx, cudaStream_t stream, const GemmArgs &args);
+int32_t gemm_init(Ctx *ctx);  // opt in to the large dynamic shared memory once per context
+
+}  // namespace dgp

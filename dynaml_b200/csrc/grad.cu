@@ -1,0 +1,319 @@
+// grad.cu -- the hyper-parameter gradient traces of gradEnergy without materialising dK/dtheta.
+//
+// Reference (CORE/models/gp/AbstractGPRegressionModel.scala:231-241): for every theta it builds
+// the full N x N matrix dK/dtheta (SVMKernel.scala:251-307), multiplies alpha alpha^T by it (an
+// N^3 GEMM), runs two N x N multi-RHS block solves, and takes the trace.  Algebraically
+//     g_theta = sum_ij (alpha_i alpha_j - (K^-1)_ij) * dK_ij/dtheta ,
+// so one streaming pass over the lower tiles of K^-1 that re-derives dK_ij/dtheta from the pair
+// distance in registers gives every g_theta at once.  HBM-read bound (8 bytes per pair).
+//
+// The kernel accumulates kind-specific "moments" S_q = sum_ij M_ij * f_q(x_i, x_j); grad_finish()
+// maps them to the reference's per-hyper-parameter derivatives on the host.
+#include "grad.cuh"
+
+namespace dgp {
+
+namespace {
+
+constexpr int GT = 128;
+constexpr int GTHREADS = 256;
+
+enum Mode { M_SE = 0, M_ARD_REF = 1, M_ARD_EXACT = 2, M_MATERN = 3, M_PERIODIC = 4, M_DIRAC = 5 };
+
+template <int MODE, int DP>
+struct NSums {
+  // [last] is always the noise moment sum M_ij 1[|x_i - x_j| == 0]
+  static constexpr int value = (MODE == M_SE) ? 3 : (MODE == M_ARD_REF) ? 3 : (MODE == M_ARD_EXACT) ? (DP + 2)
+                               : (MODE == M_MATERN) ? 2 : (MODE == M_PERIODIC) ? 3 : 2;
+};
+
+// Per-pair contribution.  `dist` is |x-y|^2 (for ARD: of the pre-scaled inputs), `plain2` the
+// unscaled |x-y|^2 (ARD reference mode), `sq[c]` the unscaled squared differences (ARD exact).
+template <int MODE, int DP>
+__device__ __forceinline__ void accumulate(const CovParams &cp, double m, double dist, double plain2, const double *sq,
+                                           double *s) {
+  constexpr int NS = NSums<MODE, DP>::value;
+  if (dist == 0.0) s[NS - 1] += m;
+  if (MODE == M_SE) {
+    // RBFKernel.scala:45-52, 82-87: d/dl = k |x-y|^2 / |l|^3 ; d/da = 2 a exp(.)
+    double e = exp(-dist * cp.c1);
+    s[0] = fma(m * e, dist, s[0]);
+    s[1] = fma(m, e, s[1]);
+  } else if (MODE == M_ARD_REF) {
+    // RBFKernel.scala:134-145: d/dh = 2 k / h ; d/db_i = k |x-y|_2^2 / b_i^3 (same for every i, defect D2)
+    double e = exp(-dist * cp.c1);
+    s[0] = fma(m, e, s[0]);
+    s[1] = fma(m * e, plain2, s[1]);
+  } else if (MODE == M_ARD_EXACT) {
+    double e = exp(-dist * cp.c1);
+    s[0] = fma(m, e, s[0]);
+    double me = m * e;
+#pragma unroll
+    for (int c = 0; c < DP; ++c) s[1 + c] = fma(me, sq[c], s[1 + c]);
+  } else if (MODE == M_MATERN) {
+    // GenericMaternKernel.scala:70-97: dk/dl = diffLead*sumTerm + diffSum*leadingTerm
+    double r = sqrt(dist);
+    double u = cp.c2 * r;
+    double sum = cp.coef[0], q = (double)cp.p * cp.coef[0];
+    for (int i = 1; i <= cp.p; ++i) {
+      sum = sum * u + cp.coef[i];
+      q = q * u + (double)(cp.p - i) * cp.coef[i];
+    }
+    double lead = exp(-cp.c1 * r);
+    // q currently holds sum_i (p-i) coef_i u^(p-i) / u^0 evaluated by Horner on the same powers
+    double dk = (cp.c1 * r * (lead * sum) - lead * q) / cp.c3;
+    s[0] = fma(m, dk, s[0]);
+  } else if (MODE == M_PERIODIC) {
+    // PeriodicKernel.scala:48-62
+    double sn = sin(dist * cp.c1);
+    double k = cp.a2 * exp(-cp.c2 * sn * sn);
+    double kap = cp.c3 * dist;
+    s[0] = fma(m, k, s[0]);
+    s[1] = fma(m * k, sin(2.0 * kap) * kap, s[1]);
+  } else {
+    // DiracKernel.scala:49-53: value / |s|
+    if (dist == 0.0) s[0] += m;
+  }
+}
+
+template <int MODE, int DP>
+__global__ void __launch_bounds__(GTHREADS) grad_trace_kernel(CovParams cp, GradArgs a) {
+  constexpr int NS = NSums<MODE, DP>::value;
+  extern __shared__ __align__(16) double sm[];
+  // layout: column points (GT x DP) | scaled column points (ARD only) | alpha_j (GT) | reduction (8 x NS)
+  constexpr bool ARD = (MODE == M_ARD_REF || MODE == M_ARD_EXACT);
+  double *sx = sm;
+  double *sxs = sm + GT * DP;
+  double *sal = sm + (ARD ? 2 : 1) * GT * DP;
+  double *red = sal + GT;
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 63, ty = tid >> 6;
+  int64_t tlin = blockIdx.x;
+  int ti = (int)((sqrt(8.0 * (double)tlin + 1.0) - 1.0) * 0.5);
+  while ((int64_t)ti * (ti + 1) / 2 > tlin) --ti;
+  while ((int64_t)(ti + 1) * (ti + 2) / 2 <= tlin) ++ti;
+  const int tj = (int)(tlin - (int64_t)ti * (ti + 1) / 2);
+  const int64_t m0 = (int64_t)ti * GT, n0 = (int64_t)tj * GT;
+
+  {
+    const double2 *src = reinterpret_cast<const double2 *>(a.X + n0 * DP);
+    double2 *dst = reinterpret_cast<double2 *>(sx);
+    for (int i = tid; i < GT * DP / 2; i += GTHREADS) dst[i] = src[i];
+    if (ARD) {
+      const double2 *src2 = reinterpret_cast<const double2 *>(a.Xs + n0 * DP);
+      double2 *dst2 = reinterpret_cast<double2 *>(sxs);
+      for (int i = tid; i < GT * DP / 2; i += GTHREADS) dst2[i] = src2[i];
+    }
+    if (tid < GT) sal[tid] = a.alpha[n0 + tid];
+  }
+
+  const int64_t r0 = m0 + 2 * tx;
+  double x0[DP], x1[DP];
+  double xs0[ARD ? DP : 1], xs1[ARD ? DP : 1];
+#pragma unroll
+  for (int c = 0; c < DP; ++c) {
+    x0[c] = a.X[r0 * DP + c];
+    x1[c] = a.X[(r0 + 1) * DP + c];
+  }
+  if (ARD) {
+#pragma unroll
+    for (int c = 0; c < DP; ++c) {
+      xs0[c] = a.Xs[r0 * DP + c];
+      xs1[c] = a.Xs[(r0 + 1) * DP + c];
+    }
+  }
+  const double al0 = a.alpha[r0], al1 = a.alpha[r0 + 1];
+  __syncthreads();
+
+  double s[NS];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) s[q] = 0.0;
+
+  const double *kinv = a.Kinv + r0 + n0 * a.ld;
+  for (int cc = 0; cc < GT / 4; ++cc) {
+    const int j = ty + 4 * cc;
+    const int64_t col = n0 + j;
+    const double2 kv = *reinterpret_cast<const double2 *>(kinv + (int64_t)j * a.ld);
+    const double aj = sal[j];
+    double d0 = 0.0, d1 = 0.0, p0 = 0.0, p1 = 0.0;
+    double sq0[MODE == M_ARD_EXACT ? DP : 1], sq1[MODE == M_ARD_EXACT ? DP : 1];
+#pragma unroll
+    for (int c = 0; c < DP; ++c) {
+      const double y = sx[j * DP + c];
+      const double e0 = x0[c] - y, e1 = x1[c] - y;
+      if (MODE == M_PERIODIC) {
+        d0 += fabs(e0);
+        d1 += fabs(e1);
+      } else if (ARD) {
+        const double ys = sxs[j * DP + c];
+        const double f0 = xs0[c] - ys, f1 = xs1[c] - ys;
+        d0 = fma(f0, f0, d0);
+        d1 = fma(f1, f1, d1);
+        if (MODE == M_ARD_EXACT) {
+          sq0[c] = e0 * e0;
+          sq1[c] = e1 * e1;
+        } else {
+          p0 = fma(e0, e0, p0);
+          p1 = fma(e1, e1, p1);
+        }
+      } else {
+        d0 = fma(e0, e0, d0);
+        d1 = fma(e1, e1, d1);
+      }
+    }
+    // weights: strictly-lower pairs count twice (symmetry), the diagonal once, everything
+    // above the diagonal or in the padding not at all
+    double w0 = (r0 > col) ? 2.0 : (r0 == col ? 1.0 : 0.0);
+    double w1 = (r0 + 1 > col) ? 2.0 : (r0 + 1 == col ? 1.0 : 0.0);
+    if (r0 >= a.n || col >= a.n) w0 = 0.0;
+    if (r0 + 1 >= a.n || col >= a.n) w1 = 0.0;
+    if (w0 != 0.0) accumulate<MODE, DP>(cp, w0 * (al0 * aj - kv.x), d0, p0, sq0, s);
+    if (w1 != 0.0) accumulate<MODE, DP>(cp, w1 * (al1 * aj - kv.y), d1, p1, sq1, s);
+  }
+
+  // ---- deterministic block reduction --------------------------------------------------------
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    double v = s[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp * NS + q] = v;
+  }
+  __syncthreads();
+  if (tid < NS) {
+    double v = 0.0;
+    for (int wdx = 0; wdx < GTHREADS / 32; ++wdx) v += red[wdx * NS + tid];
+    a.partials[(int64_t)blockIdx.x * NS + tid] = v;
+  }
+}
+
+// sums[q] = sum over tiles of partials[tile][q], fixed order
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *partials, int64_t tiles, int ns,
+                                                               double *sums) {
+  __shared__ double sh[1024];
+  const int q = blockIdx.x;
+  double v = 0.0;
+  for (int64_t t = threadIdx.x; t < tiles; t += blockDim.x) v += partials[t * ns + q];
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sums[q] = sh[0];
+}
+
+template <int MODE, int DP>
+int32_t launch(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArgs &a, int64_t tiles, int *ns_out) {
+  constexpr int NS = NSums<MODE, DP>::value;
+  constexpr bool ARD = (MODE == M_ARD_REF || MODE == M_ARD_EXACT);
+  size_t smem = ((size_t)(ARD ? 2 : 1) * GT * DP + GT + (GTHREADS / 32) * NS) * sizeof(double);
+  if (smem > 48 * 1024)
+    DGP_CUDA_OK(ctx, cudaFuncSetAttribute(grad_trace_kernel<MODE, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+  grad_trace_kernel<MODE, DP><<<(unsigned)tiles, GTHREADS, smem, st>>>(cp, a);
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  reduce_partials_kernel<<<NS, 1024, 0, st>>>(a.partials, tiles, NS, a.sums);
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  *ns_out = NS;
+  return DGP_OK;
+}
+
+template <int MODE>
+int32_t launch_dp(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArgs &a, int64_t tiles, int *ns) {
+  switch (a.dp) {
+    case 4: return launch<MODE, 4>(ctx, st, cp, a, tiles, ns);
+    case 8: return launch<MODE, 8>(ctx, st, cp, a, tiles, ns);
+    case 12: return launch<MODE, 12>(ctx, st, cp, a, tiles, ns);
+    case 16: return launch<MODE, 16>(ctx, st, cp, a, tiles, ns);
+    case 20: return launch<MODE, 20>(ctx, st, cp, a, tiles, ns);
+    case 24: return launch<MODE, 24>(ctx, st, cp, a, tiles, ns);
+    case 32: return launch<MODE, 32>(ctx, st, cp, a, tiles, ns);
+    default:
+      return ctx->fail(DGP_ERR_SHAPE, "gradEnergy supports up to 32 features (multiple-of-4 padded), got dp=%d", a.dp);
+  }
+}
+
+int mode_of(const CovParams &cp) {
+  switch (cp.kind) {
+    case DGP_KERNEL_SE:
+    case DGP_KERNEL_RBF: return M_SE;
+    case DGP_KERNEL_ARD_SE: return cp.grad_mode == DGP_GRAD_EXACT ? M_ARD_EXACT : M_ARD_REF;
+    case DGP_KERNEL_MATERN: return M_MATERN;
+    case DGP_KERNEL_PERIODIC: return M_PERIODIC;
+    default: return M_DIRAC;
+  }
+}
+
+}  // namespace
+
+int grad_partials_per_tile(const CovParams &cp, int dp) {
+  switch (mode_of(cp)) {
+    case M_ARD_EXACT: return dp + 2;
+    case M_MATERN:
+    case M_DIRAC: return 2;
+    default: return 3;
+  }
+}
+
+int32_t grad_trace(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArgs &a, int *ns) {
+  if (a.np % GT) return ctx->fail(DGP_ERR_SHAPE, "grad_trace: padded n must be a multiple of 128");
+  const int64_t mt = a.np / GT, tiles = mt * (mt + 1) / 2;
+  switch (mode_of(cp)) {
+    case M_SE: return launch_dp<M_SE>(ctx, st, cp, a, tiles, ns);
+    case M_ARD_REF: return launch_dp<M_ARD_REF>(ctx, st, cp, a, tiles, ns);
+    case M_ARD_EXACT: return launch_dp<M_ARD_EXACT>(ctx, st, cp, a, tiles, ns);
+    case M_MATERN: return launch_dp<M_MATERN>(ctx, st, cp, a, tiles, ns);
+    case M_PERIODIC: return launch_dp<M_PERIODIC>(ctx, st, cp, a, tiles, ns);
+    default: return launch_dp<M_DIRAC>(ctx, st, cp, a, tiles, ns);
+  }
+}
+
+// Map the moments to the reference's derivatives, in the order [hyp..., noise].
+void grad_finish(const Spec &sp, int d, const double *S, int ns, double *g) {
+  const double qnan = nan("");
+  const double noise_m = S[ns - 1];
+  switch (sp.kind) {
+    case DGP_KERNEL_SE: {
+      double l = sp.hyp[0], a = sp.hyp[1];
+      g[0] = a * a * S[0] / (fabs(l) * fabs(l) * fabs(l));  // k |x-y|^2 / |l|^3, k = a^2 e
+      g[1] = 2.0 * a * S[1];
+      break;
+    }
+    case DGP_KERNEL_RBF: {
+      double l = sp.hyp[0];
+      g[0] = S[0] / (fabs(l) * fabs(l) * fabs(l));
+      break;
+    }
+    case DGP_KERNEL_ARD_SE: {
+      double h = sp.hyp[0];
+      g[0] = 2.0 * (h * h * S[0]) / h;  // 2 k / h
+      for (int c = 0; c < d; ++c) {
+        double b = sp.hyp[1 + c];
+        double m = (sp.grad_mode == DGP_GRAD_EXACT) ? S[1 + c] : S[1];
+        g[1 + c] = h * h * m / (b * b * b);  // math.pow(b, 3.0): signed, as the reference
+      }
+      break;
+    }
+    case DGP_KERNEL_MATERN:
+      g[0] = qnan;  // "p" has no derivative in the reference (blocked)
+      g[1] = S[0];
+      break;
+    case DGP_KERNEL_PERIODIC: {
+      double sg = sp.hyp[0], l = sp.hyp[1], f = sp.hyp[2];
+      double s2 = sg * sg;
+      g[0] = 2.0 * S[0] / sg;
+      g[1] = 4.0 * s2 * S[1] / l;
+      g[2] = -2.0 * s2 * S[1] / f;
+      break;
+    }
+    case DGP_KERNEL_DIRAC:
+      g[0] = (sp.hyp[0] == 0.0) ? qnan : S[0];  // |s| 1[..] / |s|
+      break;
+  }
+  g[sp.n_hyp] = (sp.noise == 0.0) ? qnan : noise_m;
+}
+
+}  // namespace dgp

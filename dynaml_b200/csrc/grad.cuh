@@ -1,0 +1,24 @@
+// grad.cuh -- gradient trace pass interface.
+#pragma once
+#include "common.cuh"
+#include "covfn.cuh"
+
+namespace dgp {
+
+struct GradArgs {
+  const double *X = nullptr;      // np x dp row-major points
+  const double *Xs = nullptr;     // ARD only: points pre-scaled by 1/b_c
+  const double *alpha = nullptr;  // K^-1 r, length np (padding zero)
+  const double *Kinv = nullptr;   // lower tiles of K^-1, column-major
+  int64_t ld = 0;
+  int64_t n = 0, np = 0;
+  int dp = 0;
+  double *partials = nullptr;     // tiles x ns scratch
+  double *sums = nullptr;         // ns moments (device)
+};
+
+int grad_partials_per_tile(const CovParams &cp, int dp);
+int32_t grad_trace(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArgs &a, int *ns);
+void grad_finish(const Spec &sp, int d, const double *S, int ns, double *g);
+
+}  // namespace dgp

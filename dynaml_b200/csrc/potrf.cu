@@ -1,0 +1,260 @@
+// potrf.cu -- right-looking blocked Cholesky with look-ahead, the triangular inverse and
+// K^-1 = L^-T L^-1, all driven through the DMMA GEMM of gemm.cu.
+//
+// Reference semantics (CORE/algebra/bcholesky.scala:85-125): cholesky(A11); L21 = A21 inv(L11)^T;
+// recurse on A22 - L21 L21^T.  The reference multiplies by an explicit inverse of the diagonal
+// block, and so do we: the 128x128 leaf kernel returns both L11 and inv(L11), which turns every
+// triangular solve of the path into a tensor-core GEMM.
+#include "potrf.cuh"
+#include "gemm.cuh"
+
+namespace dgp {
+
+namespace {
+
+constexpr int LB = 128;          // leaf block
+constexpr int LDL = LB + 1;      // padded leading dimension in shared memory
+constexpr int LEAF_THREADS = 256;
+constexpr size_t LEAF_SMEM = (size_t)(LB * LDL + LB) * sizeof(double);
+
+// Cholesky + triangular inverse of one 128x128 diagonal block, entirely in shared memory.
+//   S(r,c) at S[c*LDL + r].  Lower triangle: L.  Strict upper triangle: the running rows of
+//   W = L^-1 stored transposed (W(i,j), i > j, lives at S(j,i)); dinv[] holds 1/L(k,k) = W(k,k).
+__global__ void __launch_bounds__(LEAF_THREADS, 1)
+leaf_potrf_inv_kernel(double *A, int64_t lda, double *Inv, int *info, int pivot_base) {
+  extern __shared__ __align__(16) double S[];
+  double *dinv = S + LB * LDL;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int idx = tid; idx < LB * LB; idx += LEAF_THREADS) {
+    int r = idx & (LB - 1), c = idx >> 7;
+    S[c * LDL + r] = (r >= c) ? A[r + (int64_t)c * lda] : 0.0;
+  }
+  __syncthreads();
+
+  // ---- factorisation: unblocked right-looking, one column per step ---------------------------
+  for (int j = 0; j < LB; ++j) {
+    double d = S[j * LDL + j];
+    if (!(d > 0.0)) {  // also catches NaN; uniform across the CTA
+      if (tid == 0) atomicCAS(info, 0, pivot_base + j + 1);
+      d = 1.0;
+    }
+    const double l = sqrt(d);
+    const double li = 1.0 / l;
+    __syncthreads();  // everyone has read the pivot before it is overwritten
+    if (tid == 0) {
+      S[j * LDL + j] = l;
+      dinv[j] = li;
+    }
+    if (tid < LB - 1 - j) S[j * LDL + j + 1 + tid] *= li;
+    __syncthreads();
+    for (int c = j + 1 + warp; c < LB; c += LEAF_THREADS / 32) {
+      const double lcj = S[j * LDL + c];
+      for (int r = c + lane; r < LB; r += 32) S[c * LDL + r] = fma(-S[j * LDL + r], lcj, S[c * LDL + r]);
+    }
+    __syncthreads();
+  }
+
+  // ---- inverse: L W = I, row k of W finalised at step k, then pushed into the rows below ------
+  for (int k = 0; k < LB; ++k) {
+    const double dk = dinv[k];
+    if (tid < k) S[k * LDL + tid] *= dk;  // W(k, j<k) = R(k,j) / L(k,k)
+    __syncthreads();
+    for (int i = k + 1 + warp; i < LB; i += LEAF_THREADS / 32) {
+      const double lik = S[k * LDL + i];
+      for (int j = lane; j <= k; j += 32) {
+        const double wkj = (j == k) ? dk : S[k * LDL + j];
+        S[i * LDL + j] = fma(-lik, wkj, S[i * LDL + j]);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- write back: L (upper part zeroed) and W ------------------------------------------------
+  for (int idx = tid; idx < LB * LB; idx += LEAF_THREADS) {
+    int r = idx & (LB - 1), c = idx >> 7;
+    A[r + (int64_t)c * lda] = (r >= c) ? S[c * LDL + r] : 0.0;
+    double w = 0.0;
+    if (r == c) w = dinv[r];
+    else if (r > c) w = S[r * LDL + c];
+    Inv[r + c * LB] = w;
+  }
+}
+
+// W diagonal tiles <- leaf inverses
+__global__ void copy_diag_blocks_kernel(const double *inv, double *W, int64_t ldw) {
+  const int b = blockIdx.x;
+  const double *src = inv + (int64_t)b * LB * LB;
+  double *dst = W + (int64_t)b * LB * (ldw + 1);
+  for (int idx = threadIdx.x; idx < LB * LB; idx += blockDim.x) {
+    int r = idx & (LB - 1), c = idx >> 7;
+    dst[r + (int64_t)c * ldw] = src[idx];
+  }
+}
+
+cudaEvent_t get_event(Ctx *ctx, size_t i) {
+  while (ctx->ev_pool.size() <= i) {
+    cudaEvent_t e;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    ctx->ev_pool.push_back(e);
+  }
+  return ctx->ev_pool[i];
+}
+
+// Factor the block column starting at c0 (width w): leaves, in-place panel products and the
+// updates confined to the block column.  Enqueued on `st`.
+int32_t factor_block_column(Ctx *ctx, cudaStream_t st, double *A, int64_t lda, int64_t n, int64_t c0, int64_t w,
+                            double *inv, int *info) {
+  for (int64_t cs = c0; cs < c0 + w; cs += LB) {
+    double *invb = inv + (cs / LB) * LB * LB;
+    leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM, st>>>(A + cs + cs * lda, lda, invb, info, (int)cs);
+    DGP_CUDA_OK(ctx, cudaGetLastError());
+    const int64_t rb = cs + LB;
+    if (rb >= n) break;
+    // panel: A[rb:, cs:cs+128] <- A[rb:, cs:cs+128] * inv(L_cs)^T   (in place: each CTA reads and
+    // writes exactly its own 128x128 region, and reads complete before its epilogue starts)
+    GemmArgs g;
+    g.A = A + rb + cs * lda;  g.lda = lda;  g.a_kmajor = 0;
+    g.B = invb;               g.ldb = LB;   g.b_kmajor = 0;   // op(B)(k,n) = inv(n,k)
+    g.C = A + rb + cs * lda;  g.ldc = lda;
+    g.M = (int)(n - rb);  g.N = LB;  g.K = LB;
+    g.alpha = 1.0;  g.beta = 0.0;
+    DGP_TRY(gemm(ctx, st, g));
+    // update the remaining columns of this block column with the 128 columns just finished
+    const int64_t nc = c0 + w - rb;
+    if (nc > 0) {
+      GemmArgs u;
+      u.A = A + rb + cs * lda;  u.lda = lda;  u.a_kmajor = 0;
+      u.B = A + rb + cs * lda;  u.ldb = lda;  u.b_kmajor = 0;   // op(B)(k,n) = P(n,k)
+      u.C = A + rb + rb * lda;  u.ldc = lda;
+      u.M = (int)(n - rb);  u.N = (int)nc;  u.K = LB;
+      u.alpha = -1.0;  u.beta = 1.0;
+      DGP_TRY(gemm(ctx, st, u));
+    }
+  }
+  return DGP_OK;
+}
+
+}  // namespace
+
+int32_t potrf_init(Ctx *ctx) {
+  DGP_CUDA_OK(ctx, cudaFuncSetAttribute(leaf_potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)LEAF_SMEM));
+  return DGP_OK;
+}
+
+int32_t potrf_blocked(Ctx *ctx, double *A, int64_t lda, int64_t n, double *inv, int *info) {
+  if (n % LB) return ctx->fail(DGP_ERR_SHAPE, "potrf: n=%lld must be a multiple of 128", (long long)n);
+  const int64_t nb = ctx->nb;
+  cudaStream_t S = ctx->stream;
+  const bool la = ctx->lookahead && n > nb;
+  cudaStream_t P = la ? ctx->panel : ctx->stream;
+  size_t ev = 0;
+
+  if (la) {  // the panel stream starts after whatever produced A on the main stream
+    cudaEvent_t e = get_event(ctx, ev++);
+    DGP_CUDA_OK(ctx, cudaEventRecord(e, S));
+    DGP_CUDA_OK(ctx, cudaStreamWaitEvent(P, e, 0));
+  }
+
+  for (int64_t c0 = 0; c0 < n; c0 += nb) {
+    const int64_t w = (n - c0 < nb) ? (n - c0) : nb;
+    DGP_TRY(factor_block_column(ctx, P, A, lda, n, c0, w, inv, info));
+    const int64_t c1 = c0 + w;
+    if (c1 >= n) break;
+    if (la) {
+      cudaEvent_t e = get_event(ctx, ev++);
+      DGP_CUDA_OK(ctx, cudaEventRecord(e, P));
+      DGP_CUDA_OK(ctx, cudaStreamWaitEvent(S, e, 0));
+    }
+    const int64_t w1 = (n - c1 < nb) ? (n - c1) : nb;
+    // (a) trailing update restricted to the next block column
+    GemmArgs a;
+    a.A = A + c1 + c0 * lda;  a.lda = lda;  a.a_kmajor = 0;
+    a.B = A + c1 + c0 * lda;  a.ldb = lda;  a.b_kmajor = 0;
+    a.C = A + c1 + c1 * lda;  a.ldc = lda;
+    a.M = (int)(n - c1);  a.N = (int)w1;  a.K = (int)w;
+    a.alpha = -1.0;  a.beta = 1.0;
+    DGP_TRY(gemm(ctx, S, a));
+    if (la) {
+      cudaEvent_t e = get_event(ctx, ev++);
+      DGP_CUDA_OK(ctx, cudaEventRecord(e, S));
+      DGP_CUDA_OK(ctx, cudaStreamWaitEvent(P, e, 0));
+    }
+    // (b) the rest of the trailing matrix (lower tiles), overlapped with the next panel
+    const int64_t c2 = c1 + w1;
+    if (c2 < n) {
+      GemmArgs b;
+      b.A = A + c2 + c0 * lda;  b.lda = lda;  b.a_kmajor = 0;
+      b.B = A + c2 + c0 * lda;  b.ldb = lda;  b.b_kmajor = 0;
+      b.C = A + c2 + c2 * lda;  b.ldc = lda;
+      b.M = (int)(n - c2);  b.N = (int)(n - c2);  b.K = (int)w;
+      b.alpha = -1.0;  b.beta = 1.0;
+      b.lower_only = 1;
+      DGP_TRY(gemm(ctx, S, b));
+    }
+  }
+  if (la) {  // join
+    cudaEvent_t e = get_event(ctx, ev++);
+    DGP_CUDA_OK(ctx, cudaEventRecord(e, P));
+    DGP_CUDA_OK(ctx, cudaStreamWaitEvent(S, e, 0));
+  }
+  return DGP_OK;
+}
+
+int32_t trtri_lower(Ctx *ctx, const double *L, int64_t ldl, const double *inv, int64_t n, double *W, int64_t ldw,
+                    double *scratch, int64_t lds) {
+  if (n % LB) return ctx->fail(DGP_ERR_SHAPE, "trtri: n must be a multiple of 128");
+  cudaStream_t S = ctx->stream;
+  copy_diag_blocks_kernel<<<(unsigned)(n / LB), 256, 0, S>>>(inv, W, ldw);
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  // Level h joins the inverses of two adjacent diagonal blocks [r0, r0+h) and [r0+h, r0+h+h2):
+  //   W21 = -W22 * (L21 * W11)
+  for (int64_t h = LB; h < n; h *= 2) {
+    const int64_t nfull = n / (2 * h);             // problems with h2 == h
+    const int64_t rem = n - nfull * 2 * h;         // leftover rows at the end
+    const int64_t h2_last = rem > h ? rem - h : 0; // a last, smaller problem
+    for (int pass = 0; pass < 2; ++pass) {
+      const int64_t cnt = pass == 0 ? nfull : (h2_last > 0 ? 1 : 0);
+      if (cnt == 0) continue;
+      const int64_t r0 = pass == 0 ? 0 : nfull * 2 * h;
+      const int64_t h2 = pass == 0 ? h : h2_last;
+      GemmArgs t;  // T = L21 * W11  (W11 lower triangular: k >= n0)
+      t.A = L + (r0 + h) + r0 * ldl;  t.lda = ldl;  t.a_kmajor = 0;
+      t.B = W + r0 + r0 * ldw;        t.ldb = ldw;  t.b_kmajor = 1;
+      t.C = scratch + (r0 + h) + r0 * lds;  t.ldc = lds;
+      t.M = (int)h2;  t.N = (int)h;  t.K = (int)h;
+      t.alpha = 1.0;  t.beta = 0.0;
+      t.kmode = K_GE_COL;
+      t.batch = (int)cnt;
+      t.strideA = 2 * h * (ldl + 1);  t.strideB = 2 * h * (ldw + 1);  t.strideC = 2 * h * (lds + 1);
+      DGP_TRY(gemm(ctx, S, t));
+      GemmArgs u;  // W21 = -W22 * T  (W22 lower triangular: k < m0 + 128)
+      u.A = W + (r0 + h) + (r0 + h) * ldw;  u.lda = ldw;  u.a_kmajor = 0;
+      u.B = scratch + (r0 + h) + r0 * lds;  u.ldb = lds;  u.b_kmajor = 1;
+      u.C = W + (r0 + h) + r0 * ldw;        u.ldc = ldw;
+      u.M = (int)h2;  u.N = (int)h;  u.K = (int)h2;
+      u.alpha = -1.0;  u.beta = 0.0;
+      u.kmode = K_LT_ROWEND;
+      u.reverse = 1;
+      u.batch = (int)cnt;
+      u.strideA = 2 * h * (ldw + 1);  u.strideB = 2 * h * (lds + 1);  u.strideC = 2 * h * (ldw + 1);
+      DGP_TRY(gemm(ctx, S, u));
+    }
+  }
+  return DGP_OK;
+}
+
+int32_t lauum_lower(Ctx *ctx, const double *W, int64_t ldw, int64_t n, double *Kinv, int64_t ldk) {
+  GemmArgs g;  // Kinv(i,j) = sum_{k >= i} W(k,i) W(k,j),  i >= j
+  g.A = W;  g.lda = ldw;  g.a_kmajor = 1;
+  g.B = W;  g.ldb = ldw;  g.b_kmajor = 1;
+  g.C = Kinv;  g.ldc = ldk;
+  g.M = (int)n;  g.N = (int)n;  g.K = (int)n;
+  g.alpha = 1.0;  g.beta = 0.0;
+  g.lower_only = 1;
+  g.kmode = K_GE_ROW;
+  return gemm(ctx, ctx->stream, g);
+}
+
+}  // namespace dgp

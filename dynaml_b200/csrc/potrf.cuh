@@ -1,0 +1,26 @@
+// potrf.cuh -- blocked Cholesky, triangular inverse and L^-T L^-1 on device-resident matrices.
+#pragma once
+#include "common.cuh"
+
+namespace dgp {
+
+int32_t potrf_init(Ctx *ctx);
+
+// In-place right-looking blocked Cholesky of the lower triangle of A (n x n, n % 128 == 0).
+//   A    : on exit L in the lower triangle (diagonal blocks have their upper part zeroed;
+//          tiles strictly above the diagonal are never touched)
+//   inv  : n/128 blocks of 128x128 (column-major, ld = 128): inverse of each diagonal block of L
+//   info : device int; set to (first failing global pivot index + 1) when a pivot is <= 0 or NaN
+//          (only the first failure is kept); must be zeroed by the caller.
+// Replaces bcholesky / choleskyPAcc (CORE/algebra/bcholesky.scala:85-148).
+int32_t potrf_blocked(Ctx *ctx, double *A, int64_t lda, int64_t n, double *inv, int *info);
+
+// W (lower) = L^-1 from L and the diagonal-block inverses; scratch is an n x n buffer (ld = lds)
+// whose lower triangle is clobbered.  Tiles of W strictly above the diagonal are not written.
+int32_t trtri_lower(Ctx *ctx, const double *L, int64_t ldl, const double *inv, int64_t n, double *W, int64_t ldw,
+                    double *scratch, int64_t lds);
+
+// Kinv (lower tiles) = W^T W.
+int32_t lauum_lower(Ctx *ctx, const double *W, int64_t ldw, int64_t n, double *Kinv, int64_t ldk);
+
+}  // namespace dgp

@@ -1,0 +1,216 @@
+// solve.cu -- the O(N^2) tail of the path: blocked triangular solves built on the diagonal-block
+// inverses, deterministic reductions, GEMV and layout helpers.  All HBM-read bound.
+#include "solve.cuh"
+
+namespace dgp {
+
+namespace {
+
+constexpr int SB = 128;  // block edge (= leaf block)
+
+// y[r] = sum_{j<128} M[r + j*ld] * v[j]   for r = threadIdx.x  (128 threads, v in shared memory)
+__device__ __forceinline__ double rowblock_mv(const double *M, int64_t ld, const double *v, int r) {
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll 4
+  for (int j = 0; j < SB; j += 4) {
+    acc0 = fma(M[r + (int64_t)(j + 0) * ld], v[j + 0], acc0);
+    acc1 = fma(M[r + (int64_t)(j + 1) * ld], v[j + 1], acc1);
+    acc2 = fma(M[r + (int64_t)(j + 2) * ld], v[j + 2], acc2);
+    acc3 = fma(M[r + (int64_t)(j + 3) * ld], v[j + 3], acc3);
+  }
+  return (acc0 + acc1) + (acc2 + acc3);
+}
+
+// out[c] = sum_{k<128} M[k + c*ld] * v[k] for c = 0..127: one warp per column, lanes over k.
+// 128 threads = 4 warps, each handles 32 columns.  Result for column c is returned to lane 0 and
+// written through `store(c, value)`.
+template <typename Store>
+__device__ __forceinline__ void colblock_dot(const double *M, int64_t ld, const double *v, Store store) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double v0 = v[lane], v1 = v[lane + 32], v2 = v[lane + 64], v3 = v[lane + 96];
+  for (int c = warp; c < SB; c += 4) {
+    const double *col = M + (int64_t)c * ld;
+    double s = (col[lane] * v0 + col[lane + 32] * v1) + (col[lane + 64] * v2 + col[lane + 96] * v3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) store(c, s);
+  }
+}
+
+// Forward step b: every row block i > b subtracts L(i,b) z_b; the CTA of block b+1 then applies
+// inv(L_{b+1,b+1}) so that the next launch finds z_{b+1} ready.  b == -1: only z_0 = inv_0 x_0.
+__global__ void __launch_bounds__(SB) trsv_fwd_step_kernel(const double *L, int64_t ldl, const double *inv, double *x,
+                                                           int b) {
+  __shared__ double v[SB];
+  const int tid = threadIdx.x;
+  const int i = b + 1 + blockIdx.x;
+  double xi = x[(int64_t)i * SB + tid];
+  if (b >= 0) {
+    v[tid] = x[(int64_t)b * SB + tid];
+    __syncthreads();
+    xi -= rowblock_mv(L + (int64_t)i * SB + (int64_t)b * SB * ldl, ldl, v, tid);
+  }
+  if (i == b + 1) {
+    __syncthreads();
+    v[tid] = xi;
+    __syncthreads();
+    xi = rowblock_mv(inv + (int64_t)i * SB * SB, SB, v, tid);  // inverse block is lower triangular with explicit zeros
+  }
+  x[(int64_t)i * SB + tid] = xi;
+}
+
+// Backward step b: column blocks j < b subtract L(b,j)^T x_b; the CTA of block b-1 then applies
+// inv(L_{b-1,b-1})^T.  b == nblk: only x_{nblk-1} = inv^T z_{nblk-1}.
+__global__ void __launch_bounds__(SB) trsv_bwd_step_kernel(const double *L, int64_t ldl, const double *inv, double *x,
+                                                           int b, int nblk) {
+  __shared__ double v[SB];
+  __shared__ double w[SB];
+  const int tid = threadIdx.x;
+  const int j = (b == nblk) ? nblk - 1 : (int)blockIdx.x;
+  w[tid] = x[(int64_t)j * SB + tid];
+  if (b < nblk) {
+    v[tid] = x[(int64_t)b * SB + tid];
+    __syncthreads();
+    colblock_dot(L + (int64_t)b * SB + (int64_t)j * SB * ldl, ldl, v, [&](int c, double s) { w[c] -= s; });
+  }
+  __syncthreads();
+  if (j == b - 1) {
+    v[tid] = w[tid];
+    __syncthreads();
+    colblock_dot(inv + (int64_t)j * SB * SB, SB, v, [&](int c, double s) { w[c] = s; });
+    __syncthreads();
+  }
+  x[(int64_t)j * SB + tid] = w[tid];
+}
+
+__device__ __forceinline__ double block_reduce_1024(double s, double *sh) {
+  const int tid = threadIdx.x;
+  sh[tid] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (tid < o) sh[tid] += sh[tid + o];
+    __syncthreads();
+  }
+  return sh[0];
+}
+
+__global__ void __launch_bounds__(1024) diag_log_sum_kernel(const double *A, int64_t lda, int64_t n, double *out) {
+  __shared__ double sh[1024];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += log(A[i + i * lda]);
+  s = block_reduce_1024(s, sh);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+__global__ void __launch_bounds__(1024) dot_kernel(const double *x, const double *y, int64_t n, double *out) {
+  __shared__ double sh[1024];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s = fma(x[i], y[i], s);
+  s = block_reduce_1024(s, sh);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) gemv_t_kernel(const double *A, int64_t lda, int64_t rows, const double *x,
+                                                     const double *base, double *y) {
+  __shared__ double sh[256];
+  const int64_t j = blockIdx.x;
+  const double *col = A + j * lda;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < rows; i += blockDim.x) s = fma(col[i], x[i], s);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) y[j] = (base ? base[j] : 0.0) + sh[0];
+}
+
+__global__ void __launch_bounds__(128) lower_row_sums_kernel(const double *L, int64_t ldl, int64_t n, double *bar) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int64_t j = 0; j <= i; ++j) s += L[i + j * ldl];
+  bar[i] = s;
+}
+
+__global__ void __launch_bounds__(256) mirror_lower_kernel(double *A, int64_t lda) {
+  __shared__ double tile[32][33];
+  const int ti = blockIdx.x, tj = blockIdx.y;
+  if (tj > ti) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = A[(int64_t)ti * 32 + tx + ((int64_t)tj * 32 + r) * lda];  // tile[col][row]
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    // destination element (row = tj*32 + tx, col = ti*32 + r) = source (row = ti*32 + r, col = tj*32 + tx)
+    if (ti != tj || tx < r) A[(int64_t)tj * 32 + tx + ((int64_t)ti * 32 + r) * lda] = tile[tx][r];
+  }
+}
+
+}  // namespace
+
+int32_t trsv_lower_fwd(Ctx *ctx, cudaStream_t st, const double *L, int64_t ldl, const double *inv, int64_t n,
+                       double *x) {
+  const int nblk = (int)(n / SB);
+  if (nblk == 0) return DGP_OK;
+  trsv_fwd_step_kernel<<<1, SB, 0, st>>>(L, ldl, inv, x, -1);
+  for (int b = 0; b + 1 < nblk; ++b) trsv_fwd_step_kernel<<<nblk - 1 - b, SB, 0, st>>>(L, ldl, inv, x, b);
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  return DGP_OK;
+}
+
+int32_t trsv_lower_bwd(Ctx *ctx, cudaStream_t st, const double *L, int64_t ldl, const double *inv, int64_t n,
+                       double *x) {
+  const int nblk = (int)(n / SB);
+  if (nblk == 0) return DGP_OK;
+  trsv_bwd_step_kernel<<<1, SB, 0, st>>>(L, ldl, inv, x, nblk, nblk);
+  for (int b = nblk - 1; b >= 1; --b) trsv_bwd_step_kernel<<<b, SB, 0, st>>>(L, ldl, inv, x, b, nblk);
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  return DGP_OK;
+}
+
+int32_t diag_log_sum(Ctx *ctx, cudaStream_t st, const double *A, int64_t lda, int64_t n, double *out) {
+  diag_log_sum_kernel<<<1, 1024, 0, st>>>(A, lda, n, out);
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  return DGP_OK;
+}
+
+int32_t dot(Ctx *ctx, cudaStream_t st, const double *x, const double *y, int64_t n, double *out) {
+  dot_kernel<<<1, 1024, 0, st>>>(x, y, n, out);
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  return DGP_OK;
+}
+
+int32_t gemv_t(Ctx *ctx, cudaStream_t st, const double *A, int64_t lda, int64_t rows, int64_t cols, const double *x,
+               const double *base, double *y) {
+  if (cols == 0) return DGP_OK;
+  gemv_t_kernel<<<(unsigned)cols, 256, 0, st>>>(A, lda, rows, x, base, y);
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  return DGP_OK;
+}
+
+int32_t lower_row_sums(Ctx *ctx, cudaStream_t st, const double *L, int64_t ldl, int64_t n, double *bar) {
+  if (n == 0) return DGP_OK;
+  lower_row_sums_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(L, ldl, n, bar);
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  return DGP_OK;
+}
+
+int32_t mirror_lower(Ctx *ctx, cudaStream_t st, double *A, int64_t lda, int64_t n) {
+  if (n == 0) return DGP_OK;
+  if (n % 32) return ctx->fail(DGP_ERR_SHAPE, "mirror_lower: n must be a multiple of 32");
+  dim3 grid((unsigned)(n / 32), (unsigned)(n / 32));
+  mirror_lower_kernel<<<grid, 256, 0, st>>>(A, lda);
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  return DGP_OK;
+}
+
+int32_t copy_block(Ctx *ctx, cudaStream_t st, const double *src, int64_t lds, double *dst, int64_t ldd, int64_t n,
+                   int64_t m) {
+  if (n == 0 || m == 0) return DGP_OK;
+  DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst, ldd * sizeof(double), src, lds * sizeof(double), n * sizeof(double), m,
+                                     cudaMemcpyDeviceToDevice, st));
+  return DGP_OK;
+}
+
+}  // namespace dgp

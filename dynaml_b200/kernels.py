@@ -1,0 +1,265 @@
+"""Host-side mirror of dynaml-core's covariance-function API for the GP hot path.
+
+Same names, argument meaning and error behaviour as the reference classes
+(CORE = dynaml-core/src/main/scala/io/github/tailhq/dynaml):
+
+  CovarianceFunction / LocalScalarKernel   CORE/kernels/CovarianceFunction.scala:17-59,
+                                           CORE/kernels/LocalScalarKernel.scala:35-176
+  SEKernel, RBFKernel, MahalanobisKernel   CORE/kernels/RBFKernel.scala:29-146
+  GenericMaternKernel                      CORE/kernels/GenericMaternKernel.scala:37-99
+  PeriodicKernel                           CORE/kernels/PeriodicKernel.scala:11-68
+  DiracKernel                              CORE/kernels/DiracKernel.scala:30-60
+  AdditiveCovariance                       CORE/kernels/AdditiveCovariance.scala:27-93
+
+The classes only carry hyper-parameter state; every number is produced by the CUDA library
+through the C ABI (dynaml_b200._capi).  Kernels the device path does not implement raise
+NotImplementedError -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterable, List, Sequence
+
+import numpy as np
+
+from . import _capi
+
+
+def _as_points(data) -> np.ndarray:
+    """Seq[DenseVector[Double]] -> N x d array."""
+    a = np.asarray(data, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    if a.ndim != 2:
+        raise ValueError("expected a sequence of d-vectors")
+    return np.ascontiguousarray(a)
+
+
+class SVMKernelMatrix:
+    """CORE/kernels/SVMKernelMatrix.scala -- holder returned by buildKernelMatrix."""
+
+    def __init__(self, kernel: np.ndarray, dimension: int):
+        self.kernel = kernel
+        self.rows = self.cols = dimension
+
+    def getKernelMatrix(self) -> np.ndarray:
+        return self.kernel
+
+
+class LocalScalarKernel:
+    """CovarianceFunction[DenseVector[Double], Double, DenseMatrix[Double]] with LocalScalarKernel."""
+
+    hyper_parameters: List[str] = []
+
+    def __init__(self):
+        self.blocked_hyper_parameters: List[str] = []
+        self.state: Dict[str, float] = {}
+        self.rowBlocking, self.colBlocking = 1000, 1000
+        self.grad_mode = _capi.GRAD_REFERENCE
+
+    # ---- hyper-parameter plumbing (CovarianceFunction.scala:21-44) ------------------------
+    def block(self, *h: str) -> None:
+        self.blocked_hyper_parameters = list(h)
+
+    def block_all_hyper_parameters(self) -> None:
+        self.blocked_hyper_parameters = list(self.hyper_parameters)
+
+    @property
+    def effective_state(self) -> Dict[str, float]:
+        return {k: v for k, v in self.state.items() if k not in self.blocked_hyper_parameters}
+
+    @property
+    def effective_hyper_parameters(self) -> List[str]:
+        return [h for h in self.hyper_parameters if h not in self.blocked_hyper_parameters]
+
+    def setHyperParameters(self, h: Dict[str, float]):
+        assert all(k in h for k in self.effective_hyper_parameters), \
+            "All hyper parameters must be contained in the arguments"
+        for key in self.effective_hyper_parameters:
+            self.state[key] = float(h[key])
+        return self
+
+    def setBlockSizes(self, s) -> None:
+        self.rowBlocking, self.colBlocking = int(s[0]), int(s[1])
+
+    def __str__(self) -> str:  # the reference's Object.toString: "<package>.<Class>@<hash>"
+        return f"io.github.tailhq.dynaml.kernels.{type(self).__name__}@{id(self) & 0xffffffff:x}"
+
+    # ---- device description ---------------------------------------------------------------
+    def _device_kind(self) -> int:
+        raise NotImplementedError(
+            f"{type(self).__name__} has no sm_100a implementation (supported: SEKernel, RBFKernel, "
+            "MahalanobisKernel, GenericMaternKernel, PeriodicKernel, DiracKernel); no CPU fallback")
+
+    def _device_hyp(self, config: Dict[str, float]) -> List[float]:
+        return [float(config[h]) for h in self.hyper_parameters]
+
+    def _spec(self, config: Dict[str, float] | None = None, noise: float = 0.0):
+        cfg = self.state if config is None else config
+        return _capi.make_spec(self._device_kind(), self._device_hyp(cfg), noise, self.grad_mode)
+
+    # ---- evaluation -----------------------------------------------------------------------
+    def evaluateAt(self, config: Dict[str, float]):
+        def f(x, y) -> float:
+            K = _capi.default_context().kernel_matrix(self._spec(config), _as_points([x]), _as_points([y]))
+            return float(K[0, 0])
+        return f
+
+    def evaluate(self, x, y) -> float:
+        return self.evaluateAt(self.state)(x, y)
+
+    def buildKernelMatrix(self, mappedData: Sequence, length: int) -> SVMKernelMatrix:
+        X = _as_points(mappedData)
+        assert X.shape[0] == length
+        return SVMKernelMatrix(_capi.default_context().kernel_matrix(self._spec(), X), length)
+
+    def buildCrossKernelMatrix(self, dataset1: Sequence, dataset2: Sequence) -> np.ndarray:
+        return _capi.default_context().kernel_matrix(self._spec(), _as_points(dataset1), _as_points(dataset2))
+
+    def __add__(self, other: "LocalScalarKernel") -> "AdditiveCovariance":
+        return AdditiveCovariance(self, other)
+
+
+class RBFKernel(LocalScalarKernel):
+    hyper_parameters = ["bandwidth"]
+
+    def __init__(self, bandwidth: float = 1.0):
+        super().__init__()
+        self.state = {"bandwidth": float(bandwidth)}
+
+    def setbandwidth(self, d: float) -> None:
+        self.state["bandwidth"] = float(d)
+
+    def _device_kind(self):
+        return _capi.KERNEL_RBF
+
+
+class SEKernel(RBFKernel):
+    hyper_parameters = ["bandwidth", "amplitude"]
+
+    def __init__(self, band: float = 1.0, h: float = 2.0):
+        super().__init__(band)
+        self.state = {"bandwidth": float(band), "amplitude": float(h)}
+
+    def _device_kind(self):
+        return _capi.KERNEL_SE
+
+
+class MahalanobisKernel(LocalScalarKernel):
+    """ARD squared-exponential.  grad_mode selects the reference's (defective) or the
+    exact bandwidth derivative; the default reproduces the reference."""
+
+    def __init__(self, band: Iterable[float], h: float = 2.0, grad_mode: int = _capi.GRAD_REFERENCE):
+        super().__init__()
+        band = [float(b) for b in band]
+        self.hyper_parameters = ["MahalanobisAmplitude"] + [f"MahalanobisBandwidth_{i}" for i in range(len(band))]
+        self.state = {"MahalanobisAmplitude": float(h)}
+        self.state.update({f"MahalanobisBandwidth_{i}": b for i, b in enumerate(band)})
+        self.grad_mode = grad_mode
+
+    def _device_kind(self):
+        return _capi.KERNEL_ARD_SE
+
+
+class GenericMaternKernel(LocalScalarKernel):
+    hyper_parameters = ["p", "l"]
+
+    def __init__(self, l: float, p: int = 2):
+        super().__init__()
+        self.blocked_hyper_parameters = ["p"]
+        self.state = {"p": float(p), "l": float(l)}
+
+    def setHyperParameters(self, h: Dict[str, float]):
+        super().setHyperParameters(h)
+        if "p" in h:
+            self.state["p"] = float(math.floor(abs(h["p"])))
+        return self
+
+    def _device_kind(self):
+        return _capi.KERNEL_MATERN
+
+
+class PeriodicKernel(LocalScalarKernel):
+    hyper_parameters = ["sigma", "lengthscale", "frequency"]
+
+    def __init__(self, s: float = 1.0, ls: float = 1.0, freq: float = 1.0):
+        super().__init__()
+        self.state = {"sigma": float(s), "lengthscale": float(ls), "frequency": float(freq)}
+
+    def setlengthscale(self, d: float) -> None:
+        self.state["lengthscale"] = float(d)
+
+    def setfrequency(self, f: float) -> None:
+        self.state["frequency"] = float(f)
+
+    def _device_kind(self):
+        return _capi.KERNEL_PERIODIC
+
+
+class DiracKernel(LocalScalarKernel):
+    hyper_parameters = ["noiseLevel"]
+
+    def __init__(self, noiseLevel: float = 1.0):
+        super().__init__()
+        self.state = {"noiseLevel": float(noiseLevel)}
+
+    def setNoiseLevel(self, d: float) -> None:
+        self.state["noiseLevel"] = float(d)
+
+    def _device_kind(self):
+        return _capi.KERNEL_DIRAC
+
+    def buildKernelMatrix(self, mappedData: Sequence, length: int) -> SVMKernelMatrix:
+        # DiracKernel.scala:55-58 overrides the builder: eye(length) * noiseLevel (signed, no abs)
+        return SVMKernelMatrix(np.eye(length) * self.state["noiseLevel"], length)
+
+
+class AdditiveCovariance(LocalScalarKernel):
+    """cov + noise with the reference's "<Class@hash>/<hyp>" naming (AdditiveCovariance.scala:32-58).
+    The device path supports <supported kernel> + DiracKernel."""
+
+    def __init__(self, firstKernel: LocalScalarKernel, otherKernel: LocalScalarKernel):
+        super().__init__()
+        self.firstKernel, self.otherKernel = firstKernel, otherKernel
+        self.fID = str(firstKernel).split(".")[-1]
+        self.sID = str(otherKernel).split(".")[-1]
+        self.hyper_parameters = [f"{self.fID}/{h}" for h in firstKernel.hyper_parameters] + \
+                                [f"{self.sID}/{h}" for h in otherKernel.hyper_parameters]
+        self.blocked_hyper_parameters = [f"{self.fID}/{h}" for h in firstKernel.blocked_hyper_parameters] + \
+                                        [f"{self.sID}/{h}" for h in otherKernel.blocked_hyper_parameters]
+        self.state = {f"{self.fID}/{k}": v for k, v in firstKernel.state.items()}
+        self.state.update({f"{self.sID}/{k}": v for k, v in otherKernel.state.items()})
+
+    @staticmethod
+    def _truncate(k: str) -> str:
+        return "/".join(k.split("/")[1:])
+
+    def _configs(self, config: Dict[str, float]):
+        return ({self._truncate(k): v for k, v in config.items() if self.fID in k},
+                {self._truncate(k): v for k, v in config.items() if self.sID in k})
+
+    def setHyperParameters(self, h: Dict[str, float]):
+        c1, c2 = self._configs(h)
+        self.firstKernel.setHyperParameters(c1)
+        self.otherKernel.setHyperParameters(c2)
+        return super().setHyperParameters(h)
+
+    def block(self, *h: str) -> None:
+        self.firstKernel.block(*[self._truncate(k) for k in h if self.fID in k])
+        self.otherKernel.block(*[self._truncate(k) for k in h if self.sID in k])
+        super().block(*h)
+
+    def _spec(self, config=None, noise: float = 0.0):
+        if not isinstance(self.otherKernel, DiracKernel):
+            raise NotImplementedError("device path supports <kernel> + DiracKernel only; no CPU fallback")
+        c1, c2 = self._configs(self.state if config is None else config)
+        return self.firstKernel._spec(c1, noise=c2["noiseLevel"])
+
+    def buildKernelMatrix(self, mappedData: Sequence, length: int) -> SVMKernelMatrix:
+        X = _as_points(mappedData)
+        return SVMKernelMatrix(_capi.default_context().kernel_matrix(self._spec(), X, add_noise=True), length)
+
+    def buildCrossKernelMatrix(self, dataset1: Sequence, dataset2: Sequence) -> np.ndarray:
+        # crossKernelMatrix evaluates cov + noise pairwise: the Dirac term fires only on exact duplicates
+        # across the two sets, which the device cross path does not add.
+        raise NotImplementedError("cross matrices of cov + noise are not on the GP hot path")

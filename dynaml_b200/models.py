@@ -1,0 +1,251 @@
+"""Host-side mirror of AbstractGPRegressionModel / GPRegression and their result types.
+
+Reference: CORE/models/gp/AbstractGPRegressionModel.scala:60-535, CORE/models/gp/GPRegression.scala:51-175,
+CORE/probability/GaussianRV.scala:81-103 (MultGaussianPRV),
+CORE/probability/distributions/BlockedMultiVariateGaussian.scala:21-68.
+
+`CudaGPRegression` is the class INTEGRATION.md describes on the JVM side: it overrides energy,
+gradEnergy, predictiveDistribution, predictionWithErrorBars, persist / unpersist and forwards
+them to the C ABI.  `GPRegression` is an alias so reference-style code reads unchanged.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+from .kernels import DiracKernel, LocalScalarKernel, _as_points
+
+
+class BlockedMultiVariateGaussian:
+    """mean / covariance plus the reference's error-bar rule (root * ones, lines 58-68)."""
+
+    def __init__(self, mean: np.ndarray, covariance: np.ndarray, _bars: Callable[[float], Tuple[np.ndarray, np.ndarray]]):
+        self.mean = mean
+        self.covariance = covariance
+        self._bars = _bars
+
+    @property
+    def variance(self):
+        return self.covariance
+
+    @property
+    def mode(self):
+        return self.mean
+
+    def confidenceInterval(self, s: float):
+        return self._bars(float(s))
+
+
+class MultGaussianPRV:
+    def __init__(self, mu: np.ndarray, covariance: np.ndarray, bars):
+        self.mu = mu
+        self.covariance = covariance
+        self.underlyingDist = BlockedMultiVariateGaussian(mu, covariance, bars)
+
+
+class CudaGPRegression:
+    """GPRegression(cov, noise, trainingdata, meanFunc) on one B200."""
+
+    def __init__(self, cov: LocalScalarKernel, noise: LocalScalarKernel | None = None,
+                 trainingdata: Sequence[Tuple[Sequence[float], float]] = (),
+                 meanFunc: Callable[[np.ndarray], float] | None = None,
+                 ctx: _capi.Context | None = None):
+        if noise is None:
+            noise = DiracKernel(1.0)
+        if not isinstance(noise, DiracKernel):
+            raise NotImplementedError("the device path models noise with DiracKernel only; no CPU fallback")
+        cov._device_kind()  # raises for unsupported covariance functions
+        self.covariance, self.noiseModel = cov, noise
+        self.mean = meanFunc if meanFunc is not None else (lambda _x: 0.0)
+        self.g = list(trainingdata)
+        self.npoints = len(self.g)
+        if self.npoints == 0:
+            raise ValueError("training data is empty")
+        self.ctx = ctx or _capi.default_context()
+        self.blockSize = 1000
+        self.hyper_parameters: List[str] = list(cov.hyper_parameters) + list(noise.hyper_parameters)
+        self.current_state: Dict[str, float] = {**cov.state, **noise.state}
+        self.validationSet: List[Tuple[Sequence[float], float]] = []
+        self._data = None        # dgp_data handle (training [+ validation] set resident in HBM)
+        self._data_key = None
+        self._model = None       # dgp_model handle (persisted L, alpha)
+        self.caching = False
+
+    # ---- reference accessors ----------------------------------------------------------------
+    def blockSize_(self, b: int) -> None:
+        self.blockSize = int(b)  # kept for API parity; the device path tiles on its own
+
+    @property
+    def _blockSize(self) -> int:
+        return self.blockSize
+
+    @property
+    def _current_state(self) -> Dict[str, float]:
+        return self.current_state
+
+    @property
+    def _hyper_parameters(self) -> List[str]:
+        return self.hyper_parameters
+
+    def validationSet_(self, v, append: bool = False) -> None:
+        self.validationSet = (self.validationSet + list(v)) if append else list(v)
+        self._drop_data()
+
+    def dataAsSeq(self, data):
+        return data
+
+    def setState(self, s: Dict[str, float]):
+        # AbstractGPRegressionModel.scala:117-128
+        self.covariance.setHyperParameters({k: v for k, v in s.items() if k in self.covariance.hyper_parameters})
+        self.noiseModel.setHyperParameters({k: v for k, v in s.items() if k in self.noiseModel.hyper_parameters})
+        self.current_state = {**self.covariance.state, **self.noiseModel.state}
+        return self
+
+    # ---- device residency -------------------------------------------------------------------
+    def _drop_data(self):
+        if self._data is not None:
+            self.ctx.data_destroy(self._data)
+            self._data = None
+
+    def _drop_model(self):
+        if self._model is not None:
+            self.ctx.model_destroy(self._model)
+            self._model = None
+
+    def __del__(self):
+        try:
+            self._drop_model()
+            self._drop_data()
+        except Exception:
+            pass
+
+    def _device_data(self):
+        """Training (+ validation, GPRegression.scala:148-174) set packed once into HBM."""
+        if self._data is None:
+            pts = self.g + self.validationSet
+            X = _as_points([p[0] for p in pts])
+            y = np.asarray([p[1] for p in pts], dtype=np.float64)
+            m = np.asarray([self.mean(x) for x in X], dtype=np.float64)
+            self._data = self.ctx.data_create(X, y, m)
+        return self._data
+
+    def _spec(self):
+        return self.covariance._spec(noise=self.noiseModel.state["noiseLevel"])
+
+    # ---- GloballyOptimizable ----------------------------------------------------------------
+    def energy(self, h: Dict[str, float], options: Dict[str, str] | None = None) -> float:
+        """0.5*(r'K^-1 r + sum log L_ii + n log 2pi); +Inf when K is not PD (:148-189, 516-535)."""
+        self.setState(h)
+        return self.ctx.energy(self._device_data(), self._spec())
+
+    def energyBatch(self, hs: Sequence[Dict[str, float]], options: Dict[str, str] | None = None) -> List[float]:
+        """The serial candidate loop of ModelTuner.getEnergyLandscape as one device batch.
+        Leaves the model state at the last candidate, as the serial loop would."""
+        specs = []
+        for h in hs:
+            self.setState(h)
+            specs.append(self._spec())
+        if not specs:
+            return []
+        e, status = self.ctx.energy_batch(self._device_data(), specs)
+        bad = [int(s) for s in status if s not in (_capi.DGP_OK, _capi.DGP_ERR_NOT_PD)]
+        if bad:
+            raise _capi.DgpError(bad[0], "energy batch: a candidate could not be evaluated")
+        return [float(v) for v in e]
+
+    def gradEnergy(self, h: Dict[str, float]) -> Dict[str, float]:
+        """tr((alpha alpha' - K^-1) dK/dtheta) per effective hyper-parameter, keys un-prefixed (:196-267)."""
+        self.covariance.setHyperParameters(h)
+        self.noiseModel.setHyperParameters(h)
+        _, g = self.ctx.energy_grad(self._device_data(), self._spec())
+        cov_names = list(self.covariance.hyper_parameters)
+        # hParams = (covariance + noiseModel).effective_hyper_parameters, keys stripped of the
+        # "<Class@hash>/" prefix (:239); a later key overwrites an earlier one, like Scala's toMap
+        pairs = [(h, float(g[cov_names.index(h)])) for h in self.covariance.effective_hyper_parameters]
+        pairs += [(h, float(g[len(cov_names)])) for h in self.noiseModel.effective_hyper_parameters]
+        return dict(pairs)
+
+    # ---- persistence (:399-422) -------------------------------------------------------------
+    def persist(self, state: Dict[str, float]) -> None:
+        self.setState(state)
+        self._drop_model()
+        self._model = self.ctx.fit(self._device_data_train_only(), self._spec())
+        self.caching = True
+
+    def unpersist(self) -> None:
+        self._drop_model()
+        self.caching = False
+
+    def _device_data_train_only(self):
+        if not self.validationSet:
+            return self._device_data()
+        X = _as_points([p[0] for p in self.g])
+        y = np.asarray([p[1] for p in self.g], dtype=np.float64)
+        m = np.asarray([self.mean(x) for x in X], dtype=np.float64)
+        if getattr(self, "_train_data", None) is None:
+            self._train_data = self.ctx.data_create(X, y, m)
+        return self._train_data
+
+    # ---- prediction (:304-393) --------------------------------------------------------------
+    def _fitted(self):
+        if self._model is not None and self.caching:
+            return self._model, False
+        return self.ctx.fit(self._device_data_train_only(), self._spec()), True
+
+    def predictiveDistribution(self, test: Sequence) -> MultGaussianPRV:
+        Xs = _as_points(test)
+        ms = np.asarray([self.mean(x) for x in Xs], dtype=np.float64)
+        model, temp = self._fitted()
+        try:
+            mean, cov, _, _ = self.ctx.predict(model, Xs, ms, want_cov=True, want_bars=False)
+        finally:
+            if temp:
+                self.ctx.model_destroy(model)
+
+        def bars(s: float):
+            # evaluated lazily, like `root` in BlockedMultiVariateGaussian (:32)
+            m2, t2 = self._fitted()
+            try:
+                _, _, lo, hi = self.ctx.predict(m2, Xs, ms, want_cov=False, want_bars=True, sigma=s)
+            finally:
+                if t2:
+                    self.ctx.model_destroy(m2)
+            return lo, hi
+
+        return MultGaussianPRV(mean, cov, bars)
+
+    def predictionWithErrorBars(self, testData: Sequence, sigma: int):
+        Xs = _as_points(testData)
+        ms = np.asarray([self.mean(x) for x in Xs], dtype=np.float64)
+        model, temp = self._fitted()
+        try:
+            mean, _, lo, hi = self.ctx.predict(model, Xs, ms, want_cov=False, want_bars=True, sigma=float(sigma))
+        finally:
+            if temp:
+                self.ctx.model_destroy(model)
+        return [(testData[i], float(mean[i]), float(lo[i]), float(hi[i])) for i in range(len(testData))]
+
+    def predict(self, point) -> float:
+        return self.predictionWithErrorBars([point], 1)[0][1]
+
+    def test(self, testData: Sequence[Tuple[Sequence[float], float]]):
+        """ContinuousProcessModel.test (CORE/models/StochasticProcessModel.scala:135-146)."""
+        preds = self.predictionWithErrorBars([p[0] for p in testData], 1)
+        return [(x, float(t[1]), m, lo, hi) for (x, m, lo, hi), t in zip(preds, testData)]
+
+
+GPRegression = CudaGPRegression
+
+
+def AbstractGPRegressionModel(cov, noise, meanFunc=None):
+    """AbstractGPRegressionModel(cov, noise, mean)(data, num) factory (:537-553)."""
+    def build(data, num):
+        assert len(data) == num
+        return CudaGPRegression(cov, noise, data, meanFunc)
+    return build
+
+
+LOG_2PI = math.log(2.0 * math.pi)

@@ -1,0 +1,263 @@
+"""Host-side mirror of the hyper-parameter tuners that drive the GP hot path.
+
+Reference (CORE/optimization): ModelTuner.scala:40-160, AbstractGridSearch.scala, GridSearch.scala:27-63,
+AbstractCSA.scala:30-327, CoupledSimulatedAnnealing.scala:30-54, GradBasedGlobalOptimizer.scala:27-103.
+
+The reference evaluates `system.energy` once per candidate, serially (ModelTuner.scala:131-153,
+AbstractCSA.scala:214-259).  Here each landscape / CSA sweep is one `energyBatch` call, and under
+torch.distributed (one process per GPU) the candidates of a sweep are sharded round-robin across
+ranks and gathered -- the path has no data-path collective.
+
+The reference draws from unseeded global RNGs (scala.util.Random, Breeze CauchyDistribution), so
+its CSA trajectories are not reproducible; the RNG is injected here (`rng=`).
+"""
+from __future__ import annotations
+
+import itertools
+import math
+from typing import Callable, Dict, List, Sequence, Tuple
+
+import numpy as np
+
+Config = Dict[str, float]
+
+
+def shard_indices(n: int, rank: int, world: int) -> List[int]:
+    """Round-robin candidate -> rank map (candidate i runs on GPU i mod P)."""
+    return list(range(rank, n, world))
+
+
+def sharded_energies(system, configs: Sequence[Config], options=None, group=None) -> List[float]:
+    """Evaluate `configs` across the ranks of a torch.distributed group (or locally) and return
+    the full list on every rank.  Only scalars travel; no collective touches the matrices."""
+    try:
+        import torch.distributed as dist
+        on = dist.is_available() and dist.is_initialized()
+    except Exception:  # pragma: no cover
+        on = False
+    batch = getattr(system, "energyBatch", None)
+    if batch is None:
+        def batch(cs, opts=None):
+            return [system.energy(c, opts or {}) for c in cs]
+    if not on:
+        return list(batch(list(configs), options))
+    import torch
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = shard_indices(len(configs), rank, world)
+    local = batch([configs[i] for i in mine], options)
+    gathered: List[List[Tuple[int, float]]] = [None] * world  # type: ignore
+    dist.all_gather_object(gathered, list(zip(mine, local)), group=group)
+    out = [math.nan] * len(configs)
+    for part in gathered:
+        for i, e in part:
+            out[i] = e
+    return out
+
+
+class ModelTuner:
+    def __init__(self, model):
+        self.system = model
+        self.step = 0.3
+        self.gridsize = 3
+        self.logarithmicScale = False
+        self.num_samples = 20
+        self.meanFieldPrior: Dict[str, object] = {}
+        self.group = None  # torch.distributed group used to shard candidates (None = default / local)
+
+    # fluent setters (ModelTuner.scala:52-77)
+    def setPrior(self, p):
+        self.meanFieldPrior = dict(p)
+        return self
+
+    def setNumSamples(self, n: int):
+        self.num_samples = int(n)
+        return self
+
+    def setLogScale(self, t: bool):
+        self.logarithmicScale = bool(t)
+        return self
+
+    def setGridSize(self, s: int):
+        self.gridsize = int(s)
+        return self
+
+    def setStepSize(self, s: float):
+        self.step = float(s)
+        return self
+
+    def getGrid(self, initialConfig: Config) -> List[Config]:
+        """ModelTuner.scala:79-103: per hyper-parameter `gridsize` values h0 - (i+1)*step, or
+        h0 / exp((i+1)*step) on the log scale; cartesian product in key order."""
+        keys = list(initialConfig.keys())
+        if self.logarithmicScale:
+            vecs = [[initialConfig[k] / math.exp((i + 1) * self.step) for i in range(self.gridsize)] for k in keys]
+        else:
+            vecs = [[initialConfig[k] - (i + 1) * self.step for i in range(self.gridsize)] for k in keys]
+        return [dict(zip(keys, combo)) for combo in itertools.product(*vecs)]
+
+    def getEnergyLandscape(self, initialConfig: Config, options=None, prior=None) -> List[Tuple[float, Config]]:
+        """ModelTuner.scala:105-155.  A prior covering every key switches the grid to `num_samples`
+        draws and adds -sum log prior(h); priors are objects with .sample() and .logPdf(x)."""
+        prior = prior or {}
+        use_prior = len(initialConfig) > 0 and all(k in prior for k in initialConfig)
+        if use_prior:
+            grid = [{k: float(prior[k].sample()) for k in prior} for _ in range(self.num_samples)]
+        else:
+            grid = self.getGrid(initialConfig)
+        energies = sharded_energies(self.system, grid, options, self.group)
+        out = []
+        for cfg, e in zip(grid, energies):
+            pe = -sum(prior[k].logPdf(v) for k, v in cfg.items()) if use_prior else 0.0
+            out.append((pe + e, cfg))
+        return out
+
+
+class GridSearch(ModelTuner):
+    def optimize(self, initialConfig: Config, options=None):
+        options = options or {}
+        landscape = self.getEnergyLandscape(initialConfig, options, self.meanFieldPrior)
+        # `.toMap` then `keys.min` (GridSearch.scala:47-49): ties collapse to the last config
+        as_map = {e: cfg for e, cfg in landscape}
+        optimum = min(as_map.keys())
+        best = as_map[optimum]
+        if options.get("persist") in ("true", "1"):
+            self.system.persist(best)
+        return self.system, best
+
+
+class AbstractCSA(ModelTuner):
+    MuSA, BA, M, MwVC, SA = "CSA-MuSA", "CSA-BA", "CSA-M", "CSA-MwVC", "SA"
+
+    def __init__(self, model, rng: np.random.Generator | None = None):
+        super().__init__(model)
+        self.MAX_ITERATIONS = 10
+        self.variant = AbstractCSA.MuSA
+        self.iTemp = 1.0
+        self.alpha = 0.05
+        self.rng = rng if rng is not None else np.random.default_rng()
+
+    def setVariant(self, v: str):
+        self.variant = v
+        return self
+
+    def setMaxIterations(self, m: int):
+        self.MAX_ITERATIONS = int(m)
+        return self
+
+    # ---- formulas (AbstractCSA.scala:268-327) -----------------------------------------------
+    @staticmethod
+    def couplingFactor(variant: str, landscape: Sequence[float], Tacc: float) -> float:
+        if variant in (AbstractCSA.MuSA, AbstractCSA.BA):
+            return sum(math.exp(-e / Tacc) for e in landscape)
+        if variant in (AbstractCSA.M, AbstractCSA.MwVC):
+            return sum(math.exp(e / Tacc) for e in landscape)
+        return 1.0
+
+    @staticmethod
+    def acceptanceProbability(variant: str, energy: float, oldEnergy: float, gamma: float, temperature: float) -> float:
+        if variant == AbstractCSA.MuSA:
+            x = math.exp(-energy / temperature)
+            return x / (x + gamma)
+        if variant == AbstractCSA.BA:
+            return 1.0 - math.exp(-oldEnergy / temperature) / gamma
+        if variant in (AbstractCSA.M, AbstractCSA.MwVC):
+            return math.exp(oldEnergy / temperature) / gamma
+        return gamma / (1.0 + math.exp((energy - oldEnergy) / temperature))
+
+    @staticmethod
+    def varianceDesired(variant: str, m: int) -> float:
+        if variant in (AbstractCSA.MuSA, AbstractCSA.BA):
+            return 0.99
+        return 0.99 * (m - 1) / float(m) ** 2
+
+    def acceptanceTemperature(self, initialTemp: float, k: int) -> float:
+        return initialTemp / math.log(k + 1.0)
+
+    def mutationTemperature(self, initialTemp: float, k: int) -> float:
+        return initialTemp / float(k)
+
+    def mutate(self, config: Config, temperature: float) -> Config:
+        """Cauchy(0, T) perturbation then abs (AbstractCSA.scala:112-130)."""
+        return {k: abs(v + temperature * float(self.rng.standard_cauchy())) for k, v in config.items()}
+
+    @staticmethod
+    def _sample_variance(xs: Sequence[float]) -> float:
+        """utils.getStats (CORE/utils/package.scala:110-143): unbiased variance."""
+        n = len(xs)
+        if n < 2:
+            raise ValueError("To calculate stats size of data must be > 1")
+        m = sum(xs) / n
+        return sum((x - m) ** 2 for x in xs) / (n - 1)
+
+    def performCSA(self, initialConfig: Config, options=None) -> List[Tuple[float, Config]]:
+        options = options or {}
+        sigmaD = self.varianceDesired(self.variant, int(self.gridsize ** len(initialConfig)))
+        landscape = self.getEnergyLandscape(initialConfig, options, self.meanFieldPrior)
+        gamma_init = self.couplingFactor(self.variant, [e for e, _ in landscape], self.iTemp)
+        acceptanceProbs = [self.acceptanceProbability(self.variant, e, e, gamma_init, self.iTemp) for e, _ in landscape]
+        use_prior = len(initialConfig) > 0 and all(k in self.meanFieldPrior for k in initialConfig)
+
+        accTempPrev = self.iTemp
+        for it in range(self.MAX_ITERATIONS, 0, -1):
+            mutTemp = self.mutationTemperature(self.iTemp, it)
+            if self.variant == AbstractCSA.MwVC:
+                variance = self._sample_variance(acceptanceProbs)
+                accTemp = accTempPrev * (1 - self.alpha) if variance < sigmaD else accTempPrev * (1 + self.alpha)
+            else:
+                accTemp = self.acceptanceTemperature(self.iTemp, it)
+            maxEnergy = max(e for e, _ in landscape)
+            coupling = self.couplingFactor(self.variant, [e - maxEnergy for e, _ in landscape], accTemp)
+            # candidates of one sweep are independent given the previous landscape: one batch
+            proposals = [self.mutate(cfg, mutTemp) for _, cfg in landscape]
+            energies = sharded_energies(self.system, proposals, options, self.group)
+            new_landscape, probs = [], []
+            for (old_e, old_cfg), new_cfg, e in zip(landscape, proposals, energies):
+                pe = -sum(self.meanFieldPrior[k].logPdf(v) for k, v in new_cfg.items()) if use_prior else 0.0
+                new_e = e + pe
+                p = self.acceptanceProbability(self.variant, new_e - maxEnergy, old_e - maxEnergy, coupling, accTemp)
+                if new_e < old_e or float(self.rng.random()) <= p:
+                    new_landscape.append((new_e, new_cfg))
+                else:
+                    new_landscape.append((old_e, old_cfg))
+                probs.append(p)
+            landscape, acceptanceProbs, accTempPrev = new_landscape, probs, accTemp
+        return landscape
+
+
+class CoupledSimulatedAnnealing(AbstractCSA):
+    def optimize(self, initialConfig: Config, options=None):
+        options = options or {}
+        as_map = {e: cfg for e, cfg in self.performCSA(initialConfig, options)}
+        optimum = min(as_map.keys())
+        best = as_map[optimum]
+        if options.get("persist") in ("true", "1"):
+            self.system.persist(best)
+        return self.system, best
+
+
+class GradBasedGlobalOptimizer(ModelTuner):
+    """ML-II by plain gradient descent: h <- |h - step * g| (GradBasedGlobalOptimizer.scala:37-103).
+    Note the reference descends along tr((aa' - K^-1) dK), which is -2 dE/dtheta."""
+
+    def optimize(self, initialConfig: Config, options=None):
+        options = options or {"tolerance": "0.0001", "step": "0.005", "maxIterations": "50"}
+        tolerance, alpha, maxit = float(options["tolerance"]), float(options["step"]), int(options["maxIterations"])
+        count, working = 1, dict(initialConfig)
+        while True:
+            gradient = self.system.gradEnergy(working)
+            gradNorm = math.sqrt(sum(v * v for v in gradient.values()))
+            # `working_solution.zip(gradient)` pairs the two maps positionally (:69)
+            new = {}
+            for (hyp, val), (_, gr) in zip(working.items(), gradient.items()):
+                if gr == math.inf:
+                    gr = 1.0
+                elif gr == -math.inf:
+                    gr = -1.0
+                new[hyp] = abs(val - alpha * gr)  # NaN compares unequal to itself in the reference too
+            working = new
+            count += 1
+            if not (count < maxit and gradNorm >= tolerance):
+                break
+        if options.get("persist") in ("true", "1"):
+            self.system.persist(working)
+        return self.system, working

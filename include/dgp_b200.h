@@ -1,0 +1,191 @@
+/*
+ * dgp_b200.h -- C ABI of libdgp_b200.so: the B200-native (sm_100a) Gaussian-process hot path
+ * that sits behind DynaML's dynaml-core API.
+ *
+ * DynaML has no FFI of its own; its extension mechanism is
+ * subclass-and-override.  Each entry point below is what a JVM shim (JNI or JDK FFM, see
+ * INTEGRATION.md) binds to replace one reference method.  Paths are relative to
+ *   CORE = dynaml-core/src/main/scala/io/github/tailhq/dynaml
+ *
+ * Conventions
+ *  - every function returns an int32 status (DGP_OK == 0); the message of the last failure on a
+ *    context is available from dgp_last_error().
+ *  - all matrices that cross the boundary are FP64, column-major, offset 0 (the layout of a
+ *    Breeze DenseMatrix[Double] with isTranspose == false); `ld` is the major stride in elements.
+ *  - point sets X are N x d.  x_layout == DGP_ROW_MAJOR means point i occupies
+ *    X[i*d .. i*d+d-1] (a packed Seq[DenseVector[Double]]); DGP_COL_MAJOR means a Breeze N x d matrix.
+ *  - the caller owns every host pointer; the library copies in/out before returning (synchronous).
+ *  - a dgp_ctx is bound to ONE GPU (one process per GPU) and is NOT thread-safe: the reference
+ *    model mutates kernel state in setState (CORE/models/gp/AbstractGPRegressionModel.scala:117-128).
+ *  - there is no CPU fallback: without a usable sm_100 device dgp_ctx_create fails with DGP_ERR_CUDA.
+ */
+#ifndef DGP_B200_H
+#define DGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dgp_ctx dgp_ctx;     /* one GPU, its streams and its workspace arena            */
+typedef struct dgp_data dgp_data;   /* training inputs X, targets y, prior mean m(X), resident  */
+typedef struct dgp_model dgp_model; /* a fitted model: L = chol(K), block inverses, alpha       */
+
+/* ---- status codes ------------------------------------------------------------------------ */
+enum {
+  DGP_OK = 0,
+  DGP_ERR_NOT_PD = 1,             /* Cholesky met a non-positive pivot: the reference's
+                                     NotConvergedException (-> +Inf energy, NaN gradient,
+                                     AbstractGPRegressionModel.scala:243-251, 531-533)          */
+  DGP_ERR_UNSUPPORTED_KERNEL = 2,
+  DGP_ERR_SHAPE = 3,
+  DGP_ERR_CUDA = 4,
+  DGP_ERR_NCCL = 5,
+  DGP_ERR_OOM = 6,
+  DGP_ERR_ARG = 7
+};
+
+enum { DGP_ROW_MAJOR = 0, DGP_COL_MAJOR = 1 };
+
+/* ---- covariance functions ---------------------------------------------------------------- */
+/* `hyp` is given in the order of the reference class's `hyper_parameters` list.               */
+enum {
+  DGP_KERNEL_SE = 0,       /* SEKernel            CORE/kernels/RBFKernel.scala:70-88
+                              hyp = [bandwidth, amplitude]; k = a^2 exp(-|x-y|^2 / (2 l^2))     */
+  DGP_KERNEL_RBF = 1,      /* RBFKernel           CORE/kernels/RBFKernel.scala:29-66
+                              hyp = [bandwidth]                                                  */
+  DGP_KERNEL_ARD_SE = 2,   /* MahalanobisKernel   CORE/kernels/RBFKernel.scala:101-146
+                              hyp = [MahalanobisAmplitude, MahalanobisBandwidth_0 .. _{d-1}]     */
+  DGP_KERNEL_MATERN = 3,   /* GenericMaternKernel CORE/kernels/GenericMaternKernel.scala:37-99
+                              hyp = [p, l]; half-integer order nu = p + 1/2, 0 <= p <= 8         */
+  DGP_KERNEL_PERIODIC = 4, /* PeriodicKernel      CORE/kernels/PeriodicKernel.scala:11-68
+                              hyp = [sigma, lengthscale, frequency]; uses the L1 norm            */
+  DGP_KERNEL_DIRAC = 5     /* DiracKernel         CORE/kernels/DiracKernel.scala:30-60
+                              hyp = [noiseLevel]; k = |s| * 1[|x-y|_2 == 0]                      */
+};
+
+/* Gradient conventions for hyper-parameters whose reference derivative is defective. */
+enum {
+  DGP_GRAD_REFERENCE = 0,  /* bit-for-bit the reference formulas, including
+                              MahalanobisKernel's k*|x-y|^2/b_i^3 for every i (RBFKernel.scala:142-143) */
+  DGP_GRAD_EXACT = 1       /* the mathematically exact dk/db_i = k*(x_i-y_i)^2/b_i^3             */
+};
+
+#define DGP_MAX_HYP 130    /* 1 amplitude + up to 128 ARD bandwidths + slack */
+
+typedef struct dgp_kernel_spec {
+  int32_t kind;            /* DGP_KERNEL_*                                                      */
+  int32_t n_hyp;           /* entries of hyp                                                    */
+  int32_t grad_mode;       /* DGP_GRAD_*                                                        */
+  int32_t reserved;
+  const double *hyp;       /* covariance hyper-parameters, reference order                      */
+  double noise;            /* DiracKernel noiseLevel of the noise model (signed; |.| is added
+                              wherever |x-y|_2 == 0, DiracKernel.scala:43-47)                   */
+} dgp_kernel_spec;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int32_t dgp_ctx_create(int32_t device, dgp_ctx **out);
+int32_t dgp_ctx_destroy(dgp_ctx *ctx);
+const char *dgp_last_error(const dgp_ctx *ctx);     /* NUL-terminated, owned by ctx             */
+const char *dgp_version(void);
+/* Tunables: "nb" (outer Cholesky block, multiple of 128, default 256), "lookahead" (0/1).      */
+int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value);
+/* Phase timings (ms, CUDA events) of the last energy/energy_grad/fit/predict call:
+   [0] assemble [1] potrf [2] solves+logdet [3] inverse (trtri+lauum) [4] trace pass
+   [5] cross assemble [6] trsm [7] syrk [8] total.  Unused slots are 0.                         */
+int32_t dgp_get_timings(const dgp_ctx *ctx, double *ms, int32_t n);
+
+/* ---- training data (replaces the Seq[(DenseVector[Double], Double)] the model holds,
+        CORE/models/gp/GPRegression.scala:51-60; packed once, resident in HBM) ---------------- */
+int32_t dgp_data_create(dgp_ctx *ctx, const double *X, int64_t N, int32_t d, int32_t x_layout,
+                        const double *y, const double *mean /* m(X), NULL => 0 */,
+                        dgp_data **out);
+int32_t dgp_data_destroy(dgp_ctx *ctx, dgp_data *data);
+
+/* ---- LocalScalarKernel.buildKernelMatrix / buildCrossKernelMatrix
+        (CORE/kernels/LocalScalarKernel.scala:154-158 -> SVMKernel.scala:71-105) ---------------
+   X2 == NULL: symmetric N1 x N1 matrix of X1 (both triangles written); add_noise != 0 adds the
+   Dirac term of spec->noise.  Otherwise the N1 x N2 cross matrix (never any noise).             */
+int32_t dgp_kernel_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec,
+                          const double *X1, int64_t N1, const double *X2, int64_t N2,
+                          int32_t d, int32_t x_layout, double *out, int64_t ld, int32_t add_noise);
+
+/* ---- AbstractGPRegressionModel.energy (AbstractGPRegressionModel.scala:148-189, 516-535) ----
+   E = 0.5 * ( r' K^-1 r + sum_i log L_ii + n log 2 pi ),  r = y - m(X)  (the reference's value,
+   whose log-det term is half the textbook one).  Non-PD K: *e = +Inf, returns DGP_ERR_NOT_PD.   */
+int32_t dgp_energy(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec, double *e);
+
+/* ---- gradEnergy (AbstractGPRegressionModel.scala:196-267) -----------------------------------
+   g[i] = tr( (alpha alpha' - K^-1) dK/dtheta_i ), i over spec->hyp in order, then g[n_hyp] for
+   the noise level: n_hyp + 1 values (entries with no reference derivative, e.g. Matern "p",
+   are NaN).  No -1/2 factor, exactly as the reference.  Non-PD: all NaN + DGP_ERR_NOT_PD.
+   `e` may be NULL.                                                                               */
+int32_t dgp_energy_grad(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec,
+                        double *e, double *g);
+
+/* ---- the candidate loop of ModelTuner.getEnergyLandscape / AbstractCSA
+        (CORE/optimization/ModelTuner.scala:131-153, AbstractCSA.scala:214-259) ----------------
+   Evaluates n candidates; status[i] is per candidate so one non-PD candidate yields +Inf
+   without aborting the batch.  Returns DGP_OK unless the batch itself could not run.           */
+int32_t dgp_energy_batch(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *specs,
+                         int32_t n, double *e, int32_t *status);
+
+/* ---- persist + predictiveDistribution + predictionWithErrorBars
+        (AbstractGPRegressionModel.scala:304-413, 434-466;
+         CORE/probability/distributions/BlockedMultiVariateGaussian.scala:58-68) ---------------
+   dgp_fit keeps L, the diagonal-block inverses and alpha resident (the reference caches K and
+   refactors on every call; same observable results).
+   dgp_predict:  mean[M]  = m(X*) + K*' alpha             (mean_s = m(X*), NULL => 0)
+                 cov[MxM] = K** - (L^-1 K*)' (L^-1 K*)    (both triangles; NULL to skip)
+                 lo/hi[M] = mean -/+ |sigma| * (chol(cov) . 1)   (NULL to skip; the reference's
+                            row-sum error bars, not sqrt(diag))
+   A posterior covariance that is not numerically PD makes lo/hi fail with DGP_ERR_NOT_PD
+   (the reference throws from bcholesky there); mean and cov are still valid.                    */
+int32_t dgp_fit(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec, dgp_model **out);
+int32_t dgp_model_destroy(dgp_ctx *ctx, dgp_model *model);
+int32_t dgp_model_energy(dgp_ctx *ctx, const dgp_model *model, double *e);
+int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *model, const double *Xs, int64_t M,
+                    int32_t x_layout, const double *mean_s, double *mean, double *cov,
+                    int64_t ldcov, double *lo, double *hi, double sigma);
+
+/* ---- multi-GPU: 2D block-cyclic Cholesky + NLL over NCCL (one process per GPU) --------------
+   Replaces nothing in the reference (its only distributed backend is Spark RDDs and is not on
+   the GP path); it is the N > one-GPU route to the same `energy` value.
+   Bootstrap: rank 0 calls dgp_dist_unique_id, the host side broadcasts the 128 bytes
+   (torch.distributed / any side channel), every rank calls dgp_dist_init.                      */
+int32_t dgp_dist_unique_id(void *id128);
+int32_t dgp_dist_init(dgp_ctx *ctx, const void *id128, int32_t rank, int32_t world,
+                      int32_t grid_rows, int32_t grid_cols);
+int32_t dgp_dist_finalize(dgp_ctx *ctx);
+/* X, y, mean are replicated on every rank (N*d doubles); K is never materialised on the host.
+   tile = block-cyclic tile edge (multiple of 128).  Every rank gets the same *e.
+   chol_ms (nullable) receives this rank's device time of the factorisation alone.              */
+int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec,
+                        int32_t tile, double *e, double *chol_ms);
+
+/* ---- measurement hooks (bench.py / tests; not part of the drop-in surface) ------------------ */
+/* out[0] DMMA FP64 TFLOP/s, out[1] DFMA FP64 TFLOP/s, out[2] HBM write GB/s, out[3] HBM copy GB/s
+   (read+write bytes), out[4] HBM read GB/s; each the best of a few timed launches.              */
+int32_t dgp_measure_peaks(dgp_ctx *ctx, double *out, int32_t n);
+/* Time `reps` launches of one phase on device-resident data: returns average ms per launch.
+   phase: 0 assemble (lower tiles of K+noise), 1 potrf of the assembled K, 2 trailing-update GEMM
+   at full size (M = N rows, K = nb).  Used for the roofline of the dominant kernels.            */
+int32_t dgp_time_phase(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec,
+                       int32_t phase, int32_t reps, double *avg_ms);
+/* Plain column-major FP64 GEMM / Cholesky on host buffers through the device kernels, for the
+   parity tests of the building blocks.  op flags: 0 = as stored (M x K / K x N), 1 = transposed
+   storage.  lower_only != 0 computes only tiles on or below the diagonal.                       */
+int32_t dgp_test_gemm(dgp_ctx *ctx, int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K,
+                      double alpha, const double *A, int64_t lda, const double *B, int64_t ldb,
+                      double beta, double *C, int64_t ldc, int32_t lower_only, double *ms);
+/* In: symmetric PD A (n x n, lower triangle read).  Out: L in the lower triangle of A (upper
+   zeroed), and, if Linv != NULL, L^-1 (lower, upper zeroed); if Ainv != NULL, A^-1 (both
+   triangles).  logdet_half = sum_i log L_ii.                                                    */
+int32_t dgp_test_potrf(dgp_ctx *ctx, int64_t n, double *A, int64_t lda, double *Linv, double *Ainv,
+                       double *logdet_half, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGP_B200_H */
