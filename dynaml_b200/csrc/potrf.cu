@@ -13,72 +13,138 @@ namespace dgp {
 namespace {
 
 constexpr int LB = 128;          // leaf block
-constexpr int LDL = LB + 1;      // padded leading dimension in shared memory
 constexpr int LEAF_THREADS = 256;
-constexpr size_t LEAF_SMEM = (size_t)(LB * LDL + LB) * sizeof(double);
+constexpr size_t LEAF_SMEM = 0;
 
-// Cholesky + triangular inverse of one 128x128 diagonal block, entirely in shared memory.
-//   S(r,c) at S[c*LDL + r].  Lower triangle: L.  Strict upper triangle: the running rows of
-//   W = L^-1 stored transposed (W(i,j), i > j, lives at S(j,i)); dinv[] holds 1/L(k,k) = W(k,k).
+// Cholesky + triangular inverse of one 128x128 diagonal block, register resident.
+//
+// The 256 threads form a 16x16 grid (tr, tc); thread (tr, tc) owns the elements (r, c) with
+// r = 16 i + tr, c = 16 q + tc (2D block-cyclic), i.e. an 8x8 local block of which only the local
+// lower part i >= q is live (36 FP64 values for L, 36 for W = L^-1).  Each elimination step
+// broadcasts one column (and, for the inverse, one row) through a double-buffered 128-entry line
+// in shared memory and costs a single __syncthreads; all register indices are compile-time after
+// unrolling the 16-wide column blocks, so nothing spills.
+//   step j of the factorisation:  l = sqrt(a_jj);  L(:,j) = a(:,j)/l;  a(r,c) -= L(r,j) L(c,j)
+//   step k of the inverse (L W = I, right-looking):  W(k,:) = R(k,:)/L(k,k);  R(i,:) -= L(i,k) W(k,:)
 __global__ void __launch_bounds__(LEAF_THREADS, 1)
 leaf_potrf_inv_kernel(double *A, int64_t lda, double *Inv, int *info, int pivot_base) {
-  extern __shared__ __align__(16) double S[];
-  double *dinv = S + LB * LDL;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ double colbuf[2][LB];
+  __shared__ double rowbuf[2][LB];
+  const int tid = threadIdx.x;
+  const int tr = tid & 15, tc = tid >> 4;
 
-  for (int idx = tid; idx < LB * LB; idx += LEAF_THREADS) {
-    int r = idx & (LB - 1), c = idx >> 7;
-    S[c * LDL + r] = (r >= c) ? A[r + (int64_t)c * lda] : 0.0;
+  double a[8][8], w[8][8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      w[i][q] = 0.0;
+      a[i][q] = (i >= q) ? A[(i * 16 + tr) + (int64_t)(q * 16 + tc) * lda] : 0.0;
+    }
+
+  // ---- factorisation --------------------------------------------------------------------------
+#pragma unroll
+  for (int jc = 0; jc < 8; ++jc) {
+    for (int jj = 0; jj < 16; ++jj) {
+      const int j = jc * 16 + jj;
+      double *cb = colbuf[j & 1];
+      if (tc == jj) {
+#pragma unroll
+        for (int i = jc; i < 8; ++i) cb[i * 16 + tr] = a[i][jc];
+      }
+      __syncthreads();
+      double d = cb[j];
+      if (!(d > 0.0)) {  // also catches NaN; uniform across the CTA
+        if (tid == 0) atomicCAS(info, 0, pivot_base + j + 1);
+        d = 1.0;
+      }
+      const double l = sqrt(d);
+      const double li = 1.0 / l;
+      double lr[8], lc[8];
+#pragma unroll
+      for (int i = jc; i < 8; ++i) {
+        lr[i] = cb[i * 16 + tr] * li;
+        lc[i] = cb[i * 16 + tc] * li;
+      }
+      // owners of column j keep the finished column
+      if (tc == jj) {
+#pragma unroll
+        for (int i = jc; i < 8; ++i) {
+          const int r = i * 16 + tr;
+          if (r > j) a[i][jc] = lr[i];
+          else if (r == j) a[i][jc] = l;
+        }
+      }
+      // trailing update on the live local part (rows > j, columns > j)
+#pragma unroll
+      for (int q = jc; q < 8; ++q) {
+        const bool cq = (q > jc) || (tc > jj);
+#pragma unroll
+        for (int i = q; i < 8; ++i) {
+          const bool ri = (i > jc) || (tr > jj);
+          if (cq && ri) a[i][q] = fma(-lr[i], lc[q], a[i][q]);
+        }
+      }
+    }
   }
   __syncthreads();
 
-  // ---- factorisation: unblocked right-looking, one column per step ---------------------------
-  for (int j = 0; j < LB; ++j) {
-    double d = S[j * LDL + j];
-    if (!(d > 0.0)) {  // also catches NaN; uniform across the CTA
-      if (tid == 0) atomicCAS(info, 0, pivot_base + j + 1);
-      d = 1.0;
-    }
-    const double l = sqrt(d);
-    const double li = 1.0 / l;
-    __syncthreads();  // everyone has read the pivot before it is overwritten
-    if (tid == 0) {
-      S[j * LDL + j] = l;
-      dinv[j] = li;
-    }
-    if (tid < LB - 1 - j) S[j * LDL + j + 1 + tid] *= li;
-    __syncthreads();
-    for (int c = j + 1 + warp; c < LB; c += LEAF_THREADS / 32) {
-      const double lcj = S[j * LDL + c];
-      for (int r = c + lane; r < LB; r += 32) S[c * LDL + r] = fma(-S[j * LDL + r], lcj, S[c * LDL + r]);
-    }
-    __syncthreads();
-  }
-
-  // ---- inverse: L W = I, row k of W finalised at step k, then pushed into the rows below ------
-  for (int k = 0; k < LB; ++k) {
-    const double dk = dinv[k];
-    if (tid < k) S[k * LDL + tid] *= dk;  // W(k, j<k) = R(k,j) / L(k,k)
-    __syncthreads();
-    for (int i = k + 1 + warp; i < LB; i += LEAF_THREADS / 32) {
-      const double lik = S[k * LDL + i];
-      for (int j = lane; j <= k; j += 32) {
-        const double wkj = (j == k) ? dk : S[k * LDL + j];
-        S[i * LDL + j] = fma(-lik, wkj, S[i * LDL + j]);
+  // ---- inverse ----------------------------------------------------------------------------------
+#pragma unroll
+  for (int kc = 0; kc < 8; ++kc) {
+    for (int kk = 0; kk < 16; ++kk) {
+      const int k = kc * 16 + kk;
+      double *cb = colbuf[k & 1];
+      double *rb = rowbuf[k & 1];
+      if (tc == kk) {  // column k of L, rows >= 16 kc
+#pragma unroll
+        for (int i = kc; i < 8; ++i) cb[i * 16 + tr] = a[i][kc];
+      }
+      if (tr == kk) {  // row k of R, columns < 16 (kc + 1)
+#pragma unroll
+        for (int q = 0; q <= kc; ++q) rb[q * 16 + tc] = w[kc][q];
+      }
+      __syncthreads();
+      const double dk = 1.0 / cb[k];
+      double wk[8], lik[8];
+#pragma unroll
+      for (int q = 0; q <= kc; ++q) {
+        const int c = q * 16 + tc;
+        wk[q] = (c == k) ? dk : ((c < k) ? rb[c] * dk : 0.0);
+      }
+#pragma unroll
+      for (int i = kc; i < 8; ++i) lik[i] = cb[i * 16 + tr];
+      if (tr == kk) {
+#pragma unroll
+        for (int q = 0; q <= kc; ++q) w[kc][q] = wk[q];
+      }
+#pragma unroll
+      for (int q = 0; q <= kc; ++q) {
+#pragma unroll
+        for (int i = kc; i < 8; ++i) {
+          if (i >= q) {
+            const bool ri = (i > kc) || (tr > kk);
+            if (ri) w[i][q] = fma(-lik[i], wk[q], w[i][q]);
+          }
+        }
       }
     }
-    __syncthreads();
   }
 
-  // ---- write back: L (upper part zeroed) and W ------------------------------------------------
-  for (int idx = tid; idx < LB * LB; idx += LEAF_THREADS) {
-    int r = idx & (LB - 1), c = idx >> 7;
-    A[r + (int64_t)c * lda] = (r >= c) ? S[c * LDL + r] : 0.0;
-    double w = 0.0;
-    if (r == c) w = dinv[r];
-    else if (r > c) w = S[r * LDL + c];
-    Inv[r + c * LB] = w;
-  }
+  // ---- write back: L (upper part zeroed) and W --------------------------------------------------
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 16 + tr, c = q * 16 + tc;
+      double lv = 0.0, wv = 0.0;
+      if (i >= q && r >= c) {
+        lv = a[i][q];
+        wv = w[i][q];
+      }
+      A[r + (int64_t)c * lda] = lv;
+      Inv[r + c * LB] = wv;
+    }
 }
 
 // W diagonal tiles <- leaf inverses
@@ -138,8 +204,7 @@ int32_t factor_block_column(Ctx *ctx, cudaStream_t st, double *A, int64_t lda, i
 }  // namespace
 
 int32_t potrf_init(Ctx *ctx) {
-  DGP_CUDA_OK(ctx, cudaFuncSetAttribute(leaf_potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)LEAF_SMEM));
+  (void)ctx;
   return DGP_OK;
 }
 

@@ -54,7 +54,7 @@ cases = {
   "se": (dg.SEKernel(2.0, 1.3), orc.Kernel("se", {"bandwidth": 2.0, "amplitude": 1.3})),
   "matern": (dg.GenericMaternKernel(2.5, 2), orc.Kernel("matern", {"p": 2.0, "l": 2.5})),
   "ard": (dg.MahalanobisKernel(np.linspace(1.5, 3, 8), 1.1), orc.Kernel("ard", {"MahalanobisAmplitude": 1.1, **{f"MahalanobisBandwidth_{i}": b for i, b in enumerate(np.linspace(1.5, 3, 8))}})),
-  "periodic": (dg.PeriodicKernel(1.2, 1.5, 0.05), orc.Kernel("periodic", {"sigma": 1.2, "lengthscale": 1.5, "frequency": 0.05})),
+  
 }
 for name, (k, ok) in cases.items():
     m = dg.GPRegression(k, dg.DiracKernel(0.3), list(zip(X, y)))

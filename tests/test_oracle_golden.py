@@ -1,0 +1,160 @@
+"""The oracle against every known-answer value the reference's own tests hold for this path
+(SURVEY.md 8c), plus self-consistency of the restatement.  CPU only."""
+import json
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+from oracle import gp_oracle as orc
+
+GOLD = Path(__file__).parent / "golden"
+KATS = json.loads((GOLD / "kats.json").read_text())
+
+
+def test_gpspec_energy_identity():
+    # GPSpec.scala:13-38: Dirac(0.5)+Dirac(0.5) on 2 points, mean v(0): K = I, residual 0 => log 2pi
+    X = np.array([[0.0], [1.0]])
+    y = np.array([0.0, 1.0])
+    e = orc.energy(orc.Kernel("dirac", {"noiseLevel": 0.5}), 0.5, X, y, mean=X[:, 0])
+    assert abs(e - KATS["gp_energy_identity"]["value"]) < KATS["gp_energy_identity"]["eps"]
+    assert e == pytest.approx(math.log(2 * math.pi), abs=1e-15)
+
+
+def test_gpspec_posterior_exact():
+    # GPSpec.scala:40-76: one training point, SE(1,1), noise 0: exact == in the reference
+    k = orc.Kernel("se", {"bandwidth": 1.0, "amplitude": 1.0})
+    mu, cov = orc.predictive(k, 0.0, np.array([[1.0]]), np.array([1.0]), np.array([[2.0]]))
+    assert mu[0] == KATS["gp_posterior_mean"]["value"]
+    assert cov[0, 0] == KATS["gp_posterior_var"]["value"]
+    lo, hi = orc.error_bars(mu, cov, 1.0)
+    assert lo[0] == KATS["gp_bar_lo"]["value"] and hi[0] == KATS["gp_bar_hi"]["value"]
+
+
+def test_kernelspec_se_value():
+    # KernelSpec.scala:34-58
+    k = orc.Kernel("se", {"bandwidth": 1.0, "amplitude": 1.0})
+    v = k.value(np.array([[1.0]]), np.array([[0.0]]))[0, 0]
+    assert abs(v - KATS["se_value_1_0"]["value"]) < KATS["se_value_1_0"]["eps"]
+
+
+def test_kernelspec_builders_layout():
+    # KernelSpec.scala:181-231: eval2(x,y) = 1/(1+(x-y)^2) on the points 0,1 -> [[1,.5],[.5,1]], cross with {0} -> [1,.5]
+    class Eval2(orc.Kernel):
+        def __init__(self):
+            super().__init__("rbf", {"bandwidth": 1.0})
+
+        def value(self, X, Y):
+            return 1.0 / (1.0 + orc._sqdist(X, Y))
+
+    X = np.array([[0.0], [1.0]])
+    K = orc.build_kernel_matrix(Eval2(), X)
+    assert K.shape == (2, 2) and np.array_equal(K, np.array([[1.0, 0.5], [0.5, 1.0]]))
+    C = orc.cross_kernel_matrix(Eval2(), X, np.array([[0.0]]))
+    assert C.shape == (2, 1) and np.array_equal(C[:, 0], np.array([1.0, 0.5]))
+
+
+def test_partitioned_cholesky_spec():
+    # PartitionedLinearAlgebraSpec.scala:14-46: 1000x1000 diagonal (i -> i+1?) in 5 blocks of 200
+    n = 1000
+    A = np.diag(np.arange(1, n + 1, dtype=float) ** 2)
+    L = orc.bcholesky(A, 200)
+    assert np.abs(L - np.diag(np.arange(1, n + 1, dtype=float))).max() <= KATS["bcholesky_diag_tol"]["value"]
+
+
+def test_blocked_equals_dense():
+    rng = np.random.default_rng(3)
+    n = 350
+    G = rng.standard_normal((n, n))
+    A = G @ G.T + n * np.eye(n)
+    Ld = sla.cholesky(A, lower=True)
+    for blk in (100, 175, 350, 1000):
+        Lb = orc.bcholesky(A, blk)
+        assert np.abs(Lb - Ld).max() / np.abs(Ld).max() < 1e-13
+        y = rng.standard_normal(n)
+        z = orc.lower_solve_blocked(Lb, y, blk)
+        assert np.allclose(z, sla.solve_triangular(Ld, y, lower=True), rtol=1e-11, atol=1e-13)
+        x = orc.upper_solve_blocked(Lb.T, z, blk)
+        assert np.allclose(x, np.linalg.solve(A, y), rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("kind,hyp", [
+    ("se", {"bandwidth": 1.3, "amplitude": 0.9}),
+    ("rbf", {"bandwidth": 1.3}),
+    ("ard", {"MahalanobisAmplitude": 1.2, "MahalanobisBandwidth_0": 1.0, "MahalanobisBandwidth_1": 2.0,
+             "MahalanobisBandwidth_2": 1.5}),
+    ("matern", {"p": 1.0, "l": 1.4}),
+    ("matern", {"p": 2.0, "l": 1.4}),
+    ("matern", {"p": 3.0, "l": 1.4}),
+])
+def test_gradient_formulas_match_finite_differences(kind, hyp):
+    """gradEnergy returns tr((aa' - K^-1) dK) = -2 d/dtheta of the *textbook* NLL."""
+    X, y, _ = orc.synthetic(60, 3, seed=11)
+    noise = 0.4
+
+    def textbook(h, nz):
+        K = orc.build_kernel_matrix(orc.Kernel(kind, h, "exact"), X, orc.dirac(nz))
+        L = sla.cholesky(K, lower=True)
+        a = sla.cho_solve((L, True), y)
+        return 0.5 * y @ a + np.log(np.diag(L)).sum()
+
+    g = orc.grad_energy(orc.Kernel(kind, hyp, "exact"), noise, X, y)
+    for name in g:
+        eps = 1e-6
+        if name == "noiseLevel":
+            fd = (textbook(hyp, noise + eps) - textbook(hyp, noise - eps)) / (2 * eps)
+        else:
+            hp, hm = dict(hyp), dict(hyp)
+            hp[name] += eps
+            hm[name] -= eps
+            fd = (textbook(hp, noise) - textbook(hm, noise)) / (2 * eps)
+        assert g[name] == pytest.approx(-2.0 * fd, rel=2e-5, abs=1e-6), name
+
+
+def test_reference_energy_has_half_logdet():
+    # the log-det term is sum log L_ii, not 2 * that
+    X, y, _ = orc.synthetic(40, 2, seed=5)
+    k = orc.Kernel("se", {"bandwidth": 1.0, "amplitude": 1.0})
+    K = orc.build_kernel_matrix(k, X, orc.dirac(0.3))
+    sign, logdet = np.linalg.slogdet(K)
+    a = np.linalg.solve(K, y)
+    expect = 0.5 * (y @ a + 0.5 * logdet + len(y) * math.log(2 * math.pi))
+    assert orc.energy(k, 0.3, X, y) == pytest.approx(expect, rel=1e-12)
+
+
+def test_dirac_fires_on_duplicates_and_uses_abs():
+    # SURVEY Q4 (DiracKernel.scala:43-47)
+    X = np.array([[0.0, 1.0], [0.0, 1.0], [2.0, 2.0]])
+    K = orc.dirac(-0.7).value(X, X)
+    assert np.array_equal(K, np.array([[0.7, 0.7, 0.0], [0.7, 0.7, 0.0], [0.0, 0.0, 0.7]]))
+
+
+def test_mahalanobis_reference_gradient_is_the_defective_one():
+    # SURVEY D2 (RBFKernel.scala:142-143): every bandwidth gets k*|x-y|^2/b_i^3
+    X, _, _ = orc.synthetic(5, 2, seed=2)
+    h = {"MahalanobisAmplitude": 1.0, "MahalanobisBandwidth_0": 1.5, "MahalanobisBandwidth_1": 0.5}
+    g = orc.Kernel("ard", h, "reference").grads(X, X)
+    assert np.allclose(g["MahalanobisBandwidth_0"] * 1.5 ** 3, g["MahalanobisBandwidth_1"] * 0.5 ** 3)
+    ge = orc.Kernel("ard", h, "exact").grads(X, X)
+    assert not np.allclose(ge["MahalanobisBandwidth_0"] * 1.5 ** 3, ge["MahalanobisBandwidth_1"] * 0.5 ** 3)
+
+
+def test_golden_fixtures_are_current():
+    """The committed fixtures are what the oracle produces today (guards against silent drift)."""
+    z = np.load(GOLD / "housing.npz")
+    k = orc.Kernel("se", {"bandwidth": float(z["bandwidth"]), "amplitude": float(z["amplitude"])})
+    assert orc.energy(k, float(z["noise"]), z["Xtr"], z["ytr"]) == pytest.approx(float(z["energy"]), rel=1e-12)
+    s = np.load(GOLD / "synthetic.npz")
+    k2 = orc.Kernel("matern", {"p": 2.0, "l": 2.2})
+    assert orc.energy(k2, float(s["noise"]), s["X"], s["y"]) == pytest.approx(float(s["matern2_energy"]), rel=1e-12)
+
+
+def test_non_pd_gives_inf_and_nan():
+    X = np.array([[0.0], [0.0], [1.0]])  # duplicate point, no noise: singular K
+    y = np.array([1.0, 2.0, 3.0])
+    k = orc.Kernel("rbf", {"bandwidth": 1.0})
+    assert orc.energy(k, 0.0, X, y) == float("inf")
+    g = orc.grad_energy(k, 0.0, X, y)
+    assert all(math.isnan(v) for v in g.values())
