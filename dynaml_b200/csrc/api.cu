@@ -130,6 +130,7 @@ int32_t scaled_points(Ctx *ctx, cudaStream_t st, const Spec &sp, const double *X
   for (int c = 0; c < 128; ++c) s.v[c] = (c < d) ? 1.0 / sp.hyp[1 + c] : 0.0;
   int64_t total = np * dp;
   scale_points_byval_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, Xs, s, total, dp);
+  ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   *out = Xs;
   return DGP_OK;
@@ -703,6 +704,12 @@ int32_t dgp_kernel_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec, const doubl
 }
 
 // ---- measurement hooks ---------------------------------------------------------------------------
+int32_t dgp_launch_count(const dgp_ctx *ctx, uint64_t *out) {
+  if (!ctx || !out) return DGP_ERR_ARG;
+  *out = ctx->launches;
+  return DGP_OK;
+}
+
 int32_t dgp_measure_peaks(dgp_ctx *ctx, double *out, int32_t n) {
   if (!ctx || !out) return DGP_ERR_ARG;
   cudaSetDevice(ctx->device);

@@ -175,6 +175,7 @@ int32_t assemble(Ctx *ctx, cudaStream_t st, const CovParams &cp, const AssembleA
     case DGP_KERNEL_DIRAC: launch_kind<DGP_KERNEL_DIRAC>(st, cp, a, (unsigned)tiles); break;
     default: return ctx->fail(DGP_ERR_UNSUPPORTED_KERNEL, "assemble: kernel kind %d", cp.kind);
   }
+  ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
 }

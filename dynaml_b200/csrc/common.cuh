@@ -39,6 +39,7 @@ struct Ctx {
   int lookahead = 1;
   int timing = 1;     // record per-phase events
   double timings[16];
+  uint64_t launches = 0;  // kernels launched by this library on this context
   int *d_info = nullptr;  // device-side status word(s): [0] = first failing pivot index + 1, 0 = ok
   int *h_info = nullptr;  // pinned mirror
   double *h_scal = nullptr;  // pinned scratch for scalar read-back (64 doubles)

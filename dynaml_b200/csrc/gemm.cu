@@ -241,6 +241,7 @@ int32_t gemm(Ctx *ctx, cudaStream_t stream, const GemmArgs &a) {
   else if (!a.a_kmajor && a.b_kmajor) launch<false, true>(stream, a, grid);
   else if (a.a_kmajor && !a.b_kmajor) launch<true, false>(stream, a, grid);
   else launch<true, true>(stream, a, grid);
+  ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
 }

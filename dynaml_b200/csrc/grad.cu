@@ -216,6 +216,7 @@ int32_t launch(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArgs &a
   grad_trace_kernel<MODE, DP><<<(unsigned)tiles, GTHREADS, smem, st>>>(cp, a);
   DGP_CUDA_OK(ctx, cudaGetLastError());
   reduce_partials_kernel<<<NS, 1024, 0, st>>>(a.partials, tiles, NS, a.sums);
+  ctx->launches += 2;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   *ns_out = NS;
   return DGP_OK;

@@ -174,6 +174,7 @@ int32_t factor_block_column(Ctx *ctx, cudaStream_t st, double *A, int64_t lda, i
   for (int64_t cs = c0; cs < c0 + w; cs += LB) {
     double *invb = inv + (cs / LB) * LB * LB;
     leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM, st>>>(A + cs + cs * lda, lda, invb, info, (int)cs);
+    ctx->launches++;
     DGP_CUDA_OK(ctx, cudaGetLastError());
     const int64_t rb = cs + LB;
     if (rb >= n) break;
@@ -272,6 +273,7 @@ int32_t trtri_lower(Ctx *ctx, const double *L, int64_t ldl, const double *inv, i
   if (n % LB) return ctx->fail(DGP_ERR_SHAPE, "trtri: n must be a multiple of 128");
   cudaStream_t S = ctx->stream;
   copy_diag_blocks_kernel<<<(unsigned)(n / LB), 256, 0, S>>>(inv, W, ldw);
+  ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   // Level h joins the inverses of two adjacent diagonal blocks [r0, r0+h) and [r0+h, r0+h+h2):
   //   W21 = -W22 * (L21 * W11)

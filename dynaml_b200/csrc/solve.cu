@@ -155,6 +155,7 @@ int32_t trsv_lower_fwd(Ctx *ctx, cudaStream_t st, const double *L, int64_t ldl, 
   if (nblk == 0) return DGP_OK;
   trsv_fwd_step_kernel<<<1, SB, 0, st>>>(L, ldl, inv, x, -1);
   for (int b = 0; b + 1 < nblk; ++b) trsv_fwd_step_kernel<<<nblk - 1 - b, SB, 0, st>>>(L, ldl, inv, x, b);
+  ctx->launches += nblk;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
 }
@@ -165,18 +166,21 @@ int32_t trsv_lower_bwd(Ctx *ctx, cudaStream_t st, const double *L, int64_t ldl, 
   if (nblk == 0) return DGP_OK;
   trsv_bwd_step_kernel<<<1, SB, 0, st>>>(L, ldl, inv, x, nblk, nblk);
   for (int b = nblk - 1; b >= 1; --b) trsv_bwd_step_kernel<<<b, SB, 0, st>>>(L, ldl, inv, x, b, nblk);
+  ctx->launches += nblk;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
 }
 
 int32_t diag_log_sum(Ctx *ctx, cudaStream_t st, const double *A, int64_t lda, int64_t n, double *out) {
   diag_log_sum_kernel<<<1, 1024, 0, st>>>(A, lda, n, out);
+  ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
 }
 
 int32_t dot(Ctx *ctx, cudaStream_t st, const double *x, const double *y, int64_t n, double *out) {
   dot_kernel<<<1, 1024, 0, st>>>(x, y, n, out);
+  ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
 }
@@ -185,6 +189,7 @@ int32_t gemv_t(Ctx *ctx, cudaStream_t st, const double *A, int64_t lda, int64_t 
                const double *base, double *y) {
   if (cols == 0) return DGP_OK;
   gemv_t_kernel<<<(unsigned)cols, 256, 0, st>>>(A, lda, rows, x, base, y);
+  ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
 }
@@ -192,6 +197,7 @@ int32_t gemv_t(Ctx *ctx, cudaStream_t st, const double *A, int64_t lda, int64_t 
 int32_t lower_row_sums(Ctx *ctx, cudaStream_t st, const double *L, int64_t ldl, int64_t n, double *bar) {
   if (n == 0) return DGP_OK;
   lower_row_sums_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(L, ldl, n, bar);
+  ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
 }
@@ -201,6 +207,7 @@ int32_t mirror_lower(Ctx *ctx, cudaStream_t st, double *A, int64_t lda, int64_t 
   if (n % 32) return ctx->fail(DGP_ERR_SHAPE, "mirror_lower: n must be a multiple of 32");
   dim3 grid((unsigned)(n / 32), (unsigned)(n / 32));
   mirror_lower_kernel<<<grid, 256, 0, st>>>(A, lda);
+  ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
 }

@@ -166,8 +166,11 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spe
 
 /* ---- measurement hooks (bench.py / tests; not part of the drop-in surface) ------------------ */
 /* out[0] DMMA FP64 TFLOP/s, out[1] DFMA FP64 TFLOP/s, out[2] HBM write GB/s, out[3] HBM copy GB/s
-   (read+write bytes), out[4] HBM read GB/s; each the best of a few timed launches.              */
+   (read+write bytes), out[4] HBM read GB/s, each the best of a few timed launches; out[5] DMMA TFLOP/s
+   sustained over ~1 s of back-to-back launches.              */
 int32_t dgp_measure_peaks(dgp_ctx *ctx, double *out, int32_t n);
+/* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
+int32_t dgp_launch_count(const dgp_ctx *ctx, uint64_t *out);
 /* Time `reps` launches of one phase on device-resident data: returns average ms per launch.
    phase: 0 assemble (lower tiles of K+noise), 1 potrf of the assembled K, 2 trailing-update GEMM
    at full size (M = N rows, K = nb).  Used for the roofline of the dominant kernels.            */

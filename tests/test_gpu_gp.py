@@ -1,0 +1,305 @@
+"""Parity of the GP hot path on the GPU (through the C ABI and the host-side mirror) against the
+oracle and the committed golden fixtures.
+
+Tolerances (north_star): <= 1e-12 relative on kernel entries; <= 1e-9 relative on NLL, gradient,
+predictive mean / covariance for noise sigma^2 >= 1e-6."""
+import json
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import dynaml_b200 as dg
+from dynaml_b200 import _capi
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+KATS = json.loads((GOLD / "kats.json").read_text())
+TOL_K, TOL = 1e-12, 1e-9
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def entry_rel(a, b):
+    return float((np.abs(a - b) / np.maximum(np.abs(b), 1e-300)).max())
+
+
+def make_pair(name, d, band=None):
+    """(device kernel, oracle kernel) with the fixture's hyper-parameters."""
+    if name == "se":
+        return dg.SEKernel(1.7, 1.2), orc.Kernel("se", {"bandwidth": 1.7, "amplitude": 1.2})
+    if name == "rbf":
+        return dg.RBFKernel(2.1), orc.Kernel("rbf", {"bandwidth": 2.1})
+    if name in ("ard_ref", "ard_exact"):
+        mode = "reference" if name == "ard_ref" else "exact"
+        h = {"MahalanobisAmplitude": 1.1, **{f"MahalanobisBandwidth_{i}": b for i, b in enumerate(band)}}
+        return (dg.MahalanobisKernel(band, 1.1, _capi.GRAD_REFERENCE if mode == "reference" else _capi.GRAD_EXACT),
+                orc.Kernel("ard", h, mode))
+    if name.startswith("matern"):
+        p = int(name[-1])
+        return dg.GenericMaternKernel(2.2, p), orc.Kernel("matern", {"p": float(p), "l": 2.2})
+    if name == "periodic":
+        return dg.PeriodicKernel(1.3, 1.4, 0.07), orc.Kernel("periodic",
+                                                             {"sigma": 1.3, "lengthscale": 1.4, "frequency": 0.07})
+    raise ValueError(name)
+
+
+ALL = ["se", "rbf", "ard_ref", "ard_exact", "matern1", "matern2", "matern3", "periodic"]
+
+
+# ---- the reference's own known-answer tests, through the mirrored API --------------------------
+def test_gpspec_energy():
+    # GPSpec.scala:13-38
+    data = [([0.0], 0.0), ([1.0], 1.0)]
+    model = dg.AbstractGPRegressionModel(dg.DiracKernel(0.5), dg.DiracKernel(0.5), lambda v: v[0])(data, len(data))
+    likelihood = model.energy(model._current_state)
+    assert likelihood - KATS["gp_energy_identity"]["value"] < 1e-5
+    assert likelihood == pytest.approx(math.log(2 * math.pi), abs=1e-14)
+
+
+def test_gpspec_posterior_and_error_bars():
+    # GPSpec.scala:40-76 (the reference asserts ==; the device exp may differ from java.lang.Math by 1 ulp)
+    data = [([1.0], 1.0), ([2.0], 4.0)]
+    noise = dg.DiracKernel(0.0)
+    noise.block_all_hyper_parameters()
+    model = dg.AbstractGPRegressionModel(dg.SEKernel(1.0, 1.0), noise, lambda v: 0.0)(data[:1], 1)
+    post = model.predictiveDistribution([data[1][0]])
+    rho = math.exp(-0.5)
+    assert post.underlyingDist.mean[0] == pytest.approx(rho, rel=4e-16)
+    assert post.underlyingDist.covariance[0, 0] == pytest.approx(1.0 - rho * rho, rel=1e-15)
+    bars = model.predictionWithErrorBars([data[1][0]], 1)
+    assert bars[0][2] == pytest.approx(KATS["gp_bar_lo"]["value"], abs=1e-15)
+    assert bars[0][3] == pytest.approx(KATS["gp_bar_hi"]["value"], abs=1e-15)
+
+
+def test_kernelspec_se_value():
+    # KernelSpec.scala:34-58
+    assert abs(dg.SEKernel(1.0, 1.0).evaluate([1.0], [0.0]) - 0.6065306597126334) < 1e-15
+
+
+# ---- kernel matrices ------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ALL)
+def test_kernel_matrix_entries(name):
+    z = np.load(GOLD / "synthetic.npz")
+    X = z["X"][:, :1] if name == "periodic" else z["X"]
+    Xs = z["Xs"][:, :1] if name == "periodic" else z["Xs"]
+    k, ok = make_pair(name, X.shape[1], z["band"])
+    K = k.buildKernelMatrix(X, len(X)).getKernelMatrix()
+    Ko = orc.build_kernel_matrix(ok, X)
+    assert K.shape == Ko.shape and entry_rel(K, Ko) <= TOL_K
+    assert np.array_equal(K, K.T)
+    assert entry_rel(K[:, 3], z[f"{name}_Kcol"]) <= TOL_K  # committed golden column
+    C = k.buildCrossKernelMatrix(X, Xs)
+    assert C.shape == (len(X), len(Xs)) and entry_rel(C, orc.cross_kernel_matrix(ok, X, Xs)) <= TOL_K
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 5, 13, 16, 17, 33, 40])
+def test_kernel_matrix_feature_counts(d):
+    X, _, Xs = orc.synthetic(150, d, seed=d, m=37)
+    k, ok = dg.SEKernel(1.0 + 0.1 * d, 0.8), orc.Kernel("se", {"bandwidth": 1.0 + 0.1 * d, "amplitude": 0.8})
+    assert entry_rel(k.buildKernelMatrix(X, 150).getKernelMatrix(), orc.build_kernel_matrix(ok, X)) <= TOL_K
+    assert entry_rel(k.buildCrossKernelMatrix(X, Xs), orc.cross_kernel_matrix(ok, X, Xs)) <= TOL_K
+    m, om = dg.GenericMaternKernel(1.0 + 0.1 * d, 2), orc.Kernel("matern", {"p": 2.0, "l": 1.0 + 0.1 * d})
+    assert entry_rel(m.buildKernelMatrix(X, 150).getKernelMatrix(), orc.build_kernel_matrix(om, X)) <= TOL_K
+
+
+def test_dirac_noise_on_duplicates_and_abs(ctx):
+    # |noise| wherever |x-y| == 0, duplicates included
+    X = np.array([[0.0, 1.0], [0.0, 1.0], [2.0, 2.0], [0.5, 0.5]])
+    se, ose = dg.SEKernel(1.0, 1.0), orc.Kernel("se", {"bandwidth": 1.0, "amplitude": 1.0})
+    K = (se + dg.DiracKernel(-0.7)).buildKernelMatrix(X, 4).getKernelMatrix()
+    Ko = orc.build_kernel_matrix(ose, X, orc.dirac(-0.7))
+    assert entry_rel(K, Ko) <= TOL_K and K[0, 1] == pytest.approx(1.7, rel=1e-15)
+
+
+def test_column_major_points_layout(ctx):
+    X, _, _ = orc.synthetic(70, 3, seed=1)
+    spec, keep = dg.SEKernel(1.1, 1.0)._spec()
+    import ctypes as C
+    out = np.empty((70, 70), order="F")
+    Xc = np.asfortranarray(X)
+    st = ctx.lib.dgp_kernel_matrix(ctx.h, C.byref(spec), Xc.ctypes.data_as(C.POINTER(C.c_double)), 70, None, 0, 3,
+                                   _capi.DGP_COL_MAJOR, out.ctypes.data_as(C.POINTER(C.c_double)), 70, 0)
+    assert st == 0
+    assert entry_rel(out, orc.build_kernel_matrix(orc.Kernel("se", {"bandwidth": 1.1, "amplitude": 1.0}), X)) <= TOL_K
+
+
+# ---- energy / gradient ------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ALL)
+def test_energy_and_gradient_vs_golden(name):
+    z = np.load(GOLD / "synthetic.npz")
+    X = z["X"][:, :1] if name == "periodic" else z["X"]
+    k, _ = make_pair(name, X.shape[1], z["band"])
+    model = dg.GPRegression(k, dg.DiracKernel(float(z["noise"])), list(zip(X, z["y"])))
+    e = model.energy(model._current_state)
+    assert e == pytest.approx(float(z[f"{name}_energy"]), rel=TOL)
+    g = model.gradEnergy(model._current_state)
+    names = [str(s) for s in z[f"{name}_grad_names"]]
+    assert list(g.keys()) == names
+    scale = np.abs(z[f"{name}_grad"]).max()
+    for n_, v in zip(names, z[f"{name}_grad"]):
+        assert g[n_] == pytest.approx(float(v), rel=TOL, abs=TOL * scale), n_
+
+
+def test_housing_golden():
+    """Config C1: housing, SE + Dirac."""
+    z = np.load(GOLD / "housing.npz")
+    k = dg.SEKernel(float(z["bandwidth"]), float(z["amplitude"]))
+    model = dg.GPRegression(k, dg.DiracKernel(float(z["noise"])), list(zip(z["Xtr"], z["ytr"])))
+    assert model.energy(model._current_state) == pytest.approx(float(z["energy"]), rel=TOL)
+    g = model.gradEnergy(model._current_state)
+    for n_, v in zip(z["grad_names"], z["grad"]):
+        assert g[str(n_)] == pytest.approx(float(v), rel=TOL)
+    post = model.predictiveDistribution(z["Xte"])
+    assert rel(post.mu, z["mu"]) <= TOL and rel(post.covariance, z["cov"]) <= TOL
+    lo, hi = post.underlyingDist.confidenceInterval(float(z["sigma"]))
+    assert rel(lo, z["lo"]) <= 1e-8 and rel(hi, z["hi"]) <= 1e-8
+    res = model.test(list(zip(z["Xte"], z["yte"])))
+    assert len(res) == 56 and res[0][2] == pytest.approx(float(z["mu"][0]), rel=TOL)
+
+
+@pytest.mark.parametrize("n,d,noise", [(1, 1, 0.5), (2, 1, 0.1), (127, 4, 0.1), (128, 4, 0.1), (129, 4, 0.1),
+                                       (1000, 8, 1e-3), (2500, 8, 0.05)])
+def test_energy_grad_ragged_sizes_vs_oracle(n, d, noise):
+    """Ragged N around the 128 tile, and the stress noise 1e-3 (sigma^2 = 1e-6)."""
+    X, y, _ = orc.synthetic(n, d, seed=n)
+    k, ok = dg.SEKernel(1.5 * math.sqrt(d), 1.0), orc.Kernel("se", {"bandwidth": 1.5 * math.sqrt(d), "amplitude": 1.0})
+    model = dg.GPRegression(k, dg.DiracKernel(noise), list(zip(X, y)))
+    assert model.energy(model._current_state) == pytest.approx(orc.energy(ok, noise, X, y), rel=TOL)
+    g, go = model.gradEnergy(model._current_state), orc.grad_energy(ok, noise, X, y)
+    scale = max(abs(v) for v in go.values())
+    for name, v in go.items():
+        assert g[name] == pytest.approx(v, rel=1e-7 if noise < 0.01 else TOL, abs=TOL * scale), name
+
+
+def test_mean_function_and_validation_set():
+    X, y, _ = orc.synthetic(200, 3, seed=3)
+    mean = lambda x: 0.3 * x[0] - 0.1  # noqa: E731
+    k, ok = dg.SEKernel(1.4, 1.0), orc.Kernel("se", {"bandwidth": 1.4, "amplitude": 1.0})
+    model = dg.GPRegression(k, dg.DiracKernel(0.2), list(zip(X[:150], y[:150])), mean)
+    m = 0.3 * X[:, 0] - 0.1
+    assert model.energy(model._current_state) == pytest.approx(orc.energy(ok, 0.2, X[:150], y[:150], m[:150]), rel=TOL)
+    model.validationSet_(list(zip(X[150:], y[150:])))  # GPRegression.scala:148-174: concatenated
+    assert model.energy(model._current_state) == pytest.approx(orc.energy(ok, 0.2, X, y, m), rel=TOL)
+
+
+def test_non_pd_is_inf_and_nan():
+    # AbstractGPRegressionModel.scala:243-251, 531-533
+    X = np.array([[0.0], [0.0], [1.0], [2.0]])
+    noise = dg.DiracKernel(0.0)
+    model = dg.GPRegression(dg.RBFKernel(1.0), noise, list(zip(X, [1.0, 2.0, 3.0, 4.0])))
+    assert model.energy(model._current_state) == float("inf")
+    g = model.gradEnergy(model._current_state)
+    assert set(g) == {"bandwidth", "noiseLevel"} and all(math.isnan(v) for v in g.values())
+
+
+def test_blocked_hyper_parameters_drop_out_of_the_gradient():
+    X, y, _ = orc.synthetic(100, 2, seed=8)
+    k, nz = dg.SEKernel(1.0, 1.0), dg.DiracKernel(0.3)
+    k.block("amplitude")
+    nz.block_all_hyper_parameters()
+    g = dg.GPRegression(k, nz, list(zip(X, y))).gradEnergy({"bandwidth": 1.0})
+    assert list(g) == ["bandwidth"]
+
+
+# ---- prediction ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ALL)
+def test_predictive_distribution_vs_golden(name):
+    z = np.load(GOLD / "synthetic.npz")
+    X = z["X"][:, :1] if name == "periodic" else z["X"]
+    Xs = z["Xs"][:, :1] if name == "periodic" else z["Xs"]
+    k, _ = make_pair(name, X.shape[1], z["band"])
+    model = dg.GPRegression(k, dg.DiracKernel(float(z["noise"])), list(zip(X, z["y"])))
+    post = model.predictiveDistribution(Xs)
+    assert rel(post.mu, z[f"{name}_mu"]) <= TOL
+    assert rel(post.covariance, z[f"{name}_cov"]) <= TOL
+    assert np.array_equal(post.covariance, post.covariance.T)
+
+
+def test_error_bars_are_row_sums_of_the_posterior_factor():
+    # SURVEY Q3
+    X, y, Xs = orc.synthetic(300, 4, seed=12, m=50)
+    k, ok = dg.GenericMaternKernel(2.0, 2), orc.Kernel("matern", {"p": 2.0, "l": 2.0})
+    model = dg.GPRegression(k, dg.DiracKernel(0.3), list(zip(X, y)))
+    model.persist(model._current_state)
+    bars = model.predictionWithErrorBars(Xs, 2)
+    mu, cov = orc.predictive(ok, 0.3, X, y, Xs)
+    lo, hi = orc.error_bars(mu, cov, 2.0)
+    assert rel([b[1] for b in bars], mu) <= TOL
+    assert rel([b[2] for b in bars], lo) <= 1e-8 and rel([b[3] for b in bars], hi) <= 1e-8
+    model.unpersist()
+    assert model.predict(Xs[0]) == pytest.approx(mu[0], rel=TOL)
+
+
+# ---- tuners ---------------------------------------------------------------------------------------------
+def test_energy_batch_equals_serial_and_grid_search_matches_oracle():
+    X, y, _ = orc.synthetic(300, 3, seed=21)
+    k = dg.SEKernel(2.0, 1.5)
+    model = dg.GPRegression(k, dg.DiracKernel(0.8), list(zip(X, y)))
+    gs = dg.GridSearch(model).setGridSize(3).setStepSize(0.2)
+    init = {"bandwidth": 2.0, "amplitude": 1.5, "noiseLevel": 0.8}
+    grid = gs.getGrid(init)
+    batch = model.energyBatch(grid)
+    serial = [model.energy(c) for c in grid]
+    assert batch == serial  # same kernels, same order: bitwise
+    ref = [orc.energy(orc.Kernel("se", {"bandwidth": c["bandwidth"], "amplitude": c["amplitude"]}), c["noiseLevel"],
+                      X, y) for c in grid]
+    assert rel(batch, ref) <= TOL
+    _, best = gs.optimize(init)
+    assert best == grid[int(np.argmin(ref))]
+
+
+def test_batch_survives_a_non_pd_candidate():
+    X = np.array([[0.0], [0.0], [1.0], [2.0], [3.0]])
+    model = dg.GPRegression(dg.RBFKernel(1.0), dg.DiracKernel(0.5), list(zip(X, [1.0, 2.0, 3.0, 4.0, 5.0])))
+    e = model.energyBatch([{"bandwidth": 1.0, "noiseLevel": 0.5}, {"bandwidth": 1.0, "noiseLevel": 0.0},
+                           {"bandwidth": 2.0, "noiseLevel": 0.5}])
+    assert math.isfinite(e[0]) and e[1] == float("inf") and math.isfinite(e[2])
+
+
+def test_csa_and_ml2_improve_the_energy():
+    X, y, _ = orc.synthetic(256, 2, seed=5)
+    model = dg.GPRegression(dg.SEKernel(3.0, 2.0), dg.DiracKernel(1.0), list(zip(X, y)))
+    init = {"bandwidth": 3.0, "amplitude": 2.0, "noiseLevel": 1.0}
+    e0 = model.energy(init)
+    csa = dg.CoupledSimulatedAnnealing(model, rng=np.random.default_rng(1)).setGridSize(2).setStepSize(0.3)
+    _, best = csa.setMaxIterations(4).optimize(init)
+    assert model.energy(best) < e0
+    # the reference's "gradient" is -2 dE/dtheta of the textbook NLL: ascending along +g lowers it,
+    # and its update h - step*g with a small step must not blow up
+    _, sol = dg.GradBasedGlobalOptimizer(model).optimize(init, {"tolerance": "1e-4", "step": "1e-5",
+                                                                "maxIterations": "5"})
+    assert all(math.isfinite(v) and v > 0 for v in sol.values())
+
+
+# ---- full-size, size-independent properties --------------------------------------------------------------
+def test_c2_size_energy_properties(ctx):
+    """N = 8192, d = 8 ARD-SE (BASELINE config C2): properties that need no CPU reference.
+    (1) energy() and energy_grad() agree on E; (2) look-ahead on/off agree to rounding;
+    (3) sum_i b_i^3 g_{b_i}(exact) = b_0^3 g_{b_0}(reference): the defective reference derivative is
+        the sum over dimensions of the exact ones (|x-y|^2 = sum_i (x_i-y_i)^2)."""
+    n, d = 8192, 8
+    X, y, _ = orc.synthetic(n, d, seed=0)
+    band = np.linspace(2.0, 4.0, d)
+    data = ctx.data_create(X, y)
+    try:
+        kr = dg.MahalanobisKernel(band, 1.0, _capi.GRAD_REFERENCE)
+        ke = dg.MahalanobisKernel(band, 1.0, _capi.GRAD_EXACT)
+        e0 = ctx.energy(data, kr._spec(noise=0.1))
+        e1, gr = ctx.energy_grad(data, kr._spec(noise=0.1))
+        _, ge = ctx.energy_grad(data, ke._spec(noise=0.1))
+        assert e1 == e0
+        ctx.set_option("lookahead", 0)
+        e2 = ctx.energy(data, kr._spec(noise=0.1))
+        ctx.set_option("lookahead", 1)
+        assert e2 == pytest.approx(e0, rel=1e-12)
+        lhs = float(np.sum(band ** 3 * ge[1:1 + d]))
+        assert lhs == pytest.approx(band[0] ** 3 * gr[1], rel=1e-9)
+        assert ge[0] == pytest.approx(gr[0], rel=1e-12) and ge[-1] == pytest.approx(gr[-1], rel=1e-12)
+    finally:
+        ctx.data_destroy(data)

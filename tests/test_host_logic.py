@@ -1,0 +1,199 @@
+"""Host-side mirror of the reference API: hyper-parameter plumbing, grid construction, CSA formulas,
+candidate sharding.  CPU only -- no compute call reaches the CUDA library here."""
+import math
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import dynaml_b200 as dg
+from dynaml_b200 import optimization as opt
+from oracle import gp_oracle as orc
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_block_unblock_like_kernelspec():
+    # KernelSpec.scala:12-32
+    se = dg.SEKernel(band=1.0, h=1.0)
+    hyp = se.hyper_parameters
+    se.block(hyp[0])
+    assert se.effective_hyper_parameters[0] == hyp[-1]
+    se.block_all_hyper_parameters()
+    assert se.effective_hyper_parameters == []
+    se.block()
+    assert len(se.effective_hyper_parameters) == 2
+
+
+def test_set_hyper_parameters_requires_all_effective_keys():
+    se = dg.SEKernel(1.0, 1.0)
+    with pytest.raises(AssertionError):
+        se.setHyperParameters({"bandwidth": 2.0})
+    se.block("amplitude")
+    se.setHyperParameters({"bandwidth": 2.0, "amplitude": 9.0})
+    assert se.state == {"bandwidth": 2.0, "amplitude": 1.0}  # blocked keys are not overwritten
+
+
+def test_matern_p_is_blocked_and_floored():
+    # GenericMaternKernel.scala:42-53
+    k = dg.GenericMaternKernel(1.5, 2)
+    assert k.hyper_parameters == ["p", "l"] and k.effective_hyper_parameters == ["l"]
+    k.block()
+    k.setHyperParameters({"p": -2.7, "l": 0.5})
+    assert k.state == {"p": 2.0, "l": 0.5}
+
+
+def test_mahalanobis_names():
+    k = dg.MahalanobisKernel([1.0, 2.0, 3.0], 1.5)
+    assert k.hyper_parameters == ["MahalanobisAmplitude", "MahalanobisBandwidth_0", "MahalanobisBandwidth_1",
+                                  "MahalanobisBandwidth_2"]
+    assert k._device_hyp(k.state) == [1.5, 1.0, 2.0, 3.0]
+
+
+def test_additive_covariance_naming_and_routing():
+    # KernelSpec.scala:87-129; AdditiveCovariance.scala:32-58
+    se, nz = dg.SEKernel(1.0, 2.0), dg.DiracKernel(0.5)
+    nz.block_all_hyper_parameters()
+    add = se + nz
+    fid, sid = str(se).split(".")[-1], str(nz).split(".")[-1]
+    assert add.hyper_parameters == [f"{fid}/bandwidth", f"{fid}/amplitude", f"{sid}/noiseLevel"]
+    assert add.effective_hyper_parameters == [f"{fid}/bandwidth", f"{fid}/amplitude"]
+    add.setHyperParameters({f"{fid}/bandwidth": 3.0, f"{fid}/amplitude": 4.0})
+    assert se.state == {"bandwidth": 3.0, "amplitude": 4.0} and nz.state == {"noiseLevel": 0.5}
+
+
+def test_unsupported_kernel_has_no_cpu_fallback():
+    class Cauchy(dg.LocalScalarKernel):
+        hyper_parameters = ["sigma"]
+
+    with pytest.raises(NotImplementedError):
+        Cauchy()._spec()
+
+
+def test_dirac_builder_override_is_signed():
+    # DiracKernel.scala:55-58
+    K = dg.DiracKernel(-0.3).buildKernelMatrix([[0.0], [1.0]], 2).getKernelMatrix()
+    assert np.array_equal(K, -0.3 * np.eye(2))
+
+
+class FakeSystem:
+    """A GloballyOptimizable whose energy is a known function (no GPU)."""
+
+    def __init__(self):
+        self.calls = []
+        self.persisted = None
+
+    def energy(self, h, options=None):
+        self.calls.append(dict(h))
+        return (h["a"] - 1.0) ** 2 + (h["b"] - 0.5) ** 2
+
+    def energyBatch(self, hs, options=None):
+        return [self.energy(h, options) for h in hs]
+
+    def persist(self, h):
+        self.persisted = dict(h)
+
+
+@pytest.mark.parametrize("log_scale", [False, True])
+def test_get_grid_matches_oracle(log_scale):
+    t = dg.GridSearch(FakeSystem()).setGridSize(4).setStepSize(0.2).setLogScale(log_scale)
+    init = {"a": 2.0, "b": 1.5}
+    grid = t.getGrid(init)
+    assert grid == orc.get_grid(init, 4, 0.2, log_scale)
+    assert len(grid) == 16
+    # ModelTuner.scala:83-86
+    first = 2.0 / math.exp(0.2) if log_scale else 2.0 - 0.2
+    assert grid[0]["a"] == first
+
+
+def test_grid_search_picks_minimum_and_persists():
+    sys_ = FakeSystem()
+    t = dg.GridSearch(sys_).setGridSize(5).setStepSize(0.25)
+    _, best = t.optimize({"a": 2.0, "b": 1.5}, {"persist": "true"})
+    e, cfg = orc.grid_search(lambda c: FakeSystem().energy(c), {"a": 2.0, "b": 1.5}, 5, 0.25, False)
+    assert best == cfg and sys_.persisted == cfg
+    assert len(sys_.calls) == 25
+
+
+@pytest.mark.parametrize("variant", ["CSA-MuSA", "CSA-BA", "CSA-M", "CSA-MwVC", "SA"])
+def test_csa_formulas_match_oracle(variant):
+    land = [3.0, 1.0, 2.5, 0.2]
+    t = 0.7
+    g = dg.CoupledSimulatedAnnealing.couplingFactor(variant, land, t)
+    assert g == pytest.approx(orc.csa_coupling(variant, land, t), rel=1e-15)
+    p = dg.CoupledSimulatedAnnealing.acceptanceProbability(variant, 1.2, 2.0, g, t)
+    assert p == pytest.approx(orc.csa_acceptance(variant, 1.2, 2.0, g, t), rel=1e-15)
+
+
+def test_csa_runs_and_never_worsens_best():
+    sys_ = FakeSystem()
+    csa = dg.CoupledSimulatedAnnealing(sys_, rng=np.random.default_rng(0)).setGridSize(3).setStepSize(0.3)
+    csa.setMaxIterations(6).setVariant(dg.CoupledSimulatedAnnealing.MwVC)
+    init = {"a": 2.0, "b": 1.5}
+    start = min(e for e, _ in csa.getEnergyLandscape(init))
+    _, best = csa.optimize(init)
+    assert sys_.energy(best) <= start + 1e-12
+    assert all(v >= 0 for v in best.values())  # mutate takes abs()
+    # temperatures (AbstractCSA.scala:132-136)
+    assert csa.acceptanceTemperature(1.0, 3) == 1.0 / math.log(4.0) and csa.mutationTemperature(1.0, 4) == 0.25
+
+
+def test_grad_descent_step_rule():
+    class G(FakeSystem):
+        def gradEnergy(self, h):
+            return {"a": 2 * (h["a"] - 1.0), "b": 2 * (h["b"] - 0.5)}
+
+    _, sol = dg.GradBasedGlobalOptimizer(G()).optimize({"a": 2.0, "b": 1.5},
+                                                       {"tolerance": "1e-9", "step": "0.1", "maxIterations": "200"})
+    assert sol["a"] == pytest.approx(1.0, abs=1e-6) and sol["b"] == pytest.approx(0.5, abs=1e-6)
+
+
+def test_shard_indices_cover_everything_once():
+    for n in (0, 1, 7, 256):
+        for world in (1, 2, 4, 8):
+            got = sorted(i for r in range(world) for i in opt.shard_indices(n, r, world))
+            assert got == list(range(n))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys_ = FakeSystem()
+        t = dg.GridSearch(sys_).setGridSize(4).setStepSize(0.2)
+        land = t.getEnergyLandscape({"a": 2.0, "b": 1.5})
+        _, best = t.optimize({"a": 2.0, "b": 1.5})
+        # every rank sees the full landscape but evaluated only its own shard (twice: landscape + optimize)
+        q.put((rank, [e for e, _ in land], best, len(sys_.calls)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_candidates_shard_across_two_gloo_ranks():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    serial = [e for e, _ in dg.GridSearch(FakeSystem()).setGridSize(4).setStepSize(0.2)
+              .getEnergyLandscape({"a": 2.0, "b": 1.5})]
+    assert res[0][1] == serial and res[1][1] == serial
+    assert res[0][2] == res[1][2]
+    assert res[0][3] == 16 and res[1][3] == 16  # 8 of the 16 candidates, two sweeps
