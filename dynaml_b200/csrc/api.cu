@@ -280,6 +280,7 @@ int32_t dgp_ctx_destroy(dgp_ctx *ctx) {
   if (!ctx) return DGP_OK;
   cudaSetDevice(ctx->device);
   dist_destroy(ctx);
+  gemm_release(ctx);
   ctx->release_all();
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   for (int i = 0; i < 16; ++i) cudaEventDestroy(ctx->tev[i]);

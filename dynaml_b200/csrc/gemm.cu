@@ -1,28 +1,50 @@
 // gemm.cu -- FP64 GEMM on the sm_100a DMMA tensor path (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4;
 // tcgen05 has no f64 kind).
 //
-// One CTA = 256 threads = 8 warps computes a 128x128 tile of C; each warp owns 64x32 of it as
-// 8x4 DMMA accumulators (128 FP64 registers).  Operands stream through a 4-stage cp.async
-// (LDGSTS) pipeline in slices of BK = 16; shared-memory rows are padded by 4 doubles so that the
-// 64-bit fragment loads of a half-warp hit 16 distinct bank pairs (conflict-free) for both the
-// "MN-major" and the "K-major" operand layouts.  The kernel is FP64-pipe bound by construction:
-// per BK slice a CTA moves 32 KB from L2 for 262144 FMAs (~4096 tensor-pipe cycles per SM).
+// One CTA = 256 threads = 8 warps computes a 128x64 tile of C; each warp owns 32x32 of it as 4x4
+// DMMA accumulators (64 FP64 registers), so two CTAs are resident per SM (<= 128 registers per
+// thread, <= 113 KB shared memory each).  Two co-resident CTAs matter more than a bigger tile:
+// while one CTA runs its read-modify-write epilogue or refills its pipeline, the other keeps the
+// FP64 tensor pipe busy, and the main loop has 4 warps per scheduler to hide LDS latency and the
+// per-slice barrier (ncu of the first 128x128 / one-CTA version: tensor pipe 73 % active at K = 256,
+// 86 % at K = 4096; profiles/).
+//
+// Operands stream through a cp.async (LDGSTS) pipeline in slices of BK = 16; shared-memory rows
+// are padded by 4 doubles so the 64-bit fragment loads of a half-warp hit 16 distinct bank pairs
+// for both the "MN-major" and the "K-major" layouts (ncu: 0 bank conflicts).
+//
+// Tiles are launched in the order of a host-built tile table: super-rows of 12 x 128 rows swept
+// column by column, so the ~300 concurrently resident CTAs share ~12 A panels and ~24 B panels
+// and the long-K products (triangular inverse, L^-T L^-1) stream their operands from L2 instead
+// of HBM; triangular k-ranges put the heavy tiles first.
 //
 // Replaces, in the reference, every Breeze `*` / `inv` / `\` call on blocks:
 //   CORE/algebra/bcholesky.scala:111-121 (L21 = A21 inv(L11)^T ; A22 - L21 L21^T),
 //   CORE/algebra/PartitionedMatrixSolvers.scala:120-169 (multi-RHS forward solve),
 //   CORE/algebra/PartitionedMatrixOps.scala:280-301 (block GEMM).
+#include <algorithm>
+#include <tuple>
+
 #include "gemm.cuh"
 
 namespace dgp {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, NTHREADS = 256;
-constexpr int LDS_MN = BM + 4;             // doubles per k-row of an MN-major stage   (132 = 4 mod 16)
-constexpr int LDS_K = BK + 4;              // doubles per mn-row of a K-major stage    ( 20 = 4 mod 16)
-constexpr int STAGE_MN = BK * LDS_MN;      // 2112 doubles
-constexpr int STAGE_K = BM * LDS_K;        // 2560 doubles
+constexpr int BM = 128, BN = 64, BK = 16, NTHREADS = 256;
+constexpr int LDA_MN = BM + 4;  // 132 = 4 mod 16
+constexpr int LDB_MN = BN + 4;  //  68 = 4 mod 16
+constexpr int LDS_K = BK + 4;   //  20 = 4 mod 16
+constexpr int SUPER_ROWS = 12;
+
+template <bool AK, bool BKM>
+struct Cfg {
+  static constexpr int A_STAGE = AK ? BM * LDS_K : BK * LDA_MN;   // 2560 / 2112 doubles
+  static constexpr int B_STAGE = BKM ? BN * LDS_K : BK * LDB_MN;  // 1280 / 1088 doubles
+  // two CTAs per SM must fit in 227 KB: 4 stages unless both operands are K-major
+  static constexpr int STAGES = ((A_STAGE + B_STAGE) * 4 * 8 <= 112 * 1024) ? 4 : 3;
+  static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+};
 
 __device__ __forceinline__ void cp_async16(double *smem, const double *gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -40,21 +62,24 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// Copy one 128 x 16 operand slice into a stage.  g points at the slice origin.
-template <bool KMAJOR>
+// Copy one ROWS x 16 operand slice into a stage (ROWS = 128 for A, 64 for B).  g points at the
+// slice origin.
+template <bool KMAJOR, int ROWS>
 __device__ __forceinline__ void load_slice(double *s, const double *g, int64_t ld, int tid) {
+  constexpr int CHUNKS = ROWS * BK / 2;  // 16-byte chunks
+  constexpr int LD_MN = ROWS + 4;
   if (!KMAJOR) {
-    // element (mn, k) at g[mn + k*ld]; 16 columns of 128 contiguous doubles
+    // element (mn, k) at g[mn + k*ld]; 16 columns of ROWS contiguous doubles
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < CHUNKS / NTHREADS; ++i) {
       int c = tid + i * NTHREADS;
-      int k = c >> 6, mc = c & 63;
-      cp_async16(s + k * LDS_MN + mc * 2, g + mc * 2 + (int64_t)k * ld);
+      int k = c / (ROWS / 2), mc = c % (ROWS / 2);
+      cp_async16(s + k * LD_MN + mc * 2, g + mc * 2 + (int64_t)k * ld);
     }
   } else {
-    // element (mn, k) at g[k + mn*ld]; 128 rows of 16 contiguous doubles
+    // element (mn, k) at g[k + mn*ld]; ROWS rows of 16 contiguous doubles
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < CHUNKS / NTHREADS; ++i) {
       int c = tid + i * NTHREADS;
       int mn = c >> 3, kc = c & 7;
       cp_async16(s + mn * LDS_K + kc * 2, g + kc * 2 + (int64_t)mn * ld);
@@ -63,36 +88,23 @@ __device__ __forceinline__ void load_slice(double *s, const double *g, int64_t l
 }
 
 template <bool AK, bool BKM>
-__global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
+__global__ void __launch_bounds__(NTHREADS, 2) dgemm_dmma_kernel(GemmArgs p, const uint32_t *__restrict__ tiles) {
   extern __shared__ __align__(16) double smem[];
-  constexpr int A_STAGE = AK ? STAGE_K : STAGE_MN;
-  constexpr int B_STAGE = BKM ? STAGE_K : STAGE_MN;
+  using C_ = Cfg<AK, BKM>;
+  constexpr int A_STAGE = C_::A_STAGE, B_STAGE = C_::B_STAGE, STAGES = C_::STAGES;
   double *As = smem;
   double *Bs = smem + STAGES * A_STAGE;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int wm = warp & 1, wn = warp >> 1;  // 2 x 4 warps, 64 x 32 each
+  const int wm = warp & 3, wn = warp >> 2;  // 4 x 2 warps, 32 x 32 each
 
-  // ---- tile decode -----------------------------------------------------------------------
-  int64_t tlin = blockIdx.x;
-  if (p.reverse) tlin = (int64_t)gridDim.x - 1 - tlin;
-  int ti, tj;
-  if (p.lower_only) {
-    ti = (int)((sqrt(8.0 * (double)tlin + 1.0) - 1.0) * 0.5);
-    while ((int64_t)ti * (ti + 1) / 2 > tlin) --ti;
-    while ((int64_t)(ti + 1) * (ti + 2) / 2 <= tlin) ++ti;
-    tj = (int)(tlin - (int64_t)ti * (ti + 1) / 2);
-  } else {
-    int mt = p.M / BM;
-    tj = (int)(tlin / mt);
-    ti = (int)(tlin % mt);
-  }
-  const int m0 = ti * BM, n0 = tj * BN;
+  const uint32_t tile = tiles[blockIdx.x];
+  const int m0 = (int)(tile >> 16) * BM, n0 = (int)(tile & 0xffffu) * BN;
 
   int k_lo = 0, k_hi = p.K;
-  if (p.kmode == K_GE_COL) k_lo = n0;
+  if (p.kmode == K_GE_COL) k_lo = (n0 / BK) * BK;
   else if (p.kmode == K_LT_ROWEND) k_hi = min(p.K, m0 + BM);
   else if (p.kmode == K_GE_ROW) k_lo = m0;
   const int KT = (k_hi - k_lo) / BK;
@@ -101,7 +113,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
   const double *B = p.B + (int64_t)blockIdx.y * p.strideB;
   double *C = p.C + (int64_t)blockIdx.y * p.strideC;
 
-  // slice origins at k = k_lo
   const double *Ag = AK ? (A + k_lo + (int64_t)m0 * p.lda) : (A + m0 + (int64_t)k_lo * p.lda);
   const double *Bg = BKM ? (B + k_lo + (int64_t)n0 * p.ldb) : (B + n0 + (int64_t)k_lo * p.ldb);
   const int64_t a_step = AK ? (int64_t)BK : (int64_t)BK * p.lda;
@@ -110,37 +121,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
   // Pull the C tile towards L2 while the main loop runs (read-modify-write epilogue).
   if (p.beta != 0.0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int c = tid + i * NTHREADS;  // 1024 lines of 128 B: 8 per column
+    for (int i = 0; i < 2; ++i) {
+      int c = tid + i * NTHREADS;  // 512 lines of 128 B: 8 per column
       int col = c >> 3, seg = c & 7;
       const double *ptr = C + m0 + seg * 16 + (int64_t)(n0 + col) * p.ldc;
       asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ptr));
     }
   }
 
-  double acc[8][4][2];
+  double acc[4][4][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  // ---- prologue: STAGES-1 slices in flight -------------------------------------------------
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < KT) {
-      load_slice<AK>(As + s * A_STAGE, Ag + s * a_step, p.lda, tid);
-      load_slice<BKM>(Bs + s * B_STAGE, Bg + s * b_step, p.ldb, tid);
+      load_slice<AK, BM>(As + s * A_STAGE, Ag + s * a_step, p.lda, tid);
+      load_slice<BKM, BN>(Bs + s * B_STAGE, Bg + s * b_step, p.ldb, tid);
     }
     cp_async_commit();
   }
 
-  // fragment base offsets inside a stage
-  const int a_off = AK ? ((wm * 64 + g) * LDS_K + t) : (t * LDS_MN + wm * 64 + g);
-  const int b_off = BKM ? ((wn * 32 + g) * LDS_K + t) : (t * LDS_MN + wn * 32 + g);
-  constexpr int A_I = AK ? 8 * LDS_K : 8;          // next 8 rows of the fragment grid
-  constexpr int A_KK = AK ? 4 : 4 * LDS_MN;        // next k4 step
+  const int a_off = AK ? ((wm * 32 + g) * LDS_K + t) : (t * LDA_MN + wm * 32 + g);
+  const int b_off = BKM ? ((wn * 32 + g) * LDS_K + t) : (t * LDB_MN + wn * 32 + g);
+  constexpr int A_I = AK ? 8 * LDS_K : 8;
+  constexpr int A_KK = AK ? 4 : 4 * LDA_MN;
   constexpr int B_J = BKM ? 8 * LDS_K : 8;
-  constexpr int B_KK = BKM ? 4 : 4 * LDS_MN;
+  constexpr int B_KK = BKM ? 4 : 4 * LDB_MN;
 
   for (int kt = 0; kt < KT; ++kt) {
     cp_async_wait<STAGES - 2>();
@@ -149,8 +158,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
       int nk = kt + STAGES - 1;
       if (nk < KT) {
         int s = nk % STAGES;
-        load_slice<AK>(As + s * A_STAGE, Ag + (int64_t)nk * a_step, p.lda, tid);
-        load_slice<BKM>(Bs + s * B_STAGE, Bg + (int64_t)nk * b_step, p.ldb, tid);
+        load_slice<AK, BM>(As + s * A_STAGE, Ag + (int64_t)nk * a_step, p.lda, tid);
+        load_slice<BKM, BN>(Bs + s * B_STAGE, Bg + (int64_t)nk * b_step, p.ldb, tid);
       }
       cp_async_commit();
     }
@@ -158,36 +167,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
     const double *bs = Bs + (kt % STAGES) * B_STAGE + b_off;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
-      double a[8], b[4];
+      double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = as[kk * A_KK + i * A_I];
+      for (int i = 0; i < 4; ++i) a[i] = as[kk * A_KK + i * A_I];
 #pragma unroll
       for (int j = 0; j < 4; ++j) b[j] = bs[kk * B_KK + j * B_J];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
   }
   cp_async_wait<0>();
 
-  // ---- epilogue ----------------------------------------------------------------------------
-  // acc[i][j][r] is C(m0 + wm*64 + i*8 + g, n0 + wn*32 + j*8 + 2t + r).
+  // acc[i][j][r] is C(m0 + wm*32 + i*8 + g, n0 + wn*32 + j*8 + 2t + r).
   const double alpha = p.alpha, beta = p.beta;
-  double *Cw = C + m0 + wm * 64 + g + (int64_t)(n0 + wn * 32 + 2 * t) * p.ldc;
+  double *Cw = C + m0 + wm * 32 + g + (int64_t)(n0 + wn * 32 + 2 * t) * p.ldc;
   if (beta != 0.0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      double old[8][2];
+    for (int jh = 0; jh < 2; ++jh) {
+      double old[2][4][2];
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
+      for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) old[i][r] = Cw[i * 8 + (int64_t)(j * 8 + r) * p.ldc];
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
+          for (int i = 0; i < 4; ++i) old[jj][i][r] = Cw[i * 8 + (int64_t)((jh * 2 + jj) * 8 + r) * p.ldc];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          Cw[i * 8 + (int64_t)(j * 8 + r) * p.ldc] = alpha * acc[i][j][r] + beta * old[i][r];
+      for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            Cw[i * 8 + (int64_t)((jh * 2 + jj) * 8 + r) * p.ldc] =
+                alpha * acc[i][jh * 2 + jj][r] + beta * old[jj][i][r];
     }
   } else {
 #pragma unroll
@@ -195,27 +208,74 @@ __global__ void __launch_bounds__(NTHREADS, 1) dgemm_dmma_kernel(GemmArgs p) {
 #pragma unroll
       for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) Cw[i * 8 + (int64_t)(j * 8 + r) * p.ldc] = alpha * acc[i][j][r];
+        for (int i = 0; i < 4; ++i) Cw[i * 8 + (int64_t)(j * 8 + r) * p.ldc] = alpha * acc[i][j][r];
   }
-}
-
-template <bool AK, bool BKM>
-constexpr size_t smem_bytes() {
-  return (size_t)STAGES * ((AK ? STAGE_K : STAGE_MN) + (BKM ? STAGE_K : STAGE_MN)) * sizeof(double);
 }
 
 template <bool AK, bool BKM>
 cudaError_t opt_in() {
   return cudaFuncSetAttribute(dgemm_dmma_kernel<AK, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)smem_bytes<AK, BKM>());
+                              (int)Cfg<AK, BKM>::SMEM);
 }
 
 template <bool AK, bool BKM>
-void launch(cudaStream_t stream, const GemmArgs &a, dim3 grid) {
-  dgemm_dmma_kernel<AK, BKM><<<grid, NTHREADS, smem_bytes<AK, BKM>(), stream>>>(a);
+void launch(cudaStream_t stream, const GemmArgs &a, dim3 grid, const uint32_t *tiles) {
+  dgemm_dmma_kernel<AK, BKM><<<grid, NTHREADS, Cfg<AK, BKM>::SMEM, stream>>>(a, tiles);
+}
+
+// ---- tile tables -----------------------------------------------------------------------------
+// Entry = (row tile << 16) | column tile, row tiles of 128, column tiles of 64.  Super-rows of
+// SUPER_ROWS row tiles are swept column by column; `bottom_first` reverses the super-row order
+// (used when the k-range, hence the work, grows with the row index).
+void build_tiles(int mt, int nt, bool lower, bool bottom_first, std::vector<uint32_t> &out) {
+  out.clear();
+  const int nsuper = (mt + SUPER_ROWS - 1) / SUPER_ROWS;
+  for (int s0 = 0; s0 < nsuper; ++s0) {
+    const int s = bottom_first ? nsuper - 1 - s0 : s0;
+    const int r_lo = s * SUPER_ROWS, r_hi = std::min(mt, r_lo + SUPER_ROWS);
+    auto ncols = [&](int ti) { return lower ? std::min(nt, 2 * ti + 2) : nt; };
+    const int cmax = ncols(r_hi - 1);
+    for (int tj = 0; tj < cmax; ++tj)
+      for (int ti = r_lo; ti < r_hi; ++ti)
+        if (tj < ncols(ti)) out.push_back(((uint32_t)ti << 16) | (uint32_t)tj);
+  }
 }
 
 }  // namespace
+
+struct TileTable {
+  uint32_t *dev = nullptr;
+  size_t count = 0;
+};
+
+static std::map<std::tuple<int, int, int, int>, TileTable> &tables(Ctx *ctx) {
+  // one cache per context, keyed by (row tiles, column tiles, lower, bottom_first)
+  static std::map<Ctx *, std::map<std::tuple<int, int, int, int>, TileTable>> all;
+  return all[ctx];
+}
+
+void gemm_release(Ctx *ctx) {
+  for (auto &kv : tables(ctx)) cudaFree(kv.second.dev);
+  tables(ctx).clear();
+}
+
+static int32_t get_tiles(Ctx *ctx, int mt, int nt, bool lower, bool bottom_first, TileTable *out) {
+  auto key = std::make_tuple(mt, nt, (int)lower, (int)bottom_first);
+  auto &tb = tables(ctx);
+  auto it = tb.find(key);
+  if (it == tb.end()) {
+    std::vector<uint32_t> host;
+    build_tiles(mt, nt, lower, bottom_first, host);
+    TileTable t;
+    t.count = host.size();
+    DGP_CUDA_OK(ctx, cudaMalloc(&t.dev, std::max<size_t>(1, host.size()) * sizeof(uint32_t)));
+    // synchronous copy: the table may be consumed from either stream right away
+    DGP_CUDA_OK(ctx, cudaMemcpy(t.dev, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    it = tb.emplace(key, t).first;
+  }
+  *out = it->second;
+  return DGP_OK;
+}
 
 int32_t gemm_init(Ctx *ctx) {
   DGP_CUDA_OK(ctx, (opt_in<false, false>()));
@@ -233,14 +293,16 @@ int32_t gemm(Ctx *ctx, cudaStream_t stream, const GemmArgs &a) {
     return ctx->fail(DGP_ERR_SHAPE, "gemm: operands must be 16-byte aligned with even leading dimensions");
   if (a.lower_only && a.M != a.N) return ctx->fail(DGP_ERR_SHAPE, "gemm: lower_only needs a square C");
   if (a.kmode != K_FULL && (a.K % BM)) return ctx->fail(DGP_ERR_SHAPE, "gemm: triangular k-range needs K %% 128 == 0");
-  int64_t mt = a.M / BM, nt = a.N / BN;
-  int64_t tiles = a.lower_only ? mt * (mt + 1) / 2 : mt * nt;
-  if (tiles > 0x7fffffffLL || a.batch > 65535) return ctx->fail(DGP_ERR_SHAPE, "gemm: grid too large");
-  dim3 grid((unsigned)tiles, (unsigned)a.batch, 1);
-  if (!a.a_kmajor && !a.b_kmajor) launch<false, false>(stream, a, grid);
-  else if (!a.a_kmajor && a.b_kmajor) launch<false, true>(stream, a, grid);
-  else if (a.a_kmajor && !a.b_kmajor) launch<true, false>(stream, a, grid);
-  else launch<true, true>(stream, a, grid);
+  const int mt = a.M / BM, nt = a.N / BN;
+  if (mt > 65535 || nt > 65535 || a.batch > 65535) return ctx->fail(DGP_ERR_SHAPE, "gemm: grid too large");
+  TileTable tt;
+  DGP_TRY(get_tiles(ctx, mt, nt, a.lower_only != 0, a.reverse != 0, &tt));
+  if (tt.count == 0) return DGP_OK;
+  dim3 grid((unsigned)tt.count, (unsigned)a.batch, 1);
+  if (!a.a_kmajor && !a.b_kmajor) launch<false, false>(stream, a, grid, tt.dev);
+  else if (!a.a_kmajor && a.b_kmajor) launch<false, true>(stream, a, grid, tt.dev);
+  else if (a.a_kmajor && !a.b_kmajor) launch<true, false>(stream, a, grid, tt.dev);
+  else launch<true, true>(stream, a, grid, tt.dev);
   ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;

@@ -7,7 +7,7 @@
 namespace dgp {
 
 // Per-tile restriction of the contraction range, used to skip the structurally-zero half of a
-// triangular operand.  (m0, n0) is the origin of the 128x128 output tile.
+// triangular operand.  (m0, n0) is the origin of the 128x64 output tile.
 enum KMode {
   K_FULL = 0,
   K_GE_COL = 1,      // k in [n0, K)        : op(B) is lower triangular  (B[k][n] = 0 for k < n)
@@ -25,7 +25,7 @@ struct GemmArgs {
   const double *B = nullptr;
   double *C = nullptr;
   int64_t lda = 0, ldb = 0, ldc = 0;
-  int M = 0, N = 0, K = 0;  // multiples of 128, 128, 16
+  int M = 0, N = 0, K = 0;  // multiples of 128, 64, 16
   double alpha = 1.0, beta = 0.0;
   int a_kmajor = 0, b_kmajor = 0;
   int lower_only = 0;  // square C: only tiles with m0 >= n0
@@ -38,5 +38,6 @@ struct GemmArgs {
 // Enqueue on `stream`.  Returns DGP_OK or a CUDA error recorded on ctx.
 int32_t gemm(Ctx *ctx, cudaStream_t stream, const GemmArgs &args);
 int32_t gemm_init(Ctx *ctx);  // opt in to the large dynamic shared memory once per context
+void gemm_release(Ctx *ctx);  // free the cached tile tables of a context
 
 }  // namespace dgp

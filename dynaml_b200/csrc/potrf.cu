@@ -170,7 +170,7 @@ cudaEvent_t get_event(Ctx *ctx, size_t i) {
 // Factor the block column starting at c0 (width w): leaves, in-place panel products and the
 // updates confined to the block column.  Enqueued on `st`.
 int32_t factor_block_column(Ctx *ctx, cudaStream_t st, double *A, int64_t lda, int64_t n, int64_t c0, int64_t w,
-                            double *inv, int *info) {
+                            double *inv, int *info, double *scratch) {
   for (int64_t cs = c0; cs < c0 + w; cs += LB) {
     double *invb = inv + (cs / LB) * LB * LB;
     leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM, st>>>(A + cs + cs * lda, lda, invb, info, (int)cs);
@@ -178,13 +178,16 @@ int32_t factor_block_column(Ctx *ctx, cudaStream_t st, double *A, int64_t lda, i
     DGP_CUDA_OK(ctx, cudaGetLastError());
     const int64_t rb = cs + LB;
     if (rb >= n) break;
-    // panel: A[rb:, cs:cs+128] <- A[rb:, cs:cs+128] * inv(L_cs)^T   (in place: each CTA reads and
-    // writes exactly its own 128x128 region, and reads complete before its epilogue starts)
+    // panel: A[rb:, cs:cs+128] <- A[rb:, cs:cs+128] * inv(L_cs)^T, through a scratch copy of the
+    // panel (two CTAs share each 128-row strip, so the product cannot run in place)
+    const int64_t mrows = n - rb;
+    DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(scratch, mrows * sizeof(double), A + rb + cs * lda, lda * sizeof(double),
+                                       mrows * sizeof(double), LB, cudaMemcpyDeviceToDevice, st));
     GemmArgs g;
-    g.A = A + rb + cs * lda;  g.lda = lda;  g.a_kmajor = 0;
-    g.B = invb;               g.ldb = LB;   g.b_kmajor = 0;   // op(B)(k,n) = inv(n,k)
+    g.A = scratch;            g.lda = mrows;  g.a_kmajor = 0;
+    g.B = invb;               g.ldb = LB;     g.b_kmajor = 0;   // op(B)(k,n) = inv(n,k)
     g.C = A + rb + cs * lda;  g.ldc = lda;
-    g.M = (int)(n - rb);  g.N = LB;  g.K = LB;
+    g.M = (int)mrows;  g.N = LB;  g.K = LB;
     g.alpha = 1.0;  g.beta = 0.0;
     DGP_TRY(gemm(ctx, st, g));
     // update the remaining columns of this block column with the 128 columns just finished
@@ -217,6 +220,8 @@ int32_t potrf_blocked(Ctx *ctx, double *A, int64_t lda, int64_t n, double *inv, 
   cudaStream_t P = la ? ctx->panel : ctx->stream;
   size_t ev = 0;
 
+  double *scratch = (double *)ctx->buf("potrf_panel", (size_t)n * LB * sizeof(double));
+  if (!scratch) return DGP_ERR_OOM;
   if (la) {  // the panel stream starts after whatever produced A on the main stream
     cudaEvent_t e = get_event(ctx, ev++);
     DGP_CUDA_OK(ctx, cudaEventRecord(e, S));
@@ -225,7 +230,7 @@ int32_t potrf_blocked(Ctx *ctx, double *A, int64_t lda, int64_t n, double *inv, 
 
   for (int64_t c0 = 0; c0 < n; c0 += nb) {
     const int64_t w = (n - c0 < nb) ? (n - c0) : nb;
-    DGP_TRY(factor_block_column(ctx, P, A, lda, n, c0, w, inv, info));
+    DGP_TRY(factor_block_column(ctx, P, A, lda, n, c0, w, inv, info, scratch));
     const int64_t c1 = c0 + w;
     if (c1 >= n) break;
     if (la) {

@@ -8,79 +8,109 @@ namespace {
 
 constexpr int SB = 128;  // block edge (= leaf block)
 
-// y[r] = sum_{j<128} M[r + j*ld] * v[j]   for r = threadIdx.x  (128 threads, v in shared memory)
-__device__ __forceinline__ double rowblock_mv(const double *M, int64_t ld, const double *v, int r) {
+constexpr int ST = 256;  // threads per CTA of the solve steps
+
+// sum_{j<64} M[r + j*ld] * v[j]: half of a 128-wide block row; 16 independent loads in flight
+__device__ __forceinline__ double rowhalf_mv(const double *M, int64_t ld, const double *v, int r) {
   double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-#pragma unroll 4
-  for (int j = 0; j < SB; j += 4) {
-    acc0 = fma(M[r + (int64_t)(j + 0) * ld], v[j + 0], acc0);
-    acc1 = fma(M[r + (int64_t)(j + 1) * ld], v[j + 1], acc1);
-    acc2 = fma(M[r + (int64_t)(j + 2) * ld], v[j + 2], acc2);
-    acc3 = fma(M[r + (int64_t)(j + 3) * ld], v[j + 3], acc3);
+#pragma unroll
+  for (int j0 = 0; j0 < 64; j0 += 16) {
+    double m[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) m[u] = M[r + (int64_t)(j0 + u) * ld];
+#pragma unroll
+    for (int u = 0; u < 16; u += 4) {
+      acc0 = fma(m[u + 0], v[j0 + u + 0], acc0);
+      acc1 = fma(m[u + 1], v[j0 + u + 1], acc1);
+      acc2 = fma(m[u + 2], v[j0 + u + 2], acc2);
+      acc3 = fma(m[u + 3], v[j0 + u + 3], acc3);
+    }
   }
   return (acc0 + acc1) + (acc2 + acc3);
 }
 
-// out[c] = sum_{k<128} M[k + c*ld] * v[k] for c = 0..127: one warp per column, lanes over k.
-// 128 threads = 4 warps, each handles 32 columns.  Result for column c is returned to lane 0 and
-// written through `store(c, value)`.
+// 128-row block times a 128-vector with 256 threads: thread (r, h) does half h of row r; the two
+// halves meet in `part`.  Returns the full sum to the h == 0 threads.
+__device__ __forceinline__ double rowblock_mv(const double *M, int64_t ld, const double *v, double *part) {
+  const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
+  const double acc = rowhalf_mv(M + (int64_t)(h * 64) * ld, ld, v + h * 64, r);
+  if (h == 1) part[r] = acc;
+  __syncthreads();
+  return acc + part[r];
+}
+
+// out[c] = sum_{k<128} M[k + c*ld] * v[k] for c = 0..127: 8 warps x 16 columns, four columns
+// (16 loads per lane) in flight at a time, lanes over k.
 template <typename Store>
 __device__ __forceinline__ void colblock_dot(const double *M, int64_t ld, const double *v, Store store) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double v0 = v[lane], v1 = v[lane + 32], v2 = v[lane + 64], v3 = v[lane + 96];
-  for (int c = warp; c < SB; c += 4) {
-    const double *col = M + (int64_t)c * ld;
-    double s = (col[lane] * v0 + col[lane + 32] * v1) + (col[lane + 64] * v2 + col[lane + 96] * v3);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) store(c, s);
+  for (int q = 0; q < 4; ++q) {
+    double m[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double *col = M + (int64_t)(warp * 16 + q * 4 + u) * ld;
+      m[u][0] = col[lane];
+      m[u][1] = col[lane + 32];
+      m[u][2] = col[lane + 64];
+      m[u][3] = col[lane + 96];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      double s = (m[u][0] * v0 + m[u][1] * v1) + (m[u][2] * v2 + m[u][3] * v3);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) store(warp * 16 + q * 4 + u, s);
+    }
   }
 }
 
 // Forward step b: every row block i > b subtracts L(i,b) z_b; the CTA of block b+1 then applies
 // inv(L_{b+1,b+1}) so that the next launch finds z_{b+1} ready.  b == -1: only z_0 = inv_0 x_0.
-__global__ void __launch_bounds__(SB) trsv_fwd_step_kernel(const double *L, int64_t ldl, const double *inv, double *x,
+__global__ void __launch_bounds__(ST) trsv_fwd_step_kernel(const double *L, int64_t ldl, const double *inv, double *x,
                                                            int b) {
   __shared__ double v[SB];
-  const int tid = threadIdx.x;
+  __shared__ double part[SB];
+  const int tid = threadIdx.x, r = tid & 127, h = tid >> 7;
   const int i = b + 1 + blockIdx.x;
-  double xi = x[(int64_t)i * SB + tid];
+  double xi = x[(int64_t)i * SB + r];
   if (b >= 0) {
-    v[tid] = x[(int64_t)b * SB + tid];
+    if (h == 0) v[r] = x[(int64_t)b * SB + r];
     __syncthreads();
-    xi -= rowblock_mv(L + (int64_t)i * SB + (int64_t)b * SB * ldl, ldl, v, tid);
+    xi -= rowblock_mv(L + (int64_t)i * SB + (int64_t)b * SB * ldl, ldl, v, part);
   }
   if (i == b + 1) {
     __syncthreads();
-    v[tid] = xi;
+    if (h == 0) v[r] = xi;
     __syncthreads();
-    xi = rowblock_mv(inv + (int64_t)i * SB * SB, SB, v, tid);  // inverse block is lower triangular with explicit zeros
+    xi = rowblock_mv(inv + (int64_t)i * SB * SB, SB, v, part);  // lower triangular with explicit zeros
   }
-  x[(int64_t)i * SB + tid] = xi;
+  if (h == 0) x[(int64_t)i * SB + r] = xi;
 }
 
 // Backward step b: column blocks j < b subtract L(b,j)^T x_b; the CTA of block b-1 then applies
 // inv(L_{b-1,b-1})^T.  b == nblk: only x_{nblk-1} = inv^T z_{nblk-1}.
-__global__ void __launch_bounds__(SB) trsv_bwd_step_kernel(const double *L, int64_t ldl, const double *inv, double *x,
+__global__ void __launch_bounds__(ST) trsv_bwd_step_kernel(const double *L, int64_t ldl, const double *inv, double *x,
                                                            int b, int nblk) {
   __shared__ double v[SB];
   __shared__ double w[SB];
   const int tid = threadIdx.x;
   const int j = (b == nblk) ? nblk - 1 : (int)blockIdx.x;
-  w[tid] = x[(int64_t)j * SB + tid];
+  if (tid < SB) w[tid] = x[(int64_t)j * SB + tid];
   if (b < nblk) {
-    v[tid] = x[(int64_t)b * SB + tid];
+    if (tid < SB) v[tid] = x[(int64_t)b * SB + tid];
     __syncthreads();
     colblock_dot(L + (int64_t)b * SB + (int64_t)j * SB * ldl, ldl, v, [&](int c, double s) { w[c] -= s; });
   }
   __syncthreads();
   if (j == b - 1) {
-    v[tid] = w[tid];
+    if (tid < SB) v[tid] = w[tid];
     __syncthreads();
     colblock_dot(inv + (int64_t)j * SB * SB, SB, v, [&](int c, double s) { w[c] = s; });
     __syncthreads();
   }
-  x[(int64_t)j * SB + tid] = w[tid];
+  if (tid < SB) x[(int64_t)j * SB + tid] = w[tid];
 }
 
 __device__ __forceinline__ double block_reduce_1024(double s, double *sh) {
@@ -153,8 +183,8 @@ int32_t trsv_lower_fwd(Ctx *ctx, cudaStream_t st, const double *L, int64_t ldl, 
                        double *x) {
   const int nblk = (int)(n / SB);
   if (nblk == 0) return DGP_OK;
-  trsv_fwd_step_kernel<<<1, SB, 0, st>>>(L, ldl, inv, x, -1);
-  for (int b = 0; b + 1 < nblk; ++b) trsv_fwd_step_kernel<<<nblk - 1 - b, SB, 0, st>>>(L, ldl, inv, x, b);
+  trsv_fwd_step_kernel<<<1, ST, 0, st>>>(L, ldl, inv, x, -1);
+  for (int b = 0; b + 1 < nblk; ++b) trsv_fwd_step_kernel<<<nblk - 1 - b, ST, 0, st>>>(L, ldl, inv, x, b);
   ctx->launches += nblk;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
@@ -164,8 +194,8 @@ int32_t trsv_lower_bwd(Ctx *ctx, cudaStream_t st, const double *L, int64_t ldl, 
                        double *x) {
   const int nblk = (int)(n / SB);
   if (nblk == 0) return DGP_OK;
-  trsv_bwd_step_kernel<<<1, SB, 0, st>>>(L, ldl, inv, x, nblk, nblk);
-  for (int b = nblk - 1; b >= 1; --b) trsv_bwd_step_kernel<<<b, SB, 0, st>>>(L, ldl, inv, x, b, nblk);
+  trsv_bwd_step_kernel<<<1, ST, 0, st>>>(L, ldl, inv, x, nblk, nblk);
+  for (int b = nblk - 1; b >= 1; --b) trsv_bwd_step_kernel<<<b, ST, 0, st>>>(L, ldl, inv, x, b, nblk);
   ctx->launches += nblk;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;

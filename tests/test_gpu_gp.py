@@ -255,11 +255,23 @@ def test_energy_batch_equals_serial_and_grid_search_matches_oracle():
 
 
 def test_batch_survives_a_non_pd_candidate():
-    X = np.array([[0.0], [0.0], [1.0], [2.0], [3.0]])
-    model = dg.GPRegression(dg.RBFKernel(1.0), dg.DiracKernel(0.5), list(zip(X, [1.0, 2.0, 3.0, 4.0, 5.0])))
-    e = model.energyBatch([{"bandwidth": 1.0, "noiseLevel": 0.5}, {"bandwidth": 1.0, "noiseLevel": 0.0},
+    X, y, _ = orc.synthetic(200, 2, seed=4)
+    model = dg.GPRegression(dg.RBFKernel(1.0), dg.DiracKernel(0.5), list(zip(X, y)))
+    # a NaN hyper-parameter makes every pivot NaN: Breeze throws, the reference returns +Inf (:531-533)
+    e = model.energyBatch([{"bandwidth": 1.0, "noiseLevel": 0.5}, {"bandwidth": float("nan"), "noiseLevel": 0.5},
                            {"bandwidth": 2.0, "noiseLevel": 0.5}])
     assert math.isfinite(e[0]) and e[1] == float("inf") and math.isfinite(e[2])
+    ok = orc.Kernel("rbf", {"bandwidth": 2.0})
+    assert e[2] == pytest.approx(orc.energy(ok, 0.5, X, y), rel=TOL)
+
+
+def test_duplicate_points_with_dirac_noise_are_singular_like_the_reference():
+    # the Dirac term is added to the off-diagonal entry of a duplicated pair too, so K is singular
+    X = np.array([[0.0], [0.0], [1.0], [2.0], [3.0]])
+    y = [1.0, 2.0, 3.0, 4.0, 5.0]
+    model = dg.GPRegression(dg.RBFKernel(1.0), dg.DiracKernel(0.5), list(zip(X, y)))
+    assert model.energy(model._current_state) == float("inf")
+    assert orc.energy(orc.Kernel("rbf", {"bandwidth": 1.0}), 0.5, X, np.array(y)) == float("inf")
 
 
 def test_csa_and_ml2_improve_the_energy():
