@@ -253,7 +253,9 @@ def main():
         # ---- roofline of the dominant kernel, measured live ----------------------------------------
         peaks = ctx.measure_peaks()
         nb = 256
+        ctx.set_option("nb", nb)
         gemm_ms = ctx.time_phase(data, spec, 2, reps=5)
+        ctx.set_option("nb", 0)
         mt = (n - nb) // 128
         flops = 2.0 * nb * 128 * 128 * (mt * (mt + 1) // 2)
         achieved = flops / (gemm_ms * 1e-3) / 1e12

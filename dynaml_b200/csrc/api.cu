@@ -300,7 +300,7 @@ const char *dgp_last_error(const dgp_ctx *ctx) { return ctx ? ctx->err.c_str() :
 int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
   if (!ctx || !key) return DGP_ERR_ARG;
   if (!strcmp(key, "nb")) {
-    if (value < TILE || value % TILE) return ctx->fail(DGP_ERR_ARG, "nb must be a positive multiple of 128");
+    if (value < 0 || value % TILE) return ctx->fail(DGP_ERR_ARG, "nb must be 0 (auto) or a positive multiple of 128");
     ctx->nb = value;
   } else if (!strcmp(key, "lookahead")) {
     ctx->lookahead = value != 0;
@@ -749,7 +749,8 @@ int32_t dgp_time_phase(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *s
       DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_b, S));
     } else if (phase == 2) {
       // the dominant kernel in isolation: one full-size trailing update C -= P P^T with K = nb
-      const int64_t w = ctx->nb < np ? ctx->nb : np;
+      const int64_t nbw = ctx->nb > 0 ? ctx->nb : 256;
+      const int64_t w = nbw < np ? nbw : np;
       if (r == 0) DGP_TRY(assemble(ctx, S, cp, a));
       GemmArgs g;
       g.A = K + w;  g.lda = np;  g.B = K + w;  g.ldb = np;

@@ -35,7 +35,7 @@ struct Ctx {
   cudaEvent_t tev[16];               // phase timing events
   std::string err;
   std::map<std::string, std::pair<void *, size_t>> arena;
-  int64_t nb = 256;   // outer Cholesky block
+  int64_t nb = 0;     // outer Cholesky block (0 = choose from n)
   int lookahead = 1;
   int timing = 1;     // record per-phase events
   double timings[16];

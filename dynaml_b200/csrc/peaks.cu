@@ -42,6 +42,33 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, double seed
   if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// DMMA and DFMA interleaved: do the FP64 tensor pipe and the FP64 FMA pipe add up (separate
+// units) or share the same throughput?
+__global__ void __launch_bounds__(256) mixed_peak_kernel(double *out, double seed) {
+  double c[8][2], f[8];
+  double a = seed + threadIdx.x * 1e-9, b = 1.0 - seed;
+  double fa = 1.0 + seed * 1e-9, fb = seed * 1e-12;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    c[i][0] = c[i][1] = 0.0;
+    f[i] = threadIdx.x + i;
+  }
+  for (int it = 0; it < PK_ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(c[i][0]), "+d"(c[i][1])
+                   : "d"(a), "d"(b));
+      f[i] = fma(f[i], fa, fb);
+      f[(i + 4) & 7] = fma(f[(i + 4) & 7], fa, fb);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + f[i];
+  if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(256) hbm_write_kernel(double2 *dst, int64_t n2, double v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -88,7 +115,7 @@ int32_t best_ms(Ctx *ctx, int reps, F launch, double *best) {
 
 int32_t measure_peaks(Ctx *ctx, double *out, int n) {
   cudaStream_t S = ctx->stream;
-  double res[6] = {0, 0, 0, 0, 0, 0};
+  double res[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const size_t bytes = (size_t)4 << 30;  // 4 GiB per buffer: far beyond the 126 MB L2
   double *a = (double *)ctx->buf("pk_a", bytes);
   double *b = (double *)ctx->buf("pk_b", bytes);
@@ -108,6 +135,10 @@ int32_t measure_peaks(Ctx *ctx, double *out, int n) {
   res[3] = 2.0 * (double)bytes / (ms * 1e-3) / 1e9;
   DGP_TRY(best_ms(ctx, 5, [&] { hbm_read_kernel<<<ctx->sm_count * 16, 256, 0, S>>>((const double2 *)a, n2, b); }, &ms));
   res[4] = (double)bytes / (ms * 1e-3) / 1e9;
+  // mixed: per warp and iteration 8 DMMA (512 flop each) + 16 DFMA warp instructions (64 flop each)
+  DGP_TRY(best_ms(ctx, 5, [&] { mixed_peak_kernel<<<ctas, 256, 0, S>>>(a, 0.5); }, &ms));
+  res[6] = (double)ctas * 8 * 8.0 * PK_ITERS * 512.0 / (ms * 1e-3) / 1e12;   // DMMA share
+  res[7] = (double)ctas * 8 * 16.0 * PK_ITERS * 64.0 / (ms * 1e-3) / 1e12;   // DFMA share
   {  // sustained DMMA: ~1 s of back-to-back launches under the power cap
     const int launches = 120;
     DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_a, S));
@@ -120,7 +151,7 @@ int32_t measure_peaks(Ctx *ctx, double *out, int n) {
   }
   ctx->release("pk_a");
   ctx->release("pk_b");
-  for (int i = 0; i < n && i < 6; ++i) out[i] = res[i];
+  for (int i = 0; i < n && i < 8; ++i) out[i] = res[i];
   return DGP_OK;
 }
 

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1)
 leaf_potrf_inv_kernel(double *A, int64_t lda, double *Inv, int *info, int pivot_base) {
   __shared__ double colbuf[2][LB];
   __shared__ double rowbuf[2][LB];
+  __shared__ double dinv[LB];  // 1 / L(k,k)
   const int tid = threadIdx.x;
   const int tr = tid & 15, tc = tid >> 4;
 
@@ -58,8 +59,11 @@ leaf_potrf_inv_kernel(double *A, int64_t lda, double *Inv, int *info, int pivot_
         if (tid == 0) atomicCAS(info, 0, pivot_base + j + 1);
         d = 1.0;
       }
-      const double l = sqrt(d);
-      const double li = 1.0 / l;
+      // every thread needs 1/l: rsqrt + one multiply instead of a redundant sqrt and divide on all
+      // 256 threads (the FP64 pipe, not latency, bounds this step); l = d * rsqrt(d) is within 1 ulp
+      const double li = rsqrt(d);
+      const double l = d * li;
+      if (tid == 0) dinv[j] = li;
       double lr[8], lc[8];
 #pragma unroll
       for (int i = jc; i < 8; ++i) {
@@ -105,7 +109,7 @@ leaf_potrf_inv_kernel(double *A, int64_t lda, double *Inv, int *info, int pivot_
         for (int q = 0; q <= kc; ++q) rb[q * 16 + tc] = w[kc][q];
       }
       __syncthreads();
-      const double dk = 1.0 / cb[k];
+      const double dk = dinv[k];
       double wk[8], lik[8];
 #pragma unroll
       for (int q = 0; q <= kc; ++q) {
@@ -214,7 +218,10 @@ int32_t potrf_init(Ctx *ctx) {
 
 int32_t potrf_blocked(Ctx *ctx, double *A, int64_t lda, int64_t n, double *inv, int *info) {
   if (n % LB) return ctx->fail(DGP_ERR_SHAPE, "potrf: n=%lld must be a multiple of 128", (long long)n);
-  const int64_t nb = ctx->nb;
+  // outer block: wider blocks amortise the per-tile prologue/epilogue of the trailing update
+  // (measured on B200, scripts/tune.py: N = 32768 -> 405 / 388 / 384 ms at nb = 256 / 512 / 768),
+  // narrower ones shorten the panel chain that bounds small N
+  const int64_t nb = ctx->nb > 0 ? ctx->nb : (n >= 24576 ? 768 : (n >= 12288 ? 512 : 256));
   cudaStream_t S = ctx->stream;
   const bool la = ctx->lookahead && n > nb;
   cudaStream_t P = la ? ctx->panel : ctx->stream;

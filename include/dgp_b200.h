@@ -89,7 +89,8 @@ int32_t dgp_ctx_create(int32_t device, dgp_ctx **out);
 int32_t dgp_ctx_destroy(dgp_ctx *ctx);
 const char *dgp_last_error(const dgp_ctx *ctx);     /* NUL-terminated, owned by ctx             */
 const char *dgp_version(void);
-/* Tunables: "nb" (outer Cholesky block, multiple of 128, default 256), "lookahead" (0/1).      */
+/* Tunables: "nb" (outer Cholesky block, multiple of 128; 0 = auto, the default), "lookahead"
+   (0/1), "timing" (0/1).                                                                       */
 int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value);
 /* Phase timings (ms, CUDA events) of the last energy/energy_grad/fit/predict call:
    [0] assemble [1] potrf [2] solves+logdet [3] inverse (trtri+lauum) [4] trace pass
@@ -167,7 +168,8 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spe
 /* ---- measurement hooks (bench.py / tests; not part of the drop-in surface) ------------------ */
 /* out[0] DMMA FP64 TFLOP/s, out[1] DFMA FP64 TFLOP/s, out[2] HBM write GB/s, out[3] HBM copy GB/s
    (read+write bytes), out[4] HBM read GB/s, each the best of a few timed launches; out[5] DMMA TFLOP/s
-   sustained over ~1 s of back-to-back launches.              */
+   sustained over ~1 s of back-to-back launches; out[6], out[7] DMMA and DFMA TFLOP/s when interleaved
+   in one kernel (do the two FP64 pipes add up?).              */
 int32_t dgp_measure_peaks(dgp_ctx *ctx, double *out, int32_t n);
 /* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
 int32_t dgp_launch_count(const dgp_ctx *ctx, uint64_t *out);

@@ -7,7 +7,7 @@ import dynaml_b200 as dg
 
 ctx = dg.default_context()
 rng = np.random.default_rng(0)
-n = 8192
+n = 12288
 A = rng.standard_normal((n, 256))
 C0 = np.zeros((n, n))
 for _ in range(3):

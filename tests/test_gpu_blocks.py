@@ -69,12 +69,12 @@ def test_potrf_matches_lapack(ctx, n, lookahead):
     assert np.array_equal(Ainv, Ainv.T)  # mirrored, bitwise symmetric
 
 
-@pytest.mark.parametrize("nb", [128, 256, 512])
+@pytest.mark.parametrize("nb", [128, 256, 512, 768])
 def test_potrf_outer_block_sizes_agree(ctx, nb):
     S = _spd(1536, 9)
     ctx.set_option("nb", nb)
     L, _, _, logdet, _ = ctx.test_potrf(S)
-    ctx.set_option("nb", 256)
+    ctx.set_option("nb", 0)
     Lr = sla.cholesky(S, lower=True)
     assert np.abs(L - Lr).max() <= 1e-12 * np.abs(Lr).max()
 
