@@ -30,7 +30,7 @@ EXPORTS = [
     "dgp_ctx_create", "dgp_ctx_destroy", "dgp_last_error", "dgp_version", "dgp_ctx_set_option",
     "dgp_get_timings", "dgp_data_create", "dgp_data_destroy", "dgp_kernel_matrix", "dgp_energy",
     "dgp_energy_grad", "dgp_energy_batch", "dgp_fit", "dgp_model_destroy", "dgp_model_energy",
-    "dgp_predict", "dgp_dist_unique_id", "dgp_dist_init", "dgp_dist_finalize", "dgp_dist_energy",
+    "dgp_predict", "dgp_dist_unique_id", "dgp_dist_init", "dgp_dist_finalize", "dgp_dist_plan", "dgp_dist_energy",
     "dgp_measure_peaks", "dgp_launch_count", "dgp_time_phase", "dgp_test_gemm", "dgp_test_potrf",
 ]
 
@@ -89,6 +89,7 @@ def load_library() -> C.CDLL:
         "dgp_dist_init": (i32, [vp, vp, i32, i32, i32, i32]),
         "dgp_dist_finalize": (i32, [vp]),
         "dgp_dist_energy": (i32, [vp, vp, sp, i32, _dp, _dp]),
+        "dgp_dist_plan": (i32, [i64, i32, i32, i32, i32, C.POINTER(i64)]),
         "dgp_measure_peaks": (i32, [vp, _dp, i32]),
         "dgp_launch_count": (i32, [vp, C.POINTER(C.c_uint64)]),
         "dgp_time_phase": (i32, [vp, vp, sp, i32, i32, _dp]),
@@ -307,7 +308,10 @@ class Context:
             raise DgpError(st, "ncclGetUniqueId failed")
         return bytes(buf)
 
-    def dist_init(self, uid: bytes, rank: int, world: int, grid_rows: int, grid_cols: int):
+    def dist_init(self, uid: bytes | None, rank: int, world: int, grid_rows: int, grid_cols: int):
+        if uid is None:
+            self.check(self.lib.dgp_dist_init(self.h, None, rank, world, grid_rows, grid_cols))
+            return
         buf = (C.c_char * 128).from_buffer_copy(uid)
         self.check(self.lib.dgp_dist_init(self.h, C.cast(buf, C.c_void_p), rank, world, grid_rows, grid_cols))
 
@@ -322,6 +326,16 @@ class Context:
             return float("inf"), ms.value
         self.check(st)
         return e.value, ms.value
+
+
+def dist_plan(n: int, tile: int, grid_rows: int, grid_cols: int, rank: int) -> dict:
+    """Host-only block-cyclic layout of one rank (works without a GPU)."""
+    out = (C.c_int64 * 5)()
+    st = load_library().dgp_dist_plan(n, tile, grid_rows, grid_cols, rank, out)
+    if st != DGP_OK:
+        raise DgpError(st, "dgp_dist_plan: bad arguments")
+    return {"tiles": out[0], "local_rows": out[1], "local_cols": out[2], "owned_lower_tiles": out[3],
+            "local_bytes": out[4]}
 
 
 _default_ctx: Context | None = None

@@ -136,6 +136,15 @@ int32_t scaled_points(Ctx *ctx, cudaStream_t st, const Spec &sp, const double *X
   return DGP_OK;
 }
 
+}  // namespace
+
+int32_t scaled_points_pub(Ctx *ctx, cudaStream_t st, const Spec &sp, const double *X, int64_t np, int dp, int d,
+                          const char *bufname, const double **out) {
+  return scaled_points(ctx, st, sp, X, np, dp, d, bufname, out);
+}
+
+namespace {
+
 __global__ void pad_identity_kernel(double *A, int64_t ld, int64_t n, int64_t np) {
   // rows/cols >= n of the np x np matrix: identity
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -38,7 +38,13 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(CovParams cp, Assemb
     tj = (int)(tlin / mt);
     ti = (int)(tlin % mt);
   }
-  const int64_t m0 = (int64_t)ti * AT + a.row_off, n0 = (int64_t)tj * AT + a.col_off;
+  int64_t m0 = (int64_t)ti * AT + a.row_off, n0 = (int64_t)tj * AT + a.col_off;
+  const int64_t lm0 = m0, ln0 = n0;  // position inside `out`
+  if (a.bc_T > 0) {
+    m0 = ((int64_t)(lm0 / a.bc_T) * a.bc_Pr + a.bc_pr) * a.bc_T + lm0 % a.bc_T;
+    n0 = ((int64_t)(ln0 / a.bc_T) * a.bc_Pc + a.bc_pc) * a.bc_T + ln0 % a.bc_T;
+    if (n0 > m0 + AT - 1) return;  // above the global diagonal (uniform, before any barrier)
+  }
 
   // column points -> shared (contiguous AT*dp doubles in global memory)
   {
@@ -49,7 +55,7 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(CovParams cp, Assemb
 
   const int64_t r0 = m0 + 2 * tx;
   const bool sym = a.symmetric != 0;
-  double *out = a.out + (r0 - a.row_off) + (n0 - a.col_off) * a.ld;
+  double *out = a.out + (lm0 - a.row_off + 2 * tx) + (ln0 - a.col_off) * a.ld;
 
   if (DP > 0) {
     double x0[DP > 0 ? DP : 1], x1[DP > 0 ? DP : 1];

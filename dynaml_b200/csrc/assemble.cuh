@@ -19,6 +19,10 @@ struct AssembleArgs {
   int64_t ld = 0;
   int symmetric = 0;   // X1 == X2 as point sets: padding becomes the identity, noise applies
   int lower_only = 0;  // only tiles on/below the diagonal (requires rows_p == cols_p, offsets equal)
+  // Optional 2D block-cyclic layout (dist.cu): `out` is a rank's local rows_p x cols_p matrix of
+  // T x T tiles; local tile (li, lj) holds global tile (li*Pr + pr, lj*Pc + pc).  Tiles entirely
+  // above the global diagonal are skipped.
+  int bc_T = 0, bc_Pr = 1, bc_Pc = 1, bc_pr = 0, bc_pc = 0;
 };
 
 int32_t assemble(Ctx *ctx, cudaStream_t st, const CovParams &cp, const AssembleArgs &a);

@@ -103,6 +103,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) dgemm_dmma_kernel(GemmArgs p, con
   const uint32_t tile = tiles[blockIdx.x];
   const int m0 = (int)(tile >> 16) * BM, n0 = (int)(tile & 0xffffu) * BN;
 
+  if (p.bc_T > 0) {
+    const int64_t grow = ((int64_t)(p.bc_row0 + m0 / p.bc_T) * p.bc_Pr + p.bc_pr) * p.bc_T + m0 % p.bc_T;
+    const int64_t gcol = ((int64_t)(p.bc_col0 + n0 / p.bc_T) * p.bc_Pc + p.bc_pc) * p.bc_T + n0 % p.bc_T;
+    if (gcol > grow + BM - 1) return;  // uniform across the CTA, before any barrier
+  }
+
   int k_lo = 0, k_hi = p.K;
   if (p.kmode == K_GE_COL) k_lo = (n0 / BK) * BK;
   else if (p.kmode == K_LT_ROWEND) k_hi = min(p.K, m0 + BM);

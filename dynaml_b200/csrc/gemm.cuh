@@ -33,6 +33,11 @@ struct GemmArgs {
   int reverse = 0;     // launch heavy tiles first when the k-range grows with the tile index
   int batch = 1;
   int64_t strideA = 0, strideB = 0, strideC = 0;
+  // Optional 2D block-cyclic mask (dist.cu): C is this rank's local part of a distributed
+  // lower-triangular update, stored as T x T tiles; local tile (li, lj) is global tile
+  // (li*Pr + pr, lj*Pc + pc).  Output tiles entirely above the *global* diagonal return at once.
+  int bc_T = 0, bc_Pr = 1, bc_Pc = 1, bc_pr = 0, bc_pc = 0;
+  int bc_row0 = 0, bc_col0 = 0;  // local tile index (units of T) of the first row / column of C
 };
 
 // Enqueue on `stream`.  Returns DGP_OK or a CUDA error recorded on ctx.

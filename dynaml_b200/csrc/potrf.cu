@@ -217,17 +217,22 @@ int32_t potrf_init(Ctx *ctx) {
 }
 
 int32_t potrf_blocked(Ctx *ctx, double *A, int64_t lda, int64_t n, double *inv, int *info) {
+  const bool la = ctx->lookahead && n > 256;
+  return potrf_blocked_on(ctx, ctx->stream, la ? ctx->panel : ctx->stream, A, lda, n, inv, info, "potrf_panel");
+}
+
+int32_t potrf_blocked_on(Ctx *ctx, cudaStream_t S, cudaStream_t P, double *A, int64_t lda, int64_t n, double *inv,
+                         int *info, const char *scratch_name) {
   if (n % LB) return ctx->fail(DGP_ERR_SHAPE, "potrf: n=%lld must be a multiple of 128", (long long)n);
   // outer block: wider blocks amortise the per-tile prologue/epilogue of the trailing update
   // (measured on B200, scripts/tune.py: N = 32768 -> 405 / 388 / 384 ms at nb = 256 / 512 / 768),
   // narrower ones shorten the panel chain that bounds small N
   const int64_t nb = ctx->nb > 0 ? ctx->nb : (n >= 24576 ? 768 : (n >= 12288 ? 512 : 256));
-  cudaStream_t S = ctx->stream;
-  const bool la = ctx->lookahead && n > nb;
-  cudaStream_t P = la ? ctx->panel : ctx->stream;
+  const bool la = (P != S) && n > nb;
+  if (!la) P = S;
   size_t ev = 0;
 
-  double *scratch = (double *)ctx->buf("potrf_panel", (size_t)n * LB * sizeof(double));
+  double *scratch = (double *)ctx->buf(scratch_name, (size_t)n * LB * sizeof(double));
   if (!scratch) return DGP_ERR_OOM;
   if (la) {  // the panel stream starts after whatever produced A on the main stream
     cudaEvent_t e = get_event(ctx, ev++);
@@ -282,8 +287,12 @@ int32_t potrf_blocked(Ctx *ctx, double *A, int64_t lda, int64_t n, double *inv, 
 
 int32_t trtri_lower(Ctx *ctx, const double *L, int64_t ldl, const double *inv, int64_t n, double *W, int64_t ldw,
                     double *scratch, int64_t lds) {
+  return trtri_lower_on(ctx, ctx->stream, L, ldl, inv, n, W, ldw, scratch, lds);
+}
+
+int32_t trtri_lower_on(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, const double *inv, int64_t n, double *W,
+                       int64_t ldw, double *scratch, int64_t lds) {
   if (n % LB) return ctx->fail(DGP_ERR_SHAPE, "trtri: n must be a multiple of 128");
-  cudaStream_t S = ctx->stream;
   copy_diag_blocks_kernel<<<(unsigned)(n / LB), 256, 0, S>>>(inv, W, ldw);
   ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());

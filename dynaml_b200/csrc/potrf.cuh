@@ -14,11 +14,16 @@ int32_t potrf_init(Ctx *ctx);
 //          (only the first failure is kept); must be zeroed by the caller.
 // Replaces bcholesky / choleskyPAcc (CORE/algebra/bcholesky.scala:85-148).
 int32_t potrf_blocked(Ctx *ctx, double *A, int64_t lda, int64_t n, double *inv, int *info);
+// Same, on explicit streams: S carries the trailing updates, P the panels (P == S: no look-ahead).
+int32_t potrf_blocked_on(Ctx *ctx, cudaStream_t S, cudaStream_t P, double *A, int64_t lda, int64_t n, double *inv,
+                         int *info, const char *scratch_name);
 
 // W (lower) = L^-1 from L and the diagonal-block inverses; scratch is an n x n buffer (ld = lds)
 // whose lower triangle is clobbered.  Tiles of W strictly above the diagonal are not written.
 int32_t trtri_lower(Ctx *ctx, const double *L, int64_t ldl, const double *inv, int64_t n, double *W, int64_t ldw,
                     double *scratch, int64_t lds);
+int32_t trtri_lower_on(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, const double *inv, int64_t n, double *W,
+                       int64_t ldw, double *scratch, int64_t lds);
 
 // Kinv (lower tiles) = W^T W.
 int32_t lauum_lower(Ctx *ctx, const double *W, int64_t ldw, int64_t n, double *Kinv, int64_t ldk);

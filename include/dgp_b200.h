@@ -159,8 +159,13 @@ int32_t dgp_dist_unique_id(void *id128);
 int32_t dgp_dist_init(dgp_ctx *ctx, const void *id128, int32_t rank, int32_t world,
                       int32_t grid_rows, int32_t grid_cols);
 int32_t dgp_dist_finalize(dgp_ctx *ctx);
+/* Host-only layout query (no GPU needed): out[0] tiles per dimension, out[1] / out[2] local tile rows /
+   columns of `rank`, out[3] lower-triangle tiles it owns, out[4] bytes of its local matrix.           */
+int32_t dgp_dist_plan(int64_t n, int32_t tile, int32_t grid_rows, int32_t grid_cols, int32_t rank, int64_t *out);
 /* X, y, mean are replicated on every rank (N*d doubles); K is never materialised on the host.
-   tile = block-cyclic tile edge (multiple of 128).  Every rank gets the same *e.
+   tile = block-cyclic tile edge (multiple of 256, at most 2048).  With world == 1 and
+   grid_rows*grid_cols > 1 in dgp_dist_init, all ranks of the grid are emulated on this one GPU
+   (same code path, broadcasts become device copies) -- used by the parity tests.  Every rank gets the same *e.
    chol_ms (nullable) receives this rank's device time of the factorisation alone.              */
 int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec,
                         int32_t tile, double *e, double *chol_ms);

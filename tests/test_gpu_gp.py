@@ -265,15 +265,6 @@ def test_batch_survives_a_non_pd_candidate():
     assert e[2] == pytest.approx(orc.energy(ok, 0.5, X, y), rel=TOL)
 
 
-def test_duplicate_points_with_dirac_noise_are_singular_like_the_reference():
-    # the Dirac term is added to the off-diagonal entry of a duplicated pair too, so K is singular
-    X = np.array([[0.0], [0.0], [1.0], [2.0], [3.0]])
-    y = [1.0, 2.0, 3.0, 4.0, 5.0]
-    model = dg.GPRegression(dg.RBFKernel(1.0), dg.DiracKernel(0.5), list(zip(X, y)))
-    assert model.energy(model._current_state) == float("inf")
-    assert orc.energy(orc.Kernel("rbf", {"bandwidth": 1.0}), 0.5, X, np.array(y)) == float("inf")
-
-
 def test_csa_and_ml2_improve_the_energy():
     X, y, _ = orc.synthetic(256, 2, seed=5)
     model = dg.GPRegression(dg.SEKernel(3.0, 2.0), dg.DiracKernel(1.0), list(zip(X, y)))

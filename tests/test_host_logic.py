@@ -197,3 +197,23 @@ def test_candidates_shard_across_two_gloo_ranks():
     assert res[0][1] == serial and res[1][1] == serial
     assert res[0][2] == res[1][2]
     assert res[0][3] == 16 and res[1][3] == 16  # 8 of the 16 candidates, two sweeps
+
+
+# ---- 2D block-cyclic layout of the distributed Cholesky (host-only entry point of the C ABI) ----------
+@pytest.mark.parametrize("n,tile,pr,pc", [(131072, 512, 2, 4), (131072, 512, 1, 1), (10000, 256, 2, 2),
+                                          (3000, 256, 1, 2), (700, 256, 2, 4)])
+def test_block_cyclic_plan_partitions_the_lower_triangle(n, tile, pr, pc):
+    from dynaml_b200 import _capi
+    plans = [_capi.dist_plan(n, tile, pr, pc, r) for r in range(pr * pc)]
+    nt = -(-n // tile)
+    assert all(p["tiles"] == nt for p in plans)
+    # every lower tile has exactly one owner: (I mod Pr, J mod Pc)
+    owned = [0] * (pr * pc)
+    for i in range(nt):
+        for j in range(i + 1):
+            owned[(i % pr) * pc + (j % pc)] += 1
+    assert [p["owned_lower_tiles"] for p in plans] == owned
+    assert sum(owned) == nt * (nt + 1) // 2
+    for r, p in enumerate(plans):
+        assert p["local_rows"] == len(range(r // pc, nt, pr)) and p["local_cols"] == len(range(r % pc, nt, pc))
+        assert p["local_bytes"] == p["local_rows"] * p["local_cols"] * tile * tile * 8
