@@ -31,8 +31,7 @@ void *Ctx::buf(const char *name, size_t bytes) {
   auto it = arena.find(name);
   if (it != arena.end() && it->second.second >= bytes) return it->second.first;
   if (it != arena.end()) {
-    cudaStreamSynchronize(stream);
-    cudaStreamSynchronize(panel);
+    cudaDeviceSynchronize();  // any slot's streams may still be reading the old buffer
     cudaFree(it->second.first);
     arena.erase(it);
   }
@@ -50,15 +49,13 @@ void *Ctx::buf(const char *name, size_t bytes) {
 void Ctx::release(const char *name) {
   auto it = arena.find(name);
   if (it == arena.end()) return;
-  cudaStreamSynchronize(stream);
-  cudaStreamSynchronize(panel);
+  cudaDeviceSynchronize();
   cudaFree(it->second.first);
   arena.erase(it);
 }
 
 void Ctx::release_all() {
-  cudaStreamSynchronize(stream);
-  cudaStreamSynchronize(panel);
+  cudaDeviceSynchronize();
   for (auto &kv : arena) cudaFree(kv.second.first);
   arena.clear();
 }
@@ -153,47 +150,73 @@ __global__ void pad_identity_kernel(double *A, int64_t ld, int64_t n, int64_t np
   if (r >= n || c >= n) A[r + c * ld] = (r == c) ? 1.0 : 0.0;
 }
 
-void tick(Ctx *ctx, int i) {
-  if (ctx->timing) cudaEventRecord(ctx->tev[i], ctx->stream);
+void tick(Ctx *ctx, int slot, int i) {
+  if (ctx->timing && slot == 0) cudaEventRecord(ctx->tev[i], ctx->stream);
 }
 
-// Enqueue one energy (and optionally gradient-moment) evaluation.  Results land in
-// d_scal[0] = r' K^-1 r, d_scal[1] = sum log L_ii, d_scal[2..] = gradient moments; *d_info != 0 on
-// a failed pivot.  Nothing here synchronises with the host.
-int32_t enqueue_eval(Ctx *ctx, const Data *D, const Spec &sp, bool want_grad, double *d_scal, int *d_info,
+// Stream pair of an evaluation slot; slot 0 is the context's own pair.
+int32_t slot_streams(Ctx *ctx, int slot, cudaStream_t *S, cudaStream_t *P) {
+  if (slot == 0) {
+    *S = ctx->stream;
+    *P = ctx->panel;
+    return DGP_OK;
+  }
+  if (!ctx->slot_S[slot]) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    DGP_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->slot_S[slot], cudaStreamNonBlocking, lo));
+    DGP_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->slot_P[slot], cudaStreamNonBlocking, hi));
+    DGP_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->slot_ev[slot], cudaEventDisableTiming));
+  }
+  *S = ctx->slot_S[slot];
+  *P = ctx->slot_P[slot];
+  return DGP_OK;
+}
+
+// Enqueue one energy (and optionally gradient-moment) evaluation on the streams and workspace of
+// `slot`.  Results land in d_scal[0] = r' K^-1 r, d_scal[1] = sum log L_ii, d_scal[2..] = gradient
+// moments; *d_info != 0 on a failed pivot.  Nothing here synchronises with the host.
+int32_t enqueue_eval(Ctx *ctx, int slot, const Data *D, const Spec &sp, bool want_grad, double *d_scal, int *d_info,
                      int *ns_out) {
-  cudaStream_t S = ctx->stream;
+  cudaStream_t S, P;
+  DGP_TRY(slot_streams(ctx, slot, &S, &P));
   const int64_t np = D->Np;
-  DGP_BUF(K, double, ctx, "K", (size_t)np * np * sizeof(double));
-  DGP_BUF(inv, double, ctx, "inv", (size_t)np * TILE * sizeof(double));
-  DGP_BUF(x, double, ctx, "x", (size_t)np * sizeof(double));
+  char nm[6][32];
+  const char *base[6] = {"K", "inv", "x", "Xs", "potrf_panel", "W"};
+  for (int i = 0; i < 6; ++i) {
+    if (slot == 0) snprintf(nm[i], sizeof nm[i], "%s", base[i]);
+    else snprintf(nm[i], sizeof nm[i], "%s#%d", base[i], slot);
+  }
+  DGP_BUF(K, double, ctx, nm[0], (size_t)np * np * sizeof(double));
+  DGP_BUF(inv, double, ctx, nm[1], (size_t)np * TILE * sizeof(double));
+  DGP_BUF(x, double, ctx, nm[2], (size_t)np * sizeof(double));
   const double *Xk = nullptr;
-  DGP_TRY(scaled_points(ctx, S, sp, D->X, np, D->dp, D->d, "Xs", &Xk));
+  DGP_TRY(scaled_points(ctx, S, sp, D->X, np, D->dp, D->d, nm[3], &Xk));
   CovParams cp = make_cov_params(sp, true);
 
-  tick(ctx, 0);
+  tick(ctx, slot, 0);
   AssembleArgs a;
   a.X1 = Xk;  a.X2 = Xk;  a.dp = D->dp;
   a.rows = D->N;  a.cols = D->N;  a.rows_p = np;  a.cols_p = np;
   a.out = K;  a.ld = np;
   a.symmetric = 1;  a.lower_only = 1;
   DGP_TRY(assemble(ctx, S, cp, a));
-  tick(ctx, 1);
+  tick(ctx, slot, 1);
   DGP_CUDA_OK(ctx, cudaMemsetAsync(d_info, 0, sizeof(int), S));
-  DGP_TRY(potrf_blocked(ctx, K, np, np, inv, d_info));
-  tick(ctx, 2);
+  DGP_TRY(potrf_blocked_on(ctx, S, ctx->lookahead ? P : S, K, np, np, inv, d_info, nm[4]));
+  tick(ctx, slot, 2);
   DGP_CUDA_OK(ctx, cudaMemcpyAsync(x, D->r, (size_t)np * sizeof(double), cudaMemcpyDeviceToDevice, S));
   DGP_TRY(trsv_lower_fwd(ctx, S, K, np, inv, np, x));
   DGP_TRY(trsv_lower_bwd(ctx, S, K, np, inv, np, x));
   DGP_TRY(dot(ctx, S, D->r, x, np, d_scal + 0));
   DGP_TRY(diag_log_sum(ctx, S, K, np, np, d_scal + 1));
-  tick(ctx, 3);
+  tick(ctx, slot, 3);
   if (want_grad) {
-    DGP_BUF(W, double, ctx, "W", (size_t)np * np * sizeof(double));
+    DGP_BUF(W, double, ctx, nm[5], (size_t)np * np * sizeof(double));
     DGP_BUF(Kinv, double, ctx, "Kinv", (size_t)np * np * sizeof(double));
-    DGP_TRY(trtri_lower(ctx, K, np, inv, np, W, np, Kinv, np));
-    DGP_TRY(lauum_lower(ctx, W, np, np, Kinv, np));
-    tick(ctx, 4);
+    DGP_TRY(trtri_lower_on(ctx, S, K, np, inv, np, W, np, Kinv, np));
+    DGP_TRY(lauum_lower_on(ctx, S, W, np, np, Kinv, np));
+    tick(ctx, slot, 4);
     const int64_t mt = np / TILE, tiles = mt * (mt + 1) / 2;
     const int nsmax = grad_partials_per_tile(cp, D->dp);
     DGP_BUF(partials, double, ctx, "partials", (size_t)tiles * nsmax * sizeof(double));
@@ -202,7 +225,7 @@ int32_t enqueue_eval(Ctx *ctx, const Data *D, const Spec &sp, bool want_grad, do
     g.n = D->N;  g.np = np;  g.dp = D->dp;
     g.partials = partials;  g.sums = d_scal + 2;
     DGP_TRY(grad_trace(ctx, S, cp, g, ns_out));
-    tick(ctx, 5);
+    tick(ctx, slot, 5);
   }
   return DGP_OK;
 }
@@ -298,6 +321,11 @@ int32_t dgp_ctx_destroy(dgp_ctx *ctx) {
   cudaFree(ctx->d_info);
   cudaFreeHost(ctx->h_info);
   cudaFreeHost(ctx->h_scal);
+  for (int i = 1; i < 4; ++i) {
+    if (ctx->slot_S[i]) cudaStreamDestroy(ctx->slot_S[i]);
+    if (ctx->slot_P[i]) cudaStreamDestroy(ctx->slot_P[i]);
+    if (ctx->slot_ev[i]) cudaEventDestroy(ctx->slot_ev[i]);
+  }
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->panel);
   delete ctx;
@@ -313,6 +341,9 @@ int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
     ctx->nb = value;
   } else if (!strcmp(key, "lookahead")) {
     ctx->lookahead = value != 0;
+  } else if (!strcmp(key, "batch_streams")) {
+    if (value < 1 || value > 4) return ctx->fail(DGP_ERR_ARG, "batch_streams must be in 1..4");
+    ctx->batch_streams = (int)value;
   } else if (!strcmp(key, "timing")) {
     ctx->timing = value != 0;
   } else {
@@ -378,7 +409,7 @@ static int32_t energy_impl(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spe
   DGP_BUF(d_scal, double, ctx, "scal", 4096 * 160 * sizeof(double));
   const bool want_grad = g != nullptr;
   int ns = 0;
-  int32_t st = enqueue_eval(ctx, D, sp, want_grad, d_scal, ctx->d_info, &ns);
+  int32_t st = enqueue_eval(ctx, 0, D, sp, want_grad, d_scal, ctx->d_info, &ns);
   if (st != DGP_OK) {
     cudaStreamSynchronize(ctx->stream);
     return st;
@@ -413,8 +444,12 @@ int32_t dgp_energy_batch(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec 
   if (!ctx || !D || !specs || !e || !status || n < 0) return DGP_ERR_ARG;
   cudaSetDevice(ctx->device);
   DGP_BUF(d_scal, double, ctx, "scal", 4096 * 160 * sizeof(double));
-  // Candidates are enqueued back to back on the same streams in chunks of 4096; the workspace is
-  // reused in stream order, so the GPU never waits for the host between candidates.
+  // Candidates are enqueued back to back in chunks of 4096, round-robin over `batch_streams`
+  // evaluation slots (each with its own stream pair and workspace): the GPU never waits for the
+  // host between candidates, and the panel chain of one candidate overlaps the trailing updates of
+  // another.
+  int nslots = ctx->batch_streams < 1 ? 1 : (ctx->batch_streams > 4 ? 4 : ctx->batch_streams);
+  if (n < nslots) nslots = n > 0 ? n : 1;
   for (int32_t base = 0; base < n; base += 4096) {
     const int32_t cnt = (n - base < 4096) ? n - base : 4096;
     std::vector<int32_t> pre(cnt, DGP_OK);
@@ -422,12 +457,17 @@ int32_t dgp_energy_batch(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec 
       Spec sp;
       int ns = 0;
       int32_t st = parse_spec(ctx, &specs[base + i], D->d, &sp);
-      if (st == DGP_OK) st = enqueue_eval(ctx, D, sp, false, d_scal + (size_t)i * 160, ctx->d_info + i, &ns);
+      if (st == DGP_OK) st = enqueue_eval(ctx, i % nslots, D, sp, false, d_scal + (size_t)i * 160, ctx->d_info + i, &ns);
       pre[i] = st;
       if (st == DGP_ERR_CUDA || st == DGP_ERR_OOM) {
-        cudaStreamSynchronize(ctx->stream);
+        cudaDeviceSynchronize();
         return st;
       }
+    }
+    for (int sl = 1; sl < nslots; ++sl) {  // the read-back on the main stream follows every slot
+      if (!ctx->slot_S[sl]) continue;
+      DGP_CUDA_OK(ctx, cudaEventRecord(ctx->slot_ev[sl], ctx->slot_S[sl]));
+      DGP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->slot_ev[sl], 0));
     }
     DGP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scal, d_scal, (size_t)cnt * 160 * sizeof(double), cudaMemcpyDeviceToHost,
                                      ctx->stream));
@@ -504,25 +544,25 @@ int32_t dgp_fit(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *spec, dg
   }
   CovParams cp = make_cov_params(sp, true);
   DGP_BUF(d_scal, double, ctx, "scal", 4096 * 160 * sizeof(double));
-  tick(ctx, 0);
+  tick(ctx, 0, 0);
   AssembleArgs a;
   a.X1 = m->Xk;  a.X2 = m->Xk;  a.dp = D->dp;
   a.rows = D->N;  a.cols = D->N;  a.rows_p = np;  a.cols_p = np;
   a.out = m->L;  a.ld = np;  a.symmetric = 1;  a.lower_only = 1;
   int32_t st = assemble(ctx, S, cp, a);
   if (st != DGP_OK) return bail(st);
-  tick(ctx, 1);
+  tick(ctx, 0, 1);
   cudaMemsetAsync(ctx->d_info, 0, sizeof(int), S);
   st = potrf_blocked(ctx, m->L, np, np, m->inv, ctx->d_info);
   if (st != DGP_OK) return bail(st);
-  tick(ctx, 2);
+  tick(ctx, 0, 2);
   cudaMemcpyAsync(m->alpha, D->r, (size_t)np * sizeof(double), cudaMemcpyDeviceToDevice, S);
   st = trsv_lower_fwd(ctx, S, m->L, np, m->inv, np, m->alpha);
   if (st == DGP_OK) st = trsv_lower_bwd(ctx, S, m->L, np, m->inv, np, m->alpha);
   if (st == DGP_OK) st = dot(ctx, S, D->r, m->alpha, np, d_scal);
   if (st == DGP_OK) st = diag_log_sum(ctx, S, m->L, np, np, d_scal + 1);
   if (st != DGP_OK) return bail(st);
-  tick(ctx, 3);
+  tick(ctx, 0, 3);
   cudaMemcpyAsync(ctx->h_scal, d_scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, S);
   cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, S);
   cudaError_t ce = cudaStreamSynchronize(S);
@@ -569,7 +609,7 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
 
   // K* = k(X, X*) : no noise (AbstractGPRegressionModel.scala:279-286)
   CovParams cpx = make_cov_params(m->spec, false);
-  tick(ctx, 0);
+  tick(ctx, 0, 0);
   {
     AssembleArgs a;
     a.X1 = m->Xk;  a.X2 = Xtk;  a.dp = dp;
@@ -577,10 +617,10 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
     a.out = Ks;  a.ld = np;
     DGP_TRY(assemble(ctx, S, cpx, a));
   }
-  tick(ctx, 1);
+  tick(ctx, 0, 1);
   // mean = m(X*) + K*' alpha   (:463)
   DGP_TRY(gemv_t(ctx, S, Ks, np, np, mp, m->alpha, dbase, dmean));
-  tick(ctx, 2);
+  tick(ctx, 0, 2);
   double *C = nullptr;
   if (need_cov) {
     C = (double *)ctx->buf("pcov", (size_t)mp * mp * sizeof(double));
@@ -610,7 +650,7 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
       u.alpha = -1.0;  u.beta = 1.0;
       DGP_TRY(gemm(ctx, S, u));
     }
-    tick(ctx, 3);
+    tick(ctx, 0, 3);
     GemmArgs s;  // Sigma* = K** - V' V  (lower tiles)   (:452-461)
     s.A = Ks;  s.lda = np;  s.a_kmajor = 1;
     s.B = Ks;  s.ldb = np;  s.b_kmajor = 1;
@@ -619,7 +659,7 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
     s.alpha = -1.0;  s.beta = 1.0;  s.lower_only = 1;
     DGP_TRY(gemm(ctx, S, s));
     DGP_TRY(mirror_lower(ctx, S, C, mp, mp));
-    tick(ctx, 4);
+    tick(ctx, 0, 4);
   }
   DGP_CUDA_OK(ctx, cudaMemcpyAsync(mean, dmean, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, S));
   if (cov)
@@ -698,9 +738,9 @@ int32_t dgp_kernel_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec, const doubl
   a.rows = N1;  a.cols = N2;  a.rows_p = n1p;  a.cols_p = n2p;
   a.out = Kd;  a.ld = n1p;
   a.symmetric = sym ? 1 : 0;
-  tick(ctx, 0);
+  tick(ctx, 0, 0);
   DGP_TRY(assemble(ctx, S, cp, a));
-  tick(ctx, 1);
+  tick(ctx, 0, 1);
   DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(out, ld * sizeof(double), Kd, n1p * sizeof(double), N1 * sizeof(double), N2,
                                      cudaMemcpyDeviceToHost, S));
   DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));

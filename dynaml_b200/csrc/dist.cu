@@ -587,13 +587,13 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
   if (chol_ms) *chol_ms = ms;
-  if (nranks > 1 && (ctx->h_scal[0] != ctx->h_scal[8] || ctx->h_scal[2] != ctx->h_scal[10]))
-    return ctx->fail(DGP_ERR_NCCL, "emulated grid ranks disagree: logdet %.17g vs %.17g, z'z %.17g vs %.17g",
-                     ctx->h_scal[0], ctx->h_scal[8], ctx->h_scal[2], ctx->h_scal[10]);
-  if (ctx->h_scal[1] != 0.0) {
+  if (ctx->h_scal[1] != 0.0 || (nranks > 1 && ctx->h_scal[9] != 0.0)) {
     *e = INFINITY;
     return ctx->fail(DGP_ERR_NOT_PD, "distributed Cholesky failed: a pivot is not positive");
   }
+  if (nranks > 1 && (ctx->h_scal[0] != ctx->h_scal[8] || ctx->h_scal[2] != ctx->h_scal[10]))
+    return ctx->fail(DGP_ERR_NCCL, "emulated grid ranks disagree: logdet %.17g vs %.17g, z'z %.17g vs %.17g",
+                     ctx->h_scal[0], ctx->h_scal[8], ctx->h_scal[2], ctx->h_scal[10]);
   // AbstractGPRegressionModel.scala:527-529
   *e = 0.5 * (ctx->h_scal[2] + ctx->h_scal[0] + (double)D->N * log(2.0 * M_PI));
   return DGP_OK;

@@ -334,6 +334,10 @@ int32_t trtri_lower_on(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, c
 }
 
 int32_t lauum_lower(Ctx *ctx, const double *W, int64_t ldw, int64_t n, double *Kinv, int64_t ldk) {
+  return lauum_lower_on(ctx, ctx->stream, W, ldw, n, Kinv, ldk);
+}
+
+int32_t lauum_lower_on(Ctx *ctx, cudaStream_t S, const double *W, int64_t ldw, int64_t n, double *Kinv, int64_t ldk) {
   GemmArgs g;  // Kinv(i,j) = sum_{k >= i} W(k,i) W(k,j),  i >= j
   g.A = W;  g.lda = ldw;  g.a_kmajor = 1;
   g.B = W;  g.ldb = ldw;  g.b_kmajor = 1;
@@ -342,7 +346,7 @@ int32_t lauum_lower(Ctx *ctx, const double *W, int64_t ldw, int64_t n, double *K
   g.alpha = 1.0;  g.beta = 0.0;
   g.lower_only = 1;
   g.kmode = K_GE_ROW;
-  return gemm(ctx, ctx->stream, g);
+  return gemm(ctx, S, g);
 }
 
 }  // namespace dgp

@@ -27,5 +27,6 @@ int32_t trtri_lower_on(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, c
 
 // Kinv (lower tiles) = W^T W.
 int32_t lauum_lower(Ctx *ctx, const double *W, int64_t ldw, int64_t n, double *Kinv, int64_t ldk);
+int32_t lauum_lower_on(Ctx *ctx, cudaStream_t S, const double *W, int64_t ldw, int64_t n, double *Kinv, int64_t ldk);
 
 }  // namespace dgp
