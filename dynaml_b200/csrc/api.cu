@@ -632,24 +632,7 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
     a.out = C;  a.ld = mp;  a.symmetric = 1;  a.lower_only = 1;
     DGP_TRY(assemble(ctx, S, cpx, a));
     // V = L^-1 K*  (blocked forward substitution on tensor cores, in place in Ks)
-    const int64_t nblk = np / TILE;
-    for (int64_t b = 0; b < nblk; ++b) {
-      GemmArgs d;  // V_b = inv(L_bb) * B_b, in place: a CTA reads exactly the tile it writes
-      d.A = m->inv + b * TILE * TILE;  d.lda = TILE;  d.a_kmajor = 0;
-      d.B = Ks + b * TILE;  d.ldb = np;  d.b_kmajor = 1;
-      d.C = Ks + b * TILE;  d.ldc = np;
-      d.M = TILE;  d.N = (int)mp;  d.K = TILE;
-      DGP_TRY(gemm(ctx, S, d));
-      const int64_t rb = (b + 1) * TILE;
-      if (rb >= np) break;
-      GemmArgs u;  // B[rb:] -= L[rb:, b] * V_b
-      u.A = m->L + rb + b * TILE * np;  u.lda = np;  u.a_kmajor = 0;
-      u.B = Ks + b * TILE;  u.ldb = np;  u.b_kmajor = 1;
-      u.C = Ks + rb;  u.ldc = np;
-      u.M = (int)(np - rb);  u.N = (int)mp;  u.K = TILE;
-      u.alpha = -1.0;  u.beta = 1.0;
-      DGP_TRY(gemm(ctx, S, u));
-    }
+    DGP_TRY(trsm_lower_fwd(ctx, S, m->L, np, m->inv, np, Ks, np, mp, np >= 4096 ? 512 : 256));
     tick(ctx, 0, 3);
     GemmArgs s;  // Sigma* = K** - V' V  (lower tiles)   (:452-461)
     s.A = Ks;  s.lda = np;  s.a_kmajor = 1;

@@ -37,7 +37,7 @@ struct Ctx {
   std::map<std::string, std::pair<void *, size_t>> arena;
   int64_t nb = 0;     // outer Cholesky block (0 = choose from n)
   int lookahead = 1;
-  int batch_streams = 2;  // dgp_energy_batch evaluates this many candidates concurrently (1..4)
+  int batch_streams = 3;  // dgp_energy_batch evaluates this many candidates concurrently (1..4)
   cudaStream_t slot_S[4] = {nullptr, nullptr, nullptr, nullptr};  // extra (main, panel) stream pairs, created lazily
   cudaStream_t slot_P[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t slot_ev[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -333,6 +333,40 @@ int32_t trtri_lower_on(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, c
   return DGP_OK;
 }
 
+int32_t trsm_lower_fwd(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, const double *inv, int64_t n,
+                       double *B, int64_t ldb, int64_t m, int64_t nb) {
+  if (n % LB || nb % LB || m % 64) return ctx->fail(DGP_ERR_SHAPE, "trsm: n, nb must be multiples of 128, m of 64");
+  for (int64_t c0 = 0; c0 < n; c0 += nb) {
+    const int64_t c1 = (c0 + nb < n) ? c0 + nb : n;
+    for (int64_t cs = c0; cs < c1; cs += LB) {
+      GemmArgs d;  // V_cs = inv(L_cs,cs) * B_cs, in place: a CTA reads exactly the 128 x 64 tile it writes
+      d.A = inv + (cs / LB) * LB * LB;  d.lda = LB;  d.a_kmajor = 0;
+      d.B = B + cs;  d.ldb = ldb;  d.b_kmajor = 1;
+      d.C = B + cs;  d.ldc = ldb;
+      d.M = LB;  d.N = (int)m;  d.K = LB;
+      DGP_TRY(gemm(ctx, S, d));
+      const int64_t rb = cs + LB;
+      if (rb >= c1) break;
+      GemmArgs u;  // rows of the same block: B[rb:c1] -= L[rb:c1, cs] * V_cs
+      u.A = L + rb + cs * ldl;  u.lda = ldl;  u.a_kmajor = 0;
+      u.B = B + cs;  u.ldb = ldb;  u.b_kmajor = 1;
+      u.C = B + rb;  u.ldc = ldb;
+      u.M = (int)(c1 - rb);  u.N = (int)m;  u.K = LB;
+      u.alpha = -1.0;  u.beta = 1.0;
+      DGP_TRY(gemm(ctx, S, u));
+    }
+    if (c1 >= n) break;
+    GemmArgs t;  // everything below the block: B[c1:] -= L[c1:, c0:c1] * V[c0:c1]
+    t.A = L + c1 + c0 * ldl;  t.lda = ldl;  t.a_kmajor = 0;
+    t.B = B + c0;  t.ldb = ldb;  t.b_kmajor = 1;
+    t.C = B + c1;  t.ldc = ldb;
+    t.M = (int)(n - c1);  t.N = (int)m;  t.K = (int)(c1 - c0);
+    t.alpha = -1.0;  t.beta = 1.0;
+    DGP_TRY(gemm(ctx, S, t));
+  }
+  return DGP_OK;
+}
+
 int32_t lauum_lower(Ctx *ctx, const double *W, int64_t ldw, int64_t n, double *Kinv, int64_t ldk) {
   return lauum_lower_on(ctx, ctx->stream, W, ldw, n, Kinv, ldk);
 }

@@ -25,6 +25,12 @@ int32_t trtri_lower(Ctx *ctx, const double *L, int64_t ldl, const double *inv, i
 int32_t trtri_lower_on(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, const double *inv, int64_t n, double *W,
                        int64_t ldw, double *scratch, int64_t lds);
 
+// B (n x m, m % 64 == 0) <- L^-1 B in place: blocked forward substitution on tensor cores using the
+// diagonal-block inverses; rank-128 updates inside blocks of `nb` rows, one rank-nb update below.
+// recLTriagMultiSolve, CORE/algebra/PartitionedMatrixSolvers.scala:120-169.
+int32_t trsm_lower_fwd(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, const double *inv, int64_t n,
+                       double *B, int64_t ldb, int64_t m, int64_t nb);
+
 // Kinv (lower tiles) = W^T W.
 int32_t lauum_lower(Ctx *ctx, const double *W, int64_t ldw, int64_t n, double *Kinv, int64_t ldk);
 int32_t lauum_lower_on(Ctx *ctx, cudaStream_t S, const double *W, int64_t ldw, int64_t n, double *Kinv, int64_t ldk);
