@@ -16,11 +16,11 @@ from oracle import gp_oracle as orc
 GRIDS = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=65536)
-ap.add_argument("--d", type=int, default=8)
-ap.add_argument("--tile", type=int, default=512)
-ap.add_argument("--check", type=int, default=3000, help="size of the oracle parity check run first (0 = skip)")
-ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--gp-n", dest="n", type=int, default=65536)
+ap.add_argument("--gp-d", dest="d", type=int, default=8)
+ap.add_argument("--gp-tile", dest="tile", type=int, default=512)
+ap.add_argument("--gp-check", dest="check", type=int, default=3000, help="size of the oracle parity check run first (0 = skip)")
+ap.add_argument("--gp-reps", dest="reps", type=int, default=2)
 args = ap.parse_args()
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
