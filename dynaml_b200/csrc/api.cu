@@ -93,16 +93,55 @@ int32_t parse_spec(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
 
 namespace {
 
-// Repack host points (either layout) into row-major n_p x dp with zero padding.
-void pack_points(const double *X, int64_t n, int d, int layout, int64_t np, int dp, std::vector<double> &out) {
+// Repack host points (either layout) into row-major n_p x dp with zero padding, subtracting
+// `center` (d values, nullable).  Returns the largest squared norm of the packed points.
+double pack_points(const double *X, int64_t n, int d, int layout, int64_t np, int dp, std::vector<double> &out,
+                   const double *center = nullptr) {
   out.assign((size_t)np * dp, 0.0);
   if (layout == DGP_ROW_MAJOR) {
     for (int64_t i = 0; i < n; ++i)
-      for (int c = 0; c < d; ++c) out[(size_t)i * dp + c] = X[(size_t)i * d + c];
+      for (int c = 0; c < d; ++c) out[(size_t)i * dp + c] = X[(size_t)i * d + c] - (center ? center[c] : 0.0);
   } else {
     for (int c = 0; c < d; ++c)
-      for (int64_t i = 0; i < n; ++i) out[(size_t)i * dp + c] = X[(size_t)c * n + i];
+      for (int64_t i = 0; i < n; ++i) out[(size_t)i * dp + c] = X[(size_t)c * n + i] - (center ? center[c] : 0.0);
   }
+  double mx = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (int c = 0; c < d; ++c) s += out[(size_t)i * dp + c] * out[(size_t)i * dp + c];
+    if (s > mx || s != s) mx = s;
+  }
+  return mx;
+}
+
+void column_means(const double *X, int64_t n, int d, int layout, std::vector<double> &mean) {
+  mean.assign(d, 0.0);
+  for (int64_t i = 0; i < n; ++i)
+    for (int c = 0; c < d; ++c) mean[c] += (layout == DGP_ROW_MAJOR) ? X[(size_t)i * d + c] : X[(size_t)c * n + i];
+  for (int c = 0; c < d; ++c) {
+    mean[c] /= (double)n;
+    if (!std::isfinite(mean[c])) mean[c] = 0.0;
+  }
+}
+
+// Whether the Gram/DMMA assembly may be used for points whose largest squared norm is max_sq_norm
+// (for ARD-SE the kernel sees the inputs scaled by 1/b_c: bound the scaled norm).
+int pick_gram(const Ctx *ctx, const Spec &sp, const CovParams &cp, int dp, int d, double max_sq_norm) {
+  if (ctx->assembly == 1) return 0;
+  if (cp.kind != DGP_KERNEL_SE && cp.kind != DGP_KERNEL_RBF && cp.kind != DGP_KERNEL_ARD_SE &&
+      cp.kind != DGP_KERNEL_MATERN)
+    return 0;
+  if (dp > 32) return 0;
+  if (ctx->assembly == 2) return 1;
+  double scale = 1.0;
+  if (sp.kind == DGP_KERNEL_ARD_SE) {
+    scale = 0.0;
+    for (int c = 0; c < d; ++c) {
+      const double ib2 = 1.0 / (sp.hyp[1 + c] * sp.hyp[1 + c]);
+      if (ib2 > scale || ib2 != ib2) scale = ib2;
+    }
+  }
+  return gram_is_accurate(cp, dp, max_sq_norm * scale) ? 1 : 0;
 }
 
 struct ScaleVec {
@@ -134,6 +173,10 @@ int32_t scaled_points(Ctx *ctx, cudaStream_t st, const Spec &sp, const double *X
 }
 
 }  // namespace
+
+int pick_gram_pub(const Ctx *ctx, const Spec &sp, const CovParams &cp, int dp, int d, double max_sq_norm) {
+  return pick_gram(ctx, sp, cp, dp, d, max_sq_norm);
+}
 
 int32_t scaled_points_pub(Ctx *ctx, cudaStream_t st, const Spec &sp, const double *X, int64_t np, int dp, int d,
                           const char *bufname, const double **out) {
@@ -200,6 +243,7 @@ int32_t enqueue_eval(Ctx *ctx, int slot, const Data *D, const Spec &sp, bool wan
   a.rows = D->N;  a.cols = D->N;  a.rows_p = np;  a.cols_p = np;
   a.out = K;  a.ld = np;
   a.symmetric = 1;  a.lower_only = 1;
+  a.use_gram = pick_gram(ctx, sp, cp, D->dp, D->d, D->max_sq_norm);
   DGP_TRY(assemble(ctx, S, cp, a));
   tick(ctx, slot, 1);
   DGP_CUDA_OK(ctx, cudaMemsetAsync(d_info, 0, sizeof(int), S));
@@ -264,6 +308,8 @@ struct Model {
   double *inv = nullptr;  // Np x 128
   double *alpha = nullptr;
   double energy = 0.0;
+  std::vector<double> center;  // the training set's column means (test points are shifted alike)
+  double max_sq_norm = 0.0;
 };
 
 }  // namespace dgp
@@ -341,6 +387,9 @@ int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
     ctx->nb = value;
   } else if (!strcmp(key, "lookahead")) {
     ctx->lookahead = value != 0;
+  } else if (!strcmp(key, "assembly")) {
+    if (value < 0 || value > 2) return ctx->fail(DGP_ERR_ARG, "assembly must be 0 (auto), 1 (exact differences) or 2 (Gram)");
+    ctx->assembly = (int)value;
   } else if (!strcmp(key, "batch_streams")) {
     if (value < 1 || value > 4) return ctx->fail(DGP_ERR_ARG, "batch_streams must be in 1..4");
     ctx->batch_streams = (int)value;
@@ -370,7 +419,8 @@ int32_t dgp_data_create(dgp_ctx *ctx, const double *X, int64_t N, int32_t d, int
   D->d = d;
   D->dp = (int)round_up(d, 4);
   std::vector<double> hx, hr((size_t)D->Np, 0.0);
-  pack_points(X, N, d, x_layout, D->Np, D->dp, hx);
+  column_means(X, N, d, x_layout, D->center);
+  D->max_sq_norm = pack_points(X, N, d, x_layout, D->Np, D->dp, hx, D->center.data());
   for (int64_t i = 0; i < N; ++i) hr[i] = y[i] - (mean ? mean[i] : 0.0);
   cudaError_t e1 = cudaMalloc(&D->X, hx.size() * sizeof(double));
   cudaError_t e2 = cudaMalloc(&D->r, hr.size() * sizeof(double));
@@ -518,6 +568,7 @@ int32_t dgp_fit(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *spec, dg
   dgp_model *m = new dgp_model();
   m->spec = sp;
   m->N = D->N;  m->Np = np;  m->d = D->d;  m->dp = D->dp;
+  m->center = D->center;  m->max_sq_norm = D->max_sq_norm;
   bool ok = cudaMalloc(&m->X, (size_t)np * D->dp * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&m->L, (size_t)np * np * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&m->inv, (size_t)np * TILE * sizeof(double)) == cudaSuccess &&
@@ -549,6 +600,7 @@ int32_t dgp_fit(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *spec, dg
   a.X1 = m->Xk;  a.X2 = m->Xk;  a.dp = D->dp;
   a.rows = D->N;  a.cols = D->N;  a.rows_p = np;  a.cols_p = np;
   a.out = m->L;  a.ld = np;  a.symmetric = 1;  a.lower_only = 1;
+  a.use_gram = pick_gram(ctx, sp, cp, D->dp, D->d, D->max_sq_norm);
   int32_t st = assemble(ctx, S, cp, a);
   if (st != DGP_OK) return bail(st);
   tick(ctx, 0, 1);
@@ -594,7 +646,8 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
   const bool need_cov = cov != nullptr || lo != nullptr;
 
   std::vector<double> hx;
-  pack_points(Xs, M, m->d, x_layout, mp, dp, hx);
+  double nmax = pack_points(Xs, M, m->d, x_layout, mp, dp, hx, m->center.data());
+  if (m->max_sq_norm > nmax) nmax = m->max_sq_norm;
   DGP_BUF(Xt, double, ctx, "Xt", (size_t)mp * dp * sizeof(double));
   DGP_BUF(Ks, double, ctx, "Ks", (size_t)np * mp * sizeof(double));
   DGP_BUF(dmean, double, ctx, "pmean", (size_t)mp * 3 * sizeof(double));
@@ -609,12 +662,14 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
 
   // K* = k(X, X*) : no noise (AbstractGPRegressionModel.scala:279-286)
   CovParams cpx = make_cov_params(m->spec, false);
+  const int gram = pick_gram(ctx, m->spec, cpx, dp, m->d, nmax);
   tick(ctx, 0, 0);
   {
     AssembleArgs a;
     a.X1 = m->Xk;  a.X2 = Xtk;  a.dp = dp;
     a.rows = m->N;  a.cols = M;  a.rows_p = np;  a.cols_p = mp;
     a.out = Ks;  a.ld = np;
+    a.use_gram = gram;
     DGP_TRY(assemble(ctx, S, cpx, a));
   }
   tick(ctx, 0, 1);
@@ -630,6 +685,7 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
     a.X1 = Xtk;  a.X2 = Xtk;  a.dp = dp;
     a.rows = M;  a.cols = M;  a.rows_p = mp;  a.cols_p = mp;
     a.out = C;  a.ld = mp;  a.symmetric = 1;  a.lower_only = 1;
+    a.use_gram = gram;
     DGP_TRY(assemble(ctx, S, cpx, a));
     // V = L^-1 K*  (blocked forward substitution on tensor cores, in place in Ks)
     DGP_TRY(trsm_lower_fwd(ctx, S, m->L, np, m->inv, np, Ks, np, mp, np >= 4096 ? 512 : 256));
@@ -699,13 +755,15 @@ int32_t dgp_kernel_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec, const doubl
   cudaStream_t S = ctx->stream;
   const int64_t n1p = round_up(N1, TILE), n2p = round_up(N2, TILE);
   const int dp = (int)round_up(d, 4);
-  std::vector<double> h1, h2;
-  pack_points(X1, N1, d, x_layout, n1p, dp, h1);
+  std::vector<double> h1, h2, ctr;
+  column_means(X1, N1, d, x_layout, ctr);
+  double nmax = pack_points(X1, N1, d, x_layout, n1p, dp, h1, ctr.data());
   DGP_BUF(A1, double, ctx, "km_x1", h1.size() * sizeof(double));
   DGP_CUDA_OK(ctx, cudaMemcpyAsync(A1, h1.data(), h1.size() * sizeof(double), cudaMemcpyHostToDevice, S));
   double *A2 = A1;
   if (!sym) {
-    pack_points(X2, N2, d, x_layout, n2p, dp, h2);
+    const double n2max = pack_points(X2, N2, d, x_layout, n2p, dp, h2, ctr.data());
+    if (n2max > nmax || n2max != n2max) nmax = n2max;
     A2 = (double *)ctx->buf("km_x2", h2.size() * sizeof(double));
     if (!A2) return DGP_ERR_OOM;
     DGP_CUDA_OK(ctx, cudaMemcpyAsync(A2, h2.data(), h2.size() * sizeof(double), cudaMemcpyHostToDevice, S));
@@ -721,6 +779,7 @@ int32_t dgp_kernel_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec, const doubl
   a.rows = N1;  a.cols = N2;  a.rows_p = n1p;  a.cols_p = n2p;
   a.out = Kd;  a.ld = n1p;
   a.symmetric = sym ? 1 : 0;
+  a.use_gram = pick_gram(ctx, sp, cp, dp, d, nmax);
   tick(ctx, 0, 0);
   DGP_TRY(assemble(ctx, S, cp, a));
   tick(ctx, 0, 1);
@@ -766,6 +825,7 @@ int32_t dgp_time_phase(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *s
   a.X1 = Xk;  a.X2 = Xk;  a.dp = D->dp;
   a.rows = D->N;  a.cols = D->N;  a.rows_p = np;  a.cols_p = np;
   a.out = K;  a.ld = np;  a.symmetric = 1;  a.lower_only = 1;
+  a.use_gram = pick_gram(ctx, sp, cp, D->dp, D->d, D->max_sq_norm);
   double total = 0.0;
   for (int r = 0; r < reps; ++r) {
     float ms = 0.f;

@@ -10,6 +10,8 @@
 // (DiracKernel.scala:43-47).  Every store is a 16-byte vector store and a warp writes 512
 // contiguous bytes of one column; the kernel is bound by HBM write bandwidth or by the FP64
 // pipe (exp/sqrt/sin), whichever ncu shows.
+#include <cmath>
+
 #include "assemble.cuh"
 
 namespace dgp {
@@ -134,6 +136,240 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(CovParams cp, Assemb
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2: Gram formulation on the FP64 tensor path with a lean epilogue.
+//
+// |x-y|^2 = |x|^2 + |y|^2 - 2 x.y comes out of DMMA directly by augmenting the contraction:
+//   column point j (MMA row)   : [ -2 y_1 .. -2 y_d , 1     , |y|^2 , 0 , 0 ]
+//   row point i    (MMA column): [    x_1 ..    x_d , |x|^2 , 1     , 0 , 0 ]
+// so one 8x8x4 DMMA per 4 features replaces 64 subtract + 64 FMA instructions.  ncu of v1
+// (profiles/ncu_assemble_v1_r1.txt) shows the kernel issue-bound (~176 thread instructions per
+// Matern entry, FP64 pipe 43 % busy), so the epilogue is also rebuilt from FP64 FMAs only:
+// exp() by Cody-Waite reduction + degree-13 Horner + exponent insertion, sqrt() from the FP32
+// reciprocal-square-root seed + two Goldschmidt steps + one correction.  The MMA M index is the
+// matrix column and the N index the matrix row, so each thread's accumulator pair is two adjacent
+// rows: 16-byte stores.
+// Cancellation: the Gram distance carries an absolute error ~ KA*eps*(|x|^2+|y|^2); pairs closer
+// than 1e-4 of that scale (the diagonal, duplicates, near-duplicates) are recomputed from exact
+// differences, which also keeps DiracKernel's |x-y| == 0 test exact.  The host only selects this
+// path when the resulting relative error bound on a kernel entry is below 2e-13 (assemble()).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_exp_nonpos(double x) {
+  if (x < -700.0) return exp(x);  // subnormal / zero results: rare, take the library path
+  const double L2E = 1.4426950408889634074, SHIFT = 6755399441055744.0;
+  const double LN2HI = 6.93147180369123816490e-01, LN2LO = 1.90821492927058770002e-10;
+  const double t = fma(x, L2E, SHIFT);
+  const int n = __double2loint(t);
+  const double nd = t - SHIFT;
+  double r = fma(nd, -LN2HI, x);
+  r = fma(nd, -LN2LO, r);
+  double p = 1.6059043836821613e-10;           // 1/13!
+  p = fma(p, r, 2.08767569878681e-09);         // 1/12!
+  p = fma(p, r, 2.505210838544172e-08);        // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);        // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);       // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);         // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);        // 1/7!
+  p = fma(p, r, 1.3888888888888889e-03);       // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);        // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);       // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);       // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return p * __hiloint2double((n + 1023) << 20, 0);
+}
+
+__device__ __forceinline__ double fast_sqrt_pos(double a) {
+  // a is a moderate positive number here (>= the fix-up threshold); guard the FP32 seed's range
+  if (!(a > 1e-30 && a < 1e30)) return sqrt(a);
+  const double y = (double)rsqrtf((float)a);
+  double g = a * y, h = 0.5 * y;
+  double e = fma(-g, h, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  e = fma(-g, h, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  const double d = fma(-g, g, a);
+  return fma(d, h, g);
+}
+
+template <int KIND>
+__device__ __forceinline__ double cov_value_fast(const CovParams &cp, double r2) {
+  if (KIND == DGP_KERNEL_MATERN) {
+    const double r = fast_sqrt_pos(r2);
+    const double u = cp.c2 * r;
+    double sum = cp.coef[0];
+    for (int i = 1; i <= cp.p; ++i) sum = fma(sum, u, cp.coef[i]);
+    return fast_exp_nonpos(-cp.c1 * r) * sum;
+  } else {
+    return cp.a2 * fast_exp_nonpos(-r2 * cp.c1);
+  }
+}
+
+__host__ __device__ constexpr int gram_ldk(int dp) { return (dp + 4 <= 20) ? 20 : 36; }  // row stride = 4 mod 16 doubles
+
+template <int KIND, int DP>
+__global__ void __launch_bounds__(ATHREADS, 2) assemble_gram_kernel(CovParams cp, AssembleArgs a) {
+  constexpr int KA = DP + 4, LDK = gram_ldk(DP);
+  extern __shared__ __align__(16) double sm[];
+  double *Brow = sm;                 // row points i (MMA N):    [i][k], x | |x|^2 | 1 | 0 0
+  double *Acol = sm + AT * LDK;      // column points j (MMA M): [j][k], -2y | 1 | |y|^2 | 0 0
+  __shared__ double red[ATHREADS / 32];
+  __shared__ double s_thr;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;  // per 64-column half: 2 column blocks of 32 x 4 row blocks of 32
+
+  int64_t tlin = blockIdx.x;
+  int ti, tj;
+  if (a.lower_only) {
+    ti = (int)((sqrt(8.0 * (double)tlin + 1.0) - 1.0) * 0.5);
+    while ((int64_t)ti * (ti + 1) / 2 > tlin) --ti;
+    while ((int64_t)(ti + 1) * (ti + 2) / 2 <= tlin) ++ti;
+    tj = (int)(tlin - (int64_t)ti * (ti + 1) / 2);
+  } else {
+    int mt = (int)(a.rows_p / AT);
+    tj = (int)(tlin / mt);
+    ti = (int)(tlin % mt);
+  }
+  int64_t m0 = (int64_t)ti * AT + a.row_off, n0 = (int64_t)tj * AT + a.col_off;
+  const int64_t lm0 = m0, ln0 = n0;
+  if (a.bc_T > 0) {
+    m0 = ((int64_t)(lm0 / a.bc_T) * a.bc_Pr + a.bc_pr) * a.bc_T + lm0 % a.bc_T;
+    n0 = ((int64_t)(ln0 / a.bc_T) * a.bc_Pc + a.bc_pc) * a.bc_T + ln0 % a.bc_T;
+    if (n0 > m0 + AT - 1) return;
+  }
+
+  // ---- augmented operands: thread p < 128 builds row point p, thread p >= 128 column point p-128 ----
+  double nrm;
+  {
+    const bool is_row = tid < AT;
+    const int pidx = is_row ? tid : tid - AT;
+    const double *src = is_row ? (a.X1 + (m0 + pidx) * DP) : (a.X2 + (n0 + pidx) * DP);
+    double *dst = (is_row ? Brow : Acol) + pidx * LDK;
+    double v[DP];
+    nrm = 0.0;
+#pragma unroll
+    for (int c = 0; c < DP / 2; ++c) {
+      const double2 q = reinterpret_cast<const double2 *>(src)[c];
+      v[2 * c] = q.x;
+      v[2 * c + 1] = q.y;
+    }
+#pragma unroll
+    for (int c = 0; c < DP; ++c) nrm = fma(v[c], v[c], nrm);
+#pragma unroll
+    for (int c = 0; c < DP; ++c) dst[c] = is_row ? v[c] : -2.0 * v[c];
+    dst[DP] = is_row ? nrm : 1.0;
+    dst[DP + 1] = is_row ? 1.0 : nrm;
+    dst[DP + 2] = 0.0;
+    dst[DP + 3] = 0.0;
+  }
+  // fix-up threshold from the largest squared norm in the tile
+  {
+    double mx = nrm;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+      double m2 = red[0];
+      for (int w = 1; w < ATHREADS / 32; ++w) m2 = fmax(m2, red[w]);
+      s_thr = 2.0e-4 * m2;  // 1e-4 * (|x|^2 + |y|^2) at most
+    }
+    __syncthreads();
+  }
+  const double thr = s_thr;
+
+  // ---- two column halves of 64; per half every warp owns 32 columns x 32 rows = 4 x 4 accumulator pairs ----
+  const bool sym = a.symmetric != 0;
+  const bool edge = (m0 + AT > a.rows) || (n0 + AT > a.cols);
+  double *out = a.out + (lm0 - a.row_off) + (ln0 - a.col_off) * a.ld;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    double acc[4][4][2];
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+    const int jbase = half * 64 + wm * 32, ibase = wn * 32;
+    const double *ap = Acol + (jbase + g) * LDK + t;
+    const double *bp = Brow + (ibase + g) * LDK + t;
+#pragma unroll
+    for (int kk = 0; kk < KA / 4; ++kk) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int mb = 0; mb < 4; ++mb) af[mb] = ap[mb * 8 * LDK + kk * 4];
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) bf[nb] = bp[nb * 8 * LDK + kk * 4];
+#pragma unroll
+      for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                       : "+d"(acc[mb][nb][0]), "+d"(acc[mb][nb][1])
+                       : "d"(af[mb]), "d"(bf[nb]));
+    }
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+      const int jl = jbase + mb * 8 + g;
+      const int64_t col = n0 + jl;
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) {
+        const int il = ibase + nb * 8 + 2 * t;
+        double kv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double r2 = acc[mb][nb][e];
+          double k;
+          if (r2 < thr) {  // cancellation-prone: exact differences (also gives an exact 0 for equal points)
+            const double *xr = Brow + (il + e) * LDK, *yc = Acol + jl * LDK;
+            double d = 0.0;
+            for (int c = 0; c < DP; ++c) {
+              const double df = fma(0.5, yc[c], xr[c]);  // x - y (the column operand stores -2y)
+              d = fma(df, df, d);
+            }
+            k = cov_value<KIND>(cp, d);
+            if (d == 0.0) k += cp.noise_abs;
+          } else {
+            k = cov_value_fast<KIND>(cp, r2);
+          }
+          if (edge) {
+            const int64_t row = m0 + il + e;
+            if (row >= a.rows || col >= a.cols) k = (sym && row == col) ? 1.0 : 0.0;
+          }
+          kv[e] = k;
+        }
+        *reinterpret_cast<double2 *>(out + il + (int64_t)jl * a.ld) = make_double2(kv[0], kv[1]);
+      }
+    }
+  }
+}
+
+template <int KIND, int DP>
+void launch_gram(cudaStream_t st, const CovParams &cp, const AssembleArgs &a, unsigned tiles) {
+  size_t smem = (size_t)2 * AT * gram_ldk(DP) * sizeof(double);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(assemble_gram_kernel<KIND, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  assemble_gram_kernel<KIND, DP><<<tiles, ATHREADS, smem, st>>>(cp, a);
+}
+
+template <int KIND>
+bool launch_gram_kind(cudaStream_t st, const CovParams &cp, const AssembleArgs &a, unsigned tiles) {
+  switch (a.dp) {
+    case 4: launch_gram<KIND, 4>(st, cp, a, tiles); return true;
+    case 8: launch_gram<KIND, 8>(st, cp, a, tiles); return true;
+    case 12: launch_gram<KIND, 12>(st, cp, a, tiles); return true;
+    case 16: launch_gram<KIND, 16>(st, cp, a, tiles); return true;
+    case 20: launch_gram<KIND, 20>(st, cp, a, tiles); return true;
+    case 24: launch_gram<KIND, 24>(st, cp, a, tiles); return true;
+    case 32: launch_gram<KIND, 32>(st, cp, a, tiles); return true;
+    default: return false;
+  }
+}
+
 template <int KIND, int DP>
 void launch_one(cudaStream_t st, const CovParams &cp, const AssembleArgs &a, unsigned tiles) {
   size_t smem = (size_t)AT * a.dp * sizeof(double);
@@ -172,7 +408,14 @@ int32_t assemble(Ctx *ctx, cudaStream_t st, const CovParams &cp, const AssembleA
   if (a.lower_only && mt != nt) return ctx->fail(DGP_ERR_SHAPE, "assemble: lower_only needs a square matrix");
   int64_t tiles = a.lower_only ? mt * (mt + 1) / 2 : mt * nt;
   if (tiles == 0) return DGP_OK;
-  switch (cp.kind) {
+  bool done = false;
+  if (a.use_gram) {
+    if (cp.kind == DGP_KERNEL_SE || cp.kind == DGP_KERNEL_RBF || cp.kind == DGP_KERNEL_ARD_SE)
+      done = launch_gram_kind<DGP_KERNEL_SE>(st, cp, a, (unsigned)tiles);
+    else if (cp.kind == DGP_KERNEL_MATERN)
+      done = launch_gram_kind<DGP_KERNEL_MATERN>(st, cp, a, (unsigned)tiles);
+  }
+  if (!done) switch (cp.kind) {
     case DGP_KERNEL_SE:
     case DGP_KERNEL_RBF:
     case DGP_KERNEL_ARD_SE: launch_kind<DGP_KERNEL_SE>(st, cp, a, (unsigned)tiles); break;
@@ -193,6 +436,28 @@ int32_t scale_points(Ctx *ctx, cudaStream_t st, const double *X, double *Xs, con
   scale_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, Xs, d_inv_b, n, dp);
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
+}
+
+}  // namespace dgp
+
+namespace dgp {
+
+bool gram_is_accurate(const CovParams &cp, int dp, double max_sq_norm) {
+  if (dp > 32 || !(max_sq_norm >= 0.0) || !std::isfinite(max_sq_norm)) return false;
+  double slope;  // max |d log k / d r^2|
+  switch (cp.kind) {
+    case DGP_KERNEL_SE:
+    case DGP_KERNEL_RBF:
+    case DGP_KERNEL_ARD_SE: slope = cp.c1; break;
+    case DGP_KERNEL_MATERN:
+      if (cp.p < 1) return false;        // exp(-r/l) is not smooth in r^2 at 0
+      slope = 0.5 * cp.c1 * cp.c1;       // <= nu / l^2, attained at r -> 0 for p = 1
+      break;
+    default: return false;
+  }
+  if (!std::isfinite(slope)) return false;
+  const double bound = slope * (dp + 4) * 1.2e-16 * 2.0 * max_sq_norm;
+  return bound <= 2e-13;
 }
 
 }  // namespace dgp

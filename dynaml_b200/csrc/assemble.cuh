@@ -23,7 +23,14 @@ struct AssembleArgs {
   // T x T tiles; local tile (li, lj) holds global tile (li*Pr + pr, lj*Pc + pc).  Tiles entirely
   // above the global diagonal are skipped.
   int bc_T = 0, bc_Pr = 1, bc_Pc = 1, bc_pr = 0, bc_pc = 0;
+  // 1: Gram/DMMA distance kernel (SE, RBF, ARD-SE, Matern with dp <= 32); the caller sets it only when
+  // gram_is_accurate() holds.  0: exact-difference kernel.
+  int use_gram = 0;
 };
+
+// Relative error bound of a kernel entry under the Gram formulation: |d log k / d r^2| * KA * eps * 2*max|x|^2.
+// True when it stays below 2e-13 (the parity tolerance on entries is 1e-12).
+bool gram_is_accurate(const CovParams &cp, int dp, double max_sq_norm);
 
 int32_t assemble(Ctx *ctx, cudaStream_t st, const CovParams &cp, const AssembleArgs &a);
 // Xs[i][c] = X[i][c] * inv_b[c]  (ARD-SE: MahalanobisKernel.scala:122-132 folded into the inputs)

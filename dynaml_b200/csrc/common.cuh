@@ -37,6 +37,7 @@ struct Ctx {
   std::map<std::string, std::pair<void *, size_t>> arena;
   int64_t nb = 0;     // outer Cholesky block (0 = choose from n)
   int lookahead = 1;
+  int assembly = 0;   // 0: Gram/DMMA assembly when its error bound allows, 1: always exact differences, 2: force Gram
   int batch_streams = 3;  // dgp_energy_batch evaluates this many candidates concurrently (1..4)
   cudaStream_t slot_S[4] = {nullptr, nullptr, nullptr, nullptr};  // extra (main, panel) stream pairs, created lazily
   cudaStream_t slot_P[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -78,6 +79,10 @@ struct Data {
   int dp = 0;       // padded to a multiple of 4 (zero columns; exact for every distance used here)
   double *X = nullptr;  // Np x dp, row-major (point i at X + i*dp), pad rows zero
   double *r = nullptr;  // y - m(X), length Np, pad entries zero
+  // The stored points are centred (column means subtracted): every kernel on this path is
+  // translation invariant, and small norms keep the Gram-form distances accurate.
+  std::vector<double> center;  // d column means of the original inputs
+  double max_sq_norm = 0.0;    // max_i |x_i - center|^2
 };
 
 // Host copy of a kernel spec with derived constants.

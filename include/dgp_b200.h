@@ -90,7 +90,8 @@ int32_t dgp_ctx_destroy(dgp_ctx *ctx);
 const char *dgp_last_error(const dgp_ctx *ctx);     /* NUL-terminated, owned by ctx             */
 const char *dgp_version(void);
 /* Tunables: "nb" (outer Cholesky block, multiple of 128; 0 = auto, the default), "lookahead"
-   (0/1), "timing" (0/1), "batch_streams" (1..4 candidates of dgp_energy_batch in flight; default 3). */
+   (0/1), "timing" (0/1), "batch_streams" (1..4 candidates of dgp_energy_batch in flight; default 3),
+   "assembly" (0 = Gram/DMMA kernel when its error bound allows, 1 = exact differences, 2 = force Gram). */
 int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value);
 /* Phase timings (ms, CUDA events) of the last energy/energy_grad/fit/predict call:
    [0] assemble [1] potrf [2] solves+logdet [3] inverse (trtri+lauum) [4] trace pass

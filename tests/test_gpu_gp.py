@@ -306,3 +306,66 @@ def test_c2_size_energy_properties(ctx):
         assert ge[0] == pytest.approx(gr[0], rel=1e-12) and ge[-1] == pytest.approx(gr[-1], rel=1e-12)
     finally:
         ctx.data_destroy(data)
+
+
+# ---- the Gram/DMMA assembly kernel (assembly = 2) against the exact-difference one and the oracle ------------
+@pytest.fixture()
+def gram_ctx(ctx):
+    ctx.set_option("assembly", 2)
+    yield ctx
+    ctx.set_option("assembly", 0)
+
+
+@pytest.mark.parametrize("name", ["se", "rbf", "ard_ref", "matern1", "matern2", "matern3"])
+def test_gram_assembly_entries(gram_ctx, name):
+    z = np.load(GOLD / "synthetic.npz")
+    X, Xs = z["X"], z["Xs"]
+    k, ok = make_pair(name, X.shape[1], z["band"])
+    K = k.buildKernelMatrix(X, len(X)).getKernelMatrix()
+    assert entry_rel(K, orc.build_kernel_matrix(ok, X)) <= TOL_K
+    C = k.buildCrossKernelMatrix(X, Xs)
+    assert entry_rel(C, orc.cross_kernel_matrix(ok, X, Xs)) <= TOL_K
+
+
+@pytest.mark.parametrize("d", [1, 3, 8, 13, 16, 24, 32])
+def test_gram_assembly_feature_counts_offsets_and_duplicates(gram_ctx, d):
+    """Uncentred inputs (offset 50), duplicated points (exact zero distance -> Dirac term), ragged N."""
+    X, _, _ = orc.synthetic(333, d, seed=100 + d)
+    X = X + 50.0
+    X[17] = X[5]
+    X[200] = X[5]
+    k = dg.GenericMaternKernel(1.0 + 0.2 * d, 2)
+    ok = orc.Kernel("matern", {"p": 2.0, "l": 1.0 + 0.2 * d})
+    K = (k + dg.DiracKernel(0.25)).buildKernelMatrix(X, len(X)).getKernelMatrix()
+    Ko = orc.build_kernel_matrix(ok, X, orc.dirac(0.25))
+    assert entry_rel(K, Ko) <= TOL_K
+    assert K[17, 5] == 1.25 and K[200, 17] == 1.25 and K[3, 3] == 1.25
+
+
+def test_gram_and_direct_energies_agree(ctx):
+    X, y, _ = orc.synthetic(1500, 16, seed=77)
+    spec = dg.GenericMaternKernel(4.0, 2)._spec(noise=0.1)
+    data = ctx.data_create(X, y)
+    try:
+        vals = {}
+        for mode in (1, 2, 0):
+            ctx.set_option("assembly", mode)
+            vals[mode] = ctx.energy_grad(data, spec)
+        ctx.set_option("assembly", 0)
+        assert vals[1][0] == pytest.approx(vals[2][0], rel=1e-12)
+        assert np.allclose(vals[1][1][1:], vals[2][1][1:], rtol=1e-10)
+        assert vals[0][0] == vals[2][0]  # auto picks the Gram kernel for well-scaled data
+    finally:
+        ctx.set_option("assembly", 0)
+        ctx.data_destroy(data)
+
+
+def test_auto_assembly_falls_back_to_exact_differences_for_tiny_length_scales(ctx):
+    """l = 0.01 with |x|^2 ~ 8: the Gram error bound exceeds 2e-13, auto must use exact differences."""
+    X, _, _ = orc.synthetic(300, 8, seed=5)
+    k, ok = dg.SEKernel(0.01, 1.0), orc.Kernel("se", {"bandwidth": 0.01, "amplitude": 1.0})
+    X[1] = X[0] + 1e-3  # one pair close enough for a non-negligible entry
+    K = k.buildKernelMatrix(X, len(X)).getKernelMatrix()
+    Ko = orc.build_kernel_matrix(ok, X)
+    big = Ko > 1e-200
+    assert entry_rel(K[big], Ko[big]) <= TOL_K
