@@ -779,9 +779,11 @@ int32_t dgp_kernel_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec, const doubl
   a.rows = N1;  a.cols = N2;  a.rows_p = n1p;  a.cols_p = n2p;
   a.out = Kd;  a.ld = n1p;
   a.symmetric = sym ? 1 : 0;
+  a.lower_only = sym ? 1 : 0;  // SVMKernel.scala:77-86 evaluates i >= j and mirrors: bitwise symmetric
   a.use_gram = pick_gram(ctx, sp, cp, dp, d, nmax);
   tick(ctx, 0, 0);
   DGP_TRY(assemble(ctx, S, cp, a));
+  if (sym) DGP_TRY(mirror_lower(ctx, S, Kd, n1p, n1p));
   tick(ctx, 0, 1);
   DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(out, ld * sizeof(double), Kd, n1p * sizeof(double), N1 * sizeof(double), N2,
                                      cudaMemcpyDeviceToHost, S));

@@ -195,17 +195,38 @@ __device__ __forceinline__ double fast_sqrt_pos(double a) {
   return fma(d, h, g);
 }
 
+// Hot-path covariance from scalars held in registers (no access to the by-value CovParams, which
+// the compiler would otherwise spill to local memory).  Matern: orders p <= 3, coefficients
+// right-aligned in m0..m3 (leading ones zero for smaller p).
+struct FastCov {
+  double a2, c1, c2, m0, m1, m2, m3;
+};
+
 template <int KIND>
-__device__ __forceinline__ double cov_value_fast(const CovParams &cp, double r2) {
+__device__ __forceinline__ double cov_value_fast(const FastCov &f, double r2) {
   if (KIND == DGP_KERNEL_MATERN) {
     const double r = fast_sqrt_pos(r2);
-    const double u = cp.c2 * r;
-    double sum = cp.coef[0];
-    for (int i = 1; i <= cp.p; ++i) sum = fma(sum, u, cp.coef[i]);
-    return fast_exp_nonpos(-cp.c1 * r) * sum;
+    const double u = f.c2 * r;
+    double sum = fma(f.m0, u, f.m1);
+    sum = fma(sum, u, f.m2);
+    sum = fma(sum, u, f.m3);
+    return fast_exp_nonpos(-f.c1 * r) * sum;
   } else {
-    return cp.a2 * fast_exp_nonpos(-r2 * cp.c1);
+    return f.a2 * fast_exp_nonpos(-r2 * f.c1);
   }
+}
+
+// Cold path: exact differences from the shared-memory operands (the column operand stores -2y).
+template <int KIND>
+__device__ __noinline__ double exact_entry(const CovParams *cp, const double *xr, const double *yc, int dp) {
+  double d = 0.0;
+  for (int c = 0; c < dp; ++c) {
+    const double df = fma(0.5, yc[c], xr[c]);
+    d = fma(df, df, d);
+  }
+  double k = cov_value<KIND>(*cp, d);
+  if (d == 0.0) k += cp->noise_abs;
+  return k;
 }
 
 __host__ __device__ constexpr int gram_ldk(int dp) { return (dp + 4 <= 20) ? 20 : 36; }  // row stride = 4 mod 16 doubles
@@ -282,6 +303,15 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_gram_kernel(CovParams cp
     __syncthreads();
   }
   const double thr = s_thr;
+  FastCov fc;
+  fc.a2 = cp.a2;  fc.c1 = cp.c1;  fc.c2 = cp.c2;
+  {
+    const int p = cp.p;  // launch side guarantees p <= 3 for this kernel
+    fc.m0 = (p == 3) ? cp.coef[0] : 0.0;
+    fc.m1 = (p == 3) ? cp.coef[1] : (p == 2 ? cp.coef[0] : 0.0);
+    fc.m2 = (p == 3) ? cp.coef[2] : (p == 2 ? cp.coef[1] : (p == 1 ? cp.coef[0] : 0.0));
+    fc.m3 = (p == 3) ? cp.coef[3] : (p == 2 ? cp.coef[2] : (p == 1 ? cp.coef[1] : cp.coef[0]));
+  }
 
   // ---- two column halves of 64; per half every warp owns 32 columns x 32 rows = 4 x 4 accumulator pairs ----
   const bool sym = a.symmetric != 0;
@@ -324,17 +354,10 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_gram_kernel(CovParams cp
         for (int e = 0; e < 2; ++e) {
           const double r2 = acc[mb][nb][e];
           double k;
-          if (r2 < thr) {  // cancellation-prone: exact differences (also gives an exact 0 for equal points)
-            const double *xr = Brow + (il + e) * LDK, *yc = Acol + jl * LDK;
-            double d = 0.0;
-            for (int c = 0; c < DP; ++c) {
-              const double df = fma(0.5, yc[c], xr[c]);  // x - y (the column operand stores -2y)
-              d = fma(df, df, d);
-            }
-            k = cov_value<KIND>(cp, d);
-            if (d == 0.0) k += cp.noise_abs;
+          if (r2 < thr) {  // cancellation-prone (diagonal, duplicates, near-duplicates): exact differences
+            k = exact_entry<KIND>(&cp, Brow + (il + e) * LDK, Acol + jl * LDK, DP);
           } else {
-            k = cov_value_fast<KIND>(cp, r2);
+            k = cov_value_fast<KIND>(fc, r2);
           }
           if (edge) {
             const int64_t row = m0 + il + e;
@@ -412,7 +435,7 @@ int32_t assemble(Ctx *ctx, cudaStream_t st, const CovParams &cp, const AssembleA
   if (a.use_gram) {
     if (cp.kind == DGP_KERNEL_SE || cp.kind == DGP_KERNEL_RBF || cp.kind == DGP_KERNEL_ARD_SE)
       done = launch_gram_kind<DGP_KERNEL_SE>(st, cp, a, (unsigned)tiles);
-    else if (cp.kind == DGP_KERNEL_MATERN)
+    else if (cp.kind == DGP_KERNEL_MATERN && cp.p <= 3)
       done = launch_gram_kind<DGP_KERNEL_MATERN>(st, cp, a, (unsigned)tiles);
   }
   if (!done) switch (cp.kind) {
