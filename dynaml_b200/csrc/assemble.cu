@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_gram_kernel(CovParams cp
     if (tid == 0) {
       double m2 = red[0];
       for (int w = 1; w < ATHREADS / 32; ++w) m2 = fmax(m2, red[w]);
-      s_thr = 2.0e-4 * m2;  // 1e-4 * (|x|^2 + |y|^2) at most
+      s_thr = fmax(2.0e-4 * m2, 1e-300);  // 1e-4 * (|x|^2 + |y|^2) at most; never below an exact zero
     }
     __syncthreads();
   }
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_gram_kernel(CovParams cp
         for (int e = 0; e < 2; ++e) {
           const double r2 = acc[mb][nb][e];
           double k;
-          if (r2 < thr) {  // cancellation-prone (diagonal, duplicates, near-duplicates): exact differences
+          if (!(r2 > thr)) {  // cancellation-prone (diagonal, duplicates, near-duplicates): exact differences
             k = exact_entry<KIND>(&cp, Brow + (il + e) * LDK, Acol + jl * LDK, DP);
           } else {
             k = cov_value_fast<KIND>(fc, r2);
