@@ -154,45 +154,76 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(CovParams cp, Assemb
 // differences, which also keeps DiracKernel's |x-y| == 0 test exact.  The host only selects this
 // path when the resulting relative error bound on a kernel entry is below 2e-13 (assemble()).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double fast_exp_nonpos(double x) {
-  if (x < -700.0) return exp(x);  // subnormal / zero results: rare, take the library path
+// The fast epilogue works on V independent entries at a time, written operation by operation over
+// the V lanes so that the compiler interleaves V dependency chains (the scalar version was bound by
+// FP64 latency: ncu "wait" stalls, 46 % FP64-unit utilisation).
+//
+// exp(x), x <= 0: Cody-Waite reduction x = n ln2 + r, |r| <= 0.347, degree-13 Taylor polynomial in
+// Estrin form (depth 4 instead of 13), exponent insertion.  Results below e^-700 ~ 1e-304 are flushed
+// to zero (the library would return subnormals there).
+template <int V>
+__device__ __forceinline__ void fast_exp_nonpos_v(const double (&x)[V], double (&out)[V]) {
   const double L2E = 1.4426950408889634074, SHIFT = 6755399441055744.0;
   const double LN2HI = 6.93147180369123816490e-01, LN2LO = 1.90821492927058770002e-10;
-  const double t = fma(x, L2E, SHIFT);
-  const int n = __double2loint(t);
-  const double nd = t - SHIFT;
-  double r = fma(nd, -LN2HI, x);
-  r = fma(nd, -LN2LO, r);
-  double p = 1.6059043836821613e-10;           // 1/13!
-  p = fma(p, r, 2.08767569878681e-09);         // 1/12!
-  p = fma(p, r, 2.505210838544172e-08);        // 1/11!
-  p = fma(p, r, 2.755731922398589e-07);        // 1/10!
-  p = fma(p, r, 2.7557319223985893e-06);       // 1/9!
-  p = fma(p, r, 2.48015873015873e-05);         // 1/8!
-  p = fma(p, r, 1.984126984126984e-04);        // 1/7!
-  p = fma(p, r, 1.3888888888888889e-03);       // 1/6!
-  p = fma(p, r, 8.333333333333333e-03);        // 1/5!
-  p = fma(p, r, 4.1666666666666664e-02);       // 1/4!
-  p = fma(p, r, 1.6666666666666666e-01);       // 1/3!
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  return p * __hiloint2double((n + 1023) << 20, 0);
+  double r[V], r2[V], r4[V], r8[V], sc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const double xc = fmax(x[v], -700.0);
+    const double t = fma(xc, L2E, SHIFT);
+    const int n = __double2loint(t);
+    const double nd = t - SHIFT;
+    r[v] = fma(nd, -LN2LO, fma(nd, -LN2HI, xc));
+    sc[v] = __hiloint2double((n + 1023) << 20, 0);
+  }
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    r2[v] = r[v] * r[v];
+    r4[v] = r2[v] * r2[v];
+    r8[v] = r4[v] * r4[v];
+  }
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const double a0 = fma(1.0, r[v], 1.0);                                          // 1/0! + r/1!
+    const double a1 = fma(1.6666666666666666e-01, r[v], 0.5);                       // 1/2! + r/3!
+    const double a2 = fma(8.333333333333333e-03, r[v], 4.1666666666666664e-02);     // 1/4! + r/5!
+    const double a3 = fma(1.984126984126984e-04, r[v], 1.3888888888888889e-03);     // 1/6! + r/7!
+    const double a4 = fma(2.7557319223985893e-06, r[v], 2.48015873015873e-05);      // 1/8! + r/9!
+    const double a5 = fma(2.505210838544172e-08, r[v], 2.755731922398589e-07);      // 1/10! + r/11!
+    const double a6 = fma(1.6059043836821613e-10, r[v], 2.08767569878681e-09);      // 1/12! + r/13!
+    const double b0 = fma(a1, r2[v], a0), b1 = fma(a3, r2[v], a2), b2 = fma(a5, r2[v], a4);
+    const double d0 = fma(b1, r4[v], b0), d1 = fma(a6, r4[v], b2);
+    const double p = fma(d1, r8[v], d0);
+    out[v] = (x[v] < -700.0) ? 0.0 : p * sc[v];
+  }
 }
 
-__device__ __forceinline__ double fast_sqrt_pos(double a) {
-  // a is a moderate positive number here (>= the fix-up threshold); guard the FP32 seed's range
-  if (!(a > 1e-30 && a < 1e30)) return sqrt(a);
-  const double y = (double)rsqrtf((float)a);
-  double g = a * y, h = 0.5 * y;
-  double e = fma(-g, h, 0.5);
-  g = fma(g, e, g);
-  h = fma(h, e, h);
-  e = fma(-g, h, 0.5);
-  g = fma(g, e, g);
-  h = fma(h, e, h);
-  const double d = fma(-g, g, a);
-  return fma(d, h, g);
+__device__ __noinline__ double cold_sqrt(double a) { return sqrt(a); }
+
+// sqrt(a) for moderate positive a: FP32 reciprocal-square-root seed, two Goldschmidt steps, one
+// correction (a handful of FMAs instead of the library's special-case handling).
+template <int V>
+__device__ __forceinline__ void fast_sqrt_pos_v(const double (&a)[V], double (&out)[V]) {
+  double g[V], h[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const double y = (double)rsqrtf((float)a[v]);
+    g[v] = a[v] * y;
+    h[v] = 0.5 * y;
+  }
+#pragma unroll
+  for (int it = 0; it < 2; ++it)
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const double e = fma(-g[v], h[v], 0.5);
+      g[v] = fma(g[v], e, g[v]);
+      h[v] = fma(h[v], e, h[v]);
+    }
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const double d = fma(-g[v], g[v], a[v]);
+    out[v] = fma(d, h[v], g[v]);
+    if (!(a[v] > 1e-30 && a[v] < 1e30)) out[v] = cold_sqrt(a[v]);  // outside the FP32 seed's range
+  }
 }
 
 // Hot-path covariance from scalars held in registers (no access to the by-value CovParams, which
@@ -202,17 +233,29 @@ struct FastCov {
   double a2, c1, c2, m0, m1, m2, m3;
 };
 
-template <int KIND>
-__device__ __forceinline__ double cov_value_fast(const FastCov &f, double r2) {
+template <int KIND, int V>
+__device__ __forceinline__ void cov_value_fast_v(const FastCov &f, const double (&r2)[V], double (&k)[V]) {
+  double arg[V], ex[V];
   if (KIND == DGP_KERNEL_MATERN) {
-    const double r = fast_sqrt_pos(r2);
-    const double u = f.c2 * r;
-    double sum = fma(f.m0, u, f.m1);
-    sum = fma(sum, u, f.m2);
-    sum = fma(sum, u, f.m3);
-    return fast_exp_nonpos(-f.c1 * r) * sum;
+    double r[V], sum[V];
+    fast_sqrt_pos_v<V>(r2, r);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const double u = f.c2 * r[v];
+      double s = fma(f.m0, u, f.m1);
+      s = fma(s, u, f.m2);
+      sum[v] = fma(s, u, f.m3);
+      arg[v] = -f.c1 * r[v];
+    }
+    fast_exp_nonpos_v<V>(arg, ex);
+#pragma unroll
+    for (int v = 0; v < V; ++v) k[v] = ex[v] * sum[v];
   } else {
-    return f.a2 * fast_exp_nonpos(-r2 * f.c1);
+#pragma unroll
+    for (int v = 0; v < V; ++v) arg[v] = -r2[v] * f.c1;
+    fast_exp_nonpos_v<V>(arg, ex);
+#pragma unroll
+    for (int v = 0; v < V; ++v) k[v] = f.a2 * ex[v];
   }
 }
 
@@ -347,25 +390,30 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_gram_kernel(CovParams cp
       const int jl = jbase + mb * 8 + g;
       const int64_t col = n0 + jl;
 #pragma unroll
-      for (int nb = 0; nb < 4; ++nb) {
-        const int il = ibase + nb * 8 + 2 * t;
-        double kv[2];
+      for (int q = 0; q < 2; ++q) {  // two row blocks = four entries at a time
+        double r2[4], kv[4];
+        bool exact[4];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const double r2 = acc[mb][nb][e];
-          double k;
-          if (!(r2 > thr)) {  // cancellation-prone (diagonal, duplicates, near-duplicates): exact differences
-            k = exact_entry<KIND>(&cp, Brow + (il + e) * LDK, Acol + jl * LDK, DP);
-          } else {
-            k = cov_value_fast<KIND>(fc, r2);
-          }
-          if (edge) {
-            const int64_t row = m0 + il + e;
-            if (row >= a.rows || col >= a.cols) k = (sym && row == col) ? 1.0 : 0.0;
-          }
-          kv[e] = k;
+        for (int u = 0; u < 4; ++u) {
+          const double v = acc[mb][2 * q + (u >> 1)][u & 1];
+          exact[u] = !(v > thr);  // cancellation-prone (diagonal, duplicates, near-duplicates)
+          r2[u] = fmax(v, thr);
         }
-        *reinterpret_cast<double2 *>(out + il + (int64_t)jl * a.ld) = make_double2(kv[0], kv[1]);
+        cov_value_fast_v<KIND, 4>(fc, r2, kv);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int il = ibase + (2 * q + (u >> 1)) * 8 + 2 * t + (u & 1);
+          if (exact[u]) kv[u] = exact_entry<KIND>(&cp, Brow + il * LDK, Acol + jl * LDK, DP);
+          if (edge) {
+            const int64_t row = m0 + il;
+            if (row >= a.rows || col >= a.cols) kv[u] = (sym && row == col) ? 1.0 : 0.0;
+          }
+        }
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int il = ibase + (2 * q + h2) * 8 + 2 * t;
+          *reinterpret_cast<double2 *>(out + il + (int64_t)jl * a.ld) = make_double2(kv[2 * h2], kv[2 * h2 + 1]);
+        }
       }
     }
   }

@@ -21,16 +21,13 @@ constexpr size_t LEAF_SMEM = 0;
 // The 256 threads form a 16x16 grid (tr, tc); thread (tr, tc) owns the elements (r, c) with
 // r = 16 i + tr, c = 16 q + tc (2D block-cyclic), i.e. an 8x8 local block of which only the local
 // lower part i >= q is live (36 FP64 values for L, 36 for W = L^-1).  Each elimination step
-// broadcasts one column (and, for the inverse, one row) through a double-buffered 128-entry line
-// in shared memory and costs a single __syncthreads; all register indices are compile-time after
-// unrolling the 16-wide column blocks, so nothing spills.
-//   step j of the factorisation:  l = sqrt(a_jj);  L(:,j) = a(:,j)/l;  a(r,c) -= L(r,j) L(c,j)
-//   step k of the inverse (L W = I, right-looking):  W(k,:) = R(k,:)/L(k,k);  R(i,:) -= L(i,k) W(k,:)
+// broadcasts one column of L and one row of W through double-buffered 128-entry lines in shared
+// memory and costs a single __syncthreads; all register indices are compile-time after unrolling
+// the 16-wide column blocks, so nothing spills.
 __global__ void __launch_bounds__(LEAF_THREADS, 1)
 leaf_potrf_inv_kernel(double *A, int64_t lda, double *Inv, int *info, int pivot_base) {
   __shared__ double colbuf[2][LB];
   __shared__ double rowbuf[2][LB];
-  __shared__ double dinv[LB];  // 1 / L(k,k)
   const int tid = threadIdx.x;
   const int tr = tid & 15, tc = tid >> 4;
 
@@ -43,92 +40,75 @@ leaf_potrf_inv_kernel(double *A, int64_t lda, double *Inv, int *info, int pivot_
       a[i][q] = (i >= q) ? A[(i * 16 + tr) + (int64_t)(q * 16 + tc) * lda] : 0.0;
     }
 
-  // ---- factorisation --------------------------------------------------------------------------
-#pragma unroll
-  for (int jc = 0; jc < 8; ++jc) {
-    for (int jj = 0; jj < 16; ++jj) {
-      const int j = jc * 16 + jj;
-      double *cb = colbuf[j & 1];
-      if (tc == jj) {
-#pragma unroll
-        for (int i = jc; i < 8; ++i) cb[i * 16 + tr] = a[i][jc];
-      }
-      __syncthreads();
-      double d = cb[j];
-      if (!(d > 0.0)) {  // also catches NaN; uniform across the CTA
-        if (tid == 0) atomicCAS(info, 0, pivot_base + j + 1);
-        d = 1.0;
-      }
-      // every thread needs 1/l: rsqrt + one multiply instead of a redundant sqrt and divide on all
-      // 256 threads (the FP64 pipe, not latency, bounds this step); l = d * rsqrt(d) is within 1 ulp
-      const double li = rsqrt(d);
-      const double l = d * li;
-      if (tid == 0) dinv[j] = li;
-      double lr[8], lc[8];
-#pragma unroll
-      for (int i = jc; i < 8; ++i) {
-        lr[i] = cb[i * 16 + tr] * li;
-        lc[i] = cb[i * 16 + tc] * li;
-      }
-      // owners of column j keep the finished column
-      if (tc == jj) {
-#pragma unroll
-        for (int i = jc; i < 8; ++i) {
-          const int r = i * 16 + tr;
-          if (r > j) a[i][jc] = lr[i];
-          else if (r == j) a[i][jc] = l;
-        }
-      }
-      // trailing update on the live local part (rows > j, columns > j)
-#pragma unroll
-      for (int q = jc; q < 8; ++q) {
-        const bool cq = (q > jc) || (tc > jj);
-#pragma unroll
-        for (int i = q; i < 8; ++i) {
-          const bool ri = (i > jc) || (tr > jj);
-          if (cq && ri) a[i][q] = fma(-lr[i], lc[q], a[i][q]);
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- inverse ----------------------------------------------------------------------------------
+  // ---- factorisation and inverse, fused: one elimination step and one __syncthreads per column ----
+  // Step k: column k of the trailing matrix and row k of R = (running) L W - I travel through shared
+  // memory; then  l = sqrt(a_kk), L(:,k) = a(:,k)/l, a(r,c) -= L(r,k) L(c,k)   (Cholesky)
+  // and           W(k,:) = R(k,:)/l,  R(i,:) -= L(i,k) W(k,:) for i > k        (L W = I, right-looking).
 #pragma unroll
   for (int kc = 0; kc < 8; ++kc) {
     for (int kk = 0; kk < 16; ++kk) {
       const int k = kc * 16 + kk;
       double *cb = colbuf[k & 1];
       double *rb = rowbuf[k & 1];
-      if (tc == kk) {  // column k of L, rows >= 16 kc
+      if (tc == kk) {
 #pragma unroll
         for (int i = kc; i < 8; ++i) cb[i * 16 + tr] = a[i][kc];
       }
-      if (tr == kk) {  // row k of R, columns < 16 (kc + 1)
+      if (tr == kk) {
 #pragma unroll
         for (int q = 0; q <= kc; ++q) rb[q * 16 + tc] = w[kc][q];
       }
       __syncthreads();
-      const double dk = dinv[k];
-      double wk[8], lik[8];
+      double d = cb[k];
+      if (!(d > 0.0)) {  // also catches NaN; uniform across the CTA
+        if (tid == 0) atomicCAS(info, 0, pivot_base + k + 1);
+        d = 1.0;
+      }
+      // every thread needs 1/l: rsqrt + one multiply instead of a redundant sqrt and divide on all
+      // 256 threads (the FP64 pipe, not latency, bounds this step); l = d * rsqrt(d) is within 1 ulp
+      const double li = rsqrt(d);
+      const double l = d * li;
+      double lr[8], lc[8], wk[8];
+#pragma unroll
+      for (int i = kc; i < 8; ++i) {
+        lr[i] = cb[i * 16 + tr] * li;  // L(r, k) for this thread's rows
+        lc[i] = cb[i * 16 + tc] * li;  // L(c, k) for this thread's columns
+      }
 #pragma unroll
       for (int q = 0; q <= kc; ++q) {
         const int c = q * 16 + tc;
-        wk[q] = (c == k) ? dk : ((c < k) ? rb[c] * dk : 0.0);
+        wk[q] = (c == k) ? li : ((c < k) ? rb[c] * li : 0.0);  // W(k, c)
       }
+      if (tc == kk) {  // owners of column k keep the finished column of L
 #pragma unroll
-      for (int i = kc; i < 8; ++i) lik[i] = cb[i * 16 + tr];
-      if (tr == kk) {
+        for (int i = kc; i < 8; ++i) {
+          const int r = i * 16 + tr;
+          if (r > k) a[i][kc] = lr[i];
+          else if (r == k) a[i][kc] = l;
+        }
+      }
+      if (tr == kk) {  // owners of row k keep the finished row of W
 #pragma unroll
         for (int q = 0; q <= kc; ++q) w[kc][q] = wk[q];
       }
+      // Cholesky trailing update on the live local part (rows > k, columns > k)
+#pragma unroll
+      for (int q = kc; q < 8; ++q) {
+        const bool cq = (q > kc) || (tc > kk);
+#pragma unroll
+        for (int i = q; i < 8; ++i) {
+          const bool ri = (i > kc) || (tr > kk);
+          if (cq && ri) a[i][q] = fma(-lr[i], lc[q], a[i][q]);
+        }
+      }
+      // inverse update: rows > k, columns <= k (wk is zero beyond column k)
 #pragma unroll
       for (int q = 0; q <= kc; ++q) {
 #pragma unroll
         for (int i = kc; i < 8; ++i) {
           if (i >= q) {
             const bool ri = (i > kc) || (tr > kk);
-            if (ri) w[i][q] = fma(-lik[i], wk[q], w[i][q]);
+            if (ri) w[i][q] = fma(-lr[i], wk[q], w[i][q]);
           }
         }
       }
