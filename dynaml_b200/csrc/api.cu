@@ -133,6 +133,9 @@ int pick_gram(const Ctx *ctx, const Spec &sp, const CovParams &cp, int dp, int d
     return 0;
   if (dp > 32) return 0;
   if (ctx->assembly == 2) return 1;
+  // measured on B200 (profiles/assemble_r1.json): the Gram kernel wins from 16 features up (Matern-5/2 d = 16:
+  // 0.88 vs 1.08 ms at N = 16384); below that the exact-difference kernel is faster (SE d = 8: 0.42 vs 0.57 ms)
+  if (dp < 16) return 0;
   double scale = 1.0;
   if (sp.kind == DGP_KERNEL_ARD_SE) {
     scale = 0.0;
@@ -387,6 +390,9 @@ int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
     ctx->nb = value;
   } else if (!strcmp(key, "lookahead")) {
     ctx->lookahead = value != 0;
+  } else if (!strcmp(key, "gemm_bk")) {
+    if (value != 16 && value != 32) return ctx->fail(DGP_ERR_ARG, "gemm_bk must be 16 or 32");
+    ctx->gemm_bk = (int)value;
   } else if (!strcmp(key, "assembly")) {
     if (value < 0 || value > 2) return ctx->fail(DGP_ERR_ARG, "assembly must be 0 (auto), 1 (exact differences) or 2 (Gram)");
     ctx->assembly = (int)value;

@@ -31,18 +31,21 @@ namespace dgp {
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 16, NTHREADS = 256;
+constexpr int BM = 128, BN = 64, NTHREADS = 256;
 constexpr int LDA_MN = BM + 4;  // 132 = 4 mod 16
 constexpr int LDB_MN = BN + 4;  //  68 = 4 mod 16
-constexpr int LDS_K = BK + 4;   //  20 = 4 mod 16
 constexpr int SUPER_ROWS = 12;
 
-template <bool AK, bool BKM>
+// BK = K-slice per pipeline stage and per __syncthreads: 16 with a 3-4 deep pipeline, or 32 with
+// double buffering (half as many barriers; one 32-slice is ~8k cycles of DMMA per CTA pair, several
+// times the L2/HBM latency it has to cover).
+template <bool AK, bool BKM, int BK>
 struct Cfg {
-  static constexpr int A_STAGE = AK ? BM * LDS_K : BK * LDA_MN;   // 2560 / 2112 doubles
-  static constexpr int B_STAGE = BKM ? BN * LDS_K : BK * LDB_MN;  // 1280 / 1088 doubles
-  // two CTAs per SM must fit in 227 KB: 4 stages unless both operands are K-major
-  static constexpr int STAGES = ((A_STAGE + B_STAGE) * 4 * 8 <= 112 * 1024) ? 4 : 3;
+  static constexpr int LDS_K = BK + 4;  // 20 / 36 = 4 mod 16
+  static constexpr int A_STAGE = AK ? BM * LDS_K : BK * LDA_MN;
+  static constexpr int B_STAGE = BKM ? BN * LDS_K : BK * LDB_MN;
+  // two CTAs per SM must fit in 227 KB
+  static constexpr int STAGES = BK == 32 ? 2 : (((A_STAGE + B_STAGE) * 4 * 8 <= 112 * 1024) ? 4 : 3);
   static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
 };
 
@@ -62,14 +65,15 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// Copy one ROWS x 16 operand slice into a stage (ROWS = 128 for A, 64 for B).  g points at the
+// Copy one ROWS x BK operand slice into a stage (ROWS = 128 for A, 64 for B).  g points at the
 // slice origin.
-template <bool KMAJOR, int ROWS>
+template <bool KMAJOR, int ROWS, int BK>
 __device__ __forceinline__ void load_slice(double *s, const double *g, int64_t ld, int tid) {
   constexpr int CHUNKS = ROWS * BK / 2;  // 16-byte chunks
   constexpr int LD_MN = ROWS + 4;
+  constexpr int LDS_K = BK + 4;
   if (!KMAJOR) {
-    // element (mn, k) at g[mn + k*ld]; 16 columns of ROWS contiguous doubles
+    // element (mn, k) at g[mn + k*ld]; BK columns of ROWS contiguous doubles
 #pragma unroll
     for (int i = 0; i < CHUNKS / NTHREADS; ++i) {
       int c = tid + i * NTHREADS;
@@ -77,21 +81,21 @@ __device__ __forceinline__ void load_slice(double *s, const double *g, int64_t l
       cp_async16(s + k * LD_MN + mc * 2, g + mc * 2 + (int64_t)k * ld);
     }
   } else {
-    // element (mn, k) at g[k + mn*ld]; ROWS rows of 16 contiguous doubles
+    // element (mn, k) at g[k + mn*ld]; ROWS rows of BK contiguous doubles
 #pragma unroll
     for (int i = 0; i < CHUNKS / NTHREADS; ++i) {
       int c = tid + i * NTHREADS;
-      int mn = c >> 3, kc = c & 7;
+      int mn = c / (BK / 2), kc = c % (BK / 2);
       cp_async16(s + mn * LDS_K + kc * 2, g + kc * 2 + (int64_t)mn * ld);
     }
   }
 }
 
-template <bool AK, bool BKM>
+template <bool AK, bool BKM, int BK>
 __global__ void __launch_bounds__(NTHREADS, 2) dgemm_dmma_kernel(GemmArgs p, const uint32_t *__restrict__ tiles) {
   extern __shared__ __align__(16) double smem[];
-  using C_ = Cfg<AK, BKM>;
-  constexpr int A_STAGE = C_::A_STAGE, B_STAGE = C_::B_STAGE, STAGES = C_::STAGES;
+  using C_ = Cfg<AK, BKM, BK>;
+  constexpr int A_STAGE = C_::A_STAGE, B_STAGE = C_::B_STAGE, STAGES = C_::STAGES, LDS_K = C_::LDS_K;
   double *As = smem;
   double *Bs = smem + STAGES * A_STAGE;
 
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dgemm_dmma_kernel(GemmArgs p, con
   }
 
   int k_lo = 0, k_hi = p.K;
-  if (p.kmode == K_GE_COL) k_lo = (n0 / BK) * BK;
+  if (p.kmode == K_GE_COL) k_lo = (n0 / 64) * 64;
   else if (p.kmode == K_LT_ROWEND) k_hi = min(p.K, m0 + BM);
   else if (p.kmode == K_GE_ROW) k_lo = m0;
   const int KT = (k_hi - k_lo) / BK;
@@ -144,8 +148,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) dgemm_dmma_kernel(GemmArgs p, con
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < KT) {
-      load_slice<AK, BM>(As + s * A_STAGE, Ag + s * a_step, p.lda, tid);
-      load_slice<BKM, BN>(Bs + s * B_STAGE, Bg + s * b_step, p.ldb, tid);
+      load_slice<AK, BM, BK>(As + s * A_STAGE, Ag + s * a_step, p.lda, tid);
+      load_slice<BKM, BN, BK>(Bs + s * B_STAGE, Bg + s * b_step, p.ldb, tid);
     }
     cp_async_commit();
   }
@@ -164,8 +168,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) dgemm_dmma_kernel(GemmArgs p, con
       int nk = kt + STAGES - 1;
       if (nk < KT) {
         int s = nk % STAGES;
-        load_slice<AK, BM>(As + s * A_STAGE, Ag + (int64_t)nk * a_step, p.lda, tid);
-        load_slice<BKM, BN>(Bs + s * B_STAGE, Bg + (int64_t)nk * b_step, p.ldb, tid);
+        load_slice<AK, BM, BK>(As + s * A_STAGE, Ag + (int64_t)nk * a_step, p.lda, tid);
+        load_slice<BKM, BN, BK>(Bs + s * B_STAGE, Bg + (int64_t)nk * b_step, p.ldb, tid);
       }
       cp_async_commit();
     }
@@ -220,13 +224,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) dgemm_dmma_kernel(GemmArgs p, con
 
 template <bool AK, bool BKM>
 cudaError_t opt_in() {
-  return cudaFuncSetAttribute(dgemm_dmma_kernel<AK, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)Cfg<AK, BKM>::SMEM);
+  cudaError_t e = cudaFuncSetAttribute(dgemm_dmma_kernel<AK, BKM, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg<AK, BKM, 16>::SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dgemm_dmma_kernel<AK, BKM, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)Cfg<AK, BKM, 32>::SMEM);
 }
 
 template <bool AK, bool BKM>
-void launch(cudaStream_t stream, const GemmArgs &a, dim3 grid, const uint32_t *tiles) {
-  dgemm_dmma_kernel<AK, BKM><<<grid, NTHREADS, Cfg<AK, BKM>::SMEM, stream>>>(a, tiles);
+void launch(cudaStream_t stream, const GemmArgs &a, dim3 grid, const uint32_t *tiles, int bk) {
+  if (bk == 32) dgemm_dmma_kernel<AK, BKM, 32><<<grid, NTHREADS, Cfg<AK, BKM, 32>::SMEM, stream>>>(a, tiles);
+  else dgemm_dmma_kernel<AK, BKM, 16><<<grid, NTHREADS, Cfg<AK, BKM, 16>::SMEM, stream>>>(a, tiles);
 }
 
 // ---- tile tables -----------------------------------------------------------------------------
@@ -293,8 +301,10 @@ int32_t gemm_init(Ctx *ctx) {
 
 int32_t gemm(Ctx *ctx, cudaStream_t stream, const GemmArgs &a) {
   if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return DGP_OK;
-  if (a.M % BM || a.N % BN || a.K % BK || a.K < 0)
-    return ctx->fail(DGP_ERR_SHAPE, "gemm: M=%d N=%d K=%d must be multiples of %d/%d/%d", a.M, a.N, a.K, BM, BN, BK);
+  if (a.M % BM || a.N % BN || a.K % 16 || a.K < 0)
+    return ctx->fail(DGP_ERR_SHAPE, "gemm: M=%d N=%d K=%d must be multiples of %d/%d/16", a.M, a.N, a.K, BM, BN);
+  // 32-wide slices need every k-range to be a multiple of 32 (triangular ranges are multiples of 64)
+  const int bk = (ctx->gemm_bk == 32 && a.K % 32 == 0) ? 32 : 16;
   if ((a.lda & 1) || (a.ldb & 1) || ((uintptr_t)a.A & 15) || ((uintptr_t)a.B & 15))
     return ctx->fail(DGP_ERR_SHAPE, "gemm: operands must be 16-byte aligned with even leading dimensions");
   if (a.lower_only && a.M != a.N) return ctx->fail(DGP_ERR_SHAPE, "gemm: lower_only needs a square C");
@@ -305,10 +315,10 @@ int32_t gemm(Ctx *ctx, cudaStream_t stream, const GemmArgs &a) {
   DGP_TRY(get_tiles(ctx, mt, nt, a.lower_only != 0, a.reverse != 0, &tt));
   if (tt.count == 0) return DGP_OK;
   dim3 grid((unsigned)tt.count, (unsigned)a.batch, 1);
-  if (!a.a_kmajor && !a.b_kmajor) launch<false, false>(stream, a, grid, tt.dev);
-  else if (!a.a_kmajor && a.b_kmajor) launch<false, true>(stream, a, grid, tt.dev);
-  else if (a.a_kmajor && !a.b_kmajor) launch<true, false>(stream, a, grid, tt.dev);
-  else launch<true, true>(stream, a, grid, tt.dev);
+  if (!a.a_kmajor && !a.b_kmajor) launch<false, false>(stream, a, grid, tt.dev, bk);
+  else if (!a.a_kmajor && a.b_kmajor) launch<false, true>(stream, a, grid, tt.dev, bk);
+  else if (a.a_kmajor && !a.b_kmajor) launch<true, false>(stream, a, grid, tt.dev, bk);
+  else launch<true, true>(stream, a, grid, tt.dev, bk);
   ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
