@@ -259,11 +259,12 @@ class Context:
 
     # -- measurement / building blocks ------------------------------------------------------
     def measure_peaks(self) -> dict:
-        out = np.zeros(8)
-        self.check(self.lib.dgp_measure_peaks(self.h, _ptr(out), 8))
+        out = np.zeros(9)
+        self.check(self.lib.dgp_measure_peaks(self.h, _ptr(out), 9))
         return {"dmma_tflops": float(out[0]), "dfma_tflops": float(out[1]), "hbm_write_gbs": float(out[2]),
                 "hbm_copy_gbs": float(out[3]), "hbm_read_gbs": float(out[4]), "dmma_tflops_sustained": float(out[5]),
-                "mixed_dmma_tflops": float(out[6]), "mixed_dfma_tflops": float(out[7])}
+                "mixed_dmma_tflops": float(out[6]), "mixed_dfma_tflops": float(out[7]),
+                "dmma_tflops_gemm_pattern": float(out[8])}
 
     def launch_count(self) -> int:
         n = C.c_uint64()

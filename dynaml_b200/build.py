@@ -58,7 +58,23 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    build_cpp_mirror_test(force)
     return LIB
+
+
+def build_cpp_mirror_test(force: bool = False) -> Path:
+    """The C++ host mirror (include/dynaml_b200.hpp) compiled against the C ABI: tests/cpp/host_mirror_test.cpp."""
+    root = ROOT.parent
+    src = root / "tests" / "cpp" / "host_mirror_test.cpp"
+    out = LIBDIR / "host_mirror_test"
+    deps = [src, root / "include" / "dynaml_b200.hpp", root / "include" / "dgp_b200.h", LIB]
+    if src.exists() and (force or _stale(out, deps)):
+        cmd = ["g++", "-std=c++17", "-O2", "-I", str(root / "include"), str(src), "-o", str(out),
+               "-L", str(LIBDIR), "-ldgp_b200", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed for {src}:\n{r.stdout}\n{r.stderr}")
+    return out
 
 
 if __name__ == "__main__":

@@ -37,7 +37,7 @@ struct Ctx {
   std::map<std::string, std::pair<void *, size_t>> arena;
   int64_t nb = 0;     // outer Cholesky block (0 = choose from n)
   int lookahead = 1;
-  int gemm_bk = 16;   // K-slice of the GEMM pipeline: 16 (3-4 stages) or 32 (double buffered)
+  int gemm_bk = 32;   // K-slice of the GEMM pipeline: 16 (3-4 stages) or 32 (double buffered)
   int assembly = 0;   // 0: Gram/DMMA assembly when its error bound allows, 1: always exact differences, 2: force Gram
   int batch_streams = 3;  // dgp_energy_batch evaluates this many candidates concurrently (1..4)
   cudaStream_t slot_S[4] = {nullptr, nullptr, nullptr, nullptr};  // extra (main, panel) stream pairs, created lazily

@@ -42,6 +42,40 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, double seed
   if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// DMMA with the register pattern of a real GEMM inner step: a 4x4 grid of accumulators fed by 4 + 4
+// distinct operand registers that change every step (no operand-register reuse between
+// consecutive DMMAs beyond what a 32x32 warp tile has), still without any memory traffic.
+__global__ void __launch_bounds__(256) dmma_tile_peak_kernel(double *out, double seed) {
+  double c[4][4][2], a[4], b[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a[i] = seed + (threadIdx.x + i) * 1e-9;
+    b[i] = 1.0 - seed + i * 1e-9;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+  }
+  for (int it = 0; it < PK_ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(c[i][j][0]), "+d"(c[i][j][1])
+                     : "d"(a[i]), "d"(b[j]));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // new fragments every step, as after the LDS of the next k4 slice
+      a[i] = __longlong_as_double(__double_as_longlong(a[i]) ^ (long long)(it & 1));
+      b[i] = __longlong_as_double(__double_as_longlong(b[i]) ^ (long long)(it & 1));
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += c[i][j][0] + c[i][j][1];
+  if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // DMMA and DFMA interleaved: do the FP64 tensor pipe and the FP64 FMA pipe add up (separate
 // units) or share the same throughput?
 __global__ void __launch_bounds__(256) mixed_peak_kernel(double *out, double seed) {
@@ -115,7 +149,7 @@ int32_t best_ms(Ctx *ctx, int reps, F launch, double *best) {
 
 int32_t measure_peaks(Ctx *ctx, double *out, int n) {
   cudaStream_t S = ctx->stream;
-  double res[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double res[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const size_t bytes = (size_t)4 << 30;  // 4 GiB per buffer: far beyond the 126 MB L2
   double *a = (double *)ctx->buf("pk_a", bytes);
   double *b = (double *)ctx->buf("pk_b", bytes);
@@ -139,6 +173,9 @@ int32_t measure_peaks(Ctx *ctx, double *out, int n) {
   DGP_TRY(best_ms(ctx, 5, [&] { mixed_peak_kernel<<<ctas, 256, 0, S>>>(a, 0.5); }, &ms));
   res[6] = (double)ctas * 8 * 8.0 * PK_ITERS * 512.0 / (ms * 1e-3) / 1e12;   // DMMA share
   res[7] = (double)ctas * 8 * 16.0 * PK_ITERS * 64.0 / (ms * 1e-3) / 1e12;   // DFMA share
+  // GEMM-like register pattern, at the occupancy of the GEMM kernel (2 CTAs of 256 threads per SM)
+  DGP_TRY(best_ms(ctx, 5, [&] { dmma_tile_peak_kernel<<<ctx->sm_count * 2, 256, 0, S>>>(a, 0.5); }, &ms));
+  res[8] = (double)ctx->sm_count * 2 * 8 * 16.0 * PK_ITERS * 512.0 / (ms * 1e-3) / 1e12;
   {  // sustained DMMA: ~1 s of back-to-back launches under the power cap
     const int launches = 120;
     DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_a, S));
@@ -151,7 +188,7 @@ int32_t measure_peaks(Ctx *ctx, double *out, int n) {
   }
   ctx->release("pk_a");
   ctx->release("pk_b");
-  for (int i = 0; i < n && i < 8; ++i) out[i] = res[i];
+  for (int i = 0; i < n && i < 9; ++i) out[i] = res[i];
   return DGP_OK;
 }
 

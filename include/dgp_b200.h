@@ -175,7 +175,8 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spe
 /* out[0] DMMA FP64 TFLOP/s, out[1] DFMA FP64 TFLOP/s, out[2] HBM write GB/s, out[3] HBM copy GB/s
    (read+write bytes), out[4] HBM read GB/s, each the best of a few timed launches; out[5] DMMA TFLOP/s
    sustained over ~1 s of back-to-back launches; out[6], out[7] DMMA and DFMA TFLOP/s when interleaved
-   in one kernel (do the two FP64 pipes add up?).              */
+   in one kernel (do the two FP64 pipes add up?); out[8] DMMA TFLOP/s with the register pattern and
+   occupancy of the GEMM kernel (4x4 accumulators, fresh fragments every step, 16 warps per SM).              */
 int32_t dgp_measure_peaks(dgp_ctx *ctx, double *out, int32_t n);
 /* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
 int32_t dgp_launch_count(const dgp_ctx *ctx, uint64_t *out);

@@ -1,0 +1,576 @@
+// dynaml_b200.hpp -- header-only C++17 host-side mirror of the dynaml-core classes on the GP hot path,
+// layered on the C ABI of dgp_b200.h.  The reference's host code is Scala on the JVM, which cannot be
+// built in this image; this is the compiled-language twin of the Scala shim described in
+// same class names, hyper-parameter names, argument meaning and error behaviour
+// (CORE = dynaml-core/src/main/scala/io/github/tailhq/dynaml):
+//
+//   LocalScalarKernel, SEKernel, RBFKernel, MahalanobisKernel, GenericMaternKernel, PeriodicKernel, DiracKernel
+//       CORE/kernels/{CovarianceFunction,LocalScalarKernel,RBFKernel,GenericMaternKernel,PeriodicKernel,DiracKernel}.scala
+//   GPRegression (energy, gradEnergy, predictiveDistribution, predictionWithErrorBars, persist)
+//       CORE/models/gp/{AbstractGPRegressionModel,GPRegression}.scala
+//   GridSearch, CoupledSimulatedAnnealing, GradBasedGlobalOptimizer
+//       CORE/optimization/{ModelTuner,GridSearch,AbstractCSA,CoupledSimulatedAnnealing,GradBasedGlobalOptimizer}.scala
+//
+// Every number comes from libdgp_b200.so; there is no CPU fallback.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <functional>
+#include <limits>
+#include <map>
+#include <memory>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+#include "dgp_b200.h"
+
+namespace dynaml {
+
+using Config = std::map<std::string, double>;        // Map[String, Double]
+using Options = std::map<std::string, std::string>;  // Map[String, String]
+using Vec = std::vector<double>;                     // DenseVector[Double]
+
+struct DenseMatrix {  // Breeze DenseMatrix[Double]: column-major, offset 0
+  int64_t rows = 0, cols = 0;
+  std::vector<double> data;
+  double operator()(int64_t i, int64_t j) const { return data[(size_t)(i + j * rows)]; }
+};
+
+class DgpError : public std::runtime_error {
+ public:
+  DgpError(int32_t st, const std::string &m) : std::runtime_error(m), status(st) {}
+  int32_t status;
+};
+
+// One GPU (dgp_ctx); not thread-safe, like the reference model.
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    if (dgp_ctx_create(device, &h_) != DGP_OK)
+      throw DgpError(DGP_ERR_CUDA, "dgp_ctx_create failed: a B200 (sm_100) GPU is required; there is no CPU fallback");
+  }
+  ~Context() { dgp_ctx_destroy(h_); }
+  Context(const Context &) = delete;
+  Context &operator=(const Context &) = delete;
+  dgp_ctx *get() const { return h_; }
+  void check(int32_t st) const {
+    if (st != DGP_OK) throw DgpError(st, dgp_last_error(h_));
+  }
+  static std::shared_ptr<Context> &global() {
+    static std::shared_ptr<Context> c = std::make_shared<Context>(0);
+    return c;
+  }
+
+ private:
+  dgp_ctx *h_ = nullptr;
+};
+
+inline std::vector<double> pack(const std::vector<Vec> &pts) {
+  const size_t d = pts.empty() ? 0 : pts[0].size();
+  std::vector<double> out;
+  out.reserve(pts.size() * d);
+  for (const Vec &p : pts) {
+    if (p.size() != d) throw std::invalid_argument("points disagree on dimension");
+    out.insert(out.end(), p.begin(), p.end());
+  }
+  return out;
+}
+
+// ---- covariance functions ----------------------------------------------------------------------------
+class LocalScalarKernel {
+ public:
+  virtual ~LocalScalarKernel() = default;
+  std::vector<std::string> hyper_parameters;
+  std::vector<std::string> blocked_hyper_parameters;
+  Config state;
+  int grad_mode = DGP_GRAD_REFERENCE;
+
+  void block(const std::vector<std::string> &h) { blocked_hyper_parameters = h; }
+  void block_all_hyper_parameters() { blocked_hyper_parameters = hyper_parameters; }
+  std::vector<std::string> effective_hyper_parameters() const {
+    std::vector<std::string> out;
+    for (const auto &h : hyper_parameters)
+      if (std::find(blocked_hyper_parameters.begin(), blocked_hyper_parameters.end(), h) == blocked_hyper_parameters.end())
+        out.push_back(h);
+    return out;
+  }
+  Config effective_state() const {
+    Config out;
+    for (const auto &h : effective_hyper_parameters()) out[h] = state.at(h);
+    return out;
+  }
+  // CovarianceFunction.scala:37-44: all effective keys must be present
+  virtual void setHyperParameters(const Config &h) {
+    for (const auto &k : effective_hyper_parameters())
+      if (!h.count(k)) throw std::invalid_argument("All hyper parameters must be contained in the arguments");
+    for (const auto &k : effective_hyper_parameters()) state[k] = h.at(k);
+  }
+
+  virtual int device_kind() const = 0;
+  virtual Vec device_hyp() const {
+    Vec v;
+    for (const auto &h : hyper_parameters) v.push_back(state.at(h));
+    return v;
+  }
+
+  double evaluate(const Vec &x, const Vec &y) const { return buildCrossKernelMatrix({x}, {y})(0, 0); }
+
+  DenseMatrix buildKernelMatrix(const std::vector<Vec> &data, double noise = 0.0, bool add_noise = false) const {
+    const auto ctx = Context::global();
+    Vec hyp = device_hyp();
+    dgp_kernel_spec sp{device_kind(), (int32_t)hyp.size(), grad_mode, 0, hyp.data(), noise};
+    std::vector<double> X = pack(data);
+    DenseMatrix K;
+    K.rows = K.cols = (int64_t)data.size();
+    K.data.resize((size_t)K.rows * K.cols);
+    ctx->check(dgp_kernel_matrix(ctx->get(), &sp, X.data(), K.rows, nullptr, 0, (int32_t)data[0].size(), DGP_ROW_MAJOR,
+                                 K.data.data(), K.rows, add_noise ? 1 : 0));
+    return K;
+  }
+  DenseMatrix buildCrossKernelMatrix(const std::vector<Vec> &d1, const std::vector<Vec> &d2) const {
+    const auto ctx = Context::global();
+    Vec hyp = device_hyp();
+    dgp_kernel_spec sp{device_kind(), (int32_t)hyp.size(), grad_mode, 0, hyp.data(), 0.0};
+    std::vector<double> X1 = pack(d1), X2 = pack(d2);
+    DenseMatrix K;
+    K.rows = (int64_t)d1.size();
+    K.cols = (int64_t)d2.size();
+    K.data.resize((size_t)K.rows * K.cols);
+    ctx->check(dgp_kernel_matrix(ctx->get(), &sp, X1.data(), K.rows, X2.data(), K.cols, (int32_t)d1[0].size(),
+                                 DGP_ROW_MAJOR, K.data.data(), K.rows, 0));
+    return K;
+  }
+};
+
+class RBFKernel : public LocalScalarKernel {
+ public:
+  explicit RBFKernel(double bandwidth = 1.0) {
+    hyper_parameters = {"bandwidth"};
+    state = {{"bandwidth", bandwidth}};
+  }
+  int device_kind() const override { return DGP_KERNEL_RBF; }
+};
+
+class SEKernel : public LocalScalarKernel {
+ public:
+  explicit SEKernel(double band = 1.0, double h = 2.0) {
+    hyper_parameters = {"bandwidth", "amplitude"};
+    state = {{"bandwidth", band}, {"amplitude", h}};
+  }
+  int device_kind() const override { return DGP_KERNEL_SE; }
+};
+
+class MahalanobisKernel : public LocalScalarKernel {
+ public:
+  explicit MahalanobisKernel(const Vec &band, double h = 2.0, int mode = DGP_GRAD_REFERENCE) {
+    hyper_parameters.push_back("MahalanobisAmplitude");
+    state["MahalanobisAmplitude"] = h;
+    for (size_t i = 0; i < band.size(); ++i) {
+      hyper_parameters.push_back("MahalanobisBandwidth_" + std::to_string(i));
+      state[hyper_parameters.back()] = band[i];
+    }
+    grad_mode = mode;
+  }
+  int device_kind() const override { return DGP_KERNEL_ARD_SE; }
+};
+
+class GenericMaternKernel : public LocalScalarKernel {
+ public:
+  explicit GenericMaternKernel(double l, int p = 2) {
+    hyper_parameters = {"p", "l"};
+    blocked_hyper_parameters = {"p"};
+    state = {{"p", (double)p}, {"l", l}};
+  }
+  void setHyperParameters(const Config &h) override {  // GenericMaternKernel.scala:48-53
+    LocalScalarKernel::setHyperParameters(h);
+    if (h.count("p")) state["p"] = std::floor(std::fabs(h.at("p")));
+  }
+  int device_kind() const override { return DGP_KERNEL_MATERN; }
+};
+
+class PeriodicKernel : public LocalScalarKernel {
+ public:
+  explicit PeriodicKernel(double s = 1.0, double ls = 1.0, double freq = 1.0) {
+    hyper_parameters = {"sigma", "lengthscale", "frequency"};
+    state = {{"sigma", s}, {"lengthscale", ls}, {"frequency", freq}};
+  }
+  int device_kind() const override { return DGP_KERNEL_PERIODIC; }
+};
+
+class DiracKernel : public LocalScalarKernel {
+ public:
+  explicit DiracKernel(double noiseLevel = 1.0) {
+    hyper_parameters = {"noiseLevel"};
+    state = {{"noiseLevel", noiseLevel}};
+  }
+  int device_kind() const override { return DGP_KERNEL_DIRAC; }
+};
+
+// ---- results -------------------------------------------------------------------------------------------
+struct MultGaussianPRV {
+  Vec mu;
+  DenseMatrix covariance;
+  std::function<std::pair<Vec, Vec>(double)> confidenceInterval;  // BlockedMultiVariateGaussian.scala:58-68
+};
+
+// ---- model -----------------------------------------------------------------------------------------------
+class GPRegression {
+ public:
+  using Data = std::vector<std::pair<Vec, double>>;
+  using Mean = std::function<double(const Vec &)>;
+
+  GPRegression(std::shared_ptr<LocalScalarKernel> cov, std::shared_ptr<DiracKernel> noise, Data trainingdata,
+               Mean meanFunc = [](const Vec &) { return 0.0; })
+      : covariance(std::move(cov)), noiseModel(std::move(noise)), g(std::move(trainingdata)), mean(std::move(meanFunc)),
+        ctx_(Context::global()) {
+    if (g.empty()) throw std::invalid_argument("training data is empty");
+    covariance->device_kind();
+    hyper_parameters = covariance->hyper_parameters;
+    hyper_parameters.insert(hyper_parameters.end(), noiseModel->hyper_parameters.begin(),
+                            noiseModel->hyper_parameters.end());
+    refresh_state();
+  }
+  ~GPRegression() {
+    if (model_) dgp_model_destroy(ctx_->get(), model_);
+    if (data_) dgp_data_destroy(ctx_->get(), data_);
+  }
+  GPRegression(const GPRegression &) = delete;
+
+  std::shared_ptr<LocalScalarKernel> covariance;
+  std::shared_ptr<DiracKernel> noiseModel;
+  std::vector<std::string> hyper_parameters;
+  const Config &_current_state() const { return current_state; }
+
+  void setState(const Config &s) {  // AbstractGPRegressionModel.scala:117-128
+    Config c, n;
+    for (const auto &kv : s) {
+      if (has(covariance->hyper_parameters, kv.first)) c[kv.first] = kv.second;
+      if (has(noiseModel->hyper_parameters, kv.first)) n[kv.first] = kv.second;
+    }
+    covariance->setHyperParameters(c);
+    noiseModel->setHyperParameters(n);
+    refresh_state();
+  }
+
+  // 0.5*(r'K^-1 r + sum log L_ii + n log 2pi); +Inf when K is not PD (:148-189, 516-535)
+  double energy(const Config &h, const Options & = {}) {
+    setState(h);
+    Vec hyp = covariance->device_hyp();
+    dgp_kernel_spec sp = spec(hyp);
+    double e = 0.0;
+    const int32_t st = dgp_energy(ctx_->get(), device_data(), &sp, &e);
+    if (st == DGP_ERR_NOT_PD) return std::numeric_limits<double>::infinity();
+    ctx_->check(st);
+    return e;
+  }
+
+  std::vector<double> energyBatch(const std::vector<Config> &hs) {
+    std::vector<Vec> hyps;
+    std::vector<dgp_kernel_spec> specs;
+    for (const Config &h : hs) {
+      setState(h);
+      hyps.push_back(covariance->device_hyp());
+    }
+    for (size_t i = 0; i < hs.size(); ++i) {
+      setState(hs[i]);
+      specs.push_back(spec(hyps[i]));
+    }
+    std::vector<double> e(hs.size());
+    std::vector<int32_t> status(hs.size());
+    if (!hs.empty())
+      ctx_->check(dgp_energy_batch(ctx_->get(), device_data(), specs.data(), (int32_t)specs.size(), e.data(), status.data()));
+    return e;
+  }
+
+  // tr((alpha alpha' - K^-1) dK/dtheta) per effective hyper-parameter; NaN map on failure (:196-267)
+  Config gradEnergy(const Config &h) {
+    covariance->setHyperParameters(h);
+    noiseModel->setHyperParameters(h);
+    refresh_state();
+    Vec hyp = covariance->device_hyp();
+    dgp_kernel_spec sp = spec(hyp);
+    std::vector<double> gr(hyp.size() + 1);
+    double e = 0.0;
+    const int32_t st = dgp_energy_grad(ctx_->get(), device_data(), &sp, &e, gr.data());
+    if (st != DGP_ERR_NOT_PD) ctx_->check(st);
+    Config out;
+    const auto &names = covariance->hyper_parameters;
+    for (const auto &k : covariance->effective_hyper_parameters())
+      out[k] = gr[(size_t)(std::find(names.begin(), names.end(), k) - names.begin())];
+    for (const auto &k : noiseModel->effective_hyper_parameters()) out[k] = gr.back();
+    return out;
+  }
+
+  void persist(const Config &state) {  // :399-413; keeps L and alpha resident instead of K
+    setState(state);
+    drop_model();
+    Vec hyp = covariance->device_hyp();
+    dgp_kernel_spec sp = spec(hyp);
+    ctx_->check(dgp_fit(ctx_->get(), device_data(), &sp, &model_));
+    caching_ = true;
+  }
+  void unpersist() {
+    drop_model();
+    caching_ = false;
+  }
+
+  MultGaussianPRV predictiveDistribution(const std::vector<Vec> &test) {  // :304-357
+    MultGaussianPRV out;
+    run_predict(test, 1.0, &out.mu, &out.covariance, nullptr, nullptr);
+    out.confidenceInterval = [this, test](double s) {
+      Vec mu, lo, hi;
+      run_predict(test, s, &mu, nullptr, &lo, &hi);
+      return std::make_pair(lo, hi);
+    };
+    return out;
+  }
+
+  std::vector<std::tuple<Vec, double, double, double>> predictionWithErrorBars(const std::vector<Vec> &test, int sigma) {
+    Vec mu, lo, hi;
+    run_predict(test, (double)sigma, &mu, nullptr, &lo, &hi);
+    std::vector<std::tuple<Vec, double, double, double>> out;
+    for (size_t i = 0; i < test.size(); ++i) out.emplace_back(test[i], mu[i], lo[i], hi[i]);
+    return out;
+  }
+  double predict(const Vec &point) { return std::get<1>(predictionWithErrorBars({point}, 1)[0]); }
+
+ private:
+  static bool has(const std::vector<std::string> &v, const std::string &k) {
+    return std::find(v.begin(), v.end(), k) != v.end();
+  }
+  void refresh_state() {
+    current_state = covariance->state;
+    for (const auto &kv : noiseModel->state) current_state[kv.first] = kv.second;
+  }
+  dgp_kernel_spec spec(Vec &hyp) const {
+    return dgp_kernel_spec{covariance->device_kind(), (int32_t)hyp.size(), covariance->grad_mode, 0, hyp.data(),
+                           noiseModel->state.at("noiseLevel")};
+  }
+  dgp_data *device_data() {
+    if (!data_) {
+      std::vector<Vec> pts;
+      std::vector<double> y, m;
+      for (const auto &p : g) {
+        pts.push_back(p.first);
+        y.push_back(p.second);
+        m.push_back(mean(p.first));
+      }
+      std::vector<double> X = pack(pts);
+      ctx_->check(dgp_data_create(ctx_->get(), X.data(), (int64_t)g.size(), (int32_t)pts[0].size(), DGP_ROW_MAJOR, y.data(),
+                                  m.data(), &data_));
+    }
+    return data_;
+  }
+  void drop_model() {
+    if (model_) dgp_model_destroy(ctx_->get(), model_);
+    model_ = nullptr;
+  }
+  void run_predict(const std::vector<Vec> &test, double sigma, Vec *mu, DenseMatrix *cov, Vec *lo, Vec *hi) {
+    dgp_model *m = model_;
+    const bool temp = !(model_ && caching_);
+    if (temp) {
+      Vec hyp = covariance->device_hyp();
+      dgp_kernel_spec sp = spec(hyp);
+      ctx_->check(dgp_fit(ctx_->get(), device_data(), &sp, &m));
+    }
+    const int64_t M = (int64_t)test.size();
+    std::vector<double> Xs = pack(test), ms;
+    for (const Vec &t : test) ms.push_back(mean(t));
+    mu->assign((size_t)M, 0.0);
+    if (cov) {
+      cov->rows = cov->cols = M;
+      cov->data.assign((size_t)M * M, 0.0);
+    }
+    if (lo) {
+      lo->assign((size_t)M, 0.0);
+      hi->assign((size_t)M, 0.0);
+    }
+    const int32_t st = dgp_predict(ctx_->get(), m, Xs.data(), M, DGP_ROW_MAJOR, ms.data(), mu->data(),
+                                   cov ? cov->data.data() : nullptr, M, lo ? lo->data() : nullptr,
+                                   hi ? hi->data() : nullptr, sigma);
+    if (temp) dgp_model_destroy(ctx_->get(), m);
+    ctx_->check(st);
+  }
+
+  Data g;
+  Mean mean;
+  Config current_state;
+  std::shared_ptr<Context> ctx_;
+  dgp_data *data_ = nullptr;
+  dgp_model *model_ = nullptr;
+  bool caching_ = false;
+};
+
+// ---- tuners ------------------------------------------------------------------------------------------------
+class ModelTuner {
+ public:
+  explicit ModelTuner(GPRegression &model) : system(model) {}
+  GPRegression &system;
+  ModelTuner &setGridSize(int s) { gridsize = s; return *this; }
+  ModelTuner &setStepSize(double s) { step = s; return *this; }
+  ModelTuner &setLogScale(bool t) { logarithmicScale = t; return *this; }
+
+  // ModelTuner.scala:79-103 (key order: std::map iterates keys sorted; Scala's small Maps keep insertion order)
+  std::vector<Config> getGrid(const Config &initialConfig) const {
+    std::vector<std::string> keys;
+    std::vector<Vec> vecs;
+    for (const auto &kv : initialConfig) {
+      keys.push_back(kv.first);
+      Vec v;
+      for (int i = 0; i < gridsize; ++i)
+        v.push_back(logarithmicScale ? kv.second / std::exp((i + 1) * step) : kv.second - (i + 1) * step);
+      vecs.push_back(v);
+    }
+    std::vector<Config> grid(1);
+    for (size_t k = 0; k < keys.size(); ++k) {
+      std::vector<Config> next;
+      for (const Config &c : grid)
+        for (double v : vecs[k]) {
+          Config n = c;
+          n[keys[k]] = v;
+          next.push_back(n);
+        }
+      grid.swap(next);
+    }
+    return grid;
+  }
+  std::vector<std::pair<double, Config>> getEnergyLandscape(const Config &initialConfig) {
+    std::vector<Config> grid = getGrid(initialConfig);
+    std::vector<double> e = system.energyBatch(grid);  // the reference's serial grid.map(system.energy)
+    std::vector<std::pair<double, Config>> out;
+    for (size_t i = 0; i < grid.size(); ++i) out.emplace_back(e[i], grid[i]);
+    return out;
+  }
+
+ protected:
+  double step = 0.3;
+  int gridsize = 3;
+  bool logarithmicScale = false;
+};
+
+class GridSearch : public ModelTuner {
+ public:
+  using ModelTuner::ModelTuner;
+  std::pair<GPRegression *, Config> optimize(const Config &initialConfig, const Options &options = {}) {
+    std::map<double, Config> landscape;  // `.toMap` then `keys.min` (GridSearch.scala:47-49)
+    for (auto &kv : getEnergyLandscape(initialConfig)) landscape[kv.first] = kv.second;
+    Config best = landscape.begin()->second;
+    auto it = options.find("persist");
+    if (it != options.end() && (it->second == "true" || it->second == "1")) system.persist(best);
+    return {&system, best};
+  }
+};
+
+class CoupledSimulatedAnnealing : public ModelTuner {
+ public:
+  explicit CoupledSimulatedAnnealing(GPRegression &model, uint64_t seed = 0) : ModelTuner(model), rng(seed) {}
+  CoupledSimulatedAnnealing &setMaxIterations(int m) { MAX_ITERATIONS = m; return *this; }
+  CoupledSimulatedAnnealing &setVariant(const std::string &v) { variant = v; return *this; }
+  double iTemp = 1.0, alpha = 0.05;
+
+  static double couplingFactor(const std::string &v, const std::vector<double> &land, double Tacc) {  // AbstractCSA.scala:285-297
+    double s = 0.0;
+    if (v == "CSA-MuSA" || v == "CSA-BA") { for (double e : land) s += std::exp(-e / Tacc); return s; }
+    if (v == "CSA-M" || v == "CSA-MwVC") { for (double e : land) s += std::exp(e / Tacc); return s; }
+    return 1.0;
+  }
+  static double acceptanceProbability(const std::string &v, double e, double old, double gamma, double t) {  // :299-316
+    if (v == "CSA-MuSA") return std::exp(-e / t) / (std::exp(-e / t) + gamma);
+    if (v == "CSA-BA") return 1.0 - std::exp(-old / t) / gamma;
+    if (v == "CSA-M" || v == "CSA-MwVC") return std::exp(old / t) / gamma;
+    return gamma / (1.0 + std::exp((e - old) / t));
+  }
+
+  std::pair<GPRegression *, Config> optimize(const Config &initialConfig, const Options &options = {}) {
+    auto landscape = getEnergyLandscape(initialConfig);
+    const double m = std::pow((double)gridsize, (double)initialConfig.size());
+    const double sigmaD = (variant == "CSA-MuSA" || variant == "CSA-BA") ? 0.99 : 0.99 * (m - 1) / (m * m);
+    std::vector<double> probs;
+    {
+      std::vector<double> es;
+      for (auto &kv : landscape) es.push_back(kv.first);
+      const double g0 = couplingFactor(variant, es, iTemp);
+      for (double e : es) probs.push_back(acceptanceProbability(variant, e, e, g0, iTemp));
+    }
+    double accPrev = iTemp;
+    std::cauchy_distribution<double> cauchy(0.0, 1.0);
+    std::uniform_real_distribution<double> unif(0.0, 1.0);
+    for (int it = MAX_ITERATIONS; it >= 1; --it) {
+      const double mutTemp = iTemp / it;
+      double accTemp = iTemp / std::log(it + 1.0);
+      if (variant == "CSA-MwVC") {
+        double mean = 0.0, var = 0.0;
+        for (double p : probs) mean += p / probs.size();
+        for (double p : probs) var += (p - mean) * (p - mean) / (probs.size() - 1);
+        accTemp = var < sigmaD ? accPrev * (1 - alpha) : accPrev * (1 + alpha);
+      }
+      double maxE = -std::numeric_limits<double>::infinity();
+      for (auto &kv : landscape) maxE = std::max(maxE, kv.first);
+      std::vector<double> shifted;
+      for (auto &kv : landscape) shifted.push_back(kv.first - maxE);
+      const double gamma = couplingFactor(variant, shifted, accTemp);
+      std::vector<Config> proposals;
+      for (auto &kv : landscape) {
+        Config c;
+        for (auto &p : kv.second) c[p.first] = std::fabs(p.second + mutTemp * cauchy(rng));  // :112-130
+        proposals.push_back(c);
+      }
+      std::vector<double> e = system.energyBatch(proposals);  // one sweep = one device batch
+      for (size_t i = 0; i < landscape.size(); ++i) {
+        const double p = acceptanceProbability(variant, e[i] - maxE, landscape[i].first - maxE, gamma, accTemp);
+        if (e[i] < landscape[i].first || unif(rng) <= p) landscape[i] = {e[i], proposals[i]};
+        probs[i] = p;
+      }
+      accPrev = accTemp;
+    }
+    std::map<double, Config> as_map;
+    for (auto &kv : landscape) as_map[kv.first] = kv.second;
+    Config best = as_map.begin()->second;
+    auto it = options.find("persist");
+    if (it != options.end() && (it->second == "true" || it->second == "1")) system.persist(best);
+    return {&system, best};
+  }
+
+ private:
+  int MAX_ITERATIONS = 10;
+  std::string variant = "CSA-MuSA";
+  std::mt19937_64 rng;  // the reference's RNGs are unseeded globals; injected here
+};
+
+class GradBasedGlobalOptimizer {
+ public:
+  explicit GradBasedGlobalOptimizer(GPRegression &model) : system(model) {}
+  GPRegression &system;
+  // h <- |h - step * g| until ||g|| < tolerance or maxIterations (GradBasedGlobalOptimizer.scala:37-103)
+  std::pair<GPRegression *, Config> optimize(const Config &initialConfig, double tolerance = 1e-4, double step = 0.005,
+                                             int maxIterations = 50) {
+    Config working = initialConfig;
+    int count = 1;
+    double gradNorm = 1.0;
+    do {
+      Config g = system.gradEnergy(working);
+      gradNorm = 0.0;
+      for (auto &kv : g) gradNorm += kv.second * kv.second;
+      gradNorm = std::sqrt(gradNorm);
+      Config next;
+      auto wi = working.begin();
+      auto gi = g.begin();
+      for (; wi != working.end() && gi != g.end(); ++wi, ++gi) {  // positional zip of the two maps (:69)
+        double gr = gi->second;
+        if (gr == std::numeric_limits<double>::infinity()) gr = 1.0;
+        else if (gr == -std::numeric_limits<double>::infinity()) gr = -1.0;
+        next[wi->first] = std::fabs(wi->second - step * gr);
+      }
+      working = next;
+      ++count;
+    } while (count < maxIterations && gradNorm >= tolerance);
+    return {&system, working};
+  }
+};
+
+}  // namespace dynaml

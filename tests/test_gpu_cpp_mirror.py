@@ -1,0 +1,76 @@
+"""The C++ host-side mirror (include/dynaml_b200.hpp) exercised by tests/cpp/host_mirror_test.cpp -- the
+reference's GPSpec / KernelSpec cases and a seeded synthetic problem through the compiled-language binding
+of the C ABI -- checked here against the oracle."""
+import json
+import math
+import struct
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+BIN = ROOT / "dynaml_b200" / "lib" / "host_mirror_test"
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def result(tmp_path_factory):
+    assert BIN.exists(), "build it with `python -m dynaml_b200.build` (__graft_entry__.build() does)"
+    X, y, Xs = orc.synthetic(400, 4, seed=31, m=25)
+    path = tmp_path_factory.mktemp("cpp") / "problem.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("<qqq", X.shape[0], X.shape[1], Xs.shape[0]))
+        f.write(np.ascontiguousarray(X).tobytes())
+        f.write(np.ascontiguousarray(y).tobytes())
+        f.write(np.ascontiguousarray(Xs).tobytes())
+    r = subprocess.run([str(BIN), str(path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return json.loads(r.stdout), (X, y, Xs)
+
+
+def test_reference_known_answers_through_cpp(result):
+    out, _ = result
+    rho = math.exp(-0.5)
+    assert out["gpspec_likelihood"] - (-math.log(0.15915494309189535)) < 1e-5      # GPSpec.scala:36
+    assert out["gpspec_likelihood"] == pytest.approx(math.log(2 * math.pi), abs=1e-14)
+    assert out["gpspec_pmean"] == pytest.approx(rho, rel=4e-16)                      # GPSpec.scala:68
+    assert out["gpspec_psigma"] == pytest.approx(1.0 - rho * rho, rel=1e-15)
+    assert out["gpspec_lo"] == pytest.approx(rho - math.sqrt(1.0 - rho * rho), abs=1e-15)
+    assert out["gpspec_hi"] == pytest.approx(rho + math.sqrt(1.0 - rho * rho), abs=1e-15)
+    assert abs(out["kernelspec_se"] - 0.6065306597126334) < 1e-15                    # KernelSpec.scala:53
+    assert out["block_unblock_ok"] and out["missing_key_throws"]
+
+
+def test_cpp_model_matches_oracle(result):
+    out, (X, y, Xs) = result
+    k = orc.Kernel("matern", {"p": 2.0, "l": 2.0})
+    assert out["energy"] == pytest.approx(orc.energy(k, 0.3, X, y), rel=TOL)
+    g = orc.grad_energy(k, 0.3, X, y)
+    assert out["grad_keys"] == 2
+    assert out["grad_l"] == pytest.approx(g["l"], rel=TOL) and out["grad_noiseLevel"] == pytest.approx(g["noiseLevel"], rel=TOL)
+    mu, cov = orc.predictive(k, 0.3, X, y, Xs)
+    assert np.abs(np.array(out["mu"]) - mu).max() <= TOL * np.abs(mu).max()
+    got_cov = np.array(out["cov"]).reshape(len(Xs), len(Xs), order="F")
+    assert np.abs(got_cov - cov).max() <= TOL * np.abs(cov).max()
+    lo, hi = orc.error_bars(mu, cov, 2.0)
+    assert np.abs(np.array(out["lo"]) - lo).max() <= 1e-8 * np.abs(lo).max()
+    assert np.abs(np.array(out["hi"]) - hi).max() <= 1e-8 * np.abs(hi).max()
+
+
+def test_cpp_tuners(result):
+    out, (X, y, Xs) = result
+    # grid in sorted key order (std::map): l, noiseLevel
+    grid = orc.get_grid({"l": 2.6, "noiseLevel": 0.9}, 3, 0.2, False)
+    ref = [orc.energy(orc.Kernel("matern", {"p": 2.0, "l": c["l"]}), c["noiseLevel"], X, y) for c in grid]
+    assert np.abs(np.array(out["landscape"]) - np.array(ref)).max() <= TOL * np.abs(ref).max()
+    best = grid[int(np.argmin(ref))]
+    assert out["best_l"] == best["l"] and out["best_noiseLevel"] == best["noiseLevel"]
+    mu, _ = orc.predictive(orc.Kernel("matern", {"p": 2.0, "l": best["l"]}), best["noiseLevel"], X, y, Xs[:1])
+    assert out["persisted_predict0"] == pytest.approx(mu[0], rel=TOL)
+    assert math.isfinite(out["csa_energy"]) and out["csa_energy"] <= max(ref) + 1e-9
+    assert out["nonpd_energy_is_inf"] and out["nonpd_grad_is_nan"]
