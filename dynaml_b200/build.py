@@ -20,6 +20,11 @@ NVCC_FLAGS = [
 ]
 
 
+ASAN = os.environ.get("DGP_ASAN") == "1"  # debug builds: host code under AddressSanitizer
+if ASAN:
+    NVCC_FLAGS += ["-g", "-Xcompiler", "-fsanitize=address", "-Xcompiler", "-fno-omit-frame-pointer"]
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if cand and (cand == "nvcc" or Path(cand).exists()):
@@ -55,6 +60,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         objs = list(ex.map(compile_one, SOURCES))
     if force or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", str(LIB), *map(str, objs), "-ldl"]
+        if ASAN:
+            cmd += ["-Xcompiler", "-fsanitize=address"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
@@ -71,6 +78,8 @@ def build_cpp_mirror_test(force: bool = False) -> Path:
     if src.exists() and (force or _stale(out, deps)):
         cmd = ["g++", "-std=c++17", "-O2", "-I", str(root / "include"), str(src), "-o", str(out),
                "-L", str(LIBDIR), "-ldgp_b200", "-Wl,-rpath,$ORIGIN"]
+        if ASAN:
+            cmd += ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"g++ failed for {src}:\n{r.stdout}\n{r.stderr}")

@@ -9,6 +9,7 @@
 
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/dgp_b200.h"
@@ -35,6 +36,8 @@ struct Ctx {
   cudaEvent_t tev[16];               // phase timing events
   std::string err;
   std::map<std::string, std::pair<void *, size_t>> arena;
+  // GEMM tile tables on the device, keyed by (row tiles, column tiles, lower, bottom_first)
+  std::map<std::tuple<int, int, int, int>, std::pair<uint32_t *, size_t>> tile_tables;
   int64_t nb = 0;     // outer Cholesky block (0 = choose from n)
   int lookahead = 1;
   int gemm_bk = 32;   // K-slice of the GEMM pipeline: 16 (3-4 stages) or 32 (double buffered)

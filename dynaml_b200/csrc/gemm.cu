@@ -262,32 +262,25 @@ struct TileTable {
   size_t count = 0;
 };
 
-static std::map<std::tuple<int, int, int, int>, TileTable> &tables(Ctx *ctx) {
-  // one cache per context, keyed by (row tiles, column tiles, lower, bottom_first)
-  static std::map<Ctx *, std::map<std::tuple<int, int, int, int>, TileTable>> all;
-  return all[ctx];
-}
-
 void gemm_release(Ctx *ctx) {
-  for (auto &kv : tables(ctx)) cudaFree(kv.second.dev);
-  tables(ctx).clear();
+  for (auto &kv : ctx->tile_tables) cudaFree(kv.second.first);
+  ctx->tile_tables.clear();
 }
 
 static int32_t get_tiles(Ctx *ctx, int mt, int nt, bool lower, bool bottom_first, TileTable *out) {
   auto key = std::make_tuple(mt, nt, (int)lower, (int)bottom_first);
-  auto &tb = tables(ctx);
-  auto it = tb.find(key);
-  if (it == tb.end()) {
+  auto it = ctx->tile_tables.find(key);
+  if (it == ctx->tile_tables.end()) {
     std::vector<uint32_t> host;
     build_tiles(mt, nt, lower, bottom_first, host);
-    TileTable t;
-    t.count = host.size();
-    DGP_CUDA_OK(ctx, cudaMalloc(&t.dev, std::max<size_t>(1, host.size()) * sizeof(uint32_t)));
+    uint32_t *dev = nullptr;
+    DGP_CUDA_OK(ctx, cudaMalloc(&dev, std::max<size_t>(1, host.size()) * sizeof(uint32_t)));
     // synchronous copy: the table may be consumed from either stream right away
-    DGP_CUDA_OK(ctx, cudaMemcpy(t.dev, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    it = tb.emplace(key, t).first;
+    DGP_CUDA_OK(ctx, cudaMemcpy(dev, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    it = ctx->tile_tables.emplace(key, std::make_pair(dev, host.size())).first;
   }
-  *out = it->second;
+  out->dev = it->second.first;
+  out->count = it->second.second;
   return DGP_OK;
 }
 
