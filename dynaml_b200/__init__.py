@@ -7,8 +7,9 @@ library or an sm_100 device is missing (there is no CPU fallback).
 """
 from . import _capi
 from ._capi import Context, DgpError, NotPositiveDefinite, default_context
-from .kernels import (AdditiveCovariance, DiracKernel, GenericMaternKernel, LocalScalarKernel, MahalanobisKernel,
-                      PeriodicKernel, RBFKernel, SEKernel, SVMKernelMatrix)
+from .kernels import (AdditiveCovariance, CauchyKernel, DiracKernel, GenericMaternKernel, LaplacianKernel,
+                      LocalScalarKernel, MahalanobisKernel, PeriodicKernel, RationalQuadraticKernel, RBFKernel,
+                      SEKernel, SVMKernelMatrix, TStudentKernel)
 from .models import AbstractGPRegressionModel, CudaGPRegression, GPRegression, MultGaussianPRV
 from .optimization import CoupledSimulatedAnnealing, GradBasedGlobalOptimizer, GridSearch, ModelTuner
 
@@ -16,6 +17,7 @@ __all__ = [
     "Context", "DgpError", "NotPositiveDefinite", "default_context",
     "LocalScalarKernel", "SEKernel", "RBFKernel", "MahalanobisKernel", "GenericMaternKernel", "PeriodicKernel",
     "DiracKernel", "AdditiveCovariance", "SVMKernelMatrix",
+    "CauchyKernel", "LaplacianKernel", "RationalQuadraticKernel", "TStudentKernel",
     "GPRegression", "CudaGPRegression", "AbstractGPRegressionModel", "MultGaussianPRV",
     "GridSearch", "CoupledSimulatedAnnealing", "GradBasedGlobalOptimizer", "ModelTuner",
 ]

@@ -18,6 +18,7 @@ DGP_OK, DGP_ERR_NOT_PD, DGP_ERR_UNSUPPORTED_KERNEL, DGP_ERR_SHAPE = 0, 1, 2, 3
 DGP_ERR_CUDA, DGP_ERR_NCCL, DGP_ERR_OOM, DGP_ERR_ARG = 4, 5, 6, 7
 DGP_ROW_MAJOR, DGP_COL_MAJOR = 0, 1
 KERNEL_SE, KERNEL_RBF, KERNEL_ARD_SE, KERNEL_MATERN, KERNEL_PERIODIC, KERNEL_DIRAC = range(6)
+KERNEL_CAUCHY, KERNEL_LAPLACIAN, KERNEL_RATQUAD, KERNEL_TSTUDENT = 6, 7, 8, 9
 GRAD_REFERENCE, GRAD_EXACT = 0, 1
 
 _STATUS_NAMES = {

@@ -74,6 +74,10 @@ int32_t parse_spec(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
     case DGP_KERNEL_MATERN: want = 2; break;
     case DGP_KERNEL_PERIODIC: want = 3; break;
     case DGP_KERNEL_DIRAC: want = 1; break;
+    case DGP_KERNEL_CAUCHY: want = 1; break;
+    case DGP_KERNEL_LAPLACIAN: want = 1; break;
+    case DGP_KERNEL_RATQUAD: want = 2; break;
+    case DGP_KERNEL_TSTUDENT: want = 1; break;
     default: return ctx->fail(DGP_ERR_UNSUPPORTED_KERNEL, "unsupported kernel kind %d", in->kind);
   }
   if (in->n_hyp != want || want > DGP_MAX_HYP)
@@ -238,7 +242,7 @@ int32_t enqueue_eval(Ctx *ctx, int slot, const Data *D, const Spec &sp, bool wan
   DGP_BUF(x, double, ctx, nm[2], (size_t)np * sizeof(double));
   const double *Xk = nullptr;
   DGP_TRY(scaled_points(ctx, S, sp, D->X, np, D->dp, D->d, nm[3], &Xk));
-  CovParams cp = make_cov_params(sp, true);
+  CovParams cp = make_cov_params(sp, true, D->d);
 
   tick(ctx, slot, 0);
   AssembleArgs a;
@@ -599,7 +603,7 @@ int32_t dgp_fit(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *spec, dg
   } else {
     m->Xk = m->X;
   }
-  CovParams cp = make_cov_params(sp, true);
+  CovParams cp = make_cov_params(sp, true, D->d);
   DGP_BUF(d_scal, double, ctx, "scal", 4096 * 160 * sizeof(double));
   tick(ctx, 0, 0);
   AssembleArgs a;
@@ -667,7 +671,7 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
   DGP_TRY(scaled_points(ctx, S, m->spec, Xt, mp, dp, m->d, "Xts", &Xtk));
 
   // K* = k(X, X*) : no noise (AbstractGPRegressionModel.scala:279-286)
-  CovParams cpx = make_cov_params(m->spec, false);
+  CovParams cpx = make_cov_params(m->spec, false, m->d);
   const int gram = pick_gram(ctx, m->spec, cpx, dp, m->d, nmax);
   tick(ctx, 0, 0);
   {
@@ -779,7 +783,7 @@ int32_t dgp_kernel_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec, const doubl
   if (sym) B2 = B1;
   else DGP_TRY(scaled_points(ctx, S, sp, A2, n2p, dp, d, "km_x2s", &B2));
   DGP_BUF(Kd, double, ctx, "km_out", (size_t)n1p * n2p * sizeof(double));
-  CovParams cp = make_cov_params(sp, sym && add_noise);
+  CovParams cp = make_cov_params(sp, sym && add_noise, d);
   AssembleArgs a;
   a.X1 = B1;  a.X2 = B2;  a.dp = dp;
   a.rows = N1;  a.cols = N2;  a.rows_p = n1p;  a.cols_p = n2p;
@@ -828,7 +832,7 @@ int32_t dgp_time_phase(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *s
   DGP_BUF(inv, double, ctx, "inv", (size_t)np * TILE * sizeof(double));
   const double *Xk = nullptr;
   DGP_TRY(scaled_points(ctx, S, sp, D->X, np, D->dp, D->d, "Xs", &Xk));
-  CovParams cp = make_cov_params(sp, true);
+  CovParams cp = make_cov_params(sp, true, D->d);
   AssembleArgs a;
   a.X1 = Xk;  a.X2 = Xk;  a.dp = D->dp;
   a.rows = D->N;  a.cols = D->N;  a.rows_p = np;  a.cols_p = np;

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(CovParams cp, Assemb
         double2 v = y[c];
         double e0 = x0[2 * c] - v.x, e1 = x0[2 * c + 1] - v.y;
         double f0 = x1[2 * c] - v.x, f1 = x1[2 * c + 1] - v.y;
-        if (KIND == DGP_KERNEL_PERIODIC) {
+        if (kind_is_l1(KIND)) {
           d0 += fabs(e0) + fabs(e1);
           d1 += fabs(f0) + fabs(f1);
         } else {
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(CovParams cp, Assemb
       for (int c = 0; c < dp; ++c) {
         double v = y[c];
         double e0 = p0[c] - v, f0 = p1[c] - v;
-        if (KIND == DGP_KERNEL_PERIODIC) {
+        if (kind_is_l1(KIND)) {
           d0 += fabs(e0);
           d1 += fabs(f0);
         } else {
@@ -493,6 +493,10 @@ int32_t assemble(Ctx *ctx, cudaStream_t st, const CovParams &cp, const AssembleA
     case DGP_KERNEL_MATERN: launch_kind<DGP_KERNEL_MATERN>(st, cp, a, (unsigned)tiles); break;
     case DGP_KERNEL_PERIODIC: launch_kind<DGP_KERNEL_PERIODIC>(st, cp, a, (unsigned)tiles); break;
     case DGP_KERNEL_DIRAC: launch_kind<DGP_KERNEL_DIRAC>(st, cp, a, (unsigned)tiles); break;
+    case DGP_KERNEL_CAUCHY: launch_kind<DGP_KERNEL_CAUCHY>(st, cp, a, (unsigned)tiles); break;
+    case DGP_KERNEL_LAPLACIAN: launch_kind<DGP_KERNEL_LAPLACIAN>(st, cp, a, (unsigned)tiles); break;
+    case DGP_KERNEL_RATQUAD: launch_kind<DGP_KERNEL_RATQUAD>(st, cp, a, (unsigned)tiles); break;
+    case DGP_KERNEL_TSTUDENT: launch_kind<DGP_KERNEL_TSTUDENT>(st, cp, a, (unsigned)tiles); break;
     default: return ctx->fail(DGP_ERR_UNSUPPORTED_KERNEL, "assemble: kernel kind %d", cp.kind);
   }
   ctx->launches++;

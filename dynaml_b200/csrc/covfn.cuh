@@ -41,10 +41,27 @@ __device__ __forceinline__ double cov_value(const CovParams &cp, double dist) {
     // PeriodicKernel.scala:34-46:  sigma^2 exp(-2 sin^2(pi f |x-y|_1) / l^2)
     double sn = sin(dist * cp.c1);
     return cp.a2 * exp(-cp.c2 * sn * sn);
+  } else if (KIND == DGP_KERNEL_CAUCHY) {
+    // CauchyKernel.scala: 1/(1 + (|x-y|/sigma)^2)
+    return 1.0 / fma(dist, cp.c1, 1.0);
+  } else if (KIND == DGP_KERNEL_LAPLACIAN) {
+    // LaplacianKernel.scala: exp(-|x-y|_1 / beta)
+    return exp(-dist * cp.c1);
+  } else if (KIND == DGP_KERNEL_RATQUAD) {
+    // RationalQuadraticKernel.scala: (1 + |x-y|^2/(mu l^2))^(-(d + mu)/2)
+    return pow(fma(dist, cp.c1, 1.0), cp.c2);
+  } else if (KIND == DGP_KERNEL_TSTUDENT) {
+    // TStudentKernel.scala: 1/(1 + |x-y|^d)
+    return 1.0 / (1.0 + pow(sqrt(dist), cp.c1));
   } else {
     // DiracKernel.scala:43-47
     return dist == 0.0 ? cp.a2 : 0.0;
   }
+}
+
+// Kinds whose distance is |x-y|_1 instead of |x-y|_2^2.
+__host__ __device__ constexpr bool kind_is_l1(int kind) {
+  return kind == DGP_KERNEL_PERIODIC || kind == DGP_KERNEL_LAPLACIAN;
 }
 
 // Runtime-dispatched variant for the cold paths.
@@ -55,12 +72,16 @@ __device__ __forceinline__ double cov_value_rt(const CovParams &cp, double dist)
     case DGP_KERNEL_ARD_SE: return cov_value<DGP_KERNEL_SE>(cp, dist);
     case DGP_KERNEL_MATERN: return cov_value<DGP_KERNEL_MATERN>(cp, dist);
     case DGP_KERNEL_PERIODIC: return cov_value<DGP_KERNEL_PERIODIC>(cp, dist);
+    case DGP_KERNEL_CAUCHY: return cov_value<DGP_KERNEL_CAUCHY>(cp, dist);
+    case DGP_KERNEL_LAPLACIAN: return cov_value<DGP_KERNEL_LAPLACIAN>(cp, dist);
+    case DGP_KERNEL_RATQUAD: return cov_value<DGP_KERNEL_RATQUAD>(cp, dist);
+    case DGP_KERNEL_TSTUDENT: return cov_value<DGP_KERNEL_TSTUDENT>(cp, dist);
     default: return cov_value<DGP_KERNEL_DIRAC>(cp, dist);
   }
 }
 
 // Host: fold a Spec into CovParams.  `noise` < 0 is legal (the reference takes abs()).
-inline CovParams make_cov_params(const Spec &s, bool with_noise) {
+inline CovParams make_cov_params(const Spec &s, bool with_noise, int d = 0) {
   CovParams cp;
   cp.kind = s.kind;
   cp.grad_mode = s.grad_mode;
@@ -100,6 +121,21 @@ inline CovParams make_cov_params(const Spec &s, bool with_noise) {
       break;
     case DGP_KERNEL_DIRAC:
       cp.a2 = fabs(s.hyp[0]);
+      break;
+    case DGP_KERNEL_CAUCHY:
+      cp.c1 = 1.0 / (s.hyp[0] * s.hyp[0]);
+      break;
+    case DGP_KERNEL_LAPLACIAN:
+      cp.l1 = 1;
+      cp.c1 = 1.0 / s.hyp[0];
+      break;
+    case DGP_KERNEL_RATQUAD:  // hyp = [mu, l]; the exponent uses the feature count x.length
+      cp.c1 = 1.0 / (s.hyp[0] * s.hyp[1] * s.hyp[1]);
+      cp.c2 = -0.5 * ((double)d + s.hyp[0]);
+      cp.c3 = 1.0 / ((s.hyp[0] * s.hyp[1]) * (s.hyp[0] * s.hyp[1]));
+      break;
+    case DGP_KERNEL_TSTUDENT:
+      cp.c1 = s.hyp[0];
       break;
   }
   return cp;

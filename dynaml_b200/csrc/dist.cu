@@ -368,7 +368,7 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *
   }
   const double *Xk = nullptr;
   DGP_TRY(scaled_points_pub(ctx, S, sp, Xin, Ntot, D->dp, D->d, "dist_Xs", &Xk));
-  CovParams cp = make_cov_params(sp, true);
+  CovParams cp = make_cov_params(sp, true, D->d);
 
   // ---- per-rank buffers ------------------------------------------------------------------------------
   std::vector<RankBuf> ranks(nranks);

@@ -18,13 +18,14 @@ namespace {
 constexpr int GT = 128;
 constexpr int GTHREADS = 256;
 
-enum Mode { M_SE = 0, M_ARD_REF = 1, M_ARD_EXACT = 2, M_MATERN = 3, M_PERIODIC = 4, M_DIRAC = 5 };
+enum Mode { M_SE = 0, M_ARD_REF = 1, M_ARD_EXACT = 2, M_MATERN = 3, M_PERIODIC = 4, M_DIRAC = 5, M_CAUCHY = 6,
+            M_LAPLACIAN = 7, M_RATQUAD = 8, M_TSTUDENT = 9 };
 
 template <int MODE, int DP>
 struct NSums {
   // [last] is always the noise moment sum M_ij 1[|x_i - x_j| == 0]
   static constexpr int value = (MODE == M_SE) ? 3 : (MODE == M_ARD_REF) ? 3 : (MODE == M_ARD_EXACT) ? (DP + 2)
-                               : (MODE == M_MATERN) ? 2 : (MODE == M_PERIODIC) ? 3 : 2;
+                               : (MODE == M_MATERN) ? 2 : (MODE == M_PERIODIC) ? 3 : (MODE == M_RATQUAD) ? 3 : 2;
 };
 
 // Per-pair contribution.  `dist` is |x-y|^2 (for ARD: of the pre-scaled inputs), `plain2` the
@@ -70,6 +71,28 @@ __device__ __forceinline__ void accumulate(const CovParams &cp, double m, double
     double kap = cp.c3 * dist;
     s[0] = fma(m, k, s[0]);
     s[1] = fma(m * k, sin(2.0 * kap) * kap, s[1]);
+  } else if (MODE == M_CAUCHY) {
+    // CauchyKernel.scala: d/dsigma = 2 k^2 |x-y|^2 / sigma^3
+    double k = 1.0 / fma(dist, cp.c1, 1.0);
+    s[0] = fma(m * k * k, dist, s[0]);
+  } else if (MODE == M_LAPLACIAN) {
+    // LaplacianKernel.scala: d/dbeta = k |x-y|_1 / beta^2
+    double k = exp(-dist * cp.c1);
+    s[0] = fma(m * k, dist, s[0]);
+  } else if (MODE == M_RATQUAD) {
+    // RationalQuadraticKernel.scala: grad_l = -2 e r^2 base^(e-1) / (mu l^3);
+    //                                grad_mu = k * ( -e r^2 / (base (mu l)^2) - 0.5 log(base) )
+    double base = fma(dist, cp.c1, 1.0);
+    double k = pow(base, cp.c2);
+    s[0] = fma(m * dist, k / base, s[0]);
+    s[1] = fma(m * k, -cp.c2 * dist * cp.c3 / base - 0.5 * log(base), s[1]);
+  } else if (MODE == M_TSTUDENT) {
+    // TStudentKernel.scala: d/dd = -r^d log(r) / (1 + r^d)^2 for r > 0, else 0
+    if (dist > 0.0) {
+      double r = sqrt(dist);
+      double rd = pow(r, cp.c1);
+      s[0] = fma(m, -rd * log(r) / ((1.0 + rd) * (1.0 + rd)), s[0]);
+    }
   } else {
     // DiracKernel.scala:49-53: value / |s|
     if (dist == 0.0) s[0] += m;
@@ -142,7 +165,7 @@ __global__ void __launch_bounds__(GTHREADS) grad_trace_kernel(CovParams cp, Grad
     for (int c = 0; c < DP; ++c) {
       const double y = sx[j * DP + c];
       const double e0 = x0[c] - y, e1 = x1[c] - y;
-      if (MODE == M_PERIODIC) {
+      if (MODE == M_PERIODIC || MODE == M_LAPLACIAN) {
         d0 += fabs(e0);
         d1 += fabs(e1);
       } else if (ARD) {
@@ -244,6 +267,10 @@ int mode_of(const CovParams &cp) {
     case DGP_KERNEL_ARD_SE: return cp.grad_mode == DGP_GRAD_EXACT ? M_ARD_EXACT : M_ARD_REF;
     case DGP_KERNEL_MATERN: return M_MATERN;
     case DGP_KERNEL_PERIODIC: return M_PERIODIC;
+    case DGP_KERNEL_CAUCHY: return M_CAUCHY;
+    case DGP_KERNEL_LAPLACIAN: return M_LAPLACIAN;
+    case DGP_KERNEL_RATQUAD: return M_RATQUAD;
+    case DGP_KERNEL_TSTUDENT: return M_TSTUDENT;
     default: return M_DIRAC;
   }
 }
@@ -254,7 +281,10 @@ int grad_partials_per_tile(const CovParams &cp, int dp) {
   switch (mode_of(cp)) {
     case M_ARD_EXACT: return dp + 2;
     case M_MATERN:
-    case M_DIRAC: return 2;
+    case M_DIRAC:
+    case M_CAUCHY:
+    case M_LAPLACIAN:
+    case M_TSTUDENT: return 2;
     default: return 3;
   }
 }
@@ -268,6 +298,10 @@ int32_t grad_trace(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArg
     case M_ARD_EXACT: return launch_dp<M_ARD_EXACT>(ctx, st, cp, a, tiles, ns);
     case M_MATERN: return launch_dp<M_MATERN>(ctx, st, cp, a, tiles, ns);
     case M_PERIODIC: return launch_dp<M_PERIODIC>(ctx, st, cp, a, tiles, ns);
+    case M_CAUCHY: return launch_dp<M_CAUCHY>(ctx, st, cp, a, tiles, ns);
+    case M_LAPLACIAN: return launch_dp<M_LAPLACIAN>(ctx, st, cp, a, tiles, ns);
+    case M_RATQUAD: return launch_dp<M_RATQUAD>(ctx, st, cp, a, tiles, ns);
+    case M_TSTUDENT: return launch_dp<M_TSTUDENT>(ctx, st, cp, a, tiles, ns);
     default: return launch_dp<M_DIRAC>(ctx, st, cp, a, tiles, ns);
   }
 }
@@ -312,6 +346,24 @@ void grad_finish(const Spec &sp, int d, const double *S, int ns, double *g) {
     }
     case DGP_KERNEL_DIRAC:
       g[0] = (sp.hyp[0] == 0.0) ? qnan : S[0];  // |s| 1[..] / |s|
+      break;
+    case DGP_KERNEL_CAUCHY: {
+      double sg = sp.hyp[0];
+      g[0] = 2.0 * S[0] / (sg * sg * sg);
+      break;
+    }
+    case DGP_KERNEL_LAPLACIAN:
+      g[0] = S[0] / (sp.hyp[0] * sp.hyp[0]);
+      break;
+    case DGP_KERNEL_RATQUAD: {
+      double mu = sp.hyp[0], l = sp.hyp[1];
+      double e = -0.5 * ((double)d + mu);
+      g[0] = S[1];
+      g[1] = -2.0 * e * S[0] / (mu * l * l * l);
+      break;
+    }
+    case DGP_KERNEL_TSTUDENT:
+      g[0] = S[0];
       break;
   }
   g[sp.n_hyp] = (sp.noise == 0.0) ? qnan : noise_m;

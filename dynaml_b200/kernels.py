@@ -13,7 +13,8 @@ Same names, argument meaning and error behaviour as the reference classes
 
 The classes only carry hyper-parameter state; every number is produced by the CUDA library
 through the C ABI (dynaml_b200._capi).  Kernels the device path does not implement raise
-NotImplementedError -- there is no CPU fallback.
+NotImplementedError -- there is no CPU fallback.  CauchyKernel, LaplacianKernel, RationalQuadraticKernel
+and TStudentKernel ride the same builders as extra assembly epilogues.
 """
 from __future__ import annotations
 
@@ -89,7 +90,8 @@ class LocalScalarKernel:
     def _device_kind(self) -> int:
         raise NotImplementedError(
             f"{type(self).__name__} has no sm_100a implementation (supported: SEKernel, RBFKernel, "
-            "MahalanobisKernel, GenericMaternKernel, PeriodicKernel, DiracKernel); no CPU fallback")
+            "MahalanobisKernel, GenericMaternKernel, PeriodicKernel, DiracKernel, CauchyKernel, LaplacianKernel, "
+            "RationalQuadraticKernel, TStudentKernel); no CPU fallback")
 
     def _device_hyp(self, config: Dict[str, float]) -> List[float]:
         return [float(config[h]) for h in self.hyper_parameters]
@@ -194,6 +196,70 @@ class PeriodicKernel(LocalScalarKernel):
 
     def _device_kind(self):
         return _capi.KERNEL_PERIODIC
+
+
+class CauchyKernel(LocalScalarKernel):
+    """CORE/kernels/CauchyKernel.scala: 1 / (1 + (|x-y|_2 / sigma)^2)."""
+    hyper_parameters = ["sigma"]
+
+    def __init__(self, si: float = 1.0):
+        super().__init__()
+        self.state = {"sigma": float(si)}
+
+    def setsigma(self, b: float) -> None:
+        self.state["sigma"] = float(b)
+
+    def _device_kind(self):
+        return _capi.KERNEL_CAUCHY
+
+
+class LaplacianKernel(LocalScalarKernel):
+    """CORE/kernels/LaplacianKernel.scala: exp(-|x-y|_1 / beta)."""
+    hyper_parameters = ["beta"]
+
+    def __init__(self, be: float = 1.0):
+        super().__init__()
+        self.state = {"beta": float(be)}
+
+    def setbeta(self, b: float) -> None:
+        self.state["beta"] = float(b)
+
+    def _device_kind(self):
+        return _capi.KERNEL_LAPLACIAN
+
+
+class RationalQuadraticKernel(LocalScalarKernel):
+    """CORE/kernels/RationalQuadraticKernel.scala: (1 + |x-y|^2 / (mu l^2))^(-(d + mu)/2)."""
+    hyper_parameters = ["mu", "l"]
+
+    def __init__(self, shape: float = 1.0, l: float = 1.0):
+        super().__init__()
+        self.state = {"mu": float(shape), "l": float(l)}
+
+    def setShape(self, b: float) -> None:
+        self.state["mu"] = float(b)
+
+    def setScale(self, lam: float) -> None:
+        self.state["l"] = float(lam)
+
+    def _device_kind(self):
+        return _capi.KERNEL_RATQUAD
+
+
+class TStudentKernel(LocalScalarKernel):
+    """CORE/kernels/TStudentKernel.scala: 1 / (1 + |x-y|_2^d)."""
+    hyper_parameters = ["d"]
+
+    def __init__(self, degree: float = 1.0):
+        super().__init__()
+        self.state = {"d": float(degree)}
+
+    @property
+    def d(self) -> float:
+        return self.state["d"]
+
+    def _device_kind(self):
+        return _capi.KERNEL_TSTUDENT
 
 
 class DiracKernel(LocalScalarKernel):

@@ -61,8 +61,17 @@ enum {
                               hyp = [p, l]; half-integer order nu = p + 1/2, 0 <= p <= 8         */
   DGP_KERNEL_PERIODIC = 4, /* PeriodicKernel      CORE/kernels/PeriodicKernel.scala:11-68
                               hyp = [sigma, lengthscale, frequency]; uses the L1 norm            */
-  DGP_KERNEL_DIRAC = 5     /* DiracKernel         CORE/kernels/DiracKernel.scala:30-60
+  DGP_KERNEL_DIRAC = 5,    /* DiracKernel         CORE/kernels/DiracKernel.scala:30-60
                               hyp = [noiseLevel]; k = |s| * 1[|x-y|_2 == 0]                      */
+  /* further stationary kernels of the same builder API, as assembly epilogues */
+  DGP_KERNEL_CAUCHY = 6,   /* CauchyKernel        CORE/kernels/CauchyKernel.scala
+                              hyp = [sigma]; k = 1 / (1 + |x-y|^2 / sigma^2)                     */
+  DGP_KERNEL_LAPLACIAN = 7,/* LaplacianKernel     CORE/kernels/LaplacianKernel.scala
+                              hyp = [beta]; k = exp(-|x-y|_1 / beta)   (L1 norm)                 */
+  DGP_KERNEL_RATQUAD = 8,  /* RationalQuadraticKernel CORE/kernels/RationalQuadraticKernel.scala
+                              hyp = [mu, l]; k = (1 + |x-y|^2/(mu l^2))^(-(d+mu)/2)              */
+  DGP_KERNEL_TSTUDENT = 9  /* TStudentKernel      CORE/kernels/TStudentKernel.scala
+                              hyp = [d]; k = 1 / (1 + |x-y|^d)                                   */
 };
 
 /* Gradient conventions for hyper-parameters whose reference derivative is defective. */

@@ -87,6 +87,14 @@ class Kernel:
             return ["sigma", "lengthscale", "frequency"]
         if self.kind == "dirac":
             return ["noiseLevel"]
+        if self.kind == "cauchy":
+            return ["sigma"]
+        if self.kind == "laplacian":
+            return ["beta"]
+        if self.kind == "ratquad":
+            return ["mu", "l"]
+        if self.kind == "tstudent":
+            return ["d"]
         raise ValueError(self.kind)
 
     def value(self, X: np.ndarray, Y: np.ndarray) -> np.ndarray:
@@ -111,6 +119,19 @@ class Kernel:
         if self.kind == "dirac":
             # DiracKernel.scala:43-47: norm(x-y, 2) == 0
             return np.where(np.sqrt(_sqdist(X, Y)) == 0, abs(h["noiseLevel"]) * 1.0, 0.0)
+        if self.kind == "cauchy":
+            # CauchyKernel.scala evalAt: 1/(1 + pow(norm(x,2)/sigma, 2))
+            return 1 / (1 + np.power(np.sqrt(_sqdist(X, Y)) / h["sigma"], 2))
+        if self.kind == "laplacian":
+            # LaplacianKernel.scala evalAt: exp(-1.0*norm(x,1)/beta)
+            return np.exp(-1.0 * _l1dist(X, Y) / h["beta"])
+        if self.kind == "ratquad":
+            # RationalQuadraticKernel.scala evalAt: pow(1 + norm^2/(mu*l*l), -0.5*(x.length+mu))
+            return np.power(1 + np.power(np.sqrt(_sqdist(X, Y)), 2) / (h["mu"] * h["l"] * h["l"]),
+                            -0.5 * (X.shape[1] + h["mu"]))
+        if self.kind == "tstudent":
+            # TStudentKernel.scala evalAt: 1.0/(1.0 + pow(norm(x,2), d))
+            return 1.0 / (1.0 + np.power(np.sqrt(_sqdist(X, Y)), h["d"]))
         raise ValueError(self.kind)
 
     def _matern(self, r: np.ndarray):
@@ -166,6 +187,24 @@ class Kernel:
         if self.kind == "dirac":
             with np.errstate(invalid="ignore", divide="ignore"):
                 return {"noiseLevel": 1.0 * self.value(X, Y) / abs(h["noiseLevel"])}  # :49-53
+        if self.kind == "cauchy":
+            nrm = np.sqrt(_sqdist(X, Y))
+            return {"sigma": 2.0 * np.power(self.value(X, Y), 2) * np.power(nrm, 2) / math.pow(h["sigma"], 3)}
+        if self.kind == "laplacian":
+            return {"beta": 1.0 * self.value(X, Y) * _l1dist(X, Y) / math.pow(h["beta"], 2.0)}
+        if self.kind == "ratquad":
+            n2 = np.power(np.sqrt(_sqdist(X, Y)), 2)
+            base = 1 + n2 / (h["mu"] * h["l"] * h["l"])
+            exponent = -0.5 * (X.shape[1] + h["mu"])
+            grad_l = -2.0 * exponent * n2 * np.power(base, exponent - 1.0) / (h["mu"] * math.pow(h["l"], 3.0))
+            grad_mu = -1.0 * exponent * np.power(base, -1.0) * n2 / math.pow(h["mu"] * h["l"], 2.0) - 0.5 * np.log(base)
+            return {"l": grad_l, "mu": self.value(X, Y) * grad_mu}
+        if self.kind == "tstudent":
+            dist = np.sqrt(_sqdist(X, Y))
+            with np.errstate(invalid="ignore", divide="ignore"):
+                dist_d = np.power(dist, h["d"])
+                g = -dist_d * np.log(dist) / np.power(1.0 + dist_d, 2.0)
+            return {"d": np.where(dist > 0.0, g, 0.0)}
         raise ValueError(self.kind)
 
     def effective(self, blocked: Sequence[str] = ()) -> List[str]:

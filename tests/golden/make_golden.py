@@ -62,6 +62,11 @@ def synthetic():
         "matern2": orc.Kernel("matern", {"p": 2.0, "l": 2.2}),
         "matern3": orc.Kernel("matern", {"p": 3.0, "l": 2.2}),
         "periodic": orc.Kernel("periodic", {"sigma": 1.3, "lengthscale": 1.4, "frequency": 0.07}),
+        # SURVEY 8(f) rank 1
+        "cauchy": orc.Kernel("cauchy", {"sigma": 2.3}),
+        "laplacian": orc.Kernel("laplacian", {"beta": 3.1}),
+        "ratquad": orc.Kernel("ratquad", {"mu": 1.5, "l": 1.9}),
+        "tstudent": orc.Kernel("tstudent", {"d": 1.6}),
     }
     noise = 0.25
     out["noise"] = noise
@@ -93,6 +98,8 @@ def kats():
         "se_value_1_0": {"value": 0.6065306597126334, "eps": 1e-5,
                          "ref": "dynaml-core/src/test/scala/io/github/tailhq/dynaml/kernels/KernelSpec.scala:34-58"},
         "builder_eval2_offdiag": {"value": 0.5, "ref": "KernelSpec.scala:181-231"},
+        "laplace_value_1_0": {"value": 0.36787944117144233, "eps": 1e-5, "ref": "KernelSpec.scala:34-58"},
+        "cauchy_value_1_1p5": {"value": 0.8, "eps": 1e-5, "ref": "KernelSpec.scala:34-58"},
         "bcholesky_diag_tol": {"value": 1e-6,
                                "ref": "dynaml-core/src/test/scala/io/github/tailhq/dynaml/algebra/PartitionedLinearAlgebraSpec.scala:14-46"},
     }

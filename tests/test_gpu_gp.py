@@ -48,10 +48,19 @@ def make_pair(name, d, band=None):
     if name == "periodic":
         return dg.PeriodicKernel(1.3, 1.4, 0.07), orc.Kernel("periodic",
                                                              {"sigma": 1.3, "lengthscale": 1.4, "frequency": 0.07})
+    if name == "cauchy":
+        return dg.CauchyKernel(2.3), orc.Kernel("cauchy", {"sigma": 2.3})
+    if name == "laplacian":
+        return dg.LaplacianKernel(3.1), orc.Kernel("laplacian", {"beta": 3.1})
+    if name == "ratquad":
+        return dg.RationalQuadraticKernel(1.5, 1.9), orc.Kernel("ratquad", {"mu": 1.5, "l": 1.9})
+    if name == "tstudent":
+        return dg.TStudentKernel(1.6), orc.Kernel("tstudent", {"d": 1.6})
     raise ValueError(name)
 
 
-ALL = ["se", "rbf", "ard_ref", "ard_exact", "matern1", "matern2", "matern3", "periodic"]
+ALL = ["se", "rbf", "ard_ref", "ard_exact", "matern1", "matern2", "matern3", "periodic",
+       "cauchy", "laplacian", "ratquad", "tstudent"]
 
 
 # ---- the reference's own known-answer tests, through the mirrored API --------------------------
@@ -82,6 +91,8 @@ def test_gpspec_posterior_and_error_bars():
 def test_kernelspec_se_value():
     # KernelSpec.scala:34-58
     assert abs(dg.SEKernel(1.0, 1.0).evaluate([1.0], [0.0]) - 0.6065306597126334) < 1e-15
+    assert abs(dg.LaplacianKernel(1.0).evaluate([1.0], [0.0]) - 0.36787944117144233) < 1e-15
+    assert abs(dg.CauchyKernel(1.0).evaluate([1.0], [1.5]) - 0.8) < 1e-15
 
 
 # ---- kernel matrices ------------------------------------------------------------------------------

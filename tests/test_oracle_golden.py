@@ -40,6 +40,14 @@ def test_kernelspec_se_value():
     assert abs(v - KATS["se_value_1_0"]["value"]) < KATS["se_value_1_0"]["eps"]
 
 
+def test_kernelspec_laplace_and_cauchy_values():
+    # KernelSpec.scala:34-58: laplaceKernel(be=1)(1, 0) and cauchyKernel(1.0)(1, 1.5)
+    lap = orc.Kernel("laplacian", {"beta": 1.0}).value(np.array([[1.0]]), np.array([[0.0]]))[0, 0]
+    cau = orc.Kernel("cauchy", {"sigma": 1.0}).value(np.array([[1.0]]), np.array([[1.5]]))[0, 0]
+    assert abs(lap - KATS["laplace_value_1_0"]["value"]) < KATS["laplace_value_1_0"]["eps"]
+    assert abs(cau - KATS["cauchy_value_1_1p5"]["value"]) < KATS["cauchy_value_1_1p5"]["eps"]
+
+
 def test_kernelspec_builders_layout():
     # KernelSpec.scala:181-231: eval2(x,y) = 1/(1+(x-y)^2) on the points 0,1 -> [[1,.5],[.5,1]], cross with {0} -> [1,.5]
     class Eval2(orc.Kernel):
@@ -88,6 +96,10 @@ def test_blocked_equals_dense():
     ("matern", {"p": 1.0, "l": 1.4}),
     ("matern", {"p": 2.0, "l": 1.4}),
     ("matern", {"p": 3.0, "l": 1.4}),
+    ("cauchy", {"sigma": 1.7}),
+    ("laplacian", {"beta": 2.2}),
+    ("ratquad", {"mu": 1.5, "l": 1.3}),
+    ("tstudent", {"d": 1.6}),
 ])
 def test_gradient_formulas_match_finite_differences(kind, hyp):
     """gradEnergy returns tr((aa' - K^-1) dK) = -2 d/dtheta of the *textbook* NLL."""
