@@ -11,6 +11,7 @@ from .kernels import (AdditiveCovariance, CauchyKernel, DiracKernel, GenericMate
                       LocalScalarKernel, MahalanobisKernel, PeriodicKernel, RationalQuadraticKernel, RBFKernel,
                       SEKernel, SVMKernelMatrix, TStudentKernel)
 from .models import AbstractGPRegressionModel, CudaGPRegression, GPRegression, MultGaussianPRV
+from .stp import AbstractSTPRegressionModel, MultStudentsTPRV, STPRegression
 from .optimization import CoupledSimulatedAnnealing, GradBasedGlobalOptimizer, GridSearch, ModelTuner
 
 __all__ = [
@@ -19,5 +20,6 @@ __all__ = [
     "DiracKernel", "AdditiveCovariance", "SVMKernelMatrix",
     "CauchyKernel", "LaplacianKernel", "RationalQuadraticKernel", "TStudentKernel",
     "GPRegression", "CudaGPRegression", "AbstractGPRegressionModel", "MultGaussianPRV",
+    "STPRegression", "AbstractSTPRegressionModel", "MultStudentsTPRV",
     "GridSearch", "CoupledSimulatedAnnealing", "GradBasedGlobalOptimizer", "ModelTuner",
 ]

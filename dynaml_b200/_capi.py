@@ -29,8 +29,8 @@ _STATUS_NAMES = {
 # every symbol include/dgp_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "dgp_ctx_create", "dgp_ctx_destroy", "dgp_last_error", "dgp_version", "dgp_ctx_set_option",
-    "dgp_get_timings", "dgp_data_create", "dgp_data_destroy", "dgp_kernel_matrix", "dgp_energy",
-    "dgp_energy_grad", "dgp_energy_batch", "dgp_fit", "dgp_model_destroy", "dgp_model_energy",
+    "dgp_get_timings", "dgp_data_create", "dgp_data_destroy", "dgp_kernel_matrix", "dgp_energy", "dgp_energy_terms",
+    "dgp_energy_grad", "dgp_energy_batch", "dgp_fit", "dgp_model_destroy", "dgp_model_energy", "dgp_model_terms",
     "dgp_predict", "dgp_dist_unique_id", "dgp_dist_init", "dgp_dist_finalize", "dgp_dist_plan", "dgp_dist_energy",
     "dgp_measure_peaks", "dgp_launch_count", "dgp_time_phase", "dgp_test_gemm", "dgp_test_potrf",
 ]
@@ -80,6 +80,8 @@ def load_library() -> C.CDLL:
         "dgp_data_destroy": (i32, [vp, vp]),
         "dgp_kernel_matrix": (i32, [vp, sp, _dp, i64, _dp, i64, i32, i32, _dp, i64, i32]),
         "dgp_energy": (i32, [vp, vp, sp, _dp]),
+        "dgp_energy_terms": (i32, [vp, vp, sp, _dp, _dp]),
+        "dgp_model_terms": (i32, [vp, vp, _dp, _dp]),
         "dgp_energy_grad": (i32, [vp, vp, sp, _dp, _dp]),
         "dgp_energy_batch": (i32, [vp, vp, sp, i32, _dp, C.POINTER(i32)]),
         "dgp_fit": (i32, [vp, vp, sp, C.POINTER(vp)]),
@@ -210,6 +212,18 @@ class Context:
             return float("inf")  # AbstractGPRegressionModel.scala:531-533
         self.check(st)
         return e.value
+
+    def energy_terms(self, data, spec):
+        """(r' K^-1 r, sum log L_ii); raises NotPositiveDefinite when the Cholesky fails."""
+        s, keep = spec
+        q, l = C.c_double(), C.c_double()
+        self.check(self.lib.dgp_energy_terms(self.h, data, C.byref(s), C.cast(C.byref(q), _dp), C.cast(C.byref(l), _dp)))
+        return q.value, l.value
+
+    def model_terms(self, h):
+        q, l = C.c_double(), C.c_double()
+        self.check(self.lib.dgp_model_terms(self.h, h, C.cast(C.byref(q), _dp), C.cast(C.byref(l), _dp)))
+        return q.value, l.value
 
     def energy_grad(self, data, spec):
         s, keep = spec

@@ -314,7 +314,7 @@ struct Model {
   double *L = nullptr;    // Np x Np
   double *inv = nullptr;  // Np x 128
   double *alpha = nullptr;
-  double energy = 0.0;
+  double energy = 0.0, quad = 0.0, logdet_half = 0.0;
   std::vector<double> center;  // the training set's column means (test points are shifted alike)
   double max_sq_norm = 0.0;
 };
@@ -494,6 +494,20 @@ int32_t dgp_energy(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *sp
   return energy_impl(ctx, data, spec, e, nullptr);
 }
 
+int32_t dgp_energy_terms(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec, double *quad,
+                         double *logdet_half) {
+  if (!quad || !logdet_half) return DGP_ERR_ARG;
+  double e = 0.0;
+  const int32_t st = energy_impl(ctx, data, spec, &e, nullptr);
+  if (st != DGP_OK) {
+    *quad = *logdet_half = nan("");
+    return st;
+  }
+  *quad = ctx->h_scal[0];  // left in the pinned read-back buffer by energy_impl
+  *logdet_half = ctx->h_scal[1];
+  return DGP_OK;
+}
+
 int32_t dgp_energy_grad(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec, double *e, double *g) {
   if (!g) return DGP_ERR_ARG;
   return energy_impl(ctx, data, spec, e, g);
@@ -633,6 +647,8 @@ int32_t dgp_fit(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *spec, dg
   if (ctx->h_info[0] != 0)
     return bail(ctx->fail(DGP_ERR_NOT_PD, "Cholesky failed: pivot %d is not positive", ctx->h_info[0] - 1));
   m->energy = energy_from(D, ctx->h_scal[0], ctx->h_scal[1]);
+  m->quad = ctx->h_scal[0];
+  m->logdet_half = ctx->h_scal[1];
   *out = m;
   return DGP_OK;
 }
@@ -640,6 +656,13 @@ int32_t dgp_fit(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *spec, dg
 int32_t dgp_model_energy(dgp_ctx *ctx, const dgp_model *m, double *e) {
   if (!ctx || !m || !e) return DGP_ERR_ARG;
   *e = m->energy;
+  return DGP_OK;
+}
+
+int32_t dgp_model_terms(dgp_ctx *ctx, const dgp_model *m, double *quad, double *logdet_half) {
+  if (!ctx || !m || !quad || !logdet_half) return DGP_ERR_ARG;
+  *quad = m->quad;
+  *logdet_half = m->logdet_half;
   return DGP_OK;
 }
 

@@ -127,6 +127,15 @@ int32_t dgp_kernel_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec,
    whose log-det term is half the textbook one).  Non-PD K: *e = +Inf, returns DGP_ERR_NOT_PD.   */
 int32_t dgp_energy(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec, double *e);
 
+/* The two data-dependent terms every likelihood on this path is built from:
+     *quad = r' K^-1 r,   *logdet_half = sum_i log L_ii.
+   GP: E = 0.5 (quad + logdet_half + n log 2 pi); Student-t process (SURVEY 8f rank 2,
+   CORE/models/stp/AbstractSTPRegressionModel.scala:253-283,
+   CORE/probability/distributions/BlockedMultivariateStudentsT.scala:47-61): the host combines the
+   same two numbers with the degrees of freedom.  Non-PD K: DGP_ERR_NOT_PD.                       */
+int32_t dgp_energy_terms(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec, double *quad,
+                         double *logdet_half);
+
 /* ---- gradEnergy (AbstractGPRegressionModel.scala:196-267) -----------------------------------
    g[i] = tr( (alpha alpha' - K^-1) dK/dtheta_i ), i over spec->hyp in order, then g[n_hyp] for
    the noise level: n_hyp + 1 values (entries with no reference derivative, e.g. Matern "p",
@@ -156,6 +165,7 @@ int32_t dgp_energy_batch(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_sp
 int32_t dgp_fit(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec, dgp_model **out);
 int32_t dgp_model_destroy(dgp_ctx *ctx, dgp_model *model);
 int32_t dgp_model_energy(dgp_ctx *ctx, const dgp_model *model, double *e);
+int32_t dgp_model_terms(dgp_ctx *ctx, const dgp_model *model, double *quad, double *logdet_half);
 int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *model, const double *Xs, int64_t M,
                     int32_t x_layout, const double *mean_s, double *mean, double *cov,
                     int64_t ldcov, double *lo, double *hi, double sigma);

@@ -202,6 +202,43 @@ class PeriodicKernel : public LocalScalarKernel {
   int device_kind() const override { return DGP_KERNEL_PERIODIC; }
 };
 
+// further stationary kernels of the same builder API
+class CauchyKernel : public LocalScalarKernel {  // CORE/kernels/CauchyKernel.scala
+ public:
+  explicit CauchyKernel(double si = 1.0) {
+    hyper_parameters = {"sigma"};
+    state = {{"sigma", si}};
+  }
+  int device_kind() const override { return DGP_KERNEL_CAUCHY; }
+};
+
+class LaplacianKernel : public LocalScalarKernel {  // CORE/kernels/LaplacianKernel.scala
+ public:
+  explicit LaplacianKernel(double be = 1.0) {
+    hyper_parameters = {"beta"};
+    state = {{"beta", be}};
+  }
+  int device_kind() const override { return DGP_KERNEL_LAPLACIAN; }
+};
+
+class RationalQuadraticKernel : public LocalScalarKernel {  // CORE/kernels/RationalQuadraticKernel.scala
+ public:
+  explicit RationalQuadraticKernel(double shape = 1.0, double l = 1.0) {
+    hyper_parameters = {"mu", "l"};
+    state = {{"mu", shape}, {"l", l}};
+  }
+  int device_kind() const override { return DGP_KERNEL_RATQUAD; }
+};
+
+class TStudentKernel : public LocalScalarKernel {  // CORE/kernels/TStudentKernel.scala
+ public:
+  explicit TStudentKernel(double degree = 1.0) {
+    hyper_parameters = {"d"};
+    state = {{"d", degree}};
+  }
+  int device_kind() const override { return DGP_KERNEL_TSTUDENT; }
+};
+
 class DiracKernel : public LocalScalarKernel {
  public:
   explicit DiracKernel(double noiseLevel = 1.0) {

@@ -356,6 +356,49 @@ def error_bars(mu: np.ndarray, cov_post: np.ndarray, sigma: float):
 
 
 # ------------------------------------------------------------------------------------------------
+# Student-t process sibling
+# ------------------------------------------------------------------------------------------------
+
+def stp_energy(mu: float, cov: Kernel, noise_level: float, X: np.ndarray, y: np.ndarray,
+               mean: np.ndarray | None = None) -> float:
+    """AbstractSTPRegressionModel.logLikelihood (:285-304) -> -BlockedMultivariateStudentsT.logPdf
+    (BlockedMultivariateStudentsT.scala:47-61).  `mu` is the degrees of freedom the density is
+    evaluated at (the model's setState has already added its 2.0)."""
+    from scipy.special import gammaln as lg
+    r = y - (0.0 if mean is None else mean)
+    K = build_kernel_matrix(cov, X, dirac(noise_level))
+    try:
+        root = sla.cholesky(K, lower=True)
+    except np.linalg.LinAlgError:
+        return float("inf")
+    z = sla.solve_triangular(root, r, lower=True)
+    slv = sla.solve_triangular(root.T, z, lower=False)
+    n = r.shape[0]
+    unnorm = -0.5 * (mu + n) * math.log(1.0 + (float(slv @ r) / mu))
+    det = float(np.sum(np.log(np.diag(root))))
+    log_norm = ((n // 2) * (math.log(mu) + math.log(math.pi))) + 0.5 * det + lg(mu / 2.0) - lg((mu + n) / 2.0)
+    return -1.0 * (unnorm - log_norm)
+
+
+def stp_predictive(dof: float, cov: Kernel, noise_level: float, X: np.ndarray, y: np.ndarray, Xs: np.ndarray,
+                   mean: np.ndarray | None = None, mean_s: np.ndarray | None = None):
+    """AbstractSTPRegressionModel.predictiveDistribution (:97-188): returns (mu, mean, covariance)."""
+    r = y - (0.0 if mean is None else mean)
+    mu_gp, cov_gp = predictive(cov, noise_level, X, y, Xs, mean, mean_s)
+    K = build_kernel_matrix(cov, X, dirac(noise_level))
+    beta = float(r @ np.linalg.solve(K, r))
+    adj = (dof + beta - 2.0) / (dof + X.shape[0] - 2.0)
+    return X.shape[0] + dof, mu_gp, cov_gp * adj
+
+
+def stp_error_bars(mu: float, mean: np.ndarray, covariance: np.ndarray, sigma: float):
+    """BlockedMultivariateStudentsT.confidenceInterval (:79-90)."""
+    root = sla.cholesky(covariance, lower=True)
+    bar = root @ (np.ones(mean.shape[0]) * (abs(sigma) * math.sqrt(mu / (mu - 2.0))))
+    return mean - bar, mean + bar
+
+
+# ------------------------------------------------------------------------------------------------
 # tuners (host logic only; energies come from a callable)
 # ------------------------------------------------------------------------------------------------
 

@@ -52,6 +52,8 @@ int main(int argc, char **argv) {
     }
     // ---- KernelSpec: SE(1,1)(1, 0)
     std::printf("\"kernelspec_se\": %.17g,\n", SEKernel(1.0, 1.0).evaluate({1.0}, {0.0}));
+    std::printf("\"kernelspec_laplace\": %.17g, \"kernelspec_cauchy\": %.17g,\n",
+                LaplacianKernel(1.0).evaluate({1.0}, {0.0}), CauchyKernel(1.0).evaluate({1.0}, {1.5}));
     // ---- block / unblock plumbing (KernelSpec.scala:12-32)
     {
       SEKernel se(1.0, 1.0);

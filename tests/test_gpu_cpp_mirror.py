@@ -43,6 +43,8 @@ def test_reference_known_answers_through_cpp(result):
     assert out["gpspec_lo"] == pytest.approx(rho - math.sqrt(1.0 - rho * rho), abs=1e-15)
     assert out["gpspec_hi"] == pytest.approx(rho + math.sqrt(1.0 - rho * rho), abs=1e-15)
     assert abs(out["kernelspec_se"] - 0.6065306597126334) < 1e-15                    # KernelSpec.scala:53
+    assert abs(out["kernelspec_laplace"] - 0.36787944117144233) < 1e-15
+    assert abs(out["kernelspec_cauchy"] - 0.8) < 1e-15
     assert out["block_unblock_ok"] and out["missing_key_throws"]
 
 

@@ -170,3 +170,24 @@ def test_non_pd_gives_inf_and_nan():
     assert orc.energy(k, 0.0, X, y) == float("inf")
     g = orc.grad_energy(k, 0.0, X, y)
     assert all(math.isnan(v) for v in g.values())
+
+
+# ---- Student-t process sibling: the reference's STPSpec known answers ----------------
+def test_stpspec_likelihood():
+    # STPSpec.scala:13-39: Dirac(0.5)+Dirac(0.5), mean v(0), mu = 4 -> state 6 -> energy() evaluates at 8
+    X = np.array([[0.0], [1.0]])
+    y = np.array([0.0, 1.0])
+    e = orc.stp_energy(8.0, orc.Kernel("dirac", {"noiseLevel": 0.5}), 0.5, X, y, mean=X[:, 0])
+    assert abs(e - (-math.log(1 / (2.0 * math.pi)))) < 1e-5
+
+
+def test_stpspec_posterior_and_error_bars():
+    # STPSpec.scala:41-80: one training point, SE(1,1), noise 0, degrees of freedom 4 + 2
+    k = orc.Kernel("se", {"bandwidth": 1.0, "amplitude": 1.0})
+    mu, mean, cov = orc.stp_predictive(6.0, k, 0.0, np.array([[1.0]]), np.array([1.0]), np.array([[2.0]]))
+    rho = math.exp(-0.5)
+    assert mean[0] == rho
+    assert abs(cov[0, 0] * mu / (mu - 2.0) - (1.0 - rho * rho) * 7 / 5) < 1e-5
+    lo, hi = orc.stp_error_bars(mu, mean, cov, 1.0)
+    assert lo[0] == pytest.approx(rho - math.sqrt((1.0 - rho * rho) * 7 / 5), abs=1e-15)
+    assert hi[0] == pytest.approx(rho + math.sqrt((1.0 - rho * rho) * 7 / 5), abs=1e-15)
