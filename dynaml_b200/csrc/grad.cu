@@ -228,6 +228,106 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *par
   if (threadIdx.x == 0) sums[q] = sh[0];
 }
 
+// Any feature count (dp > 32): same tiling, row points re-read from global/L1, column points in
+// shared memory, runtime loop over the features.  ARD exact mode (one sum per dimension) is not
+// offered here.
+template <int MODE>
+__global__ void __launch_bounds__(GTHREADS) grad_trace_generic_kernel(CovParams cp, GradArgs a) {
+  constexpr int NS = NSums<MODE, 0>::value;
+  extern __shared__ __align__(16) double sm[];
+  constexpr bool ARD = (MODE == M_ARD_REF);
+  const int dp = a.dp;
+  double *sx = sm;
+  double *sxs = sm + GT * dp;
+  double *sal = sm + (ARD ? 2 : 1) * GT * dp;
+  double *red = sal + GT;
+  const int tid = threadIdx.x;
+  const int tx = tid & 63, ty = tid >> 6;
+  int64_t tlin = blockIdx.x;
+  int ti = (int)((sqrt(8.0 * (double)tlin + 1.0) - 1.0) * 0.5);
+  while ((int64_t)ti * (ti + 1) / 2 > tlin) --ti;
+  while ((int64_t)(ti + 1) * (ti + 2) / 2 <= tlin) ++ti;
+  const int tj = (int)(tlin - (int64_t)ti * (ti + 1) / 2);
+  const int64_t m0 = (int64_t)ti * GT, n0 = (int64_t)tj * GT;
+  for (int i = tid; i < GT * dp; i += GTHREADS) {
+    sx[i] = a.X[n0 * dp + i];
+    if (ARD) sxs[i] = a.Xs[n0 * dp + i];
+  }
+  if (tid < GT) sal[tid] = a.alpha[n0 + tid];
+  const int64_t r0 = m0 + 2 * tx;
+  const double *x0 = a.X + r0 * dp, *x1 = x0 + dp;
+  const double *xs0 = ARD ? a.Xs + r0 * dp : x0, *xs1 = xs0 + dp;
+  const double al0 = a.alpha[r0], al1 = a.alpha[r0 + 1];
+  __syncthreads();
+  double s[NS];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) s[q] = 0.0;
+  const double *kinv = a.Kinv + r0 + n0 * a.ld;
+  for (int cc = 0; cc < GT / 4; ++cc) {
+    const int j = ty + 4 * cc;
+    const int64_t col = n0 + j;
+    const double2 kv = *reinterpret_cast<const double2 *>(kinv + (int64_t)j * a.ld);
+    const double aj = sal[j];
+    double d0 = 0.0, d1 = 0.0, p0 = 0.0, p1 = 0.0;
+    for (int c = 0; c < dp; ++c) {
+      const double y = sx[j * dp + c];
+      const double e0 = x0[c] - y, e1 = x1[c] - y;
+      if (MODE == M_PERIODIC || MODE == M_LAPLACIAN) {
+        d0 += fabs(e0);
+        d1 += fabs(e1);
+      } else if (ARD) {
+        const double ys = sxs[j * dp + c];
+        const double f0 = xs0[c] - ys, f1 = xs1[c] - ys;
+        d0 = fma(f0, f0, d0);
+        d1 = fma(f1, f1, d1);
+        p0 = fma(e0, e0, p0);
+        p1 = fma(e1, e1, p1);
+      } else {
+        d0 = fma(e0, e0, d0);
+        d1 = fma(e1, e1, d1);
+      }
+    }
+    double w0 = (r0 > col) ? 2.0 : (r0 == col ? 1.0 : 0.0);
+    double w1 = (r0 + 1 > col) ? 2.0 : (r0 + 1 == col ? 1.0 : 0.0);
+    if (r0 >= a.n || col >= a.n) w0 = 0.0;
+    if (r0 + 1 >= a.n || col >= a.n) w1 = 0.0;
+    if (w0 != 0.0) accumulate<MODE, 0>(cp, w0 * (al0 * aj - kv.x), d0, p0, nullptr, s);
+    if (w1 != 0.0) accumulate<MODE, 0>(cp, w1 * (al1 * aj - kv.y), d1, p1, nullptr, s);
+  }
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    double v = s[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp * NS + q] = v;
+  }
+  __syncthreads();
+  if (tid < NS) {
+    double v = 0.0;
+    for (int wdx = 0; wdx < GTHREADS / 32; ++wdx) v += red[wdx * NS + tid];
+    a.partials[(int64_t)blockIdx.x * NS + tid] = v;
+  }
+}
+
+template <int MODE>
+int32_t launch_generic(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArgs &a, int64_t tiles, int *ns_out) {
+  constexpr int NS = NSums<MODE, 0>::value;
+  constexpr bool ARD = (MODE == M_ARD_REF);
+  size_t smem = ((size_t)(ARD ? 2 : 1) * GT * a.dp + GT + (GTHREADS / 32) * NS) * sizeof(double);
+  if (smem > 200 * 1024) return ctx->fail(DGP_ERR_SHAPE, "gradEnergy: too many features (dp=%d)", a.dp);
+  if (smem > 48 * 1024)
+    DGP_CUDA_OK(ctx, cudaFuncSetAttribute(grad_trace_generic_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+  grad_trace_generic_kernel<MODE><<<(unsigned)tiles, GTHREADS, smem, st>>>(cp, a);
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  reduce_partials_kernel<<<NS, 1024, 0, st>>>(a.partials, tiles, NS, a.sums);
+  ctx->launches += 2;
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  *ns_out = NS;
+  return DGP_OK;
+}
+
 template <int MODE, int DP>
 int32_t launch(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArgs &a, int64_t tiles, int *ns_out) {
   constexpr int NS = NSums<MODE, DP>::value;
@@ -256,7 +356,9 @@ int32_t launch_dp(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArgs
     case 24: return launch<MODE, 24>(ctx, st, cp, a, tiles, ns);
     case 32: return launch<MODE, 32>(ctx, st, cp, a, tiles, ns);
     default:
-      return ctx->fail(DGP_ERR_SHAPE, "gradEnergy supports up to 32 features (multiple-of-4 padded), got dp=%d", a.dp);
+      if (MODE == M_ARD_EXACT)
+        return ctx->fail(DGP_ERR_SHAPE, "exact ARD gradients support up to 32 features, got dp=%d", a.dp);
+      return launch_generic<(MODE == M_ARD_EXACT ? M_ARD_REF : MODE)>(ctx, st, cp, a, tiles, ns);
   }
 }
 

@@ -382,3 +382,49 @@ def test_auto_assembly_falls_back_to_exact_differences_for_tiny_length_scales(ct
     Ko = orc.build_kernel_matrix(ok, X)
     big = Ko > 1e-200
     assert entry_rel(K[big], Ko[big]) <= TOL_K
+
+
+@pytest.mark.parametrize("name", ["se", "matern2", "ard_ref", "laplacian"])
+def test_energy_grad_with_many_features(name):
+    """d = 40 (> 32): the generic-feature-count assembly and gradient kernels."""
+    d = 40
+    X, y, _ = orc.synthetic(260, d, seed=40)
+    band = np.linspace(4.0, 8.0, d)
+    if name == "se":
+        k, ok = dg.SEKernel(5.0, 1.1), orc.Kernel("se", {"bandwidth": 5.0, "amplitude": 1.1})
+    elif name == "matern2":
+        k, ok = dg.GenericMaternKernel(6.0, 2), orc.Kernel("matern", {"p": 2.0, "l": 6.0})
+    elif name == "ard_ref":
+        k = dg.MahalanobisKernel(band, 1.2)
+        ok = orc.Kernel("ard", {"MahalanobisAmplitude": 1.2, **{f"MahalanobisBandwidth_{i}": b for i, b in enumerate(band)}})
+    else:
+        k, ok = dg.LaplacianKernel(30.0), orc.Kernel("laplacian", {"beta": 30.0})
+    model = dg.GPRegression(k, dg.DiracKernel(0.3), list(zip(X, y)))
+    assert model.energy(model._current_state) == pytest.approx(orc.energy(ok, 0.3, X, y), rel=TOL)
+    g, go = model.gradEnergy(model._current_state), orc.grad_energy(ok, 0.3, X, y)
+    scale = max(abs(v) for v in go.values())
+    for key, v in go.items():
+        assert g[key] == pytest.approx(v, rel=TOL, abs=TOL * scale), key
+
+
+def test_exact_ard_gradient_beyond_32_features_is_refused_not_faked():
+    X, y, _ = orc.synthetic(130, 40, seed=41)
+    k = dg.MahalanobisKernel(np.full(40, 6.0), 1.0, _capi.GRAD_EXACT)
+    model = dg.GPRegression(k, dg.DiracKernel(0.3), list(zip(X, y)))
+    with pytest.raises(dg.DgpError):
+        model.gradEnergy(model._current_state)
+
+
+def test_housing_workflow_end_to_end():
+    """Config C1 as the reference example drives it (TestGPHousing.scala:77-140): scaled housing data ->
+    GPRegression(SE + Dirac) -> gpTuning("GS") -> model.test -> RegressionMetrics."""
+    from dynaml_b200 import workflow as wf
+    z = np.load(GOLD / "housing.npz")
+    train, test = list(zip(z["Xtr"], z["ytr"])), list(zip(z["Xte"], z["yte"]))
+    model = dg.GPRegression(dg.SEKernel(2.5, 1.5), dg.DiracKernel(1.5), train)
+    start = dict(model._current_state)
+    tuned, best = wf.gpTuning(start, "GS", grid=2, step=0.4)(model)
+    assert tuned.energy(best) <= tuned.energy({k: v - 0.4 for k, v in start.items()}) + 1e-9
+    res = tuned.test(test)
+    metrics = wf.RegressionMetrics([(r[2], r[1]) for r in res], len(res))
+    assert len(res) == 56 and math.isfinite(metrics.rmse) and metrics.rmse < 1.0 and metrics.corr > 0.5

@@ -217,3 +217,17 @@ def test_block_cyclic_plan_partitions_the_lower_triangle(n, tile, pr, pc):
     for r, p in enumerate(plans):
         assert p["local_rows"] == len(range(r // pc, nt, pr)) and p["local_cols"] == len(range(r % pc, nt, pc))
         assert p["local_bytes"] == p["local_rows"] * p["local_cols"] * tile * tile * 8
+
+
+def test_gaussian_scaling_and_regression_metrics():
+    from dynaml_b200 import workflow as wf
+    rng = np.random.default_rng(0)
+    X = rng.normal(3.0, 2.0, size=(40, 3))
+    y = rng.normal(-1.0, 5.0, size=40)
+    tr, te, (mx, sx, my, sy) = wf.gaussianScalingTrainTest(list(zip(X[:30], y[:30])), list(zip(X[30:], y[30:])))
+    Xs = np.array([t[0] for t in tr])
+    assert np.allclose(Xs.mean(0), 0.0, atol=1e-12) and np.allclose(Xs.std(0, ddof=1), 1.0)
+    assert np.allclose(np.array([t[0] for t in te]), (X[30:] - mx) / sx)
+    m = wf.RegressionMetrics([(1.0, 1.5), (2.0, 1.0), (3.0, 3.5)])
+    assert m.mae == pytest.approx((0.5 + 1.0 + 0.5) / 3) and m.rmse == pytest.approx(math.sqrt((0.25 + 1 + 0.25) / 3))
+    assert m.Rsq == pytest.approx(1 - 1.5 / ((1.5 - 2) ** 2 + (1 - 2) ** 2 + (3.5 - 2) ** 2))
