@@ -66,6 +66,17 @@ def workload_config(name: str) -> dict:
             "l2": "per-step working set (K, L^-1, K^-1: 3 x 8*N^2 bytes) exceeds the 126 MB L2; no flush needed"}
 
 
+def synthetic(n: int, d: int, seed: int = 0):
+    """SURVEY 8(d) inputs: X ~ N(0,1)^{n x d}; y = sin(X w) + 0.1 eps, w ~ N(0, I/d).  (Same generator as
+    oracle.gp_oracle.synthetic; restated here so the measured arm does not touch oracle/.)"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, d))
+    w = rng.standard_normal(d) / math.sqrt(d)
+    y = np.sin(X @ w) + 0.1 * rng.standard_normal(n)
+    return X, y
+
+
 def make_kernel(kern: str, d: int, rank: int):
     """Device kernel object; each rank gets its own candidate (length-scale scaled by the rank)."""
     import dynaml_b200 as dg
@@ -184,7 +195,6 @@ def main():
 
     import numpy as np
     import dynaml_b200 as dg
-    from oracle import gp_oracle as orc  # synthetic-input generator only (bench.py may use oracle/ for inputs + cpu_baseline)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,7 +220,7 @@ def main():
 
     ctx = dg.Context(local)
     n, d, kern = WORKLOADS[args.workload]
-    X, y, _ = orc.synthetic(n, d, seed=0)
+    X, y = synthetic(n, d, seed=0)
     kernel = make_kernel(kern, d, rank)
     spec = kernel._spec(noise=0.1)
     data = ctx.data_create(X, y)

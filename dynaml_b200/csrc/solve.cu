@@ -8,61 +8,71 @@ namespace {
 
 constexpr int SB = 128;  // block edge (= leaf block)
 
-constexpr int ST = 256;  // threads per CTA of the solve steps
+constexpr int ST = 1024;  // threads per CTA of the solve steps
 
-// sum_{j<64} M[r + j*ld] * v[j]: half of a 128-wide block row; 16 independent loads in flight
-__device__ __forceinline__ double rowhalf_mv(const double *M, int64_t ld, const double *v, int r) {
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
+// Pull a 128 x 128 block (column-major, leading dimension ld) towards L2: 8 lines of 128 B per
+// column, one line per thread of a 1024-thread CTA.  The solve steps are latency bound (one dependent
+// HBM round trip per launch), so each launch prefetches what the *next* launch will read.
+__device__ __forceinline__ void prefetch_block_l2(const double *M, int64_t ld) {
+  const int c = threadIdx.x;
+  prefetch_l2(M + (c & 7) * 16 + (int64_t)(c >> 3) * ld);
+}
+
+// sum_{j<16} M[r + j*ld] * v[j]: one eighth of a 128-wide block row; the 16 loads are independent
+// and the compiler keeps them all in flight (1024 threads per CTA give the memory-level parallelism
+// that a wider per-thread loop does not: ptxas interleaves loads and FMAs to save registers).
+__device__ __forceinline__ double rowpart_mv(const double *M, int64_t ld, const double *v, int r) {
+  double m[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) m[u] = M[r + (int64_t)u * ld];
   double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
 #pragma unroll
-  for (int j0 = 0; j0 < 64; j0 += 16) {
-    double m[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) m[u] = M[r + (int64_t)(j0 + u) * ld];
-#pragma unroll
-    for (int u = 0; u < 16; u += 4) {
-      acc0 = fma(m[u + 0], v[j0 + u + 0], acc0);
-      acc1 = fma(m[u + 1], v[j0 + u + 1], acc1);
-      acc2 = fma(m[u + 2], v[j0 + u + 2], acc2);
-      acc3 = fma(m[u + 3], v[j0 + u + 3], acc3);
-    }
+  for (int u = 0; u < 16; u += 4) {
+    acc0 = fma(m[u + 0], v[u + 0], acc0);
+    acc1 = fma(m[u + 1], v[u + 1], acc1);
+    acc2 = fma(m[u + 2], v[u + 2], acc2);
+    acc3 = fma(m[u + 3], v[u + 3], acc3);
   }
   return (acc0 + acc1) + (acc2 + acc3);
 }
 
-// 128-row block times a 128-vector with 256 threads: thread (r, h) does half h of row r; the two
-// halves meet in `part`.  Returns the full sum to the h == 0 threads.
+// 128-row block times a 128-vector with 1024 threads: thread (r, h) does columns [16h, 16h+16) of
+// row r; the eight parts meet in `part` (8 x 128).  Returns the full sum to the h == 0 threads.
 __device__ __forceinline__ double rowblock_mv(const double *M, int64_t ld, const double *v, double *part) {
   const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
-  const double acc = rowhalf_mv(M + (int64_t)(h * 64) * ld, ld, v + h * 64, r);
-  if (h == 1) part[r] = acc;
+  part[h * SB + r] = rowpart_mv(M + (int64_t)(h * 16) * ld, ld, v + h * 16, r);
   __syncthreads();
-  return acc + part[r];
+  double s = 0.0;
+  if (h == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += part[q * SB + r];
+  }
+  return s;
 }
 
-// out[c] = sum_{k<128} M[k + c*ld] * v[k] for c = 0..127: 8 warps x 16 columns, four columns
-// (16 loads per lane) in flight at a time, lanes over k.
+// out[c] = sum_{k<128} M[k + c*ld] * v[k] for c = 0..127: 32 warps x 4 columns, lanes over k
+// (16 loads per lane in flight).
 template <typename Store>
 __device__ __forceinline__ void colblock_dot(const double *M, int64_t ld, const double *v, Store store) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double v0 = v[lane], v1 = v[lane + 32], v2 = v[lane + 64], v3 = v[lane + 96];
+  double m[4][4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    double m[4][4];
+  for (int u = 0; u < 4; ++u) {
+    const double *col = M + (int64_t)(warp * 4 + u) * ld;
+    m[u][0] = col[lane];
+    m[u][1] = col[lane + 32];
+    m[u][2] = col[lane + 64];
+    m[u][3] = col[lane + 96];
+  }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const double *col = M + (int64_t)(warp * 16 + q * 4 + u) * ld;
-      m[u][0] = col[lane];
-      m[u][1] = col[lane + 32];
-      m[u][2] = col[lane + 64];
-      m[u][3] = col[lane + 96];
-    }
+  for (int u = 0; u < 4; ++u) {
+    double s = (m[u][0] * v0 + m[u][1] * v1) + (m[u][2] * v2 + m[u][3] * v3);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      double s = (m[u][0] * v0 + m[u][1] * v1) + (m[u][2] * v2 + m[u][3] * v3);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) store(warp * 16 + q * 4 + u, s);
-    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) store(warp * 4 + u, s);
   }
 }
 
@@ -71,9 +81,12 @@ __device__ __forceinline__ void colblock_dot(const double *M, int64_t ld, const 
 __global__ void __launch_bounds__(ST) trsv_fwd_step_kernel(const double *L, int64_t ldl, const double *inv, double *x,
                                                            int b) {
   __shared__ double v[SB];
-  __shared__ double part[SB];
+  __shared__ double part[8 * SB];
   const int tid = threadIdx.x, r = tid & 127, h = tid >> 7;
   const int i = b + 1 + blockIdx.x;
+  // next launch: this row block reads L(i, b+1) (or, as the new head block, its diagonal inverse)
+  if (i > b + 1) prefetch_block_l2(L + (int64_t)i * SB + (int64_t)(b + 1) * SB * ldl, ldl);
+  if (i <= b + 2) prefetch_block_l2(inv + (int64_t)i * SB * SB, SB);
   double xi = x[(int64_t)i * SB + r];
   if (b >= 0) {
     if (h == 0) v[r] = x[(int64_t)b * SB + r];
@@ -97,6 +110,11 @@ __global__ void __launch_bounds__(ST) trsv_bwd_step_kernel(const double *L, int6
   __shared__ double w[SB];
   const int tid = threadIdx.x;
   const int j = (b == nblk) ? nblk - 1 : (int)blockIdx.x;
+  // next launch (step b-1): this column block reads L(b-1, j), or its own diagonal inverse as the head
+  if (b >= 1) {
+    if (j < b - 1) prefetch_block_l2(L + (int64_t)(b - 1) * SB + (int64_t)j * SB * ldl, ldl);
+    else if (j == b - 1) prefetch_block_l2(inv + (int64_t)j * SB * SB, SB);
+  }
   if (tid < SB) w[tid] = x[(int64_t)j * SB + tid];
   if (b < nblk) {
     if (tid < SB) v[tid] = x[(int64_t)b * SB + tid];
