@@ -463,11 +463,6 @@ void launch_kind(cudaStream_t st, const CovParams &cp, const AssembleArgs &a, un
   }
 }
 
-__global__ void scale_points_kernel(const double *X, double *Xs, const double *inv_b, int64_t n, int dp) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n * dp) Xs[i] = X[i] * inv_b[i % dp];
-}
-
 }  // namespace
 
 int32_t assemble(Ctx *ctx, cudaStream_t st, const CovParams &cp, const AssembleArgs &a) {
@@ -500,15 +495,6 @@ int32_t assemble(Ctx *ctx, cudaStream_t st, const CovParams &cp, const AssembleA
     default: return ctx->fail(DGP_ERR_UNSUPPORTED_KERNEL, "assemble: kernel kind %d", cp.kind);
   }
   ctx->launches++;
-  DGP_CUDA_OK(ctx, cudaGetLastError());
-  return DGP_OK;
-}
-
-int32_t scale_points(Ctx *ctx, cudaStream_t st, const double *X, double *Xs, const double *d_inv_b, int64_t n,
-                     int dp) {
-  int64_t total = n * dp;
-  if (total == 0) return DGP_OK;
-  scale_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, Xs, d_inv_b, n, dp);
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
 }

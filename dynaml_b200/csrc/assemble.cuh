@@ -33,8 +33,4 @@ struct AssembleArgs {
 bool gram_is_accurate(const CovParams &cp, int dp, double max_sq_norm);
 
 int32_t assemble(Ctx *ctx, cudaStream_t st, const CovParams &cp, const AssembleArgs &a);
-// Xs[i][c] = X[i][c] * inv_b[c]  (ARD-SE: MahalanobisKernel.scala:122-132 folded into the inputs)
-int32_t scale_points(Ctx *ctx, cudaStream_t st, const double *X, double *Xs, const double *d_inv_b, int64_t n,
-                     int dp);
-
 }  // namespace dgp

@@ -1,6 +1,6 @@
 // covfn.cuh -- device-side covariance functions and their hyper-parameter derivatives.
 // Each formula restates the reference's scalar closure (file:line in the comments); the
-// host-side CovParams::make() folds the hyper-parameters into the constants used here.
+// host-side make_cov_params() folds the hyper-parameters into the constants used here.
 #pragma once
 #include <math.h>
 #include "common.cuh"
@@ -8,7 +8,6 @@
 namespace dgp {
 
 constexpr int MAX_MATERN_P = 8;
-constexpr int MAX_SUMS = 132;  // gradient moment accumulators (ARD exact mode: 1 + d, + noise)
 
 struct CovParams {
   int kind = 0;
@@ -62,22 +61,6 @@ __device__ __forceinline__ double cov_value(const CovParams &cp, double dist) {
 // Kinds whose distance is |x-y|_1 instead of |x-y|_2^2.
 __host__ __device__ constexpr bool kind_is_l1(int kind) {
   return kind == DGP_KERNEL_PERIODIC || kind == DGP_KERNEL_LAPLACIAN;
-}
-
-// Runtime-dispatched variant for the cold paths.
-__device__ __forceinline__ double cov_value_rt(const CovParams &cp, double dist) {
-  switch (cp.kind) {
-    case DGP_KERNEL_SE:
-    case DGP_KERNEL_RBF:
-    case DGP_KERNEL_ARD_SE: return cov_value<DGP_KERNEL_SE>(cp, dist);
-    case DGP_KERNEL_MATERN: return cov_value<DGP_KERNEL_MATERN>(cp, dist);
-    case DGP_KERNEL_PERIODIC: return cov_value<DGP_KERNEL_PERIODIC>(cp, dist);
-    case DGP_KERNEL_CAUCHY: return cov_value<DGP_KERNEL_CAUCHY>(cp, dist);
-    case DGP_KERNEL_LAPLACIAN: return cov_value<DGP_KERNEL_LAPLACIAN>(cp, dist);
-    case DGP_KERNEL_RATQUAD: return cov_value<DGP_KERNEL_RATQUAD>(cp, dist);
-    case DGP_KERNEL_TSTUDENT: return cov_value<DGP_KERNEL_TSTUDENT>(cp, dist);
-    default: return cov_value<DGP_KERNEL_DIRAC>(cp, dist);
-  }
 }
 
 // Host: fold a Spec into CovParams.  `noise` < 0 is legal (the reference takes abs()).

@@ -428,3 +428,31 @@ def test_housing_workflow_end_to_end():
     res = tuned.test(test)
     metrics = wf.RegressionMetrics([(r[2], r[1]) for r in res], len(res))
     assert len(res) == 56 and math.isfinite(metrics.rmse) and metrics.rmse < 1.0 and metrics.corr > 0.5
+
+
+def test_c3_size_energy_properties(ctx):
+    """N = 32768, d = 16 Matern-5/2 (BASELINE config C3, the bench workload): size-independent checks.
+    (1) energy() and energy_grad() return the same E; (2) the 2D block-cyclic path (1x1 grid, tile 512, look-ahead)
+    agrees with the dense path; (3) amplitude scaling: for SE, a -> c a and noise -> c^2 noise gives K' = c^2 K, so
+    quad' = quad / c^2 and sum log L'_ii = sum log L_ii + n log c."""
+    n, d = 32768, 16
+    X, y, _ = orc.synthetic(n, d, seed=0)
+    data = ctx.data_create(X, y)
+    try:
+        spec = dg.GenericMaternKernel(math.sqrt(d), 2)._spec(noise=0.1)
+        e0 = ctx.energy(data, spec)
+        e1, g = ctx.energy_grad(data, spec)
+        assert e1 == e0 and np.isnan(g[0]) and np.all(np.isfinite(g[1:]))
+        ctx.dist_init(None, 0, 1, 1, 1)
+        try:
+            ed, _ = ctx.dist_energy(data, spec, 512)
+        finally:
+            ctx.dist_finalize()
+        assert ed == pytest.approx(e0, rel=1e-11)
+        c = 1.75
+        q1, l1 = ctx.energy_terms(data, dg.SEKernel(2.0 * math.sqrt(d), 1.0)._spec(noise=0.1))
+        q2, l2 = ctx.energy_terms(data, dg.SEKernel(2.0 * math.sqrt(d), c)._spec(noise=0.1 * c * c))
+        assert q2 == pytest.approx(q1 / (c * c), rel=1e-9)
+        assert l2 == pytest.approx(l1 + n * math.log(c), rel=1e-11)
+    finally:
+        ctx.data_destroy(data)
