@@ -151,11 +151,23 @@ cudaEvent_t get_event(Ctx *ctx, size_t i) {
   return ctx->ev_pool[i];
 }
 
-// Factor the block column starting at c0 (width w): leaves, in-place panel products and the
-// updates confined to the block column.  Enqueued on `st`.
+// Factor the block column starting at c0 (width w), 128 columns at a time, left-looking inside the
+// block column: before a 128-wide sub-panel is factored it receives, in ONE product with K = cs - c0,
+// the updates of all sub-panels already finished in this block column (the right-looking variant
+// issued a rank-128 update per sub-panel; profiles/launches_c3_step_r1.txt showed those K = 128
+// launches at half the efficiency of the K >= 256 ones).  Enqueued on `st`.
 int32_t factor_block_column(Ctx *ctx, cudaStream_t st, double *A, int64_t lda, int64_t n, int64_t c0, int64_t w,
                             double *inv, int *info, double *scratch) {
   for (int64_t cs = c0; cs < c0 + w; cs += LB) {
+    if (cs > c0) {
+      GemmArgs u;  // A[cs:, cs:cs+128] -= A[cs:, c0:cs] * A[cs:cs+128, c0:cs]^T
+      u.A = A + cs + c0 * lda;  u.lda = lda;  u.a_kmajor = 0;
+      u.B = A + cs + c0 * lda;  u.ldb = lda;  u.b_kmajor = 0;   // op(B)(k,n) = L(cs + n, c0 + k)
+      u.C = A + cs + cs * lda;  u.ldc = lda;
+      u.M = (int)(n - cs);  u.N = LB;  u.K = (int)(cs - c0);
+      u.alpha = -1.0;  u.beta = 1.0;
+      DGP_TRY(gemm(ctx, st, u));
+    }
     double *invb = inv + (cs / LB) * LB * LB;
     leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM, st>>>(A + cs + cs * lda, lda, invb, info, (int)cs);
     ctx->launches++;
@@ -174,17 +186,6 @@ int32_t factor_block_column(Ctx *ctx, cudaStream_t st, double *A, int64_t lda, i
     g.M = (int)mrows;  g.N = LB;  g.K = LB;
     g.alpha = 1.0;  g.beta = 0.0;
     DGP_TRY(gemm(ctx, st, g));
-    // update the remaining columns of this block column with the 128 columns just finished
-    const int64_t nc = c0 + w - rb;
-    if (nc > 0) {
-      GemmArgs u;
-      u.A = A + rb + cs * lda;  u.lda = lda;  u.a_kmajor = 0;
-      u.B = A + rb + cs * lda;  u.ldb = lda;  u.b_kmajor = 0;   // op(B)(k,n) = P(n,k)
-      u.C = A + rb + rb * lda;  u.ldc = lda;
-      u.M = (int)(n - rb);  u.N = (int)nc;  u.K = LB;
-      u.alpha = -1.0;  u.beta = 1.0;
-      DGP_TRY(gemm(ctx, st, u));
-    }
   }
   return DGP_OK;
 }
