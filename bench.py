@@ -14,7 +14,7 @@ collective), so `value` = N*K evaluations / max-over-ranks time and scaling is "
 
 Roofline: the dominant kernel is the FP64 DMMA GEMM (dgemm_dmma_kernel).  `achieved` is the
 algorithmic flops of its largest launch in the step -- the first trailing update of the Cholesky,
-C -= P P^T over the lower tiles with M = N - nb rows and K = nb (2 * K * 128^2 flop per lower tile)
+C -= P P^T over the lower tiles with M = N - nb rows and K = nb = 768 at this N (2 * K * 128^2 flop per lower tile)
 -- divided by that launch's CUDA-event duration, measured live after the timed steps on the
 library's own stream; `peak` is the FP64 DMMA peak measured live by a register-resident
 mma.sync.m8n8k4.f64 loop (MEASURED_PEAKS.json carries no FP64 figure).
@@ -262,10 +262,8 @@ def main():
     if rank == 0:
         # ---- roofline of the dominant kernel, measured live ----------------------------------------
         peaks = ctx.measure_peaks()
-        nb = 256
-        ctx.set_option("nb", nb)
+        nb = ctx.outer_block(n)
         gemm_ms = ctx.time_phase(data, spec, 2, reps=5)
-        ctx.set_option("nb", 0)
         mt = (n - nb) // 128
         flops = 2.0 * nb * 128 * 128 * (mt * (mt + 1) // 2)
         achieved = flops / (gemm_ms * 1e-3) / 1e12
@@ -273,7 +271,7 @@ def main():
         rf = ROOT / "profiles" / "roofline_traffic.json"
         if rf.exists():
             try:
-                traffic = json.loads(rf.read_text()).get(args.workload, {}).get("dram_bytes_per_launch")
+                traffic = json.loads(rf.read_text()).get(f"{args.workload}_nb{nb}", {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         potrf_tf = (n ** 3 / 3.0) / (phase["potrf"] * 1e-3) / 1e12
@@ -284,7 +282,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload),
             "device_ms_per_step": dev / args.steps * 1e3,
-            "roofline": {"bound": "tensor", "kernel": "dgemm_dmma_kernel (trailing update, M=N-256, K=256, lower tiles)",
+            "roofline": {"bound": "tensor", "kernel": f"dgemm_dmma_kernel (first trailing update of the Cholesky: M = N - {nb} rows, K = {nb}, lower tiles)",
                          "achieved": achieved, "peak": peaks["dmma_tflops"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["dmma_tflops"], "traffic": traffic,
                          "peak_source": "FP64 DMMA peak measured live by dgp_measure_peaks (register-resident "

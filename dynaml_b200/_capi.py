@@ -32,7 +32,7 @@ EXPORTS = [
     "dgp_get_timings", "dgp_data_create", "dgp_data_destroy", "dgp_kernel_matrix", "dgp_energy", "dgp_energy_terms",
     "dgp_energy_grad", "dgp_energy_batch", "dgp_fit", "dgp_model_destroy", "dgp_model_energy", "dgp_model_terms",
     "dgp_predict", "dgp_dist_unique_id", "dgp_dist_init", "dgp_dist_finalize", "dgp_dist_plan", "dgp_dist_energy",
-    "dgp_measure_peaks", "dgp_launch_count", "dgp_time_phase", "dgp_test_gemm", "dgp_test_potrf",
+    "dgp_measure_peaks", "dgp_launch_count", "dgp_outer_block", "dgp_time_phase", "dgp_test_gemm", "dgp_test_potrf",
 ]
 
 
@@ -95,6 +95,7 @@ def load_library() -> C.CDLL:
         "dgp_dist_plan": (i32, [i64, i32, i32, i32, i32, C.POINTER(i64)]),
         "dgp_measure_peaks": (i32, [vp, _dp, i32]),
         "dgp_launch_count": (i32, [vp, C.POINTER(C.c_uint64)]),
+        "dgp_outer_block": (i64, [vp, i64]),
         "dgp_time_phase": (i32, [vp, vp, sp, i32, i32, _dp]),
         "dgp_test_gemm": (i32, [vp, i32, i32, i64, i64, i64, f64, _dp, i64, _dp, i64, f64, _dp, i64, i32, _dp]),
         "dgp_test_potrf": (i32, [vp, i64, _dp, i64, _dp, _dp, _dp, _dp]),
@@ -285,6 +286,9 @@ class Context:
         n = C.c_uint64()
         self.check(self.lib.dgp_launch_count(self.h, C.byref(n)))
         return int(n.value)
+
+    def outer_block(self, n: int) -> int:
+        return int(self.lib.dgp_outer_block(self.h, int(n)))
 
     def time_phase(self, data, spec, phase: int, reps: int = 3) -> float:
         s, keep = spec

@@ -831,6 +831,10 @@ int32_t dgp_kernel_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec, const doubl
 }
 
 // ---- measurement hooks ---------------------------------------------------------------------------
+int64_t dgp_outer_block(const dgp_ctx *ctx, int64_t n) {
+  return ctx ? potrf_outer_block(ctx, round_up(n, TILE)) : 0;
+}
+
 int32_t dgp_launch_count(const dgp_ctx *ctx, uint64_t *out) {
   if (!ctx || !out) return DGP_ERR_ARG;
   *out = ctx->launches;
@@ -876,7 +880,7 @@ int32_t dgp_time_phase(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *s
       DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_b, S));
     } else if (phase == 2) {
       // the dominant kernel in isolation: one full-size trailing update C -= P P^T with K = nb
-      const int64_t nbw = ctx->nb > 0 ? ctx->nb : 256;
+      const int64_t nbw = potrf_outer_block(ctx, np);
       const int64_t w = nbw < np ? nbw : np;
       if (r == 0) DGP_TRY(assemble(ctx, S, cp, a));
       GemmArgs g;

@@ -197,6 +197,13 @@ int32_t potrf_init(Ctx *ctx) {
   return DGP_OK;
 }
 
+// Wider blocks amortise the per-tile prologue/epilogue of the trailing update (measured on B200,
+// scripts/tune.py: N = 32768 -> 404 / 386 / 382 ms at nb = 256 / 512 / 768), narrower ones shorten
+// the leaf -> panel -> update chain that bounds small N.
+int64_t potrf_outer_block(const Ctx *ctx, int64_t n) {
+  return ctx->nb > 0 ? ctx->nb : (n >= 24576 ? 768 : (n >= 12288 ? 512 : 256));
+}
+
 int32_t potrf_blocked(Ctx *ctx, double *A, int64_t lda, int64_t n, double *inv, int *info) {
   const bool la = ctx->lookahead && n > 256;
   return potrf_blocked_on(ctx, ctx->stream, la ? ctx->panel : ctx->stream, A, lda, n, inv, info, "potrf_panel");
@@ -205,10 +212,7 @@ int32_t potrf_blocked(Ctx *ctx, double *A, int64_t lda, int64_t n, double *inv, 
 int32_t potrf_blocked_on(Ctx *ctx, cudaStream_t S, cudaStream_t P, double *A, int64_t lda, int64_t n, double *inv,
                          int *info, const char *scratch_name) {
   if (n % LB) return ctx->fail(DGP_ERR_SHAPE, "potrf: n=%lld must be a multiple of 128", (long long)n);
-  // outer block: wider blocks amortise the per-tile prologue/epilogue of the trailing update
-  // (measured on B200, scripts/tune.py: N = 32768 -> 405 / 388 / 384 ms at nb = 256 / 512 / 768),
-  // narrower ones shorten the panel chain that bounds small N
-  const int64_t nb = ctx->nb > 0 ? ctx->nb : (n >= 24576 ? 768 : (n >= 12288 ? 512 : 256));
+  const int64_t nb = potrf_outer_block(ctx, n);
   const bool la = (P != S) && n > nb;
   if (!la) P = S;
   size_t ev = 0;

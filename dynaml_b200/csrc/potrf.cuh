@@ -6,6 +6,9 @@ namespace dgp {
 
 int32_t potrf_init(Ctx *ctx);
 
+// Outer block of the blocked Cholesky for an n x n matrix: ctx->nb when set, else chosen from n.
+int64_t potrf_outer_block(const Ctx *ctx, int64_t n);
+
 // In-place right-looking blocked Cholesky of the lower triangle of A (n x n, n % 128 == 0).
 //   A    : on exit L in the lower triangle (diagonal blocks have their upper part zeroed;
 //          tiles strictly above the diagonal are never touched)

@@ -199,9 +199,11 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spe
 int32_t dgp_measure_peaks(dgp_ctx *ctx, double *out, int32_t n);
 /* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
 int32_t dgp_launch_count(const dgp_ctx *ctx, uint64_t *out);
+/* Outer block (trailing-update K) the blocked Cholesky uses for an n x n matrix on this context. */
+int64_t dgp_outer_block(const dgp_ctx *ctx, int64_t n);
 /* Time `reps` launches of one phase on device-resident data: returns average ms per launch.
    phase: 0 assemble (lower tiles of K+noise), 1 potrf of the assembled K, 2 trailing-update GEMM
-   at full size (M = N rows, K = nb).  Used for the roofline of the dominant kernels.            */
+   at full size (M = N - nb rows, K = nb = dgp_outer_block(N): the largest launch of the step).  Used for the roofline of the dominant kernels.            */
 int32_t dgp_time_phase(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec,
                        int32_t phase, int32_t reps, double *avg_ms);
 /* Plain column-major FP64 GEMM / Cholesky on host buffers through the device kernels, for the
