@@ -394,6 +394,8 @@ int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
     ctx->nb = value;
   } else if (!strcmp(key, "lookahead")) {
     ctx->lookahead = value != 0;
+  } else if (!strcmp(key, "gemm_persistent")) {
+    ctx->gemm_persistent = value != 0;
   } else if (!strcmp(key, "gemm_bk")) {
     if (value != 16 && value != 32) return ctx->fail(DGP_ERR_ARG, "gemm_bk must be 16 or 32");
     ctx->gemm_bk = (int)value;

@@ -40,6 +40,7 @@ struct Ctx {
   std::map<std::tuple<int, int, int, int>, std::pair<uint32_t *, size_t>> tile_tables;
   int64_t nb = 0;     // outer Cholesky block (0 = choose from n)
   int lookahead = 1;
+  int gemm_persistent = 1;  // persistent CTAs with a cross-tile pipeline (needs gemm_bk == 32)
   int gemm_bk = 32;   // K-slice of the GEMM pipeline: 16 (3-4 stages) or 32 (double buffered)
   int assembly = 0;   // 0: Gram/DMMA assembly when its error bound allows, 1: always exact differences, 2: force Gram
   int batch_streams = 3;  // dgp_energy_batch evaluates this many candidates concurrently (1..4)

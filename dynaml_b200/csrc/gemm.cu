@@ -222,18 +222,194 @@ __global__ void __launch_bounds__(NTHREADS, 2) dgemm_dmma_kernel(GemmArgs p, con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent variant (BK = 32, double buffered): a CTA walks the tile table with stride gridDim.x
+// and keeps ONE continuous pipeline across tiles -- while the last K-slice of a tile is multiplied
+// the first slice of the next tile is already in flight, and the read-modify-write epilogue runs
+// under it.  The per-tile start-up (tile-table load, address set-up, pipeline fill) that the ncu
+// source view of the one-tile-per-CTA kernel shows as ~8 % long-scoreboard waits at K = 256
+// disappears; grid = min(tiles, 2 CTAs per SM).
+// ---------------------------------------------------------------------------------------------
+struct TileRef {
+  const double *Ag;
+  const double *Bg;
+  int m0, n0, KT;
+  int64_t idx;  // position in the tile table; < 0: none
+};
+
+template <bool AK, bool BKM>
+__device__ __forceinline__ TileRef next_tile(const GemmArgs &p, const uint32_t *__restrict__ tiles, int64_t ntiles,
+                                             int64_t idx, const double *A, const double *B) {
+  TileRef r;
+  r.Ag = nullptr;  r.Bg = nullptr;  r.m0 = r.n0 = r.KT = 0;  r.idx = -1;
+  for (; idx < ntiles; idx += gridDim.x) {
+    const uint32_t tile = tiles[idx];
+    const int m0 = (int)(tile >> 16) * BM, n0 = (int)(tile & 0xffffu) * BN;
+    if (p.bc_T > 0) {
+      const int64_t grow = ((int64_t)(p.bc_row0 + m0 / p.bc_T) * p.bc_Pr + p.bc_pr) * p.bc_T + m0 % p.bc_T;
+      const int64_t gcol = ((int64_t)(p.bc_col0 + n0 / p.bc_T) * p.bc_Pc + p.bc_pc) * p.bc_T + n0 % p.bc_T;
+      if (gcol > grow + BM - 1) continue;
+    }
+    int k_lo = 0, k_hi = p.K;
+    if (p.kmode == K_GE_COL) k_lo = (n0 / 64) * 64;
+    else if (p.kmode == K_LT_ROWEND) k_hi = min(p.K, m0 + BM);
+    else if (p.kmode == K_GE_ROW) k_lo = m0;
+    r.m0 = m0;  r.n0 = n0;  r.KT = (k_hi - k_lo) / 32;  r.idx = idx;
+    r.Ag = AK ? (A + k_lo + (int64_t)m0 * p.lda) : (A + m0 + (int64_t)k_lo * p.lda);
+    r.Bg = BKM ? (B + k_lo + (int64_t)n0 * p.ldb) : (B + n0 + (int64_t)k_lo * p.ldb);
+    return r;
+  }
+  return r;
+}
+
+template <bool AK, bool BKM>
+__global__ void __launch_bounds__(NTHREADS, 2)
+dgemm_dmma_persistent_kernel(GemmArgs p, const uint32_t *__restrict__ tiles, int64_t ntiles) {
+  constexpr int BK = 32;
+  extern __shared__ __align__(16) double smem[];
+  using C_ = Cfg<AK, BKM, BK>;
+  constexpr int A_STAGE = C_::A_STAGE, B_STAGE = C_::B_STAGE, LDS_K = C_::LDS_K;
+  static_assert(C_::STAGES == 2, "the cross-tile pipeline is written for double buffering");
+  double *As = smem;
+  double *Bs = smem + 2 * A_STAGE;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 3, wn = warp >> 2;
+
+  const double *A = p.A + (int64_t)blockIdx.y * p.strideA;
+  const double *B = p.B + (int64_t)blockIdx.y * p.strideB;
+  double *C = p.C + (int64_t)blockIdx.y * p.strideC;
+  const int64_t a_step = AK ? (int64_t)BK : (int64_t)BK * p.lda;
+  const int64_t b_step = BKM ? (int64_t)BK : (int64_t)BK * p.ldb;
+
+  const int a_off = AK ? ((wm * 32 + g) * LDS_K + t) : (t * LDA_MN + wm * 32 + g);
+  const int b_off = BKM ? ((wn * 32 + g) * LDS_K + t) : (t * LDB_MN + wn * 32 + g);
+  constexpr int A_I = AK ? 8 * LDS_K : 8;
+  constexpr int A_KK = AK ? 4 : 4 * LDA_MN;
+  constexpr int B_J = BKM ? 8 * LDS_K : 8;
+  constexpr int B_KK = BKM ? 4 : 4 * LDB_MN;
+  const double alpha = p.alpha, beta = p.beta;
+
+  TileRef cur = next_tile<AK, BKM>(p, tiles, ntiles, blockIdx.x, A, B);
+  if (cur.idx < 0) return;
+  // slice 0 of the first tile
+  if (cur.KT > 0) {
+    load_slice<AK, BM, BK>(As, cur.Ag, p.lda, tid);
+    load_slice<BKM, BN, BK>(Bs, cur.Bg, p.ldb, tid);
+  }
+  cp_async_commit();
+  unsigned gslice = 0;  // global slice counter: stage = gslice & 1
+
+  while (true) {
+    TileRef nxt = next_tile<AK, BKM>(p, tiles, ntiles, cur.idx + gridDim.x, A, B);
+    if (beta != 0.0) {  // pull the C tile towards L2 for the read-modify-write epilogue
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        int c = tid + i * NTHREADS;
+        int col = c >> 3, seg = c & 7;
+        const double *ptr = C + cur.m0 + seg * 16 + (int64_t)(cur.n0 + col) * p.ldc;
+        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ptr));
+      }
+    }
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int cs = 0; cs < cur.KT; ++cs) {
+      cp_async_wait<0>();
+      __syncthreads();
+      {  // next slice: of this tile, or the first one of the next tile
+        const int st = (gslice + 1) & 1;
+        if (cs + 1 < cur.KT) {
+          load_slice<AK, BM, BK>(As + st * A_STAGE, cur.Ag + (int64_t)(cs + 1) * a_step, p.lda, tid);
+          load_slice<BKM, BN, BK>(Bs + st * B_STAGE, cur.Bg + (int64_t)(cs + 1) * b_step, p.ldb, tid);
+        } else if (nxt.idx >= 0 && nxt.KT > 0) {
+          load_slice<AK, BM, BK>(As + st * A_STAGE, nxt.Ag, p.lda, tid);
+          load_slice<BKM, BN, BK>(Bs + st * B_STAGE, nxt.Bg, p.ldb, tid);
+        }
+        cp_async_commit();
+      }
+      const double *as = As + (gslice & 1) * A_STAGE + a_off;
+      const double *bs = Bs + (gslice & 1) * B_STAGE + b_off;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = as[kk * A_KK + i * A_I];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = bs[kk * B_KK + j * B_J];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+      ++gslice;
+    }
+    if (cur.KT == 0 && nxt.idx >= 0 && nxt.KT > 0) {
+      // an empty k-range never started a pipeline slot for this tile: start the next tile's here
+      load_slice<AK, BM, BK>(As + (gslice & 1) * A_STAGE, nxt.Ag, p.lda, tid);
+      load_slice<BKM, BN, BK>(Bs + (gslice & 1) * B_STAGE, nxt.Bg, p.ldb, tid);
+      cp_async_commit();
+    }
+
+    // epilogue of `cur` (the next tile's first slice is already in flight)
+    double *Cw = C + cur.m0 + wm * 32 + g + (int64_t)(cur.n0 + wn * 32 + 2 * t) * p.ldc;
+    if (beta != 0.0) {
+#pragma unroll
+      for (int jh = 0; jh < 2; ++jh) {
+        double old[2][4][2];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) old[jj][i][r] = Cw[i * 8 + (int64_t)((jh * 2 + jj) * 8 + r) * p.ldc];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              Cw[i * 8 + (int64_t)((jh * 2 + jj) * 8 + r) * p.ldc] =
+                  alpha * acc[i][jh * 2 + jj][r] + beta * old[jj][i][r];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) Cw[i * 8 + (int64_t)(j * 8 + r) * p.ldc] = alpha * acc[i][j][r];
+    }
+    if (nxt.idx < 0) break;
+    cur = nxt;
+  }
+  cp_async_wait<0>();
+}
+
 template <bool AK, bool BKM>
 cudaError_t opt_in() {
   cudaError_t e = cudaFuncSetAttribute(dgemm_dmma_kernel<AK, BKM, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg<AK, BKM, 16>::SMEM);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(dgemm_dmma_kernel<AK, BKM, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(dgemm_dmma_kernel<AK, BKM, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)Cfg<AK, BKM, 32>::SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dgemm_dmma_persistent_kernel<AK, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)Cfg<AK, BKM, 32>::SMEM);
 }
 
 template <bool AK, bool BKM>
-void launch(cudaStream_t stream, const GemmArgs &a, dim3 grid, const uint32_t *tiles, int bk) {
-  if (bk == 32) dgemm_dmma_kernel<AK, BKM, 32><<<grid, NTHREADS, Cfg<AK, BKM, 32>::SMEM, stream>>>(a, tiles);
+void launch(cudaStream_t stream, const GemmArgs &a, dim3 grid, const uint32_t *tiles, int bk, int persistent_ctas) {
+  if (bk == 32 && persistent_ctas > 0) {
+    const int64_t ntiles = grid.x;
+    dim3 pg((unsigned)std::min<int64_t>(ntiles, persistent_ctas), grid.y, 1);
+    dgemm_dmma_persistent_kernel<AK, BKM><<<pg, NTHREADS, Cfg<AK, BKM, 32>::SMEM, stream>>>(a, tiles, ntiles);
+  } else if (bk == 32) dgemm_dmma_kernel<AK, BKM, 32><<<grid, NTHREADS, Cfg<AK, BKM, 32>::SMEM, stream>>>(a, tiles);
   else dgemm_dmma_kernel<AK, BKM, 16><<<grid, NTHREADS, Cfg<AK, BKM, 16>::SMEM, stream>>>(a, tiles);
 }
 
@@ -298,6 +474,8 @@ int32_t gemm(Ctx *ctx, cudaStream_t stream, const GemmArgs &a) {
     return ctx->fail(DGP_ERR_SHAPE, "gemm: M=%d N=%d K=%d must be multiples of %d/%d/16", a.M, a.N, a.K, BM, BN);
   // 32-wide slices need every k-range to be a multiple of 32 (triangular ranges are multiples of 64)
   const int bk = (ctx->gemm_bk == 32 && a.K % 32 == 0) ? 32 : 16;
+  // persistent grid: two CTAs per SM, shared among the batch entries
+  const int pc = ctx->gemm_persistent ? std::max(1, 2 * ctx->sm_count / std::max(1, a.batch)) : 0;
   if ((a.lda & 1) || (a.ldb & 1) || ((uintptr_t)a.A & 15) || ((uintptr_t)a.B & 15))
     return ctx->fail(DGP_ERR_SHAPE, "gemm: operands must be 16-byte aligned with even leading dimensions");
   if (a.lower_only && a.M != a.N) return ctx->fail(DGP_ERR_SHAPE, "gemm: lower_only needs a square C");
@@ -308,10 +486,10 @@ int32_t gemm(Ctx *ctx, cudaStream_t stream, const GemmArgs &a) {
   DGP_TRY(get_tiles(ctx, mt, nt, a.lower_only != 0, a.reverse != 0, &tt));
   if (tt.count == 0) return DGP_OK;
   dim3 grid((unsigned)tt.count, (unsigned)a.batch, 1);
-  if (!a.a_kmajor && !a.b_kmajor) launch<false, false>(stream, a, grid, tt.dev, bk);
-  else if (!a.a_kmajor && a.b_kmajor) launch<false, true>(stream, a, grid, tt.dev, bk);
-  else if (a.a_kmajor && !a.b_kmajor) launch<true, false>(stream, a, grid, tt.dev, bk);
-  else launch<true, true>(stream, a, grid, tt.dev, bk);
+  if (!a.a_kmajor && !a.b_kmajor) launch<false, false>(stream, a, grid, tt.dev, bk, pc);
+  else if (!a.a_kmajor && a.b_kmajor) launch<false, true>(stream, a, grid, tt.dev, bk, pc);
+  else if (a.a_kmajor && !a.b_kmajor) launch<true, false>(stream, a, grid, tt.dev, bk, pc);
+  else launch<true, true>(stream, a, grid, tt.dev, bk, pc);
   ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
