@@ -3,6 +3,10 @@
 // measurement / building-block hooks used by tests and bench.py.
 #include <math.h>
 #include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <utility>
 
 #include "assemble.cuh"
 #include "common.cuh"
@@ -118,6 +122,45 @@ double pack_points(const double *X, int64_t n, int d, int layout, int64_t np, in
   return mx;
 }
 
+// True when two of the first n packed rows are equal as points (x - y == 0 in every coordinate).
+// Rows are hashed (with -0.0 folded onto +0.0) and only hash collisions are compared exactly.
+bool has_duplicate_rows(const std::vector<double> &pts, int64_t n, int dp) {
+  std::vector<std::pair<uint64_t, int64_t>> h((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    uint64_t acc = 0x9e3779b97f4a7c15ull;
+    for (int c = 0; c < dp; ++c) {
+      const double v = pts[(size_t)i * dp + c] + 0.0;
+      uint64_t b;
+      memcpy(&b, &v, sizeof b);
+      acc ^= b + 0x9e3779b97f4a7c15ull + (acc << 6) + (acc >> 2);
+      acc *= 0xff51afd7ed558ccdull;
+      acc ^= acc >> 33;
+    }
+    h[(size_t)i] = {acc, i};
+  }
+  std::sort(h.begin(), h.end());
+  for (int64_t i = 1; i < n; ++i) {
+    if (h[(size_t)i].first != h[(size_t)i - 1].first) continue;
+    const double *p = &pts[(size_t)h[(size_t)i].second * dp], *q = &pts[(size_t)h[(size_t)i - 1].second * dp];
+    bool same = true;
+    for (int c = 0; c < dp && same; ++c) same = (p[c] - q[c] == 0.0);
+    if (same) return true;
+  }
+  return false;
+}
+
+// Lean assembly precondition for a training matrix with a noise term: distinct points stay distinct
+// under the kernel's own input scaling (ARD-SE divides by b_c; extreme b_c could collapse them).
+int points_stay_distinct(bool has_dup, const Spec &sp, int d) {
+  if (has_dup) return 0;
+  if (sp.kind == DGP_KERNEL_ARD_SE)
+    for (int c = 0; c < d; ++c) {
+      const double ib = fabs(1.0 / sp.hyp[1 + c]);
+      if (!(ib >= 1e-100 && ib <= 1e100)) return 0;
+    }
+  return 1;
+}
+
 void column_means(const double *X, int64_t n, int d, int layout, std::vector<double> &mean) {
   mean.assign(d, 0.0);
   for (int64_t i = 0; i < n; ++i)
@@ -136,10 +179,7 @@ int pick_gram(const Ctx *ctx, const Spec &sp, const CovParams &cp, int dp, int d
       cp.kind != DGP_KERNEL_MATERN)
     return 0;
   if (dp > 32) return 0;
-  if (ctx->assembly == 2) return 1;
-  // measured on B200 (profiles/assemble_r1.json): the Gram kernel wins from 16 features up (Matern-5/2 d = 16:
-  // 0.88 vs 1.08 ms at N = 16384); below that the exact-difference kernel is faster (SE d = 8: 0.42 vs 0.57 ms)
-  if (dp < 16) return 0;
+  if (ctx->assembly >= 2) return 1;
   double scale = 1.0;
   if (sp.kind == DGP_KERNEL_ARD_SE) {
     scale = 0.0;
@@ -180,6 +220,8 @@ int32_t scaled_points(Ctx *ctx, cudaStream_t st, const Spec &sp, const double *X
 }
 
 }  // namespace
+
+int points_stay_distinct_pub(bool has_dup, const Spec &sp, int d) { return points_stay_distinct(has_dup, sp, d); }
 
 int pick_gram_pub(const Ctx *ctx, const Spec &sp, const CovParams &cp, int dp, int d, double max_sq_norm) {
   return pick_gram(ctx, sp, cp, dp, d, max_sq_norm);
@@ -251,6 +293,7 @@ int32_t enqueue_eval(Ctx *ctx, int slot, const Data *D, const Spec &sp, bool wan
   a.out = K;  a.ld = np;
   a.symmetric = 1;  a.lower_only = 1;
   a.use_gram = pick_gram(ctx, sp, cp, D->dp, D->d, D->max_sq_norm);
+  a.nodup = points_stay_distinct(D->has_dup, sp, D->d);
   DGP_TRY(assemble(ctx, S, cp, a));
   tick(ctx, slot, 1);
   DGP_CUDA_OK(ctx, cudaMemsetAsync(d_info, 0, sizeof(int), S));
@@ -400,7 +443,8 @@ int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
     if (value != 16 && value != 32) return ctx->fail(DGP_ERR_ARG, "gemm_bk must be 16 or 32");
     ctx->gemm_bk = (int)value;
   } else if (!strcmp(key, "assembly")) {
-    if (value < 0 || value > 2) return ctx->fail(DGP_ERR_ARG, "assembly must be 0 (auto), 1 (exact differences) or 2 (Gram)");
+    if (value < 0 || value > 3)
+      return ctx->fail(DGP_ERR_ARG, "assembly must be 0 (auto), 1 (exact differences), 2 (Gram) or 3 (checked Gram)");
     ctx->assembly = (int)value;
   } else if (!strcmp(key, "batch_streams")) {
     if (value < 1 || value > 4) return ctx->fail(DGP_ERR_ARG, "batch_streams must be in 1..4");
@@ -433,6 +477,7 @@ int32_t dgp_data_create(dgp_ctx *ctx, const double *X, int64_t N, int32_t d, int
   std::vector<double> hx, hr((size_t)D->Np, 0.0);
   column_means(X, N, d, x_layout, D->center);
   D->max_sq_norm = pack_points(X, N, d, x_layout, D->Np, D->dp, hx, D->center.data());
+  D->has_dup = has_duplicate_rows(hx, N, D->dp);
   for (int64_t i = 0; i < N; ++i) hr[i] = y[i] - (mean ? mean[i] : 0.0);
   cudaError_t e1 = cudaMalloc(&D->X, hx.size() * sizeof(double));
   cudaError_t e2 = cudaMalloc(&D->r, hr.size() * sizeof(double));
@@ -627,6 +672,7 @@ int32_t dgp_fit(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *spec, dg
   a.rows = D->N;  a.cols = D->N;  a.rows_p = np;  a.cols_p = np;
   a.out = m->L;  a.ld = np;  a.symmetric = 1;  a.lower_only = 1;
   a.use_gram = pick_gram(ctx, sp, cp, D->dp, D->d, D->max_sq_norm);
+  a.nodup = points_stay_distinct(D->has_dup, sp, D->d);
   int32_t st = assemble(ctx, S, cp, a);
   if (st != DGP_OK) return bail(st);
   tick(ctx, 0, 1);
@@ -816,6 +862,7 @@ int32_t dgp_kernel_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec, const doubl
   a.symmetric = sym ? 1 : 0;
   a.lower_only = sym ? 1 : 0;  // SVMKernel.scala:77-86 evaluates i >= j and mirrors: bitwise symmetric
   a.use_gram = pick_gram(ctx, sp, cp, dp, d, nmax);
+  if (sym && add_noise && a.use_gram) a.nodup = points_stay_distinct(has_duplicate_rows(h1, N1, dp), sp, d);
   tick(ctx, 0, 0);
   DGP_TRY(assemble(ctx, S, cp, a));
   if (sym) DGP_TRY(mirror_lower(ctx, S, Kd, n1p, n1p));
@@ -867,6 +914,7 @@ int32_t dgp_time_phase(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *s
   a.rows = D->N;  a.cols = D->N;  a.rows_p = np;  a.cols_p = np;
   a.out = K;  a.ld = np;  a.symmetric = 1;  a.lower_only = 1;
   a.use_gram = pick_gram(ctx, sp, cp, D->dp, D->d, D->max_sq_norm);
+  a.nodup = points_stay_distinct(D->has_dup, sp, D->d);
   double total = 0.0;
   for (int r = 0; r < reps; ++r) {
     float ms = 0.f;

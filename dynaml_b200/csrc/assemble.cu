@@ -289,7 +289,10 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_gram_kernel(CovParams cp
 
   int64_t tlin = blockIdx.x;
   int ti, tj;
-  if (a.lower_only) {
+  if (a.diag_only && a.lower_only && a.bc_T == 0) {
+    ti = (int)(a.rows_p / AT) - 1;  // the launch covers the last tile row (the padded one)
+    tj = (int)tlin;
+  } else if (a.lower_only) {
     ti = (int)((sqrt(8.0 * (double)tlin + 1.0) - 1.0) * 0.5);
     while ((int64_t)ti * (ti + 1) / 2 > tlin) --ti;
     while ((int64_t)(ti + 1) * (ti + 2) / 2 <= tlin) ++ti;
@@ -306,6 +309,8 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_gram_kernel(CovParams cp
     n0 = ((int64_t)(ln0 / a.bc_T) * a.bc_Pc + a.bc_pc) * a.bc_T + ln0 % a.bc_T;
     if (n0 > m0 + AT - 1) return;
   }
+  // diag_only (edge pass): just the tiles assemble_gram_lean_kernel leaves out, those touching the padding
+  if (a.diag_only && !(m0 + AT > a.rows || n0 + AT > a.cols)) return;
 
   // ---- augmented operands: thread p < 128 builds row point p, thread p >= 128 column point p-128 ----
   double nrm;
@@ -419,6 +424,285 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_gram_kernel(CovParams cp
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// v3: lean Gram epilogue for tiles in which no pair can be at distance exactly zero (every tile of
+// a cross matrix without noise; the strictly-lower tiles of a training matrix whose points are
+// pairwise distinct -- Data::has_dup is established once on the host).  There the only use of the
+// exact-difference fallback, DiracKernel's |x-y| == 0 test, cannot fire, and the relative error of
+// an entry is bounded by the same slope * KA * eps * 2 max|x|^2 the host gate checks (k is smooth
+// in r^2, so a small r^2 does not amplify it).  Diagonal tiles go to assemble_gram_kernel.
+//
+// Per entry: 1 DADD (|x|^2 + |y|^2 seeds the accumulator) + DP DMMA slots (-2 x.y) + epilogue of
+//   SE      x = -c r^2; n = rint(64 x / ln 2); r = x - n ln2/64 (two FMAs); degree-5 polynomial;
+//           a^2 2^(j/64) from a 64-entry shared-memory table; exponent added as an integer: 10 DFMA/DMUL/DADD
+//   Matern  clamp; MUFU.RSQ64H seed + one Goldschmidt step + one Newton correction (7); polynomial in r (3);
+//           the exponential as above (10) and one product
+// against ~45 (SE) / ~75 (Matern) instructions in v2's epilogue.  16 columns x 32 rows per warp and pass
+// keep the accumulators at 32 registers so that three CTAs fit per SM.
+// ---------------------------------------------------------------------------------------------
+struct LeanCov {
+  double c1;          // SE: 1/(2 l^2);  Matern: sqrt(2 nu)/l
+  double m0, m1, m2, m3;  // Matern: polynomial in r, coefficients right-aligned (m3 is the constant term)
+};
+
+__device__ __forceinline__ double rsqrt_seed(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));  // MUFU.RSQ64H, ~2^-22 relative
+  return y;
+}
+
+// exp(x) * scale for x <= ~0, scale folded into the table; exact zero below e^-700 like fast_exp_nonpos_v.
+// Every instruction that is not FP64 arithmetic still costs FP64-pipe time on this part
+// (scripts/ubench/fp64_mix.cu: the same FP64 sequence retires at 2.0 warp-instructions/clk/SM alone,
+// 1.76 with the integer epilogue and 1.49 with the table load), so the integer side is pared down:
+// the reduction constants come from the kernel parameters (constant-bank operands, no MOVs), the
+// table address is one shift + one LOP3 into a 512-byte-aligned table, the exponent one LOP3 + one
+// shift-add, and the underflow test is one integer minimum per four entries with a cold fix-up branch.
+struct LeanConst {
+  double l2e64, ln2hi64, ln2lo64, c5, c4, c3;
+};
+
+template <int V>
+__device__ __forceinline__ void lean_exp_v(const double (&x)[V], const LeanConst &c, unsigned tab_s,
+                                           double (&out)[V]) {
+  const double SHIFT = 6755399441055744.0;
+  int n[V];
+  double r[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const double t = fma(x[v], c.l2e64, SHIFT);
+    n[v] = __double2loint(t);
+    const double nd = t - SHIFT;
+    r[v] = fma(nd, -c.ln2lo64, fma(nd, -c.ln2hi64, x[v]));
+  }
+  int nmin = n[0];
+#pragma unroll
+  for (int v = 1; v < V; ++v) nmin = min(nmin, n[v]);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    double p = fma(r[v], c.c5, c.c4);
+    p = fma(p, r[v], c.c3);
+    p = fma(p, r[v], 0.5);
+    p = fma(p, r[v], 1.0);
+    p = fma(p, r[v], 1.0);
+    double tj;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab_s | ((unsigned)(n[v] << 3) & 0x1f8u)));
+    const double w = tj * p;
+    const int hi = __double2hiint(w) + (n[v] >> 6) * 0x100000;  // exponent += n >> 6
+    out[v] = __hiloint2double(hi, __double2loint(w));
+  }
+  if (nmin < -64634) {  // some x < -700: rare, kept out of the straight-line code
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      if (n[v] < -64634) out[v] = 0.0;
+  }
+}
+
+template <int DP>
+__host__ __device__ constexpr int lean_ldk() { return (DP % 8 == 0) ? DP + 4 : DP; }  // == 4 mod 8 doubles
+
+struct ExpTab {
+  double v[64];  // amplitude * 2^(j/64), built on the host per launch
+};
+
+// P3: Matern order 3 (cubic polynomial in r); orders 1 and 2 share the quadratic form.
+template <int KIND, int DP, bool P3>
+__global__ void __launch_bounds__(ATHREADS, 3)
+    assemble_gram_lean_kernel(LeanCov f, LeanConst lc, ExpTab T, double kdiag, AssembleArgs a) {
+  constexpr int LDK = lean_ldk<DP>();
+  extern __shared__ __align__(16) double sm_raw[];
+  // the exp table first, on a 512-byte boundary (its address is OR-ed with the index)
+  const unsigned raw_s = (unsigned)__cvta_generic_to_shared(sm_raw);
+  const unsigned tab_s = (raw_s + 511u) & ~511u;
+  double *tab = sm_raw + (tab_s - raw_s) / 8;
+  double *Brow = tab + 64;              // row points i (MMA N):    [i][k] = x
+  double *Acol = Brow + AT * LDK;       // column points j (MMA M): [j][k] = -2 y
+  double *nx = Acol + AT * LDK;         // |x_i|^2
+  double *ny = nx + AT;                 // |y_j|^2
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;
+
+  int64_t tlin = blockIdx.x;
+  int ti, tj;
+  if (a.lower_only) {
+    // FP32 estimate of the triangular root, corrected by the two loops (no FP64 sqrt chain in the prologue)
+    ti = (int)((sqrtf(8.0f * (float)tlin + 1.0f) - 1.0f) * 0.5f);
+    while ((int64_t)ti * (ti + 1) / 2 > tlin) --ti;
+    while ((int64_t)(ti + 1) * (ti + 2) / 2 <= tlin) ++ti;
+    tj = (int)(tlin - (int64_t)ti * (ti + 1) / 2);
+  } else {
+    int mt = (int)(a.rows_p / AT);
+    tj = (int)(tlin / mt);
+    ti = (int)(tlin % mt);
+  }
+  int64_t m0 = (int64_t)ti * AT + a.row_off, n0 = (int64_t)tj * AT + a.col_off;
+  const int64_t lm0 = m0, ln0 = n0;
+  if (a.bc_T > 0) {
+    m0 = ((int64_t)(lm0 / a.bc_T) * a.bc_Pr + a.bc_pr) * a.bc_T + lm0 % a.bc_T;
+    n0 = ((int64_t)(ln0 / a.bc_T) * a.bc_Pc + a.bc_pc) * a.bc_T + ln0 % a.bc_T;
+    if (n0 > m0 + AT - 1) return;
+  }
+  // tiles touching the padding are left to assemble_gram_kernel (edge pass)
+  if (m0 + AT > a.rows || n0 + AT > a.cols) return;
+  // diagonal tile of a symmetric matrix: the launch side guarantees that only i == j is at distance zero
+  // (or that there is no noise term), so those entries are simply k(0) + noise
+  const bool diag_tile = a.symmetric && m0 == n0;
+
+  {
+    const bool is_row = tid < AT;
+    const int pidx = is_row ? tid : tid - AT;
+    const double *src = is_row ? (a.X1 + (m0 + pidx) * DP) : (a.X2 + (n0 + pidx) * DP);
+    double *dst = (is_row ? Brow : Acol) + pidx * LDK;
+    double v[DP];
+#pragma unroll
+    for (int c = 0; c < DP / 2; ++c) {
+      const double2 q = reinterpret_cast<const double2 *>(src)[c];
+      v[2 * c] = q.x;
+      v[2 * c + 1] = q.y;
+    }
+    double nrm = 0.0;
+#pragma unroll
+    for (int c = 0; c < DP; ++c) nrm = fma(v[c], v[c], nrm);
+    const double sc = is_row ? 1.0 : -2.0;
+#pragma unroll
+    for (int c = 0; c < DP / 2; ++c)
+      reinterpret_cast<double2 *>(dst)[c] = make_double2(sc * v[2 * c], sc * v[2 * c + 1]);
+    (is_row ? nx : ny)[pidx] = nrm;
+    if (tid < 64) tab[tid] = T.v[tid];
+  }
+  __syncthreads();
+
+  double *out = a.out + (lm0 - a.row_off) + (ln0 - a.col_off) * a.ld;
+  const int ibase = wn * 32;
+  const double *bp = Brow + (ibase + g) * LDK + t;
+#pragma unroll 1
+  for (int chunk = 0; chunk < 4; ++chunk) {
+    const int jbase = chunk * 32 + wm * 16;
+    const double *ap = Acol + (jbase + g) * LDK + t;
+    double acc[2][4][2];
+    {
+      const double y0 = ny[jbase + g], y1 = ny[jbase + 8 + g];
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) {
+        const double2 xn = *reinterpret_cast<const double2 *>(nx + ibase + nb * 8 + 2 * t);
+        acc[0][nb][0] = y0 + xn.x;  acc[0][nb][1] = y0 + xn.y;
+        acc[1][nb][0] = y1 + xn.x;  acc[1][nb][1] = y1 + xn.y;
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < DP / 4; ++kk) {
+      double af[2], bf[4];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) af[mb] = ap[mb * 8 * LDK + kk * 4];
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) bf[nb] = bp[nb * 8 * LDK + kk * 4];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                       : "+d"(acc[mb][nb][0]), "+d"(acc[mb][nb][1])
+                       : "d"(af[mb]), "d"(bf[nb]));
+    }
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+      const int jl = jbase + mb * 8 + g;
+      double *ocol = out + (int64_t)jl * a.ld + ibase + 2 * t;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        double x[4], kv[4];
+        if (KIND == DGP_KERNEL_MATERN) {
+          double r[4], s[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            // clamp to >= ~1e-290 on the high word (an integer max: negative and tiny values alike)
+            const double av = acc[mb][2 * q + (u >> 1)][u & 1];
+            const double v = __hiloint2double(max(__double2hiint(av), 0x03c00000), __double2loint(av));
+            // sqrt: 2^-22 seed, one Goldschmidt step (-> 2^-43), one Newton correction with the seed's
+            // half reciprocal (its 2^-22 error only scales the 2^-43 residual)
+            const double y = rsqrt_seed(v);
+            double gg = v * y;
+            const double hh = 0.5 * y;
+            const double e = fma(-gg, hh, 0.5);
+            gg = fma(gg, e, gg);
+            const double dd = fma(-gg, gg, v);
+            r[u] = fma(dd, hh, gg);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            double p = P3 ? fma(f.m0, r[u], f.m1) : f.m1;
+            p = fma(p, r[u], f.m2);
+            s[u] = fma(p, r[u], f.m3);
+            x[u] = -f.c1 * r[u];
+          }
+          lean_exp_v<4>(x, lc, tab_s, kv);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) kv[u] *= s[u];
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) x[u] = -f.c1 * acc[mb][2 * q + (u >> 1)][u & 1];
+          lean_exp_v<4>(x, lc, tab_s, kv);
+        }
+        *reinterpret_cast<double2 *>(ocol + (2 * q) * 8) = make_double2(kv[0], kv[1]);
+        *reinterpret_cast<double2 *>(ocol + (2 * q + 1) * 8) = make_double2(kv[2], kv[3]);
+      }
+    }
+  }
+  if (diag_tile) {  // CTA-uniform; the barrier orders these stores after the tile's own
+    __syncthreads();
+    if (tid < AT) out[tid + (int64_t)tid * a.ld] = kdiag;
+  }
+}
+
+template <int KIND, int DP>
+void launch_lean(cudaStream_t st, const CovParams &cp, const AssembleArgs &a, unsigned tiles) {
+  LeanCov f;
+  f.c1 = cp.c1;
+  f.m0 = f.m1 = f.m2 = f.m3 = 0.0;
+  if (KIND == DGP_KERNEL_MATERN) {  // sum_i coef[i] (c2 r)^(p-i), right-aligned in m0..m3
+    double *m[4] = {&f.m0, &f.m1, &f.m2, &f.m3};
+    for (int i = 0; i <= cp.p; ++i) *m[3 - (cp.p - i)] = cp.coef[i] * pow(cp.c2, (double)(cp.p - i));
+  }
+  const double a2 = (KIND == DGP_KERNEL_MATERN) ? 1.0 : cp.a2;
+  ExpTab T;
+  for (int j = 0; j < 64; ++j) T.v[j] = a2 * exp2((double)j / 64.0);
+  LeanConst lc;
+  lc.l2e64 = 92.33248261689366;         // 64 / ln 2
+  lc.ln2hi64 = 0.01083042469326756;     // ln2/64 with the low 21 bits cleared (n * ln2hi64 is exact)
+  lc.ln2lo64 = 2.9815858269852933e-12;
+  lc.c5 = 1.0 / 120.0;  lc.c4 = 1.0 / 24.0;  lc.c3 = 1.0 / 6.0;
+  // value at distance zero plus the noise term (DiracKernel.scala:43-47 adds |sigma| where |x-y| == 0)
+  const double kdiag = ((KIND == DGP_KERNEL_MATERN) ? cp.coef[cp.p] : cp.a2) + cp.noise_abs;
+  size_t smem = ((size_t)2 * AT * lean_ldk<DP>() + 2 * AT + 64) * sizeof(double) + 512;
+  auto go = [&](auto kern) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<tiles, ATHREADS, smem, st>>>(f, lc, T, kdiag, a);
+  };
+  if constexpr (KIND == DGP_KERNEL_MATERN) {
+    if (cp.p == 3) {
+      go(assemble_gram_lean_kernel<KIND, DP, true>);
+      return;
+    }
+  }
+  go(assemble_gram_lean_kernel<KIND, DP, false>);
+}
+
+template <int KIND>
+bool launch_lean_kind(cudaStream_t st, const CovParams &cp, const AssembleArgs &a, unsigned tiles) {
+  switch (a.dp) {
+    case 4: launch_lean<KIND, 4>(st, cp, a, tiles); return true;
+    case 8: launch_lean<KIND, 8>(st, cp, a, tiles); return true;
+    case 12: launch_lean<KIND, 12>(st, cp, a, tiles); return true;
+    case 16: launch_lean<KIND, 16>(st, cp, a, tiles); return true;
+    case 20: launch_lean<KIND, 20>(st, cp, a, tiles); return true;
+    case 24: launch_lean<KIND, 24>(st, cp, a, tiles); return true;
+    case 32: launch_lean<KIND, 32>(st, cp, a, tiles); return true;
+    default: return false;
+  }
+}
+
 template <int KIND, int DP>
 void launch_gram(cudaStream_t st, const CovParams &cp, const AssembleArgs &a, unsigned tiles) {
   size_t smem = (size_t)2 * AT * gram_ldk(DP) * sizeof(double);
@@ -475,11 +759,31 @@ int32_t assemble(Ctx *ctx, cudaStream_t st, const CovParams &cp, const AssembleA
   int64_t tiles = a.lower_only ? mt * (mt + 1) / 2 : mt * nt;
   if (tiles == 0) return DGP_OK;
   bool done = false;
-  if (a.use_gram) {
-    if (cp.kind == DGP_KERNEL_SE || cp.kind == DGP_KERNEL_RBF || cp.kind == DGP_KERNEL_ARD_SE)
-      done = launch_gram_kind<DGP_KERNEL_SE>(st, cp, a, (unsigned)tiles);
-    else if (cp.kind == DGP_KERNEL_MATERN && cp.p <= 3)
-      done = launch_gram_kind<DGP_KERNEL_MATERN>(st, cp, a, (unsigned)tiles);
+  const bool se_like = cp.kind == DGP_KERNEL_SE || cp.kind == DGP_KERNEL_RBF || cp.kind == DGP_KERNEL_ARD_SE;
+  const bool matern_ok = cp.kind == DGP_KERNEL_MATERN && cp.p <= 3;
+  if (a.use_gram && (se_like || matern_ok)) {
+    // lean epilogue wherever no pair can be at distance zero; the amplitude is folded into its exp table,
+    // so it must be far from the exponent limits
+    const bool lean = ctx->assembly != 3 && (cp.noise_abs == 0.0 || (a.symmetric && a.nodup)) &&
+                      cp.a2 >= 1e-150 && cp.a2 <= 1e150;
+    if (lean) {
+      done = se_like ? launch_lean_kind<DGP_KERNEL_SE>(st, cp, a, (unsigned)tiles)
+                     : launch_lean_kind<DGP_KERNEL_MATERN>(st, cp, a, (unsigned)tiles);
+      const bool padded = a.rows_p != a.rows || a.cols_p != a.cols;
+      if (done && padded) {  // edge pass: tiles touching the padding, with the checked epilogue
+        AssembleArgs ad = a;
+        ad.diag_only = 1;
+        const unsigned etiles = (a.lower_only && a.bc_T == 0) ? (unsigned)mt : (unsigned)tiles;
+        if (se_like) launch_gram_kind<DGP_KERNEL_SE>(st, cp, ad, etiles);
+        else launch_gram_kind<DGP_KERNEL_MATERN>(st, cp, ad, etiles);
+        ctx->launches++;
+      }
+    } else if (a.dp >= 16 || ctx->assembly >= 2) {
+      // measured on B200 (profiles/assemble_r1.json): with the checked epilogue the Gram kernel only wins
+      // from 16 features up (Matern-5/2 d = 16: 0.88 vs 1.08 ms at N = 16384; SE d = 8: 0.57 vs 0.42 ms)
+      done = se_like ? launch_gram_kind<DGP_KERNEL_SE>(st, cp, a, (unsigned)tiles)
+                     : launch_gram_kind<DGP_KERNEL_MATERN>(st, cp, a, (unsigned)tiles);
+    }
   }
   if (!done) switch (cp.kind) {
     case DGP_KERNEL_SE:

@@ -26,6 +26,11 @@ struct AssembleArgs {
   // 1: Gram/DMMA distance kernel (SE, RBF, ARD-SE, Matern with dp <= 32); the caller sets it only when
   // gram_is_accurate() holds.  0: exact-difference kernel.
   int use_gram = 0;
+  // 1: the points of a symmetric assembly are pairwise distinct (Data::has_dup == false and the ARD
+  // scaling cannot collapse them), so zero distances occur on the diagonal only and the strictly-lower
+  // tiles may take the lean Gram epilogue even with a Dirac noise term.
+  int nodup = 0;
+  int diag_only = 0;  // internal (edge pass): assemble_gram_kernel produces only the tiles touching the padding
 };
 
 // Relative error bound of a kernel entry under the Gram formulation: |d log k / d r^2| * KA * eps * 2*max|x|^2.

@@ -40,7 +40,7 @@ struct Ctx {
   std::map<std::tuple<int, int, int, int>, std::pair<uint32_t *, size_t>> tile_tables;
   int64_t nb = 0;     // outer Cholesky block (0 = choose from n)
   int lookahead = 1;
-  int gemm_persistent = 1;  // persistent CTAs with a cross-tile pipeline (needs gemm_bk == 32)
+  int gemm_persistent = 0;  // 1: persistent CTAs with a cross-tile pipeline (measured 3-8 % slower; kept as an experiment)
   int gemm_bk = 32;   // K-slice of the GEMM pipeline: 16 (3-4 stages) or 32 (double buffered)
   int assembly = 0;   // 0: Gram/DMMA assembly when its error bound allows, 1: always exact differences, 2: force Gram
   int batch_streams = 3;  // dgp_energy_batch evaluates this many candidates concurrently (1..4)
@@ -88,6 +88,7 @@ struct Data {
   // translation invariant, and small norms keep the Gram-form distances accurate.
   std::vector<double> center;  // d column means of the original inputs
   double max_sq_norm = 0.0;    // max_i |x_i - center|^2
+  bool has_dup = true;         // two training points coincide (decides where Dirac noise can land)
 };
 
 // Host copy of a kernel spec with derived constants.

@@ -41,6 +41,7 @@ namespace dgp {
 
 int32_t scaled_points_pub(Ctx *ctx, cudaStream_t st, const Spec &sp, const double *X, int64_t np, int dp, int d,
                           const char *bufname, const double **out);  // api.cu
+int points_stay_distinct_pub(bool has_dup, const Spec &sp, int d);
 int pick_gram_pub(const Ctx *ctx, const Spec &sp, const CovParams &cp, int dp, int d, double max_sq_norm);
 
 struct NcclApi {
@@ -421,6 +422,7 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *
     a.symmetric = 1;
     a.bc_T = T;  a.bc_Pr = ds->Pr;  a.bc_Pc = ds->Pc;  a.bc_pr = R.pr;  a.bc_pc = R.pc;
     a.use_gram = pick_gram_pub(ctx, sp, cp, D->dp, D->d, D->max_sq_norm);
+    a.nodup = points_stay_distinct_pub(D->has_dup, sp, D->d);
     DGP_TRY(assemble(ctx, S, cp, a));
   }
   DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_a, S));

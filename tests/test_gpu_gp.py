@@ -355,6 +355,45 @@ def test_gram_assembly_feature_counts_offsets_and_duplicates(gram_ctx, d):
     assert K[17, 5] == 1.25 and K[200, 17] == 1.25 and K[3, 3] == 1.25
 
 
+@pytest.mark.parametrize("d", [1, 3, 8, 13, 16, 24, 32])
+@pytest.mark.parametrize("name", ["se", "ard_ref", "matern1", "matern2", "matern3"])
+def test_lean_gram_assembly_many_tiles(gram_ctx, name, d):
+    """Pairwise-distinct, uncentred points over several 128-tiles: the strictly-lower tiles take the lean
+    epilogue (table-based exp, MUFU seed sqrt), the diagonal / padded tiles the checked one; noise lands on
+    the diagonal only.  Also the rectangular cross matrix (every full tile lean, no noise)."""
+    rng = np.random.default_rng(300 + d)
+    X = rng.standard_normal((700, d)) * 1.5 + 20.0
+    Xs = rng.standard_normal((450, d)) * 1.5 + 20.0
+    band = np.linspace(1.5, 3.0, d)
+    k, ok = make_pair(name, d, band)
+    K = (k + dg.DiracKernel(0.3)).buildKernelMatrix(X, len(X)).getKernelMatrix()
+    Ko = orc.build_kernel_matrix(ok, X, orc.dirac(0.3))
+    assert entry_rel(K, Ko) <= TOL_K
+    assert np.array_equal(K, K.T)
+    C = k.buildCrossKernelMatrix(X, Xs)
+    assert entry_rel(C, orc.cross_kernel_matrix(ok, X, Xs)) <= TOL_K
+    gram_ctx.set_option("assembly", 3)  # the checked epilogue on every tile
+    K3 = (k + dg.DiracKernel(0.3)).buildKernelMatrix(X, len(X)).getKernelMatrix()
+    assert entry_rel(K, K3) <= 1e-13
+
+
+def test_lean_gram_assembly_underflow_and_exact_multiple_of_tile(gram_ctx):
+    """N a multiple of 128 (no padded tiles); a short length scale drives most entries through the
+    flush-to-zero branch of the lean exponential."""
+    rng = np.random.default_rng(9)
+    X = rng.standard_normal((512, 8)) * 4.0
+    for k, ok in ((dg.SEKernel(0.45, 2.0), orc.Kernel("se", {"bandwidth": 0.45, "amplitude": 2.0})),
+                  (dg.GenericMaternKernel(0.05, 2), orc.Kernel("matern", {"p": 2.0, "l": 0.05}))):
+        K = k.buildKernelMatrix(X, len(X)).getKernelMatrix()
+        Ko = orc.build_kernel_matrix(ok, X)
+        assert (Ko < 1e-300).mean() > 0.1 and (Ko > 1e-280).mean() > 0.1
+        # forced Gram at this length scale is outside the accuracy gate: compare where the gate's bound
+        # (slope * 12 eps * 2 max|x|^2) still leaves 1e-9, and require exact zeros where the oracle has them
+        assert np.all(K[Ko == 0.0] == 0.0)
+        big = Ko > 1e-280
+        assert float((np.abs(K - Ko)[big] / Ko[big]).max()) <= 1e-9
+
+
 def test_gram_and_direct_energies_agree(ctx):
     X, y, _ = orc.synthetic(1500, 16, seed=77)
     spec = dg.GenericMaternKernel(4.0, 2)._spec(noise=0.1)
