@@ -7,9 +7,9 @@ library or an sm_100 device is missing (there is no CPU fallback).
 """
 from . import _capi
 from ._capi import Context, DgpError, NotPositiveDefinite, default_context
-from .kernels import (AdditiveCovariance, CauchyKernel, DiracKernel, GenericMaternKernel, LaplacianKernel,
-                      LocalScalarKernel, MahalanobisKernel, PeriodicKernel, RationalQuadraticKernel, RBFKernel,
-                      SEKernel, SVMKernelMatrix, TStudentKernel)
+from .kernels import (AdditiveCovariance, CauchyKernel, CompositeCovariance, DiracKernel, GenericMaternKernel,
+                      LaplacianKernel, LocalScalarKernel, MahalanobisKernel, MultiplicativeCovariance, PeriodicKernel,
+                      RationalQuadraticKernel, RBFKernel, ScaledKernel, SEKernel, SVMKernelMatrix, TStudentKernel)
 from .models import AbstractGPRegressionModel, CudaGPRegression, GPRegression, MultGaussianPRV
 from .stp import AbstractSTPRegressionModel, MultStudentsTPRV, STPRegression
 from .optimization import CoupledSimulatedAnnealing, GradBasedGlobalOptimizer, GridSearch, ModelTuner
@@ -17,7 +17,8 @@ from .optimization import CoupledSimulatedAnnealing, GradBasedGlobalOptimizer, G
 __all__ = [
     "Context", "DgpError", "NotPositiveDefinite", "default_context",
     "LocalScalarKernel", "SEKernel", "RBFKernel", "MahalanobisKernel", "GenericMaternKernel", "PeriodicKernel",
-    "DiracKernel", "AdditiveCovariance", "SVMKernelMatrix",
+    "DiracKernel", "AdditiveCovariance", "MultiplicativeCovariance", "CompositeCovariance", "ScaledKernel",
+    "SVMKernelMatrix",
     "CauchyKernel", "LaplacianKernel", "RationalQuadraticKernel", "TStudentKernel",
     "GPRegression", "CudaGPRegression", "AbstractGPRegressionModel", "MultGaussianPRV",
     "STPRegression", "AbstractSTPRegressionModel", "MultStudentsTPRV",

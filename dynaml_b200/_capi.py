@@ -33,6 +33,7 @@ EXPORTS = [
     "dgp_energy_grad", "dgp_energy_batch", "dgp_fit", "dgp_model_destroy", "dgp_model_energy", "dgp_model_terms",
     "dgp_predict", "dgp_dist_unique_id", "dgp_dist_init", "dgp_dist_finalize", "dgp_dist_plan", "dgp_dist_energy",
     "dgp_measure_peaks", "dgp_launch_count", "dgp_outer_block", "dgp_time_phase", "dgp_test_gemm", "dgp_test_potrf",
+    "dgp_spec_grad_len",
 ]
 
 
@@ -99,6 +100,7 @@ def load_library() -> C.CDLL:
         "dgp_time_phase": (i32, [vp, vp, sp, i32, i32, _dp]),
         "dgp_test_gemm": (i32, [vp, i32, i32, i64, i64, i64, f64, _dp, i64, _dp, i64, f64, _dp, i64, i32, _dp]),
         "dgp_test_potrf": (i32, [vp, i64, _dp, i64, _dp, _dp, _dp, _dp]),
+        "dgp_spec_grad_len": (i32, [sp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -120,6 +122,26 @@ def make_spec(kind: int, hyp, noise: float = 0.0, grad_mode: int = GRAD_REFERENC
     h = np.ascontiguousarray(np.asarray(hyp, dtype=np.float64).ravel())
     s = KernelSpec(kind, h.size, grad_mode, 0, h.ctypes.data_as(_dp), float(noise))
     return s, h
+
+
+KERNEL_COMPOSITE = 10
+MAX_FACTORS, MAX_TERMS = 6, 16
+
+
+def make_composite_spec(factors, terms, noise: float = 0.0):
+    """DGP_KERNEL_COMPOSITE: k = sum_t coef_t prod_f k_f^e_tf.  `factors` = [(kind, grad_mode, hyp), ...];
+    `terms` = [(coef, [e_0 .. e_{F-1}]), ...].  Returns (KernelSpec, keepalive) like make_spec."""
+    if not (1 <= len(factors) <= MAX_FACTORS and 1 <= len(terms) <= MAX_TERMS):
+        raise ValueError(f"a composite kernel takes 1..{MAX_FACTORS} base kernels and 1..{MAX_TERMS} terms "
+                         f"(got {len(factors)}, {len(terms)}); no CPU fallback")
+    prog = [float(len(factors)), float(len(terms))]
+    for kind, grad_mode, hyp in factors:
+        hyp = [float(v) for v in hyp]
+        prog += [float(kind), float(grad_mode), float(len(hyp))] + hyp
+    for coef, expo in terms:
+        assert len(expo) == len(factors)
+        prog += [float(coef)] + [float(e) for e in expo]
+    return make_spec(KERNEL_COMPOSITE, prog, noise, GRAD_REFERENCE)
 
 
 class Context:
@@ -229,10 +251,13 @@ class Context:
     def energy_grad(self, data, spec):
         s, keep = spec
         e = C.c_double()
-        g = np.empty(s.n_hyp + 1)
+        ng = int(self.lib.dgp_spec_grad_len(C.byref(s)))
+        if ng < 0:
+            raise DgpError(-ng, "malformed kernel spec")
+        g = np.empty(ng)
         st = self.lib.dgp_energy_grad(self.h, data, C.byref(s), C.cast(C.byref(e), _dp), _ptr(g))
         if st == DGP_ERR_NOT_PD:
-            return float("inf"), np.full(s.n_hyp + 1, np.nan)  # :243-251
+            return float("inf"), np.full(ng, np.nan)  # :243-251
         self.check(st)
         return e.value, g
 

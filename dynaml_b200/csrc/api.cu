@@ -68,8 +68,90 @@ void Ctx::release_all() {
   type *var = (type *)(ctx)->buf(name, bytes);           \
   if (!var) return DGP_ERR_OOM
 
+namespace {
+
+// DGP_KERNEL_COMPOSITE: decode the flat program (layout in dgp_b200.h) into a Composite.
+int32_t parse_composite(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
+  const double *p = in->hyp;
+  const int n = in->n_hyp;
+  auto as_int = [](double v, int lo, int hi, int *o) {
+    if (!(v >= lo && v <= hi) || v != floor(v)) return false;
+    *o = (int)v;
+    return true;
+  };
+  int F = 0, T = 0;
+  if (n < 2 || !as_int(p[0], 1, MAXF, &F) || !as_int(p[1], 1, MAXT, &T))
+    return ctx->fail(DGP_ERR_ARG, "composite kernel: needs 1..%d base kernels and 1..%d terms", MAXF, MAXT);
+  auto comp = std::make_shared<Composite>();
+  CompositeDev &dev = comp->dev;
+  dev.F = F;
+  dev.T = T;
+  const int dp = (int)round_up(d, 4);
+  int pos = 2, slots = 0, total_hyp = 0, moments = 0;
+  for (int s = 0; s < MAX_ARD_SLOTS; ++s)
+    for (int c = 0; c < MAX_ARD_DIM; ++c) dev.w[s][c] = 0.0;
+  for (int f = 0; f < MAXF; ++f) {
+    dev.metric[f] = 0;
+    dev.ard_exact[f] = 0;
+    dev.moment_off[f] = 0;
+  }
+  for (int f = 0; f < F; ++f) {
+    int kind = 0, gm = 0, nf = 0;
+    if (pos + 3 > n || !as_int(p[pos], 0, DGP_KERNEL_COMPOSITE - 1, &kind) || !as_int(p[pos + 1], 0, 1, &gm) ||
+        !as_int(p[pos + 2], 0, DGP_MAX_HYP, &nf) || pos + 3 + nf > n)
+      return ctx->fail(DGP_ERR_ARG, "composite kernel: malformed base kernel %d", f);
+    dgp_kernel_spec fs;
+    fs.kind = kind;  fs.n_hyp = nf;  fs.grad_mode = gm;  fs.reserved = 0;  fs.hyp = p + pos + 3;  fs.noise = 0.0;
+    DGP_TRY(parse_spec(ctx, &fs, d, &comp->factor[f]));
+    pos += 3 + nf;
+    total_hyp += nf;
+    const Spec &sf = comp->factor[f];
+    dev.cp[f] = make_cov_params(sf, false, d);
+    if (kind_is_l1(kind)) {
+      dev.metric[f] = 1;
+      dev.any_l1 = 1;
+    } else if (kind == DGP_KERNEL_ARD_SE) {
+      if (slots >= MAX_ARD_SLOTS || dp > MAX_ARD_DIM)
+        return ctx->fail(DGP_ERR_UNSUPPORTED_KERNEL, "composite kernel: at most %d ARD-SE factors with d <= %d",
+                         MAX_ARD_SLOTS, MAX_ARD_DIM);
+      for (int c = 0; c < d; ++c) dev.w[slots][c] = 1.0 / (sf.hyp[1 + c] * sf.hyp[1 + c]);
+      dev.metric[f] = 2 + slots++;
+      dev.ard_exact[f] = gm == DGP_GRAD_EXACT;
+    }
+    dev.moment_off[f] = moments;
+    moments += grad_partials_per_tile(dev.cp[f], dp);
+  }
+  dev.moment_off[F] = moments;
+  for (int f = F + 1; f <= MAXF; ++f) dev.moment_off[f] = moments;
+  if (total_hyp > DGP_MAX_HYP) return ctx->fail(DGP_ERR_ARG, "composite kernel: too many hyper-parameters");
+  for (int t = 0; t < MAXT; ++t) {
+    dev.coef[t] = 0.0;
+    for (int f = 0; f < MAXF; ++f) dev.expo[t][f] = 0;
+  }
+  for (int t = 0; t < T; ++t) {
+    if (pos + 1 + F > n) return ctx->fail(DGP_ERR_ARG, "composite kernel: malformed term %d", t);
+    dev.coef[t] = p[pos];
+    for (int f = 0; f < F; ++f) {
+      int e = 0;
+      if (!as_int(p[pos + 1 + f], 0, 8, &e)) return ctx->fail(DGP_ERR_ARG, "composite kernel: bad exponent");
+      dev.expo[t][f] = (unsigned char)e;
+    }
+    pos += 1 + F;
+  }
+  if (pos != n) return ctx->fail(DGP_ERR_ARG, "composite kernel: %d trailing values in the program", n - pos);
+  out->kind = DGP_KERNEL_COMPOSITE;
+  out->n_hyp = total_hyp;
+  out->grad_mode = in->grad_mode;
+  out->noise = in->noise;
+  out->comp = comp;
+  return DGP_OK;
+}
+
+}  // namespace
+
 int32_t parse_spec(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
   if (!in || !in->hyp) return ctx->fail(DGP_ERR_ARG, "kernel spec / hyp is NULL");
+  if (in->kind == DGP_KERNEL_COMPOSITE) return parse_composite(ctx, in, d, out);
   int want = -1;
   switch (in->kind) {
     case DGP_KERNEL_SE: want = 2; break;
@@ -369,6 +451,21 @@ struct dgp_model : dgp::Model {};
 using namespace dgp;
 
 extern "C" {
+
+int32_t dgp_spec_grad_len(const dgp_kernel_spec *spec) {
+  if (!spec || !spec->hyp || spec->n_hyp < 0) return -DGP_ERR_ARG;
+  if (spec->kind != DGP_KERNEL_COMPOSITE) return spec->n_hyp + 1;
+  const double *p = spec->hyp;
+  const int n = spec->n_hyp;
+  if (n < 2 || !(p[0] >= 1 && p[0] <= MAXF)) return -DGP_ERR_ARG;
+  int pos = 2, total = 0;
+  for (int f = 0; f < (int)p[0]; ++f) {
+    if (pos + 3 > n || !(p[pos + 2] >= 0 && p[pos + 2] <= DGP_MAX_HYP)) return -DGP_ERR_ARG;
+    total += (int)p[pos + 2];
+    pos += 3 + (int)p[pos + 2];
+  }
+  return total + 1;
+}
 
 const char *dgp_version(void) { return "dgp-b200 0.1 (sm_100a, FP64 DMMA)"; }
 

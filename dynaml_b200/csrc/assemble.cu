@@ -137,6 +137,92 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(CovParams cp, Assemb
 }
 
 // ---------------------------------------------------------------------------------------------
+// Kernel algebra (DGP_KERNEL_COMPOSITE): sums / products / scalings of base kernels evaluated per
+// pair from one pass over the coordinate differences -- |x-y|_2^2, |x-y|_1 when some factor needs it,
+// and a weighted |.|^2 per ARD factor -- then combined as sum_t coef_t prod_f k_f^e_tf.  Replaces the
+// nested closures of AdditiveCovariance.evaluateAt / MultiplicativeCovariance.evaluateAt
+// (AdditiveCovariance.scala:47-52, MultiplicativeCovariance.scala:33-39), which re-filter the
+// hyper-parameter Map for every pair.  Same tiling as assemble_kernel's generic branch.
+// ---------------------------------------------------------------------------------------------
+struct PairMetrics {
+  double r2 = 0.0, l1 = 0.0, ard[MAX_ARD_SLOTS] = {0.0, 0.0};
+};
+
+__device__ __forceinline__ void pair_metrics(const CompositeDev &c, const double *x, const double *y, int dp,
+                                             PairMetrics &m) {
+  for (int k = 0; k < dp; ++k) {
+    const double e = x[k] - y[k];
+    const double e2 = e * e;
+    m.r2 += e2;
+    if (c.any_l1) m.l1 += fabs(e);
+#pragma unroll
+    for (int s = 0; s < MAX_ARD_SLOTS; ++s)
+      if (k < MAX_ARD_DIM) m.ard[s] = fma(c.w[s][k], e2, m.ard[s]);
+  }
+}
+
+__device__ __forceinline__ double metric_of(const CompositeDev &c, const PairMetrics &m, int f) {
+  const int id = c.metric[f];
+  return id == 0 ? m.r2 : (id == 1 ? m.l1 : m.ard[id - 2]);
+}
+
+__device__ __forceinline__ double composite_entry(const CompositeDev &c, const PairMetrics &m) {
+  double v[MAXF];
+#pragma unroll
+  for (int f = 0; f < MAXF; ++f) v[f] = (f < c.F) ? cov_value_rt(c.cp[f], metric_of(c, m, f)) : 1.0;
+  return composite_combine(c, v);
+}
+
+__global__ void __launch_bounds__(ATHREADS) assemble_composite_kernel(CompositeDev c, double noise_abs,
+                                                                      AssembleArgs a) {
+  extern __shared__ __align__(16) double sm[];  // column points: AT x dp, row-major
+  const int dp = a.dp;
+  const int tid = threadIdx.x;
+  const int tx = tid & 63, ty = tid >> 6;
+
+  int64_t tlin = blockIdx.x;
+  int ti, tj;
+  if (a.lower_only) {
+    ti = (int)((sqrt(8.0 * (double)tlin + 1.0) - 1.0) * 0.5);
+    while ((int64_t)ti * (ti + 1) / 2 > tlin) --ti;
+    while ((int64_t)(ti + 1) * (ti + 2) / 2 <= tlin) ++ti;
+    tj = (int)(tlin - (int64_t)ti * (ti + 1) / 2);
+  } else {
+    int mt = (int)(a.rows_p / AT);
+    tj = (int)(tlin / mt);
+    ti = (int)(tlin % mt);
+  }
+  int64_t m0 = (int64_t)ti * AT + a.row_off, n0 = (int64_t)tj * AT + a.col_off;
+  const int64_t lm0 = m0, ln0 = n0;
+  if (a.bc_T > 0) {
+    m0 = ((int64_t)(lm0 / a.bc_T) * a.bc_Pr + a.bc_pr) * a.bc_T + lm0 % a.bc_T;
+    n0 = ((int64_t)(ln0 / a.bc_T) * a.bc_Pc + a.bc_pc) * a.bc_T + ln0 % a.bc_T;
+    if (n0 > m0 + AT - 1) return;
+  }
+  for (int i = tid; i < AT * dp; i += ATHREADS) sm[i] = a.X2[n0 * dp + i];
+  __syncthreads();
+
+  const int64_t r0 = m0 + 2 * tx;
+  const bool sym = a.symmetric != 0;
+  double *out = a.out + (lm0 - a.row_off + 2 * tx) + (ln0 - a.col_off) * a.ld;
+  const double *p0 = a.X1 + r0 * dp, *p1 = p0 + dp;
+  for (int cc = 0; cc < AT / 4; ++cc) {
+    const int j = ty + 4 * cc;
+    const double *y = sm + j * dp;
+    PairMetrics q0, q1;
+    pair_metrics(c, p0, y, dp, q0);
+    pair_metrics(c, p1, y, dp, q1);
+    double k0 = composite_entry(c, q0), k1 = composite_entry(c, q1);
+    if (q0.r2 == 0.0) k0 += noise_abs;
+    if (q1.r2 == 0.0) k1 += noise_abs;
+    const int64_t col = n0 + j;
+    if (r0 >= a.rows || col >= a.cols) k0 = (sym && r0 == col) ? 1.0 : 0.0;
+    if (r0 + 1 >= a.rows || col >= a.cols) k1 = (sym && r0 + 1 == col) ? 1.0 : 0.0;
+    *reinterpret_cast<double2 *>(out + (int64_t)j * a.ld) = make_double2(k0, k1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // v2: Gram formulation on the FP64 tensor path with a lean epilogue.
 //
 // |x-y|^2 = |x|^2 + |y|^2 - 2 x.y comes out of DMMA directly by augmenting the contraction:
@@ -758,6 +844,16 @@ int32_t assemble(Ctx *ctx, cudaStream_t st, const CovParams &cp, const AssembleA
   if (a.lower_only && mt != nt) return ctx->fail(DGP_ERR_SHAPE, "assemble: lower_only needs a square matrix");
   int64_t tiles = a.lower_only ? mt * (mt + 1) / 2 : mt * nt;
   if (tiles == 0) return DGP_OK;
+  if (cp.kind == DGP_KERNEL_COMPOSITE) {
+    if (!cp.comp) return ctx->fail(DGP_ERR_ARG, "assemble: composite kernel without an expression");
+    size_t smem = (size_t)AT * a.dp * sizeof(double);
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(assemble_composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    assemble_composite_kernel<<<(unsigned)tiles, ATHREADS, smem, st>>>(*cp.comp, cp.noise_abs, a);
+    ctx->launches++;
+    DGP_CUDA_OK(ctx, cudaGetLastError());
+    return DGP_OK;
+  }
   bool done = false;
   const bool se_like = cp.kind == DGP_KERNEL_SE || cp.kind == DGP_KERNEL_RBF || cp.kind == DGP_KERNEL_ARD_SE;
   const bool matern_ok = cp.kind == DGP_KERNEL_MATERN && cp.p <= 3;

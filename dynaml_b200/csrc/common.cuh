@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <map>
+#include <memory>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -91,13 +92,18 @@ struct Data {
   bool has_dup = true;         // two training points coincide (decides where Dirac noise can land)
 };
 
-// Host copy of a kernel spec with derived constants.
+struct Composite;  // covfn.cuh
+
+// Host copy of a kernel spec with derived constants.  For DGP_KERNEL_COMPOSITE `n_hyp` is the total
+// number of base-kernel hyper-parameters (the gradient length minus one) and `comp` holds the parsed
+// expression; `hyp` is unused.
 struct Spec {
   int kind = 0;
   int n_hyp = 0;
   int grad_mode = 0;
   double hyp[DGP_MAX_HYP];
   double noise = 0.0;
+  std::shared_ptr<const Composite> comp;
 };
 
 int32_t parse_spec(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out);

@@ -9,7 +9,10 @@ namespace dgp {
 
 constexpr int MAX_MATERN_P = 8;
 
+struct CompositeDev;
+
 struct CovParams {
+  const CompositeDev *comp = nullptr;  // host pointer, DGP_KERNEL_COMPOSITE only (copied by value at launch)
   int kind = 0;
   int p = 0;           // Matern order
   int grad_mode = 0;
@@ -63,8 +66,83 @@ __host__ __device__ constexpr bool kind_is_l1(int kind) {
   return kind == DGP_KERNEL_PERIODIC || kind == DGP_KERNEL_LAPLACIAN;
 }
 
+// Runtime-dispatched value (composite kernels evaluate several kinds per pair; the switch is warp-uniform).
+__device__ __forceinline__ double cov_value_rt(const CovParams &cp, double dist) {
+  switch (cp.kind) {
+    case DGP_KERNEL_SE:
+    case DGP_KERNEL_RBF:
+    case DGP_KERNEL_ARD_SE: return cov_value<DGP_KERNEL_SE>(cp, dist);
+    case DGP_KERNEL_MATERN: return cov_value<DGP_KERNEL_MATERN>(cp, dist);
+    case DGP_KERNEL_PERIODIC: return cov_value<DGP_KERNEL_PERIODIC>(cp, dist);
+    case DGP_KERNEL_CAUCHY: return cov_value<DGP_KERNEL_CAUCHY>(cp, dist);
+    case DGP_KERNEL_LAPLACIAN: return cov_value<DGP_KERNEL_LAPLACIAN>(cp, dist);
+    case DGP_KERNEL_RATQUAD: return cov_value<DGP_KERNEL_RATQUAD>(cp, dist);
+    case DGP_KERNEL_TSTUDENT: return cov_value<DGP_KERNEL_TSTUDENT>(cp, dist);
+    default: return cov_value<DGP_KERNEL_DIRAC>(cp, dist);
+  }
+}
+
+// ---- kernel algebra: k = sum_t coef_t prod_f v_f^e_tf (DGP_KERNEL_COMPOSITE) -------------------------
+constexpr int MAXF = DGP_MAX_FACTORS, MAXT = DGP_MAX_TERMS, MAX_ARD_SLOTS = 2, MAX_ARD_DIM = 32;
+
+// Everything the device needs, passed to the kernels by value (~1.7 KB of parameter space).
+struct CompositeDev {
+  int F = 0, T = 0;
+  int any_l1 = 0;                 // some factor consumes |x-y|_1
+  int metric[MAXF];               // per factor: 0 = |x-y|_2^2, 1 = |x-y|_1, 2 + s = ARD slot s
+  int moment_off[MAXF + 1];       // gradient pass: first moment of each factor; [F] = the noise moment
+  int ard_exact[MAXF];            // ARD factor with the exact per-dimension derivative
+  CovParams cp[MAXF];
+  double coef[MAXT];
+  unsigned char expo[MAXT][MAXF];
+  double w[MAX_ARD_SLOTS][MAX_ARD_DIM];  // ARD slots: 1 / b_c^2
+};
+
+__device__ __forceinline__ double ipow_small(double v, int e) {
+  double r = 1.0;
+  for (int i = 0; i < e; ++i) r *= v;
+  return r;
+}
+
+// Value of the expression from the base-kernel values v[0..F).
+__device__ __forceinline__ double composite_combine(const CompositeDev &c, const double (&v)[MAXF]) {
+  double k = 0.0;
+  for (int t = 0; t < c.T; ++t) {
+    double prod = c.coef[t];
+#pragma unroll
+    for (int f = 0; f < MAXF; ++f)
+      if (f < c.F) prod *= ipow_small(v[f], c.expo[t][f]);
+    k += prod;
+  }
+  return k;
+}
+
+// d k / d v_f : the factor every derivative of base kernel f is multiplied by
+// (MultiplicativeCovariance.scala:68-77; `* c` scales value and gradient alike, LocalScalarKernel.scala:81-85).
+__device__ __forceinline__ double composite_cofactor(const CompositeDev &c, const double (&v)[MAXF], int f) {
+  double out = 0.0;
+  for (int t = 0; t < c.T; ++t) {
+    const int e = c.expo[t][f];
+    if (e == 0) continue;
+    double prod = c.coef[t] * (double)e;
+#pragma unroll
+    for (int g = 0; g < MAXF; ++g)
+      if (g < c.F) prod *= ipow_small(v[g], g == f ? e - 1 : c.expo[t][g]);
+    out += prod;
+  }
+  return out;
+}
+
 // Host: fold a Spec into CovParams.  `noise` < 0 is legal (the reference takes abs()).
-inline CovParams make_cov_params(const Spec &s, bool with_noise, int d = 0) {
+inline CovParams make_cov_params(const Spec &s, bool with_noise, int d = 0);
+
+// Parsed composite: the device block plus the base-kernel specs (for grad_finish).
+struct Composite {
+  CompositeDev dev;
+  Spec factor[MAXF];
+};
+
+inline CovParams make_cov_params(const Spec &s, bool with_noise, int d) {
   CovParams cp;
   cp.kind = s.kind;
   cp.grad_mode = s.grad_mode;
@@ -119,6 +197,9 @@ inline CovParams make_cov_params(const Spec &s, bool with_noise, int d = 0) {
       break;
     case DGP_KERNEL_TSTUDENT:
       cp.c1 = s.hyp[0];
+      break;
+    case DGP_KERNEL_COMPOSITE:
+      cp.comp = s.comp ? &s.comp->dev : nullptr;
       break;
   }
   return cp;

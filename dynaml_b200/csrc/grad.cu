@@ -310,6 +310,123 @@ __global__ void __launch_bounds__(GTHREADS) grad_trace_generic_kernel(CovParams 
   }
 }
 
+// ---- kernel algebra (DGP_KERNEL_COMPOSITE) -----------------------------------------------------------
+// d k / d theta_{f,i} = (d k / d v_f) * d v_f / d theta_{f,i}  (AdditiveCovariance.scala:77-84,
+// MultiplicativeCovariance.scala:68-77): every base kernel accumulates its own moments exactly as in the
+// single-kernel pass, with the pair weight M_ij multiplied by the cofactor d k / d v_f.  Moments of
+// factor f start at moment_off[f]; the last moment is the noise one, sum M_ij 1[|x_i - x_j| == 0].
+constexpr int MAX_COMPOSITE_MOMENTS = 48;
+
+__device__ __forceinline__ void accumulate_rt(int mode, const CovParams &cp, double m, double dist, double plain2,
+                                              double *s) {
+  switch (mode) {
+    case M_SE: accumulate<M_SE, 0>(cp, m, dist, plain2, nullptr, s); break;
+    case M_ARD_REF: accumulate<M_ARD_REF, 0>(cp, m, dist, plain2, nullptr, s); break;
+    case M_MATERN: accumulate<M_MATERN, 0>(cp, m, dist, plain2, nullptr, s); break;
+    case M_PERIODIC: accumulate<M_PERIODIC, 0>(cp, m, dist, plain2, nullptr, s); break;
+    case M_CAUCHY: accumulate<M_CAUCHY, 0>(cp, m, dist, plain2, nullptr, s); break;
+    case M_LAPLACIAN: accumulate<M_LAPLACIAN, 0>(cp, m, dist, plain2, nullptr, s); break;
+    case M_RATQUAD: accumulate<M_RATQUAD, 0>(cp, m, dist, plain2, nullptr, s); break;
+    case M_TSTUDENT: accumulate<M_TSTUDENT, 0>(cp, m, dist, plain2, nullptr, s); break;
+    default: accumulate<M_DIRAC, 0>(cp, m, dist, plain2, nullptr, s); break;
+  }
+}
+
+struct CompositeModes {
+  int mode[MAXF];
+};
+
+__device__ __forceinline__ void composite_pair(const CompositeDev &c, const CompositeModes &md, const double *x,
+                                               const double *y, int dp, double m, double *s) {
+  double r2 = 0.0, l1 = 0.0, ard[MAX_ARD_SLOTS] = {0.0, 0.0};
+  for (int k = 0; k < dp; ++k) {
+    const double e = x[k] - y[k];
+    const double e2 = e * e;
+    r2 += e2;
+    if (c.any_l1) l1 += fabs(e);
+#pragma unroll
+    for (int q = 0; q < MAX_ARD_SLOTS; ++q)
+      if (k < MAX_ARD_DIM) ard[q] = fma(c.w[q][k], e2, ard[q]);
+  }
+  double v[MAXF], dist[MAXF];
+#pragma unroll
+  for (int f = 0; f < MAXF; ++f) {
+    const int id = (f < c.F) ? c.metric[f] : 0;
+    dist[f] = id == 0 ? r2 : (id == 1 ? l1 : ard[id - 2]);
+    v[f] = (f < c.F) ? cov_value_rt(c.cp[f], dist[f]) : 1.0;
+  }
+#pragma unroll
+  for (int f = 0; f < MAXF; ++f) {
+    if (f >= c.F) continue;
+    const double w = m * composite_cofactor(c, v, f);
+    double *sf = s + c.moment_off[f];
+    if (c.ard_exact[f]) {
+      // exact dk/db_c = k (x_c - y_c)^2 / b_c^3: one moment per dimension (cf. M_ARD_EXACT)
+      const double e = exp(-dist[f] * c.cp[f].c1);
+      sf[0] = fma(w, e, sf[0]);
+      const double we = w * e;
+      for (int k = 0; k < dp; ++k) {
+        const double df = x[k] - y[k];
+        sf[1 + k] = fma(we, df * df, sf[1 + k]);
+      }
+    } else {
+      accumulate_rt(md.mode[f], c.cp[f], w, dist[f], r2, sf);
+    }
+  }
+  if (r2 == 0.0) s[c.moment_off[c.F]] += m;
+}
+
+__global__ void __launch_bounds__(GTHREADS) grad_trace_composite_kernel(CompositeDev c, CompositeModes md, GradArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int dp = a.dp;
+  const int NS = c.moment_off[c.F] + 1;
+  double *sx = sm;
+  double *sal = sm + GT * dp;
+  double *red = sal + GT;
+  const int tid = threadIdx.x;
+  const int tx = tid & 63, ty = tid >> 6;
+  int64_t tlin = blockIdx.x;
+  int ti = (int)((sqrt(8.0 * (double)tlin + 1.0) - 1.0) * 0.5);
+  while ((int64_t)ti * (ti + 1) / 2 > tlin) --ti;
+  while ((int64_t)(ti + 1) * (ti + 2) / 2 <= tlin) ++ti;
+  const int tj = (int)(tlin - (int64_t)ti * (ti + 1) / 2);
+  const int64_t m0 = (int64_t)ti * GT, n0 = (int64_t)tj * GT;
+  for (int i = tid; i < GT * dp; i += GTHREADS) sx[i] = a.X[n0 * dp + i];
+  if (tid < GT) sal[tid] = a.alpha[n0 + tid];
+  const int64_t r0 = m0 + 2 * tx;
+  const double *x0 = a.X + r0 * dp, *x1 = x0 + dp;
+  const double al0 = a.alpha[r0], al1 = a.alpha[r0 + 1];
+  __syncthreads();
+  double s[MAX_COMPOSITE_MOMENTS];
+  for (int q = 0; q < MAX_COMPOSITE_MOMENTS; ++q) s[q] = 0.0;
+  const double *kinv = a.Kinv + r0 + n0 * a.ld;
+  for (int cc = 0; cc < GT / 4; ++cc) {
+    const int j = ty + 4 * cc;
+    const int64_t col = n0 + j;
+    const double2 kv = *reinterpret_cast<const double2 *>(kinv + (int64_t)j * a.ld);
+    const double aj = sal[j];
+    double w0 = (r0 > col) ? 2.0 : (r0 == col ? 1.0 : 0.0);
+    double w1 = (r0 + 1 > col) ? 2.0 : (r0 + 1 == col ? 1.0 : 0.0);
+    if (r0 >= a.n || col >= a.n) w0 = 0.0;
+    if (r0 + 1 >= a.n || col >= a.n) w1 = 0.0;
+    if (w0 != 0.0) composite_pair(c, md, x0, sx + j * dp, dp, w0 * (al0 * aj - kv.x), s);
+    if (w1 != 0.0) composite_pair(c, md, x1, sx + j * dp, dp, w1 * (al1 * aj - kv.y), s);
+  }
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int q = 0; q < NS; ++q) {
+    double v = s[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp * NS + q] = v;
+  }
+  __syncthreads();
+  if (tid < NS) {
+    double v = 0.0;
+    for (int wdx = 0; wdx < GTHREADS / 32; ++wdx) v += red[wdx * NS + tid];
+    a.partials[(int64_t)blockIdx.x * NS + tid] = v;
+  }
+}
+
 template <int MODE>
 int32_t launch_generic(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArgs &a, int64_t tiles, int *ns_out) {
   constexpr int NS = NSums<MODE, 0>::value;
@@ -380,6 +497,7 @@ int mode_of(const CovParams &cp) {
 }  // namespace
 
 int grad_partials_per_tile(const CovParams &cp, int dp) {
+  if (cp.kind == DGP_KERNEL_COMPOSITE) return cp.comp ? cp.comp->moment_off[cp.comp->F] + 1 : 1;
   switch (mode_of(cp)) {
     case M_ARD_EXACT: return dp + 2;
     case M_MATERN:
@@ -394,6 +512,28 @@ int grad_partials_per_tile(const CovParams &cp, int dp) {
 int32_t grad_trace(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArgs &a, int *ns) {
   if (a.np % GT) return ctx->fail(DGP_ERR_SHAPE, "grad_trace: padded n must be a multiple of 128");
   const int64_t mt = a.np / GT, tiles = mt * (mt + 1) / 2;
+  if (cp.kind == DGP_KERNEL_COMPOSITE) {
+    if (!cp.comp) return ctx->fail(DGP_ERR_ARG, "grad_trace: composite kernel without an expression");
+    const CompositeDev &c = *cp.comp;
+    const int NS = c.moment_off[c.F] + 1;
+    if (NS > MAX_COMPOSITE_MOMENTS)
+      return ctx->fail(DGP_ERR_SHAPE, "composite gradient needs %d moments, at most %d are supported", NS,
+                       MAX_COMPOSITE_MOMENTS);
+    CompositeModes md;
+    for (int f = 0; f < MAXF; ++f) md.mode[f] = f < c.F ? mode_of(c.cp[f]) : M_DIRAC;
+    size_t smem = ((size_t)GT * a.dp + GT + (GTHREADS / 32) * NS) * sizeof(double);
+    if (smem > 200 * 1024) return ctx->fail(DGP_ERR_SHAPE, "gradEnergy: too many features (dp=%d)", a.dp);
+    if (smem > 48 * 1024)
+      DGP_CUDA_OK(ctx, cudaFuncSetAttribute(grad_trace_composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+    grad_trace_composite_kernel<<<(unsigned)tiles, GTHREADS, smem, st>>>(c, md, a);
+    DGP_CUDA_OK(ctx, cudaGetLastError());
+    reduce_partials_kernel<<<NS, 1024, 0, st>>>(a.partials, tiles, NS, a.sums);
+    ctx->launches += 2;
+    DGP_CUDA_OK(ctx, cudaGetLastError());
+    *ns = NS;
+    return DGP_OK;
+  }
   switch (mode_of(cp)) {
     case M_SE: return launch_dp<M_SE>(ctx, st, cp, a, tiles, ns);
     case M_ARD_REF: return launch_dp<M_ARD_REF>(ctx, st, cp, a, tiles, ns);
@@ -411,6 +551,17 @@ int32_t grad_trace(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArg
 // Map the moments to the reference's derivatives, in the order [hyp..., noise].
 void grad_finish(const Spec &sp, int d, const double *S, int ns, double *g) {
   const double qnan = nan("");
+  if (sp.kind == DGP_KERNEL_COMPOSITE) {
+    const Composite &cm = *sp.comp;
+    int pos = 0;
+    for (int f = 0; f < cm.dev.F; ++f) {
+      double tmp[DGP_MAX_HYP + 1];
+      grad_finish(cm.factor[f], d, S + cm.dev.moment_off[f], cm.dev.moment_off[f + 1] - cm.dev.moment_off[f], tmp);
+      for (int i = 0; i < cm.factor[f].n_hyp; ++i) g[pos++] = tmp[i];
+    }
+    g[pos] = (sp.noise == 0.0) ? qnan : S[ns - 1];
+    return;
+  }
   const double noise_m = S[ns - 1];
   switch (sp.kind) {
     case DGP_KERNEL_SE: {

@@ -118,8 +118,28 @@ class LocalScalarKernel:
     def buildCrossKernelMatrix(self, dataset1: Sequence, dataset2: Sequence) -> np.ndarray:
         return _capi.default_context().kernel_matrix(self._spec(), _as_points(dataset1), _as_points(dataset2))
 
+    # ---- kernel algebra (LocalScalarKernel.scala:53-91) -------------------------------------
+    # Every kernel reduces to the normal form  sum_t coef_t * prod_f leaf_f ^ e_tf  that the device
+    # evaluates (DGP_KERNEL_COMPOSITE): `_leaves()` lists the base kernels in hyper-parameter order,
+    # `_terms(config)` the terms as (coef, {leaf position: exponent}).
+    def _leaves(self) -> List["LocalScalarKernel"]:
+        return [self]
+
+    def _leaf_configs(self, config: Dict[str, float]) -> List[Dict[str, float]]:
+        return [config]
+
+    def _terms(self) -> List[tuple]:
+        return [(1.0, {0: 1})]
+
     def __add__(self, other: "LocalScalarKernel") -> "AdditiveCovariance":
         return AdditiveCovariance(self, other)
+
+    def __mul__(self, other):
+        if isinstance(other, LocalScalarKernel):
+            return MultiplicativeCovariance(self, other)
+        return ScaledKernel(self, float(other))
+
+    __rmul__ = __mul__
 
 
 class RBFKernel(LocalScalarKernel):
@@ -280,9 +300,10 @@ class DiracKernel(LocalScalarKernel):
         return SVMKernelMatrix(np.eye(length) * self.state["noiseLevel"], length)
 
 
-class AdditiveCovariance(LocalScalarKernel):
-    """cov + noise with the reference's "<Class@hash>/<hyp>" naming (AdditiveCovariance.scala:32-58).
-    The device path supports <supported kernel> + DiracKernel."""
+class CompositeCovariance(LocalScalarKernel):
+    """Shared plumbing of AdditiveCovariance / MultiplicativeCovariance: "<Class@hash>/<hyp>" naming and
+    substring routing of configurations (AdditiveCovariance.scala:32-58, CompositeCovariance.truncateState),
+    plus the reduction to the device's sum-of-products form."""
 
     def __init__(self, firstKernel: LocalScalarKernel, otherKernel: LocalScalarKernel):
         super().__init__()
@@ -315,17 +336,108 @@ class AdditiveCovariance(LocalScalarKernel):
         self.otherKernel.block(*[self._truncate(k) for k in h if self.sID in k])
         super().block(*h)
 
+    # ---- normal form ----------------------------------------------------------------------
+    def _device_kind(self) -> int:
+        for leaf in self._leaves():
+            leaf._device_kind()  # raises for base kernels without a device implementation
+        return _capi.KERNEL_COMPOSITE
+
+    def _leaves(self):
+        return self.firstKernel._leaves() + self.otherKernel._leaves()
+
+    def _leaf_configs(self, config):
+        c1, c2 = self._configs(config)
+        return self.firstKernel._leaf_configs(c1) + self.otherKernel._leaf_configs(c2)
+
+    def _shifted_other_terms(self):
+        off = len(self.firstKernel._leaves())
+        return [(c, {f + off: e for f, e in m.items()}) for c, m in self.otherKernel._terms()]
+
     def _spec(self, config=None, noise: float = 0.0):
-        if not isinstance(self.otherKernel, DiracKernel):
-            raise NotImplementedError("device path supports <kernel> + DiracKernel only; no CPU fallback")
-        c1, c2 = self._configs(self.state if config is None else config)
-        return self.firstKernel._spec(c1, noise=c2["noiseLevel"])
+        cfg = self.state if config is None else config
+        leaves, cfgs = self._leaves(), self._leaf_configs(cfg)
+        factors = [(k._device_kind(), k.grad_mode, k._device_hyp(c)) for k, c in zip(leaves, cfgs)]
+        terms = [(c, [m.get(f, 0) for f in range(len(leaves))]) for c, m in self._terms()]
+        return _capi.make_composite_spec(factors, terms, noise)
+
+
+class AdditiveCovariance(CompositeCovariance):
+    """k = k1 + k2 (AdditiveCovariance.scala:27-93).  `<kernel> + DiracKernel` keeps the dedicated noise path of
+    the single-kernel spec (the GP model's cov + noise); every other sum runs as a device composite."""
+
+    def _terms(self):
+        return self.firstKernel._terms() + self._shifted_other_terms()
+
+    def _is_cov_plus_noise(self) -> bool:
+        return isinstance(self.otherKernel, DiracKernel) and not isinstance(self.firstKernel, CompositeCovariance) \
+            and not isinstance(self.firstKernel, ScaledKernel)
+
+    def _spec(self, config=None, noise: float = 0.0):
+        if self._is_cov_plus_noise() and noise == 0.0:
+            c1, c2 = self._configs(self.state if config is None else config)
+            return self.firstKernel._spec(c1, noise=c2["noiseLevel"])
+        return super()._spec(config, noise)
 
     def buildKernelMatrix(self, mappedData: Sequence, length: int) -> SVMKernelMatrix:
         X = _as_points(mappedData)
         return SVMKernelMatrix(_capi.default_context().kernel_matrix(self._spec(), X, add_noise=True), length)
 
     def buildCrossKernelMatrix(self, dataset1: Sequence, dataset2: Sequence) -> np.ndarray:
-        # crossKernelMatrix evaluates cov + noise pairwise: the Dirac term fires only on exact duplicates
-        # across the two sets, which the device cross path does not add.
-        raise NotImplementedError("cross matrices of cov + noise are not on the GP hot path")
+        if self._is_cov_plus_noise():
+            # crossKernelMatrix evaluates cov + noise pairwise: the Dirac term fires only on exact duplicates
+            # across the two sets, which the dedicated noise path does not add.
+            raise NotImplementedError("cross matrices of cov + noise are not on the GP hot path")
+        return super().buildCrossKernelMatrix(dataset1, dataset2)
+
+
+class MultiplicativeCovariance(CompositeCovariance):
+    """k = k1 * k2 (MultiplicativeCovariance.scala:11-90): every term of k1 times every term of k2."""
+
+    def _terms(self):
+        out = []
+        for c1, m1 in self.firstKernel._terms():
+            for c2, m2 in self._shifted_other_terms():
+                m = dict(m1)
+                for f, e in m2.items():
+                    m[f] = m.get(f, 0) + e
+                out.append((c1 * c2, m))
+        return out
+
+
+class ScaledKernel(LocalScalarKernel):
+    """k * c for a positive constant (LocalScalarKernel.scala:68-91): shares the hyper-parameters and state of the
+    wrapped kernel; value and gradient are scaled by c."""
+
+    def __init__(self, base: LocalScalarKernel, c: float):
+        if not c > 0:
+            raise ValueError("Multiplicative constant applied on a kernel must be positive!")
+        super().__init__()
+        self.base, self.c = base, float(c)
+        self.hyper_parameters = list(base.hyper_parameters)
+        self.state = base.state                      # shared, as in the reference (`state = self.state`)
+        self.blocked_hyper_parameters = list(base.blocked_hyper_parameters)
+
+    def setHyperParameters(self, h: Dict[str, float]):
+        self.base.setHyperParameters(h)
+        return super().setHyperParameters(h)
+
+    def _device_kind(self) -> int:
+        for leaf in self._leaves():
+            leaf._device_kind()
+        return _capi.KERNEL_COMPOSITE
+
+    def _leaves(self):
+        return self.base._leaves()
+
+    def _leaf_configs(self, config):
+        return self.base._leaf_configs(config)
+
+    def _terms(self):
+        return [(self.c * c, m) for c, m in self.base._terms()]
+
+    def _spec(self, config=None, noise: float = 0.0):
+        cfg = self.state if config is None else config
+        leaves, cfgs = self._leaves(), self._leaf_configs(cfg)
+        factors = [(k._device_kind(), k.grad_mode, k._device_hyp(c)) for k, c in zip(leaves, cfgs)]
+        terms = [(c, [m.get(f, 0) for f in range(len(leaves))]) for c, m in self._terms()]
+        return _capi.make_composite_spec(factors, terms, noise)

@@ -70,9 +70,22 @@ enum {
                               hyp = [beta]; k = exp(-|x-y|_1 / beta)   (L1 norm)                 */
   DGP_KERNEL_RATQUAD = 8,  /* RationalQuadraticKernel CORE/kernels/RationalQuadraticKernel.scala
                               hyp = [mu, l]; k = (1 + |x-y|^2/(mu l^2))^(-(d+mu)/2)              */
-  DGP_KERNEL_TSTUDENT = 9  /* TStudentKernel      CORE/kernels/TStudentKernel.scala
+  DGP_KERNEL_TSTUDENT = 9, /* TStudentKernel      CORE/kernels/TStudentKernel.scala
                               hyp = [d]; k = 1 / (1 + |x-y|^d)                                   */
+  /* Kernel algebra of LocalScalarKernel (`+`, `*`, `* c`; CORE/kernels/LocalScalarKernel.scala:53-91,
+     AdditiveCovariance.scala:27-93, MultiplicativeCovariance.scala:11-90) in sum-of-products normal
+     form  k = sum_t coef_t * prod_f k_f ^ e_tf  over F <= DGP_MAX_FACTORS base kernels (any kind
+     above) and T <= DGP_MAX_TERMS terms.  `hyp` is then a flat program of n_hyp doubles:
+        [ F, T,
+          F x { kind, grad_mode, n_f, hyp_0 .. hyp_{n_f - 1} },        base kernels, reference order
+          T x { coef_t, e_t0 .. e_t,F-1 } ]                           small non-negative integers
+     gradEnergy returns the derivatives of the base kernels' hyper-parameters factor by factor,
+     then the noise level: dgp_spec_grad_len() values.  ARD-SE factors need d <= 32 (two at most). */
+  DGP_KERNEL_COMPOSITE = 10
 };
+
+#define DGP_MAX_FACTORS 6
+#define DGP_MAX_TERMS 16
 
 /* Gradient conventions for hyper-parameters whose reference derivative is defective. */
 enum {
@@ -92,6 +105,10 @@ typedef struct dgp_kernel_spec {
   double noise;            /* DiracKernel noiseLevel of the noise model (signed; |.| is added
                               wherever |x-y|_2 == 0, DiracKernel.scala:43-47)                   */
 } dgp_kernel_spec;
+
+/* Number of values dgp_energy_grad writes for this spec (n_hyp + 1, or for a composite the sum of
+   its base kernels' hyper-parameter counts + 1); negative DGP_ERR_* on a malformed spec.       */
+int32_t dgp_spec_grad_len(const dgp_kernel_spec *spec);
 
 /* ---- context ------------------------------------------------------------------------------ */
 int32_t dgp_ctx_create(int32_t device, dgp_ctx **out);

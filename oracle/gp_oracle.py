@@ -217,6 +217,70 @@ def dirac(noise: float) -> Kernel:
 
 
 # ------------------------------------------------------------------------------------------------
+# kernel algebra (LocalScalarKernel.scala:53-91): the same value / grads / names interface as Kernel,
+# hyper-parameter names prefixed "<id>/" like AdditiveCovariance (AdditiveCovariance.scala:34-40)
+# ------------------------------------------------------------------------------------------------
+
+class _Pair:
+    def __init__(self, first, other, ids=("k1", "k2")):
+        self.first, self.other, self.ids = first, other, tuple(ids)
+
+    def names(self, d: int | None = None) -> List[str]:
+        return [f"{self.ids[0]}/{n}" for n in self.first.names(d)] + [f"{self.ids[1]}/{n}" for n in self.other.names(d)]
+
+    def effective(self, blocked: Sequence[str] = ()) -> List[str]:
+        b1 = [n.split("/", 1)[1] for n in blocked if n.startswith(self.ids[0] + "/")]
+        b2 = [n.split("/", 1)[1] for n in blocked if n.startswith(self.ids[1] + "/")]
+        return [f"{self.ids[0]}/{n}" for n in self.first.effective(b1)] + \
+               [f"{self.ids[1]}/{n}" for n in self.other.effective(b2)]
+
+
+class Sum(_Pair):
+    """AdditiveCovariance.scala:47-52 (value), :77-84 (gradient = the two gradient maps, prefixed)."""
+
+    def value(self, X, Y):
+        return self.first.value(X, Y) + self.other.value(X, Y)
+
+    def grads(self, X, Y):
+        out = {f"{self.ids[0]}/{n}": g for n, g in self.first.grads(X, Y).items()}
+        out.update({f"{self.ids[1]}/{n}": g for n, g in self.other.grads(X, Y).items()})
+        return out
+
+
+class Prod(_Pair):
+    """MultiplicativeCovariance.scala:33-39 (value), :68-77 (each gradient times the other kernel's value)."""
+
+    def value(self, X, Y):
+        return self.first.value(X, Y) * self.other.value(X, Y)
+
+    def grads(self, X, Y):
+        v1, v2 = self.first.value(X, Y), self.other.value(X, Y)
+        out = {f"{self.ids[0]}/{n}": g * v2 for n, g in self.first.grads(X, Y).items()}
+        out.update({f"{self.ids[1]}/{n}": g * v1 for n, g in self.other.grads(X, Y).items()})
+        return out
+
+
+class Scaled:
+    """kernel * c, c > 0 (LocalScalarKernel.scala:68-91): same hyper-parameters, value and gradient times c."""
+
+    def __init__(self, base, c: float):
+        assert c > 0, "Multiplicative constant applied on a kernel must be positive!"
+        self.base, self.c = base, float(c)
+
+    def names(self, d: int | None = None):
+        return self.base.names(d)
+
+    def effective(self, blocked: Sequence[str] = ()):
+        return self.base.effective(blocked)
+
+    def value(self, X, Y):
+        return self.base.value(X, Y) * self.c
+
+    def grads(self, X, Y):
+        return {n: g * self.c for n, g in self.base.grads(X, Y).items()}
+
+
+# ------------------------------------------------------------------------------------------------
 # matrix builders (SVMKernel.scala:71-105): symmetric build evaluates i >= j and mirrors
 # ------------------------------------------------------------------------------------------------
 

@@ -1,0 +1,166 @@
+"""Kernel algebra on the device: `+`, `*`, `* c` of LocalScalarKernel
+(CORE/kernels/LocalScalarKernel.scala:53-91, AdditiveCovariance.scala, MultiplicativeCovariance.scala) as
+DGP_KERNEL_COMPOSITE, against the oracle's Sum / Prod / Scaled through the same model API."""
+import math
+
+import numpy as np
+import pytest
+
+import dynaml_b200 as dg
+from dynaml_b200 import _capi
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL_K, TOL = 1e-12, 1e-9
+
+
+def entry_rel(a, b):
+    return float((np.abs(a - b) / np.maximum(np.abs(b), 1e-290)).max())
+
+
+def expressions(d):
+    """name -> (device kernel, oracle kernel); leaves in the same order on both sides."""
+    band = np.linspace(1.5, 3.0, d)
+    ard_h = {"MahalanobisAmplitude": 1.1, **{f"MahalanobisBandwidth_{i}": b for i, b in enumerate(band)}}
+    se = lambda: (dg.SEKernel(1.7, 1.2), orc.Kernel("se", {"bandwidth": 1.7, "amplitude": 1.2}))  # noqa: E731
+    rbf = lambda: (dg.RBFKernel(2.4), orc.Kernel("rbf", {"bandwidth": 2.4}))  # noqa: E731
+    mat = lambda: (dg.GenericMaternKernel(2.2, 2), orc.Kernel("matern", {"p": 2.0, "l": 2.2}))  # noqa: E731
+    cau = lambda: (dg.CauchyKernel(2.3), orc.Kernel("cauchy", {"sigma": 2.3}))  # noqa: E731
+    lap = lambda: (dg.LaplacianKernel(3.1), orc.Kernel("laplacian", {"beta": 3.1}))  # noqa: E731
+    rq = lambda: (dg.RationalQuadraticKernel(1.5, 1.9), orc.Kernel("ratquad", {"mu": 1.5, "l": 1.9}))  # noqa: E731
+    ard = lambda mode: (dg.MahalanobisKernel(band, 1.1, _capi.GRAD_EXACT if mode == "exact" else _capi.GRAD_REFERENCE),  # noqa: E731
+                        orc.Kernel("ard", ard_h, mode))
+    out = {}
+    (a, oa), (b, ob) = se(), mat()
+    out["se+matern"] = (a + b, orc.Sum(oa, ob))
+    (a, oa), (b, ob) = se(), cau()
+    out["se*cauchy"] = (a * b, orc.Prod(oa, ob))
+    (a, oa) = mat()
+    out["matern*2.5"] = (a * 2.5, orc.Scaled(oa, 2.5))
+    (a, oa), (b, ob), (c, oc) = se(), lap(), rbf()
+    out["se*laplacian+rbf*0.5"] = (a * b + c * 0.5, orc.Sum(orc.Prod(oa, ob), orc.Scaled(oc, 0.5)))
+    (a, oa), (b, ob), (c, oc) = rbf(), rq(), mat()
+    out["(rbf+ratquad)*matern"] = ((a + b) * c, orc.Prod(orc.Sum(oa, ob), oc))
+    (a, oa), (b, ob) = ard("reference"), mat()
+    out["ard_ref+matern"] = (a + b, orc.Sum(oa, ob))
+    (a, oa), (b, ob) = ard("exact"), se()
+    out["ard_exact*se"] = (a * b, orc.Prod(oa, ob))
+    (a, oa) = se()
+    out["se*se"] = (a * a, None)  # the same instance twice: exponent 2 (checked against se^2 below)
+    return out
+
+
+NAMES = ["se+matern", "se*cauchy", "matern*2.5", "se*laplacian+rbf*0.5", "(rbf+ratquad)*matern", "ard_ref+matern",
+         "ard_exact*se"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_composite_kernel_matrices(name):
+    X, _, _ = orc.synthetic(300, 5, seed=11)
+    Xs, _, _ = orc.synthetic(140, 5, seed=12)
+    k, ok = expressions(5)[name]
+    K = k.buildKernelMatrix(X, len(X)).getKernelMatrix()
+    assert entry_rel(K, orc.build_kernel_matrix(ok, X)) <= TOL_K
+    assert np.array_equal(K, K.T)
+    C = k.buildCrossKernelMatrix(X, Xs)
+    assert entry_rel(C, orc.cross_kernel_matrix(ok, X, Xs)) <= TOL_K
+
+
+def test_same_kernel_twice_is_a_square():
+    X, _, _ = orc.synthetic(150, 3, seed=5)
+    k, _ = expressions(3)["se*se"]
+    K = k.buildKernelMatrix(X, len(X)).getKernelMatrix()
+    K1 = orc.build_kernel_matrix(orc.Kernel("se", {"bandwidth": 1.7, "amplitude": 1.2}), X)
+    assert entry_rel(K, K1 * K1) <= TOL_K
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_composite_energy_gradient_and_posterior(name):
+    n, d = 260, 4
+    X, y, Xs = orc.synthetic(n, d, seed=21, m=40)
+    k, ok = expressions(d)[name]
+    noise = 0.3
+    model = dg.GPRegression(k, dg.DiracKernel(noise), list(zip(X, y)))
+    h = model._current_state
+    assert model.energy(h) == pytest.approx(orc.energy(ok, noise, X, y), rel=TOL)
+    g, go = model.gradEnergy(h), orc.grad_energy(ok, noise, X, y)
+    # same order on both sides: effective leaves of the expression, then the noise level
+    assert len(g) == len(go)
+    scale = max(abs(v) for v in go.values())
+    for (gn, gv), (on, ov) in zip(g.items(), go.items()):
+        assert gn.split("/")[-1] == on.split("/")[-1]
+        assert gv == pytest.approx(ov, rel=TOL, abs=TOL * scale), (gn, on)
+    post = model.predictiveDistribution(Xs)
+    mu, cov = orc.predictive(ok, noise, X, y, Xs)
+    assert np.abs(post.mu - mu).max() <= TOL * max(1.0, np.abs(mu).max())
+    assert np.abs(post.covariance - cov).max() <= TOL * np.abs(cov).max()
+
+
+def test_composite_with_dirac_factor_and_duplicates():
+    """A DiracKernel inside the expression keeps the reference's |x-y| == 0 rule (duplicates included)."""
+    X, y, _ = orc.synthetic(200, 3, seed=8)
+    X[50] = X[7]
+    se, dr = dg.SEKernel(1.3, 1.0), dg.DiracKernel(0.4)
+    k = se * 0.7 + dr
+    ok = orc.Sum(orc.Scaled(orc.Kernel("se", {"bandwidth": 1.3, "amplitude": 1.0}), 0.7), orc.dirac(0.4))
+    # `<scaled kernel> + Dirac` is not the single-kernel noise path: the Dirac term is a base kernel of the composite
+    K = k.buildKernelMatrix(X, len(X)).getKernelMatrix()
+    assert entry_rel(K, orc.build_kernel_matrix(ok, X)) <= TOL_K
+    assert K[50, 7] == pytest.approx(0.7 + 0.4, rel=1e-15)
+    X[50] += 0.25  # with the duplicate K is singular by the reference's own rule; the gradient needs distinct points
+    model = dg.GPRegression(k, dg.DiracKernel(0.2), list(zip(X, y)))
+    g, go = model.gradEnergy(model._current_state), orc.grad_energy(ok, 0.2, X, y)
+    scale = max(abs(v) for v in go.values())
+    for (gn, gv), (on, ov) in zip(g.items(), go.items()):
+        assert gv == pytest.approx(ov, rel=TOL, abs=TOL * scale), (gn, on)
+
+
+def test_composite_batch_and_grid_search(ctx):
+    X, y, _ = orc.synthetic(300, 3, seed=31)
+    se, per = dg.SEKernel(1.5, 1.0), dg.CauchyKernel(2.0)
+    k = se + per
+    model = dg.GPRegression(k, dg.DiracKernel(0.25), list(zip(X, y)))
+    names = model._hyper_parameters
+    cands = []
+    for s in (0.8, 1.0, 1.3, 1.7):
+        c = dict(model._current_state)
+        c[[n for n in names if n.endswith("bandwidth")][0]] *= s
+        cands.append(c)
+    es = model.energyBatch(cands)
+    for c, e in zip(cands, es):
+        lsc = c[[n for n in names if n.endswith("bandwidth")][0]]
+        ok = orc.Sum(orc.Kernel("se", {"bandwidth": lsc, "amplitude": 1.0}), orc.Kernel("cauchy", {"sigma": 2.0}))
+        assert e == pytest.approx(orc.energy(ok, 0.25, X, y), rel=TOL)
+
+
+def test_composite_limits_and_malformed_programs(ctx):
+    ks = [dg.RBFKernel(1.0 + 0.1 * i) for i in range(7)]
+    big = ks[0]
+    for k in ks[1:]:
+        big = big + k
+    with pytest.raises(ValueError):
+        big._spec()
+    X, y, _ = orc.synthetic(40, 2, seed=1)
+    data = ctx.data_create(X, y)
+    try:
+        for prog in ([1.0], [1.0, 1.0, 99.0, 0.0, 1.0, 1.0, 1.0, 1.0], [1.0, 1.0, 1.0, 0.0, 1.0, 2.0, 1.0],
+                     [1.0, 1.0, 1.0, 0.0, 1.0, 2.0, 1.0, 1.5], [1.0, 1.0, 10.0, 0.0, 0.0, 1.0, 1.0]):
+            spec = _capi.make_spec(_capi.KERNEL_COMPOSITE, prog, 0.1)
+            with pytest.raises(dg.DgpError):
+                ctx.energy(data, spec)
+    finally:
+        ctx.data_destroy(data)
+
+
+def test_composite_many_features_and_ragged_n():
+    """d = 40 (> 32 features, generic loops) and N not a multiple of the tile."""
+    X, y, _ = orc.synthetic(333, 40, seed=2)
+    k = dg.SEKernel(6.0, 1.0) * dg.GenericMaternKernel(9.0, 1) + dg.LaplacianKernel(30.0) * 0.3
+    ok = orc.Sum(orc.Prod(orc.Kernel("se", {"bandwidth": 6.0, "amplitude": 1.0}), orc.Kernel("matern", {"p": 1.0, "l": 9.0})),
+                 orc.Scaled(orc.Kernel("laplacian", {"beta": 30.0}), 0.3))
+    model = dg.GPRegression(k, dg.DiracKernel(0.2), list(zip(X, y)))
+    assert model.energy(model._current_state) == pytest.approx(orc.energy(ok, 0.2, X, y), rel=TOL)
+    g, go = model.gradEnergy(model._current_state), orc.grad_energy(ok, 0.2, X, y)
+    scale = max(abs(v) for v in go.values())
+    for (gn, gv), (on, ov) in zip(g.items(), go.items()):
+        assert gv == pytest.approx(ov, rel=TOL, abs=TOL * scale), (gn, on)

@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 import dynaml_b200 as dg
+from dynaml_b200 import _capi
 from dynaml_b200 import optimization as opt
 from oracle import gp_oracle as orc
 
@@ -63,6 +64,40 @@ def test_additive_covariance_naming_and_routing():
     assert add.effective_hyper_parameters == [f"{fid}/bandwidth", f"{fid}/amplitude"]
     add.setHyperParameters({f"{fid}/bandwidth": 3.0, f"{fid}/amplitude": 4.0})
     assert se.state == {"bandwidth": 3.0, "amplitude": 4.0} and nz.state == {"noiseLevel": 0.5}
+
+
+def test_kernel_algebra_reduces_to_sum_of_products():
+    # LocalScalarKernel.scala:53-91: +, *, * c; the device evaluates sum_t coef_t prod_f leaf_f^e_tf
+    se, per, rbf, mat = dg.SEKernel(1.5, 1.2), dg.PeriodicKernel(1.0, 1.3, 0.2), dg.RBFKernel(2.0), \
+        dg.GenericMaternKernel(1.1, 2)
+    k = (se + per * 2.0) * (rbf + mat) * 0.5
+    assert [type(x).__name__ for x in k._leaves()] == ["SEKernel", "PeriodicKernel", "RBFKernel", "GenericMaternKernel"]
+    terms = sorted((c, tuple(sorted(m.items()))) for c, m in k._terms())
+    assert terms == sorted([(0.5, ((0, 1), (2, 1))), (0.5, ((0, 1), (3, 1))), (1.0, ((1, 1), (2, 1))),
+                            (1.0, ((1, 1), (3, 1)))])
+    # names nest one "<Class@hash>/" per combinator, in leaf order; Matern's p stays blocked through the nesting
+    assert [h.split("/")[-1] for h in k.hyper_parameters] == ["bandwidth", "amplitude", "sigma", "lengthscale",
+                                                              "frequency", "bandwidth", "p", "l"]
+    assert [h.split("/")[-1] for h in k.effective_hyper_parameters][-1] == "l" and \
+        "p" not in [h.split("/")[-1] for h in k.effective_hyper_parameters]
+    k.setHyperParameters({h: 3.0 for h in k.effective_hyper_parameters})
+    assert se.state == {"bandwidth": 3.0, "amplitude": 3.0} and rbf.state == {"bandwidth": 3.0}
+    assert mat.state["l"] == 3.0 and mat.state["p"] == 2.0
+    spec, prog = k._spec(noise=0.1)
+    assert spec.kind == _capi.KERNEL_COMPOSITE and prog[0] == 4 and prog[1] == 4
+    assert _capi.load_library().dgp_spec_grad_len(spec) == 2 + 3 + 1 + 2 + 1
+    s1, _ = dg.SEKernel(1.0, 1.0)._spec()
+    assert _capi.load_library().dgp_spec_grad_len(s1) == 3
+    with pytest.raises(ValueError):
+        _ = se * -1.0  # "Multiplicative constant applied on a kernel must be positive!"
+
+
+def test_cov_plus_dirac_keeps_the_single_kernel_noise_path():
+    se, nz = dg.SEKernel(1.0, 2.0), dg.DiracKernel(0.5)
+    spec, _ = (se + nz)._spec()
+    assert spec.kind == _capi.KERNEL_SE and spec.noise == 0.5
+    spec2, _ = ((se * 2.0) + nz)._spec()
+    assert spec2.kind == _capi.KERNEL_COMPOSITE and spec2.noise == 0.0
 
 
 def test_unsupported_kernel_has_no_cpu_fallback():
