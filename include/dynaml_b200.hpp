@@ -16,6 +16,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
+#include <cstdio>
 #include <functional>
 #include <limits>
 #include <map>
@@ -248,6 +250,163 @@ class DiracKernel : public LocalScalarKernel {
   int device_kind() const override { return DGP_KERNEL_DIRAC; }
 };
 
+// ---- kernel algebra (LocalScalarKernel.scala:53-91) -------------------------------------------------------
+// k1 + k2, k1 * k2 and k * c reduce to  sum_t coef_t prod_f leaf_f^e_tf ; device_hyp() is then the flat
+// DGP_KERNEL_COMPOSITE program of dgp_b200.h.  Hyper-parameter names carry one "<Class@id>/" prefix per
+// combinator and configurations are routed by prefix, as AdditiveCovariance.scala:34-58 does.
+class CompositeCovariance : public LocalScalarKernel {
+ public:
+  using Term = std::pair<double, std::map<int, int>>;  // coefficient, leaf position -> exponent
+  using KernelPtr = std::shared_ptr<LocalScalarKernel>;
+
+  int device_kind() const override { return DGP_KERNEL_COMPOSITE; }
+  Vec device_hyp() const override {
+    std::vector<const LocalScalarKernel *> lv;
+    leaves(lv);
+    std::vector<Term> ts = terms();
+    if (lv.empty() || lv.size() > DGP_MAX_FACTORS || ts.empty() || ts.size() > DGP_MAX_TERMS)
+      throw std::invalid_argument("a composite kernel takes 1..6 base kernels and 1..16 terms (no CPU fallback)");
+    Vec prog{(double)lv.size(), (double)ts.size()};
+    for (const auto *k : lv) {
+      Vec h = k->device_hyp();
+      prog.push_back((double)k->device_kind());
+      prog.push_back((double)k->grad_mode);
+      prog.push_back((double)h.size());
+      prog.insert(prog.end(), h.begin(), h.end());
+    }
+    for (const auto &t : ts) {
+      prog.push_back(t.first);
+      for (size_t f = 0; f < lv.size(); ++f) {
+        auto it = t.second.find((int)f);
+        prog.push_back(it == t.second.end() ? 0.0 : (double)it->second);
+      }
+    }
+    return prog;
+  }
+  virtual void leaves(std::vector<const LocalScalarKernel *> &out) const = 0;
+  virtual std::vector<Term> terms() const = 0;
+
+  static void leaves_of(const LocalScalarKernel &k, std::vector<const LocalScalarKernel *> &out) {
+    if (auto *c = dynamic_cast<const CompositeCovariance *>(&k)) c->leaves(out);
+    else out.push_back(&k);
+  }
+  static std::vector<Term> terms_of(const LocalScalarKernel &k) {
+    if (auto *c = dynamic_cast<const CompositeCovariance *>(&k)) return c->terms();
+    return {Term{1.0, {{0, 1}}}};
+  }
+  static std::string id_of(const LocalScalarKernel &k, const char *cls) {
+    char buf[96];
+    snprintf(buf, sizeof buf, "%s@%llx", cls, (unsigned long long)(uintptr_t)&k & 0xffffffffull);
+    return buf;
+  }
+};
+
+class PairCovariance : public CompositeCovariance {
+ public:
+  PairCovariance(KernelPtr first, KernelPtr other, const char *fcls, const char *scls)
+      : firstKernel(std::move(first)), otherKernel(std::move(other)) {
+    fID = id_of(*firstKernel, fcls);
+    sID = id_of(*otherKernel, scls);
+    for (const auto &h : firstKernel->hyper_parameters) hyper_parameters.push_back(fID + "/" + h);
+    for (const auto &h : otherKernel->hyper_parameters) hyper_parameters.push_back(sID + "/" + h);
+    for (const auto &h : firstKernel->blocked_hyper_parameters) blocked_hyper_parameters.push_back(fID + "/" + h);
+    for (const auto &h : otherKernel->blocked_hyper_parameters) blocked_hyper_parameters.push_back(sID + "/" + h);
+    for (const auto &kv : firstKernel->state) state[fID + "/" + kv.first] = kv.second;
+    for (const auto &kv : otherKernel->state) state[sID + "/" + kv.first] = kv.second;
+  }
+  KernelPtr firstKernel, otherKernel;
+  std::string fID, sID;
+
+  void setHyperParameters(const Config &h) override {
+    Config c1, c2;
+    for (const auto &kv : h) {
+      if (kv.first.rfind(fID + "/", 0) == 0) c1[kv.first.substr(fID.size() + 1)] = kv.second;
+      if (kv.first.rfind(sID + "/", 0) == 0) c2[kv.first.substr(sID.size() + 1)] = kv.second;
+    }
+    firstKernel->setHyperParameters(c1);
+    otherKernel->setHyperParameters(c2);
+    LocalScalarKernel::setHyperParameters(h);
+  }
+  void leaves(std::vector<const LocalScalarKernel *> &out) const override {
+    leaves_of(*firstKernel, out);
+    leaves_of(*otherKernel, out);
+  }
+
+ protected:
+  std::vector<Term> shifted_other() const {
+    std::vector<const LocalScalarKernel *> lv;
+    leaves_of(*firstKernel, lv);
+    std::vector<Term> out;
+    for (const auto &t : terms_of(*otherKernel)) {
+      Term s{t.first, {}};
+      for (const auto &fe : t.second) s.second[fe.first + (int)lv.size()] = fe.second;
+      out.push_back(s);
+    }
+    return out;
+  }
+};
+
+class AdditiveCovariance : public PairCovariance {  // AdditiveCovariance.scala:27-93
+ public:
+  AdditiveCovariance(KernelPtr first, KernelPtr other)
+      : PairCovariance(std::move(first), std::move(other), "Kernel", "Kernel") {}
+  std::vector<Term> terms() const override {
+    std::vector<Term> out = terms_of(*firstKernel), o = shifted_other();
+    out.insert(out.end(), o.begin(), o.end());
+    return out;
+  }
+};
+
+class MultiplicativeCovariance : public PairCovariance {  // MultiplicativeCovariance.scala:11-90
+ public:
+  MultiplicativeCovariance(KernelPtr first, KernelPtr other)
+      : PairCovariance(std::move(first), std::move(other), "Kernel", "Kernel") {}
+  std::vector<Term> terms() const override {
+    std::vector<Term> out;
+    for (const auto &a : terms_of(*firstKernel))
+      for (const auto &b : shifted_other()) {
+        Term t{a.first * b.first, a.second};
+        for (const auto &fe : b.second) t.second[fe.first] += fe.second;
+        out.push_back(t);
+      }
+    return out;
+  }
+};
+
+class ScaledKernel : public CompositeCovariance {  // kernel * c, LocalScalarKernel.scala:68-91
+ public:
+  ScaledKernel(KernelPtr base_, double c_) : base(std::move(base_)), c(c_) {
+    if (!(c > 0)) throw std::invalid_argument("Multiplicative constant applied on a kernel must be positive!");
+    hyper_parameters = base->hyper_parameters;
+    blocked_hyper_parameters = base->blocked_hyper_parameters;
+    state = base->state;
+  }
+  KernelPtr base;
+  double c;
+  void setHyperParameters(const Config &h) override {
+    base->setHyperParameters(h);
+    LocalScalarKernel::setHyperParameters(h);
+  }
+  void leaves(std::vector<const LocalScalarKernel *> &out) const override { leaves_of(*base, out); }
+  std::vector<Term> terms() const override {
+    std::vector<Term> out = terms_of(*base);
+    for (auto &t : out) t.first *= c;
+    return out;
+  }
+};
+
+inline std::shared_ptr<LocalScalarKernel> operator+(std::shared_ptr<LocalScalarKernel> a,
+                                                    std::shared_ptr<LocalScalarKernel> b) {
+  return std::make_shared<AdditiveCovariance>(std::move(a), std::move(b));
+}
+inline std::shared_ptr<LocalScalarKernel> operator*(std::shared_ptr<LocalScalarKernel> a,
+                                                    std::shared_ptr<LocalScalarKernel> b) {
+  return std::make_shared<MultiplicativeCovariance>(std::move(a), std::move(b));
+}
+inline std::shared_ptr<LocalScalarKernel> operator*(std::shared_ptr<LocalScalarKernel> a, double c) {
+  return std::make_shared<ScaledKernel>(std::move(a), c);
+}
+
 // ---- results -------------------------------------------------------------------------------------------
 struct MultGaussianPRV {
   Vec mu;
@@ -331,7 +490,9 @@ class GPRegression {
     refresh_state();
     Vec hyp = covariance->device_hyp();
     dgp_kernel_spec sp = spec(hyp);
-    std::vector<double> gr(hyp.size() + 1);
+    const int32_t ng = dgp_spec_grad_len(&sp);
+    if (ng < 1) throw std::invalid_argument("malformed kernel spec");
+    std::vector<double> gr((size_t)ng);
     double e = 0.0;
     const int32_t st = dgp_energy_grad(ctx_->get(), device_data(), &sp, &e, gr.data());
     if (st != DGP_ERR_NOT_PD) ctx_->check(st);

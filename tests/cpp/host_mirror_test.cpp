@@ -103,6 +103,23 @@ int main(int argc, char **argv) {
     Config gbad = gp.gradEnergy({{"p", 2.0}, {"l", std::nan("")}, {"noiseLevel", 0.3}});
     std::printf("\"nonpd_energy_is_inf\": %s, \"nonpd_grad_is_nan\": %s,\n", std::isinf(bad) ? "true" : "false",
                 (std::isnan(gbad.at("l")) && std::isnan(gbad.at("noiseLevel"))) ? "true" : "false");
+    // ---- kernel algebra (LocalScalarKernel.scala:53-91): (SE * Cauchy + Matern * 0.6) as a device composite
+    {
+      std::shared_ptr<LocalScalarKernel> se = std::make_shared<SEKernel>(1.4, 1.1);
+      std::shared_ptr<LocalScalarKernel> ca = std::make_shared<CauchyKernel>(2.0);
+      std::shared_ptr<LocalScalarKernel> ma = std::make_shared<GenericMaternKernel>(1.7, 2);
+      std::shared_ptr<LocalScalarKernel> k = se * ca + ma * 0.6;
+      GPRegression cgp(k, std::make_shared<DiracKernel>(0.3), data);
+      Config ch = cgp._current_state();
+      std::printf("\"composite_energy\": %.17g,\n", cgp.energy(ch));
+      Config cg = cgp.gradEnergy(ch);
+      std::vector<double> ordered;
+      for (const auto &name : k->effective_hyper_parameters()) ordered.push_back(cg.at(name));
+      ordered.push_back(cg.at("noiseLevel"));
+      print_vec("composite_grad", ordered);
+      MultGaussianPRV cpost = cgp.predictiveDistribution(test);
+      print_vec("composite_mu", cpost.mu);
+    }
     // ---- unsupported / bad arguments surface as exceptions, never as a CPU fallback
     bool threw = false;
     try {

@@ -76,3 +76,15 @@ def test_cpp_tuners(result):
     assert out["persisted_predict0"] == pytest.approx(mu[0], rel=TOL)
     assert math.isfinite(out["csa_energy"]) and out["csa_energy"] <= max(ref) + 1e-9
     assert out["nonpd_energy_is_inf"] and out["nonpd_grad_is_nan"]
+
+
+def test_cpp_kernel_algebra(result):
+    out, (X, y, Xs) = result
+    ok = orc.Sum(orc.Prod(orc.Kernel("se", {"bandwidth": 1.4, "amplitude": 1.1}), orc.Kernel("cauchy", {"sigma": 2.0})),
+                 orc.Scaled(orc.Kernel("matern", {"p": 2.0, "l": 1.7}), 0.6))
+    assert out["composite_energy"] == pytest.approx(orc.energy(ok, 0.3, X, y), rel=TOL)
+    go = orc.grad_energy(ok, 0.3, X, y)
+    ref = np.array(list(go.values()))  # bandwidth, amplitude, sigma, l, noiseLevel
+    assert np.abs(np.array(out["composite_grad"]) - ref).max() <= TOL * np.abs(ref).max()
+    mu, _ = orc.predictive(ok, 0.3, X, y, Xs)
+    assert np.abs(np.array(out["composite_mu"]) - mu).max() <= TOL * np.abs(mu).max()
