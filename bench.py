@@ -276,6 +276,28 @@ def main():
                 traffic = None
         potrf_tf = (n ** 3 / 3.0) / (phase["potrf"] * 1e-3) / 1e12
         asm_gbs = 8.0 * n * (n + 1) / 2 / (phase["assemble"] * 1e-3) / 1e9
+        # ---- assembly against HBM bandwidth (north star: >= 70 %), timed alone: this workload's kernel and the
+        #      SE d = 8 kernel of config C4 at the same N.  Algorithmic bytes = 8 N (N + 1) / 2 (lower triangle).
+        hbm_peak, hbm_src = peaks["hbm_write_gbs"], "HBM write bandwidth measured live by dgp_measure_peaks"
+        mp = ROOT / "MEASURED_PEAKS.json"
+        if mp.exists():
+            try:
+                hbm_peak, hbm_src = float(json.loads(mp.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+            except Exception:
+                pass
+        asm_bytes = 8.0 * n * (n + 1) / 2
+        asm_ms = ctx.time_phase(data, spec, 0, reps=10)
+        rng8 = np.random.default_rng(1)
+        data8 = ctx.data_create(rng8.standard_normal((n, 8)), rng8.standard_normal(n))
+        se_ms = ctx.time_phase(data8, dg.SEKernel(2.0, 1.0)._spec(noise=0.1), 0, reps=10)
+        ctx.data_destroy(data8)
+        roofline_assembly = {
+            "bound": "hbm", "unit": "GB/s", "peak": hbm_peak, "peak_source": hbm_src,
+            "kernel": "assemble_gram_lean_kernel (lower tiles of K, N = %d)" % n,
+            "workload_kernel": {"ms": asm_ms, "achieved": asm_bytes / asm_ms / 1e6,
+                                "frac": asm_bytes / asm_ms / 1e6 / hbm_peak},
+            "se_d8": {"ms": se_ms, "achieved": asm_bytes / se_ms / 1e6, "frac": asm_bytes / se_ms / 1e6 / hbm_peak},
+        }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
@@ -292,6 +314,7 @@ def main():
                          "step_frac": n ** 3 / (wall / args.steps) / 1e12 / peaks["dmma_tflops"],
                          "potrf_tflops": potrf_tf, "potrf_frac": potrf_tf / peaks["dmma_tflops"],
                          "assemble_gbs": asm_gbs, "assemble_frac_of_hbm_write": asm_gbs / peaks["hbm_write_gbs"]},
+            "roofline_assembly": roofline_assembly,
             "phases_ms": phase,
             "peaks_measured": peaks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * (n * d + n)),

@@ -7,7 +7,8 @@ library or an sm_100 device is missing (there is no CPU fallback).
 """
 from . import _capi
 from ._capi import Context, DgpError, NotPositiveDefinite, default_context
-from .kernels import (AdditiveCovariance, CauchyKernel, CompositeCovariance, DiracKernel, GenericMaternKernel,
+from .kernels import (AdditiveCovariance, CauchyKernel, CompositeCovariance, DiracKernel, FBMKernel,
+                      GenericMaternKernel, PolynomialKernel,
                       LaplacianKernel, LocalScalarKernel, MahalanobisKernel, MultiplicativeCovariance, PeriodicKernel,
                       RationalQuadraticKernel, RBFKernel, ScaledKernel, SEKernel, SVMKernelMatrix, TStudentKernel)
 from .models import AbstractGPRegressionModel, CudaGPRegression, GPRegression, MultGaussianPRV
@@ -19,7 +20,7 @@ __all__ = [
     "LocalScalarKernel", "SEKernel", "RBFKernel", "MahalanobisKernel", "GenericMaternKernel", "PeriodicKernel",
     "DiracKernel", "AdditiveCovariance", "MultiplicativeCovariance", "CompositeCovariance", "ScaledKernel",
     "SVMKernelMatrix",
-    "CauchyKernel", "LaplacianKernel", "RationalQuadraticKernel", "TStudentKernel",
+    "CauchyKernel", "LaplacianKernel", "RationalQuadraticKernel", "TStudentKernel", "PolynomialKernel", "FBMKernel",
     "GPRegression", "CudaGPRegression", "AbstractGPRegressionModel", "MultGaussianPRV",
     "STPRegression", "AbstractSTPRegressionModel", "MultStudentsTPRV",
     "GridSearch", "CoupledSimulatedAnnealing", "GradBasedGlobalOptimizer", "ModelTuner",

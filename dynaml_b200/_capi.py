@@ -124,7 +124,7 @@ def make_spec(kind: int, hyp, noise: float = 0.0, grad_mode: int = GRAD_REFERENC
     return s, h
 
 
-KERNEL_COMPOSITE = 10
+KERNEL_COMPOSITE, KERNEL_POLYNOMIAL, KERNEL_FBM = 10, 11, 12
 MAX_FACTORS, MAX_TERMS = 6, 16
 
 

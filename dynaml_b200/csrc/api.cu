@@ -70,6 +70,8 @@ void Ctx::release_all() {
 
 namespace {
 
+int32_t parse_simple(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out);
+
 // DGP_KERNEL_COMPOSITE: decode the flat program (layout in dgp_b200.h) into a Composite.
 int32_t parse_composite(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
   const double *p = in->hyp;
@@ -97,17 +99,20 @@ int32_t parse_composite(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
   }
   for (int f = 0; f < F; ++f) {
     int kind = 0, gm = 0, nf = 0;
-    if (pos + 3 > n || !as_int(p[pos], 0, DGP_KERNEL_COMPOSITE - 1, &kind) || !as_int(p[pos + 1], 0, 1, &gm) ||
+    if (pos + 3 > n || !as_int(p[pos], 0, DGP_KERNEL_FBM, &kind) || kind == DGP_KERNEL_COMPOSITE ||
+        !as_int(p[pos + 1], 0, 1, &gm) ||
         !as_int(p[pos + 2], 0, DGP_MAX_HYP, &nf) || pos + 3 + nf > n)
       return ctx->fail(DGP_ERR_ARG, "composite kernel: malformed base kernel %d", f);
     dgp_kernel_spec fs;
     fs.kind = kind;  fs.n_hyp = nf;  fs.grad_mode = gm;  fs.reserved = 0;  fs.hyp = p + pos + 3;  fs.noise = 0.0;
-    DGP_TRY(parse_spec(ctx, &fs, d, &comp->factor[f]));
+    DGP_TRY(parse_simple(ctx, &fs, d, &comp->factor[f]));
     pos += 3 + nf;
     total_hyp += nf;
     const Spec &sf = comp->factor[f];
     dev.cp[f] = make_cov_params(sf, false, d);
-    if (kind_is_l1(kind)) {
+    if (kind_is_inner_product(kind)) {
+      dev.any_ip = 1;
+    } else if (kind_is_l1(kind)) {
       dev.metric[f] = 1;
       dev.any_l1 = 1;
     } else if (kind == DGP_KERNEL_ARD_SE) {
@@ -149,9 +154,31 @@ int32_t parse_composite(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
 
 }  // namespace
 
+bool spec_uses_raw_points(const Spec &sp) { return sp.comp && sp.comp->dev.any_ip; }
+
 int32_t parse_spec(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
   if (!in || !in->hyp) return ctx->fail(DGP_ERR_ARG, "kernel spec / hyp is NULL");
   if (in->kind == DGP_KERNEL_COMPOSITE) return parse_composite(ctx, in, d, out);
+  if (kind_is_inner_product(in->kind)) {
+    // the non-stationary kernels run on the composite evaluation path: wrap as a one-factor expression
+    if (in->n_hyp < 0 || in->n_hyp > 2) return ctx->fail(DGP_ERR_ARG, "kernel kind %d: bad n_hyp", in->kind);
+    double prog[2 + 3 + 2 + 2] = {1.0, 1.0, (double)in->kind, (double)in->grad_mode, (double)in->n_hyp};
+    int pos = 5;
+    for (int i = 0; i < in->n_hyp; ++i) prog[pos++] = in->hyp[i];
+    prog[pos++] = 1.0;  // coefficient
+    prog[pos++] = 1.0;  // exponent
+    dgp_kernel_spec w = *in;
+    w.kind = DGP_KERNEL_COMPOSITE;
+    w.n_hyp = pos;
+    w.hyp = prog;
+    return parse_composite(ctx, &w, d, out);
+  }
+  return parse_simple(ctx, in, d, out);
+}
+
+namespace {
+
+int32_t parse_simple(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
   int want = -1;
   switch (in->kind) {
     case DGP_KERNEL_SE: want = 2; break;
@@ -164,6 +191,8 @@ int32_t parse_spec(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
     case DGP_KERNEL_LAPLACIAN: want = 1; break;
     case DGP_KERNEL_RATQUAD: want = 2; break;
     case DGP_KERNEL_TSTUDENT: want = 1; break;
+    case DGP_KERNEL_POLYNOMIAL: want = 2; break;
+    case DGP_KERNEL_FBM: want = 1; break;
     default: return ctx->fail(DGP_ERR_UNSUPPORTED_KERNEL, "unsupported kernel kind %d", in->kind);
   }
   if (in->n_hyp != want || want > DGP_MAX_HYP)
@@ -180,6 +209,8 @@ int32_t parse_spec(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
   }
   return DGP_OK;
 }
+
+}  // namespace
 
 namespace {
 
@@ -365,7 +396,8 @@ int32_t enqueue_eval(Ctx *ctx, int slot, const Data *D, const Spec &sp, bool wan
   DGP_BUF(inv, double, ctx, nm[1], (size_t)np * TILE * sizeof(double));
   DGP_BUF(x, double, ctx, nm[2], (size_t)np * sizeof(double));
   const double *Xk = nullptr;
-  DGP_TRY(scaled_points(ctx, S, sp, D->X, np, D->dp, D->d, nm[3], &Xk));
+  const double *Xbase = spec_uses_raw_points(sp) ? D->Xraw : D->X;
+  DGP_TRY(scaled_points(ctx, S, sp, Xbase, np, D->dp, D->d, nm[3], &Xk));
   CovParams cp = make_cov_params(sp, true, D->d);
 
   tick(ctx, slot, 0);
@@ -397,7 +429,7 @@ int32_t enqueue_eval(Ctx *ctx, int slot, const Data *D, const Spec &sp, bool wan
     const int nsmax = grad_partials_per_tile(cp, D->dp);
     DGP_BUF(partials, double, ctx, "partials", (size_t)tiles * nsmax * sizeof(double));
     GradArgs g;
-    g.X = D->X;  g.Xs = Xk;  g.alpha = x;  g.Kinv = Kinv;  g.ld = np;
+    g.X = Xbase;  g.Xs = Xk;  g.alpha = x;  g.Kinv = Kinv;  g.ld = np;
     g.n = D->N;  g.np = np;  g.dp = D->dp;
     g.partials = partials;  g.sums = d_scal + 2;
     DGP_TRY(grad_trace(ctx, S, cp, g, ns_out));
@@ -575,17 +607,22 @@ int32_t dgp_data_create(dgp_ctx *ctx, const double *X, int64_t N, int32_t d, int
   column_means(X, N, d, x_layout, D->center);
   D->max_sq_norm = pack_points(X, N, d, x_layout, D->Np, D->dp, hx, D->center.data());
   D->has_dup = has_duplicate_rows(hx, N, D->dp);
+  std::vector<double> hraw;
+  pack_points(X, N, d, x_layout, D->Np, D->dp, hraw, nullptr);
   for (int64_t i = 0; i < N; ++i) hr[i] = y[i] - (mean ? mean[i] : 0.0);
   cudaError_t e1 = cudaMalloc(&D->X, hx.size() * sizeof(double));
   cudaError_t e2 = cudaMalloc(&D->r, hr.size() * sizeof(double));
-  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+  cudaError_t e3 = cudaMalloc(&D->Xraw, hraw.size() * sizeof(double));
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
     cudaFree(D->X);
+    cudaFree(D->Xraw);
     cudaFree(D->r);
     delete D;
     cudaGetLastError();
     return ctx->fail(DGP_ERR_OOM, "data: device allocation failed");
   }
   cudaMemcpyAsync(D->X, hx.data(), hx.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(D->Xraw, hraw.data(), hraw.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
   cudaMemcpyAsync(D->r, hr.data(), hr.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
   DGP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   *out = D;
@@ -599,6 +636,7 @@ int32_t dgp_data_destroy(dgp_ctx *ctx, dgp_data *D) {
     cudaStreamSynchronize(ctx->stream);
   }
   cudaFree(D->X);
+  cudaFree(D->Xraw);
   cudaFree(D->r);
   delete D;
   return DGP_OK;
@@ -737,6 +775,8 @@ int32_t dgp_fit(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *spec, dg
   m->spec = sp;
   m->N = D->N;  m->Np = np;  m->d = D->d;  m->dp = D->dp;
   m->center = D->center;  m->max_sq_norm = D->max_sq_norm;
+  const bool raw = spec_uses_raw_points(sp);
+  if (raw) m->center.assign(D->center.size(), 0.0);  // test points are then taken as they are
   bool ok = cudaMalloc(&m->X, (size_t)np * D->dp * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&m->L, (size_t)np * np * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&m->inv, (size_t)np * TILE * sizeof(double)) == cudaSuccess &&
@@ -752,7 +792,7 @@ int32_t dgp_fit(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *spec, dg
     dgp_model_destroy(ctx, m);
     return st;
   };
-  cudaMemcpyAsync(m->X, D->X, (size_t)np * D->dp * sizeof(double), cudaMemcpyDeviceToDevice, S);
+  cudaMemcpyAsync(m->X, raw ? D->Xraw : D->X, (size_t)np * D->dp * sizeof(double), cudaMemcpyDeviceToDevice, S);
   if (sp.kind == DGP_KERNEL_ARD_SE) {
     ScaleVec s;
     for (int c = 0; c < 128; ++c) s.v[c] = (c < D->d) ? 1.0 / sp.hyp[1 + c] : 0.0;
@@ -935,6 +975,7 @@ int32_t dgp_kernel_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec, const doubl
   const int dp = (int)round_up(d, 4);
   std::vector<double> h1, h2, ctr;
   column_means(X1, N1, d, x_layout, ctr);
+  if (spec_uses_raw_points(sp)) ctr.assign(ctr.size(), 0.0);
   double nmax = pack_points(X1, N1, d, x_layout, n1p, dp, h1, ctr.data());
   DGP_BUF(A1, double, ctx, "km_x1", h1.size() * sizeof(double));
   DGP_CUDA_OK(ctx, cudaMemcpyAsync(A1, h1.data(), h1.size() * sizeof(double), cudaMemcpyHostToDevice, S));
@@ -1004,7 +1045,7 @@ int32_t dgp_time_phase(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *s
   DGP_BUF(K, double, ctx, "K", (size_t)np * np * sizeof(double));
   DGP_BUF(inv, double, ctx, "inv", (size_t)np * TILE * sizeof(double));
   const double *Xk = nullptr;
-  DGP_TRY(scaled_points(ctx, S, sp, D->X, np, D->dp, D->d, "Xs", &Xk));
+  DGP_TRY(scaled_points(ctx, S, sp, spec_uses_raw_points(sp) ? D->Xraw : D->X, np, D->dp, D->d, "Xs", &Xk));
   CovParams cp = make_cov_params(sp, true, D->d);
   AssembleArgs a;
   a.X1 = Xk;  a.X2 = Xk;  a.dp = D->dp;

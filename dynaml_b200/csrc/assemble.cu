@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(CovParams cp, Assemb
 // hyper-parameter Map for every pair.  Same tiling as assemble_kernel's generic branch.
 // ---------------------------------------------------------------------------------------------
 struct PairMetrics {
-  double r2 = 0.0, l1 = 0.0, ard[MAX_ARD_SLOTS] = {0.0, 0.0};
+  PairGeom g;
+  double ard[MAX_ARD_SLOTS] = {0.0, 0.0};
 };
 
 __device__ __forceinline__ void pair_metrics(const CompositeDev &c, const double *x, const double *y, int dp,
@@ -153,8 +154,13 @@ __device__ __forceinline__ void pair_metrics(const CompositeDev &c, const double
   for (int k = 0; k < dp; ++k) {
     const double e = x[k] - y[k];
     const double e2 = e * e;
-    m.r2 += e2;
-    if (c.any_l1) m.l1 += fabs(e);
+    m.g.r2 += e2;
+    if (c.any_l1) m.g.l1 += fabs(e);
+    if (c.any_ip) {
+      m.g.dot = fma(x[k], y[k], m.g.dot);
+      m.g.nx = fma(x[k], x[k], m.g.nx);
+      m.g.ny = fma(y[k], y[k], m.g.ny);
+    }
 #pragma unroll
     for (int s = 0; s < MAX_ARD_SLOTS; ++s)
       if (k < MAX_ARD_DIM) m.ard[s] = fma(c.w[s][k], e2, m.ard[s]);
@@ -163,13 +169,17 @@ __device__ __forceinline__ void pair_metrics(const CompositeDev &c, const double
 
 __device__ __forceinline__ double metric_of(const CompositeDev &c, const PairMetrics &m, int f) {
   const int id = c.metric[f];
-  return id == 0 ? m.r2 : (id == 1 ? m.l1 : m.ard[id - 2]);
+  return id == 0 ? m.g.r2 : (id == 1 ? m.g.l1 : m.ard[id - 2]);
 }
 
 __device__ __forceinline__ double composite_entry(const CompositeDev &c, const PairMetrics &m) {
   double v[MAXF];
 #pragma unroll
-  for (int f = 0; f < MAXF; ++f) v[f] = (f < c.F) ? cov_value_rt(c.cp[f], metric_of(c, m, f)) : 1.0;
+  for (int f = 0; f < MAXF; ++f) {
+    if (f >= c.F) v[f] = 1.0;
+    else if (kind_is_inner_product(c.cp[f].kind)) v[f] = cov_value_ip(c.cp[f], m.g);
+    else v[f] = cov_value_rt(c.cp[f], metric_of(c, m, f));
+  }
   return composite_combine(c, v);
 }
 
@@ -213,8 +223,8 @@ __global__ void __launch_bounds__(ATHREADS) assemble_composite_kernel(CompositeD
     pair_metrics(c, p0, y, dp, q0);
     pair_metrics(c, p1, y, dp, q1);
     double k0 = composite_entry(c, q0), k1 = composite_entry(c, q1);
-    if (q0.r2 == 0.0) k0 += noise_abs;
-    if (q1.r2 == 0.0) k1 += noise_abs;
+    if (q0.g.r2 == 0.0) k0 += noise_abs;
+    if (q1.g.r2 == 0.0) k1 += noise_abs;
     const int64_t col = n0 + j;
     if (r0 >= a.rows || col >= a.cols) k0 = (sym && r0 == col) ? 1.0 : 0.0;
     if (r0 + 1 >= a.rows || col >= a.cols) k1 = (sym && r0 + 1 == col) ? 1.0 : 0.0;

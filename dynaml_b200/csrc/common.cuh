@@ -84,6 +84,7 @@ struct Data {
   int d = 0;        // real feature count
   int dp = 0;       // padded to a multiple of 4 (zero columns; exact for every distance used here)
   double *X = nullptr;  // Np x dp, row-major (point i at X + i*dp), pad rows zero
+  double *Xraw = nullptr;  // the same points without the centring, for the kernels that are not translation invariant
   double *r = nullptr;  // y - m(X), length Np, pad entries zero
   // The stored points are centred (column means subtracted): every kernel on this path is
   // translation invariant, and small norms keep the Gram-form distances accurate.
@@ -107,6 +108,7 @@ struct Spec {
 };
 
 int32_t parse_spec(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out);
+bool spec_uses_raw_points(const Spec &sp);  // PolynomialKernel / FBMKernel somewhere in the expression
 
 }  // namespace dgp
 

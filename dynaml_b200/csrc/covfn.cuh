@@ -66,6 +66,25 @@ __host__ __device__ constexpr bool kind_is_l1(int kind) {
   return kind == DGP_KERNEL_PERIODIC || kind == DGP_KERNEL_LAPLACIAN;
 }
 
+// Kinds that are not functions of x - y: they consume x.y, |x|^2, |y|^2 of the original points.
+__host__ __device__ constexpr bool kind_is_inner_product(int kind) {
+  return kind == DGP_KERNEL_POLYNOMIAL || kind == DGP_KERNEL_FBM;
+}
+
+// Pair geometry a composite evaluation has at hand.
+struct PairGeom {
+  double r2 = 0.0, l1 = 0.0, dot = 0.0, nx = 0.0, ny = 0.0;
+};
+
+__device__ __forceinline__ double cov_value_ip(const CovParams &cp, const PairGeom &q) {
+  if (cp.kind == DGP_KERNEL_POLYNOMIAL) {
+    // PolynomialKernel.scala:30-33: math.pow((x.t * y) + offset, degree.toInt)
+    return pow(q.dot + cp.c1, (double)cp.p);
+  }
+  // FBMKernel.scala:84-91: 0.5 (|x|^2H + |y|^2H - |x-y|^2H) with the norms themselves raised to 2H
+  return 0.5 * (pow(sqrt(q.nx), cp.c2) + pow(sqrt(q.ny), cp.c2) - pow(sqrt(q.r2), cp.c2));
+}
+
 // Runtime-dispatched value (composite kernels evaluate several kinds per pair; the switch is warp-uniform).
 __device__ __forceinline__ double cov_value_rt(const CovParams &cp, double dist) {
   switch (cp.kind) {
@@ -89,6 +108,7 @@ constexpr int MAXF = DGP_MAX_FACTORS, MAXT = DGP_MAX_TERMS, MAX_ARD_SLOTS = 2, M
 struct CompositeDev {
   int F = 0, T = 0;
   int any_l1 = 0;                 // some factor consumes |x-y|_1
+  int any_ip = 0;                 // some factor consumes x.y / |x|^2 / |y|^2 (the points are then the raw ones)
   int metric[MAXF];               // per factor: 0 = |x-y|_2^2, 1 = |x-y|_1, 2 + s = ARD slot s
   int moment_off[MAXF + 1];       // gradient pass: first moment of each factor; [F] = the noise moment
   int ard_exact[MAXF];            // ARD factor with the exact per-dimension derivative
@@ -200,6 +220,14 @@ inline CovParams make_cov_params(const Spec &s, bool with_noise, int d) {
       break;
     case DGP_KERNEL_COMPOSITE:
       cp.comp = s.comp ? &s.comp->dev : nullptr;
+      break;
+    case DGP_KERNEL_POLYNOMIAL:
+      cp.p = (int)s.hyp[0];  // config("degree").toInt
+      cp.c1 = s.hyp[1];
+      break;
+    case DGP_KERNEL_FBM:
+      cp.c1 = s.hyp[0];
+      cp.c2 = 2.0 * s.hyp[0];
       break;
   }
   return cp;

@@ -354,7 +354,8 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *
   cudaStream_t P = la ? ctx->panel : ctx->stream;
 
   // ---- inputs padded to whole tiles -----------------------------------------------------------------
-  const double *Xin = D->X;
+  const double *Xsrc = spec_uses_raw_points(sp) ? D->Xraw : D->X;
+  const double *Xin = Xsrc;
   const double *rin = D->r;
   if (Ntot > D->Np) {
     double *Xp = (double *)ctx->buf("dist_X", (size_t)Ntot * D->dp * sizeof(double));
@@ -362,7 +363,7 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *
     if (!Xp || !rp) return DGP_ERR_OOM;
     DGP_CUDA_OK(ctx, cudaMemsetAsync(Xp, 0, (size_t)Ntot * D->dp * sizeof(double), S));
     DGP_CUDA_OK(ctx, cudaMemsetAsync(rp, 0, (size_t)Ntot * sizeof(double), S));
-    DGP_CUDA_OK(ctx, cudaMemcpyAsync(Xp, D->X, (size_t)D->Np * D->dp * sizeof(double), cudaMemcpyDeviceToDevice, S));
+    DGP_CUDA_OK(ctx, cudaMemcpyAsync(Xp, Xsrc, (size_t)D->Np * D->dp * sizeof(double), cudaMemcpyDeviceToDevice, S));
     DGP_CUDA_OK(ctx, cudaMemcpyAsync(rp, D->r, (size_t)D->Np * sizeof(double), cudaMemcpyDeviceToDevice, S));
     Xin = Xp;
     rin = rp;

@@ -19,7 +19,7 @@ constexpr int GT = 128;
 constexpr int GTHREADS = 256;
 
 enum Mode { M_SE = 0, M_ARD_REF = 1, M_ARD_EXACT = 2, M_MATERN = 3, M_PERIODIC = 4, M_DIRAC = 5, M_CAUCHY = 6,
-            M_LAPLACIAN = 7, M_RATQUAD = 8, M_TSTUDENT = 9 };
+            M_LAPLACIAN = 7, M_RATQUAD = 8, M_TSTUDENT = 9, M_POLY = 10, M_FBM = 11 };
 
 template <int MODE, int DP>
 struct NSums {
@@ -336,24 +336,44 @@ struct CompositeModes {
   int mode[MAXF];
 };
 
+// FBMKernel.scala:96-120: a^H ln a + b^H ln b - c^H ln c with a = |x|^2, b = |y|^2, c = |x-y|^2 (its NaN guards
+// compare against Double.NaN and never fire, so 0 ln 0 = NaN reaches the sum); exact mode: the true derivative.
+__device__ __forceinline__ double fbm_dhurst(const CovParams &cp, const PairGeom &q) {
+  const double h = cp.c1;
+  if (cp.grad_mode == DGP_GRAD_EXACT) {
+    auto term = [h](double a) { return a > 0.0 ? pow(a, h) * log(a) : 0.0; };
+    return 0.5 * (term(q.nx) + term(q.ny) - term(q.r2));
+  }
+  return pow(q.nx, h) * log(q.nx) + pow(q.ny, h) * log(q.ny) - pow(q.r2, h) * log(q.r2);
+}
+
 __device__ __forceinline__ void composite_pair(const CompositeDev &c, const CompositeModes &md, const double *x,
                                                const double *y, int dp, double m, double *s) {
-  double r2 = 0.0, l1 = 0.0, ard[MAX_ARD_SLOTS] = {0.0, 0.0};
+  PairGeom q;
+  double ard[MAX_ARD_SLOTS] = {0.0, 0.0};
   for (int k = 0; k < dp; ++k) {
     const double e = x[k] - y[k];
     const double e2 = e * e;
-    r2 += e2;
-    if (c.any_l1) l1 += fabs(e);
+    q.r2 += e2;
+    if (c.any_l1) q.l1 += fabs(e);
+    if (c.any_ip) {
+      q.dot = fma(x[k], y[k], q.dot);
+      q.nx = fma(x[k], x[k], q.nx);
+      q.ny = fma(y[k], y[k], q.ny);
+    }
 #pragma unroll
-    for (int q = 0; q < MAX_ARD_SLOTS; ++q)
-      if (k < MAX_ARD_DIM) ard[q] = fma(c.w[q][k], e2, ard[q]);
+    for (int a = 0; a < MAX_ARD_SLOTS; ++a)
+      if (k < MAX_ARD_DIM) ard[a] = fma(c.w[a][k], e2, ard[a]);
   }
+  const double r2 = q.r2;
   double v[MAXF], dist[MAXF];
 #pragma unroll
   for (int f = 0; f < MAXF; ++f) {
     const int id = (f < c.F) ? c.metric[f] : 0;
-    dist[f] = id == 0 ? r2 : (id == 1 ? l1 : ard[id - 2]);
-    v[f] = (f < c.F) ? cov_value_rt(c.cp[f], dist[f]) : 1.0;
+    dist[f] = id == 0 ? q.r2 : (id == 1 ? q.l1 : ard[id - 2]);
+    if (f >= c.F) v[f] = 1.0;
+    else if (kind_is_inner_product(c.cp[f].kind)) v[f] = cov_value_ip(c.cp[f], q);
+    else v[f] = cov_value_rt(c.cp[f], dist[f]);
   }
 #pragma unroll
   for (int f = 0; f < MAXF; ++f) {
@@ -369,6 +389,10 @@ __device__ __forceinline__ void composite_pair(const CompositeDev &c, const Comp
         const double df = x[k] - y[k];
         sf[1 + k] = fma(we, df * df, sf[1 + k]);
       }
+    } else if (md.mode[f] == M_FBM) {
+      sf[0] = fma(w, fbm_dhurst(c.cp[f], q), sf[0]);
+    } else if (md.mode[f] == M_POLY) {
+      // no derivative in the reference (stub returning 0.0 per hyper-parameter)
     } else {
       accumulate_rt(md.mode[f], c.cp[f], w, dist[f], r2, sf);
     }
@@ -490,6 +514,8 @@ int mode_of(const CovParams &cp) {
     case DGP_KERNEL_LAPLACIAN: return M_LAPLACIAN;
     case DGP_KERNEL_RATQUAD: return M_RATQUAD;
     case DGP_KERNEL_TSTUDENT: return M_TSTUDENT;
+    case DGP_KERNEL_POLYNOMIAL: return M_POLY;
+    case DGP_KERNEL_FBM: return M_FBM;
     default: return M_DIRAC;
   }
 }
@@ -616,6 +642,13 @@ void grad_finish(const Spec &sp, int d, const double *S, int ns, double *g) {
       break;
     }
     case DGP_KERNEL_TSTUDENT:
+      g[0] = S[0];
+      break;
+    case DGP_KERNEL_POLYNOMIAL:
+      g[0] = 0.0;  // LocalSVMKernel.scala:37-41: "gradientAt function not defined, continuing with a stub"
+      g[1] = 0.0;
+      break;
+    case DGP_KERNEL_FBM:
       g[0] = S[0];
       break;
   }

@@ -91,7 +91,8 @@ class LocalScalarKernel:
         raise NotImplementedError(
             f"{type(self).__name__} has no sm_100a implementation (supported: SEKernel, RBFKernel, "
             "MahalanobisKernel, GenericMaternKernel, PeriodicKernel, DiracKernel, CauchyKernel, LaplacianKernel, "
-            "RationalQuadraticKernel, TStudentKernel); no CPU fallback")
+            "RationalQuadraticKernel, TStudentKernel, PolynomialKernel, FBMKernel and their sums / products); "
+            "no CPU fallback")
 
     def _device_hyp(self, config: Dict[str, float]) -> List[float]:
         return [float(config[h]) for h in self.hyper_parameters]
@@ -280,6 +281,50 @@ class TStudentKernel(LocalScalarKernel):
 
     def _device_kind(self):
         return _capi.KERNEL_TSTUDENT
+
+
+class PolynomialKernel(LocalScalarKernel):
+    """k = (x.y + offset)^int(degree) (PolynomialKernel.scala:9-45); setHyperParameters stores |offset|; the
+    reference defines no gradient for it (stub zeros)."""
+    hyper_parameters = ["degree", "offset"]
+
+    def __init__(self, degree: int = 2, offset: float = 1.0):
+        super().__init__()
+        self.state = {"degree": float(degree), "offset": float(offset)}
+
+    def setdegree(self, d: int) -> None:
+        self.state["degree"] = float(d)
+
+    def setoffset(self, o: float) -> None:
+        self.state["offset"] = float(o)
+
+    def setHyperParameters(self, h: Dict[str, float]):
+        super().setHyperParameters(h)
+        if "offset" in h:
+            self.state["offset"] = abs(float(h["offset"]))
+        return self
+
+    def _device_kind(self):
+        return _capi.KERNEL_POLYNOMIAL
+
+
+class FBMKernel(LocalScalarKernel):
+    """Fractional Brownian motion covariance (|x|^2H + |y|^2H - |x-y|^2H)/2 (FBMKernel.scala:70-122)."""
+    hyper_parameters = ["hurst"]
+
+    def __init__(self, hurst: float = 0.75, grad_mode: int = _capi.GRAD_REFERENCE):
+        super().__init__()
+        self.state = {"hurst": float(hurst)}
+        self.grad_mode = grad_mode
+
+    def sethurst(self, d: float) -> None:
+        self.state["hurst"] = float(d)
+
+    def getHurst(self) -> float:
+        return self.state["hurst"]
+
+    def _device_kind(self):
+        return _capi.KERNEL_FBM
 
 
 class DiracKernel(LocalScalarKernel):

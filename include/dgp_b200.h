@@ -81,7 +81,17 @@ enum {
           T x { coef_t, e_t0 .. e_t,F-1 } ]                           small non-negative integers
      gradEnergy returns the derivatives of the base kernels' hyper-parameters factor by factor,
      then the noise level: dgp_spec_grad_len() values.  ARD-SE factors need d <= 32 (two at most). */
-  DGP_KERNEL_COMPOSITE = 10
+  DGP_KERNEL_COMPOSITE = 10,
+  /* The two non-stationary kernels of SURVEY 8(f) rank 1.  They read the original (uncentred) points and run
+     on the composite evaluation path (also usable as base kernels of a composite).                          */
+  DGP_KERNEL_POLYNOMIAL = 11, /* PolynomialKernel  CORE/kernels/PolynomialKernel.scala:9-45
+                              hyp = [degree, offset]; k = (x.y + offset)^int(degree); the reference
+                              defines no gradient (LocalSVMKernel.scala:37-41 stub): derivatives are 0 */
+  DGP_KERNEL_FBM = 12      /* FBMKernel           CORE/kernels/FBMKernel.scala:70-122
+                              hyp = [hurst]; k = (|x|^2H + |y|^2H - |x-y|^2H) / 2.  DGP_GRAD_REFERENCE
+                              reproduces the reference derivative a^H ln a + b^H ln b - c^H ln c with
+                              c = |x-y|^2 (no 1/2; NaN wherever c == 0, hence NaN for every training set);
+                              DGP_GRAD_EXACT gives the true one (1/2, and 0 ln 0 = 0)                  */
 };
 
 #define DGP_MAX_FACTORS 6

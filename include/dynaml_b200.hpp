@@ -241,6 +241,28 @@ class TStudentKernel : public LocalScalarKernel {  // CORE/kernels/TStudentKerne
   int device_kind() const override { return DGP_KERNEL_TSTUDENT; }
 };
 
+class PolynomialKernel : public LocalScalarKernel {  // CORE/kernels/PolynomialKernel.scala:9-45
+ public:
+  explicit PolynomialKernel(int degree = 2, double offset = 1.0) {
+    hyper_parameters = {"degree", "offset"};
+    state = {{"degree", (double)degree}, {"offset", offset}};
+  }
+  void setHyperParameters(const Config &h) override {
+    LocalScalarKernel::setHyperParameters(h);
+    if (h.count("offset")) state["offset"] = std::fabs(h.at("offset"));
+  }
+  int device_kind() const override { return DGP_KERNEL_POLYNOMIAL; }
+};
+
+class FBMKernel : public LocalScalarKernel {  // CORE/kernels/FBMKernel.scala:70-122
+ public:
+  explicit FBMKernel(double hurst = 0.75) {
+    hyper_parameters = {"hurst"};
+    state = {{"hurst", hurst}};
+  }
+  int device_kind() const override { return DGP_KERNEL_FBM; }
+};
+
 class DiracKernel : public LocalScalarKernel {
  public:
   explicit DiracKernel(double noiseLevel = 1.0) {

@@ -95,10 +95,23 @@ class Kernel:
             return ["mu", "l"]
         if self.kind == "tstudent":
             return ["d"]
+        if self.kind == "polynomial":
+            return ["degree", "offset"]
+        if self.kind == "fbm":
+            return ["hurst"]
         raise ValueError(self.kind)
 
     def value(self, X: np.ndarray, Y: np.ndarray) -> np.ndarray:
         h = self.hyp
+        if self.kind == "polynomial":
+            # PolynomialKernel.scala:30-33: math.pow((x.t * y) + offset, degree.toInt)
+            return np.power(X @ Y.T + h["offset"], float(int(h["degree"])))
+        if self.kind == "fbm":
+            # FBMKernel.scala:84-91
+            nx, ny = np.sqrt((X * X).sum(axis=1)), np.sqrt((Y * Y).sum(axis=1))
+            two_h = 2 * h["hurst"]
+            return 0.5 * (np.power(nx, two_h)[:, None] + np.power(ny, two_h)[None, :]
+                          - np.power(np.sqrt(_sqdist(X, Y)), two_h))
         if self.kind in ("se", "rbf"):
             # RBFKernel.scala:42-43 (evalAt) and :79-80 (SEKernel multiplies by amplitude^2)
             r2 = _sqdist(X, Y)
@@ -149,6 +162,24 @@ class Kernel:
         return lead * sum_term, diff_lead * sum_term + diff_sum * lead
 
     def grads(self, X: np.ndarray, Y: np.ndarray) -> Dict[str, np.ndarray]:
+        if self.kind == "polynomial":
+            # no gradientAt: the LocalSVMKernel stub returns 0.0 per effective hyper-parameter (LocalSVMKernel.scala:37-41)
+            z = np.zeros((X.shape[0], Y.shape[0]))
+            return {"degree": z, "offset": z.copy()}
+        if self.kind == "fbm":
+            # FBMKernel.scala:96-120: the NaN guards compare with `!= Double.NaN` (always true), so the first branch
+            # always runs: a^H ln a + b^H ln b - c^H ln c, NaN wherever a, b or c is 0 (every diagonal entry)
+            hh = self.hyp["hurst"]
+            a, b = (X * X).sum(axis=1)[:, None], (Y * Y).sum(axis=1)[None, :]
+            c = _sqdist(X, Y)
+            if self.grad_mode == "exact":
+                def term(v):
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        return np.where(v > 0.0, np.power(v, hh) * np.log(np.where(v > 0.0, v, 1.0)), 0.0)
+                return {"hurst": 0.5 * (term(a) + term(b) - term(c))}
+            with np.errstate(divide="ignore", invalid="ignore"):
+                g = np.power(a, hh) * np.log(a) + np.power(b, hh) * np.log(b) - np.power(c, hh) * np.log(c)
+            return {"hurst": g}
         """dK/dtheta for every theta the reference's gradientAt returns."""
         h = self.hyp
         if self.kind in ("se", "rbf"):
@@ -388,7 +419,9 @@ def grad_energy(cov: Kernel, noise_level: float, X: np.ndarray, y: np.ndarray, m
     out: Config = {}
     for n in cov.effective(blocked):
         dK = cg[n]
-        sol = sla.solve_triangular(L.T, sla.solve_triangular(L, dK, lower=True), lower=False)
+        # check_finite=False: a NaN derivative matrix (FBMKernel's reference gradient) propagates as in Breeze
+        sol = sla.solve_triangular(L.T, sla.solve_triangular(L, dK, lower=True, check_finite=False), lower=False,
+                                   check_finite=False)
         out[n] = float(alpha @ dK @ alpha - np.trace(sol))
     if not noise_blocked:
         dK = ng["noiseLevel"]

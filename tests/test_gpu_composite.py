@@ -164,3 +164,64 @@ def test_composite_many_features_and_ragged_n():
     scale = max(abs(v) for v in go.values())
     for (gn, gv), (on, ov) in zip(g.items(), go.items()):
         assert gv == pytest.approx(ov, rel=TOL, abs=TOL * scale), (gn, on)
+
+
+# ---- the two non-stationary kernels (PolynomialKernel, FBMKernel): evaluated from the uncentred points -----------
+def test_polynomial_and_fbm_matrices_on_uncentred_points():
+    rng = np.random.default_rng(41)
+    X = rng.standard_normal((300, 4)) * 0.6 + 1.5   # far from the origin: centring must not leak in
+    Xs = rng.standard_normal((130, 4)) * 0.6 + 1.5
+    for k, ok in ((dg.PolynomialKernel(3, 1.5), orc.Kernel("polynomial", {"degree": 3.0, "offset": 1.5})),
+                  (dg.FBMKernel(0.7), orc.Kernel("fbm", {"hurst": 0.7}))):
+        K = k.buildKernelMatrix(X, len(X)).getKernelMatrix()
+        assert entry_rel(K, orc.build_kernel_matrix(ok, X)) <= TOL_K
+        C = k.buildCrossKernelMatrix(X, Xs)
+        Co = orc.cross_kernel_matrix(ok, X, Xs)
+        assert float(np.abs(C - Co).max() / np.abs(Co).max()) <= TOL_K  # FBM cross entries cancel towards 0
+    assert dg.PolynomialKernel(2, 1.0).evaluate([1.0, 2.0], [0.5, -1.0]) == pytest.approx((0.5 - 2.0 + 1.0) ** 2, rel=1e-15)
+
+
+def test_polynomial_model_energy_gradient_and_posterior():
+    X, y, Xs = orc.synthetic(220, 3, seed=43, m=30)
+    X, Xs = X + 0.8, Xs + 0.8
+    k, ok = dg.PolynomialKernel(2, 1.0), orc.Kernel("polynomial", {"degree": 2.0, "offset": 1.0})
+    model = dg.GPRegression(k, dg.DiracKernel(0.5), list(zip(X, y)))
+    h = model._current_state
+    assert model.energy(h) == pytest.approx(orc.energy(ok, 0.5, X, y), rel=TOL)
+    g, go = model.gradEnergy(h), orc.grad_energy(ok, 0.5, X, y)
+    assert g["degree"] == 0.0 and g["offset"] == 0.0          # the reference's stub gradient
+    assert g["noiseLevel"] == pytest.approx(go["noiseLevel"], rel=TOL)
+    post = model.predictiveDistribution(Xs)
+    mu, cov = orc.predictive(ok, 0.5, X, y, Xs)
+    assert np.abs(post.mu - mu).max() <= TOL * max(1.0, np.abs(mu).max())
+    assert np.abs(post.covariance - cov).max() <= TOL * np.abs(cov).max()
+
+
+def test_fbm_gradient_reference_is_nan_and_exact_matches_oracle():
+    X, y, _ = orc.synthetic(200, 2, seed=47)
+    X = X + 2.0
+    for mode, cmode in (("reference", _capi.GRAD_REFERENCE), ("exact", _capi.GRAD_EXACT)):
+        k, ok = dg.FBMKernel(0.6, cmode), orc.Kernel("fbm", {"hurst": 0.6}, mode)
+        model = dg.GPRegression(k, dg.DiracKernel(0.4), list(zip(X, y)))
+        h = model._current_state
+        assert model.energy(h) == pytest.approx(orc.energy(ok, 0.4, X, y), rel=TOL)
+        g, go = model.gradEnergy(h), orc.grad_energy(ok, 0.4, X, y)
+        if mode == "reference":
+            assert math.isnan(g["hurst"]) and math.isnan(go["hurst"])   # 0^H ln 0 on the diagonal
+        else:
+            assert g["hurst"] == pytest.approx(go["hurst"], rel=TOL)
+        assert g["noiseLevel"] == pytest.approx(go["noiseLevel"], rel=TOL)
+
+
+def test_polynomial_times_se_composite():
+    X, y, _ = orc.synthetic(200, 3, seed=49)
+    X = X + 0.5
+    k = dg.PolynomialKernel(2, 1.0) * dg.SEKernel(1.5, 1.0)
+    ok = orc.Prod(orc.Kernel("polynomial", {"degree": 2.0, "offset": 1.0}),
+                  orc.Kernel("se", {"bandwidth": 1.5, "amplitude": 1.0}))
+    model = dg.GPRegression(k, dg.DiracKernel(0.3), list(zip(X, y)))
+    assert model.energy(model._current_state) == pytest.approx(orc.energy(ok, 0.3, X, y), rel=TOL)
+    g, go = model.gradEnergy(model._current_state), orc.grad_energy(ok, 0.3, X, y)
+    scale = max(abs(v) for v in go.values())
+    for (gn, gv), (on, ov) in zip(g.items(), go.items()):
+        assert gv == pytest.approx(ov, rel=TOL, abs=TOL * scale), (gn, on)
