@@ -11,7 +11,8 @@ from .kernels import (AdditiveCovariance, CauchyKernel, CompositeCovariance, Dir
                       GenericMaternKernel, PolynomialKernel,
                       LaplacianKernel, LocalScalarKernel, MahalanobisKernel, MultiplicativeCovariance, PeriodicKernel,
                       RationalQuadraticKernel, RBFKernel, ScaledKernel, SEKernel, SVMKernelMatrix, TStudentKernel)
-from .models import AbstractGPRegressionModel, CudaGPRegression, GPRegression, MultGaussianPRV
+from .models import (AbstractGPRegressionModel, CudaGPRegression, GPBasisFuncRegression, GPRegression,
+                     MultGaussianPRV)
 from .stp import AbstractSTPRegressionModel, MultStudentsTPRV, STPRegression
 from .optimization import CoupledSimulatedAnnealing, GradBasedGlobalOptimizer, GridSearch, ModelTuner
 
@@ -21,7 +22,7 @@ __all__ = [
     "DiracKernel", "AdditiveCovariance", "MultiplicativeCovariance", "CompositeCovariance", "ScaledKernel",
     "SVMKernelMatrix",
     "CauchyKernel", "LaplacianKernel", "RationalQuadraticKernel", "TStudentKernel", "PolynomialKernel", "FBMKernel",
-    "GPRegression", "CudaGPRegression", "AbstractGPRegressionModel", "MultGaussianPRV",
+    "GPRegression", "CudaGPRegression", "GPBasisFuncRegression", "AbstractGPRegressionModel", "MultGaussianPRV",
     "STPRegression", "AbstractSTPRegressionModel", "MultStudentsTPRV",
     "GridSearch", "CoupledSimulatedAnnealing", "GradBasedGlobalOptimizer", "ModelTuner",
 ]

@@ -33,7 +33,7 @@ EXPORTS = [
     "dgp_energy_grad", "dgp_energy_batch", "dgp_fit", "dgp_model_destroy", "dgp_model_energy", "dgp_model_terms",
     "dgp_predict", "dgp_dist_unique_id", "dgp_dist_init", "dgp_dist_finalize", "dgp_dist_plan", "dgp_dist_energy",
     "dgp_measure_peaks", "dgp_launch_count", "dgp_outer_block", "dgp_time_phase", "dgp_test_gemm", "dgp_test_potrf",
-    "dgp_spec_grad_len",
+    "dgp_spec_grad_len", "dgp_data_set_basis", "dgp_model_set_test_basis",
 ]
 
 
@@ -101,6 +101,8 @@ def load_library() -> C.CDLL:
         "dgp_test_gemm": (i32, [vp, i32, i32, i64, i64, i64, f64, _dp, i64, _dp, i64, f64, _dp, i64, i32, _dp]),
         "dgp_test_potrf": (i32, [vp, i64, _dp, i64, _dp, _dp, _dp, _dp]),
         "dgp_spec_grad_len": (i32, [sp]),
+        "dgp_data_set_basis": (i32, [vp, vp, _dp, i32]),
+        "dgp_model_set_test_basis": (i32, [vp, vp, _dp, i64, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -247,6 +249,19 @@ class Context:
         q, l = C.c_double(), C.c_double()
         self.check(self.lib.dgp_model_terms(self.h, h, C.cast(C.byref(q), _dp), C.cast(C.byref(l), _dp)))
         return q.value, l.value
+
+    def data_set_basis(self, data, psi):
+        """GPBasisFuncRegressionModel: psi is n x m (row i = lowB basisFunc(x_i)); None removes the term."""
+        if psi is None:
+            self.check(self.lib.dgp_data_set_basis(self.h, data, None, 0))
+            return
+        psi = _f64(psi)
+        self.check(self.lib.dgp_data_set_basis(self.h, data, _ptr(psi), int(psi.shape[1])))
+
+    def model_set_test_basis(self, model, psi_s):
+        psi_s = _f64(psi_s)
+        self.check(self.lib.dgp_model_set_test_basis(self.h, model, _ptr(psi_s), int(psi_s.shape[0]),
+                                                     int(psi_s.shape[1])))
 
     def energy_grad(self, data, spec):
         s, keep = spec

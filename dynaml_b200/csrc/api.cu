@@ -378,6 +378,34 @@ int32_t slot_streams(Ctx *ctx, int slot, cudaStream_t *S, cudaStream_t *P) {
   return DGP_OK;
 }
 
+// C += Psi1 Psi2'  (rank-basis_mp DMMA update; GPBasisFuncRegressionModel.scala:91-109)
+int32_t add_basis_term(Ctx *ctx, cudaStream_t S, const double *psi1, int64_t ld1, const double *psi2, int64_t ld2,
+                       int mp, double *Cm, int64_t ldc, int64_t rows_p, int64_t cols_p, bool lower) {
+  GemmArgs g;
+  g.A = psi1;  g.lda = ld1;  g.a_kmajor = 0;
+  g.B = psi2;  g.ldb = ld2;  g.b_kmajor = 0;
+  g.C = Cm;  g.ldc = ldc;
+  g.M = (int)rows_p;  g.N = (int)cols_p;  g.K = mp;
+  g.alpha = 1.0;  g.beta = 1.0;  g.lower_only = lower ? 1 : 0;
+  return gemm(ctx, S, g);
+}
+
+// Upload row-major n x m features as column-major np x mp, zero padded.
+int32_t upload_basis(Ctx *ctx, const double *psi, int64_t n, int64_t np, int m, int mp, double **out) {
+  std::vector<double> h((size_t)np * mp, 0.0);
+  for (int64_t i = 0; i < n; ++i)
+    for (int c = 0; c < m; ++c) h[(size_t)c * np + i] = psi[(size_t)i * m + c];
+  double *d = nullptr;
+  if (cudaMalloc(&d, h.size() * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    return ctx->fail(DGP_ERR_OOM, "basis features: device allocation failed");
+  }
+  cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  DGP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = d;
+  return DGP_OK;
+}
+
 // Enqueue one energy (and optionally gradient-moment) evaluation on the streams and workspace of
 // `slot`.  Results land in d_scal[0] = r' K^-1 r, d_scal[1] = sum log L_ii, d_scal[2..] = gradient
 // moments; *d_info != 0 on a failed pivot.  Nothing here synchronises with the host.
@@ -409,6 +437,7 @@ int32_t enqueue_eval(Ctx *ctx, int slot, const Data *D, const Spec &sp, bool wan
   a.use_gram = pick_gram(ctx, sp, cp, D->dp, D->d, D->max_sq_norm);
   a.nodup = points_stay_distinct(D->has_dup, sp, D->d);
   DGP_TRY(assemble(ctx, S, cp, a));
+  if (D->psi) DGP_TRY(add_basis_term(ctx, S, D->psi, np, D->psi, np, D->basis_mp, K, np, np, np, true));
   tick(ctx, slot, 1);
   DGP_CUDA_OK(ctx, cudaMemsetAsync(d_info, 0, sizeof(int), S));
   DGP_TRY(potrf_blocked_on(ctx, S, ctx->lookahead ? P : S, K, np, np, inv, d_info, nm[4]));
@@ -474,6 +503,10 @@ struct Model {
   double energy = 0.0, quad = 0.0, logdet_half = 0.0;
   std::vector<double> center;  // the training set's column means (test points are shifted alike)
   double max_sq_norm = 0.0;
+  // GPBasisFuncRegressionModel: own copy of the training features, and the test features of the next predict
+  double *psi = nullptr, *psi_s = nullptr;
+  int basis_m = 0, basis_mp = 0;
+  int64_t psi_s_n = 0;
 };
 
 }  // namespace dgp
@@ -637,8 +670,24 @@ int32_t dgp_data_destroy(dgp_ctx *ctx, dgp_data *D) {
   }
   cudaFree(D->X);
   cudaFree(D->Xraw);
+  cudaFree(D->psi);
   cudaFree(D->r);
   delete D;
+  return DGP_OK;
+}
+
+int32_t dgp_data_set_basis(dgp_ctx *ctx, dgp_data *D, const double *psi, int32_t m) {
+  if (!ctx || !D || m < 0 || (m > 0 && !psi)) return DGP_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(D->psi);
+  D->psi = nullptr;
+  D->basis_m = D->basis_mp = 0;
+  if (m == 0) return DGP_OK;
+  const int mp = (int)round_up(m, 32);
+  DGP_TRY(upload_basis(ctx, psi, D->N, D->Np, m, mp, &D->psi));
+  D->basis_m = m;
+  D->basis_mp = mp;
   return DGP_OK;
 }
 
@@ -756,6 +805,8 @@ int32_t dgp_model_destroy(dgp_ctx *ctx, dgp_model *m) {
   }
   if (m->Xk != m->X) cudaFree(m->Xk);
   cudaFree(m->X);
+  cudaFree(m->psi);
+  cudaFree(m->psi_s);
   cudaFree(m->L);
   cudaFree(m->inv);
   cudaFree(m->alpha);
@@ -812,6 +863,18 @@ int32_t dgp_fit(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *spec, dg
   a.nodup = points_stay_distinct(D->has_dup, sp, D->d);
   int32_t st = assemble(ctx, S, cp, a);
   if (st != DGP_OK) return bail(st);
+  if (D->psi) {
+    ok = cudaMalloc(&m->psi, (size_t)np * D->basis_mp * sizeof(double)) == cudaSuccess;
+    if (!ok) {
+      cudaGetLastError();
+      return bail(ctx->fail(DGP_ERR_OOM, "fit: device allocation failed"));
+    }
+    cudaMemcpyAsync(m->psi, D->psi, (size_t)np * D->basis_mp * sizeof(double), cudaMemcpyDeviceToDevice, S);
+    m->basis_m = D->basis_m;
+    m->basis_mp = D->basis_mp;
+    st = add_basis_term(ctx, S, m->psi, np, m->psi, np, m->basis_mp, m->L, np, np, np, true);
+    if (st != DGP_OK) return bail(st);
+  }
   tick(ctx, 0, 1);
   cudaMemsetAsync(ctx->d_info, 0, sizeof(int), S);
   st = potrf_blocked(ctx, m->L, np, np, m->inv, ctx->d_info);
@@ -851,6 +914,20 @@ int32_t dgp_model_terms(dgp_ctx *ctx, const dgp_model *m, double *quad, double *
   return DGP_OK;
 }
 
+int32_t dgp_model_set_test_basis(dgp_ctx *ctx, dgp_model *m, const double *psi_s, int64_t n_test, int32_t mb) {
+  if (!ctx || !m || !psi_s || n_test <= 0) return DGP_ERR_ARG;
+  if (!m->psi || mb != m->basis_m)
+    return ctx->fail(DGP_ERR_SHAPE, "test basis: the model was fitted with %d basis functions, got %d", m->basis_m, mb);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(m->psi_s);
+  m->psi_s = nullptr;
+  m->psi_s_n = 0;
+  DGP_TRY(upload_basis(ctx, psi_s, n_test, round_up(n_test, TILE), mb, m->basis_mp, &m->psi_s));
+  m->psi_s_n = n_test;
+  return DGP_OK;
+}
+
 int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t M, int32_t x_layout,
                     const double *mean_s, double *mean, double *cov, int64_t ldcov, double *lo, double *hi,
                     double sigma) {
@@ -863,6 +940,9 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
   const int dp = m->dp;
   const bool need_cov = cov != nullptr || lo != nullptr;
 
+  if (m->psi && (!m->psi_s || m->psi_s_n != M))
+    return ctx->fail(DGP_ERR_ARG, "predict: the model has basis functions; call dgp_model_set_test_basis for these "
+                                  "%lld test points first", (long long)M);
   std::vector<double> hx;
   double nmax = pack_points(Xs, M, m->d, x_layout, mp, dp, hx, m->center.data());
   if (m->max_sq_norm > nmax) nmax = m->max_sq_norm;
@@ -889,6 +969,7 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
     a.out = Ks;  a.ld = np;
     a.use_gram = gram;
     DGP_TRY(assemble(ctx, S, cpx, a));
+    if (m->psi) DGP_TRY(add_basis_term(ctx, S, m->psi, np, m->psi_s, mp, m->basis_mp, Ks, np, np, mp, false));
   }
   tick(ctx, 0, 1);
   // mean = m(X*) + K*' alpha   (:463)
@@ -905,6 +986,7 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
     a.out = C;  a.ld = mp;  a.symmetric = 1;  a.lower_only = 1;
     a.use_gram = gram;
     DGP_TRY(assemble(ctx, S, cpx, a));
+    if (m->psi) DGP_TRY(add_basis_term(ctx, S, m->psi_s, mp, m->psi_s, mp, m->basis_mp, C, mp, mp, mp, true));
     // V = L^-1 K*  (blocked forward substitution on tensor cores, in place in Ks)
     DGP_TRY(trsm_lower_fwd(ctx, S, m->L, np, m->inv, np, Ks, np, mp, np >= 4096 ? 512 : 256));
     tick(ctx, 0, 3);

@@ -91,6 +91,9 @@ struct Data {
   std::vector<double> center;  // d column means of the original inputs
   double max_sq_norm = 0.0;    // max_i |x_i - center|^2
   bool has_dup = true;         // two training points coincide (decides where Dirac noise can land)
+  // GPBasisFuncRegressionModel: Psi, column-major Np x basis_mp (zero padded), or nullptr
+  double *psi = nullptr;
+  int basis_m = 0, basis_mp = 0;
 };
 
 struct Composite;  // covfn.cuh

@@ -130,7 +130,15 @@ class CudaGPRegression:
             y = np.asarray([p[1] for p in pts], dtype=np.float64)
             m = np.asarray([self.mean(x) for x in X], dtype=np.float64)
             self._data = self.ctx.data_create(X, y, m)
+            self._attach_basis(self._data, X)
         return self._data
+
+    # hooks of GPBasisFuncRegression (explicit basis functions); no-ops for the plain model
+    def _attach_basis(self, handle, X: np.ndarray) -> None:
+        pass
+
+    def _attach_test_basis(self, model, Xs: np.ndarray) -> None:
+        pass
 
     def _spec(self):
         return self.covariance._spec(noise=self.noiseModel.state["noiseLevel"])
@@ -187,6 +195,7 @@ class CudaGPRegression:
         m = np.asarray([self.mean(x) for x in X], dtype=np.float64)
         if getattr(self, "_train_data", None) is None:
             self._train_data = self.ctx.data_create(X, y, m)
+            self._attach_basis(self._train_data, X)
         return self._train_data
 
     # ---- prediction (:304-393) --------------------------------------------------------------
@@ -200,6 +209,7 @@ class CudaGPRegression:
         ms = np.asarray([self.mean(x) for x in Xs], dtype=np.float64)
         model, temp = self._fitted()
         try:
+            self._attach_test_basis(model, Xs)
             mean, cov, _, _ = self.ctx.predict(model, Xs, ms, want_cov=True, want_bars=False)
         finally:
             if temp:
@@ -209,6 +219,7 @@ class CudaGPRegression:
             # evaluated lazily, like `root` in BlockedMultiVariateGaussian (:32)
             m2, t2 = self._fitted()
             try:
+                self._attach_test_basis(m2, Xs)
                 _, _, lo, hi = self.ctx.predict(m2, Xs, ms, want_cov=False, want_bars=True, sigma=s)
             finally:
                 if t2:
@@ -222,6 +233,7 @@ class CudaGPRegression:
         ms = np.asarray([self.mean(x) for x in Xs], dtype=np.float64)
         model, temp = self._fitted()
         try:
+            self._attach_test_basis(model, Xs)
             mean, _, lo, hi = self.ctx.predict(model, Xs, ms, want_cov=False, want_bars=True, sigma=float(sigma))
         finally:
             if temp:
@@ -238,6 +250,67 @@ class CudaGPRegression:
 
 
 GPRegression = CudaGPRegression
+
+
+class GPBasisFuncRegression(CudaGPRegression):
+    """GPBasisFuncRegressionModel (CORE/models/gp/GPBasisFuncRegressionModel.scala:70-109): explicit basis functions
+    parameterise the trend, with a Gaussian prior N(b, covB) on their coefficients.
+
+    mean(x) = basisFunc(x).b, and the training / cross / test kernel matrices gain
+    feature_map_cov(x, y) = (lowB basisFunc(x)).(lowB basisFunc(y)), lowB = cholesky(covB) -- written as in the
+    reference (which therefore adds phi' lowB' lowB phi).  `basisFunc` is an arbitrary host function, so the features
+    are evaluated here and handed to the device, which applies them as a rank-m tensor-core update of K.
+    gradEnergy is inherited from AbstractGPRegressionModel, which differentiates covariance + noiseModel *without*
+    the feature-map term (:196-253); grad_with_basis=True uses the full training matrix instead."""
+
+    def __init__(self, cov, noise, trainingdata, basisFunc: Callable[[np.ndarray], Sequence[float]],
+                 basis_param_prior: Tuple[Sequence[float], Sequence[Sequence[float]]], ctx=None,
+                 grad_with_basis: bool = False):
+        b, covB = basis_param_prior
+        self.b = np.asarray(b, dtype=np.float64).ravel()
+        self.covB = np.asarray(covB, dtype=np.float64)
+        if self.covB.shape != (self.b.size, self.b.size):
+            raise ValueError("basis_param_prior: covariance must be m x m for m trend coefficients")
+        self.lowB = np.linalg.cholesky(self.covB)
+        self.basisFunc = basisFunc
+        self.grad_with_basis = grad_with_basis
+        self._plain = None
+        super().__init__(cov, noise, trainingdata,
+                         meanFunc=lambda x: float(np.dot(np.asarray(basisFunc(x), dtype=np.float64), self.b)), ctx=ctx)
+
+    def _features(self, X: np.ndarray) -> np.ndarray:
+        phi = np.asarray([np.asarray(self.basisFunc(x), dtype=np.float64).ravel() for x in X])
+        if phi.ndim != 2 or phi.shape[1] != self.b.size:
+            raise ValueError("basisFunc must return as many features as there are trend coefficients")
+        return np.ascontiguousarray(phi @ self.lowB.T)  # row i = (lowB phi(x_i))'
+
+    def _attach_basis(self, handle, X):
+        self.ctx.data_set_basis(handle, self._features(X))
+
+    def _attach_test_basis(self, model, Xs):
+        self.ctx.model_set_test_basis(model, self._features(Xs))
+
+    def gradEnergy(self, h):
+        if self.grad_with_basis:
+            return super().gradEnergy(h)
+        # reference behaviour: a second resident copy of the data without the feature-map term
+        if self._plain is None:
+            pts = self.g + self.validationSet
+            X = _as_points([p[0] for p in pts])
+            y = np.asarray([p[1] for p in pts], dtype=np.float64)
+            m = np.asarray([self.mean(x) for x in X], dtype=np.float64)
+            self._plain = self.ctx.data_create(X, y, m)
+        full, self._data = self._data, self._plain
+        try:
+            return super().gradEnergy(h)
+        finally:
+            self._data = full
+
+    def _drop_data(self):
+        super()._drop_data()
+        if getattr(self, "_plain", None) is not None:
+            self.ctx.data_destroy(self._plain)
+            self._plain = None
 
 
 def AbstractGPRegressionModel(cov, noise, meanFunc=None):

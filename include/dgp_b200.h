@@ -163,6 +163,16 @@ int32_t dgp_energy(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *sp
 int32_t dgp_energy_terms(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec, double *quad,
                          double *logdet_half);
 
+/* ---- explicit basis functions (GPBasisFuncRegressionModel,
+        CORE/models/gp/GPBasisFuncRegressionModel.scala:70-109) ------------------------------------
+   The model adds feature_map_cov(x, y) = psi(x).psi(y), psi(x) = chol(covB) * basisFunc(x), to the training,
+   cross and test kernel matrices (getTrainKernelMatrix / getCrossKernelMatrix / getTestKernelMatrix overrides).
+   The host evaluates basisFunc (an arbitrary user function) and hands over Psi, row-major n x m; the device
+   adds Psi Psi' as a rank-m DMMA update after the assembly.  dgp_data_set_basis(m = 0) removes it.
+   A model fitted from such data needs the test points' features before every dgp_predict.            */
+int32_t dgp_data_set_basis(dgp_ctx *ctx, dgp_data *data, const double *psi, int32_t m);
+int32_t dgp_model_set_test_basis(dgp_ctx *ctx, dgp_model *model, const double *psi_s, int64_t n_test, int32_t m);
+
 /* ---- gradEnergy (AbstractGPRegressionModel.scala:196-267) -----------------------------------
    g[i] = tr( (alpha alpha' - K^-1) dK/dtheta_i ), i over spec->hyp in order, then g[n_hyp] for
    the noise level: n_hyp + 1 values (entries with no reference derivative, e.g. Matern "p",

@@ -291,6 +291,31 @@ class Prod(_Pair):
         return out
 
 
+class WithFeatureMap:
+    """GPBasisFuncRegressionModel's kernel matrices (GPBasisFuncRegressionModel.scala:83-109):
+    covariance.evaluate + feature_map_cov.evaluate with feature_map_cov(x, y) = (lowB phi(x)).(lowB phi(y)),
+    lowB = cholesky(covB).  Hyper-parameters and gradients are those of the wrapped covariance."""
+
+    def __init__(self, base, basis_func, cov_b: np.ndarray):
+        self.base, self.basis_func = base, basis_func
+        self.low_b = np.linalg.cholesky(np.asarray(cov_b, dtype=float))
+
+    def _psi(self, X):
+        return np.asarray([np.asarray(self.basis_func(x), dtype=float) for x in X]) @ self.low_b.T
+
+    def names(self, d: int | None = None):
+        return self.base.names(d)
+
+    def effective(self, blocked: Sequence[str] = ()):
+        return self.base.effective(blocked)
+
+    def value(self, X, Y):
+        return self.base.value(X, Y) + self._psi(X) @ self._psi(Y).T
+
+    def grads(self, X, Y):
+        return self.base.grads(X, Y)
+
+
 class Scaled:
     """kernel * c, c > 0 (LocalScalarKernel.scala:68-91): same hyper-parameters, value and gradient times c."""
 
