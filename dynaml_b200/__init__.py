@@ -7,14 +7,17 @@ library or an sm_100 device is missing (there is no CPU fallback).
 """
 from . import _capi
 from ._capi import Context, DgpError, NotPositiveDefinite, default_context
-from .kernels import (AdditiveCovariance, CauchyKernel, CompositeCovariance, DiracKernel, FBMKernel,
+from .kernels import (AdditiveCovariance, CauchyKernel, CompositeCovariance, DecomposableCovariance, DiracKernel,
+                      FBMKernel,
                       GenericMaternKernel, PolynomialKernel,
                       LaplacianKernel, LocalScalarKernel, MahalanobisKernel, MultiplicativeCovariance, PeriodicKernel,
                       RationalQuadraticKernel, RBFKernel, ScaledKernel, SEKernel, SVMKernelMatrix, TStudentKernel)
 from .models import (AbstractGPRegressionModel, CudaGPRegression, GPBasisFuncRegression, GPRegression,
                      MultGaussianPRV)
 from .stp import AbstractSTPRegressionModel, MultStudentsTPRV, STPRegression
-from .optimization import CoupledSimulatedAnnealing, GradBasedGlobalOptimizer, GridSearch, ModelTuner
+from .optimization import (CoupledSimulatedAnnealing, GradBasedGlobalOptimizer, GridSearch, ModelTuner,
+                           ProbGPCommMachine)
+from .mcmc import AdaptiveHyperParameterMCMC, HyperParameterMCMC, HyperParameterSCAM
 
 __all__ = [
     "Context", "DgpError", "NotPositiveDefinite", "default_context",
@@ -24,5 +27,6 @@ __all__ = [
     "CauchyKernel", "LaplacianKernel", "RationalQuadraticKernel", "TStudentKernel", "PolynomialKernel", "FBMKernel",
     "GPRegression", "CudaGPRegression", "GPBasisFuncRegression", "AbstractGPRegressionModel", "MultGaussianPRV",
     "STPRegression", "AbstractSTPRegressionModel", "MultStudentsTPRV",
-    "GridSearch", "CoupledSimulatedAnnealing", "GradBasedGlobalOptimizer", "ModelTuner",
+    "GridSearch", "CoupledSimulatedAnnealing", "GradBasedGlobalOptimizer", "ModelTuner", "ProbGPCommMachine",
+    "AdaptiveHyperParameterMCMC", "HyperParameterMCMC", "HyperParameterSCAM", "DecomposableCovariance",
 ]

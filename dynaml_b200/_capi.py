@@ -127,7 +127,7 @@ def make_spec(kind: int, hyp, noise: float = 0.0, grad_mode: int = GRAD_REFERENC
 
 
 KERNEL_COMPOSITE, KERNEL_POLYNOMIAL, KERNEL_FBM = 10, 11, 12
-MAX_FACTORS, MAX_TERMS = 6, 16
+MAX_FACTORS, MAX_TERMS = 32, 64
 
 
 def make_composite_spec(factors, terms, noise: float = 0.0):

@@ -174,10 +174,8 @@ __device__ __forceinline__ double metric_of(const CompositeDev &c, const PairMet
 
 __device__ __forceinline__ double composite_entry(const CompositeDev &c, const PairMetrics &m) {
   double v[MAXF];
-#pragma unroll
-  for (int f = 0; f < MAXF; ++f) {
-    if (f >= c.F) v[f] = 1.0;
-    else if (kind_is_inner_product(c.cp[f].kind)) v[f] = cov_value_ip(c.cp[f], m.g);
+  for (int f = 0; f < c.F; ++f) {
+    if (kind_is_inner_product(c.cp[f].kind)) v[f] = cov_value_ip(c.cp[f], m.g);
     else v[f] = cov_value_rt(c.cp[f], metric_of(c, m, f));
   }
   return composite_combine(c, v);

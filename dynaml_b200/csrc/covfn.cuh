@@ -125,32 +125,42 @@ __device__ __forceinline__ double ipow_small(double v, int e) {
 }
 
 // Value of the expression from the base-kernel values v[0..F).
-__device__ __forceinline__ double composite_combine(const CompositeDev &c, const double (&v)[MAXF]) {
+__device__ __forceinline__ double composite_combine(const CompositeDev &c, const double *v) {
   double k = 0.0;
   for (int t = 0; t < c.T; ++t) {
     double prod = c.coef[t];
-#pragma unroll
-    for (int f = 0; f < MAXF; ++f)
-      if (f < c.F) prod *= ipow_small(v[f], c.expo[t][f]);
+    for (int f = 0; f < c.F; ++f) {
+      const int e = c.expo[t][f];
+      if (e) prod *= ipow_small(v[f], e);
+    }
     k += prod;
   }
   return k;
 }
 
-// d k / d v_f : the factor every derivative of base kernel f is multiplied by
+// cof[f] = d k / d v_f for every base kernel: the factor each derivative of base kernel f is multiplied by
 // (MultiplicativeCovariance.scala:68-77; `* c` scales value and gradient alike, LocalScalarKernel.scala:81-85).
-__device__ __forceinline__ double composite_cofactor(const CompositeDev &c, const double (&v)[MAXF], int f) {
-  double out = 0.0;
+// One pass per term with running prefix products, so the cost is O(T F) per pair and no division by v_f.
+__device__ __forceinline__ void composite_cofactors(const CompositeDev &c, const double *v, double *cof) {
+  for (int f = 0; f < c.F; ++f) cof[f] = 0.0;
   for (int t = 0; t < c.T; ++t) {
-    const int e = c.expo[t][f];
-    if (e == 0) continue;
-    double prod = c.coef[t] * (double)e;
-#pragma unroll
-    for (int g = 0; g < MAXF; ++g)
-      if (g < c.F) prod *= ipow_small(v[g], g == f ? e - 1 : c.expo[t][g]);
-    out += prod;
+    // suffix[f] = prod_{g >= f} v_g^e_g is rebuilt backwards into cof-sized scratch held in registers/local
+    double suffix = 1.0;
+    double tmp[MAXF];
+    for (int f = c.F - 1; f >= 0; --f) {
+      tmp[f] = suffix;  // product over g > f
+      const int e = c.expo[t][f];
+      if (e) suffix *= ipow_small(v[f], e);
+    }
+    double prefix = c.coef[t];
+    for (int f = 0; f < c.F; ++f) {
+      const int e = c.expo[t][f];
+      if (e) {
+        cof[f] = fma((double)e * ipow_small(v[f], e - 1), prefix * tmp[f], cof[f]);
+        prefix *= ipow_small(v[f], e);
+      }
+    }
   }
-  return out;
 }
 
 // Host: fold a Spec into CovParams.  `noise` < 0 is legal (the reference takes abs()).

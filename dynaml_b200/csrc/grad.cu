@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(GTHREADS) grad_trace_generic_kernel(CovParams 
 // MultiplicativeCovariance.scala:68-77): every base kernel accumulates its own moments exactly as in the
 // single-kernel pass, with the pair weight M_ij multiplied by the cofactor d k / d v_f.  Moments of
 // factor f start at moment_off[f]; the last moment is the noise one, sum M_ij 1[|x_i - x_j| == 0].
-constexpr int MAX_COMPOSITE_MOMENTS = 48;
+constexpr int MAX_COMPOSITE_MOMENTS = 128;
 
 __device__ __forceinline__ void accumulate_rt(int mode, const CovParams &cp, double m, double dist, double plain2,
                                               double *s) {
@@ -366,23 +366,21 @@ __device__ __forceinline__ void composite_pair(const CompositeDev &c, const Comp
       if (k < MAX_ARD_DIM) ard[a] = fma(c.w[a][k], e2, ard[a]);
   }
   const double r2 = q.r2;
-  double v[MAXF], dist[MAXF];
-#pragma unroll
-  for (int f = 0; f < MAXF; ++f) {
-    const int id = (f < c.F) ? c.metric[f] : 0;
-    dist[f] = id == 0 ? q.r2 : (id == 1 ? q.l1 : ard[id - 2]);
-    if (f >= c.F) v[f] = 1.0;
-    else if (kind_is_inner_product(c.cp[f].kind)) v[f] = cov_value_ip(c.cp[f], q);
-    else v[f] = cov_value_rt(c.cp[f], dist[f]);
+  double v[MAXF], cof[MAXF];
+  for (int f = 0; f < c.F; ++f) {
+    const int id = c.metric[f];
+    const double dist = id == 0 ? q.r2 : (id == 1 ? q.l1 : ard[id - 2]);
+    v[f] = kind_is_inner_product(c.cp[f].kind) ? cov_value_ip(c.cp[f], q) : cov_value_rt(c.cp[f], dist);
   }
-#pragma unroll
-  for (int f = 0; f < MAXF; ++f) {
-    if (f >= c.F) continue;
-    const double w = m * composite_cofactor(c, v, f);
+  composite_cofactors(c, v, cof);
+  for (int f = 0; f < c.F; ++f) {
+    const int id = c.metric[f];
+    const double dist = id == 0 ? q.r2 : (id == 1 ? q.l1 : ard[id - 2]);
+    const double w = m * cof[f];
     double *sf = s + c.moment_off[f];
     if (c.ard_exact[f]) {
       // exact dk/db_c = k (x_c - y_c)^2 / b_c^3: one moment per dimension (cf. M_ARD_EXACT)
-      const double e = exp(-dist[f] * c.cp[f].c1);
+      const double e = exp(-dist * c.cp[f].c1);
       sf[0] = fma(w, e, sf[0]);
       const double we = w * e;
       for (int k = 0; k < dp; ++k) {
@@ -394,7 +392,7 @@ __device__ __forceinline__ void composite_pair(const CompositeDev &c, const Comp
     } else if (md.mode[f] == M_POLY) {
       // no derivative in the reference (stub returning 0.0 per hyper-parameter)
     } else {
-      accumulate_rt(md.mode[f], c.cp[f], w, dist[f], r2, sf);
+      accumulate_rt(md.mode[f], c.cp[f], w, dist, r2, sf);
     }
   }
   if (r2 == 0.0) s[c.moment_off[c.F]] += m;
@@ -422,7 +420,7 @@ __global__ void __launch_bounds__(GTHREADS) grad_trace_composite_kernel(Composit
   const double al0 = a.alpha[r0], al1 = a.alpha[r0 + 1];
   __syncthreads();
   double s[MAX_COMPOSITE_MOMENTS];
-  for (int q = 0; q < MAX_COMPOSITE_MOMENTS; ++q) s[q] = 0.0;
+  for (int q = 0; q < NS; ++q) s[q] = 0.0;
   const double *kinv = a.Kinv + r0 + n0 * a.ld;
   for (int cc = 0; cc < GT / 4; ++cc) {
     const int j = ty + 4 * cc;

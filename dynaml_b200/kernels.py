@@ -486,3 +486,66 @@ class ScaledKernel(LocalScalarKernel):
         factors = [(k._device_kind(), k.grad_mode, k._device_hyp(c)) for k, c in zip(leaves, cfgs)]
         terms = [(c, [m.get(f, 0) for f in range(len(leaves))]) for c, m in self._terms()]
         return _capi.make_composite_spec(factors, terms, noise)
+
+
+class DecomposableCovariance(LocalScalarKernel):
+    """DecomposableCovariance(kernels*)(replication encoder, WeightedSumReducer(weights)) as ProbGPCommMachine builds it
+    (CORE/kernels/DecomposableCovariance.scala:28-120, CORE/optimization/ProbGPCommMachine.scala:92-121):
+    k(x, y) = sum_i weights_i * k_i(x, y) over the same inputs, hyper-parameters "<Class@hash>/<name>" per member.
+    (The reference pairs weights with kernels in the iteration order of an immutable Map keyed by the ids, i.e. in
+    hash order for more than four members; the intended pairing -- position i with weight i -- is used here.)"""
+
+    def __init__(self, kernels: Sequence[LocalScalarKernel], weights: Sequence[float] | None = None):
+        super().__init__()
+        self.kernels = list(kernels)
+        if not self.kernels:
+            raise ValueError("DecomposableCovariance needs at least one kernel")
+        self.weights = [1.0] * len(self.kernels) if weights is None else [float(w) for w in weights]
+        if len(self.weights) != len(self.kernels):
+            raise ValueError("one weight per kernel")
+        self.ids = [str(k).split(".")[-1] for k in self.kernels]
+        self.hyper_parameters = [f"{i}/{h}" for i, k in zip(self.ids, self.kernels) for h in k.hyper_parameters]
+        self.blocked_hyper_parameters = [f"{i}/{h}" for i, k in zip(self.ids, self.kernels)
+                                         for h in k.blocked_hyper_parameters]
+        self.state = {f"{i}/{h}": v for i, k in zip(self.ids, self.kernels) for h, v in k.state.items()}
+
+    def setHyperParameters(self, h: Dict[str, float]):
+        assert all(k in h for k in self.effective_hyper_parameters), \
+            "All hyper parameters must be contained in the arguments"
+        for i, k in zip(self.ids, self.kernels):
+            sub = {key.split("/", 1)[1]: v for key, v in h.items() if key.split("/")[0] == i and "/" in key}
+            if sub:
+                k.setHyperParameters(sub)
+        for i, k in zip(self.ids, self.kernels):
+            for name, v in k.state.items():
+                self.state[f"{i}/{name}"] = v
+        return self
+
+    def _device_kind(self) -> int:
+        for leaf in self._leaves():
+            leaf._device_kind()
+        return _capi.KERNEL_COMPOSITE
+
+    def _leaves(self):
+        return [leaf for k in self.kernels for leaf in k._leaves()]
+
+    def _leaf_configs(self, config):
+        out = []
+        for i, k in zip(self.ids, self.kernels):
+            sub = {key.split("/", 1)[1]: v for key, v in config.items() if key.split("/")[0] == i and "/" in key}
+            out += k._leaf_configs(sub)
+        return out
+
+    def _terms(self):
+        out, off = [], 0
+        for w, k in zip(self.weights, self.kernels):
+            out += [(w * c, {f + off: e for f, e in m.items()}) for c, m in k._terms()]
+            off += len(k._leaves())
+        return out
+
+    def _spec(self, config=None, noise: float = 0.0):
+        cfg = self.state if config is None else config
+        leaves, cfgs = self._leaves(), self._leaf_configs(cfg)
+        factors = [(k._device_kind(), k.grad_mode, k._device_hyp(c)) for k, c in zip(leaves, cfgs)]
+        terms = [(c, [m.get(f, 0) for f in range(len(leaves))]) for c, m in self._terms()]
+        return _capi.make_composite_spec(factors, terms, noise)

@@ -235,6 +235,95 @@ class CoupledSimulatedAnnealing(AbstractCSA):
         return self.system, best
 
 
+class ProbGPCommMachine(CoupledSimulatedAnnealing):
+    """Build a GP committee from the energy landscape (CORE/optimization/ProbGPCommMachine.scala:36-229): every
+    configuration of the landscape becomes a member with weight w_i; the committee is one GP with kernel
+    sum_i w_i^2 k_i, noise sum_i w_i^2 noise_i and mean (sum_i w_i) m(x).  On the device the committee kernel is a
+    DGP_KERNEL_COMPOSITE of the members (at most DGP_MAX_FACTORS base kernels)."""
+
+    def __init__(self, model, rng: np.random.Generator | None = None):
+        super().__init__(model, rng)
+        self.policy = "CSA"
+        self.baselinePolicy = "max"
+
+    @property
+    def _policy(self) -> str:
+        return self.policy
+
+    def setPolicy(self, p: str):
+        self.policy = "CSA" if p in ("CSA", "Coupled Simulated Annealing") else "GS"
+        return self
+
+    def setBaseLinePolicy(self, p: str):
+        if p in ("avg", "mean", "average"):
+            self.baselinePolicy = "mean"
+        elif p in ("min", "max"):
+            self.baselinePolicy = p
+        else:
+            self.baselinePolicy = "mean"
+        return self
+
+    @staticmethod
+    def calculateModelWeights(energyLandscape: Sequence[Tuple[float, Config]]) -> List[Tuple[float, Config]]:
+        """:180-192: w_i = (1 - h_i / sum h) / (n - 1)."""
+        h = [e for e, _ in energyLandscape]
+        total = sum(h)
+        alpha = 1.0 if len(h) == 1 else 1.0 / (len(h) - 1)
+        return [((1.0 - e / total) * alpha, cfg) for e, cfg in energyLandscape]
+
+    @staticmethod
+    def calculateModelWeightsSigmoid(baselineMethod: str = "mean"):
+        """:194-227: w_i = 1 / sum_{r != i} exp(-(h_r - h_i) / baseline) -- row i of the mask matrix is zero, so that
+        term contributes exp(0) = 1 as well, exactly as `sum(exp((mask * h) *:* (-1/baseline)))` does."""
+        def weights(energyLandscape: Sequence[Tuple[float, Config]]) -> List[Tuple[float, Config]]:
+            h = [e for e, _ in energyLandscape]
+            if baselineMethod == "min":
+                baseline = min(h)
+            elif baselineMethod == "max":
+                baseline = max(h)
+            else:
+                baseline = sum(h) / len(h)
+            out = []
+            for i, (_, cfg) in enumerate(energyLandscape):
+                tot = sum(math.exp((0.0 if r == i else h[r] - h[i]) * (-1.0 / baseline)) for r in range(len(h)))
+                out.append((1.0 / tot, cfg))
+            return out
+        return weights
+
+    def optimize(self, initialConfig: Config, options=None):
+        import copy
+        from .kernels import DecomposableCovariance, DiracKernel
+        from .models import CudaGPRegression
+        options = options or {}
+        system = self.system
+        blocked = list(system.covariance.blocked_hyper_parameters) + list(system.noiseModel.blocked_hyper_parameters)
+        kernelParams, noiseParams = list(system.covariance.hyper_parameters), list(system.noiseModel.hyper_parameters)
+        blockedState = {k: v for k, v in system._current_state.items() if k in blocked}
+        if self.policy == "CSA":
+            landscape = self.performCSA(initialConfig, options)
+        else:
+            landscape = self.getEnergyLandscape(initialConfig, options, self.meanFieldPrior)
+        weights = [(w, {**cfg, **blockedState})
+                   for w, cfg in self.calculateModelWeightsSigmoid(self.baselinePolicy)(landscape)]
+        kernels, noise_level, wsum = [], 0.0, 0.0
+        for w, conf in weights:
+            k = copy.deepcopy(system.covariance)   # covariance.asPipe(conf): a fresh kernel fixed at this configuration
+            k.setHyperParameters({h: conf[h] for h in k.effective_hyper_parameters if h in conf})
+            n = copy.deepcopy(system.noiseModel)
+            n.setHyperParameters({h: conf[h] for h in n.effective_hyper_parameters if h in conf})
+            kernels.append(k)
+            noise_level += w * w * abs(n.state["noiseLevel"])   # WeightedSumReducer(w^2) over Dirac terms
+            wsum += w
+        netKernel = DecomposableCovariance(kernels, [w * w for w, _ in weights])
+        netNoise = DiracKernel(noise_level)
+        base_mean = system.mean
+        committee = CudaGPRegression(netKernel, netNoise, system.g, lambda x: wsum * base_mean(x), ctx=system.ctx)
+        self.weights = weights
+        if options.get("persist") in ("true", "1"):
+            committee.persist(committee._current_state)
+        return committee, committee._current_state
+
+
 class GradBasedGlobalOptimizer(ModelTuner):
     """ML-II by plain gradient descent: h <- |h - step * g| (GradBasedGlobalOptimizer.scala:37-103).
     Note the reference descends along tr((aa' - K^-1) dK), which is -2 dE/dtheta."""

@@ -94,8 +94,8 @@ enum {
                               DGP_GRAD_EXACT gives the true one (1/2, and 0 ln 0 = 0)                  */
 };
 
-#define DGP_MAX_FACTORS 6
-#define DGP_MAX_TERMS 16
+#define DGP_MAX_FACTORS 32
+#define DGP_MAX_TERMS 64
 
 /* Gradient conventions for hyper-parameters whose reference derivative is defective. */
 enum {

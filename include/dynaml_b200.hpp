@@ -287,7 +287,7 @@ class CompositeCovariance : public LocalScalarKernel {
     leaves(lv);
     std::vector<Term> ts = terms();
     if (lv.empty() || lv.size() > DGP_MAX_FACTORS || ts.empty() || ts.size() > DGP_MAX_TERMS)
-      throw std::invalid_argument("a composite kernel takes 1..6 base kernels and 1..16 terms (no CPU fallback)");
+      throw std::invalid_argument("a composite kernel takes 1..32 base kernels and 1..64 terms (no CPU fallback)");
     Vec prog{(double)lv.size(), (double)ts.size()};
     for (const auto *k : lv) {
       Vec h = k->device_hyp();

@@ -134,7 +134,7 @@ def test_composite_batch_and_grid_search(ctx):
 
 
 def test_composite_limits_and_malformed_programs(ctx):
-    ks = [dg.RBFKernel(1.0 + 0.1 * i) for i in range(7)]
+    ks = [dg.RBFKernel(1.0 + 0.1 * i) for i in range(33)]
     big = ks[0]
     for k in ks[1:]:
         big = big + k

@@ -266,3 +266,101 @@ def test_gaussian_scaling_and_regression_metrics():
     m = wf.RegressionMetrics([(1.0, 1.5), (2.0, 1.0), (3.0, 3.5)])
     assert m.mae == pytest.approx((0.5 + 1.0 + 0.5) / 3) and m.rmse == pytest.approx(math.sqrt((0.25 + 1 + 0.25) / 3))
     assert m.Rsq == pytest.approx(1 - 1.5 / ((1.5 - 2) ** 2 + (1 - 2) ** 2 + (3.5 - 2) ** 2))
+
+
+# ---- consumers of `energy` ----------------------------------------------------------------
+class _QuadraticSystem:
+    """GloballyOptimizable stand-in: energy = 0.5 (h - mu)' P (h - mu), i.e. a Gaussian posterior N(mu, P^-1)."""
+
+    def __init__(self):
+        self.mu = np.array([1.5, 0.7])
+        self.P = np.array([[4.0, 1.0], [1.0, 9.0]])
+        self._current_state = {"a": 1.0, "b": 1.0}
+        self.calls = 0
+
+    def energy(self, h, options=None):
+        self.calls += 1
+        v = np.array([h["a"], h["b"]]) - self.mu
+        return 0.5 * float(v @ self.P @ v)
+
+
+class _FlatPrior:
+    def logPdf(self, x):
+        return 0.0
+
+
+def test_adaptive_mcmc_samples_the_posterior_and_follows_the_reference_formulas():
+    from dynaml_b200.mcmc import AdaptiveHyperParameterMCMC, HyperParameterMCMC, HyperParameterSCAM
+    sys_ = _QuadraticSystem()
+    prior = {"a": _FlatPrior(), "b": _FlatPrior()}
+    mc = AdaptiveHyperParameterMCMC(sys_, prior, burnIn=300, rng=np.random.default_rng(0))
+    draws = np.array([[s["a"], s["b"]] for s in mc.iid(3000)])
+    assert np.abs(draws.mean(axis=0) - sys_.mu).max() < 0.08
+    assert np.abs(np.cov(draws.T) - np.linalg.inv(sys_.P)).max() < 0.05
+    assert 0.0 < mc.sampleAcceptenceRate <= 1.0 and mc._count > 3300
+    # HyperParameterMCMC.scala:221-227 with the chain's own count / sigma
+    adj = mc.count / (mc.count - 1)
+    want = mc.sigma * ((1 - 0.05) * 2.38) ** 2 * adj / 2.0 + np.eye(2) * (0.1 * 0.05) ** 2 / 2.0
+    assert np.allclose(mc.getExplorationVar(), want, rtol=0, atol=0)
+    # :278-287 against a plain restatement
+    m, s, x = mc.mean.copy(), mc.sigma.copy(), np.array([0.3, -0.2])
+    mc.updateMoments(x)
+    mnew = m + (x - m) / (mc.count + 1)
+    assert np.allclose(mc.mean, mnew) and np.allclose(
+        mc.sigma, s + np.outer(m, m) - np.outer(mnew, mnew) + (np.outer(x, x) - s - np.outer(m, m)) / (mc.count + 1))
+    # the first 2 d proposals use eye * 0.01 / d
+    fresh = AdaptiveHyperParameterMCMC(_QuadraticSystem(), prior, burnIn=0, rng=np.random.default_rng(1))
+    assert np.array_equal(fresh.getExplorationVar(), np.eye(2) * 0.01 / 2.0)
+    assert fresh._previous_sample == {"a": 1.0, "b": 1.0} and np.array_equal(fresh.sigma, np.ones((2, 2)))
+    # SCAM: eye * 25 for count <= 10, then the scaled diagonal (:337-343)
+    scam = HyperParameterSCAM(_QuadraticSystem(), prior, burnIn=0, rng=np.random.default_rng(2))
+    assert np.array_equal(scam.getExplorationVar(), np.eye(2) * 25.0)
+    scam.iid(30)
+    adj = scam.count / (scam.count - 1)
+    assert np.allclose(scam.getExplorationVar(), np.diag((np.diag(scam.sigma) * adj + 0.05) * 2.4 * 2.4))
+
+    class _Proposal:          # vanilla MCMC draws candidates from a fixed random variable (:71-74)
+        def __init__(self, rng):
+            self.rng = rng
+
+        def draw(self):
+            return np.array([1.5, 0.7]) + 0.6 * self.rng.standard_normal(2)
+    van = HyperParameterMCMC(_QuadraticSystem(), prior, _Proposal(np.random.default_rng(3)), burnIn=50,
+                             rng=np.random.default_rng(4))
+    sig0 = van.sigma.copy()
+    van.iid(20)
+    assert np.array_equal(van.sigma, sig0)  # never adapted
+
+
+def test_committee_weights_match_the_mask_matrix_formula():
+    # ProbGPCommMachine.scala:194-227 restated with the explicit mask matrices
+    h = np.array([10.0, 12.5, 9.0, 30.0])
+    landscape = [(float(e), {"i": float(i)}) for i, e in enumerate(h)]
+    for method, baseline in (("mean", h.mean()), ("min", h.min()), ("max", h.max()), ("other", h.mean())):
+        want = []
+        for i in range(len(h)):
+            mask = np.zeros((len(h), len(h)))
+            for r in range(len(h)):
+                for s in range(len(h)):
+                    mask[r, s] = 0.0 if r == i else (-1.0 if s == i else (1.0 if r == s else 0.0))
+            want.append(1.0 / np.exp((mask @ h) * (-1.0 / baseline)).sum())
+        got = opt.ProbGPCommMachine.calculateModelWeightsSigmoid(method)(landscape)
+        assert np.allclose([w for w, _ in got], want, rtol=1e-15)
+        assert [c for _, c in got] == [c for _, c in landscape]
+    lin = opt.ProbGPCommMachine.calculateModelWeights(landscape)   # :180-192
+    assert np.allclose([w for w, _ in lin], (1.0 - h / h.sum()) / 3.0)
+    m = opt.ProbGPCommMachine.__new__(opt.ProbGPCommMachine)
+    m.policy, m.baselinePolicy = "CSA", "max"
+    assert m.setPolicy("GS")._policy == "GS" and m.setPolicy("Coupled Simulated Annealing")._policy == "CSA"
+    assert m.setBaseLinePolicy("average").baselinePolicy == "mean" and m.setBaseLinePolicy("zzz").baselinePolicy == "mean"
+
+
+def test_decomposable_covariance_naming_and_terms():
+    a, b = dg.SEKernel(1.0, 2.0), dg.RBFKernel(3.0)
+    k = dg.DecomposableCovariance([a, b], [0.25, 0.75])
+    ia, ib = str(a).split(".")[-1], str(b).split(".")[-1]
+    assert k.hyper_parameters == [f"{ia}/bandwidth", f"{ia}/amplitude", f"{ib}/bandwidth"]
+    assert k._terms() == [(0.25, {0: 1}), (0.75, {1: 1})]
+    k.setHyperParameters({f"{ia}/bandwidth": 5.0, f"{ia}/amplitude": 6.0, f"{ib}/bandwidth": 7.0})
+    assert a.state == {"bandwidth": 5.0, "amplitude": 6.0} and b.state == {"bandwidth": 7.0}
+    assert k.state[f"{ib}/bandwidth"] == 7.0
