@@ -236,28 +236,33 @@ double pack_points(const double *X, int64_t n, int d, int layout, int64_t np, in
 }
 
 // True when two of the first n packed rows are equal as points (x - y == 0 in every coordinate).
-// Rows are hashed (with -0.0 folded onto +0.0) and only hash collisions are compared exactly.
+// Open-addressing table over a 64-bit row hash (-0.0 folded onto +0.0); equal hashes are compared exactly.
 bool has_duplicate_rows(const std::vector<double> &pts, int64_t n, int dp) {
-  std::vector<std::pair<uint64_t, int64_t>> h((size_t)n);
+  size_t cap = 1;
+  while (cap < (size_t)n * 2) cap <<= 1;
+  std::vector<int64_t> slot(cap, -1);
+  std::vector<uint64_t> hs(cap);
   for (int64_t i = 0; i < n; ++i) {
     uint64_t acc = 0x9e3779b97f4a7c15ull;
     for (int c = 0; c < dp; ++c) {
       const double v = pts[(size_t)i * dp + c] + 0.0;
       uint64_t b;
       memcpy(&b, &v, sizeof b);
-      acc ^= b + 0x9e3779b97f4a7c15ull + (acc << 6) + (acc >> 2);
-      acc *= 0xff51afd7ed558ccdull;
-      acc ^= acc >> 33;
+      acc = (acc ^ b) * 0xff51afd7ed558ccdull;
+      acc ^= acc >> 29;
     }
-    h[(size_t)i] = {acc, i};
-  }
-  std::sort(h.begin(), h.end());
-  for (int64_t i = 1; i < n; ++i) {
-    if (h[(size_t)i].first != h[(size_t)i - 1].first) continue;
-    const double *p = &pts[(size_t)h[(size_t)i].second * dp], *q = &pts[(size_t)h[(size_t)i - 1].second * dp];
-    bool same = true;
-    for (int c = 0; c < dp && same; ++c) same = (p[c] - q[c] == 0.0);
-    if (same) return true;
+    size_t p = acc & (cap - 1);
+    while (slot[p] >= 0) {
+      if (hs[p] == acc) {
+        const double *a = &pts[(size_t)i * dp], *q = &pts[(size_t)slot[p] * dp];
+        bool same = true;
+        for (int c = 0; c < dp && same; ++c) same = (a[c] - q[c] == 0.0);
+        if (same) return true;
+      }
+      p = (p + 1) & (cap - 1);
+    }
+    slot[p] = i;
+    hs[p] = acc;
   }
   return false;
 }
@@ -556,6 +561,14 @@ int32_t dgp_ctx_create(int32_t device, dgp_ctx **out) {
   ok = ok && cudaMalloc(&ctx->d_info, 4096 * sizeof(int)) == cudaSuccess &&
        cudaMallocHost(&ctx->h_info, 4096 * sizeof(int)) == cudaSuccess &&
        cudaMallocHost(&ctx->h_scal, 4096 * 160 * sizeof(double)) == cudaSuccess;
+  if (ok) {
+    // keep freed dgp_data blocks in the stream-ordered pool instead of returning them to the driver at every sync
+    cudaMemPool_t pool;
+    uint64_t keep = UINT64_MAX;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    cudaGetLastError();
+  }
   if (ok) ok = gemm_init(ctx) == DGP_OK && potrf_init(ctx) == DGP_OK;
   if (!ok) {
     delete ctx;
@@ -579,6 +592,7 @@ int32_t dgp_ctx_destroy(dgp_ctx *ctx) {
   cudaFree(ctx->d_info);
   cudaFreeHost(ctx->h_info);
   cudaFreeHost(ctx->h_scal);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   for (int i = 1; i < 4; ++i) {
     if (ctx->slot_S[i]) cudaStreamDestroy(ctx->slot_S[i]);
     if (ctx->slot_P[i]) cudaStreamDestroy(ctx->slot_P[i]);
@@ -636,27 +650,38 @@ int32_t dgp_data_create(dgp_ctx *ctx, const double *X, int64_t N, int32_t d, int
   D->Np = round_up(N, TILE);
   D->d = d;
   D->dp = (int)round_up(d, 4);
-  std::vector<double> hx, hr((size_t)D->Np, 0.0);
+  // one device block [ centred X | raw X | r ] from the stream-ordered pool, filled by one copy out of a
+  // pinned staging buffer: a create / destroy pair costs host packing only (cudaMalloc / cudaFree took ~2 ms each)
+  const size_t nx = (size_t)D->Np * D->dp, nr = (size_t)D->Np, total = 2 * nx + nr;
+  if (ctx->h_stage_bytes < total * sizeof(double)) {
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr;
+    ctx->h_stage_bytes = 0;
+    if (cudaMallocHost(&ctx->h_stage, total * sizeof(double)) != cudaSuccess) {
+      cudaGetLastError();
+      delete D;
+      return ctx->fail(DGP_ERR_OOM, "data: pinned staging allocation failed");
+    }
+    ctx->h_stage_bytes = total * sizeof(double);
+  }
+  double *hs = (double *)ctx->h_stage;
+  std::vector<double> hx;
   column_means(X, N, d, x_layout, D->center);
   D->max_sq_norm = pack_points(X, N, d, x_layout, D->Np, D->dp, hx, D->center.data());
   D->has_dup = has_duplicate_rows(hx, N, D->dp);
-  std::vector<double> hraw;
-  pack_points(X, N, d, x_layout, D->Np, D->dp, hraw, nullptr);
-  for (int64_t i = 0; i < N; ++i) hr[i] = y[i] - (mean ? mean[i] : 0.0);
-  cudaError_t e1 = cudaMalloc(&D->X, hx.size() * sizeof(double));
-  cudaError_t e2 = cudaMalloc(&D->r, hr.size() * sizeof(double));
-  cudaError_t e3 = cudaMalloc(&D->Xraw, hraw.size() * sizeof(double));
-  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-    cudaFree(D->X);
-    cudaFree(D->Xraw);
-    cudaFree(D->r);
-    delete D;
+  memcpy(hs, hx.data(), nx * sizeof(double));
+  pack_points(X, N, d, x_layout, D->Np, D->dp, hx, nullptr);
+  memcpy(hs + nx, hx.data(), nx * sizeof(double));
+  for (int64_t i = 0; i < D->Np; ++i) hs[2 * nx + i] = i < N ? y[i] - (mean ? mean[i] : 0.0) : 0.0;
+  if (cudaMallocAsync((void **)&D->block, total * sizeof(double), ctx->stream) != cudaSuccess) {
     cudaGetLastError();
+    delete D;
     return ctx->fail(DGP_ERR_OOM, "data: device allocation failed");
   }
-  cudaMemcpyAsync(D->X, hx.data(), hx.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-  cudaMemcpyAsync(D->Xraw, hraw.data(), hraw.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-  cudaMemcpyAsync(D->r, hr.data(), hr.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  D->X = D->block;
+  D->Xraw = D->block + nx;
+  D->r = D->block + 2 * nx;
+  cudaMemcpyAsync(D->block, hs, total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
   DGP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   *out = D;
   return DGP_OK;
@@ -668,10 +693,9 @@ int32_t dgp_data_destroy(dgp_ctx *ctx, dgp_data *D) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
   }
-  cudaFree(D->X);
-  cudaFree(D->Xraw);
+  if (ctx) cudaFreeAsync(D->block, ctx->stream);
+  else cudaFree(D->block);
   cudaFree(D->psi);
-  cudaFree(D->r);
   delete D;
   return DGP_OK;
 }

@@ -535,8 +535,11 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_gram_kernel(CovParams cp
 // keep the accumulators at 32 registers so that three CTAs fit per SM.
 // ---------------------------------------------------------------------------------------------
 struct LeanCov {
-  double c1;          // SE: 1/(2 l^2);  Matern: sqrt(2 nu)/l
-  double m0, m1, m2, m3;  // Matern: polynomial in r, coefficients right-aligned (m3 is the constant term)
+  // The operands are scaled by `scale` when they are staged in shared memory, so that the accumulator already
+  // holds the exponent's argument: SE scale = sqrt(1/(2 l^2)) -> acc = r^2/(2 l^2); Matern scale = sqrt(2 nu)/l
+  // -> sqrt(acc) = sqrt(2 nu) r / l.  This removes one FP64 multiply per entry.
+  double scale;
+  double m0, m1, m2, m3;  // Matern: polynomial in sqrt(acc), coefficients right-aligned (m3 is the constant term)
 };
 
 __device__ __forceinline__ double rsqrt_seed(double a) {
@@ -550,8 +553,11 @@ __device__ __forceinline__ double rsqrt_seed(double a) {
 // (scripts/ubench/fp64_mix.cu: the same FP64 sequence retires at 2.0 warp-instructions/clk/SM alone,
 // 1.76 with the integer epilogue and 1.49 with the table load), so the integer side is pared down:
 // the reduction constants come from the kernel parameters (constant-bank operands, no MOVs), the
-// table address is one shift + one LOP3 into a 512-byte-aligned table, the exponent one LOP3 + one
-// shift-add, and the underflow test is one integer minimum per four entries with a cold fix-up branch.
+// table address is one LOP3 + one shift-add, the exponent one LOP3 + one shift-add, and the underflow test
+// is one integer minimum per four entries with a cold fix-up branch.  The table is replicated 16 times
+// (entry j, copy c at (16 j + c) * 8 bytes) and lane l reads copy l & 15, so the 16 lanes of a half-warp hit
+// 16 distinct bank pairs whatever their j: the random lookups are conflict free (the single-copy table cost
+// 3.4 extra wavefronts per load, ncu l1tex__data_bank_conflicts, and ~10 % of the kernel time).
 struct LeanConst {
   double l2e64, ln2hi64, ln2lo64, c5, c4, c3;
 };
@@ -580,7 +586,7 @@ __device__ __forceinline__ void lean_exp_v(const double (&x)[V], const LeanConst
     p = fma(p, r[v], 1.0);
     p = fma(p, r[v], 1.0);
     double tj;
-    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab_s | ((unsigned)(n[v] << 3) & 0x1f8u)));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab_s + (((unsigned)n[v] & 63u) << 7)));
     const double w = tj * p;
     const int hi = __double2hiint(w) + (n[v] >> 6) * 0x100000;  // exponent += n >> 6
     out[v] = __hiloint2double(hi, __double2loint(w));
@@ -605,11 +611,8 @@ __global__ void __launch_bounds__(ATHREADS, 3)
     assemble_gram_lean_kernel(LeanCov f, LeanConst lc, ExpTab T, double kdiag, AssembleArgs a) {
   constexpr int LDK = lean_ldk<DP>();
   extern __shared__ __align__(16) double sm_raw[];
-  // the exp table first, on a 512-byte boundary (its address is OR-ed with the index)
-  const unsigned raw_s = (unsigned)__cvta_generic_to_shared(sm_raw);
-  const unsigned tab_s = (raw_s + 511u) & ~511u;
-  double *tab = sm_raw + (tab_s - raw_s) / 8;
-  double *Brow = tab + 64;              // row points i (MMA N):    [i][k] = x
+  double *tab = sm_raw;                 // 64 entries x 16 copies
+  double *Brow = tab + 64 * 16;         // row points i (MMA N):    [i][k] = x
   double *Acol = Brow + AT * LDK;       // column points j (MMA M): [j][k] = -2 y
   double *nx = Acol + AT * LDK;         // |x_i|^2
   double *ny = nx + AT;                 // |y_j|^2
@@ -658,19 +661,24 @@ __global__ void __launch_bounds__(ATHREADS, 3)
     }
     double nrm = 0.0;
 #pragma unroll
-    for (int c = 0; c < DP; ++c) nrm = fma(v[c], v[c], nrm);
+    for (int c = 0; c < DP; ++c) {
+      v[c] *= f.scale;
+      nrm = fma(v[c], v[c], nrm);
+    }
     const double sc = is_row ? 1.0 : -2.0;
 #pragma unroll
     for (int c = 0; c < DP / 2; ++c)
       reinterpret_cast<double2 *>(dst)[c] = make_double2(sc * v[2 * c], sc * v[2 * c + 1]);
     (is_row ? nx : ny)[pidx] = nrm;
-    if (tid < 64) tab[tid] = T.v[tid];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) tab[tid * 4 + e] = T.v[(tid * 4 + e) >> 4];
   }
   __syncthreads();
 
   double *out = a.out + (lm0 - a.row_off) + (ln0 - a.col_off) * a.ld;
   const int ibase = wn * 32;
   const double *bp = Brow + (ibase + g) * LDK + t;
+  const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab) + ((unsigned)(lane & 15) << 3);  // this lane's copy
 #pragma unroll 1
   for (int chunk = 0; chunk < 4; ++chunk) {
     const int jbase = chunk * 32 + wm * 16;
@@ -729,14 +737,14 @@ __global__ void __launch_bounds__(ATHREADS, 3)
             double p = P3 ? fma(f.m0, r[u], f.m1) : f.m1;
             p = fma(p, r[u], f.m2);
             s[u] = fma(p, r[u], f.m3);
-            x[u] = -f.c1 * r[u];
+            x[u] = -r[u];
           }
           lean_exp_v<4>(x, lc, tab_s, kv);
 #pragma unroll
           for (int u = 0; u < 4; ++u) kv[u] *= s[u];
         } else {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) x[u] = -f.c1 * acc[mb][2 * q + (u >> 1)][u & 1];
+          for (int u = 0; u < 4; ++u) x[u] = -acc[mb][2 * q + (u >> 1)][u & 1];
           lean_exp_v<4>(x, lc, tab_s, kv);
         }
         *reinterpret_cast<double2 *>(ocol + (2 * q) * 8) = make_double2(kv[0], kv[1]);
@@ -753,11 +761,12 @@ __global__ void __launch_bounds__(ATHREADS, 3)
 template <int KIND, int DP>
 void launch_lean(cudaStream_t st, const CovParams &cp, const AssembleArgs &a, unsigned tiles) {
   LeanCov f;
-  f.c1 = cp.c1;
+  f.scale = (KIND == DGP_KERNEL_MATERN) ? cp.c1 : sqrt(cp.c1);
   f.m0 = f.m1 = f.m2 = f.m3 = 0.0;
-  if (KIND == DGP_KERNEL_MATERN) {  // sum_i coef[i] (c2 r)^(p-i), right-aligned in m0..m3
+  if (KIND == DGP_KERNEL_MATERN) {
+    // sum_i coef[i] (c2 r)^(p-i) in terms of u = c1 r (c2 = 2 c1): coef[i] 2^(p-i) u^(p-i), right-aligned in m0..m3
     double *m[4] = {&f.m0, &f.m1, &f.m2, &f.m3};
-    for (int i = 0; i <= cp.p; ++i) *m[3 - (cp.p - i)] = cp.coef[i] * pow(cp.c2, (double)(cp.p - i));
+    for (int i = 0; i <= cp.p; ++i) *m[3 - (cp.p - i)] = cp.coef[i] * ldexp(1.0, cp.p - i);
   }
   const double a2 = (KIND == DGP_KERNEL_MATERN) ? 1.0 : cp.a2;
   ExpTab T;
@@ -769,7 +778,7 @@ void launch_lean(cudaStream_t st, const CovParams &cp, const AssembleArgs &a, un
   lc.c5 = 1.0 / 120.0;  lc.c4 = 1.0 / 24.0;  lc.c3 = 1.0 / 6.0;
   // value at distance zero plus the noise term (DiracKernel.scala:43-47 adds |sigma| where |x-y| == 0)
   const double kdiag = ((KIND == DGP_KERNEL_MATERN) ? cp.coef[cp.p] : cp.a2) + cp.noise_abs;
-  size_t smem = ((size_t)2 * AT * lean_ldk<DP>() + 2 * AT + 64) * sizeof(double) + 512;
+  size_t smem = ((size_t)2 * AT * lean_ldk<DP>() + 2 * AT + 64 * 16) * sizeof(double);
   auto go = [&](auto kern) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<tiles, ATHREADS, smem, st>>>(f, lc, T, kdiag, a);

@@ -54,6 +54,8 @@ struct Ctx {
   int *d_info = nullptr;  // device-side status word(s): [0] = first failing pivot index + 1, 0 = ok
   int *h_info = nullptr;  // pinned mirror
   double *h_scal = nullptr;  // pinned scratch for scalar read-back (64 doubles)
+  void *h_stage = nullptr;   // pinned, grow-only staging buffer of dgp_data_create
+  size_t h_stage_bytes = 0;
   DistState *dist = nullptr;
 
   int32_t fail(int32_t code, const char *fmt, ...);
@@ -83,6 +85,7 @@ struct Data {
   int64_t Np = 0;   // padded to a multiple of the outer block
   int d = 0;        // real feature count
   int dp = 0;       // padded to a multiple of 4 (zero columns; exact for every distance used here)
+  double *block = nullptr;  // one stream-ordered allocation holding X, Xraw and r
   double *X = nullptr;  // Np x dp, row-major (point i at X + i*dp), pad rows zero
   double *Xraw = nullptr;  // the same points without the centring, for the kernels that are not translation invariant
   double *r = nullptr;  // y - m(X), length Np, pad entries zero
