@@ -317,7 +317,8 @@ def main():
             "roofline_assembly": roofline_assembly,
             "phases_ms": phase,
             "peaks_measured": peaks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * (n * d + n)),
+            "e2e": {"value": e2e_value, "unit": UNIT, # dgp_data_create copies the centred points, the raw points and the residual vector (padded) in one transfer
+                    "h2d_bytes_per_step": int(8 * (2 * (-(-n // 128) * 128) * (-(-d // 4) * 4) + (-(-n // 128) * 128))),
                     "d2h_bytes_per_step": int(8 * (1 + len(g)))},
             "gpu_launches": int(launches),
             "clocks": clocks,
