@@ -18,6 +18,7 @@ from .stp import AbstractSTPRegressionModel, MultStudentsTPRV, STPRegression
 from .optimization import (CoupledSimulatedAnnealing, GradBasedGlobalOptimizer, GridSearch, ModelTuner,
                            ProbGPCommMachine)
 from .mcmc import AdaptiveHyperParameterMCMC, HyperParameterMCMC, HyperParameterSCAM
+from .esgp import BlockedMESNRV, ESGPModel
 
 __all__ = [
     "Context", "DgpError", "NotPositiveDefinite", "default_context",
@@ -29,4 +30,5 @@ __all__ = [
     "STPRegression", "AbstractSTPRegressionModel", "MultStudentsTPRV",
     "GridSearch", "CoupledSimulatedAnnealing", "GradBasedGlobalOptimizer", "ModelTuner", "ProbGPCommMachine",
     "AdaptiveHyperParameterMCMC", "HyperParameterMCMC", "HyperParameterSCAM", "DecomposableCovariance",
+    "ESGPModel", "BlockedMESNRV",
 ]

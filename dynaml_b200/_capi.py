@@ -33,7 +33,7 @@ EXPORTS = [
     "dgp_energy_grad", "dgp_energy_batch", "dgp_fit", "dgp_model_destroy", "dgp_model_energy", "dgp_model_terms",
     "dgp_predict", "dgp_dist_unique_id", "dgp_dist_init", "dgp_dist_finalize", "dgp_dist_plan", "dgp_dist_energy",
     "dgp_measure_peaks", "dgp_launch_count", "dgp_outer_block", "dgp_time_phase", "dgp_test_gemm", "dgp_test_potrf",
-    "dgp_spec_grad_len", "dgp_data_set_basis", "dgp_model_set_test_basis",
+    "dgp_spec_grad_len", "dgp_data_set_basis", "dgp_model_set_test_basis", "dgp_model_solve", "dgp_model_cross_apply",
 ]
 
 
@@ -103,6 +103,8 @@ def load_library() -> C.CDLL:
         "dgp_spec_grad_len": (i32, [sp]),
         "dgp_data_set_basis": (i32, [vp, vp, _dp, i32]),
         "dgp_model_set_test_basis": (i32, [vp, vp, _dp, i64, i32]),
+        "dgp_model_solve": (i32, [vp, vp, _dp, i32, _dp]),
+        "dgp_model_cross_apply": (i32, [vp, vp, _dp, i64, i32, _dp, i32, _dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -262,6 +264,26 @@ class Context:
         psi_s = _f64(psi_s)
         self.check(self.lib.dgp_model_set_test_basis(self.h, model, _ptr(psi_s), int(psi_s.shape[0]),
                                                      int(psi_s.shape[1])))
+
+    def model_solve(self, model, B):
+        """(K + noise)^-1 B for the columns of B (n or n x k) with the factor kept by fit()."""
+        B = np.asarray(B, dtype=np.float64)
+        one = B.ndim == 1
+        Bf = np.asfortranarray(B.reshape(B.shape[0], -1))
+        out = np.empty_like(Bf, order="F")
+        self.check(self.lib.dgp_model_solve(self.h, model, _ptr(Bf), int(Bf.shape[1]), _ptr(out)))
+        return out[:, 0] if one else out
+
+    def model_cross_apply(self, model, Xs, V):
+        """k(X, X*)' V for the columns of V (n or n x k); returns n_test (x k)."""
+        Xs = _f64(Xs)
+        V = np.asarray(V, dtype=np.float64)
+        one = V.ndim == 1
+        Vf = np.asfortranarray(V.reshape(V.shape[0], -1))
+        out = np.empty((Xs.shape[0], Vf.shape[1]), order="F")
+        self.check(self.lib.dgp_model_cross_apply(self.h, model, _ptr(Xs), Xs.shape[0], DGP_ROW_MAJOR, _ptr(Vf),
+                                                  int(Vf.shape[1]), _ptr(out)))
+        return out[:, 0] if one else out
 
     def energy_grad(self, data, spec):
         s, keep = spec

@@ -938,6 +938,61 @@ int32_t dgp_model_terms(dgp_ctx *ctx, const dgp_model *m, double *quad, double *
   return DGP_OK;
 }
 
+int32_t dgp_model_solve(dgp_ctx *ctx, const dgp_model *m, const double *b, int32_t k, double *out) {
+  if (!ctx || !m || !b || !out || k <= 0) return DGP_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStream_t S = ctx->stream;
+  const int64_t np = m->Np, n = m->N;
+  DGP_BUF(x, double, ctx, "solve_x", (size_t)np * sizeof(double));
+  for (int j = 0; j < k; ++j) {
+    // Lmat.t \\ (Lmat \\ b_j) with the padded tail zero (the padding block of L is the identity)
+    DGP_CUDA_OK(ctx, cudaMemsetAsync(x, 0, (size_t)np * sizeof(double), S));
+    DGP_CUDA_OK(ctx, cudaMemcpyAsync(x, b + (size_t)j * n, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, S));
+    DGP_TRY(trsv_lower_fwd(ctx, S, m->L, np, m->inv, np, x));
+    DGP_TRY(trsv_lower_bwd(ctx, S, m->L, np, m->inv, np, x));
+    DGP_CUDA_OK(ctx, cudaMemcpyAsync(out + (size_t)j * n, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, S));
+    DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));  // b / out are pageable host memory reused per column
+  }
+  return DGP_OK;
+}
+
+int32_t dgp_model_cross_apply(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t M, int32_t x_layout,
+                              const double *v, int32_t k, double *out) {
+  if (!ctx || !m || !Xs || !v || !out || M <= 0 || k <= 0) return DGP_ERR_ARG;
+  if (m->psi && (!m->psi_s || m->psi_s_n != M))
+    return ctx->fail(DGP_ERR_ARG, "cross_apply: the model has basis functions; call dgp_model_set_test_basis first");
+  cudaSetDevice(ctx->device);
+  cudaStream_t S = ctx->stream;
+  const int64_t np = m->Np, mp = round_up(M, TILE), n = m->N;
+  const int dp = m->dp;
+  std::vector<double> hx;
+  double nmax = pack_points(Xs, M, m->d, x_layout, mp, dp, hx, m->center.data());
+  if (m->max_sq_norm > nmax) nmax = m->max_sq_norm;
+  DGP_BUF(Xt, double, ctx, "Xt", (size_t)mp * dp * sizeof(double));
+  DGP_BUF(Ks, double, ctx, "Ks", (size_t)np * mp * sizeof(double));
+  DGP_BUF(vin, double, ctx, "cross_v", (size_t)np * sizeof(double));
+  DGP_BUF(vout, double, ctx, "cross_out", (size_t)mp * sizeof(double));
+  DGP_CUDA_OK(ctx, cudaMemcpyAsync(Xt, hx.data(), hx.size() * sizeof(double), cudaMemcpyHostToDevice, S));
+  const double *Xtk = nullptr;
+  DGP_TRY(scaled_points(ctx, S, m->spec, Xt, mp, dp, m->d, "Xts", &Xtk));
+  CovParams cpx = make_cov_params(m->spec, false, m->d);  // K* carries no noise (:279-286)
+  AssembleArgs a;
+  a.X1 = m->Xk;  a.X2 = Xtk;  a.dp = dp;
+  a.rows = n;  a.cols = M;  a.rows_p = np;  a.cols_p = mp;
+  a.out = Ks;  a.ld = np;
+  a.use_gram = pick_gram(ctx, m->spec, cpx, dp, m->d, nmax);
+  DGP_TRY(assemble(ctx, S, cpx, a));
+  if (m->psi) DGP_TRY(add_basis_term(ctx, S, m->psi, np, m->psi_s, mp, m->basis_mp, Ks, np, np, mp, false));
+  for (int j = 0; j < k; ++j) {
+    DGP_CUDA_OK(ctx, cudaMemsetAsync(vin, 0, (size_t)np * sizeof(double), S));
+    DGP_CUDA_OK(ctx, cudaMemcpyAsync(vin, v + (size_t)j * n, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, S));
+    DGP_TRY(gemv_t(ctx, S, Ks, np, np, mp, vin, nullptr, vout));
+    DGP_CUDA_OK(ctx, cudaMemcpyAsync(out + (size_t)j * M, vout, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, S));
+    DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
+  }
+  return DGP_OK;
+}
+
 int32_t dgp_model_set_test_basis(dgp_ctx *ctx, dgp_model *m, const double *psi_s, int64_t n_test, int32_t mb) {
   if (!ctx || !m || !psi_s || n_test <= 0) return DGP_ERR_ARG;
   if (!m->psi || mb != m->basis_m)

@@ -163,6 +163,17 @@ int32_t dgp_energy(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *sp
 int32_t dgp_energy_terms(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec, double *quad,
                          double *logdet_half);
 
+/* ---- building blocks for sibling models that share the Cholesky / solve core (SURVEY 8f rank 2:
+        ESGPModel.solve, CORE/models/sgp/ESGPModel.scala:349-389; the `\\` solvers of
+        CORE/algebra/PartitionedMatrixSolvers.scala) ----------------------------------------------
+   dgp_model_solve:       out = (K + noise)^-1 B for k right-hand sides (B, out column-major n x k) using the
+                          factor kept by dgp_fit  (Lmat.t \\ (Lmat \\ b)).
+   dgp_model_cross_apply: out = k(X, X*)' V for k vectors (V column-major n x k, out n_test x k): crossKernel.t * v.
+   Both copy in / out of host memory and synchronise.                                                */
+int32_t dgp_model_solve(dgp_ctx *ctx, const dgp_model *model, const double *b, int32_t k, double *out);
+int32_t dgp_model_cross_apply(dgp_ctx *ctx, const dgp_model *model, const double *xs, int64_t n_test,
+                              int32_t x_layout, const double *v, int32_t k, double *out);
+
 /* ---- explicit basis functions (GPBasisFuncRegressionModel,
         CORE/models/gp/GPBasisFuncRegressionModel.scala:70-109) ------------------------------------
    The model adds feature_map_cov(x, y) = psi(x).psi(y), psi(x) = chol(covB) * basisFunc(x), to the training,

@@ -521,6 +521,61 @@ def stp_error_bars(mu: float, mean: np.ndarray, covariance: np.ndarray, sigma: f
 
 
 # ------------------------------------------------------------------------------------------------
+# extended skew Gaussian process (CORE/models/sgp/ESGPModel.scala, probability/distributions/SkewGaussian.scala)
+# ------------------------------------------------------------------------------------------------
+
+def _phi_cdf(x: float) -> float:
+    return 0.5 * (1.0 + math.erf(x / math.sqrt(2.0)))
+
+
+def esgp_energy(cov, noise_level: float, X: np.ndarray, y: np.ndarray, lam: float, tau: float,
+                mean: np.ndarray | None = None) -> float:
+    """ESGPModel.logLikelihood (:337-348) = -BlockedMESN(tau, alpha, mu, Sigma).logPdf(y), alpha = lam * 1:
+    SkewSymmDistribution (:46-50): unnormalizedLogPdf = basis.unnormalizedLogPdf + log Phi(w(y) + tau delta),
+    logNormalizer = log Phi(tau) + basis.logNormalizer; basis = N(mu + alpha tau, Sigma + alpha alpha') with
+    BlockedMultiVariateGaussian's logNormalizer n/2 log 2 pi + 0.5 sum log diag chol (:45-50);
+    w(y) = alpha' Sigma^-1 (y - centre) / delta, delta = sqrt(1 + alpha' Sigma^-1 alpha) (SkewGaussian.scala:218-242)."""
+    n = X.shape[0]
+    mu = np.zeros(n) if mean is None else mean
+    alpha = np.full(n, lam)
+    sigma = build_kernel_matrix(cov, X, dirac(noise_level))
+    centre = mu + alpha * tau
+    adjusted = sigma + np.outer(alpha, alpha)
+    try:
+        root_sigma = sla.cholesky(sigma, lower=True)
+        root_adj = sla.cholesky(adjusted, lower=True)
+    except np.linalg.LinAlgError:
+        return float("inf")
+    solve = lambda L, b: sla.solve_triangular(L.T, sla.solve_triangular(L, b, lower=True), lower=False)  # noqa: E731
+    delta = math.sqrt(1.0 + float(alpha @ solve(root_sigma, alpha)))
+    r = y - centre
+    w = float(alpha @ solve(root_sigma, r)) / delta
+    unnorm = -0.5 * float(r @ solve(root_adj, r)) + math.log(_phi_cdf(w + tau * delta))
+    log_norm = math.log(_phi_cdf(tau)) + 0.5 * n * math.log(2 * math.pi) + 0.5 * float(np.sum(np.log(np.diag(root_adj))))
+    return -(unnorm - log_norm)
+
+
+def esgp_predictive(cov, noise_level: float, X: np.ndarray, y: np.ndarray, Xs: np.ndarray, lam: float, tau: float,
+                    mean: np.ndarray | None = None, mean_s: np.ndarray | None = None):
+    """ESGPModel.solve (:349-389): (mean, covariance, skewness, cutoff) of the posterior predictive."""
+    n, m = X.shape[0], Xs.shape[0]
+    mu = np.zeros(n) if mean is None else mean
+    mu_s = np.zeros(m) if mean_s is None else mean_s
+    smoothing = build_kernel_matrix(cov, X, dirac(noise_level))
+    Kss = build_kernel_matrix(cov, Xs)
+    Ks = cross_kernel_matrix(cov, X, Xs)
+    L = sla.cholesky(smoothing, lower=True)
+    solve = lambda b: sla.solve_triangular(L.T, sla.solve_triangular(L, b, lower=True), lower=False)  # noqa: E731
+    skew_tr = np.full(n, lam)
+    alpha = solve(y - mu)
+    beta = solve(skew_tr)
+    delta = 1.0 / math.sqrt(1.0 + float(skew_tr @ beta))
+    v = sla.solve_triangular(L, Ks, lower=True)
+    return (mu_s + Ks.T @ alpha, Kss - v.T @ v, (np.full(m, lam) - Ks.T @ beta) * delta,
+            (tau + float(skew_tr @ alpha)) * delta)
+
+
+# ------------------------------------------------------------------------------------------------
 # tuners (host logic only; energies come from a callable)
 # ------------------------------------------------------------------------------------------------
 
