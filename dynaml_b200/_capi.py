@@ -34,6 +34,7 @@ EXPORTS = [
     "dgp_predict", "dgp_dist_unique_id", "dgp_dist_init", "dgp_dist_finalize", "dgp_dist_plan", "dgp_dist_energy",
     "dgp_measure_peaks", "dgp_launch_count", "dgp_outer_block", "dgp_time_phase", "dgp_test_gemm", "dgp_test_potrf",
     "dgp_spec_grad_len", "dgp_data_set_basis", "dgp_model_set_test_basis", "dgp_model_solve", "dgp_model_cross_apply",
+    "dgp_model_set_cross_spec",
 ]
 
 
@@ -104,6 +105,7 @@ def load_library() -> C.CDLL:
         "dgp_data_set_basis": (i32, [vp, vp, _dp, i32]),
         "dgp_model_set_test_basis": (i32, [vp, vp, _dp, i64, i32]),
         "dgp_model_solve": (i32, [vp, vp, _dp, i32, _dp]),
+        "dgp_model_set_cross_spec": (i32, [vp, vp, sp]),
         "dgp_model_cross_apply": (i32, [vp, vp, _dp, i64, i32, _dp, i32, _dp]),
     }
     for name, (res, args) in sig.items():
@@ -264,6 +266,11 @@ class Context:
         psi_s = _f64(psi_s)
         self.check(self.lib.dgp_model_set_test_basis(self.h, model, _ptr(psi_s), int(psi_s.shape[0]),
                                                      int(psi_s.shape[1])))
+
+    def model_set_cross_spec(self, model, spec):
+        """General noise models: the covariance-only spec used for k(X, X*) and k(X*, X*)."""
+        s, keep = spec
+        self.check(self.lib.dgp_model_set_cross_spec(self.h, model, C.byref(s)))
 
     def model_solve(self, model, B):
         """(K + noise)^-1 B for the columns of B (n or n x k) with the factor kept by fit()."""

@@ -508,6 +508,10 @@ struct Model {
   double energy = 0.0, quad = 0.0, logdet_half = 0.0;
   std::vector<double> center;  // the training set's column means (test points are shifted alike)
   double max_sq_norm = 0.0;
+  // optional covariance-only spec for the cross / test matrices (general noise models)
+  bool has_cross = false;
+  Spec cross_spec;
+  double *Xk_cross = nullptr;  // training points as cross_spec consumes them (ARD: scaled copy, else == X)
   // GPBasisFuncRegressionModel: own copy of the training features, and the test features of the next predict
   double *psi = nullptr, *psi_s = nullptr;
   int basis_m = 0, basis_mp = 0;
@@ -831,6 +835,7 @@ int32_t dgp_model_destroy(dgp_ctx *ctx, dgp_model *m) {
   cudaFree(m->X);
   cudaFree(m->psi);
   cudaFree(m->psi_s);
+  if (m->Xk_cross && m->Xk_cross != m->X) cudaFree(m->Xk_cross);
   cudaFree(m->L);
   cudaFree(m->inv);
   cudaFree(m->alpha);
@@ -938,6 +943,35 @@ int32_t dgp_model_terms(dgp_ctx *ctx, const dgp_model *m, double *quad, double *
   return DGP_OK;
 }
 
+int32_t dgp_model_set_cross_spec(dgp_ctx *ctx, dgp_model *m, const dgp_kernel_spec *spec) {
+  if (!ctx || !m || !spec) return DGP_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  Spec sp;
+  DGP_TRY(parse_spec(ctx, spec, m->d, &sp));
+  if (spec_uses_raw_points(sp) != spec_uses_raw_points(m->spec))
+    return ctx->fail(DGP_ERR_ARG, "cross spec: inner-product kernels must appear in both specs or in neither");
+  cudaStream_t S = ctx->stream;
+  cudaStreamSynchronize(S);
+  if (m->Xk_cross && m->Xk_cross != m->X) cudaFree(m->Xk_cross);
+  m->Xk_cross = m->X;
+  if (sp.kind == DGP_KERNEL_ARD_SE) {
+    if (cudaMalloc(&m->Xk_cross, (size_t)m->Np * m->dp * sizeof(double)) != cudaSuccess) {
+      cudaGetLastError();
+      m->Xk_cross = nullptr;
+      return ctx->fail(DGP_ERR_OOM, "cross spec: device allocation failed");
+    }
+    ScaleVec sv;
+    for (int c = 0; c < 128; ++c) sv.v[c] = (c < m->d) ? 1.0 / sp.hyp[1 + c] : 0.0;
+    const int64_t total = m->Np * m->dp;
+    scale_points_byval_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S>>>(m->X, m->Xk_cross, sv, total, m->dp);
+    ctx->launches++;
+    DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
+  }
+  m->cross_spec = sp;
+  m->has_cross = true;
+  return DGP_OK;
+}
+
 int32_t dgp_model_solve(dgp_ctx *ctx, const dgp_model *m, const double *b, int32_t k, double *out) {
   if (!ctx || !m || !b || !out || k <= 0) return DGP_ERR_ARG;
   cudaSetDevice(ctx->device);
@@ -973,14 +1007,16 @@ int32_t dgp_model_cross_apply(dgp_ctx *ctx, const dgp_model *m, const double *Xs
   DGP_BUF(vin, double, ctx, "cross_v", (size_t)np * sizeof(double));
   DGP_BUF(vout, double, ctx, "cross_out", (size_t)mp * sizeof(double));
   DGP_CUDA_OK(ctx, cudaMemcpyAsync(Xt, hx.data(), hx.size() * sizeof(double), cudaMemcpyHostToDevice, S));
+  const Spec &cs = m->has_cross ? m->cross_spec : m->spec;
+  const double *Xtrain = m->has_cross ? m->Xk_cross : m->Xk;
   const double *Xtk = nullptr;
-  DGP_TRY(scaled_points(ctx, S, m->spec, Xt, mp, dp, m->d, "Xts", &Xtk));
-  CovParams cpx = make_cov_params(m->spec, false, m->d);  // K* carries no noise (:279-286)
+  DGP_TRY(scaled_points(ctx, S, cs, Xt, mp, dp, m->d, "Xts", &Xtk));
+  CovParams cpx = make_cov_params(cs, false, m->d);  // K* carries no noise (:279-286)
   AssembleArgs a;
-  a.X1 = m->Xk;  a.X2 = Xtk;  a.dp = dp;
+  a.X1 = Xtrain;  a.X2 = Xtk;  a.dp = dp;
   a.rows = n;  a.cols = M;  a.rows_p = np;  a.cols_p = mp;
   a.out = Ks;  a.ld = np;
-  a.use_gram = pick_gram(ctx, m->spec, cpx, dp, m->d, nmax);
+  a.use_gram = pick_gram(ctx, cs, cpx, dp, m->d, nmax);
   DGP_TRY(assemble(ctx, S, cpx, a));
   if (m->psi) DGP_TRY(add_basis_term(ctx, S, m->psi, np, m->psi_s, mp, m->basis_mp, Ks, np, np, mp, false));
   for (int j = 0; j < k; ++j) {
@@ -1034,16 +1070,18 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
     for (int64_t i = 0; i < M; ++i) hbase[i] = mean_s[i];
   DGP_CUDA_OK(ctx, cudaMemcpyAsync(Xt, hx.data(), hx.size() * sizeof(double), cudaMemcpyHostToDevice, S));
   DGP_CUDA_OK(ctx, cudaMemcpyAsync(dbase, hbase.data(), (size_t)mp * sizeof(double), cudaMemcpyHostToDevice, S));
+  const Spec &cs = m->has_cross ? m->cross_spec : m->spec;
+  const double *Xtrain = m->has_cross ? m->Xk_cross : m->Xk;
   const double *Xtk = nullptr;
-  DGP_TRY(scaled_points(ctx, S, m->spec, Xt, mp, dp, m->d, "Xts", &Xtk));
+  DGP_TRY(scaled_points(ctx, S, cs, Xt, mp, dp, m->d, "Xts", &Xtk));
 
   // K* = k(X, X*) : no noise (AbstractGPRegressionModel.scala:279-286)
-  CovParams cpx = make_cov_params(m->spec, false, m->d);
-  const int gram = pick_gram(ctx, m->spec, cpx, dp, m->d, nmax);
+  CovParams cpx = make_cov_params(cs, false, m->d);
+  const int gram = pick_gram(ctx, cs, cpx, dp, m->d, nmax);
   tick(ctx, 0, 0);
   {
     AssembleArgs a;
-    a.X1 = m->Xk;  a.X2 = Xtk;  a.dp = dp;
+    a.X1 = Xtrain;  a.X2 = Xtk;  a.dp = dp;
     a.rows = m->N;  a.cols = M;  a.rows_p = np;  a.cols_p = mp;
     a.out = Ks;  a.ld = np;
     a.use_gram = gram;

@@ -55,9 +55,11 @@ class CudaGPRegression:
                  ctx: _capi.Context | None = None):
         if noise is None:
             noise = DiracKernel(1.0)
-        if not isinstance(noise, DiracKernel):
-            raise NotImplementedError("the device path models noise with DiracKernel only; no CPU fallback")
         cov._device_kind()  # raises for unsupported covariance functions
+        noise._device_kind()
+        # a DiracKernel noise is the spec's dedicated noise term; any other LocalScalarKernel joins the training
+        # matrix as part of a composite and is left out of the cross / test matrices (:269-295)
+        self._dirac_noise = isinstance(noise, DiracKernel)
         self.covariance, self.noiseModel = cov, noise
         self.mean = meanFunc if meanFunc is not None else (lambda _x: 0.0)
         self.g = list(trainingdata)
@@ -141,7 +143,25 @@ class CudaGPRegression:
         pass
 
     def _spec(self):
-        return self.covariance._spec(noise=self.noiseModel.state["noiseLevel"])
+        if self._dirac_noise:
+            return self.covariance._spec(noise=self.noiseModel.state["noiseLevel"])
+        cov, nz = self.covariance, self.noiseModel
+        leaves = cov._leaves() + nz._leaves()
+        cfgs = cov._leaf_configs(cov.state) + nz._leaf_configs(nz.state)
+        off = len(cov._leaves())
+        terms = cov._terms() + [(c, {f + off: e for f, e in m.items()}) for c, m in nz._terms()]
+        factors = [(k._device_kind(), k.grad_mode, k._device_hyp(c)) for k, c in zip(leaves, cfgs)]
+        return _capi.make_composite_spec(factors, [(c, [m.get(f, 0) for f in range(len(leaves))]) for c, m in terms], 0.0)
+
+    def _fit(self, data):
+        model = self.ctx.fit(data, self._spec())
+        if not self._dirac_noise:
+            try:
+                self.ctx.model_set_cross_spec(model, self.covariance._spec())
+            except Exception:
+                self.ctx.model_destroy(model)
+                raise
+        return model
 
     # ---- GloballyOptimizable ----------------------------------------------------------------
     def energy(self, h: Dict[str, float], options: Dict[str, str] | None = None) -> float:
@@ -173,14 +193,19 @@ class CudaGPRegression:
         # hParams = (covariance + noiseModel).effective_hyper_parameters, keys stripped of the
         # "<Class@hash>/" prefix (:239); a later key overwrites an earlier one, like Scala's toMap
         pairs = [(h, float(g[cov_names.index(h)])) for h in self.covariance.effective_hyper_parameters]
-        pairs += [(h, float(g[len(cov_names)])) for h in self.noiseModel.effective_hyper_parameters]
+        if self._dirac_noise:
+            pairs += [(h, float(g[len(cov_names)])) for h in self.noiseModel.effective_hyper_parameters]
+        else:
+            noise_names = list(self.noiseModel.hyper_parameters)
+            pairs += [(h, float(g[len(cov_names) + noise_names.index(h)]))
+                      for h in self.noiseModel.effective_hyper_parameters]
         return dict(pairs)
 
     # ---- persistence (:399-422) -------------------------------------------------------------
     def persist(self, state: Dict[str, float]) -> None:
         self.setState(state)
         self._drop_model()
-        self._model = self.ctx.fit(self._device_data_train_only(), self._spec())
+        self._model = self._fit(self._device_data_train_only())
         self.caching = True
 
     def unpersist(self) -> None:
@@ -202,7 +227,7 @@ class CudaGPRegression:
     def _fitted(self):
         if self._model is not None and self.caching:
             return self._model, False
-        return self.ctx.fit(self._device_data_train_only(), self._spec()), True
+        return self._fit(self._device_data_train_only()), True
 
     def predictiveDistribution(self, test: Sequence) -> MultGaussianPRV:
         Xs = _as_points(test)

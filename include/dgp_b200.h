@@ -163,6 +163,14 @@ int32_t dgp_energy(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *sp
 int32_t dgp_energy_terms(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec, double *quad,
                          double *logdet_half);
 
+/* ---- general noise models ----------------------------------------------------------------------
+   AbstractGPRegressionModel takes any LocalScalarKernel as noise model: the training matrix is built from
+   covariance + noiseModel, the cross and test matrices from the covariance alone (:269-295).  A DiracKernel
+   noise is the `noise` field of the spec.  For any other noise kernel fit the model with the composite
+   covariance + noise (noise = 0) and hand the covariance-only spec to dgp_model_set_cross_spec: dgp_predict
+   and dgp_model_cross_apply then use it for k(X, X*) and k(X*, X*).                                     */
+int32_t dgp_model_set_cross_spec(dgp_ctx *ctx, dgp_model *model, const dgp_kernel_spec *spec);
+
 /* ---- building blocks for sibling models that share the Cholesky / solve core (SURVEY 8f rank 2:
         ESGPModel.solve, CORE/models/sgp/ESGPModel.scala:349-389; the `\\` solvers of
         CORE/algebra/PartitionedMatrixSolvers.scala) ----------------------------------------------

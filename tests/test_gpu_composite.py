@@ -225,3 +225,36 @@ def test_polynomial_times_se_composite():
     scale = max(abs(v) for v in go.values())
     for (gn, gv), (on, ov) in zip(g.items(), go.items()):
         assert gv == pytest.approx(ov, rel=TOL, abs=TOL * scale), (gn, on)
+
+
+def test_general_noise_kernel_enters_training_matrix_only():
+    """AbstractGPRegressionModel takes any LocalScalarKernel as noise model (:269-295): K = cov + noise on the
+    training set, the covariance alone for K* and K**; gradients over both kernels' hyper-parameters."""
+    X, y, Xs = orc.synthetic(230, 3, seed=91, m=35)
+    cov, ocov = dg.SEKernel(1.6, 1.1), orc.Kernel("se", {"bandwidth": 1.6, "amplitude": 1.1})
+    noise = dg.LaplacianKernel(0.4) * 0.2 + dg.DiracKernel(0.3)          # short-range correlated + white noise
+    onoise = orc.Sum(orc.Scaled(orc.Kernel("laplacian", {"beta": 0.4}), 0.2), orc.dirac(0.3))
+    model = dg.GPRegression(cov, noise, list(zip(X, y)))
+    K = orc.build_kernel_matrix(ocov, X) + orc.build_kernel_matrix(onoise, X)
+    h = model._current_state
+    assert model.energy(h) == pytest.approx(orc.log_likelihood(y, K), rel=TOL)
+    # posterior: K*, K** without the noise kernel
+    import scipy.linalg as sla
+    L = sla.cholesky(K, lower=True)
+    Ks, Kss = orc.cross_kernel_matrix(ocov, X, Xs), orc.build_kernel_matrix(ocov, Xs)
+    alpha = sla.cho_solve((L, True), y)
+    v = sla.solve_triangular(L, Ks, lower=True)
+    post = model.predictiveDistribution(Xs)
+    assert np.abs(post.mu - Ks.T @ alpha).max() <= TOL * np.abs(Ks.T @ alpha).max()
+    assert np.abs(post.covariance - (Kss - v.T @ v)).max() <= TOL * np.abs(Kss).max()
+    # gradient over covariance + noiseModel
+    g = model.gradEnergy(h)
+    go = orc.grad_energy(orc.Sum(ocov, onoise), 0.0, X, y, noise_blocked=True)
+    ref = list(go.values())   # bandwidth, amplitude, beta, noiseLevel (of the Dirac inside the noise model)
+    got = list(g.values())
+    assert len(got) == 4
+    scale = max(abs(v_) for v_ in ref)
+    assert np.allclose(got, ref, rtol=TOL, atol=TOL * scale)
+    # persisted model keeps the cross spec
+    model.persist(h)
+    assert model.predict(Xs[0]) == pytest.approx(float((Ks.T @ alpha)[0]), rel=TOL)
