@@ -11,7 +11,8 @@ from .kernels import (AdditiveCovariance, CauchyKernel, CompositeCovariance, Dec
                       FBMKernel,
                       GenericMaternKernel, PolynomialKernel,
                       LaplacianKernel, LocalScalarKernel, MahalanobisKernel, MultiplicativeCovariance, PeriodicKernel,
-                      RationalQuadraticKernel, RBFKernel, ScaledKernel, SEKernel, SVMKernelMatrix, TStudentKernel)
+                      RationalQuadraticKernel, RBFKernel, ScaledKernel, SEKernel, SVMKernelMatrix, TStudentKernel,
+                      KroneckerProductKernel, TensorCombinationKernel)
 from .models import (AbstractGPRegressionModel, CudaGPRegression, GPBasisFuncRegression, GPRegression,
                      MultGaussianPRV)
 from .stp import AbstractSTPRegressionModel, MultStudentsTPRV, STPRegression
@@ -30,5 +31,5 @@ __all__ = [
     "STPRegression", "AbstractSTPRegressionModel", "MultStudentsTPRV",
     "GridSearch", "CoupledSimulatedAnnealing", "GradBasedGlobalOptimizer", "ModelTuner", "ProbGPCommMachine",
     "AdaptiveHyperParameterMCMC", "HyperParameterMCMC", "HyperParameterSCAM", "DecomposableCovariance",
-    "ESGPModel", "BlockedMESNRV",
+    "ESGPModel", "BlockedMESNRV", "TensorCombinationKernel", "KroneckerProductKernel",
 ]

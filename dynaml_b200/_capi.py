@@ -134,9 +134,10 @@ KERNEL_COMPOSITE, KERNEL_POLYNOMIAL, KERNEL_FBM = 10, 11, 12
 MAX_FACTORS, MAX_TERMS = 32, 64
 
 
-def make_composite_spec(factors, terms, noise: float = 0.0):
+def make_composite_spec(factors, terms, noise: float = 0.0, ranges=None):
     """DGP_KERNEL_COMPOSITE: k = sum_t coef_t prod_f k_f^e_tf.  `factors` = [(kind, grad_mode, hyp), ...];
-    `terms` = [(coef, [e_0 .. e_{F-1}]), ...].  Returns (KernelSpec, keepalive) like make_spec."""
+    `terms` = [(coef, [e_0 .. e_{F-1}]), ...]; `ranges` (optional) = per factor the (start, count) slice of the
+    input vector it sees, count 0 = to the end.  Returns (KernelSpec, keepalive) like make_spec."""
     if not (1 <= len(factors) <= MAX_FACTORS and 1 <= len(terms) <= MAX_TERMS):
         raise ValueError(f"a composite kernel takes 1..{MAX_FACTORS} base kernels and 1..{MAX_TERMS} terms "
                          f"(got {len(factors)}, {len(terms)}); no CPU fallback")
@@ -147,6 +148,10 @@ def make_composite_spec(factors, terms, noise: float = 0.0):
     for coef, expo in terms:
         assert len(expo) == len(factors)
         prog += [float(coef)] + [float(e) for e in expo]
+    if ranges is not None:
+        assert len(ranges) == len(factors)
+        for start, count in ranges:
+            prog += [float(start), float(count)]
     return make_spec(KERNEL_COMPOSITE, prog, noise, GRAD_REFERENCE)
 
 

@@ -90,38 +90,88 @@ int32_t parse_composite(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
   dev.T = T;
   const int dp = (int)round_up(d, 4);
   int pos = 2, slots = 0, total_hyp = 0, moments = 0;
-  for (int s = 0; s < MAX_ARD_SLOTS; ++s)
+  for (int s = 0; s < MAX_ARD_SLOTS; ++s) {
+    dev.slot_l1[s] = 0;
     for (int c = 0; c < MAX_ARD_DIM; ++c) dev.w[s][c] = 0.0;
+  }
   for (int f = 0; f < MAXF; ++f) {
     dev.metric[f] = 0;
     dev.ard_exact[f] = 0;
     dev.moment_off[f] = 0;
+    dev.dim0[f] = 0;
+    dev.dimn[f] = d;
+    comp->factor_d[f] = d;
   }
+  // ---- optional trailer: per base kernel the (start, count) slice of the input vector it sees ----------------
+  {
+    int q = 2;
+    bool ok = true;
+    for (int f = 0; f < F && ok; ++f) {
+      int nf = 0;
+      ok = q + 3 <= n && as_int(p[q + 2], 0, DGP_MAX_HYP, &nf);
+      q += 3 + nf;
+    }
+    q += T * (1 + F);
+    if (ok && q + 2 * F == n) {
+      for (int f = 0; f < F; ++f) {
+        int s0 = 0, c0 = 0;
+        if (!as_int(p[q + 2 * f], 0, d - 1, &s0) || !as_int(p[q + 2 * f + 1], 0, d, &c0) || s0 + c0 > d)
+          return ctx->fail(DGP_ERR_ARG, "composite kernel: bad coordinate range for base kernel %d (d = %d)", f, d);
+        if (c0 == 0) c0 = d - s0;
+        dev.dim0[f] = s0;
+        dev.dimn[f] = c0;
+        comp->factor_d[f] = c0;
+      }
+    }
+  }
+  // a weighted-distance slot: reuse an identical one, else take the next
+  auto take_slot = [&](const double *w, int l1) -> int {
+    for (int s = 0; s < slots; ++s) {
+      bool same = dev.slot_l1[s] == l1;
+      for (int c = 0; c < MAX_ARD_DIM && same; ++c) same = dev.w[s][c] == w[c];
+      if (same) return s;
+    }
+    if (slots >= MAX_ARD_SLOTS) return -1;
+    for (int c = 0; c < MAX_ARD_DIM; ++c) dev.w[slots][c] = w[c];
+    dev.slot_l1[slots] = l1;
+    return slots++;
+  };
   for (int f = 0; f < F; ++f) {
     int kind = 0, gm = 0, nf = 0;
     if (pos + 3 > n || !as_int(p[pos], 0, DGP_KERNEL_FBM, &kind) || kind == DGP_KERNEL_COMPOSITE ||
         !as_int(p[pos + 1], 0, 1, &gm) ||
         !as_int(p[pos + 2], 0, DGP_MAX_HYP, &nf) || pos + 3 + nf > n)
       return ctx->fail(DGP_ERR_ARG, "composite kernel: malformed base kernel %d", f);
+    const int df = comp->factor_d[f], d0 = dev.dim0[f];
+    const bool sliced = df != d;
     dgp_kernel_spec fs;
     fs.kind = kind;  fs.n_hyp = nf;  fs.grad_mode = gm;  fs.reserved = 0;  fs.hyp = p + pos + 3;  fs.noise = 0.0;
-    DGP_TRY(parse_simple(ctx, &fs, d, &comp->factor[f]));
+    DGP_TRY(parse_simple(ctx, &fs, df, &comp->factor[f]));
     pos += 3 + nf;
     total_hyp += nf;
     const Spec &sf = comp->factor[f];
-    dev.cp[f] = make_cov_params(sf, false, d);
+    dev.cp[f] = make_cov_params(sf, false, df);
     if (kind_is_inner_product(kind)) {
+      if (sliced)
+        return ctx->fail(DGP_ERR_UNSUPPORTED_KERNEL, "composite kernel: Polynomial / FBM on a slice of the input");
       dev.any_ip = 1;
+    } else if (kind == DGP_KERNEL_ARD_SE || sliced) {
+      if (dp > MAX_ARD_DIM)
+        return ctx->fail(DGP_ERR_UNSUPPORTED_KERNEL, "composite kernel: ARD-SE or sliced base kernels need d <= %d",
+                         MAX_ARD_DIM);
+      double w[MAX_ARD_DIM];
+      for (int c = 0; c < MAX_ARD_DIM; ++c) w[c] = 0.0;
+      for (int c = 0; c < df; ++c)
+        w[d0 + c] = kind == DGP_KERNEL_ARD_SE ? 1.0 / (sf.hyp[1 + c] * sf.hyp[1 + c]) : 1.0;
+      const int s = take_slot(w, kind_is_l1(kind) ? 1 : 0);
+      if (s < 0)
+        return ctx->fail(DGP_ERR_UNSUPPORTED_KERNEL, "composite kernel: more than %d distinct ARD-SE / sliced metrics",
+                         MAX_ARD_SLOTS);
+      dev.metric[f] = 2 + s;
+      dev.ard_exact[f] = kind == DGP_KERNEL_ARD_SE && gm == DGP_GRAD_EXACT;
     } else if (kind_is_l1(kind)) {
       dev.metric[f] = 1;
       dev.any_l1 = 1;
-    } else if (kind == DGP_KERNEL_ARD_SE) {
-      if (slots >= MAX_ARD_SLOTS || dp > MAX_ARD_DIM)
-        return ctx->fail(DGP_ERR_UNSUPPORTED_KERNEL, "composite kernel: at most %d ARD-SE factors with d <= %d",
-                         MAX_ARD_SLOTS, MAX_ARD_DIM);
-      for (int c = 0; c < d; ++c) dev.w[slots][c] = 1.0 / (sf.hyp[1 + c] * sf.hyp[1 + c]);
-      dev.metric[f] = 2 + slots++;
-      dev.ard_exact[f] = gm == DGP_GRAD_EXACT;
     }
     dev.moment_off[f] = moments;
     moments += grad_partials_per_tile(dev.cp[f], dp);
@@ -143,7 +193,8 @@ int32_t parse_composite(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
     }
     pos += 1 + F;
   }
-  if (pos != n) return ctx->fail(DGP_ERR_ARG, "composite kernel: %d trailing values in the program", n - pos);
+  if (pos != n && pos + 2 * F != n)
+    return ctx->fail(DGP_ERR_ARG, "composite kernel: %d trailing values in the program", n - pos);
   out->kind = DGP_KERNEL_COMPOSITE;
   out->n_hyp = total_hyp;
   out->grad_mode = in->grad_mode;

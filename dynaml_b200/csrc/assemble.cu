@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(CovParams cp, Assemb
 // ---------------------------------------------------------------------------------------------
 struct PairMetrics {
   PairGeom g;
-  double ard[MAX_ARD_SLOTS] = {0.0, 0.0};
+  double ard[MAX_ARD_SLOTS] = {0.0, 0.0, 0.0, 0.0};
 };
 
 __device__ __forceinline__ void pair_metrics(const CompositeDev &c, const double *x, const double *y, int dp,
@@ -163,7 +163,7 @@ __device__ __forceinline__ void pair_metrics(const CompositeDev &c, const double
     }
 #pragma unroll
     for (int s = 0; s < MAX_ARD_SLOTS; ++s)
-      if (k < MAX_ARD_DIM) m.ard[s] = fma(c.w[s][k], e2, m.ard[s]);
+      if (k < MAX_ARD_DIM) m.ard[s] = fma(c.w[s][k], c.slot_l1[s] ? fabs(e) : e2, m.ard[s]);
   }
 }
 

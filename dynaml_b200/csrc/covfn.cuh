@@ -102,20 +102,22 @@ __device__ __forceinline__ double cov_value_rt(const CovParams &cp, double dist)
 }
 
 // ---- kernel algebra: k = sum_t coef_t prod_f v_f^e_tf (DGP_KERNEL_COMPOSITE) -------------------------
-constexpr int MAXF = DGP_MAX_FACTORS, MAXT = DGP_MAX_TERMS, MAX_ARD_SLOTS = 2, MAX_ARD_DIM = 32;
+constexpr int MAXF = DGP_MAX_FACTORS, MAXT = DGP_MAX_TERMS, MAX_ARD_SLOTS = 4, MAX_ARD_DIM = 32;
 
 // Everything the device needs, passed to the kernels by value (~1.7 KB of parameter space).
 struct CompositeDev {
   int F = 0, T = 0;
   int any_l1 = 0;                 // some factor consumes |x-y|_1
   int any_ip = 0;                 // some factor consumes x.y / |x|^2 / |y|^2 (the points are then the raw ones)
-  int metric[MAXF];               // per factor: 0 = |x-y|_2^2, 1 = |x-y|_1, 2 + s = ARD slot s
+  int metric[MAXF];               // per factor: 0 = |x-y|_2^2, 1 = |x-y|_1, 2 + s = weighted slot s
+  int slot_l1[MAX_ARD_SLOTS];     // slot s accumulates sum_c w_c |x_c - y_c| instead of sum_c w_c (x_c - y_c)^2
+  int dim0[MAXF], dimn[MAXF];     // coordinates [dim0, dim0 + dimn) a factor sees (tensor kernels); whole vector by default
   int moment_off[MAXF + 1];       // gradient pass: first moment of each factor; [F] = the noise moment
   int ard_exact[MAXF];            // ARD factor with the exact per-dimension derivative
   CovParams cp[MAXF];
   double coef[MAXT];
   unsigned char expo[MAXT][MAXF];
-  double w[MAX_ARD_SLOTS][MAX_ARD_DIM];  // ARD slots: 1 / b_c^2
+  double w[MAX_ARD_SLOTS][MAX_ARD_DIM];  // slot weights: 1 / b_c^2 (ARD-SE) and / or a 0-1 coordinate mask
 };
 
 __device__ __forceinline__ double ipow_small(double v, int e) {
@@ -170,6 +172,7 @@ inline CovParams make_cov_params(const Spec &s, bool with_noise, int d = 0);
 struct Composite {
   CompositeDev dev;
   Spec factor[MAXF];
+  int factor_d[MAXF];  // feature count each base kernel sees (its slice of the input vector)
 };
 
 inline CovParams make_cov_params(const Spec &s, bool with_noise, int d) {

@@ -350,7 +350,7 @@ __device__ __forceinline__ double fbm_dhurst(const CovParams &cp, const PairGeom
 __device__ __forceinline__ void composite_pair(const CompositeDev &c, const CompositeModes &md, const double *x,
                                                const double *y, int dp, double m, double *s) {
   PairGeom q;
-  double ard[MAX_ARD_SLOTS] = {0.0, 0.0};
+  double ard[MAX_ARD_SLOTS] = {0.0, 0.0, 0.0, 0.0};
   for (int k = 0; k < dp; ++k) {
     const double e = x[k] - y[k];
     const double e2 = e * e;
@@ -363,7 +363,7 @@ __device__ __forceinline__ void composite_pair(const CompositeDev &c, const Comp
     }
 #pragma unroll
     for (int a = 0; a < MAX_ARD_SLOTS; ++a)
-      if (k < MAX_ARD_DIM) ard[a] = fma(c.w[a][k], e2, ard[a]);
+      if (k < MAX_ARD_DIM) ard[a] = fma(c.w[a][k], c.slot_l1[a] ? fabs(e) : e2, ard[a]);
   }
   const double r2 = q.r2;
   double v[MAXF], cof[MAXF];
@@ -383,9 +383,9 @@ __device__ __forceinline__ void composite_pair(const CompositeDev &c, const Comp
       const double e = exp(-dist * c.cp[f].c1);
       sf[0] = fma(w, e, sf[0]);
       const double we = w * e;
-      for (int k = 0; k < dp; ++k) {
+      for (int k = c.dim0[f]; k < c.dim0[f] + c.dimn[f]; ++k) {
         const double df = x[k] - y[k];
-        sf[1 + k] = fma(we, df * df, sf[1 + k]);
+        sf[1 + k - c.dim0[f]] = fma(we, df * df, sf[1 + k - c.dim0[f]]);
       }
     } else if (md.mode[f] == M_FBM) {
       sf[0] = fma(w, fbm_dhurst(c.cp[f], q), sf[0]);
@@ -580,7 +580,8 @@ void grad_finish(const Spec &sp, int d, const double *S, int ns, double *g) {
     int pos = 0;
     for (int f = 0; f < cm.dev.F; ++f) {
       double tmp[DGP_MAX_HYP + 1];
-      grad_finish(cm.factor[f], d, S + cm.dev.moment_off[f], cm.dev.moment_off[f + 1] - cm.dev.moment_off[f], tmp);
+      grad_finish(cm.factor[f], cm.factor_d[f], S + cm.dev.moment_off[f],
+                  cm.dev.moment_off[f + 1] - cm.dev.moment_off[f], tmp);
       for (int i = 0; i < cm.factor[f].n_hyp; ++i) g[pos++] = tmp[i];
     }
     g[pos] = (sp.noise == 0.0) ? qnan : S[ns - 1];

@@ -90,12 +90,9 @@ class ESGPModel:
     def _spec_adjusted(self, lam: float):
         """covariance + noise + alpha alpha' with alpha = lambda 1: the constant lambda^2 is one more term (all
         exponents zero) of the covariance's sum-of-products form."""
-        leaves = self.covariance._leaves()
-        cfgs = self.covariance._leaf_configs(self.covariance.state)
-        factors = [(k._device_kind(), k.grad_mode, k._device_hyp(c)) for k, c in zip(leaves, cfgs)]
-        terms = [(c, [m.get(f, 0) for f in range(len(leaves))]) for c, m in self.covariance._terms()]
-        terms.append((lam * lam, [0] * len(leaves)))
-        return _capi.make_composite_spec(factors, terms, self.noiseModel.state["noiseLevel"])
+        from .kernels import composite_spec
+        return composite_spec([(self.covariance, self.covariance.state)], self.noiseModel.state["noiseLevel"],
+                              extra_terms=[(lam * lam, {})])
 
     # ---- GloballyOptimizable ----------------------------------------------------------------------------------
     def energy(self, h: Dict[str, float], options: Dict[str, str] | None = None) -> float:

@@ -132,6 +132,10 @@ class LocalScalarKernel:
     def _terms(self) -> List[tuple]:
         return [(1.0, {0: 1})]
 
+    def _leaf_ranges(self) -> List[tuple]:
+        """Per leaf the (start, count) slice of the input vector it sees; count 0 = up to the last coordinate."""
+        return [(0, 0)]
+
     def __add__(self, other: "LocalScalarKernel") -> "AdditiveCovariance":
         return AdditiveCovariance(self, other)
 
@@ -141,6 +145,21 @@ class LocalScalarKernel:
         return ScaledKernel(self, float(other))
 
     __rmul__ = __mul__
+
+
+def composite_spec(parts: Sequence[tuple], noise: float = 0.0, extra_terms: Sequence[tuple] = ()):
+    """DGP_KERNEL_COMPOSITE spec of a sum of kernels: `parts` = [(kernel, config), ...]; `extra_terms` adds
+    (coefficient, {leaf position: exponent}) terms over the joint leaf list (e.g. a constant: (c, {}))."""
+    factors, terms, ranges, off = [], [], [], 0
+    for kernel, config in parts:
+        leaves, cfgs = kernel._leaves(), kernel._leaf_configs(config)
+        factors += [(k._device_kind(), k.grad_mode, k._device_hyp(c)) for k, c in zip(leaves, cfgs)]
+        terms += [(c, {f + off: e for f, e in m.items()}) for c, m in kernel._terms()]
+        ranges += list(kernel._leaf_ranges())
+        off += len(leaves)
+    terms += list(extra_terms)
+    dense = [(c, [m.get(f, 0) for f in range(off)]) for c, m in terms]
+    return _capi.make_composite_spec(factors, dense, noise, ranges if any(r != (0, 0) for r in ranges) else None)
 
 
 class RBFKernel(LocalScalarKernel):
@@ -394,16 +413,15 @@ class CompositeCovariance(LocalScalarKernel):
         c1, c2 = self._configs(config)
         return self.firstKernel._leaf_configs(c1) + self.otherKernel._leaf_configs(c2)
 
+    def _leaf_ranges(self):
+        return self.firstKernel._leaf_ranges() + self.otherKernel._leaf_ranges()
+
     def _shifted_other_terms(self):
         off = len(self.firstKernel._leaves())
         return [(c, {f + off: e for f, e in m.items()}) for c, m in self.otherKernel._terms()]
 
     def _spec(self, config=None, noise: float = 0.0):
-        cfg = self.state if config is None else config
-        leaves, cfgs = self._leaves(), self._leaf_configs(cfg)
-        factors = [(k._device_kind(), k.grad_mode, k._device_hyp(c)) for k, c in zip(leaves, cfgs)]
-        terms = [(c, [m.get(f, 0) for f in range(len(leaves))]) for c, m in self._terms()]
-        return _capi.make_composite_spec(factors, terms, noise)
+        return composite_spec([(self, self.state if config is None else config)], noise)
 
 
 class AdditiveCovariance(CompositeCovariance):
@@ -480,12 +498,11 @@ class ScaledKernel(LocalScalarKernel):
     def _terms(self):
         return [(self.c * c, m) for c, m in self.base._terms()]
 
+    def _leaf_ranges(self):
+        return self.base._leaf_ranges()
+
     def _spec(self, config=None, noise: float = 0.0):
-        cfg = self.state if config is None else config
-        leaves, cfgs = self._leaves(), self._leaf_configs(cfg)
-        factors = [(k._device_kind(), k.grad_mode, k._device_hyp(c)) for k, c in zip(leaves, cfgs)]
-        terms = [(c, [m.get(f, 0) for f in range(len(leaves))]) for c, m in self._terms()]
-        return _capi.make_composite_spec(factors, terms, noise)
+        return composite_spec([(self, self.state if config is None else config)], noise)
 
 
 class DecomposableCovariance(LocalScalarKernel):
@@ -536,6 +553,9 @@ class DecomposableCovariance(LocalScalarKernel):
             out += k._leaf_configs(sub)
         return out
 
+    def _leaf_ranges(self):
+        return [r for k in self.kernels for r in k._leaf_ranges()]
+
     def _terms(self):
         out, off = [], 0
         for w, k in zip(self.weights, self.kernels):
@@ -544,8 +564,45 @@ class DecomposableCovariance(LocalScalarKernel):
         return out
 
     def _spec(self, config=None, noise: float = 0.0):
-        cfg = self.state if config is None else config
-        leaves, cfgs = self._leaves(), self._leaf_configs(cfg)
-        factors = [(k._device_kind(), k.grad_mode, k._device_hyp(c)) for k, c in zip(leaves, cfgs)]
-        terms = [(c, [m.get(f, 0) for f in range(len(leaves))]) for c, m in self._terms()]
-        return _capi.make_composite_spec(factors, terms, noise)
+        return composite_spec([(self, self.state if config is None else config)], noise)
+
+
+class TensorCombinationKernel(CompositeCovariance):
+    """Kernels on tuple inputs (x1, x2): k((x1, x2), (y1, y2)) = reduce(k1(x1, y1), k2(x2, y2))
+    (CORE/kernels/TensorCombinationKernel.scala:12-97).  Inputs are the concatenated vectors; `split` is the length
+    of the first component, so k1 sees coordinates [0, split) and k2 the rest.  `k1 :* k2` is
+    KroneckerProductKernel (product reducer), `k1 :+ k2` the sum reducer."""
+
+    def __init__(self, firstK: LocalScalarKernel, secondK: LocalScalarKernel, split: int, reducer: str = "*"):
+        if reducer not in ("*", "+"):
+            raise ValueError("reducer must be '*' (Reducer.:*:) or '+' (Reducer.:+:)")
+        if split <= 0:
+            raise ValueError("split must be the positive length of the first component")
+        super().__init__(firstK, secondK)
+        self.split, self.reducer = int(split), reducer
+
+    def _terms(self):
+        if self.reducer == "+":
+            return self.firstKernel._terms() + self._shifted_other_terms()
+        out = []
+        for c1, m1 in self.firstKernel._terms():
+            for c2, m2 in self._shifted_other_terms():
+                m = dict(m1)
+                for f, e in m2.items():
+                    m[f] = m.get(f, 0) + e
+                out.append((c1 * c2, m))
+        return out
+
+    def _leaf_ranges(self):
+        first = []
+        for s0, c0 in self.firstKernel._leaf_ranges():
+            if s0 >= self.split:
+                raise ValueError("a kernel of the first component addresses coordinates beyond the split")
+            first.append((s0, c0 if c0 else self.split - s0))
+        second = [(self.split + s0, c0) for s0, c0 in self.otherKernel._leaf_ranges()]
+        return first + second
+
+
+class KroneckerProductKernel(TensorCombinationKernel):
+    def __init__(self, firstK: LocalScalarKernel, secondK: LocalScalarKernel, split: int):
+        super().__init__(firstK, secondK, split, "*")

@@ -145,13 +145,8 @@ class CudaGPRegression:
     def _spec(self):
         if self._dirac_noise:
             return self.covariance._spec(noise=self.noiseModel.state["noiseLevel"])
-        cov, nz = self.covariance, self.noiseModel
-        leaves = cov._leaves() + nz._leaves()
-        cfgs = cov._leaf_configs(cov.state) + nz._leaf_configs(nz.state)
-        off = len(cov._leaves())
-        terms = cov._terms() + [(c, {f + off: e for f, e in m.items()}) for c, m in nz._terms()]
-        factors = [(k._device_kind(), k.grad_mode, k._device_hyp(c)) for k, c in zip(leaves, cfgs)]
-        return _capi.make_composite_spec(factors, [(c, [m.get(f, 0) for f in range(len(leaves))]) for c, m in terms], 0.0)
+        from .kernels import composite_spec
+        return composite_spec([(self.covariance, self.covariance.state), (self.noiseModel, self.noiseModel.state)], 0.0)
 
     def _fit(self, data):
         model = self.ctx.fit(data, self._spec())

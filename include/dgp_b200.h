@@ -78,9 +78,14 @@ enum {
      above) and T <= DGP_MAX_TERMS terms.  `hyp` is then a flat program of n_hyp doubles:
         [ F, T,
           F x { kind, grad_mode, n_f, hyp_0 .. hyp_{n_f - 1} },        base kernels, reference order
-          T x { coef_t, e_t0 .. e_t,F-1 } ]                           small non-negative integers
+          T x { coef_t, e_t0 .. e_t,F-1 },                            small non-negative integers
+          optionally F x { start_f, count_f } ]                       tensor kernels, see below
      gradEnergy returns the derivatives of the base kernels' hyper-parameters factor by factor,
-     then the noise level: dgp_spec_grad_len() values.  ARD-SE factors need d <= 32 (two at most). */
+     then the noise level: dgp_spec_grad_len() values.
+     The optional trailer restricts base kernel f to the coordinates [start_f, start_f + count_f) of the input
+     vector (count 0 = to the end): kernels on tuple inputs, TensorCombinationKernel / KroneckerProductKernel
+     (CORE/kernels/TensorCombinationKernel.scala:12-97) over the concatenated vectors; an ARD-SE factor then has
+     count_f bandwidths.  ARD-SE and sliced factors need d <= 32 and at most four distinct metrics.        */
   DGP_KERNEL_COMPOSITE = 10,
   /* The two non-stationary kernels of SURVEY 8(f) rank 1.  They read the original (uncentred) points and run
      on the composite evaluation path (also usable as base kernels of a composite).                          */

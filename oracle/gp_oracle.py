@@ -316,6 +316,29 @@ class WithFeatureMap:
         return self.base.grads(X, Y)
 
 
+class Sliced:
+    """A kernel that sees coordinates [start, start + count) of the input vectors: one component of a kernel on
+    tuple inputs (TensorCombinationKernel.scala:43-55 evaluates firstK on x._1, y._1 and secondK on x._2, y._2)."""
+
+    def __init__(self, base, start: int, count: int | None = None):
+        self.base, self.start, self.count = base, int(start), count
+
+    def _cut(self, X):
+        return X[:, self.start:] if not self.count else X[:, self.start:self.start + self.count]
+
+    def names(self, d: int | None = None):
+        return self.base.names(d)
+
+    def effective(self, blocked: Sequence[str] = ()):
+        return self.base.effective(blocked)
+
+    def value(self, X, Y):
+        return self.base.value(self._cut(X), self._cut(Y))
+
+    def grads(self, X, Y):
+        return self.base.grads(self._cut(X), self._cut(Y))
+
+
 class Scaled:
     """kernel * c, c > 0 (LocalScalarKernel.scala:68-91): same hyper-parameters, value and gradient times c."""
 

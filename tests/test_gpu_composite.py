@@ -258,3 +258,53 @@ def test_general_noise_kernel_enters_training_matrix_only():
     # persisted model keeps the cross spec
     model.persist(h)
     assert model.predict(Xs[0]) == pytest.approx(float((Ks.T @ alpha)[0]), rel=TOL)
+
+
+# ---- kernels on tuple inputs: TensorCombinationKernel / KroneckerProductKernel over concatenated vectors ---------
+def test_tensor_combination_kernels():
+    X, y, Xs = orc.synthetic(240, 5, seed=93, m=30)
+    band = [1.5, 2.5, 2.0]
+    ard_h = {"MahalanobisAmplitude": 1.1, **{f"MahalanobisBandwidth_{i}": b for i, b in enumerate(band)}}
+    cases = {
+        "se (x) laplacian": (dg.KroneckerProductKernel(dg.SEKernel(1.4, 1.0), dg.LaplacianKernel(2.0), 2),
+                             orc.Prod(orc.Sliced(orc.Kernel("se", {"bandwidth": 1.4, "amplitude": 1.0}), 0, 2),
+                                      orc.Sliced(orc.Kernel("laplacian", {"beta": 2.0}), 2))),
+        "matern (+) ard_exact": (dg.TensorCombinationKernel(dg.GenericMaternKernel(1.8, 1),
+                                                            dg.MahalanobisKernel(band, 1.1, _capi.GRAD_EXACT), 2, "+"),
+                                 orc.Sum(orc.Sliced(orc.Kernel("matern", {"p": 1.0, "l": 1.8}), 0, 2),
+                                         orc.Sliced(orc.Kernel("ard", ard_h, "exact"), 2))),
+        "(rbf (x) cauchy) (x) rbf": (dg.KroneckerProductKernel(
+            dg.KroneckerProductKernel(dg.RBFKernel(1.6), dg.CauchyKernel(2.2), 2), dg.RBFKernel(2.4), 4),
+            orc.Prod(orc.Prod(orc.Sliced(orc.Kernel("rbf", {"bandwidth": 1.6}), 0, 2),
+                              orc.Sliced(orc.Kernel("cauchy", {"sigma": 2.2}), 2, 2)),
+                     orc.Sliced(orc.Kernel("rbf", {"bandwidth": 2.4}), 4))),
+    }
+    for name, (k, ok) in cases.items():
+        K = k.buildKernelMatrix(X, len(X)).getKernelMatrix()
+        assert entry_rel(K, orc.build_kernel_matrix(ok, X)) <= TOL_K, name
+        model = dg.GPRegression(k, dg.DiracKernel(0.3), list(zip(X, y)))
+        h = model._current_state
+        assert model.energy(h) == pytest.approx(orc.energy(ok, 0.3, X, y), rel=TOL), name
+        g, go = model.gradEnergy(h), orc.grad_energy(ok, 0.3, X, y)
+        assert len(g) == len(go), name
+        scale = max(abs(v) for v in go.values())
+        for (gn, gv), (on, ov) in zip(g.items(), go.items()):
+            assert gv == pytest.approx(ov, rel=TOL, abs=TOL * scale), (name, gn, on)
+        post = model.predictiveDistribution(Xs)
+        mu, cov = orc.predictive(ok, 0.3, X, y, Xs)
+        assert np.abs(post.mu - mu).max() <= TOL * max(1.0, np.abs(mu).max()), name
+        assert np.abs(post.covariance - cov).max() <= TOL * np.abs(cov).max(), name
+
+
+def test_tensor_kernel_range_errors(ctx):
+    X, y, _ = orc.synthetic(40, 3, seed=1)
+    data = ctx.data_create(X, y)
+    try:
+        bad = dg.KroneckerProductKernel(dg.RBFKernel(1.0), dg.RBFKernel(1.0), 5)   # split beyond d = 3
+        with pytest.raises(dg.DgpError):
+            ctx.energy(data, bad._spec(noise=0.1))
+        poly = dg.KroneckerProductKernel(dg.PolynomialKernel(2, 1.0), dg.RBFKernel(1.0), 2)
+        with pytest.raises(dg.DgpError):
+            ctx.energy(data, poly._spec(noise=0.1))                                # inner-product kernel on a slice
+    finally:
+        ctx.data_destroy(data)
