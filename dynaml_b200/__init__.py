@@ -20,6 +20,9 @@ from .optimization import (CoupledSimulatedAnnealing, GradBasedGlobalOptimizer, 
                            ProbGPCommMachine)
 from .mcmc import AdaptiveHyperParameterMCMC, HyperParameterMCMC, HyperParameterSCAM
 from .esgp import BlockedMESNRV, ESGPModel
+from .mogp import KroneckerMOGPModel, MOGPRegressionModel
+from .kernels import (CoRegCauchyKernel, CoRegDiracKernel, CoRegLaplaceKernel, CoRegRBFKernel,
+                      CoRegTStudentKernel)
 
 __all__ = [
     "Context", "DgpError", "NotPositiveDefinite", "default_context",
@@ -32,4 +35,6 @@ __all__ = [
     "GridSearch", "CoupledSimulatedAnnealing", "GradBasedGlobalOptimizer", "ModelTuner", "ProbGPCommMachine",
     "AdaptiveHyperParameterMCMC", "HyperParameterMCMC", "HyperParameterSCAM", "DecomposableCovariance",
     "ESGPModel", "BlockedMESNRV", "TensorCombinationKernel", "KroneckerProductKernel",
+    "MOGPRegressionModel", "KroneckerMOGPModel", "CoRegRBFKernel", "CoRegCauchyKernel", "CoRegLaplaceKernel",
+    "CoRegTStudentKernel", "CoRegDiracKernel",
 ]

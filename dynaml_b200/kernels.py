@@ -136,6 +136,11 @@ class LocalScalarKernel:
         """Per leaf the (start, count) slice of the input vector it sees; count 0 = up to the last coordinate."""
         return [(0, 0)]
 
+    def _fix_device_grad(self, config: Dict[str, float], g: List[float]) -> List[float]:
+        """Map the device derivatives (w.r.t. `_device_hyp`) to the reference's for this kernel's own
+        hyper-parameters; identity unless the kernel is a re-parametrisation of a device kind."""
+        return g
+
     def __add__(self, other: "LocalScalarKernel") -> "AdditiveCovariance":
         return AdditiveCovariance(self, other)
 
@@ -606,3 +611,68 @@ class TensorCombinationKernel(CompositeCovariance):
 class KroneckerProductKernel(TensorCombinationKernel):
     def __init__(self, firstK: LocalScalarKernel, secondK: LocalScalarKernel, split: int):
         super().__init__(firstK, secondK, split, "*")
+
+
+# ---- co-regionalisation kernels over the output index (LocalScalarKernel[Int] in the reference) -----------------
+# In the multi-output models the output index travels as the last coordinate of the input vector, so these are the
+# device kernels of the same functional form restricted to that coordinate, with the reference's names.
+class CoRegRBFKernel(LocalScalarKernel):
+    """exp(-(i - j)^2 / coRegB) (RBFKernel.scala:182-194).  Device: RBF with l = sqrt(coRegB / 2); the reference's
+    derivative is k (i-j)^2 / |coRegB|^3 (not the chain rule), i.e. the device's k (i-j)^2 / l^3 times l^3 / |b|^3."""
+    hyper_parameters = ["coRegB"]
+
+    def __init__(self, bandwidth: float):
+        super().__init__()
+        self.state = {"coRegB": float(bandwidth)}
+
+    def _device_kind(self):
+        return _capi.KERNEL_RBF
+
+    def _device_hyp(self, config):
+        return [math.sqrt(float(config["coRegB"]) / 2.0)]
+
+    def _fix_device_grad(self, config, g):
+        b = float(config["coRegB"])
+        l = math.sqrt(b / 2.0)
+        return [g[0] * l ** 3 / abs(b) ** 3]
+
+
+class CoRegCauchyKernel(CauchyKernel):
+    hyper_parameters = ["CoRegSigma"]        # CauchyKernel.scala:53-65
+
+    def __init__(self, bandwidth: float):
+        LocalScalarKernel.__init__(self)
+        self.state = {"CoRegSigma": float(bandwidth)}
+
+
+class CoRegLaplaceKernel(LaplacianKernel):
+    hyper_parameters = ["coRegLB"]           # LaplacianKernel.scala:53-65
+
+    def __init__(self, bandwidth: float):
+        LocalScalarKernel.__init__(self)
+        self.state = {"coRegLB": float(bandwidth)}
+
+
+class CoRegTStudentKernel(TStudentKernel):
+    hyper_parameters = ["CoRegD"]            # TStudentKernel.scala:74-94
+
+    def __init__(self, bandwidth: float):
+        LocalScalarKernel.__init__(self)
+        self.state = {"CoRegD": float(bandwidth)}
+
+
+class CoRegDiracKernel(LocalScalarKernel):
+    """1 if i == j else 0 (DiracKernel.scala:91-98).  The reference class has no hyper-parameters; the device Dirac
+    kind carries a level, kept here as the permanently blocked `coRegDiracLevel` = 1."""
+    hyper_parameters = ["coRegDiracLevel"]
+
+    def __init__(self):
+        super().__init__()
+        self.state = {"coRegDiracLevel": 1.0}
+        self.blocked_hyper_parameters = ["coRegDiracLevel"]
+
+    def block(self, *h: str) -> None:
+        self.blocked_hyper_parameters = ["coRegDiracLevel"]
+
+    def _device_kind(self):
+        return _capi.KERNEL_DIRAC

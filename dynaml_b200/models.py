@@ -184,6 +184,14 @@ class CudaGPRegression:
         self.covariance.setHyperParameters(h)
         self.noiseModel.setHyperParameters(h)
         _, g = self.ctx.energy_grad(self._device_data(), self._spec())
+        g = np.array(g, dtype=np.float64)
+        # kernels that re-parametrise a device kind translate their own derivatives (e.g. CoRegRBFKernel)
+        off = 0
+        for kern in [self.covariance] + ([] if self._dirac_noise else [self.noiseModel]):
+            for leaf, cfg in zip(kern._leaves(), kern._leaf_configs(kern.state)):
+                nh = len(leaf.hyper_parameters)
+                g[off:off + nh] = leaf._fix_device_grad(cfg, [float(v) for v in g[off:off + nh]])
+                off += nh
         cov_names = list(self.covariance.hyper_parameters)
         # hParams = (covariance + noiseModel).effective_hyper_parameters, keys stripped of the
         # "<Class@hash>/" prefix (:239); a later key overwrites an earlier one, like Scala's toMap

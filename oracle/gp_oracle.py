@@ -544,6 +544,38 @@ def stp_error_bars(mu: float, mean: np.ndarray, covariance: np.ndarray, sigma: f
 
 
 # ------------------------------------------------------------------------------------------------
+# multi-output GP (CORE/models/gp/MOGPRegressionModel.scala)
+# ------------------------------------------------------------------------------------------------
+
+def mogp_flatten(X: np.ndarray, Y: np.ndarray):
+    """dataAsSeq (:37-43): ((x, o), y_o) pattern-major; the output index is appended as the last coordinate."""
+    n, q = Y.shape
+    Z = np.array([np.append(X[i], float(o)) for i in range(n) for o in range(q)])
+    return Z, Y.reshape(-1)
+
+
+def kronecker_mogp_energy(cov, noise_level: float, coreg, X: np.ndarray, Y: np.ndarray,
+                          mean_mat: np.ndarray | None = None) -> float:
+    """KroneckerMOGPModel.energy (:57-79) = -MatrixNormal(M, U, V).logPdf(Y) (MatrixNormal.scala:49-62):
+    U = covFunc matrix + noiseCovFunc matrix (DiracKernel.buildKernelMatrix = eye * sigma), V = coRegCov over 0..q-1;
+    unnormalizedLogPdf = -0.5 tr(V^-1 D' U^-1 D); logNormalizer = 0.5 (log(2 pi) n p + detU p + detV n) with
+    det* = sum log diag chol (half log-determinants, as everywhere in the reference)."""
+    n, q = Y.shape
+    U = build_kernel_matrix(cov, X) + np.eye(n) * noise_level
+    V = build_kernel_matrix(coreg, np.arange(q, dtype=float)[:, None])
+    D = Y - (0.0 if mean_mat is None else mean_mat)
+    try:
+        ru, rv = sla.cholesky(U, lower=True), sla.cholesky(V, lower=True)
+    except np.linalg.LinAlgError:
+        return float("inf")
+    y = sla.cho_solve((ru, True), D)
+    unnorm = -0.5 * float(np.trace(sla.cho_solve((rv, True), D.T @ y)))
+    log_norm = 0.5 * (math.log(2 * math.pi) * n * q + float(np.log(np.diag(ru)).sum()) * q
+                      + float(np.log(np.diag(rv)).sum()) * n)
+    return -(unnorm - log_norm)
+
+
+# ------------------------------------------------------------------------------------------------
 # extended skew Gaussian process (CORE/models/sgp/ESGPModel.scala, probability/distributions/SkewGaussian.scala)
 # ------------------------------------------------------------------------------------------------
 
