@@ -176,6 +176,7 @@ int32_t parse_composite(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
     dev.moment_off[f] = moments;
     moments += grad_partials_per_tile(dev.cp[f], dp);
   }
+  dev.nslots = slots;
   dev.moment_off[F] = moments;
   for (int f = F + 1; f <= MAXF; ++f) dev.moment_off[f] = moments;
   if (total_hyp > DGP_MAX_HYP) return ctx->fail(DGP_ERR_ARG, "composite kernel: too many hyper-parameters");
@@ -183,6 +184,8 @@ int32_t parse_composite(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
     dev.coef[t] = 0.0;
     for (int f = 0; f < MAXF; ++f) dev.expo[t][f] = 0;
   }
+  dev.simple = 1;
+  for (int t = 0; t < MAXT; ++t) dev.mask[t] = 0u;
   for (int t = 0; t < T; ++t) {
     if (pos + 1 + F > n) return ctx->fail(DGP_ERR_ARG, "composite kernel: malformed term %d", t);
     dev.coef[t] = p[pos];
@@ -190,6 +193,8 @@ int32_t parse_composite(Ctx *ctx, const dgp_kernel_spec *in, int d, Spec *out) {
       int e = 0;
       if (!as_int(p[pos + 1 + f], 0, 8, &e)) return ctx->fail(DGP_ERR_ARG, "composite kernel: bad exponent");
       dev.expo[t][f] = (unsigned char)e;
+      if (e > 1) dev.simple = 0;
+      if (e) dev.mask[t] |= 1u << f;
     }
     pos += 1 + F;
   }

@@ -149,9 +149,13 @@ struct PairMetrics {
   double ard[MAX_ARD_SLOTS] = {0.0, 0.0, 0.0, 0.0};
 };
 
+// DP > 0: compile-time feature count (x is a register array, the loop unrolls); DP == 0: runtime count `dp`.
+template <int DP>
 __device__ __forceinline__ void pair_metrics(const CompositeDev &c, const double *x, const double *y, int dp,
                                              PairMetrics &m) {
-  for (int k = 0; k < dp; ++k) {
+  const int n = DP > 0 ? DP : dp;
+#pragma unroll
+  for (int k = 0; k < n; ++k) {
     const double e = x[k] - y[k];
     const double e2 = e * e;
     m.g.r2 += e2;
@@ -163,7 +167,7 @@ __device__ __forceinline__ void pair_metrics(const CompositeDev &c, const double
     }
 #pragma unroll
     for (int s = 0; s < MAX_ARD_SLOTS; ++s)
-      if (k < MAX_ARD_DIM) m.ard[s] = fma(c.w[s][k], c.slot_l1[s] ? fabs(e) : e2, m.ard[s]);
+      if (s < c.nslots && k < MAX_ARD_DIM) m.ard[s] = fma(c.w[s][k], c.slot_l1[s] ? fabs(e) : e2, m.ard[s]);
   }
 }
 
@@ -172,19 +176,30 @@ __device__ __forceinline__ double metric_of(const CompositeDev &c, const PairMet
   return id == 0 ? m.g.r2 : (id == 1 ? m.g.l1 : m.ard[id - 2]);
 }
 
+template <int FT>
 __device__ __forceinline__ double composite_entry(const CompositeDev &c, const PairMetrics &m) {
-  double v[MAXF];
-  for (int f = 0; f < c.F; ++f) {
-    if (kind_is_inner_product(c.cp[f].kind)) v[f] = cov_value_ip(c.cp[f], m.g);
-    else v[f] = cov_value_rt(c.cp[f], metric_of(c, m, f));
+  double v[FT];
+  if (FactorLoop<FT>::unrolled) {
+#pragma unroll
+    for (int f = 0; f < FT; ++f) {
+      if (f >= c.F) v[f] = 1.0;
+      else if (kind_is_inner_product(c.cp[f].kind)) v[f] = cov_value_ip(c.cp[f], m.g);
+      else v[f] = cov_value_rt(c.cp[f], metric_of(c, m, f));
+    }
+  } else {
+    for (int f = 0; f < c.F; ++f) {
+      if (kind_is_inner_product(c.cp[f].kind)) v[f] = cov_value_ip(c.cp[f], m.g);
+      else v[f] = cov_value_rt(c.cp[f], metric_of(c, m, f));
+    }
   }
-  return composite_combine(c, v);
+  return composite_combine<FT>(c, v);
 }
 
+template <int DP, int FT>
 __global__ void __launch_bounds__(ATHREADS) assemble_composite_kernel(CompositeDev c, double noise_abs,
                                                                       AssembleArgs a) {
   extern __shared__ __align__(16) double sm[];  // column points: AT x dp, row-major
-  const int dp = a.dp;
+  const int dp = DP > 0 ? DP : a.dp;
   const int tid = threadIdx.x;
   const int tx = tid & 63, ty = tid >> 6;
 
@@ -208,25 +223,60 @@ __global__ void __launch_bounds__(ATHREADS) assemble_composite_kernel(CompositeD
     if (n0 > m0 + AT - 1) return;
   }
   for (int i = tid; i < AT * dp; i += ATHREADS) sm[i] = a.X2[n0 * dp + i];
-  __syncthreads();
 
   const int64_t r0 = m0 + 2 * tx;
   const bool sym = a.symmetric != 0;
   double *out = a.out + (lm0 - a.row_off + 2 * tx) + (ln0 - a.col_off) * a.ld;
   const double *p0 = a.X1 + r0 * dp, *p1 = p0 + dp;
+  double x0[DP > 0 ? DP : 1], x1[DP > 0 ? DP : 1];
+  if (DP > 0) {
+#pragma unroll
+    for (int k = 0; k < DP; ++k) {
+      x0[k] = p0[k];
+      x1[k] = p1[k];
+    }
+  }
+  __syncthreads();
   for (int cc = 0; cc < AT / 4; ++cc) {
     const int j = ty + 4 * cc;
     const double *y = sm + j * dp;
     PairMetrics q0, q1;
-    pair_metrics(c, p0, y, dp, q0);
-    pair_metrics(c, p1, y, dp, q1);
-    double k0 = composite_entry(c, q0), k1 = composite_entry(c, q1);
+    pair_metrics<DP>(c, DP > 0 ? x0 : p0, y, dp, q0);
+    pair_metrics<DP>(c, DP > 0 ? x1 : p1, y, dp, q1);
+    double k0 = composite_entry<FT>(c, q0), k1 = composite_entry<FT>(c, q1);
     if (q0.g.r2 == 0.0) k0 += noise_abs;
     if (q1.g.r2 == 0.0) k1 += noise_abs;
     const int64_t col = n0 + j;
     if (r0 >= a.rows || col >= a.cols) k0 = (sym && r0 == col) ? 1.0 : 0.0;
     if (r0 + 1 >= a.rows || col >= a.cols) k1 = (sym && r0 + 1 == col) ? 1.0 : 0.0;
     *reinterpret_cast<double2 *>(out + (int64_t)j * a.ld) = make_double2(k0, k1);
+  }
+}
+
+template <int DP, int FT>
+void launch_composite_one(cudaStream_t st, const CompositeDev &c, double noise_abs, const AssembleArgs &a,
+                          unsigned tiles) {
+  size_t smem = (size_t)AT * a.dp * sizeof(double);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(assemble_composite_kernel<DP, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  assemble_composite_kernel<DP, FT><<<tiles, ATHREADS, smem, st>>>(c, noise_abs, a);
+}
+
+template <int FT>
+void launch_composite(cudaStream_t st, const CompositeDev &c, double noise_abs, const AssembleArgs &a, unsigned tiles) {
+  if (!FactorLoop<FT>::unrolled) {  // many base kernels: the runtime-loop variant measured faster than the unrolled-DP one
+    launch_composite_one<0, FT>(st, c, noise_abs, a, tiles);
+    return;
+  }
+  switch (a.dp) {
+    case 4: launch_composite_one<4, FT>(st, c, noise_abs, a, tiles); break;
+    case 8: launch_composite_one<8, FT>(st, c, noise_abs, a, tiles); break;
+    case 12: launch_composite_one<12, FT>(st, c, noise_abs, a, tiles); break;
+    case 16: launch_composite_one<16, FT>(st, c, noise_abs, a, tiles); break;
+    case 20: launch_composite_one<20, FT>(st, c, noise_abs, a, tiles); break;
+    case 24: launch_composite_one<24, FT>(st, c, noise_abs, a, tiles); break;
+    case 32: launch_composite_one<32, FT>(st, c, noise_abs, a, tiles); break;
+    default: launch_composite_one<0, FT>(st, c, noise_abs, a, tiles); break;
   }
 }
 
@@ -863,10 +913,8 @@ int32_t assemble(Ctx *ctx, cudaStream_t st, const CovParams &cp, const AssembleA
   if (tiles == 0) return DGP_OK;
   if (cp.kind == DGP_KERNEL_COMPOSITE) {
     if (!cp.comp) return ctx->fail(DGP_ERR_ARG, "assemble: composite kernel without an expression");
-    size_t smem = (size_t)AT * a.dp * sizeof(double);
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(assemble_composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    assemble_composite_kernel<<<(unsigned)tiles, ATHREADS, smem, st>>>(*cp.comp, cp.noise_abs, a);
+    if (cp.comp->F <= 4) launch_composite<4>(st, *cp.comp, cp.noise_abs, a, (unsigned)tiles);
+    else launch_composite<MAXF>(st, *cp.comp, cp.noise_abs, a, (unsigned)tiles);
     ctx->launches++;
     DGP_CUDA_OK(ctx, cudaGetLastError());
     return DGP_OK;

@@ -109,6 +109,9 @@ struct CompositeDev {
   int F = 0, T = 0;
   int any_l1 = 0;                 // some factor consumes |x-y|_1
   int any_ip = 0;                 // some factor consumes x.y / |x|^2 / |y|^2 (the points are then the raw ones)
+  int nslots = 0;                 // weighted-metric slots in use
+  int simple = 0;                 // every exponent is 0 or 1: terms are products over the bit sets mask[t]
+  unsigned mask[MAXT];            // bit f set: base kernel f is a factor of term t
   int metric[MAXF];               // per factor: 0 = |x-y|_2^2, 1 = |x-y|_1, 2 + s = weighted slot s
   int slot_l1[MAX_ARD_SLOTS];     // slot s accumulates sum_c w_c |x_c - y_c| instead of sum_c w_c (x_c - y_c)^2
   int dim0[MAXF], dimn[MAXF];     // coordinates [dim0, dim0 + dimn) a factor sees (tensor kernels); whole vector by default
@@ -126,14 +129,40 @@ __device__ __forceinline__ double ipow_small(double v, int e) {
   return r;
 }
 
+// The composite kernels are instantiated for FT = 4 (expressions of up to four base kernels: every loop over the
+// factors is unrolled and v / cof live in registers) and FT = MAXF (runtime loops, local-memory arrays).
+template <int FT>
+struct FactorLoop {
+  static constexpr bool unrolled = FT <= 4;
+};
+
 // Value of the expression from the base-kernel values v[0..F).
-__device__ __forceinline__ double composite_combine(const CompositeDev &c, const double *v) {
+template <int FT>
+__device__ __forceinline__ double composite_combine(const CompositeDev &c, const double (&v)[FT]) {
   double k = 0.0;
+  if (FactorLoop<FT>::unrolled && c.simple) {  // branch-free: the usual sums / products of distinct kernels
+    for (int t = 0; t < c.T; ++t) {
+      const unsigned mk = c.mask[t];
+      double prod = c.coef[t];
+#pragma unroll
+      for (int f = 0; f < FT; ++f) prod *= ((mk >> f) & 1u) ? v[f] : 1.0;
+      k += prod;
+    }
+    return k;
+  }
   for (int t = 0; t < c.T; ++t) {
     double prod = c.coef[t];
-    for (int f = 0; f < c.F; ++f) {
-      const int e = c.expo[t][f];
-      if (e) prod *= ipow_small(v[f], e);
+    if (FactorLoop<FT>::unrolled) {
+#pragma unroll
+      for (int f = 0; f < FT; ++f) {
+        const int e = (f < c.F) ? c.expo[t][f] : 0;
+        if (e) prod *= ipow_small(v[f], e);
+      }
+    } else {
+      for (int f = 0; f < c.F; ++f) {
+        const int e = c.expo[t][f];
+        if (e) prod *= ipow_small(v[f], e);
+      }
     }
     k += prod;
   }
@@ -142,24 +171,66 @@ __device__ __forceinline__ double composite_combine(const CompositeDev &c, const
 
 // cof[f] = d k / d v_f for every base kernel: the factor each derivative of base kernel f is multiplied by
 // (MultiplicativeCovariance.scala:68-77; `* c` scales value and gradient alike, LocalScalarKernel.scala:81-85).
-// One pass per term with running prefix products, so the cost is O(T F) per pair and no division by v_f.
-__device__ __forceinline__ void composite_cofactors(const CompositeDev &c, const double *v, double *cof) {
-  for (int f = 0; f < c.F; ++f) cof[f] = 0.0;
-  for (int t = 0; t < c.T; ++t) {
-    // suffix[f] = prod_{g >= f} v_g^e_g is rebuilt backwards into cof-sized scratch held in registers/local
-    double suffix = 1.0;
-    double tmp[MAXF];
-    for (int f = c.F - 1; f >= 0; --f) {
-      tmp[f] = suffix;  // product over g > f
-      const int e = c.expo[t][f];
-      if (e) suffix *= ipow_small(v[f], e);
+// One pass per term with running prefix / suffix products: O(T F) per pair and no division by v_f.
+template <int FT>
+__device__ __forceinline__ void composite_cofactors(const CompositeDev &c, const double (&v)[FT], double (&cof)[FT]) {
+  if (FactorLoop<FT>::unrolled && c.simple) {
+#pragma unroll
+    for (int f = 0; f < FT; ++f) cof[f] = 0.0;
+    for (int t = 0; t < c.T; ++t) {
+      const unsigned mk = c.mask[t];
+      double u[FT], suffix[FT + 1];
+#pragma unroll
+      for (int f = 0; f < FT; ++f) u[f] = ((mk >> f) & 1u) ? v[f] : 1.0;
+      suffix[FT] = 1.0;
+#pragma unroll
+      for (int f = FT - 1; f >= 0; --f) suffix[f] = suffix[f + 1] * u[f];
+      double prefix = c.coef[t];
+#pragma unroll
+      for (int f = 0; f < FT; ++f) {
+        cof[f] += ((mk >> f) & 1u) ? prefix * suffix[f + 1] : 0.0;
+        prefix *= u[f];
+      }
     }
-    double prefix = c.coef[t];
-    for (int f = 0; f < c.F; ++f) {
-      const int e = c.expo[t][f];
-      if (e) {
-        cof[f] = fma((double)e * ipow_small(v[f], e - 1), prefix * tmp[f], cof[f]);
-        prefix *= ipow_small(v[f], e);
+    return;
+  }
+  if (FactorLoop<FT>::unrolled) {
+#pragma unroll
+    for (int f = 0; f < FT; ++f) cof[f] = 0.0;
+    for (int t = 0; t < c.T; ++t) {
+      double suffix = 1.0, tmp[FT];
+#pragma unroll
+      for (int f = FT - 1; f >= 0; --f) {
+        tmp[f] = suffix;
+        const int e = (f < c.F) ? c.expo[t][f] : 0;
+        if (e) suffix *= ipow_small(v[f], e);
+      }
+      double prefix = c.coef[t];
+#pragma unroll
+      for (int f = 0; f < FT; ++f) {
+        const int e = (f < c.F) ? c.expo[t][f] : 0;
+        if (e) {
+          cof[f] = fma((double)e * ipow_small(v[f], e - 1), prefix * tmp[f], cof[f]);
+          prefix *= ipow_small(v[f], e);
+        }
+      }
+    }
+  } else {
+    for (int f = 0; f < c.F; ++f) cof[f] = 0.0;
+    for (int t = 0; t < c.T; ++t) {
+      double suffix = 1.0, tmp[FT];
+      for (int f = c.F - 1; f >= 0; --f) {
+        tmp[f] = suffix;  // product over g > f
+        const int e = c.expo[t][f];
+        if (e) suffix *= ipow_small(v[f], e);
+      }
+      double prefix = c.coef[t];
+      for (int f = 0; f < c.F; ++f) {
+        const int e = c.expo[t][f];
+        if (e) {
+          cof[f] = fma((double)e * ipow_small(v[f], e - 1), prefix * tmp[f], cof[f]);
+          prefix *= ipow_small(v[f], e);
+        }
       }
     }
   }

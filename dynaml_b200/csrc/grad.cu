@@ -347,11 +347,14 @@ __device__ __forceinline__ double fbm_dhurst(const CovParams &cp, const PairGeom
   return pow(q.nx, h) * log(q.nx) + pow(q.ny, h) * log(q.ny) - pow(q.r2, h) * log(q.r2);
 }
 
+template <int DP, int FT>
 __device__ __forceinline__ void composite_pair(const CompositeDev &c, const CompositeModes &md, const double *x,
                                                const double *y, int dp, double m, double *s) {
+  const int n = DP > 0 ? DP : dp;
   PairGeom q;
   double ard[MAX_ARD_SLOTS] = {0.0, 0.0, 0.0, 0.0};
-  for (int k = 0; k < dp; ++k) {
+#pragma unroll
+  for (int k = 0; k < n; ++k) {
     const double e = x[k] - y[k];
     const double e2 = e * e;
     q.r2 += e2;
@@ -363,19 +366,19 @@ __device__ __forceinline__ void composite_pair(const CompositeDev &c, const Comp
     }
 #pragma unroll
     for (int a = 0; a < MAX_ARD_SLOTS; ++a)
-      if (k < MAX_ARD_DIM) ard[a] = fma(c.w[a][k], c.slot_l1[a] ? fabs(e) : e2, ard[a]);
+      if (a < c.nslots && k < MAX_ARD_DIM) ard[a] = fma(c.w[a][k], c.slot_l1[a] ? fabs(e) : e2, ard[a]);
   }
   const double r2 = q.r2;
-  double v[MAXF], cof[MAXF];
-  for (int f = 0; f < c.F; ++f) {
+  double v[FT], cof[FT];
+  auto dist_of = [&](int f) {
     const int id = c.metric[f];
-    const double dist = id == 0 ? q.r2 : (id == 1 ? q.l1 : ard[id - 2]);
-    v[f] = kind_is_inner_product(c.cp[f].kind) ? cov_value_ip(c.cp[f], q) : cov_value_rt(c.cp[f], dist);
-  }
-  composite_cofactors(c, v, cof);
-  for (int f = 0; f < c.F; ++f) {
-    const int id = c.metric[f];
-    const double dist = id == 0 ? q.r2 : (id == 1 ? q.l1 : ard[id - 2]);
+    return id == 0 ? q.r2 : (id == 1 ? q.l1 : ard[id - 2]);
+  };
+  auto value_of = [&](int f) {
+    return kind_is_inner_product(c.cp[f].kind) ? cov_value_ip(c.cp[f], q) : cov_value_rt(c.cp[f], dist_of(f));
+  };
+  auto accumulate_factor = [&](int f) {
+    const double dist = dist_of(f);
     const double w = m * cof[f];
     double *sf = s + c.moment_off[f];
     if (c.ard_exact[f]) {
@@ -383,9 +386,12 @@ __device__ __forceinline__ void composite_pair(const CompositeDev &c, const Comp
       const double e = exp(-dist * c.cp[f].c1);
       sf[0] = fma(w, e, sf[0]);
       const double we = w * e;
-      for (int k = c.dim0[f]; k < c.dim0[f] + c.dimn[f]; ++k) {
+      const int k0 = c.dim0[f], k1 = k0 + c.dimn[f];
+#pragma unroll
+      for (int k = 0; k < n; ++k) {  // static index into x (a register array when DP > 0)
+        if (k < k0 || k >= k1) continue;
         const double df = x[k] - y[k];
-        sf[1 + k - c.dim0[f]] = fma(we, df * df, sf[1 + k - c.dim0[f]]);
+        sf[1 + k - k0] = fma(we, df * df, sf[1 + k - k0]);
       }
     } else if (md.mode[f] == M_FBM) {
       sf[0] = fma(w, fbm_dhurst(c.cp[f], q), sf[0]);
@@ -394,13 +400,26 @@ __device__ __forceinline__ void composite_pair(const CompositeDev &c, const Comp
     } else {
       accumulate_rt(md.mode[f], c.cp[f], w, dist, r2, sf);
     }
+  };
+  if (FactorLoop<FT>::unrolled) {
+#pragma unroll
+    for (int f = 0; f < FT; ++f) v[f] = (f < c.F) ? value_of(f) : 1.0;
+    composite_cofactors<FT>(c, v, cof);
+#pragma unroll
+    for (int f = 0; f < FT; ++f)
+      if (f < c.F) accumulate_factor(f);
+  } else {
+    for (int f = 0; f < c.F; ++f) v[f] = value_of(f);
+    composite_cofactors<FT>(c, v, cof);
+    for (int f = 0; f < c.F; ++f) accumulate_factor(f);
   }
   if (r2 == 0.0) s[c.moment_off[c.F]] += m;
 }
 
+template <int DP, int FT>
 __global__ void __launch_bounds__(GTHREADS) grad_trace_composite_kernel(CompositeDev c, CompositeModes md, GradArgs a) {
   extern __shared__ __align__(16) double sm[];
-  const int dp = a.dp;
+  const int dp = DP > 0 ? DP : a.dp;
   const int NS = c.moment_off[c.F] + 1;
   double *sx = sm;
   double *sal = sm + GT * dp;
@@ -416,7 +435,15 @@ __global__ void __launch_bounds__(GTHREADS) grad_trace_composite_kernel(Composit
   for (int i = tid; i < GT * dp; i += GTHREADS) sx[i] = a.X[n0 * dp + i];
   if (tid < GT) sal[tid] = a.alpha[n0 + tid];
   const int64_t r0 = m0 + 2 * tx;
-  const double *x0 = a.X + r0 * dp, *x1 = x0 + dp;
+  const double *p0 = a.X + r0 * dp, *p1 = p0 + dp;
+  double x0[DP > 0 ? DP : 1], x1[DP > 0 ? DP : 1];
+  if (DP > 0) {
+#pragma unroll
+    for (int k = 0; k < DP; ++k) {
+      x0[k] = p0[k];
+      x1[k] = p1[k];
+    }
+  }
   const double al0 = a.alpha[r0], al1 = a.alpha[r0 + 1];
   __syncthreads();
   double s[MAX_COMPOSITE_MOMENTS];
@@ -431,8 +458,8 @@ __global__ void __launch_bounds__(GTHREADS) grad_trace_composite_kernel(Composit
     double w1 = (r0 + 1 > col) ? 2.0 : (r0 + 1 == col ? 1.0 : 0.0);
     if (r0 >= a.n || col >= a.n) w0 = 0.0;
     if (r0 + 1 >= a.n || col >= a.n) w1 = 0.0;
-    if (w0 != 0.0) composite_pair(c, md, x0, sx + j * dp, dp, w0 * (al0 * aj - kv.x), s);
-    if (w1 != 0.0) composite_pair(c, md, x1, sx + j * dp, dp, w1 * (al1 * aj - kv.y), s);
+    if (w0 != 0.0) composite_pair<DP, FT>(c, md, DP > 0 ? x0 : p0, sx + j * dp, dp, w0 * (al0 * aj - kv.x), s);
+    if (w1 != 0.0) composite_pair<DP, FT>(c, md, DP > 0 ? x1 : p1, sx + j * dp, dp, w1 * (al1 * aj - kv.y), s);
   }
   const int warp = tid >> 5, lane = tid & 31;
   for (int q = 0; q < NS; ++q) {
@@ -446,6 +473,35 @@ __global__ void __launch_bounds__(GTHREADS) grad_trace_composite_kernel(Composit
     double v = 0.0;
     for (int wdx = 0; wdx < GTHREADS / 32; ++wdx) v += red[wdx * NS + tid];
     a.partials[(int64_t)blockIdx.x * NS + tid] = v;
+  }
+}
+
+template <int DP, int FT>
+int32_t launch_composite_trace(Ctx *ctx, cudaStream_t st, const CompositeDev &c, const CompositeModes &md,
+                               const GradArgs &a, int64_t tiles, int NS) {
+  size_t smem = ((size_t)GT * a.dp + GT + (GTHREADS / 32) * NS) * sizeof(double);
+  if (smem > 200 * 1024) return ctx->fail(DGP_ERR_SHAPE, "gradEnergy: too many features (dp=%d)", a.dp);
+  if (smem > 48 * 1024)
+    DGP_CUDA_OK(ctx, cudaFuncSetAttribute(grad_trace_composite_kernel<DP, FT>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  grad_trace_composite_kernel<DP, FT><<<(unsigned)tiles, GTHREADS, smem, st>>>(c, md, a);
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  return DGP_OK;
+}
+
+template <int FT>
+int32_t launch_composite_trace_dp(Ctx *ctx, cudaStream_t st, const CompositeDev &c, const CompositeModes &md,
+                                  const GradArgs &a, int64_t tiles, int NS) {
+  if (!FactorLoop<FT>::unrolled) return launch_composite_trace<0, FT>(ctx, st, c, md, a, tiles, NS);
+  switch (a.dp) {
+    case 4: return launch_composite_trace<4, FT>(ctx, st, c, md, a, tiles, NS);
+    case 8: return launch_composite_trace<8, FT>(ctx, st, c, md, a, tiles, NS);
+    case 12: return launch_composite_trace<12, FT>(ctx, st, c, md, a, tiles, NS);
+    case 16: return launch_composite_trace<16, FT>(ctx, st, c, md, a, tiles, NS);
+    case 20: return launch_composite_trace<20, FT>(ctx, st, c, md, a, tiles, NS);
+    case 24: return launch_composite_trace<24, FT>(ctx, st, c, md, a, tiles, NS);
+    case 32: return launch_composite_trace<32, FT>(ctx, st, c, md, a, tiles, NS);
+    default: return launch_composite_trace<0, FT>(ctx, st, c, md, a, tiles, NS);
   }
 }
 
@@ -545,13 +601,8 @@ int32_t grad_trace(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArg
                        MAX_COMPOSITE_MOMENTS);
     CompositeModes md;
     for (int f = 0; f < MAXF; ++f) md.mode[f] = f < c.F ? mode_of(c.cp[f]) : M_DIRAC;
-    size_t smem = ((size_t)GT * a.dp + GT + (GTHREADS / 32) * NS) * sizeof(double);
-    if (smem > 200 * 1024) return ctx->fail(DGP_ERR_SHAPE, "gradEnergy: too many features (dp=%d)", a.dp);
-    if (smem > 48 * 1024)
-      DGP_CUDA_OK(ctx, cudaFuncSetAttribute(grad_trace_composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
-    grad_trace_composite_kernel<<<(unsigned)tiles, GTHREADS, smem, st>>>(c, md, a);
-    DGP_CUDA_OK(ctx, cudaGetLastError());
+    if (c.F <= 4) DGP_TRY(launch_composite_trace_dp<4>(ctx, st, c, md, a, tiles, NS));
+    else DGP_TRY(launch_composite_trace_dp<MAXF>(ctx, st, c, md, a, tiles, NS));
     reduce_partials_kernel<<<NS, 1024, 0, st>>>(a.partials, tiles, NS, a.sums);
     ctx->launches += 2;
     DGP_CUDA_OK(ctx, cudaGetLastError());
