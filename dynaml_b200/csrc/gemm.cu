@@ -67,12 +67,14 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 
 // Copy one ROWS x BK operand slice into a stage (ROWS = 128 for A, 64 for B).  g points at the
 // slice origin.
-template <bool KMAJOR, int ROWS, int BK>
+template <bool KMAJOR, int ROWS, int BK, bool INC = false>
 __device__ __forceinline__ void load_slice(double *s, const double *g, int64_t ld, int tid) {
   constexpr int CHUNKS = ROWS * BK / 2;  // 16-byte chunks
   constexpr int LD_MN = ROWS + 4;
   constexpr int LDS_K = BK + 4;
-  if (!KMAJOR) {
+  // Chunk c = tid + i * NTHREADS: consecutive i advance the slow index by a compile-time step, so every address is
+  // the previous one plus a loop-invariant stride (one 64-bit add per chunk instead of a multiply-add chain).
+  if (!KMAJOR && !INC) {
     // element (mn, k) at g[mn + k*ld]; BK columns of ROWS contiguous doubles
 #pragma unroll
     for (int i = 0; i < CHUNKS / NTHREADS; ++i) {
@@ -80,8 +82,25 @@ __device__ __forceinline__ void load_slice(double *s, const double *g, int64_t l
       int k = c / (ROWS / 2), mc = c % (ROWS / 2);
       cp_async16(s + k * LD_MN + mc * 2, g + mc * 2 + (int64_t)k * ld);
     }
+  } else if (!KMAJOR) {
+    // the same with incremental addresses.  Measured per GEMM variant: it pays for the B tile
+    // whenever B is MN-major and for the A tile in the NT kernel only (SYRK K = 768 31.4 -> 32.2 TFLOP/s), while the
+    // NN / TN main loops are faster with independent address computations for A.
+    constexpr int KSTEP = NTHREADS / (ROWS / 2);
+    static_assert(NTHREADS % (ROWS / 2) == 0, "chunk rows must tile the thread count");
+    const int k0 = tid / (ROWS / 2), mc = tid % (ROWS / 2);
+    const double *gp = g + mc * 2 + (int64_t)k0 * ld;
+    double *sp = s + k0 * LD_MN + mc * 2;
+    const int64_t gstep = (int64_t)KSTEP * ld;
+#pragma unroll
+    for (int i = 0; i < CHUNKS / NTHREADS; ++i) {
+      cp_async16(sp, gp);
+      gp += gstep;
+      sp += KSTEP * LD_MN;
+    }
   } else {
-    // element (mn, k) at g[k + mn*ld]; ROWS rows of BK contiguous doubles
+    // element (mn, k) at g[k + mn*ld]; ROWS rows of BK contiguous doubles.  (The incremental form measured
+    // slower here: NN 4096^3 33.0 -> 32.6 TFLOP/s, so the K-major copy keeps independent address computations.)
 #pragma unroll
     for (int i = 0; i < CHUNKS / NTHREADS; ++i) {
       int c = tid + i * NTHREADS;
@@ -148,8 +167,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) dgemm_dmma_kernel(GemmArgs p, con
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < KT) {
-      load_slice<AK, BM, BK>(As + s * A_STAGE, Ag + s * a_step, p.lda, tid);
-      load_slice<BKM, BN, BK>(Bs + s * B_STAGE, Bg + s * b_step, p.ldb, tid);
+      load_slice<AK, BM, BK, (!AK && !BKM)>(As + s * A_STAGE, Ag + s * a_step, p.lda, tid);
+      load_slice<BKM, BN, BK, true>(Bs + s * B_STAGE, Bg + s * b_step, p.ldb, tid);
     }
     cp_async_commit();
   }
@@ -168,8 +187,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) dgemm_dmma_kernel(GemmArgs p, con
       int nk = kt + STAGES - 1;
       if (nk < KT) {
         int s = nk % STAGES;
-        load_slice<AK, BM, BK>(As + s * A_STAGE, Ag + (int64_t)nk * a_step, p.lda, tid);
-        load_slice<BKM, BN, BK>(Bs + s * B_STAGE, Bg + (int64_t)nk * b_step, p.ldb, tid);
+        load_slice<AK, BM, BK, (!AK && !BKM)>(As + s * A_STAGE, Ag + (int64_t)nk * a_step, p.lda, tid);
+        load_slice<BKM, BN, BK, true>(Bs + s * B_STAGE, Bg + (int64_t)nk * b_step, p.ldb, tid);
       }
       cp_async_commit();
     }
@@ -296,8 +315,8 @@ dgemm_dmma_persistent_kernel(GemmArgs p, const uint32_t *__restrict__ tiles, int
   if (cur.idx < 0) return;
   // slice 0 of the first tile
   if (cur.KT > 0) {
-    load_slice<AK, BM, BK>(As, cur.Ag, p.lda, tid);
-    load_slice<BKM, BN, BK>(Bs, cur.Bg, p.ldb, tid);
+    load_slice<AK, BM, BK, (!AK && !BKM)>(As, cur.Ag, p.lda, tid);
+    load_slice<BKM, BN, BK, true>(Bs, cur.Bg, p.ldb, tid);
   }
   cp_async_commit();
   unsigned gslice = 0;  // global slice counter: stage = gslice & 1
@@ -325,11 +344,11 @@ dgemm_dmma_persistent_kernel(GemmArgs p, const uint32_t *__restrict__ tiles, int
       {  // next slice: of this tile, or the first one of the next tile
         const int st = (gslice + 1) & 1;
         if (cs + 1 < cur.KT) {
-          load_slice<AK, BM, BK>(As + st * A_STAGE, cur.Ag + (int64_t)(cs + 1) * a_step, p.lda, tid);
-          load_slice<BKM, BN, BK>(Bs + st * B_STAGE, cur.Bg + (int64_t)(cs + 1) * b_step, p.ldb, tid);
+          load_slice<AK, BM, BK, (!AK && !BKM)>(As + st * A_STAGE, cur.Ag + (int64_t)(cs + 1) * a_step, p.lda, tid);
+          load_slice<BKM, BN, BK, true>(Bs + st * B_STAGE, cur.Bg + (int64_t)(cs + 1) * b_step, p.ldb, tid);
         } else if (nxt.idx >= 0 && nxt.KT > 0) {
-          load_slice<AK, BM, BK>(As + st * A_STAGE, nxt.Ag, p.lda, tid);
-          load_slice<BKM, BN, BK>(Bs + st * B_STAGE, nxt.Bg, p.ldb, tid);
+          load_slice<AK, BM, BK, (!AK && !BKM)>(As + st * A_STAGE, nxt.Ag, p.lda, tid);
+          load_slice<BKM, BN, BK, true>(Bs + st * B_STAGE, nxt.Bg, p.ldb, tid);
         }
         cp_async_commit();
       }
@@ -351,8 +370,8 @@ dgemm_dmma_persistent_kernel(GemmArgs p, const uint32_t *__restrict__ tiles, int
     }
     if (cur.KT == 0 && nxt.idx >= 0 && nxt.KT > 0) {
       // an empty k-range never started a pipeline slot for this tile: start the next tile's here
-      load_slice<AK, BM, BK>(As + (gslice & 1) * A_STAGE, nxt.Ag, p.lda, tid);
-      load_slice<BKM, BN, BK>(Bs + (gslice & 1) * B_STAGE, nxt.Bg, p.ldb, tid);
+      load_slice<AK, BM, BK, (!AK && !BKM)>(As + (gslice & 1) * A_STAGE, nxt.Ag, p.lda, tid);
+      load_slice<BKM, BN, BK, true>(Bs + (gslice & 1) * B_STAGE, nxt.Bg, p.ldb, tid);
       cp_async_commit();
     }
 
