@@ -184,7 +184,7 @@ __device__ __forceinline__ double composite_entry(const CompositeDev &c, const P
     for (int f = 0; f < FT; ++f) {
       if (f >= c.F) v[f] = 1.0;
       else if (kind_is_inner_product(c.cp[f].kind)) v[f] = cov_value_ip(c.cp[f], m.g);
-      else v[f] = cov_value_rt(c.cp[f], metric_of(c, m, f));
+      else v[f] = cov_value_shared(c.cp[f], metric_of(c, m, f));
     }
   } else {
     for (int f = 0; f < c.F; ++f) {

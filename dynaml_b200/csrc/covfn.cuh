@@ -101,6 +101,41 @@ __device__ __forceinline__ double cov_value_rt(const CovParams &cp, double dist)
   }
 }
 
+// One out-of-line copy of the kind switch for the composite kernels: their factor loops are unrolled, and four
+// inlined copies of every transcendental path made the kernels instruction-cache bound (ncu: `no_instruction`
+// was the second largest stall).  The covariance constants travel by value; Matern orders above 3 (coefficients
+// do not fit the four scalars) and the inner-product kinds take the inline paths.
+static __device__ __noinline__ double cov_value_call(int kind, double dist, double a2, double c1, double c2, int p, double k0,
+                                              double k1, double k2, double k3) {
+  switch (kind) {
+    case DGP_KERNEL_SE:
+    case DGP_KERNEL_RBF:
+    case DGP_KERNEL_ARD_SE: return a2 * exp(-dist * c1);
+    case DGP_KERNEL_MATERN: {
+      const double r = sqrt(dist), u = c2 * r;
+      double s = k0;
+      if (p >= 1) s = s * u + k1;
+      if (p >= 2) s = s * u + k2;
+      if (p >= 3) s = s * u + k3;
+      return exp(-c1 * r) * s;
+    }
+    case DGP_KERNEL_PERIODIC: {
+      const double sn = sin(dist * c1);
+      return a2 * exp(-c2 * sn * sn);
+    }
+    case DGP_KERNEL_CAUCHY: return 1.0 / fma(dist, c1, 1.0);
+    case DGP_KERNEL_LAPLACIAN: return exp(-dist * c1);
+    case DGP_KERNEL_RATQUAD: return pow(fma(dist, c1, 1.0), c2);
+    case DGP_KERNEL_TSTUDENT: return 1.0 / (1.0 + pow(sqrt(dist), c1));
+    default: return dist == 0.0 ? a2 : 0.0;
+  }
+}
+
+__device__ __forceinline__ double cov_value_shared(const CovParams &cp, double dist) {
+  if (cp.kind == DGP_KERNEL_MATERN && cp.p > 3) return cov_value<DGP_KERNEL_MATERN>(cp, dist);
+  return cov_value_call(cp.kind, dist, cp.a2, cp.c1, cp.c2, cp.p, cp.coef[0], cp.coef[1], cp.coef[2], cp.coef[3]);
+}
+
 // ---- kernel algebra: k = sum_t coef_t prod_f v_f^e_tf (DGP_KERNEL_COMPOSITE) -------------------------
 constexpr int MAXF = DGP_MAX_FACTORS, MAXT = DGP_MAX_TERMS, MAX_ARD_SLOTS = 4, MAX_ARD_DIM = 32;
 

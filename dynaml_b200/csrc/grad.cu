@@ -375,7 +375,7 @@ __device__ __forceinline__ void composite_pair(const CompositeDev &c, const Comp
     return id == 0 ? q.r2 : (id == 1 ? q.l1 : ard[id - 2]);
   };
   auto value_of = [&](int f) {
-    return kind_is_inner_product(c.cp[f].kind) ? cov_value_ip(c.cp[f], q) : cov_value_rt(c.cp[f], dist_of(f));
+    return kind_is_inner_product(c.cp[f].kind) ? cov_value_ip(c.cp[f], q) : cov_value_shared(c.cp[f], dist_of(f));
   };
   auto accumulate_factor = [&](int f) {
     const double dist = dist_of(f);
