@@ -453,7 +453,7 @@ class GPRegression {
                             noiseModel->hyper_parameters.end());
     refresh_state();
   }
-  ~GPRegression() {
+  virtual ~GPRegression() {
     if (model_) dgp_model_destroy(ctx_->get(), model_);
     if (data_) dgp_data_destroy(ctx_->get(), data_);
   }
@@ -559,7 +559,10 @@ class GPRegression {
   }
   double predict(const Vec &point) { return std::get<1>(predictionWithErrorBars({point}, 1)[0]); }
 
- private:
+ protected:
+  // hooks of GPBasisFuncRegression (explicit basis functions); no-ops for the plain model
+  virtual void after_data_create(dgp_data *, const std::vector<Vec> &) {}
+  virtual void before_predict(dgp_model *, const std::vector<Vec> &) {}
   static bool has(const std::vector<std::string> &v, const std::string &k) {
     return std::find(v.begin(), v.end(), k) != v.end();
   }
@@ -583,6 +586,7 @@ class GPRegression {
       std::vector<double> X = pack(pts);
       ctx_->check(dgp_data_create(ctx_->get(), X.data(), (int64_t)g.size(), (int32_t)pts[0].size(), DGP_ROW_MAJOR, y.data(),
                                   m.data(), &data_));
+      after_data_create(data_, pts);
     }
     return data_;
   }
@@ -610,6 +614,7 @@ class GPRegression {
       lo->assign((size_t)M, 0.0);
       hi->assign((size_t)M, 0.0);
     }
+    before_predict(m, test);
     const int32_t st = dgp_predict(ctx_->get(), m, Xs.data(), M, DGP_ROW_MAJOR, ms.data(), mu->data(),
                                    cov ? cov->data.data() : nullptr, M, lo ? lo->data() : nullptr,
                                    hi ? hi->data() : nullptr, sigma);
@@ -624,6 +629,69 @@ class GPRegression {
   dgp_data *data_ = nullptr;
   dgp_model *model_ = nullptr;
   bool caching_ = false;
+};
+
+// GPBasisFuncRegressionModel (CORE/models/gp/GPBasisFuncRegressionModel.scala:70-109): explicit basis functions for
+// the trend with a Gaussian prior N(b, covB) on their coefficients.  mean(x) = basisFunc(x).b and every kernel matrix
+// gains (lowB basisFunc(x)).(lowB basisFunc(y)), lowB = cholesky(covB) -- applied on the device as a rank-m update.
+// gradEnergy is the inherited one of the reference, which leaves the feature-map term out (:196-253).
+class GPBasisFuncRegression : public GPRegression {
+ public:
+  using Basis = std::function<Vec(const Vec &)>;
+  GPBasisFuncRegression(std::shared_ptr<LocalScalarKernel> cov, std::shared_ptr<DiracKernel> noise, Data trainingdata,
+                        Basis basisFunc, Vec b, const DenseMatrix &covB)
+      : GPRegression(std::move(cov), std::move(noise), std::move(trainingdata), make_mean(basisFunc, b)),
+        basis_(std::move(basisFunc)), m_((int)b.size()) {
+    if (covB.rows != m_ || covB.cols != m_) throw std::invalid_argument("basis_param_prior: covariance must be m x m");
+    low_.assign((size_t)m_ * m_, 0.0);  // lower Cholesky factor, row-major
+    for (int j = 0; j < m_; ++j)
+      for (int i = j; i < m_; ++i) {
+        double s = covB(i, j);
+        for (int k = 0; k < j; ++k) s -= low_[(size_t)i * m_ + k] * low_[(size_t)j * m_ + k];
+        if (i == j) {
+          if (!(s > 0.0)) throw std::invalid_argument("basis_param_prior: covariance is not positive definite");
+          low_[(size_t)i * m_ + j] = std::sqrt(s);
+        } else {
+          low_[(size_t)i * m_ + j] = s / low_[(size_t)j * m_ + j];
+        }
+      }
+  }
+
+ protected:
+  void after_data_create(dgp_data *d, const std::vector<Vec> &pts) override {
+    std::vector<double> psi = features(pts);
+    ctx_->check(dgp_data_set_basis(ctx_->get(), d, psi.data(), m_));
+  }
+  void before_predict(dgp_model *m, const std::vector<Vec> &test) override {
+    std::vector<double> psi = features(test);
+    ctx_->check(dgp_model_set_test_basis(ctx_->get(), m, psi.data(), (int64_t)test.size(), m_));
+  }
+
+ private:
+  static Mean make_mean(Basis f, Vec b) {
+    return [f, b](const Vec &x) {
+      Vec phi = f(x);
+      double s = 0.0;
+      for (size_t i = 0; i < b.size(); ++i) s += phi[i] * b[i];
+      return s;
+    };
+  }
+  std::vector<double> features(const std::vector<Vec> &pts) const {  // row i = (lowB basisFunc(x_i))'
+    std::vector<double> psi(pts.size() * (size_t)m_);
+    for (size_t p = 0; p < pts.size(); ++p) {
+      Vec phi = basis_(pts[p]);
+      if ((int)phi.size() != m_) throw std::invalid_argument("basisFunc must return one feature per trend coefficient");
+      for (int i = 0; i < m_; ++i) {
+        double s = 0.0;
+        for (int k = 0; k <= i; ++k) s += low_[(size_t)i * m_ + k] * phi[(size_t)k];
+        psi[p * (size_t)m_ + i] = s;
+      }
+    }
+    return psi;
+  }
+  Basis basis_;
+  int m_;
+  std::vector<double> low_;
 };
 
 // ---- tuners ------------------------------------------------------------------------------------------------

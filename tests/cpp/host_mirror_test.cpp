@@ -120,6 +120,18 @@ int main(int argc, char **argv) {
       MultGaussianPRV cpost = cgp.predictiveDistribution(test);
       print_vec("composite_mu", cpost.mu);
     }
+    // ---- GPBasisFuncRegressionModel: trend 0.3 + 0.5 x0 - 0.2 x1 x2 with prior covariance diag(0.5, 0.2, 0.3) + 0.02
+    {
+      auto basis = [](const Vec &x) { return Vec{1.0, x[0], x[1] * x[2]}; };
+      DenseMatrix covB;
+      covB.rows = covB.cols = 3;
+      covB.data = {0.52, 0.02, 0.02, 0.02, 0.22, 0.02, 0.02, 0.02, 0.32};
+      GPBasisFuncRegression bgp(std::make_shared<SEKernel>(1.6, 1.1), std::make_shared<DiracKernel>(0.3), data, basis,
+                                Vec{0.3, 0.5, -0.2}, covB);
+      std::printf("\"basis_energy\": %.17g,\n", bgp.energy(bgp._current_state()));
+      MultGaussianPRV bpost = bgp.predictiveDistribution(test);
+      print_vec("basis_mu", bpost.mu);
+    }
     // ---- unsupported / bad arguments surface as exceptions, never as a CPU fallback
     bool threw = false;
     try {

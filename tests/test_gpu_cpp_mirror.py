@@ -88,3 +88,16 @@ def test_cpp_kernel_algebra(result):
     assert np.abs(np.array(out["composite_grad"]) - ref).max() <= TOL * np.abs(ref).max()
     mu, _ = orc.predictive(ok, 0.3, X, y, Xs)
     assert np.abs(np.array(out["composite_mu"]) - mu).max() <= TOL * np.abs(mu).max()
+
+
+def test_cpp_basis_function_model(result):
+    out, (X, y, Xs) = result
+    basis = lambda x: np.array([1.0, x[0], x[1] * x[2]])  # noqa: E731
+    b = np.array([0.3, 0.5, -0.2])
+    covB = np.diag([0.5, 0.2, 0.3]) + 0.02
+    ok = orc.WithFeatureMap(orc.Kernel("se", {"bandwidth": 1.6, "amplitude": 1.1}), basis, covB)
+    mean = np.array([basis(x) @ b for x in X])
+    mean_s = np.array([basis(x) @ b for x in Xs])
+    assert out["basis_energy"] == pytest.approx(orc.energy(ok, 0.3, X, y, mean), rel=TOL)
+    mu, _ = orc.predictive(ok, 0.3, X, y, Xs, mean, mean_s)
+    assert np.abs(np.array(out["basis_mu"]) - mu).max() <= TOL * np.abs(mu).max()
