@@ -308,3 +308,24 @@ def test_tensor_kernel_range_errors(ctx):
             ctx.energy(data, poly._spec(noise=0.1))                                # inner-product kernel on a slice
     finally:
         ctx.data_destroy(data)
+
+
+def test_general_noise_with_ard_covariance_cross_spec():
+    """The covariance-only cross spec of an ARD-SE kernel keeps its own pre-scaled copy of the training points."""
+    import scipy.linalg as sla
+    X, y, Xs = orc.synthetic(200, 3, seed=95, m=25)
+    band = [1.5, 2.5, 2.0]
+    cov = dg.MahalanobisKernel(band, 1.2)
+    ocov = orc.Kernel("ard", {"MahalanobisAmplitude": 1.2, **{f"MahalanobisBandwidth_{i}": b for i, b in enumerate(band)}})
+    noise = dg.CauchyKernel(0.3) * 0.15 + dg.DiracKernel(0.25)
+    onoise = orc.Sum(orc.Scaled(orc.Kernel("cauchy", {"sigma": 0.3}), 0.15), orc.dirac(0.25))
+    model = dg.GPRegression(cov, noise, list(zip(X, y)))
+    K = orc.build_kernel_matrix(ocov, X) + orc.build_kernel_matrix(onoise, X)
+    assert model.energy(model._current_state) == pytest.approx(orc.log_likelihood(y, K), rel=TOL)
+    L = sla.cholesky(K, lower=True)
+    Ks, Kss = orc.cross_kernel_matrix(ocov, X, Xs), orc.build_kernel_matrix(ocov, Xs)
+    alpha = sla.cho_solve((L, True), y)
+    v = sla.solve_triangular(L, Ks, lower=True)
+    post = model.predictiveDistribution(Xs)
+    assert np.abs(post.mu - Ks.T @ alpha).max() <= TOL * np.abs(Ks.T @ alpha).max()
+    assert np.abs(post.covariance - (Kss - v.T @ v)).max() <= TOL * np.abs(Kss).max()
