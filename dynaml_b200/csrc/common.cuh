@@ -34,6 +34,7 @@ struct Ctx {
   cudaStream_t panel = nullptr;   // high-priority stream (leaf factorisations, panels) for look-ahead
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   std::vector<cudaEvent_t> ev_pool;  // look-ahead fork/join events
+  std::vector<cudaEvent_t> ev_misc;  // fork/join of the solves running under the triangular inverse
   cudaEvent_t tev[16];               // phase timing events
   std::string err;
   std::map<std::string, std::pair<void *, size_t>> arena;
