@@ -8,6 +8,8 @@
   synthetic.npz -- seeded synthetic problems for every kernel: energy, gradient (both
                    grad modes for ARD), posterior mean / covariance.
   kats.json     -- the reference's own known-answer values for this path, with file:line.
+  extended.npz  -- the rows of SURVEY 8(f): kernel algebra, tensor kernels, basis-function GP, extended skew GP,
+                   Kronecker multi-output GP and the Student-t process on one seeded problem (oracle values).
 """
 import json
 import sys
@@ -106,8 +108,53 @@ def kats():
     (HERE / "kats.json").write_text(json.dumps(k, indent=1))
 
 
+def extended_basis(x):
+    return np.array([1.0, x[0], x[1] * x[2]])
+
+
+EXT_B = np.array([0.3, 0.5, -0.2])
+EXT_COVB = np.diag([0.5, 0.2, 0.3]) + 0.02
+
+
+def extended_kernels():
+    se = lambda: orc.Kernel("se", {"bandwidth": 1.4, "amplitude": 1.1})  # noqa: E731
+    cau = lambda: orc.Kernel("cauchy", {"sigma": 2.0})  # noqa: E731
+    mat = lambda: orc.Kernel("matern", {"p": 2.0, "l": 1.7})  # noqa: E731
+    lap = lambda: orc.Kernel("laplacian", {"beta": 2.0})  # noqa: E731
+    return {
+        "algebra": orc.Sum(orc.Prod(se(), cau()), orc.Scaled(mat(), 0.6)),          # se * cauchy + matern * 0.6
+        "tensor": orc.Prod(orc.Sliced(se(), 0, 2), orc.Sliced(lap(), 2)),           # se (x) laplacian, split 2
+    }
+
+
+def extended():
+    X, y, Xs = orc.synthetic(220, 4, seed=77, m=12)
+    noise = 0.3
+    out = {"X": X, "y": y, "Xs": Xs, "noise": noise}
+    for name, k in extended_kernels().items():
+        out[f"{name}_energy"] = orc.energy(k, noise, X, y)
+        g = orc.grad_energy(k, noise, X, y)
+        out[f"{name}_grad"] = np.array(list(g.values()))
+        mu, cov = orc.predictive(k, noise, X, y, Xs)
+        out[f"{name}_mu"], out[f"{name}_cov"] = mu, cov
+    se = orc.Kernel("se", {"bandwidth": 1.6, "amplitude": 1.1})
+    mean = np.array([extended_basis(x) @ EXT_B for x in X])
+    out["basis_energy"] = orc.energy(orc.WithFeatureMap(se, extended_basis, EXT_COVB), noise, X, y, mean)
+    out["esgp_energy"] = orc.esgp_energy(se, noise, X, y, 0.6, 0.3)
+    mu, cov, skew, cutoff = orc.esgp_predictive(se, noise, X, y, Xs, 0.6, 0.3)
+    out["esgp_mu"], out["esgp_skew"], out["esgp_cutoff"] = mu, skew, cutoff
+    rng = np.random.default_rng(78)
+    Y = np.column_stack([y, np.cos(X[:, 0]) + 0.1 * rng.standard_normal(len(y)), 0.5 * y + 0.2 * rng.standard_normal(len(y))])
+    out["Y"] = Y
+    out["mogp_energy"] = orc.kronecker_mogp_energy(orc.Kernel("matern", {"p": 2.0, "l": 1.7}), 0.4,
+                                                   orc.Kernel("cauchy", {"sigma": 2.0}), X, Y)
+    out["stp_energy"] = orc.stp_energy(4.5, se, noise, X, y)
+    np.savez_compressed(HERE / "extended.npz", **out)
+
+
 if __name__ == "__main__":
     housing()
     synthetic()
     kats()
+    extended()
     print("golden fixtures written to", HERE)

@@ -194,6 +194,25 @@ def test_golden_fixtures_are_current():
     assert orc.energy(k2, float(s["noise"]), s["X"], s["y"]) == pytest.approx(float(s["matern2_energy"]), rel=1e-12)
 
 
+def test_extended_fixture_is_current():
+    """tests/golden/extended.npz (the SURVEY 8f rows) is what the oracle produces today."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", GOLD / "make_golden.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    z = np.load(GOLD / "extended.npz")
+    X, y, noise = z["X"], z["y"], float(z["noise"])
+    for name, k in mg.extended_kernels().items():
+        assert orc.energy(k, noise, X, y) == pytest.approx(float(z[f"{name}_energy"]), rel=1e-12)
+    se = orc.Kernel("se", {"bandwidth": 1.6, "amplitude": 1.1})
+    assert orc.esgp_energy(se, noise, X, y, 0.6, 0.3) == pytest.approx(float(z["esgp_energy"]), rel=1e-12)
+    assert orc.kronecker_mogp_energy(orc.Kernel("matern", {"p": 2.0, "l": 1.7}), 0.4, orc.Kernel("cauchy", {"sigma": 2.0}),
+                                     X, z["Y"]) == pytest.approx(float(z["mogp_energy"]), rel=1e-12)
+    assert orc.stp_energy(4.5, se, noise, X, y) == pytest.approx(float(z["stp_energy"]), rel=1e-12)
+    # lambda = 0 collapses the extended skew GP onto the GP (SkewGaussian.scala:218-242 with alpha = 0)
+    assert orc.esgp_energy(se, noise, X, y, 0.0, 0.3) == pytest.approx(orc.energy(se, noise, X, y), rel=1e-13)
+
+
 def test_non_pd_gives_inf_and_nan():
     X = np.array([[0.0], [0.0], [1.0]])  # duplicate point, no noise: singular K
     y = np.array([1.0, 2.0, 3.0])
