@@ -488,6 +488,13 @@ def test_c3_size_energy_properties(ctx):
         finally:
             ctx.dist_finalize()
         assert ed == pytest.approx(e0, rel=1e-11)
+        # (2b) the lean Gram assembly (auto) against the exact-difference kernel at full size
+        ctx.set_option("assembly", 1)
+        try:
+            e_exact = ctx.energy(data, spec)
+        finally:
+            ctx.set_option("assembly", 0)
+        assert e_exact == pytest.approx(e0, rel=1e-12)
         c = 1.75
         q1, l1 = ctx.energy_terms(data, dg.SEKernel(2.0 * math.sqrt(d), 1.0)._spec(noise=0.1))
         q2, l2 = ctx.energy_terms(data, dg.SEKernel(2.0 * math.sqrt(d), c)._spec(noise=0.1 * c * c))
