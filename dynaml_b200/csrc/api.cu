@@ -699,6 +699,17 @@ int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
     ctx->lookahead = value != 0;
   } else if (!strcmp(key, "gemm_persistent")) {
     ctx->gemm_persistent = value != 0;
+  } else if (!strcmp(key, "gemm_variant")) {
+    if (value != 2 && value != 4) return ctx->fail(DGP_ERR_ARG, "gemm_variant must be 2 (cp.async) or 4 (bulk copy)");
+    ctx->gemm_variant = (int)value;
+  } else if (!strcmp(key, "gemm_v4_bk32_mask")) {
+    if (value < 0 || value > 15) return ctx->fail(DGP_ERR_ARG, "gemm_v4_bk32_mask must be in 0..15");
+    ctx->gemm_v4_bk32_mask = (int)value;
+  } else if (!strcmp(key, "gemm_v4_mask")) {
+    if (value < 0 || value > 15) return ctx->fail(DGP_ERR_ARG, "gemm_v4_mask must be in 0..15");
+    ctx->gemm_v4_mask = (int)value;
+  } else if (!strcmp(key, "gemm_no_prefetch")) {
+    ctx->gemm_no_prefetch = value != 0;
   } else if (!strcmp(key, "gemm_bk")) {
     if (value != 16 && value != 32) return ctx->fail(DGP_ERR_ARG, "gemm_bk must be 16 or 32");
     ctx->gemm_bk = (int)value;

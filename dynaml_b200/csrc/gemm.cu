@@ -67,10 +67,9 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 
 // Copy one ROWS x BK operand slice into a stage (ROWS = 128 for A, 64 for B).  g points at the
 // slice origin.
-template <bool KMAJOR, int ROWS, int BK, bool INC = false>
+template <bool KMAJOR, int ROWS, int BK, bool INC = false, int LD_MN = ROWS + 4>
 __device__ __forceinline__ void load_slice(double *s, const double *g, int64_t ld, int tid) {
   constexpr int CHUNKS = ROWS * BK / 2;  // 16-byte chunks
-  constexpr int LD_MN = ROWS + 4;
   constexpr int LDS_K = BK + 4;
   // Chunk c = tid + i * NTHREADS: consecutive i advance the slow index by a compile-time step, so every address is
   // the previous one plus a loop-invariant stride (one 64-bit add per chunk instead of a multiply-add chain).
@@ -410,6 +409,291 @@ dgemm_dmma_persistent_kernel(GemmArgs p, const uint32_t *__restrict__ tiles, int
   cp_async_wait<0>();
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Bulk-copy version of the kernel (gemm_variant 4, the default): operands moved by the bulk-copy (TMA) engine
+// through an mbarrier pipeline, 128-bit fragment loads, 16-byte read-modify-write epilogue.
+//
+// Knock-out timings of the cp.async kernel above (SYRK, K = 3072, 34.2 TFLOP/s): without the per-slice
+// __syncthreads 35.8, without the cp.async copies (12 LDGSTS + address arithmetic per thread and slice) 36.5,
+// without both 36.8 = the DMMA peak; without the fragment loads 35.3.  The LSU-side copy instructions and the
+// block-wide barrier cost ~8 % of the tensor pipe, and both go away here: a ninth warp issues, from one elected
+// lane with warp-uniform addresses, one `cp.async.bulk` per operand row (rows are contiguous in global memory and
+// padded in shared memory, so no tensor map is needed) and the eight DMMA warps only wait on a `full` mbarrier,
+// multiply, and arrive on an `empty` one -- no warp ever waits for another except through data it needs.
+// K-slices of 16, four stages.
+//
+// Fragment mapping.  The m8n8k4 fragment of lane (g, t) is one element per 8-row block, i.e. one LDS.64 per
+// fragment element in the kernel above.  Any permutation of the rows of the warp's 32x32 sub-tile is a valid
+// assignment as long as the epilogue uses the same one, so here fragment i of lane g stands for row
+// 16*(i>>1) + 2*g + (i&1): rows 2g and 2g+1 are adjacent in an MN-major stage and come from ONE LDS.128
+// (rows padded to 132 / 68 doubles = 4 mod 16 keep each quarter-warp on 8 distinct 16-byte bank groups), and in
+// the epilogue they are adjacent in the column-major C (16-byte loads / stores, 128 contiguous bytes per column
+// and warp instruction).  K-major stages keep 64-bit loads; their rows are padded to 18 doubles, which with this
+// row assignment puts each half-warp on 16 distinct banks.
+// ---------------------------------------------------------------------------------------------
+template <bool AK, bool BKM, int BK_>
+struct CfgB {
+  static constexpr int BK = BK_;        // 16 with four stages, or 32 with two (half as many copies per flop)
+  static constexpr int LDS_K = BK + 2;  // 18 / 34 = 2 mod 16
+  static constexpr int LDA = BM + 4;
+  static constexpr int LDB = BN + 4;
+  static constexpr int A_STAGE = AK ? BM * LDS_K : BK * LDA;
+  static constexpr int B_STAGE = BKM ? BN * LDS_K : BK * LDB;
+  static constexpr int STAGES = BK == 16 ? 4 : 2;
+  static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double) + 64;  // + 2 x STAGES mbarriers
+  static constexpr uint32_t STAGE_BYTES = (BM + BN) * BK * sizeof(double);  // bytes landed per stage
+  static_assert(2 * (SMEM + 1024) <= 227 * 1024, "two CTAs per SM");
+};
+constexpr int NTHREADS_B = NTHREADS + 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_copy(uint32_t dst, const double *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// One 16-slice of DMMAs.  as / bs point at the lane's fragment origin inside the stage; `dep` folds every
+// fragment register that was loaded (see the `empty` arrival in the kernel).
+template <bool AK, bool BKM, int BK>
+__device__ __forceinline__ void mma_slice_v4(double (&acc)[4][4][2], const double *as, const double *bs, int &dep) {
+  using C_ = CfgB<AK, BKM, BK>;
+  constexpr int LDS_K = C_::LDS_K, LDA = C_::LDA, LDB = C_::LDB;
+#pragma unroll
+  for (int kk = 0; kk < BK / 4; ++kk) {
+    double a[4], b[4];
+    if constexpr (AK) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = as[((i >> 1) * 16 + (i & 1)) * LDS_K + 4 * kk];
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const double2 v = *reinterpret_cast<const double2 *>(as + kk * 4 * LDA + 16 * h);
+        a[2 * h] = v.x;  a[2 * h + 1] = v.y;
+      }
+    }
+    if constexpr (BKM) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = bs[((j >> 1) * 16 + (j & 1)) * LDS_K + 4 * kk];
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const double2 w = *reinterpret_cast<const double2 *>(bs + kk * 4 * LDB + 16 * h);
+        b[2 * h] = w.x;  b[2 * h + 1] = w.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dep ^= __double2hiint(a[i]) ^ __double2hiint(b[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
+// acc[i][j][r] is C(m0 + wm*32 + 16*(i>>1) + 2g + (i&1), n0 + wn*32 + 16*(j>>1) + 4t + 2r + (j&1));
+// Cw points at C(m0 + wm*32 + 2g, n0 + wn*32 + 4t).
+__device__ __forceinline__ void epilogue_v4(const double (&acc)[4][4][2], double *Cw, int64_t ldc, double alpha,
+                                            double beta) {
+  if (beta != 0.0) {
+#pragma unroll
+    for (int jp = 0; jp < 2; ++jp) {  // column block of 16
+      double2 old[2][2][2];           // [j&1][r][h]
+#pragma unroll
+      for (int jl = 0; jl < 2; ++jl)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            old[jl][r][h] = *reinterpret_cast<const double2 *>(Cw + 16 * h + (int64_t)(16 * jp + 2 * r + jl) * ldc);
+#pragma unroll
+      for (int jl = 0; jl < 2; ++jl)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            double2 o = old[jl][r][h];
+            o.x = alpha * acc[2 * h][2 * jp + jl][r] + beta * o.x;
+            o.y = alpha * acc[2 * h + 1][2 * jp + jl][r] + beta * o.y;
+            *reinterpret_cast<double2 *>(Cw + 16 * h + (int64_t)(16 * jp + 2 * r + jl) * ldc) = o;
+          }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          double2 o;
+          o.x = alpha * acc[2 * h][j][r];
+          o.y = alpha * acc[2 * h + 1][j][r];
+          *reinterpret_cast<double2 *>(Cw + 16 * h + (int64_t)(16 * (j >> 1) + 2 * r + (j & 1)) * ldc) = o;
+        }
+  }
+}
+
+template <bool AK, bool BKM, int BK>
+__global__ void __launch_bounds__(NTHREADS_B, 2) dgemm_dmma_v4_kernel(GemmArgs p, const uint32_t *__restrict__ tiles) {
+  extern __shared__ __align__(16) double smem[];
+  using C_ = CfgB<AK, BKM, BK>;
+  constexpr int A_STAGE = C_::A_STAGE, B_STAGE = C_::B_STAGE, LDS_K = C_::LDS_K, STAGES = C_::STAGES;
+  constexpr int LDA = C_::LDA, LDB = C_::LDB;
+  double *As = smem;
+  double *Bs = smem + STAGES * A_STAGE;
+  const uint32_t bars = smem_u32(smem + STAGES * (A_STAGE + B_STAGE));  // full[s] at bars + 8 s, empty[s] after them
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler as well
+
+  const uint32_t tile = tiles[blockIdx.x];
+  const int m0 = (int)(tile >> 16) * BM, n0 = (int)(tile & 0xffffu) * BN;
+
+  if (p.bc_T > 0) {
+    const int64_t grow = ((int64_t)(p.bc_row0 + m0 / p.bc_T) * p.bc_Pr + p.bc_pr) * p.bc_T + m0 % p.bc_T;
+    const int64_t gcol = ((int64_t)(p.bc_col0 + n0 / p.bc_T) * p.bc_Pc + p.bc_pc) * p.bc_T + n0 % p.bc_T;
+    if (gcol > grow + BM - 1) return;  // uniform across the CTA, before any barrier
+  }
+
+  int k_lo = 0, k_hi = p.K;
+  if (p.kmode == K_GE_COL) k_lo = (n0 / 64) * 64;
+  else if (p.kmode == K_LT_ROWEND) k_hi = min(p.K, m0 + BM);
+  else if (p.kmode == K_GE_ROW) k_lo = m0;
+  const int KT = (k_hi - k_lo) / BK;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bars + 8 * s, 1);             // full: the producer's expect_tx arrival + the bytes
+      mbar_init(bars + 8 * (STAGES + s), 8);  // empty: one arrival per DMMA warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  double *C = p.C + (int64_t)blockIdx.y * p.strideC;
+
+  if (warp == 8) {
+    // ---- producer warp --------------------------------------------------------------------------------
+    if (p.beta != 0.0 && !p.no_prefetch) {  // pull the C tile towards L2 for the read-modify-write epilogue
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        int c = lane + i * 32;  // 512 lines of 128 B: 8 per column
+        int col = c >> 3, seg = c & 7;
+        const double *ptr = C + m0 + seg * 16 + (int64_t)(n0 + col) * p.ldc;
+        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ptr));
+      }
+    }
+    if (elect_one()) {
+      // One bulk copy per operand row and slice.  MN-major operands have BK rows (one per k) of BM / BN doubles,
+      // K-major ones BM / BN rows of BK doubles; every address is the previous one plus a uniform stride.
+      constexpr int A_ROWS = AK ? BM : BK, B_ROWS = BKM ? BN : BK;
+      constexpr uint32_t A_BYTES = (AK ? BK : BM) * 8, B_BYTES = (BKM ? BK : BN) * 8;
+      constexpr uint32_t A_LD = (AK ? LDS_K : LDA) * 8, B_LD = (BKM ? LDS_K : LDB) * 8;  // bytes
+      const double *A = p.A + (int64_t)blockIdx.y * p.strideA;
+      const double *B = p.B + (int64_t)blockIdx.y * p.strideB;
+      const double *ag = AK ? (A + k_lo + (int64_t)m0 * p.lda) : (A + m0 + (int64_t)k_lo * p.lda);
+      const double *bg = BKM ? (B + k_lo + (int64_t)n0 * p.ldb) : (B + n0 + (int64_t)k_lo * p.ldb);
+      // after the rows of one slice: MN-major advances by BK columns (the row loop already did), K-major by BK
+      // doubles from the slice origin
+      const int64_t a_back = AK ? (int64_t)BK - (int64_t)A_ROWS * p.lda : 0;
+      const int64_t b_back = BKM ? (int64_t)BK - (int64_t)B_ROWS * p.ldb : 0;
+      const uint32_t As_u = smem_u32(As), Bs_u = smem_u32(Bs);
+      int s = 0;
+      uint32_t parity = 1;  // of the `empty` phase a refill waits for: phase -1 counts as complete
+      for (int i = 0; i < KT; ++i) {
+        const uint32_t full = bars + 8 * s;
+        if (i >= STAGES) mbar_wait(bars + 8 * (STAGES + s), parity);
+        mbar_expect_tx(full, C_::STAGE_BYTES);
+        uint32_t dst = As_u + (uint32_t)(s * A_STAGE) * 8;
+#pragma unroll 8
+        for (int r = 0; r < A_ROWS; ++r) {
+          bulk_copy(dst, ag, A_BYTES, full);
+          dst += A_LD;
+          ag += p.lda;
+        }
+        ag += a_back;
+        dst = Bs_u + (uint32_t)(s * B_STAGE) * 8;
+#pragma unroll 8
+        for (int r = 0; r < B_ROWS; ++r) {
+          bulk_copy(dst, bg, B_BYTES, full);
+          dst += B_LD;
+          bg += p.ldb;
+        }
+        bg += b_back;
+        if (++s == STAGES) { s = 0; parity ^= 1; }
+      }
+    }
+    return;
+  }
+
+  // ---- DMMA warps ---------------------------------------------------------------------------------------
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 3, wn = warp >> 2;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int a_off = AK ? ((wm * 32 + 2 * g) * LDS_K + t) : (t * LDA + wm * 32 + 2 * g);
+  const int b_off = BKM ? ((wn * 32 + 2 * g) * LDS_K + t) : (t * LDB + wn * 32 + 2 * g);
+
+  int s = 0;
+  uint32_t phase = 0;
+  const int zero = p.zero;
+  for (int kt = 0; kt < KT; ++kt) {
+    mbar_wait(bars + 8 * s, phase);
+    int dep = 0;
+    mma_slice_v4<AK, BKM, BK>(acc, As + s * A_STAGE + a_off, Bs + s * B_STAGE + b_off, dep);
+    __syncwarp();
+    // An `empty` arrival hands the stage back to the bulk-copy engine (async proxy), and the arrival instruction is not
+    // ordered behind shared-memory loads that have only been *issued*: with a second CTA's global-memory epilogue
+    // backing up the load/store pipe, the refill was observed to land before queued fragment loads of the released
+    // stage had read it (rows of one warp wrong by one slice's worth).  `dep` folds every fragment register of the
+    // slice and p.zero is a run-time 0 the compiler cannot see through, so the arrival's address depends on the loads.
+    if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s) + (uint32_t)(dep & zero));
+    if (++s == STAGES) { s = 0; phase ^= 1; }
+  }
+
+  double *Cw = C + m0 + wm * 32 + 2 * g + (int64_t)(n0 + wn * 32 + 4 * t) * p.ldc;
+  epilogue_v4(acc, Cw, p.ldc, p.alpha, p.beta);
+}
+
 template <bool AK, bool BKM>
 cudaError_t opt_in() {
   cudaError_t e = cudaFuncSetAttribute(dgemm_dmma_kernel<AK, BKM, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -418,13 +702,24 @@ cudaError_t opt_in() {
   e = cudaFuncSetAttribute(dgemm_dmma_kernel<AK, BKM, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)Cfg<AK, BKM, 32>::SMEM);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(dgemm_dmma_persistent_kernel<AK, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)Cfg<AK, BKM, 32>::SMEM);
+  e = cudaFuncSetAttribute(dgemm_dmma_persistent_kernel<AK, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)Cfg<AK, BKM, 32>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(dgemm_dmma_v4_kernel<AK, BKM, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)CfgB<AK, BKM, 16>::SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dgemm_dmma_v4_kernel<AK, BKM, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)CfgB<AK, BKM, 32>::SMEM);
 }
 
 template <bool AK, bool BKM>
-void launch(cudaStream_t stream, const GemmArgs &a, dim3 grid, const uint32_t *tiles, int bk, int persistent_ctas) {
-  if (bk == 32 && persistent_ctas > 0) {
+void launch(cudaStream_t stream, const GemmArgs &a, dim3 grid, const uint32_t *tiles, int bk, int persistent_ctas,
+            int variant) {
+  if (variant == 4 && bk == 32) {
+    dgemm_dmma_v4_kernel<AK, BKM, 32><<<grid, NTHREADS_B, CfgB<AK, BKM, 32>::SMEM, stream>>>(a, tiles);
+  } else if (variant == 4) {
+    dgemm_dmma_v4_kernel<AK, BKM, 16><<<grid, NTHREADS_B, CfgB<AK, BKM, 16>::SMEM, stream>>>(a, tiles);
+  } else if (bk == 32 && persistent_ctas > 0) {
     const int64_t ntiles = grid.x;
     dim3 pg((unsigned)std::min<int64_t>(ntiles, persistent_ctas), grid.y, 1);
     dgemm_dmma_persistent_kernel<AK, BKM><<<pg, NTHREADS, Cfg<AK, BKM, 32>::SMEM, stream>>>(a, tiles, ntiles);
@@ -487,12 +782,14 @@ int32_t gemm_init(Ctx *ctx) {
   return DGP_OK;
 }
 
-int32_t gemm(Ctx *ctx, cudaStream_t stream, const GemmArgs &a) {
+int32_t gemm(Ctx *ctx, cudaStream_t stream, const GemmArgs &a_in) {
+  GemmArgs a = a_in;
+  a.no_prefetch = ctx->gemm_no_prefetch;
   if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return DGP_OK;
   if (a.M % BM || a.N % BN || a.K % 16 || a.K < 0)
     return ctx->fail(DGP_ERR_SHAPE, "gemm: M=%d N=%d K=%d must be multiples of %d/%d/16", a.M, a.N, a.K, BM, BN);
   // 32-wide slices need every k-range to be a multiple of 32 (triangular ranges are multiples of 64)
-  const int bk = (ctx->gemm_bk == 32 && a.K % 32 == 0) ? 32 : 16;
+  int bk = (ctx->gemm_bk == 32 && a.K % 32 == 0) ? 32 : 16;
   // persistent grid: two CTAs per SM, shared among the batch entries
   const int pc = ctx->gemm_persistent ? std::max(1, 2 * ctx->sm_count / std::max(1, a.batch)) : 0;
   if ((a.lda & 1) || (a.ldb & 1) || ((uintptr_t)a.A & 15) || ((uintptr_t)a.B & 15))
@@ -505,10 +802,18 @@ int32_t gemm(Ctx *ctx, cudaStream_t stream, const GemmArgs &a) {
   DGP_TRY(get_tiles(ctx, mt, nt, a.lower_only != 0, a.reverse != 0, &tt));
   if (tt.count == 0) return DGP_OK;
   dim3 grid((unsigned)tt.count, (unsigned)a.batch, 1);
-  if (!a.a_kmajor && !a.b_kmajor) launch<false, false>(stream, a, grid, tt.dev, bk, pc);
-  else if (!a.a_kmajor && a.b_kmajor) launch<false, true>(stream, a, grid, tt.dev, bk, pc);
-  else if (a.a_kmajor && !a.b_kmajor) launch<true, false>(stream, a, grid, tt.dev, bk, pc);
-  else launch<true, true>(stream, a, grid, tt.dev, bk, pc);
+  // version 3 (128-bit fragment loads / 16-byte epilogue) needs a 16-byte aligned C with an even leading dimension
+  // The bulk-copy kernel needs a 16-byte aligned C with an even leading dimension (16-byte epilogue); gemm_v4_mask
+  // selects the operand layouts it is used for (bit 2*a_kmajor + b_kmajor), the cp.async kernel takes the rest.
+  const bool v4_layout = (ctx->gemm_v4_mask >> (2 * (a.a_kmajor ? 1 : 0) + (a.b_kmajor ? 1 : 0))) & 1;
+  const int variant =
+      (ctx->gemm_variant == 4 && v4_layout && !(a.ldc & 1) && !((uintptr_t)a.C & 15) && !(a.strideC & 1)) ? 4 : 2;
+  const int layout = 2 * (a.a_kmajor ? 1 : 0) + (a.b_kmajor ? 1 : 0);
+  if (variant == 4) bk = (((ctx->gemm_v4_bk32_mask >> layout) & 1) && a.K % 32 == 0) ? 32 : 16;
+  if (!a.a_kmajor && !a.b_kmajor) launch<false, false>(stream, a, grid, tt.dev, bk, pc, variant);
+  else if (!a.a_kmajor && a.b_kmajor) launch<false, true>(stream, a, grid, tt.dev, bk, pc, variant);
+  else if (a.a_kmajor && !a.b_kmajor) launch<true, false>(stream, a, grid, tt.dev, bk, pc, variant);
+  else launch<true, true>(stream, a, grid, tt.dev, bk, pc, variant);
   ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;

@@ -32,6 +32,8 @@ struct GemmArgs {
   int kmode = K_FULL;
   int reverse = 0;     // launch heavy tiles first when the k-range grows with the tile index
   int batch = 1;
+  int no_prefetch = 0; // testing: skip the L2 prefetch of the C tile (makes the epilogue slow; stresses stage hand-over)
+  int zero = 0;        // always 0: a value the compiler cannot fold (see the `empty` arrival in gemm.cu)
   int64_t strideA = 0, strideB = 0, strideC = 0;
   // Optional 2D block-cyclic mask (dist.cu): C is this rank's local part of a distributed
   // lower-triangular update, stored as T x T tiles; local tile (li, lj) is global tile
