@@ -12,8 +12,8 @@ for (n, d) in [(8192, 8), (16384, 8), (32768, 16)]:
     X, y, _ = orc.synthetic(n, d, 0)
     data = ctx.data_create(X, y)
     spec = dg.GenericMaternKernel(math.sqrt(d), 2)._spec(noise=0.1)
-    for nb in (256, 384, 512, 768):
-        for la in (1, 0):
+    for nb in (256, 384, 512, 768, 1024):
+        for la in ((1, 0) if len(sys.argv) > 1 else (1,)):  # any argument: also time look-ahead off
             ctx.set_option("nb", nb); ctx.set_option("lookahead", la)
             ctx.time_phase(data, spec, 1, 1)
             ms = ctx.time_phase(data, spec, 1, 3)

@@ -1,5 +1,6 @@
 """Which operand layouts should use the bulk-copy GEMM kernel, and with which slice width: option gemm_v4_mask
-(bit 2*a_kmajor + b_kmajor: 1 = NT, 2 = NN, 4 = TT, 8 = TN) and gemm_v4_bk32_mask (same bits: 32-wide slices, 2 stages)."""
+(bit 2*a_kmajor + b_kmajor: 1 = NT, 2 = NN, 4 = TT, 8 = TN) and gemm_v4_bk32_mask (same bits: 32-wide slices, 2 stages).
+usage: tune_v4_layouts.py [v4_mask,bk32_mask ...]"""
 import sys
 from pathlib import Path
 import numpy as np
@@ -16,7 +17,10 @@ X, y, _ = orc.synthetic(32768, 16, 0)
 data = ctx.data_create(X, y)
 spec = dg.GenericMaternKernel(4.0, 2)._spec(noise=0.1)
 ref = None
-for (mask, bk32) in ((0, 0), (1, 0), (1, 1), (3, 0), (3, 2), (15, 8), (15, 10), (11, 10)):
+combos = ((0, 0), (1, 0), (1, 1), (3, 0), (3, 2), (15, 8), (15, 10))
+if len(sys.argv) > 1:
+    combos = tuple(tuple(int(v) for v in c.split(",")) for c in sys.argv[1:])
+for (mask, bk32) in combos:
     ctx.set_option("gemm_v4_mask", mask); ctx.set_option("gemm_v4_bk32_mask", bk32)
     ctx.test_gemm(A768, A768, C0, alpha=-1.0, beta=1.0, transB=True, lower_only=True)
     ms = min(ctx.test_gemm(A768, A768, C0, alpha=-1.0, beta=1.0, transB=True, lower_only=True)[1] for _ in range(2))

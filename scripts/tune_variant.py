@@ -7,8 +7,12 @@ import numpy as np
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import dynaml_b200 as dg
 
+import os
 variants = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [2, 4]
 ctx = dg.default_context()
+for key in ("gemm_v4_mask", "gemm_v4_bk32_mask"):  # e.g. gemm_v4_mask=15 python scripts/tune_variant.py
+    if key in os.environ:
+        ctx.set_option(key, int(os.environ[key]))
 rng = np.random.default_rng(0)
 
 # ---- correctness: every layout, beta != 0, lower_only, small and ragged-in-tiles sizes -------------------

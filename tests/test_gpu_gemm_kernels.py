@@ -1,0 +1,92 @@
+"""The two FP64 GEMM kernels behind every O(N^3) step -- the bulk-copy (TMA) / mbarrier kernel and the cp.async
+kernel (dynaml_b200/csrc/gemm.cu) -- must agree BIT FOR BIT: both add the k-terms of an output element in the same
+order, so any difference is a data hazard, not rounding.  Also the regression test of the stage hand-over hazard
+(DESIGN.md 4.1): with the C-tile prefetch off, the earlier kernel returned a wrong factor in every N = 8192 run."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+DEFAULTS = {"gemm_variant": 4, "gemm_v4_mask": 3, "gemm_v4_bk32_mask": 2, "gemm_no_prefetch": 0}
+
+
+@pytest.fixture
+def gemm_options(ctx):
+    def set_all(**kw):
+        for k, v in {**DEFAULTS, **kw}.items():
+            ctx.set_option(k, v)
+    yield set_all
+    set_all()
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("bk32", [0, 15])
+def test_bulk_copy_kernel_equals_cp_async_kernel(ctx, gemm_options, ta, tb, bk32):
+    rng = np.random.default_rng(7 + 2 * ta + tb)
+    for (M, N, K) in ((128, 64, 32), (384, 320, 160), (640, 256, 1056), (200, 300, 150)):
+        A = rng.standard_normal((K, M) if ta else (M, K))
+        B = rng.standard_normal((N, K) if tb else (K, N))
+        C0 = rng.standard_normal((M, N))
+        gemm_options(gemm_variant=2)
+        want, _ = ctx.test_gemm(A, B, C0, alpha=0.5, beta=-1.5, transA=ta, transB=tb)
+        want0, _ = ctx.test_gemm(A, B, transA=ta, transB=tb)
+        gemm_options(gemm_variant=4, gemm_v4_mask=15, gemm_v4_bk32_mask=bk32)
+        got, _ = ctx.test_gemm(A, B, C0, alpha=0.5, beta=-1.5, transA=ta, transB=tb)
+        got0, _ = ctx.test_gemm(A, B, transA=ta, transB=tb)
+        assert np.array_equal(got, want) and np.array_equal(got0, want0), (M, N, K)
+        ref = 0.5 * (A.T if ta else A) @ (B.T if tb else B) - 1.5 * C0
+        assert np.abs(got - ref).max() <= 64 * K * np.finfo(float).eps * max(1.0, np.abs(ref).max())
+
+
+def test_bulk_copy_kernel_lower_only_syrk(ctx, gemm_options):
+    rng = np.random.default_rng(3)
+    n, k = 1536, 768
+    A = rng.standard_normal((n, k))
+    C0 = rng.standard_normal((n, n))
+    gemm_options(gemm_variant=2)
+    want, _ = ctx.test_gemm(A, A, C0, alpha=-1.0, beta=1.0, transB=True, lower_only=True)
+    gemm_options()
+    got, _ = ctx.test_gemm(A, A, C0, alpha=-1.0, beta=1.0, transB=True, lower_only=True)
+    assert np.array_equal(got, want)
+    iu = np.triu_indices(n, 128)          # tiles strictly above the diagonal tiles are never written
+    assert np.array_equal(got[iu], C0[iu])
+
+
+def test_stage_handover_under_a_slow_epilogue(ctx, gemm_options):
+    """N = 8192 energy (assembly + blocked Cholesky + solves): trailing updates fill every SM with two CTAs, and without
+    the L2 prefetch of the C tile one CTA's read-modify-write epilogue backs up the load/store pipe while the other is
+    in its main loop -- the condition under which a stage was refilled before its fragment loads had read it."""
+    import dynaml_b200 as dg
+    from oracle import gp_oracle as orc
+    X, y, _ = orc.synthetic(8192, 8, seed=5)
+    data = ctx.data_create(X, y)
+    spec = dg.SEKernel(3.0, 1.0)._spec(noise=0.05)
+    try:
+        gemm_options(gemm_variant=2)
+        e_ref = ctx.energy(data, spec)
+        assert np.isfinite(e_ref)
+        for no_prefetch, reps in ((1, 10), (0, 4)):
+            gemm_options(gemm_no_prefetch=no_prefetch)
+            for _ in range(reps):
+                assert ctx.energy(data, spec) == e_ref
+    finally:
+        ctx.data_destroy(data)
+
+
+def test_energy_grad_identical_across_gemm_kernels(ctx, gemm_options):
+    import dynaml_b200 as dg
+    from oracle import gp_oracle as orc
+    X, y, _ = orc.synthetic(3000, 6, seed=11)     # ragged: padded to 3072
+    data = ctx.data_create(X, y)
+    spec = dg.GenericMaternKernel(2.5, 2)._spec(noise=0.1)
+    try:
+        gemm_options(gemm_variant=2)
+        e2, g2 = ctx.energy_grad(data, spec)
+        gemm_options()
+        e4, g4 = ctx.energy_grad(data, spec)
+        assert e4 == e2
+        assert all(a == b or (a != a and b != b) for a, b in zip(g4, g2))
+        eo = orc.energy(orc.Kernel("matern", {"p": 2.0, "l": 2.5}), 0.1, X, y)
+        assert abs(e4 - eo) <= 1e-9 * abs(eo)
+    finally:
+        ctx.data_destroy(data)
