@@ -530,8 +530,13 @@ int32_t enqueue_eval(Ctx *ctx, int slot, const Data *D, const Spec &sp, bool wan
   if (want_grad) {
     DGP_BUF(W, double, ctx, nm[5], (size_t)np * np * sizeof(double));
     DGP_BUF(Kinv, double, ctx, "Kinv", (size_t)np * np * sizeof(double));
-    DGP_TRY(trtri_lower_on(ctx, S, K, np, inv, np, W, np, Kinv, np));
-    DGP_TRY(lauum_lower_on(ctx, S, W, np, np, Kinv, np));
+    if (ctx->inverse_transposed) {  // W holds U = L^-T
+      DGP_TRY(trtri_lower_transposed_on(ctx, S, K, np, inv, np, W, np, Kinv, np));
+      DGP_TRY(lauum_upper_on(ctx, S, W, np, np, Kinv, np));
+    } else {
+      DGP_TRY(trtri_lower_on(ctx, S, K, np, inv, np, W, np, Kinv, np));
+      DGP_TRY(lauum_lower_on(ctx, S, W, np, np, Kinv, np));
+    }
     tick(ctx, slot, 4);
     if (Z != S) {  // the trace pass needs alpha
       cudaEvent_t e = misc_event(ctx, 2 * slot + 1);
@@ -708,6 +713,8 @@ int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
   } else if (!strcmp(key, "gemm_v4_mask")) {
     if (value < 0 || value > 15) return ctx->fail(DGP_ERR_ARG, "gemm_v4_mask must be in 0..15");
     ctx->gemm_v4_mask = (int)value;
+  } else if (!strcmp(key, "inverse_transposed")) {
+    ctx->inverse_transposed = value != 0;
   } else if (!strcmp(key, "gemm_no_prefetch")) {
     ctx->gemm_no_prefetch = value != 0;
   } else if (!strcmp(key, "gemm_bk")) {
@@ -1448,7 +1455,12 @@ int32_t dgp_test_potrf(dgp_ctx *ctx, int64_t n, double *A, int64_t lda, double *
     if (!dW || !dKi) return DGP_ERR_OOM;
     DGP_CUDA_OK(ctx, cudaMemsetAsync(dW, 0, (size_t)np * np * sizeof(double), S));
     DGP_TRY(trtri_lower(ctx, dA, np, inv, np, dW, np, dKi, np));
-    if (Ainv) {
+    if (Ainv && ctx->inverse_transposed) {  // the gradient path's pair: U = L^-T in its own buffer, K^-1 = U U^T
+      DGP_BUF(dU, double, ctx, "tp_u", (size_t)np * np * sizeof(double));
+      DGP_TRY(trtri_lower_transposed_on(ctx, S, dA, np, inv, np, dU, np, dKi, np));
+      DGP_TRY(lauum_upper_on(ctx, S, dU, np, np, dKi, np));
+      DGP_TRY(mirror_lower(ctx, S, dKi, np, np));
+    } else if (Ainv) {
       DGP_TRY(lauum_lower(ctx, dW, np, np, dKi, np));
       DGP_TRY(mirror_lower(ctx, S, dKi, np, np));
     }

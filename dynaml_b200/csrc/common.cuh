@@ -46,6 +46,7 @@ struct Ctx {
   int gemm_variant = 4;  // 4 = bulk-copy / mbarrier kernel (dgemm_dmma_v4_kernel), 2 = cp.async kernel (dgemm_dmma_kernel)
   int gemm_v4_bk32_mask = 2; // layouts whose bulk-copy kernel uses 32-wide slices / two stages (NN: 34.6 vs 33.9 TFLOP/s)
   int gemm_v4_mask = 3;  // operand layouts (bit 2*a_kmajor + b_kmajor) that use the bulk-copy kernel: NT and NN (TN: 32.2 vs 33.9 for cp.async)
+  int inverse_transposed = 1;  // gradient path: K^-1 = U U^T from U = L^-T (all NT / NN products) instead of W^T W from W = L^-1
   int gemm_no_prefetch = 0;  // testing only: GEMMs skip the L2 prefetch of their C tile
   int gemm_bk = 32;   // K-slice of the GEMM pipeline: 16 (3-4 stages) or 32 (double buffered)
   int assembly = 0;   // 0: Gram/DMMA assembly when its error bound allows, 1: always exact differences, 2: force Gram

@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dgemm_dmma_kernel(GemmArgs p, con
   if (p.kmode == K_GE_COL) k_lo = (n0 / 64) * 64;
   else if (p.kmode == K_LT_ROWEND) k_hi = min(p.K, m0 + BM);
   else if (p.kmode == K_GE_ROW) k_lo = m0;
+  else if (p.kmode == K_LT_COLEND) k_hi = min(p.K, n0 + BN);
   const int KT = (k_hi - k_lo) / BK;
 
   const double *A = p.A + (int64_t)blockIdx.y * p.strideA;
@@ -272,6 +273,7 @@ __device__ __forceinline__ TileRef next_tile(const GemmArgs &p, const uint32_t *
     if (p.kmode == K_GE_COL) k_lo = (n0 / 64) * 64;
     else if (p.kmode == K_LT_ROWEND) k_hi = min(p.K, m0 + BM);
     else if (p.kmode == K_GE_ROW) k_lo = m0;
+    else if (p.kmode == K_LT_COLEND) k_hi = min(p.K, n0 + BN);
     r.m0 = m0;  r.n0 = n0;  r.KT = (k_hi - k_lo) / 32;  r.idx = idx;
     r.Ag = AK ? (A + k_lo + (int64_t)m0 * p.lda) : (A + m0 + (int64_t)k_lo * p.lda);
     r.Bg = BKM ? (B + k_lo + (int64_t)n0 * p.ldb) : (B + n0 + (int64_t)k_lo * p.ldb);
@@ -593,6 +595,7 @@ __global__ void __launch_bounds__(NTHREADS_B, 2) dgemm_dmma_v4_kernel(GemmArgs p
   if (p.kmode == K_GE_COL) k_lo = (n0 / 64) * 64;
   else if (p.kmode == K_LT_ROWEND) k_hi = min(p.K, m0 + BM);
   else if (p.kmode == K_GE_ROW) k_lo = m0;
+  else if (p.kmode == K_LT_COLEND) k_hi = min(p.K, n0 + BN);
   const int KT = (k_hi - k_lo) / BK;
 
   if (tid == 0) {

@@ -12,7 +12,8 @@ enum KMode {
   K_FULL = 0,
   K_GE_COL = 1,      // k in [n0, K)        : op(B) is lower triangular  (B[k][n] = 0 for k < n)
   K_LT_ROWEND = 2,   // k in [0, m0 + 128)  : op(A) is lower triangular  (A[m][k] = 0 for k > m)
-  K_GE_ROW = 3       // k in [m0, K)        : op(A) is upper triangular  (A[m][k] = 0 for k < m), lower output
+  K_GE_ROW = 3,      // k in [m0, K)        : op(A) is upper triangular  (A[m][k] = 0 for k < m)
+  K_LT_COLEND = 4    // k in [0, n0 + 64)   : op(B) is upper triangular  (B[k][n] = 0 for k > n)
 };
 
 struct GemmArgs {

@@ -142,6 +142,22 @@ __global__ void copy_diag_blocks_kernel(const double *inv, double *W, int64_t ld
   }
 }
 
+// U diagonal tiles <- transposed leaf inverses
+__global__ void copy_diag_blocks_transposed_kernel(const double *inv, double *U, int64_t ldu) {
+  __shared__ double tile[32][33];
+  const int b = blockIdx.x;
+  const double *src = inv + (int64_t)b * LB * LB;
+  double *dst = U + (int64_t)b * LB * (ldu + 1);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int bt = 0; bt < 16; ++bt) {
+    const int r0 = (bt & 3) * 32, c0 = (bt >> 2) * 32;
+    for (int j = ty; j < 32; j += 8) tile[j][tx] = src[r0 + tx + (c0 + j) * LB];  // tile[c][r] = inv(r0 + r, c0 + c)
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) dst[c0 + tx + (int64_t)(r0 + j) * ldu] = tile[tx][j];  // U(c0 + c, r0 + r)
+    __syncthreads();
+  }
+}
+
 cudaEvent_t get_event(Ctx *ctx, size_t i) {
   while (ctx->ev_pool.size() <= i) {
     cudaEvent_t e;
@@ -318,6 +334,48 @@ int32_t trtri_lower_on(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, c
   return DGP_OK;
 }
 
+int32_t trtri_lower_transposed_on(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, const double *inv, int64_t n,
+                                  double *U, int64_t ldu, double *scratch, int64_t lds) {
+  if (n % LB) return ctx->fail(DGP_ERR_SHAPE, "trtri: n must be a multiple of 128");
+  copy_diag_blocks_transposed_kernel<<<(unsigned)(n / LB), 256, 0, S>>>(inv, U, ldu);
+  ctx->launches++;
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  // Level h joins the transposed inverses of two adjacent diagonal blocks [r0, r0+h) and [r0+h, r0+h+h2):
+  //   U12 = W21^T = -(W22 L21 W11)^T = -(U11 * L21^T) * U22
+  for (int64_t h = LB; h < n; h *= 2) {
+    const int64_t nfull = n / (2 * h);
+    const int64_t rem = n - nfull * 2 * h;
+    const int64_t h2_last = rem > h ? rem - h : 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int64_t cnt = pass == 0 ? nfull : (h2_last > 0 ? 1 : 0);
+      if (cnt == 0) continue;
+      const int64_t r0 = pass == 0 ? 0 : nfull * 2 * h;
+      const int64_t h2 = pass == 0 ? h : h2_last;
+      GemmArgs t;  // X = U11 * L21^T  (NT; U11 upper triangular: k >= m0)
+      t.A = U + r0 + r0 * ldu;        t.lda = ldu;  t.a_kmajor = 0;
+      t.B = L + (r0 + h) + r0 * ldl;  t.ldb = ldl;  t.b_kmajor = 0;   // op(B)(k,n) = L21(n,k)
+      t.C = scratch + r0 + (r0 + h) * lds;  t.ldc = lds;
+      t.M = (int)h;  t.N = (int)h2;  t.K = (int)h;
+      t.alpha = 1.0;  t.beta = 0.0;
+      t.kmode = K_GE_ROW;
+      t.batch = (int)cnt;
+      t.strideA = 2 * h * (ldu + 1);  t.strideB = 2 * h * (ldl + 1);  t.strideC = 2 * h * (lds + 1);
+      DGP_TRY(gemm(ctx, S, t));
+      GemmArgs u;  // U12 = -X * U22  (NN; U22 upper triangular: k < n0 + 64)
+      u.A = scratch + r0 + (r0 + h) * lds;  u.lda = lds;  u.a_kmajor = 0;
+      u.B = U + (r0 + h) + (r0 + h) * ldu;  u.ldb = ldu;  u.b_kmajor = 1;
+      u.C = U + r0 + (r0 + h) * ldu;        u.ldc = ldu;
+      u.M = (int)h;  u.N = (int)h2;  u.K = (int)h2;
+      u.alpha = -1.0;  u.beta = 0.0;
+      u.kmode = K_LT_COLEND;
+      u.batch = (int)cnt;
+      u.strideA = 2 * h * (lds + 1);  u.strideB = 2 * h * (ldu + 1);  u.strideC = 2 * h * (ldu + 1);
+      DGP_TRY(gemm(ctx, S, u));
+    }
+  }
+  return DGP_OK;
+}
+
 int32_t trsm_lower_fwd(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, const double *inv, int64_t n,
                        double *B, int64_t ldb, int64_t m, int64_t nb) {
   if (n % LB || nb % LB || m % 64) return ctx->fail(DGP_ERR_SHAPE, "trsm: n, nb must be multiples of 128, m of 64");
@@ -350,6 +408,18 @@ int32_t trsm_lower_fwd(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, c
     DGP_TRY(gemm(ctx, S, t));
   }
   return DGP_OK;
+}
+
+int32_t lauum_upper_on(Ctx *ctx, cudaStream_t S, const double *U, int64_t ldu, int64_t n, double *Kinv, int64_t ldk) {
+  GemmArgs g;  // Kinv(i,j) = sum_{k >= i} U(i,k) U(j,k),  i >= j  (NT)
+  g.A = U;  g.lda = ldu;  g.a_kmajor = 0;
+  g.B = U;  g.ldb = ldu;  g.b_kmajor = 0;
+  g.C = Kinv;  g.ldc = ldk;
+  g.M = (int)n;  g.N = (int)n;  g.K = (int)n;
+  g.alpha = 1.0;  g.beta = 0.0;
+  g.lower_only = 1;
+  g.kmode = K_GE_ROW;
+  return gemm(ctx, S, g);
 }
 
 int32_t lauum_lower(Ctx *ctx, const double *W, int64_t ldw, int64_t n, double *Kinv, int64_t ldk) {

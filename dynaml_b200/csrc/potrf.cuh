@@ -35,6 +35,11 @@ int32_t trsm_lower_fwd(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, c
                        double *B, int64_t ldb, int64_t m, int64_t nb);
 
 // Kinv (lower tiles) = W^T W.
+// The same inverse stored transposed, U = L^-T (upper triangular), and K^-1 = U U^T from it: with U every product of the
+// pair is NT or NN (MN-major A), so the whole inverse runs on the bulk-copy GEMM kernel; W^T W is a TN product.
+int32_t trtri_lower_transposed_on(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, const double *inv, int64_t n,
+                                  double *U, int64_t ldu, double *scratch, int64_t lds);
+int32_t lauum_upper_on(Ctx *ctx, cudaStream_t S, const double *U, int64_t ldu, int64_t n, double *Kinv, int64_t ldk);
 int32_t lauum_lower(Ctx *ctx, const double *W, int64_t ldw, int64_t n, double *Kinv, int64_t ldk);
 int32_t lauum_lower_on(Ctx *ctx, cudaStream_t S, const double *W, int64_t ldw, int64_t n, double *Kinv, int64_t ldk);
 

@@ -132,7 +132,13 @@ const char *dgp_last_error(const dgp_ctx *ctx);     /* NUL-terminated, owned by 
 const char *dgp_version(void);
 /* Tunables: "nb" (outer Cholesky block, multiple of 128; 0 = auto, the default), "lookahead"
    (0/1), "timing" (0/1), "batch_streams" (1..4 candidates of dgp_energy_batch in flight; default 3),
-   "assembly" (0 = Gram/DMMA kernel when its error bound allows, 1 = exact differences, 2 = force Gram). */
+   "assembly" (0 = Gram/DMMA kernel when its error bound allows, 1 = exact differences, 2 = force Gram).
+   GEMM kernel selection (results are bit-identical for every choice): "gemm_variant" (4 = bulk-copy /
+   mbarrier kernel where "gemm_v4_mask" allows, the default; 2 = cp.async kernel everywhere), "gemm_v4_mask" and
+   "gemm_v4_bk32_mask" (bit 2*a_kmajor + b_kmajor per operand layout: layouts on the bulk-copy kernel, and
+   those of them using 32-wide K-slices; defaults 3 and 2), "gemm_bk" (16/32, cp.async kernel),
+   "gemm_persistent" (0/1, experiment), "gemm_no_prefetch" (0/1, testing: no L2 prefetch of the C tile),
+   "inverse_transposed" (1 = K^-1 as U U^T from U = L^-T, the default; 0 = W^T W from W = L^-1).          */
 int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value);
 /* Phase timings (ms, CUDA events) of the last energy/energy_grad/fit/predict call:
    [0] assemble [1] potrf [2] solves+logdet [3] inverse (trtri+lauum) [4] trace pass

@@ -27,14 +27,16 @@ def test_bulk_copy_kernel_equals_cp_async_kernel(ctx, gemm_options, ta, tb, bk32
         A = rng.standard_normal((K, M) if ta else (M, K))
         B = rng.standard_normal((N, K) if tb else (K, N))
         C0 = rng.standard_normal((M, N))
+        # alpha, beta powers of two: both products of the epilogue's alpha * acc + beta * C are exact, so the result
+        # does not depend on which of them the compiler contracts into the FMA
         gemm_options(gemm_variant=2)
-        want, _ = ctx.test_gemm(A, B, C0, alpha=0.5, beta=-1.5, transA=ta, transB=tb)
+        want, _ = ctx.test_gemm(A, B, C0, alpha=2.0, beta=-0.5, transA=ta, transB=tb)
         want0, _ = ctx.test_gemm(A, B, transA=ta, transB=tb)
         gemm_options(gemm_variant=4, gemm_v4_mask=15, gemm_v4_bk32_mask=bk32)
-        got, _ = ctx.test_gemm(A, B, C0, alpha=0.5, beta=-1.5, transA=ta, transB=tb)
+        got, _ = ctx.test_gemm(A, B, C0, alpha=2.0, beta=-0.5, transA=ta, transB=tb)
         got0, _ = ctx.test_gemm(A, B, transA=ta, transB=tb)
         assert np.array_equal(got, want) and np.array_equal(got0, want0), (M, N, K)
-        ref = 0.5 * (A.T if ta else A) @ (B.T if tb else B) - 1.5 * C0
+        ref = 2.0 * (A.T if ta else A) @ (B.T if tb else B) - 0.5 * C0
         assert np.abs(got - ref).max() <= 64 * K * np.finfo(float).eps * max(1.0, np.abs(ref).max())
 
 
@@ -89,4 +91,28 @@ def test_energy_grad_identical_across_gemm_kernels(ctx, gemm_options):
         eo = orc.energy(orc.Kernel("matern", {"p": 2.0, "l": 2.5}), 0.1, X, y)
         assert abs(e4 - eo) <= 1e-9 * abs(eo)
     finally:
+        ctx.data_destroy(data)
+
+
+def test_transposed_inverse_equals_the_lower_one(ctx, gemm_options):
+    """K^-1 for the gradient is U U^T with U = L^-T (NT / NN products only); the W = L^-1, W^T W route adds the same
+    terms in the same order, so the two gradients agree bit for bit (option inverse_transposed)."""
+    import dynaml_b200 as dg
+    from oracle import gp_oracle as orc
+    X, y, _ = orc.synthetic(2500, 7, seed=3)      # 2560 padded: a last, smaller join at every level
+    data = ctx.data_create(X, y)
+    spec = dg.MahalanobisKernel(np.linspace(1.5, 3.0, 7), 1.2)._spec(noise=0.05)
+    try:
+        ctx.set_option("inverse_transposed", 0)
+        e0, g0 = ctx.energy_grad(data, spec)
+        ctx.set_option("inverse_transposed", 1)
+        e1, g1 = ctx.energy_grad(data, spec)
+        assert e0 == e1 and np.array_equal(np.asarray(g0), np.asarray(g1))
+        # and the factor's inverse itself against LAPACK
+        rng = np.random.default_rng(0)
+        A = rng.standard_normal((640, 640)); A = A @ A.T + 640 * np.eye(640)
+        _, _, ainv, _, _ = ctx.test_potrf(A, want_ainv=True)
+        assert np.abs(ainv - np.linalg.inv(A)).max() <= 1e-12 * np.abs(ainv).max()
+    finally:
+        ctx.set_option("inverse_transposed", 1)
         ctx.data_destroy(data)
