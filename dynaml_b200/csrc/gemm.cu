@@ -1,17 +1,19 @@
 // gemm.cu -- FP64 GEMM on the sm_100a DMMA tensor path (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4;
 // tcgen05 has no f64 kind).
 //
-// One CTA = 256 threads = 8 warps computes a 128x64 tile of C; each warp owns 32x32 of it as 4x4
-// DMMA accumulators (64 FP64 registers), so two CTAs are resident per SM (<= 128 registers per
-// thread, <= 113 KB shared memory each).  Two co-resident CTAs matter more than a bigger tile:
-// while one CTA runs its read-modify-write epilogue or refills its pipeline, the other keeps the
-// FP64 tensor pipe busy, and the main loop has 4 warps per scheduler to hide LDS latency and the
-// per-slice barrier (ncu of the first 128x128 / one-CTA version: tensor pipe 73 % active at K = 256,
-// 86 % at K = 4096; profiles/).
+// One CTA computes a 128x64 tile of C with 8 DMMA warps; each warp owns 32x32 of it as 4x4 DMMA
+// accumulators (64 FP64 registers), so two CTAs are resident per SM.  Two co-resident CTAs matter
+// more than a bigger tile: while one CTA runs its read-modify-write epilogue or refills its
+// pipeline, the other keeps the FP64 tensor pipe busy (ncu of the first 128x128 / one-CTA version:
+// tensor pipe 73 % active at K = 256, 86 % at K = 4096; profiles/).
 //
-// Operands stream through a cp.async (LDGSTS) pipeline in slices of BK = 16; shared-memory rows
-// are padded by 4 doubles so the 64-bit fragment loads of a half-warp hit 16 distinct bank pairs
-// for both the "MN-major" and the "K-major" layouts (ncu: 0 bank conflicts).
+// Two kernels, bit-identical results (same order of the k-terms):
+//   dgemm_dmma_v4_kernel  (default for MN-major A: NT and NN products, i.e. everything on the energy /
+//                         gradient path) -- a ninth warp feeds the stages with cp.async.bulk row copies
+//                         through full / empty mbarriers, 128-bit fragment loads, 16-byte epilogue;
+//   dgemm_dmma_kernel     (K-major A: TN / TT products; option gemm_variant = 2 for everything) -- all
+//                         eight warps copy with cp.async (LDGSTS) and meet at one __syncthreads per slice;
+//                         rows padded by 4 doubles make its 64-bit fragment loads conflict-free.
 //
 // Tiles are launched in the order of a host-built tile table: super-rows of 12 x 128 rows swept
 // column by column, so the ~300 concurrently resident CTAs share ~12 A panels and ~24 B panels
@@ -67,9 +69,10 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 
 // Copy one ROWS x BK operand slice into a stage (ROWS = 128 for A, 64 for B).  g points at the
 // slice origin.
-template <bool KMAJOR, int ROWS, int BK, bool INC = false, int LD_MN = ROWS + 4>
+template <bool KMAJOR, int ROWS, int BK, bool INC = false>
 __device__ __forceinline__ void load_slice(double *s, const double *g, int64_t ld, int tid) {
   constexpr int CHUNKS = ROWS * BK / 2;  // 16-byte chunks
+  constexpr int LD_MN = ROWS + 4;
   constexpr int LDS_K = BK + 4;
   // Chunk c = tid + i * NTHREADS: consecutive i advance the slow index by a compile-time step, so every address is
   // the previous one plus a loop-invariant stride (one 64-bit add per chunk instead of a multiply-add chain).
