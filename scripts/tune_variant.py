@@ -1,6 +1,6 @@
-"""GEMM main-loop variants (option gemm_variant: 2 = 64-bit fragment loads, 3 = 128-bit fragment loads + 16-byte
-epilogue, 4 = variant 3 fed by bulk copies through an mbarrier pipeline): correctness of all four operand layouts
-against NumPy, then trailing-update SYRK at several K, long-K NN / TN products, a panel shape and the whole C3 step."""
+"""The two GEMM kernels (option gemm_variant: 2 = cp.async kernel, 4 = bulk-copy / mbarrier kernel on the layouts of
+gemm_v4_mask): correctness of all four operand layouts against NumPy, then trailing-update SYRK at several K, long-K
+NN / TN products, a panel shape and the whole C3 step.  usage: tune_variant.py [2,4]"""
 import sys
 from pathlib import Path
 import numpy as np
