@@ -426,7 +426,8 @@ dgemm_dmma_persistent_kernel(GemmArgs p, const uint32_t *__restrict__ tiles, int
 // lane with warp-uniform addresses, one `cp.async.bulk` per operand row (rows are contiguous in global memory and
 // padded in shared memory, so no tensor map is needed) and the eight DMMA warps only wait on a `full` mbarrier,
 // multiply, and arrive on an `empty` one -- no warp ever waits for another except through data it needs.
-// K-slices of 16, four stages.
+// K-slices of 16 through four stages (NT), or of 32 through two (NN: half as many copies per flop; option
+// gemm_v4_bk32_mask).
 //
 // Fragment mapping.  The m8n8k4 fragment of lane (g, t) is one element per 8-row block, i.e. one LDS.64 per
 // fragment element in the kernel above.  Any permutation of the rows of the warp's 32x32 sub-tile is a valid
@@ -434,7 +435,7 @@ dgemm_dmma_persistent_kernel(GemmArgs p, const uint32_t *__restrict__ tiles, int
 // 16*(i>>1) + 2*g + (i&1): rows 2g and 2g+1 are adjacent in an MN-major stage and come from ONE LDS.128
 // (rows padded to 132 / 68 doubles = 4 mod 16 keep each quarter-warp on 8 distinct 16-byte bank groups), and in
 // the epilogue they are adjacent in the column-major C (16-byte loads / stores, 128 contiguous bytes per column
-// and warp instruction).  K-major stages keep 64-bit loads; their rows are padded to 18 doubles, which with this
+// and warp instruction).  K-major stages keep 64-bit loads; their rows are padded to 18 / 34 doubles, which with this
 // row assignment puts each half-warp on 16 distinct banks.
 // ---------------------------------------------------------------------------------------------
 template <bool AK, bool BKM, int BK_>
