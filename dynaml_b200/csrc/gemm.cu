@@ -616,15 +616,6 @@ __global__ void __launch_bounds__(NTHREADS_B, 2) dgemm_dmma_v4_kernel(GemmArgs p
 
   if (warp == 8) {
     // ---- producer warp --------------------------------------------------------------------------------
-    if (p.beta != 0.0 && !p.no_prefetch) {  // pull the C tile towards L2 for the read-modify-write epilogue
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        int c = lane + i * 32;  // 512 lines of 128 B: 8 per column
-        int col = c >> 3, seg = c & 7;
-        const double *ptr = C + m0 + seg * 16 + (int64_t)(n0 + col) * p.ldc;
-        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ptr));
-      }
-    }
     if (elect_one()) {
       // One bulk copy per operand row and slice.  MN-major operands have BK rows (one per k) of BM / BN doubles,
       // K-major ones BM / BN rows of BK doubles; every address is the previous one plus a uniform stride.
@@ -669,6 +660,17 @@ __global__ void __launch_bounds__(NTHREADS_B, 2) dgemm_dmma_v4_kernel(GemmArgs p
   }
 
   // ---- DMMA warps ---------------------------------------------------------------------------------------
+  // Pull the C tile towards L2 for the read-modify-write epilogue; these warps have nothing else to do until the
+  // first stage lands, and the producer gets to its first copies sooner.
+  if (p.beta != 0.0 && !p.no_prefetch) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int c = tid + i * NTHREADS;  // 512 lines of 128 B: 8 per column
+      int col = c >> 3, seg = c & 7;
+      const double *ptr = C + m0 + seg * 16 + (int64_t)(n0 + col) * p.ldc;
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ptr));
+    }
+  }
   const int g = lane >> 2, t = lane & 3;
   const int wm = warp & 3, wn = warp >> 2;
   double acc[4][4][2];
