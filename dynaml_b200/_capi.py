@@ -34,7 +34,7 @@ EXPORTS = [
     "dgp_predict", "dgp_dist_unique_id", "dgp_dist_init", "dgp_dist_finalize", "dgp_dist_plan", "dgp_dist_energy",
     "dgp_measure_peaks", "dgp_launch_count", "dgp_outer_block", "dgp_time_phase", "dgp_test_gemm", "dgp_test_potrf",
     "dgp_spec_grad_len", "dgp_data_set_basis", "dgp_model_set_test_basis", "dgp_model_solve", "dgp_model_cross_apply",
-    "dgp_model_set_cross_spec",
+    "dgp_model_set_cross_spec", "dgp_ctx_trim", "dgp_dist_info", "dgp_ctx_info",
 ]
 
 
@@ -93,6 +93,9 @@ def load_library() -> C.CDLL:
         "dgp_dist_unique_id": (i32, [vp]),
         "dgp_dist_init": (i32, [vp, vp, i32, i32, i32, i32]),
         "dgp_dist_finalize": (i32, [vp]),
+        "dgp_dist_info": (i32, [vp, C.POINTER(i32), i32]),
+        "dgp_ctx_trim": (i32, [vp]),
+        "dgp_ctx_info": (i32, [vp, C.POINTER(i64), i32]),
         "dgp_dist_energy": (i32, [vp, vp, sp, i32, _dp, _dp]),
         "dgp_dist_plan": (i32, [i64, i32, i32, i32, i32, C.POINTER(i64)]),
         "dgp_measure_peaks": (i32, [vp, _dp, i32]),
@@ -193,10 +196,20 @@ class Context:
     def set_option(self, key: str, value: int):
         self.check(self.lib.dgp_ctx_set_option(self.h, key.encode(), int(value)))
 
+    def trim(self):
+        """Give the workspace arena back to the driver (handles stay valid)."""
+        self.check(self.lib.dgp_ctx_trim(self.h))
+
+    def info(self) -> dict:
+        out = (C.c_int64 * 4)()
+        self.check(self.lib.dgp_ctx_info(self.h, out, 4))
+        return {"device": int(out[0]), "sm_count": int(out[1]), "mem_total": int(out[2]), "mem_free": int(out[3])}
+
     def timings(self) -> dict:
         out = np.zeros(16)
         self.check(self.lib.dgp_get_timings(self.h, _ptr(out), 16))
-        names = ["assemble", "potrf", "solves", "inverse", "trace", "cross_assemble", "trsm", "syrk", "total"]
+        names = ["assemble", "potrf", "solves", "inverse", "trace", "cross_assemble", "trsm", "syrk", "total",
+                 "batch_total"]
         return {n: float(out[i]) for i, n in enumerate(names)}
 
     # -- data -------------------------------------------------------------------------------
@@ -408,6 +421,12 @@ class Context:
             return
         buf = (C.c_char * 128).from_buffer_copy(uid)
         self.check(self.lib.dgp_dist_init(self.h, C.cast(buf, C.c_void_p), rank, world, grid_rows, grid_cols))
+
+    def dist_info(self) -> dict:
+        out = (C.c_int32 * 6)()
+        self.check(self.lib.dgp_dist_info(self.h, out, 6))
+        return {"nccl_ranks": int(out[0]), "nccl_rank": int(out[1]), "grid": [int(out[2]), int(out[3])],
+                "emulated": bool(out[4]), "nccl_version": int(out[5])}
 
     def dist_finalize(self):
         self.check(self.lib.dgp_dist_finalize(self.h))

@@ -650,12 +650,18 @@ int32_t dgp_ctx_create(int32_t device, dgp_ctx **out) {
        cudaMallocHost(&ctx->h_info, 4096 * sizeof(int)) == cudaSuccess &&
        cudaMallocHost(&ctx->h_scal, 4096 * 160 * sizeof(double)) == cudaSuccess;
   if (ok) {
-    // keep freed dgp_data blocks in the stream-ordered pool instead of returning them to the driver at every sync
-    cudaMemPool_t pool;
+    // dgp_data blocks come from a pool of the library's own, which keeps freed blocks instead of returning them to
+    // the driver at every synchronisation (a create / destroy pair per evaluation is the e2e pattern); the device's
+    // default pool, shared with every other cudaMallocAsync user of the process, is left alone.
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
     uint64_t keep = UINT64_MAX;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    cudaGetLastError();
+    ok = cudaMemPoolCreate(&ctx->data_pool, &props) == cudaSuccess &&
+         cudaMemPoolSetAttribute(ctx->data_pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess;
   }
   if (ok) ok = gemm_init(ctx) == DGP_OK && potrf_init(ctx) == DGP_OK;
   if (!ok) {
@@ -682,6 +688,7 @@ int32_t dgp_ctx_destroy(dgp_ctx *ctx) {
   cudaFreeHost(ctx->h_info);
   cudaFreeHost(ctx->h_scal);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->data_pool) cudaMemPoolDestroy(ctx->data_pool);
   for (int i = 1; i < 4; ++i) {
     if (ctx->slot_S[i]) cudaStreamDestroy(ctx->slot_S[i]);
     if (ctx->slot_P[i]) cudaStreamDestroy(ctx->slot_P[i]);
@@ -690,6 +697,27 @@ int32_t dgp_ctx_destroy(dgp_ctx *ctx) {
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->panel);
   delete ctx;
+  return DGP_OK;
+}
+
+int32_t dgp_ctx_trim(dgp_ctx *ctx) {
+  if (!ctx) return DGP_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  ctx->release_all();  // synchronises the device first
+  gemm_release(ctx);
+  if (ctx->data_pool) cudaMemPoolTrimTo(ctx->data_pool, 0);
+  return DGP_OK;
+}
+
+int32_t dgp_ctx_info(dgp_ctx *ctx, int64_t *out, int32_t n) {
+  if (!ctx || !out || n < 4) return DGP_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  size_t fr = 0, tot = 0;
+  DGP_CUDA_OK(ctx, cudaMemGetInfo(&fr, &tot));
+  out[0] = ctx->device;
+  out[1] = ctx->sm_count;
+  out[2] = (int64_t)tot;
+  out[3] = (int64_t)fr;
   return DGP_OK;
 }
 
@@ -702,8 +730,9 @@ int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
     ctx->nb = value;
   } else if (!strcmp(key, "lookahead")) {
     ctx->lookahead = value != 0;
-  } else if (!strcmp(key, "gemm_persistent")) {
-    ctx->gemm_persistent = value != 0;
+  } else if (!strcmp(key, "gemm_handover")) {
+    if (value < 0 || value > 3) return ctx->fail(DGP_ERR_ARG, "gemm_handover must be in 0..3");
+    ctx->gemm_handover = (int)value;
   } else if (!strcmp(key, "gemm_variant")) {
     if (value != 2 && value != 4) return ctx->fail(DGP_ERR_ARG, "gemm_variant must be 2 (cp.async) or 4 (bulk copy)");
     ctx->gemm_variant = (int)value;
@@ -775,7 +804,7 @@ int32_t dgp_data_create(dgp_ctx *ctx, const double *X, int64_t N, int32_t d, int
   pack_points(X, N, d, x_layout, D->Np, D->dp, hx, nullptr);
   memcpy(hs + nx, hx.data(), nx * sizeof(double));
   for (int64_t i = 0; i < D->Np; ++i) hs[2 * nx + i] = i < N ? y[i] - (mean ? mean[i] : 0.0) : 0.0;
-  if (cudaMallocAsync((void **)&D->block, total * sizeof(double), ctx->stream) != cudaSuccess) {
+  if (cudaMallocFromPoolAsync((void **)&D->block, total * sizeof(double), ctx->data_pool, ctx->stream) != cudaSuccess) {
     cudaGetLastError();
     delete D;
     return ctx->fail(DGP_ERR_OOM, "data: device allocation failed");
@@ -881,13 +910,20 @@ int32_t dgp_energy_batch(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec 
   // another.
   int nslots = ctx->batch_streams < 1 ? 1 : (ctx->batch_streams > 4 ? 4 : ctx->batch_streams);
   if (n < nslots) nslots = n > 0 ? n : 1;
+  double batch_ms = 0.0;
   for (int32_t base = 0; base < n; base += 4096) {
+    DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));  // every slot's stream starts behind the main stream
     const int32_t cnt = (n - base < 4096) ? n - base : 4096;
     std::vector<int32_t> pre(cnt, DGP_OK);
     for (int32_t i = 0; i < cnt; ++i) {
       Spec sp;
       int ns = 0;
       int32_t st = parse_spec(ctx, &specs[base + i], D->d, &sp);
+      if (st == DGP_OK && i < nslots && i > 0) {  // first use of a slot in this chunk: order it behind ev_a
+        cudaStream_t S1, P1;
+        st = slot_streams(ctx, i % nslots, &S1, &P1);
+        if (st == DGP_OK) cudaStreamWaitEvent(S1, ctx->ev_a, 0);
+      }
       if (st == DGP_OK) st = enqueue_eval(ctx, i % nslots, D, sp, false, d_scal + (size_t)i * 160, ctx->d_info + i, &ns);
       pre[i] = st;
       if (st == DGP_ERR_CUDA || st == DGP_ERR_OOM) {
@@ -904,7 +940,13 @@ int32_t dgp_energy_batch(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec 
                                      ctx->stream));
     DGP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost,
                                      ctx->stream));
+    DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
     DGP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+      batch_ms += ms;
+    }
     for (int32_t i = 0; i < cnt; ++i) {
       if (pre[i] != DGP_OK) {
         status[base + i] = pre[i];
@@ -919,6 +961,7 @@ int32_t dgp_energy_batch(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec 
     }
   }
   collect_timings(ctx, false);
+  ctx->timings[9] = batch_ms;  // device time of the whole batch (first enqueue to the last read-back)
   return DGP_OK;
 }
 
@@ -1373,6 +1416,32 @@ int32_t dgp_time_phase(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *s
       g.C = K + w + w * np;  g.ldc = np;
       g.M = (int)(np - w);  g.N = (int)(np - w);  g.K = (int)w;
       g.alpha = -1e-9;  g.beta = 1.0;  g.lower_only = 1;
+      DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_a, S));
+      DGP_TRY(gemm(ctx, S, g));
+      DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_b, S));
+    } else if (phase == 3) {
+      // the largest single launch of the gradient path: K^-1 = U U^T over lower tiles with k >= row (N^3/3 flop, NT)
+      DGP_BUF(W, double, ctx, "W", (size_t)np * np * sizeof(double));
+      DGP_BUF(Kinv, double, ctx, "Kinv", (size_t)np * np * sizeof(double));
+      if (r == 0) {
+        DGP_TRY(assemble(ctx, S, cp, a));
+        DGP_TRY(mirror_lower(ctx, S, K, np, np));
+        DGP_TRY(copy_block(ctx, S, K, np, W, np, np, np));
+      }
+      DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_a, S));
+      DGP_TRY(lauum_upper_on(ctx, S, W, np, np, Kinv, np));
+      DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_b, S));
+    } else if (phase == 4) {
+      // the NN instantiation (TRMM / TRSM-type products of the triangular inverse and the prediction):
+      // C = A B with M = N = K = min(np, 8192), full k-range (2 M^3 flop)
+      const int64_t m = np < 8192 ? np : 8192;
+      DGP_BUF(W, double, ctx, "W", (size_t)np * np * sizeof(double));
+      if (r == 0) DGP_TRY(assemble(ctx, S, cp, a));
+      GemmArgs g;
+      g.A = K;  g.lda = np;  g.a_kmajor = 0;
+      g.B = K;  g.ldb = np;  g.b_kmajor = 1;
+      g.C = W;  g.ldc = np;
+      g.M = (int)m;  g.N = (int)m;  g.K = (int)m;
       DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_a, S));
       DGP_TRY(gemm(ctx, S, g));
       DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_b, S));

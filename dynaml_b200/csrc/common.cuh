@@ -42,7 +42,7 @@ struct Ctx {
   std::map<std::tuple<int, int, int, int>, std::pair<uint32_t *, size_t>> tile_tables;
   int64_t nb = 0;     // outer Cholesky block (0 = choose from n)
   int lookahead = 1;
-  int gemm_persistent = 0;  // 1: persistent CTAs with a cross-tile pipeline (measured 3-8 % slower; kept as an experiment)
+  int gemm_handover = 0;  // how a DMMA warp hands a stage back to the bulk-copy engine (gemm.cu, Handover)
   int gemm_variant = 4;  // 4 = bulk-copy / mbarrier kernel (dgemm_dmma_v4_kernel), 2 = cp.async kernel (dgemm_dmma_kernel)
   int gemm_v4_bk32_mask = 2; // layouts whose bulk-copy kernel uses 32-wide slices / two stages (NN: 34.6 vs 33.9 TFLOP/s)
   int gemm_v4_mask = 3;  // operand layouts (bit 2*a_kmajor + b_kmajor) that use the bulk-copy kernel: NT and NN (TN: 32.2 vs 33.9 for cp.async)
@@ -60,6 +60,7 @@ struct Ctx {
   int *d_info = nullptr;  // device-side status word(s): [0] = first failing pivot index + 1, 0 = ok
   int *h_info = nullptr;  // pinned mirror
   double *h_scal = nullptr;  // pinned scratch for scalar read-back (64 doubles)
+  cudaMemPool_t data_pool = nullptr;  // the library's own stream-ordered pool for dgp_data blocks (never trimmed at syncs)
   void *h_stage = nullptr;   // pinned, grow-only staging buffer of dgp_data_create
   size_t h_stage_bytes = 0;
   DistState *dist = nullptr;

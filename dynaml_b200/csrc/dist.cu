@@ -30,6 +30,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <nccl.h>
+#include <time.h>
 
 #include "assemble.cuh"
 #include "common.cuh"
@@ -53,6 +54,12 @@ struct NcclApi {
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  // optional (present in every NCCL >= 2.4 / 2.18): communicator introspection, async-error polling, abort
+  ncclResult_t (*CommCount)(const ncclComm_t, int *) = nullptr;
+  ncclResult_t (*CommUserRank)(const ncclComm_t, int *) = nullptr;
+  ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t *) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
+  ncclResult_t (*GetVersion)(int *) = nullptr;
 };
 
 static NcclApi *nccl_api() {
@@ -72,6 +79,11 @@ static NcclApi *nccl_api() {
       api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
       api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
       api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+      api.CommCount = (decltype(api.CommCount))dlsym(h, "ncclCommCount");
+      api.CommUserRank = (decltype(api.CommUserRank))dlsym(h, "ncclCommUserRank");
+      api.CommGetAsyncError = (decltype(api.CommGetAsyncError))dlsym(h, "ncclCommGetAsyncError");
+      api.CommAbort = (decltype(api.CommAbort))dlsym(h, "ncclCommAbort");
+      api.GetVersion = (decltype(api.GetVersion))dlsym(h, "ncclGetVersion");
       if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Broadcast || !api.GroupStart ||
           !api.GroupEnd)
         api.handle = nullptr;
@@ -245,6 +257,32 @@ __global__ void __launch_bounds__(256) gather_cols_kernel(const double *P, Chunk
     for (int i = threadIdx.x; i < T; i += blockDim.x) dst[i + (int64_t)c * ldd] = src[i + (int64_t)c * lds];
 }
 
+// Wait for a stream while polling the communicator for asynchronous NCCL errors (a failed peer or link shows up
+// there, not in the CUDA status); on error the communicator is aborted so the enqueued collectives cannot hang.
+int32_t wait_polling(Ctx *ctx, DistState *d, NcclApi *api, cudaStream_t st) {
+  if (!api || !d->comm || !api->CommGetAsyncError) {
+    DGP_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return DGP_OK;
+  }
+  for (;;) {
+    const cudaError_t q = cudaStreamQuery(st);
+    if (q == cudaSuccess) return DGP_OK;
+    if (q != cudaErrorNotReady)
+      return ctx->fail(DGP_ERR_CUDA, "dist: stream failed: %s", cudaGetErrorString(q));
+    ncclResult_t ar = ncclSuccess;
+    const ncclResult_t r = api->CommGetAsyncError(d->comm, &ar);
+    if (r != ncclSuccess || (ar != ncclSuccess && ar != ncclInProgress)) {
+      const ncclResult_t bad = r != ncclSuccess ? r : ar;
+      if (api->CommAbort) api->CommAbort(d->comm);
+      d->comm = nullptr;
+      return ctx->fail(DGP_ERR_NCCL, "dist: asynchronous NCCL error: %s (communicator aborted)",
+                       api->GetErrorString ? api->GetErrorString(bad) : "nccl error");
+    }
+    struct timespec ts = {0, 50000};
+    nanosleep(&ts, nullptr);
+  }
+}
+
 cudaEvent_t dist_event(DistState *d, size_t i) {
   while (d->events.size() <= i) {
     cudaEvent_t e;
@@ -314,6 +352,21 @@ int32_t dgp_dist_finalize(dgp_ctx *ctx) {
   return DGP_OK;
 }
 
+int32_t dgp_dist_info(dgp_ctx *ctx, int32_t *out, int32_t n) {
+  if (!ctx || !out || n < 6) return DGP_ERR_ARG;
+  DistState *d = ctx->dist;
+  if (!d) return ctx->fail(DGP_ERR_ARG, "dist_info: call dgp_dist_init first");
+  out[0] = 0;  out[1] = -1;  out[2] = d->Pr;  out[3] = d->Pc;  out[4] = d->emulate ? 1 : 0;  out[5] = 0;
+  NcclApi *api = d->comm ? nccl_api() : nullptr;
+  if (api) {
+    int v = 0;
+    if (api->CommCount && api->CommCount(d->comm, &v) == ncclSuccess) out[0] = v;
+    if (api->CommUserRank && api->CommUserRank(d->comm, &v) == ncclSuccess) out[1] = v;
+    if (api->GetVersion && api->GetVersion(&v) == ncclSuccess) out[5] = v;
+  }
+  return DGP_OK;
+}
+
 // Host-only description of the layout (tests / planning): out[0] tiles per dimension, out[1] local
 // tile rows, out[2] local tile columns, out[3] lower tiles owned by `rank`, out[4] local matrix bytes.
 int32_t dgp_dist_plan(int64_t n, int32_t tile, int32_t grid_rows, int32_t grid_cols, int32_t rank, int64_t *out) {
@@ -339,6 +392,8 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *
   cudaSetDevice(ctx->device);
   DistState *ds = ctx->dist;
   if (!ds) return ctx->fail(DGP_ERR_ARG, "dist_energy: call dgp_dist_init first");
+  if (ds->world > 1 && !ds->comm)
+    return ctx->fail(DGP_ERR_NCCL, "dist_energy: the communicator was aborted after an NCCL error; call dgp_dist_init again");
   if (tile < 256 || tile % 256 || tile > 2048)
     return ctx->fail(DGP_ERR_ARG, "dist_energy: tile must be a multiple of 256 in [256, 2048]");
   Spec sp;
@@ -426,6 +481,20 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *
     a.nodup = points_stay_distinct_pub(D->has_dup, sp, D->d);
     DGP_TRY(assemble(ctx, S, cp, a));
   }
+  // tile tables of every product of the loop, built before the timed pipeline starts (get_tiles allocates and
+  // copies synchronously on first use of a shape; there are O(Nt) distinct trailing shapes)
+  for (int64_t k = 0; k + 1 < g.Nt; ++k)
+    for (RankBuf &R : ranks) {
+      const int64_t nrow = g.count_row(k, R.pr), ncol = g.count_col(k, R.pc);
+      if (R.pc == (int)(k % ds->Pc)) DGP_TRY(gemm_prepare(ctx, (int)(nrow * T), T, 0, 0));
+      if (nrow == 0 || ncol == 0) continue;
+      if (la && g.first_col(k, R.pc) == k + 1) {
+        DGP_TRY(gemm_prepare(ctx, (int)(nrow * T), T, 0, 0));
+        DGP_TRY(gemm_prepare(ctx, (int)(nrow * T), (int)((ncol - 1) * T), 0, 0));
+      } else {
+        DGP_TRY(gemm_prepare(ctx, (int)(nrow * T), (int)(ncol * T), 0, 0));
+      }
+    }
   DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_a, S));
   size_t ev = 0;
   auto fork = [&](cudaStream_t from, cudaStream_t to) -> int32_t {
@@ -587,8 +656,8 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *
   if (nranks > 1)
     DGP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_scal + 8, ranks[nranks - 1].scal, 8 * sizeof(double),
                                      cudaMemcpyDeviceToHost, S));
-  DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
-  DGP_CUDA_OK(ctx, cudaStreamSynchronize(P));
+  DGP_TRY(wait_polling(ctx, ds, api, S));
+  DGP_TRY(wait_polling(ctx, ds, api, P));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
   if (chol_ms) *chol_ms = ms;

@@ -245,177 +245,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) dgemm_dmma_kernel(GemmArgs p, con
 }
 
 // ---------------------------------------------------------------------------------------------
-// Persistent variant (BK = 32, double buffered): a CTA walks the tile table with stride gridDim.x
-// and keeps ONE continuous pipeline across tiles -- while the last K-slice of a tile is multiplied
-// the first slice of the next tile is already in flight, and the read-modify-write epilogue runs
-// under it.  The per-tile start-up (tile-table load, address set-up, pipeline fill) that the ncu
-// source view of the one-tile-per-CTA kernel shows as ~8 % long-scoreboard waits at K = 256
-// disappears; grid = min(tiles, 2 CTAs per SM).
-// ---------------------------------------------------------------------------------------------
-struct TileRef {
-  const double *Ag;
-  const double *Bg;
-  int m0, n0, KT;
-  int64_t idx;  // position in the tile table; < 0: none
-};
-
-template <bool AK, bool BKM>
-__device__ __forceinline__ TileRef next_tile(const GemmArgs &p, const uint32_t *__restrict__ tiles, int64_t ntiles,
-                                             int64_t idx, const double *A, const double *B) {
-  TileRef r;
-  r.Ag = nullptr;  r.Bg = nullptr;  r.m0 = r.n0 = r.KT = 0;  r.idx = -1;
-  for (; idx < ntiles; idx += gridDim.x) {
-    const uint32_t tile = tiles[idx];
-    const int m0 = (int)(tile >> 16) * BM, n0 = (int)(tile & 0xffffu) * BN;
-    if (p.bc_T > 0) {
-      const int64_t grow = ((int64_t)(p.bc_row0 + m0 / p.bc_T) * p.bc_Pr + p.bc_pr) * p.bc_T + m0 % p.bc_T;
-      const int64_t gcol = ((int64_t)(p.bc_col0 + n0 / p.bc_T) * p.bc_Pc + p.bc_pc) * p.bc_T + n0 % p.bc_T;
-      if (gcol > grow + BM - 1) continue;
-    }
-    int k_lo = 0, k_hi = p.K;
-    if (p.kmode == K_GE_COL) k_lo = (n0 / 64) * 64;
-    else if (p.kmode == K_LT_ROWEND) k_hi = min(p.K, m0 + BM);
-    else if (p.kmode == K_GE_ROW) k_lo = m0;
-    else if (p.kmode == K_LT_COLEND) k_hi = min(p.K, n0 + BN);
-    r.m0 = m0;  r.n0 = n0;  r.KT = (k_hi - k_lo) / 32;  r.idx = idx;
-    r.Ag = AK ? (A + k_lo + (int64_t)m0 * p.lda) : (A + m0 + (int64_t)k_lo * p.lda);
-    r.Bg = BKM ? (B + k_lo + (int64_t)n0 * p.ldb) : (B + n0 + (int64_t)k_lo * p.ldb);
-    return r;
-  }
-  return r;
-}
-
-template <bool AK, bool BKM>
-__global__ void __launch_bounds__(NTHREADS, 2)
-dgemm_dmma_persistent_kernel(GemmArgs p, const uint32_t *__restrict__ tiles, int64_t ntiles) {
-  constexpr int BK = 32;
-  extern __shared__ __align__(16) double smem[];
-  using C_ = Cfg<AK, BKM, BK>;
-  constexpr int A_STAGE = C_::A_STAGE, B_STAGE = C_::B_STAGE, LDS_K = C_::LDS_K;
-  static_assert(C_::STAGES == 2, "the cross-tile pipeline is written for double buffering");
-  double *As = smem;
-  double *Bs = smem + 2 * A_STAGE;
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int wm = warp & 3, wn = warp >> 2;
-
-  const double *A = p.A + (int64_t)blockIdx.y * p.strideA;
-  const double *B = p.B + (int64_t)blockIdx.y * p.strideB;
-  double *C = p.C + (int64_t)blockIdx.y * p.strideC;
-  const int64_t a_step = AK ? (int64_t)BK : (int64_t)BK * p.lda;
-  const int64_t b_step = BKM ? (int64_t)BK : (int64_t)BK * p.ldb;
-
-  const int a_off = AK ? ((wm * 32 + g) * LDS_K + t) : (t * LDA_MN + wm * 32 + g);
-  const int b_off = BKM ? ((wn * 32 + g) * LDS_K + t) : (t * LDB_MN + wn * 32 + g);
-  constexpr int A_I = AK ? 8 * LDS_K : 8;
-  constexpr int A_KK = AK ? 4 : 4 * LDA_MN;
-  constexpr int B_J = BKM ? 8 * LDS_K : 8;
-  constexpr int B_KK = BKM ? 4 : 4 * LDB_MN;
-  const double alpha = p.alpha, beta = p.beta;
-
-  TileRef cur = next_tile<AK, BKM>(p, tiles, ntiles, blockIdx.x, A, B);
-  if (cur.idx < 0) return;
-  // slice 0 of the first tile
-  if (cur.KT > 0) {
-    load_slice<AK, BM, BK, (!AK && !BKM)>(As, cur.Ag, p.lda, tid);
-    load_slice<BKM, BN, BK, true>(Bs, cur.Bg, p.ldb, tid);
-  }
-  cp_async_commit();
-  unsigned gslice = 0;  // global slice counter: stage = gslice & 1
-
-  while (true) {
-    TileRef nxt = next_tile<AK, BKM>(p, tiles, ntiles, cur.idx + gridDim.x, A, B);
-    if (beta != 0.0) {  // pull the C tile towards L2 for the read-modify-write epilogue
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        int c = tid + i * NTHREADS;
-        int col = c >> 3, seg = c & 7;
-        const double *ptr = C + cur.m0 + seg * 16 + (int64_t)(cur.n0 + col) * p.ldc;
-        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ptr));
-      }
-    }
-    double acc[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    for (int cs = 0; cs < cur.KT; ++cs) {
-      cp_async_wait<0>();
-      __syncthreads();
-      {  // next slice: of this tile, or the first one of the next tile
-        const int st = (gslice + 1) & 1;
-        if (cs + 1 < cur.KT) {
-          load_slice<AK, BM, BK, (!AK && !BKM)>(As + st * A_STAGE, cur.Ag + (int64_t)(cs + 1) * a_step, p.lda, tid);
-          load_slice<BKM, BN, BK, true>(Bs + st * B_STAGE, cur.Bg + (int64_t)(cs + 1) * b_step, p.ldb, tid);
-        } else if (nxt.idx >= 0 && nxt.KT > 0) {
-          load_slice<AK, BM, BK, (!AK && !BKM)>(As + st * A_STAGE, nxt.Ag, p.lda, tid);
-          load_slice<BKM, BN, BK, true>(Bs + st * B_STAGE, nxt.Bg, p.ldb, tid);
-        }
-        cp_async_commit();
-      }
-      const double *as = As + (gslice & 1) * A_STAGE + a_off;
-      const double *bs = Bs + (gslice & 1) * B_STAGE + b_off;
-#pragma unroll
-      for (int kk = 0; kk < BK / 4; ++kk) {
-        double a[4], b[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = as[kk * A_KK + i * A_I];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = bs[kk * B_KK + j * B_J];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-      }
-      ++gslice;
-    }
-    if (cur.KT == 0 && nxt.idx >= 0 && nxt.KT > 0) {
-      // an empty k-range never started a pipeline slot for this tile: start the next tile's here
-      load_slice<AK, BM, BK, (!AK && !BKM)>(As + (gslice & 1) * A_STAGE, nxt.Ag, p.lda, tid);
-      load_slice<BKM, BN, BK, true>(Bs + (gslice & 1) * B_STAGE, nxt.Bg, p.ldb, tid);
-      cp_async_commit();
-    }
-
-    // epilogue of `cur` (the next tile's first slice is already in flight)
-    double *Cw = C + cur.m0 + wm * 32 + g + (int64_t)(cur.n0 + wn * 32 + 2 * t) * p.ldc;
-    if (beta != 0.0) {
-#pragma unroll
-      for (int jh = 0; jh < 2; ++jh) {
-        double old[2][4][2];
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-          for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) old[jj][i][r] = Cw[i * 8 + (int64_t)((jh * 2 + jj) * 8 + r) * p.ldc];
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-          for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              Cw[i * 8 + (int64_t)((jh * 2 + jj) * 8 + r) * p.ldc] =
-                  alpha * acc[i][jh * 2 + jj][r] + beta * old[jj][i][r];
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) Cw[i * 8 + (int64_t)(j * 8 + r) * p.ldc] = alpha * acc[i][j][r];
-    }
-    if (nxt.idx < 0) break;
-    cur = nxt;
-  }
-  cp_async_wait<0>();
-}
-
-
-// ---------------------------------------------------------------------------------------------
 // Bulk-copy version of the kernel (gemm_variant 4, the default): operands moved by the bulk-copy (TMA) engine
 // through an mbarrier pipeline, 128-bit fragment loads, 16-byte read-modify-write epilogue.
 //
@@ -494,7 +323,7 @@ __device__ __forceinline__ bool elect_one() {
 
 // One 16-slice of DMMAs.  as / bs point at the lane's fragment origin inside the stage; `dep` folds every
 // fragment register that was loaded (see the `empty` arrival in the kernel).
-template <bool AK, bool BKM, int BK>
+template <bool AK, bool BKM, int BK, bool FOLD>
 __device__ __forceinline__ void mma_slice_v4(double (&acc)[4][4][2], const double *as, const double *bs, int &dep) {
   using C_ = CfgB<AK, BKM, BK>;
   constexpr int LDS_K = C_::LDS_K, LDA = C_::LDA, LDB = C_::LDB;
@@ -521,8 +350,10 @@ __device__ __forceinline__ void mma_slice_v4(double (&acc)[4][4][2], const doubl
         b[2 * h] = w.x;  b[2 * h + 1] = w.y;
       }
     }
+    if constexpr (FOLD) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) dep ^= __double2hiint(a[i]) ^ __double2hiint(b[i]);
+      for (int i = 0; i < 4; ++i) dep ^= __double2hiint(a[i]) ^ __double2hiint(b[i]);
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -572,7 +403,15 @@ __device__ __forceinline__ void epilogue_v4(const double (&acc)[4][4][2], double
   }
 }
 
-template <bool AK, bool BKM, int BK>
+// Stage hand-over (consumer warp -> bulk-copy engine), selectable for measurement (option gemm_handover):
+//   HO_DEPFOLD   the arrival's address depends on every fragment register of the slice (see the main loop)
+//   HO_PRODFENCE plain arrival; the producer executes fence.proxy.async.shared::cta between its acquire of `empty` and
+//                the refill (the generic -> async proxy ordering the PTX memory model asks for, paid by the producer)
+//   HO_CONSFENCE every consumer lane executes fence.proxy.async.shared::cta before lane 0 arrives
+//   HO_NONE      plain arrival (reproduces the hazard; testing only)
+enum Handover { HO_DEPFOLD = 0, HO_PRODFENCE = 1, HO_CONSFENCE = 2, HO_NONE = 3 };
+
+template <bool AK, bool BKM, int BK, int HO>
 __global__ void __launch_bounds__(NTHREADS_B, 2) dgemm_dmma_v4_kernel(GemmArgs p, const uint32_t *__restrict__ tiles) {
   extern __shared__ __align__(16) double smem[];
   using C_ = CfgB<AK, BKM, BK>;
@@ -635,7 +474,10 @@ __global__ void __launch_bounds__(NTHREADS_B, 2) dgemm_dmma_v4_kernel(GemmArgs p
       uint32_t parity = 1;  // of the `empty` phase a refill waits for: phase -1 counts as complete
       for (int i = 0; i < KT; ++i) {
         const uint32_t full = bars + 8 * s;
-        if (i >= STAGES) mbar_wait(bars + 8 * (STAGES + s), parity);
+        if (i >= STAGES) {
+          mbar_wait(bars + 8 * (STAGES + s), parity);
+          if constexpr (HO == HO_PRODFENCE) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        }
         mbar_expect_tx(full, C_::STAGE_BYTES);
         uint32_t dst = As_u + (uint32_t)(s * A_STAGE) * 8;
 #pragma unroll 8
@@ -688,19 +530,33 @@ __global__ void __launch_bounds__(NTHREADS_B, 2) dgemm_dmma_v4_kernel(GemmArgs p
   for (int kt = 0; kt < KT; ++kt) {
     mbar_wait(bars + 8 * s, phase);
     int dep = 0;
-    mma_slice_v4<AK, BKM, BK>(acc, As + s * A_STAGE + a_off, Bs + s * B_STAGE + b_off, dep);
+    mma_slice_v4<AK, BKM, BK, HO == HO_DEPFOLD>(acc, As + s * A_STAGE + a_off, Bs + s * B_STAGE + b_off, dep);
     __syncwarp();
+    if constexpr (HO == HO_CONSFENCE) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     // An `empty` arrival hands the stage back to the bulk-copy engine (async proxy), and the arrival instruction is not
     // ordered behind shared-memory loads that have only been *issued*: with a second CTA's global-memory epilogue
     // backing up the load/store pipe, the refill was observed to land before queued fragment loads of the released
     // stage had read it (rows of one warp wrong by one slice's worth).  `dep` folds every fragment register of the
     // slice and p.zero is a run-time 0 the compiler cannot see through, so the arrival's address depends on the loads.
-    if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s) + (uint32_t)(dep & zero));
+    if constexpr (HO == HO_DEPFOLD) {
+      if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s) + (uint32_t)(dep & zero));
+    } else {
+      if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s));
+    }
     if (++s == STAGES) { s = 0; phase ^= 1; }
   }
 
   double *Cw = C + m0 + wm * 32 + 2 * g + (int64_t)(n0 + wn * 32 + 4 * t) * p.ldc;
   epilogue_v4(acc, Cw, p.ldc, p.alpha, p.beta);
+}
+
+template <bool AK, bool BKM, int HO>
+cudaError_t opt_in_v4() {
+  cudaError_t e = cudaFuncSetAttribute(dgemm_dmma_v4_kernel<AK, BKM, 16, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)CfgB<AK, BKM, 16>::SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dgemm_dmma_v4_kernel<AK, BKM, 32, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)CfgB<AK, BKM, 32>::SMEM);
 }
 
 template <bool AK, bool BKM>
@@ -711,27 +567,25 @@ cudaError_t opt_in() {
   e = cudaFuncSetAttribute(dgemm_dmma_kernel<AK, BKM, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)Cfg<AK, BKM, 32>::SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(dgemm_dmma_persistent_kernel<AK, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)Cfg<AK, BKM, 32>::SMEM);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(dgemm_dmma_v4_kernel<AK, BKM, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)CfgB<AK, BKM, 16>::SMEM);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(dgemm_dmma_v4_kernel<AK, BKM, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)CfgB<AK, BKM, 32>::SMEM);
+  return opt_in_v4<AK, BKM, HO_DEPFOLD>();
 }
 
 template <bool AK, bool BKM>
-void launch(cudaStream_t stream, const GemmArgs &a, dim3 grid, const uint32_t *tiles, int bk, int persistent_ctas,
-            int variant) {
-  if (variant == 4 && bk == 32) {
-    dgemm_dmma_v4_kernel<AK, BKM, 32><<<grid, NTHREADS_B, CfgB<AK, BKM, 32>::SMEM, stream>>>(a, tiles);
-  } else if (variant == 4) {
-    dgemm_dmma_v4_kernel<AK, BKM, 16><<<grid, NTHREADS_B, CfgB<AK, BKM, 16>::SMEM, stream>>>(a, tiles);
-  } else if (bk == 32 && persistent_ctas > 0) {
-    const int64_t ntiles = grid.x;
-    dim3 pg((unsigned)std::min<int64_t>(ntiles, persistent_ctas), grid.y, 1);
-    dgemm_dmma_persistent_kernel<AK, BKM><<<pg, NTHREADS, Cfg<AK, BKM, 32>::SMEM, stream>>>(a, tiles, ntiles);
+void launch(cudaStream_t stream, const GemmArgs &a, dim3 grid, const uint32_t *tiles, int bk, int variant) {
+  if (variant == 4) {
+    // the alternative hand-over modes exist for the MN-major-A layouts the path uses (NT, NN); others keep the default
+    const int ho = AK ? HO_DEPFOLD : a.handover;
+    auto go = [&](auto k16, auto k32) {
+      if (bk == 32) k32<<<grid, NTHREADS_B, CfgB<AK, BKM, 32>::SMEM, stream>>>(a, tiles);
+      else k16<<<grid, NTHREADS_B, CfgB<AK, BKM, 16>::SMEM, stream>>>(a, tiles);
+    };
+    if constexpr (!AK) {
+      if (ho == HO_PRODFENCE) return go(dgemm_dmma_v4_kernel<AK, BKM, 16, HO_PRODFENCE>, dgemm_dmma_v4_kernel<AK, BKM, 32, HO_PRODFENCE>);
+      if (ho == HO_CONSFENCE) return go(dgemm_dmma_v4_kernel<AK, BKM, 16, HO_CONSFENCE>, dgemm_dmma_v4_kernel<AK, BKM, 32, HO_CONSFENCE>);
+      if (ho == HO_NONE) return go(dgemm_dmma_v4_kernel<AK, BKM, 16, HO_NONE>, dgemm_dmma_v4_kernel<AK, BKM, 32, HO_NONE>);
+    }
+    (void)ho;
+    go(dgemm_dmma_v4_kernel<AK, BKM, 16, HO_DEPFOLD>, dgemm_dmma_v4_kernel<AK, BKM, 32, HO_DEPFOLD>);
   } else if (bk == 32) dgemm_dmma_kernel<AK, BKM, 32><<<grid, NTHREADS, Cfg<AK, BKM, 32>::SMEM, stream>>>(a, tiles);
   else dgemm_dmma_kernel<AK, BKM, 16><<<grid, NTHREADS, Cfg<AK, BKM, 16>::SMEM, stream>>>(a, tiles);
 }
@@ -783,24 +637,35 @@ static int32_t get_tiles(Ctx *ctx, int mt, int nt, bool lower, bool bottom_first
   return DGP_OK;
 }
 
+int32_t gemm_prepare(Ctx *ctx, int M, int N, int lower_only, int reverse) {
+  if (M <= 0 || N <= 0) return DGP_OK;
+  TileTable tt;
+  return get_tiles(ctx, M / BM, N / BN, lower_only != 0, reverse != 0, &tt);
+}
+
 int32_t gemm_init(Ctx *ctx) {
   DGP_CUDA_OK(ctx, (opt_in<false, false>()));
   DGP_CUDA_OK(ctx, (opt_in<false, true>()));
   DGP_CUDA_OK(ctx, (opt_in<true, false>()));
   DGP_CUDA_OK(ctx, (opt_in<true, true>()));
+  DGP_CUDA_OK(ctx, (opt_in_v4<false, false, HO_PRODFENCE>()));
+  DGP_CUDA_OK(ctx, (opt_in_v4<false, true, HO_PRODFENCE>()));
+  DGP_CUDA_OK(ctx, (opt_in_v4<false, false, HO_CONSFENCE>()));
+  DGP_CUDA_OK(ctx, (opt_in_v4<false, true, HO_CONSFENCE>()));
+  DGP_CUDA_OK(ctx, (opt_in_v4<false, false, HO_NONE>()));
+  DGP_CUDA_OK(ctx, (opt_in_v4<false, true, HO_NONE>()));
   return DGP_OK;
 }
 
 int32_t gemm(Ctx *ctx, cudaStream_t stream, const GemmArgs &a_in) {
   GemmArgs a = a_in;
   a.no_prefetch = ctx->gemm_no_prefetch;
+  a.handover = ctx->gemm_handover;
   if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return DGP_OK;
   if (a.M % BM || a.N % BN || a.K % 16 || a.K < 0)
     return ctx->fail(DGP_ERR_SHAPE, "gemm: M=%d N=%d K=%d must be multiples of %d/%d/16", a.M, a.N, a.K, BM, BN);
   // 32-wide slices need every k-range to be a multiple of 32 (triangular ranges are multiples of 64)
   int bk = (ctx->gemm_bk == 32 && a.K % 32 == 0) ? 32 : 16;
-  // persistent grid: two CTAs per SM, shared among the batch entries
-  const int pc = ctx->gemm_persistent ? std::max(1, 2 * ctx->sm_count / std::max(1, a.batch)) : 0;
   if ((a.lda & 1) || (a.ldb & 1) || ((uintptr_t)a.A & 15) || ((uintptr_t)a.B & 15))
     return ctx->fail(DGP_ERR_SHAPE, "gemm: operands must be 16-byte aligned with even leading dimensions");
   if (a.lower_only && a.M != a.N) return ctx->fail(DGP_ERR_SHAPE, "gemm: lower_only needs a square C");
@@ -819,10 +684,10 @@ int32_t gemm(Ctx *ctx, cudaStream_t stream, const GemmArgs &a_in) {
       (ctx->gemm_variant == 4 && v4_layout && !(a.ldc & 1) && !((uintptr_t)a.C & 15) && !(a.strideC & 1)) ? 4 : 2;
   const int layout = 2 * (a.a_kmajor ? 1 : 0) + (a.b_kmajor ? 1 : 0);
   if (variant == 4) bk = (((ctx->gemm_v4_bk32_mask >> layout) & 1) && a.K % 32 == 0) ? 32 : 16;
-  if (!a.a_kmajor && !a.b_kmajor) launch<false, false>(stream, a, grid, tt.dev, bk, pc, variant);
-  else if (!a.a_kmajor && a.b_kmajor) launch<false, true>(stream, a, grid, tt.dev, bk, pc, variant);
-  else if (a.a_kmajor && !a.b_kmajor) launch<true, false>(stream, a, grid, tt.dev, bk, pc, variant);
-  else launch<true, true>(stream, a, grid, tt.dev, bk, pc, variant);
+  if (!a.a_kmajor && !a.b_kmajor) launch<false, false>(stream, a, grid, tt.dev, bk, variant);
+  else if (!a.a_kmajor && a.b_kmajor) launch<false, true>(stream, a, grid, tt.dev, bk, variant);
+  else if (a.a_kmajor && !a.b_kmajor) launch<true, false>(stream, a, grid, tt.dev, bk, variant);
+  else launch<true, true>(stream, a, grid, tt.dev, bk, variant);
   ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;

@@ -35,6 +35,7 @@ struct GemmArgs {
   int batch = 1;
   int no_prefetch = 0; // testing: skip the L2 prefetch of the C tile (makes the epilogue slow; stresses stage hand-over)
   int zero = 0;        // always 0: a value the compiler cannot fold (see the `empty` arrival in gemm.cu)
+  int handover = 0;    // set by gemm() from ctx->gemm_handover
   int64_t strideA = 0, strideB = 0, strideC = 0;
   // Optional 2D block-cyclic mask (dist.cu): C is this rank's local part of a distributed
   // lower-triangular update, stored as T x T tiles; local tile (li, lj) is global tile
@@ -45,6 +46,9 @@ struct GemmArgs {
 
 // Enqueue on `stream`.  Returns DGP_OK or a CUDA error recorded on ctx.
 int32_t gemm(Ctx *ctx, cudaStream_t stream, const GemmArgs &args);
+// Build (and cache) the tile table an M x N product will use, so that a later gemm() of that shape neither
+// allocates nor copies inside a stream pipeline.
+int32_t gemm_prepare(Ctx *ctx, int M, int N, int lower_only, int reverse);
 int32_t gemm_init(Ctx *ctx);  // opt in to the large dynamic shared memory once per context
 void gemm_release(Ctx *ctx);  // free the cached tile tables of a context
 

@@ -440,8 +440,10 @@ class AdditiveCovariance(CompositeCovariance):
         return isinstance(self.otherKernel, DiracKernel) and not isinstance(self.firstKernel, CompositeCovariance) \
             and not isinstance(self.firstKernel, ScaledKernel)
 
-    def _spec(self, config=None, noise: float = 0.0):
-        if self._is_cov_plus_noise() and noise == 0.0:
+    def _spec(self, config=None, noise: float = 0.0, as_model_covariance: bool = False):
+        # Inside a GP model the gradient is indexed by this kernel's own hyper-parameter list followed by the
+        # model's noise level, so the sum must stay a composite there (its Dirac member is an ordinary factor).
+        if self._is_cov_plus_noise() and noise == 0.0 and not as_model_covariance:
             c1, c2 = self._configs(self.state if config is None else config)
             return self.firstKernel._spec(c1, noise=c2["noiseLevel"])
         return super()._spec(config, noise)

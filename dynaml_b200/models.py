@@ -74,6 +74,7 @@ class CudaGPRegression:
         self._data = None        # dgp_data handle (training [+ validation] set resident in HBM)
         self._data_key = None
         self._model = None       # dgp_model handle (persisted L, alpha)
+        self._train_data = None  # second resident copy without the validation set (persist / predict), made lazily
         self.caching = False
 
     # ---- reference accessors ----------------------------------------------------------------
@@ -111,6 +112,9 @@ class CudaGPRegression:
         if self._data is not None:
             self.ctx.data_destroy(self._data)
             self._data = None
+        if getattr(self, "_train_data", None) is not None:
+            self.ctx.data_destroy(self._train_data)
+            self._train_data = None
 
     def _drop_model(self):
         if self._model is not None:
@@ -144,6 +148,9 @@ class CudaGPRegression:
 
     def _spec(self):
         if self._dirac_noise:
+            from .kernels import AdditiveCovariance
+            if isinstance(self.covariance, AdditiveCovariance):
+                return self.covariance._spec(noise=self.noiseModel.state["noiseLevel"], as_model_covariance=True)
             return self.covariance._spec(noise=self.noiseModel.state["noiseLevel"])
         from .kernels import composite_spec
         return composite_spec([(self.covariance, self.covariance.state), (self.noiseModel, self.noiseModel.state)], 0.0)
@@ -221,7 +228,7 @@ class CudaGPRegression:
         X = _as_points([p[0] for p in self.g])
         y = np.asarray([p[1] for p in self.g], dtype=np.float64)
         m = np.asarray([self.mean(x) for x in X], dtype=np.float64)
-        if getattr(self, "_train_data", None) is None:
+        if self._train_data is None:
             self._train_data = self.ctx.data_create(X, y, m)
             self._attach_basis(self._train_data, X)
         return self._train_data

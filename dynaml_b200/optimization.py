@@ -22,6 +22,51 @@ import numpy as np
 Config = Dict[str, float]
 
 
+def _exp(x: float) -> float:
+    """math.exp with the JVM's IEEE semantics: overflow gives +Inf instead of raising (scala.math.exp)."""
+    with np.errstate(all="ignore"):
+        return float(np.exp(np.float64(x)))
+
+
+def _div(a: float, b: float) -> float:
+    """Double division with the JVM's IEEE semantics: x/0 = +-Inf, 0/0 = Inf/Inf = NaN, never an exception."""
+    with np.errstate(all="ignore"):
+        return float(np.float64(a) / np.float64(b))
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist
+    except Exception:  # pragma: no cover
+        pass
+    return None
+
+
+def broadcast_from_rank0(obj, group=None):
+    """Rank 0's copy of a small host object on every rank (identity outside torch.distributed).  Grids drawn from
+    priors, CSA proposals and the accept draws come from unseeded RNGs in the reference; under one process per
+    GPU they must be ONE rank's draws, or the gathered energies would be paired with other ranks' proposals."""
+    dist = _dist()
+    if dist is None or dist.get_world_size(group) == 1:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return box[0]
+
+
+def _configs_digest(configs: Sequence[Config]) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for c in configs:
+        for k in sorted(c):
+            h.update(k.encode())
+            h.update(np.float64(c[k]).tobytes())
+        h.update(b"|")
+    return h.hexdigest()
+
+
 def shard_indices(n: int, rank: int, world: int) -> List[int]:
     """Round-robin candidate -> rank map (candidate i runs on GPU i mod P)."""
     return list(range(rank, n, world))
@@ -30,25 +75,25 @@ def shard_indices(n: int, rank: int, world: int) -> List[int]:
 def sharded_energies(system, configs: Sequence[Config], options=None, group=None) -> List[float]:
     """Evaluate `configs` across the ranks of a torch.distributed group (or locally) and return
     the full list on every rank.  Only scalars travel; no collective touches the matrices."""
-    try:
-        import torch.distributed as dist
-        on = dist.is_available() and dist.is_initialized()
-    except Exception:  # pragma: no cover
-        on = False
+    dist = _dist()
+    on = dist is not None
     batch = getattr(system, "energyBatch", None)
     if batch is None:
         def batch(cs, opts=None):
             return [system.energy(c, opts or {}) for c in cs]
     if not on:
         return list(batch(list(configs), options))
-    import torch
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     mine = shard_indices(len(configs), rank, world)
     local = batch([configs[i] for i in mine], options)
-    gathered: List[List[Tuple[int, float]]] = [None] * world  # type: ignore
-    dist.all_gather_object(gathered, list(zip(mine, local)), group=group)
+    gathered: List[Tuple[str, List[Tuple[int, float]]]] = [None] * world  # type: ignore
+    dist.all_gather_object(gathered, (_configs_digest(configs), list(zip(mine, local))), group=group)
+    digests = {d for d, _ in gathered}
+    if len(digests) != 1:
+        raise RuntimeError("sharded_energies: the ranks hold different candidate lists (unsynchronised RNG?); "
+                           "every rank must pass the same configs -- see broadcast_from_rank0")
     out = [math.nan] * len(configs)
-    for part in gathered:
+    for _, part in gathered:
         for i, e in part:
             out[i] = e
     return out
@@ -102,6 +147,7 @@ class ModelTuner:
         use_prior = len(initialConfig) > 0 and all(k in prior for k in initialConfig)
         if use_prior:
             grid = [{k: float(prior[k].sample()) for k in prior} for _ in range(self.num_samples)]
+            grid = broadcast_from_rank0(grid, self.group)
         else:
             grid = self.getGrid(initialConfig)
         energies = sharded_energies(self.system, grid, options, self.group)
@@ -147,22 +193,25 @@ class AbstractCSA(ModelTuner):
     # ---- formulas (AbstractCSA.scala:268-327) -----------------------------------------------
     @staticmethod
     def couplingFactor(variant: str, landscape: Sequence[float], Tacc: float) -> float:
+        # scala.math.exp / Double arithmetic: overflow is +Inf, Inf - Inf is NaN, nothing throws (:285-300)
         if variant in (AbstractCSA.MuSA, AbstractCSA.BA):
-            return sum(math.exp(-e / Tacc) for e in landscape)
+            return float(sum(np.float64(_exp(_div(-e, Tacc))) for e in landscape))
         if variant in (AbstractCSA.M, AbstractCSA.MwVC):
-            return sum(math.exp(e / Tacc) for e in landscape)
+            return float(sum(np.float64(_exp(_div(e, Tacc))) for e in landscape))
         return 1.0
 
     @staticmethod
     def acceptanceProbability(variant: str, energy: float, oldEnergy: float, gamma: float, temperature: float) -> float:
-        if variant == AbstractCSA.MuSA:
-            x = math.exp(-energy / temperature)
-            return x / (x + gamma)
-        if variant == AbstractCSA.BA:
-            return 1.0 - math.exp(-oldEnergy / temperature) / gamma
-        if variant in (AbstractCSA.M, AbstractCSA.MwVC):
-            return math.exp(oldEnergy / temperature) / gamma
-        return gamma / (1.0 + math.exp((energy - oldEnergy) / temperature))
+        with np.errstate(all="ignore"):
+            if variant == AbstractCSA.MuSA:
+                x = np.float64(_exp(_div(-energy, temperature)))
+                return _div(x, x + np.float64(gamma))
+            if variant == AbstractCSA.BA:
+                return float(np.float64(1.0) - np.float64(_div(_exp(_div(-oldEnergy, temperature)), gamma)))
+            if variant in (AbstractCSA.M, AbstractCSA.MwVC):
+                return _div(_exp(_div(oldEnergy, temperature)), gamma)
+            return _div(gamma, np.float64(1.0) + np.float64(_exp(_div(np.float64(energy) - np.float64(oldEnergy),
+                                                                      temperature))))
 
     @staticmethod
     def varianceDesired(variant: str, m: int) -> float:
@@ -171,7 +220,7 @@ class AbstractCSA(ModelTuner):
         return 0.99 * (m - 1) / float(m) ** 2
 
     def acceptanceTemperature(self, initialTemp: float, k: int) -> float:
-        return initialTemp / math.log(k + 1.0)
+        return _div(initialTemp, math.log(k + 1.0))
 
     def mutationTemperature(self, initialTemp: float, k: int) -> float:
         return initialTemp / float(k)
@@ -186,11 +235,15 @@ class AbstractCSA(ModelTuner):
         n = len(xs)
         if n < 2:
             raise ValueError("To calculate stats size of data must be > 1")
-        m = sum(xs) / n
-        return sum((x - m) ** 2 for x in xs) / (n - 1)
+        with np.errstate(all="ignore"):
+            a = np.asarray(xs, dtype=np.float64)
+            m = a.sum() / n
+            return float(((a - m) * (a - m)).sum() / (n - 1))
 
     def performCSA(self, initialConfig: Config, options=None) -> List[Tuple[float, Config]]:
         options = options or {}
+        # one process per GPU: every rank replays rank 0's random stream (mutations, accept draws)
+        self.rng.bit_generator.state = broadcast_from_rank0(self.rng.bit_generator.state, self.group)
         sigmaD = self.varianceDesired(self.variant, int(self.gridsize ** len(initialConfig)))
         landscape = self.getEnergyLandscape(initialConfig, options, self.meanFieldPrior)
         gamma_init = self.couplingFactor(self.variant, [e for e, _ in landscape], self.iTemp)
@@ -206,7 +259,9 @@ class AbstractCSA(ModelTuner):
             else:
                 accTemp = self.acceptanceTemperature(self.iTemp, it)
             maxEnergy = max(e for e, _ in landscape)
-            coupling = self.couplingFactor(self.variant, [e - maxEnergy for e, _ in landscape], accTemp)
+            with np.errstate(all="ignore"):
+                shifted = [float(np.float64(e) - np.float64(maxEnergy)) for e, _ in landscape]
+            coupling = self.couplingFactor(self.variant, shifted, accTemp)
             # candidates of one sweep are independent given the previous landscape: one batch
             proposals = [self.mutate(cfg, mutTemp) for _, cfg in landscape]
             energies = sharded_energies(self.system, proposals, options, self.group)
@@ -214,7 +269,9 @@ class AbstractCSA(ModelTuner):
             for (old_e, old_cfg), new_cfg, e in zip(landscape, proposals, energies):
                 pe = -sum(self.meanFieldPrior[k].logPdf(v) for k, v in new_cfg.items()) if use_prior else 0.0
                 new_e = e + pe
-                p = self.acceptanceProbability(self.variant, new_e - maxEnergy, old_e - maxEnergy, coupling, accTemp)
+                with np.errstate(all="ignore"):
+                    d_new, d_old = float(np.float64(new_e) - np.float64(maxEnergy)), float(np.float64(old_e) - np.float64(maxEnergy))
+                p = self.acceptanceProbability(self.variant, d_new, d_old, coupling, accTemp)
                 if new_e < old_e or float(self.rng.random()) <= p:
                     new_landscape.append((new_e, new_cfg))
                 else:

@@ -129,6 +129,12 @@ int32_t dgp_spec_grad_len(const dgp_kernel_spec *spec);
 int32_t dgp_ctx_create(int32_t device, dgp_ctx **out);
 int32_t dgp_ctx_destroy(dgp_ctx *ctx);
 const char *dgp_last_error(const dgp_ctx *ctx);     /* NUL-terminated, owned by ctx             */
+/* Return the context's grow-only workspace (kernel matrix, inverse, panels, tile tables) to the driver.
+   Data and model handles stay valid; the next evaluation allocates again.  The analogue of the reference's
+   unpersist (AbstractGPRegressionModel.scala:418-422) for the library's own scratch.                  */
+int32_t dgp_ctx_trim(dgp_ctx *ctx);
+/* out[0] CUDA device ordinal, out[1] SM count, out[2] total / out[3] free device memory in bytes; n >= 4. */
+int32_t dgp_ctx_info(dgp_ctx *ctx, int64_t *out, int32_t n);
 const char *dgp_version(void);
 /* Tunables: "nb" (outer Cholesky block, multiple of 128; 0 = auto, the default), "lookahead"
    (0/1), "timing" (0/1), "batch_streams" (1..4 candidates of dgp_energy_batch in flight; default 3),
@@ -137,12 +143,13 @@ const char *dgp_version(void);
    mbarrier kernel where "gemm_v4_mask" allows, the default; 2 = cp.async kernel everywhere), "gemm_v4_mask" and
    "gemm_v4_bk32_mask" (bit 2*a_kmajor + b_kmajor per operand layout: layouts on the bulk-copy kernel, and
    those of them using 32-wide K-slices; defaults 3 and 2), "gemm_bk" (16/32, cp.async kernel),
-   "gemm_persistent" (0/1, experiment), "gemm_no_prefetch" (0/1, testing: no L2 prefetch of the C tile),
+   "gemm_handover" (stage hand-over of the bulk-copy kernel), "gemm_no_prefetch" (0/1, testing: no L2 prefetch of the C tile),
    "inverse_transposed" (1 = K^-1 as U U^T from U = L^-T, the default; 0 = W^T W from W = L^-1).          */
 int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value);
 /* Phase timings (ms, CUDA events) of the last energy/energy_grad/fit/predict call:
    [0] assemble [1] potrf [2] solves+logdet [3] inverse (trtri+lauum) [4] trace pass
-   [5] cross assemble [6] trsm [7] syrk [8] total.  Unused slots are 0.                         */
+   [5] cross assemble [6] trsm [7] syrk [8] total; after dgp_energy_batch [9] is the device time of the whole
+   batch.  Unused slots are 0.                                                                    */
 int32_t dgp_get_timings(const dgp_ctx *ctx, double *ms, int32_t n);
 
 /* ---- training data (replaces the Seq[(DenseVector[Double], Double)] the model holds,
@@ -246,6 +253,10 @@ int32_t dgp_dist_unique_id(void *id128);
 int32_t dgp_dist_init(dgp_ctx *ctx, const void *id128, int32_t rank, int32_t world,
                       int32_t grid_rows, int32_t grid_cols);
 int32_t dgp_dist_finalize(dgp_ctx *ctx);
+/* out[0] ranks of the library's NCCL communicator (0: none, world == 1), out[1] this context's rank in it,
+   out[2] / out[3] process grid rows / columns, out[4] 1 if the grid is emulated on one GPU, out[5] NCCL version
+   code; n >= 6.                                                                                           */
+int32_t dgp_dist_info(dgp_ctx *ctx, int32_t *out, int32_t n);
 /* Host-only layout query (no GPU needed): out[0] tiles per dimension, out[1] / out[2] local tile rows /
    columns of `rank`, out[3] lower-triangle tiles it owns, out[4] bytes of its local matrix.           */
 int32_t dgp_dist_plan(int64_t n, int32_t tile, int32_t grid_rows, int32_t grid_cols, int32_t rank, int64_t *out);
@@ -270,7 +281,9 @@ int32_t dgp_launch_count(const dgp_ctx *ctx, uint64_t *out);
 int64_t dgp_outer_block(const dgp_ctx *ctx, int64_t n);
 /* Time `reps` launches of one phase on device-resident data: returns average ms per launch.
    phase: 0 assemble (lower tiles of K+noise), 1 potrf of the assembled K, 2 trailing-update GEMM
-   at full size (M = N - nb rows, K = nb = dgp_outer_block(N): the largest launch of the step).  Used for the roofline of the dominant kernels.            */
+   at full size (M = N - nb rows, K = nb = dgp_outer_block(N): the NT launch the Cholesky repeats), 3 the
+   K^-1 = U U^T launch of the gradient path (NT, k >= row, N^3/3 flop: the largest single launch of a step),
+   4 an NN product with M = N = K = min(N, 8192) (2 M^3 flop).  Used for the roofline of the dominant kernels. */
 int32_t dgp_time_phase(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec,
                        int32_t phase, int32_t reps, double *avg_ms);
 /* Plain column-major FP64 GEMM / Cholesky on host buffers through the device kernels, for the

@@ -1,0 +1,168 @@
+"""Oracle values at the BASELINE configuration sizes -> tests/golden/large.json.
+
+The oracle needs minutes of CPU time and tens of GB of host memory at these sizes, so it is run once, here in the
+build container, and the values are committed; the GPU tests (tests/test_gpu_large.py) and bench.py's parity legs
+compare against them on the same seeded inputs (oracle.gp_oracle.synthetic).  The arithmetic is the oracle's:
+kernel entries by direct differences (orc.Kernel.value / .grads, evaluated in row blocks to bound memory), LAPACK
+dpotrf / dtrtrs / dpotri through SciPy, the energy and gradient formulas of gp_oracle.energy / grad_energy in the
+dpotri formulation of oracle/cpu_baseline.py (tests/test_cpu_baseline.py pins that formulation to gp_oracle).
+
+    python tests/golden/make_golden_large.py [case ...]       # default: every case
+"""
+import json
+import math
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import scipy.linalg as sla
+from scipy.linalg import lapack
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE.parent.parent))
+from oracle import gp_oracle as orc  # noqa: E402
+
+OUT = HERE / "large.json"
+BLOCK = 1024
+
+
+def kernel_matrix(cov, X, noise):
+    """orc.build_kernel_matrix(cov, X, dirac(noise)) in row blocks (same per-entry arithmetic)."""
+    n = X.shape[0]
+    K = np.empty((n, n))
+    for i0 in range(0, n, BLOCK):
+        K[i0:i0 + BLOCK, :] = cov.value(X[i0:i0 + BLOCK], X)
+    # DiracKernel: |noise| wherever |x - y|_2 == 0 -- for pairwise distinct points, the diagonal
+    assert len(np.unique(X, axis=0)) == n
+    K[np.diag_indices(n)] += abs(noise)
+    return K
+
+
+def energy_and_grad(cov, noise, X, y, want_grad=True):
+    n = X.shape[0]
+    t0 = time.perf_counter()
+    K = kernel_matrix(cov, X, noise)
+    c, info = lapack.dpotrf(K, lower=1, overwrite_a=1)
+    assert info == 0
+    del K
+    alpha = sla.solve_triangular(c, y, lower=True)
+    quad = float(alpha @ alpha)
+    logdet_half = float(np.log(np.diag(c)).sum())
+    e = 0.5 * (quad + logdet_half + n * math.log(2 * math.pi))
+    out = {"energy": e, "quad": quad, "logdet_half": logdet_half}
+    if want_grad:
+        alpha = sla.solve_triangular(c, alpha, lower=True, trans="T")
+        kinv, info = lapack.dpotri(c, lower=1, overwrite_c=1)  # lower triangle of K^-1
+        assert info == 0
+        names = cov.effective()
+        g = {k: 0.0 for k in names}
+        for i0 in range(0, n, BLOCK):
+            i1 = min(n, i0 + BLOCK)
+            blk = kinv[i0:i1, :i1].copy()
+            # symmetric M = alpha alpha' - K^-1 on rows i0:i1, columns 0:i1 (lower part), strict lower counted twice
+            Mb = np.outer(alpha[i0:i1], alpha[:i1]) - blk
+            Mb[:, :i0] *= 2.0
+            D = Mb[:, i0:i1]
+            D[:] = 2.0 * np.tril(D, -1) + np.diag(np.diag(D))
+            dK = cov.grads(X[i0:i1], X[:i1])
+            for k in names:
+                g[k] += float(np.sum(Mb * dK[k]))
+        # noise: d|s|/ds on the diagonal (DiracKernel.scala:49-53: value / |s| = 1 wherever |x-y| == 0)
+        g["noiseLevel"] = float(np.sum(alpha * alpha) - np.trace(kinv))
+        out["grad"] = g
+    out["seconds"] = time.perf_counter() - t0
+    return out
+
+
+def ard_kernel(d, scale=1.0):
+    return orc.Kernel("ard", {"MahalanobisAmplitude": 1.0,
+                              **{f"MahalanobisBandwidth_{i}": math.sqrt(d) * scale * (1.0 + 0.05 * i) for i in range(d)}})
+
+
+CASES = {}
+
+
+def case(f):
+    CASES[f.__name__] = f
+    return f
+
+
+@case
+def c4_check():
+    """bench.py's distributed-Cholesky parity leg: n = 8192, d = 8, SE(sqrt 8, 1), noise 0.1, seed 0."""
+    X, y, _ = orc.synthetic(8192, 8, seed=0)
+    r = energy_and_grad(orc.Kernel("se", {"bandwidth": math.sqrt(8), "amplitude": 1.0}), 0.1, X, y, want_grad=False)
+    return {"n": 8192, "d": 8, "seed": 0, "kernel": "se", "bandwidth": math.sqrt(8), "amplitude": 1.0, "noise": 0.1, **r}
+
+
+@case
+def c2():
+    """Config C2: N = 8192, d = 8, ARD-SE, energy + gradient (reference grad mode, D2)."""
+    X, y, _ = orc.synthetic(8192, 8, seed=0)
+    r = energy_and_grad(ard_kernel(8), 0.1, X, y)
+    return {"n": 8192, "d": 8, "seed": 0, "kernel": "ard", "noise": 0.1,
+            "bandwidths": [math.sqrt(8) * (1.0 + 0.05 * i) for i in range(8)], "amplitude": 1.0, **r}
+
+
+@case
+def se_stress():
+    """the worst-conditioned configuration of the tolerance contract: SE, sigma = 1e-3, N = 8192."""
+    X, y, _ = orc.synthetic(8192, 8, seed=0)
+    r = energy_and_grad(orc.Kernel("se", {"bandwidth": math.sqrt(8), "amplitude": 1.0}), 1e-3, X, y)
+    return {"n": 8192, "d": 8, "seed": 0, "kernel": "se", "bandwidth": math.sqrt(8), "amplitude": 1.0, "noise": 1e-3, **r}
+
+
+@case
+def c5():
+    """Config C5: N = 16384, d = 8, SE; three candidates of bench.py's 16 x 16 GridSearch grid (first, middle, last)."""
+    X, y, _ = orc.synthetic(16384, 8, seed=0)
+    init = {"bandwidth": 2.5 * math.sqrt(8), "noiseLevel": 0.6}
+    grid = orc.get_grid(init, 16, 0.08, True)
+    out = []
+    for idx in (0, 119, 255):
+        cfg = grid[idx]
+        r = energy_and_grad(orc.Kernel("se", {"bandwidth": cfg["bandwidth"], "amplitude": 1.0}), cfg["noiseLevel"], X, y,
+                            want_grad=False)
+        out.append({"index": idx, **cfg, **r})
+    return {"n": 16384, "d": 8, "seed": 0, "kernel": "se", "amplitude": 1.0, "init": init, "gridsize": 16, "step": 0.08,
+            "log_scale": True, "candidates": out}
+
+
+@case
+def c3():
+    """Config C3: N = 32768, d = 16, Matern-5/2 (p = 2, l = 4), noise 0.1: energy + gradient."""
+    X, y, _ = orc.synthetic(32768, 16, seed=0)
+    r = energy_and_grad(orc.Kernel("matern", {"p": 2.0, "l": 4.0}), 0.1, X, y)
+    return {"n": 32768, "d": 16, "seed": 0, "kernel": "matern", "p": 2, "l": 4.0, "noise": 0.1, **r}
+
+
+def selftest():
+    """The blocked formulation against gp_oracle.energy / grad_energy at a size the oracle does directly."""
+    global BLOCK
+    BLOCK = 100
+    X, y, _ = orc.synthetic(333, 5, seed=2)
+    for cov in (ard_kernel(5), orc.Kernel("matern", {"p": 2.0, "l": 2.0}), orc.Kernel("se", {"bandwidth": 2.0, "amplitude": 1.3})):
+        r = energy_and_grad(cov, 0.05, X, y)
+        eo, go = orc.energy(cov, 0.05, X, y), orc.grad_energy(cov, 0.05, X, y)
+        assert abs(r["energy"] - eo) <= 1e-11 * abs(eo), (r["energy"], eo)
+        scale = max(abs(v) for v in go.values())
+        for k, v in go.items():
+            assert abs(r["grad"][k] - v) <= 1e-9 * scale, (k, r["grad"][k], v)
+    BLOCK = 1024
+    print("selftest ok", flush=True)
+
+
+def main():
+    selftest()
+    want = sys.argv[1:] or list(CASES)
+    data = json.loads(OUT.read_text()) if OUT.exists() else {}
+    for name in want:
+        t0 = time.perf_counter()
+        data[name] = CASES[name]()
+        OUT.write_text(json.dumps(data, indent=1, sort_keys=True))
+        print(f"{name}: {time.perf_counter() - t0:.1f} s", flush=True)
+
+
+if __name__ == "__main__":
+    main()

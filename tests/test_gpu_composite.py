@@ -329,3 +329,24 @@ def test_general_noise_with_ard_covariance_cross_spec():
     post = model.predictiveDistribution(Xs)
     assert np.abs(post.mu - Ks.T @ alpha).max() <= TOL * np.abs(Ks.T @ alpha).max()
     assert np.abs(post.covariance - (Kss - v.T @ v)).max() <= TOL * np.abs(Kss).max()
+
+
+def test_cov_plus_dirac_as_model_covariance_with_zero_model_noise():
+    """`k + DiracKernel` used as the covariance of a model whose own noise is DiracKernel(0.0): the sum has to stay a
+    composite inside the model so that the gradient lines up with the covariance's hyper-parameter list."""
+    X, y, _ = orc.synthetic(200, 3, seed=4)
+    cov = dg.SEKernel(1.4, 1.1) + dg.DiracKernel(0.3)
+    model = dg.GPRegression(cov, dg.DiracKernel(0.0), list(zip(X, y)))
+    ok = orc.Kernel("se", {"bandwidth": 1.4, "amplitude": 1.1})
+    assert model.energy(model._current_state) == pytest.approx(orc.energy(ok, 0.3, X, y), rel=TOL)
+    g, go = model.gradEnergy(model._current_state), orc.grad_energy(ok, 0.3, X, y)
+    scale = max(abs(v) for v in go.values())
+    for name in ("bandwidth", "amplitude"):
+        assert g[name] == pytest.approx(go[name], rel=TOL, abs=TOL * scale)
+    assert "noiseLevel" in g
+    # the validation-set copy of the data is released with the model's other device blocks
+    model.validationSet_(list(zip(X[:20], y[:20])))
+    model.persist(model._current_state)
+    assert model._train_data is not None
+    model._drop_data()
+    assert model._train_data is None and model._data is None

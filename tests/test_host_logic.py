@@ -234,6 +234,82 @@ def test_candidates_shard_across_two_gloo_ranks():
     assert res[0][3] == 16 and res[1][3] == 16  # 8 of the 16 candidates, two sweeps
 
 
+class _HugeEnergySystem(FakeSystem):
+    """Energies of the size a GP NLL has at N = 32768 (|E| ~ 3e4), one candidate non-PD (+Inf)."""
+
+    def __init__(self, sign):
+        super().__init__()
+        self.sign = sign
+
+    def energy(self, h, options=None):
+        self.calls.append(dict(h))
+        if len(self.calls) % 7 == 3:
+            return math.inf
+        return self.sign * 1e4 * (1.0 + (h["a"] - 1.0) ** 2 + (h["b"] - 0.5) ** 2)
+
+
+@pytest.mark.parametrize("variant", ["CSA-MuSA", "CSA-BA", "CSA-M", "CSA-MwVC", "SA"])
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+def test_csa_runs_at_realistic_energy_magnitudes(variant, sign):
+    """AbstractCSA.scala:285-325 is plain Double arithmetic: exp overflows to Inf, Inf/Inf is NaN, nothing throws
+    (math.exp would raise OverflowError above ~709).  Every variant must get through a whole annealing run."""
+    sys_ = _HugeEnergySystem(sign)
+    csa = dg.CoupledSimulatedAnnealing(sys_, rng=np.random.default_rng(3)).setGridSize(3).setStepSize(0.2)
+    csa.setVariant(variant).setMaxIterations(4)
+    land = csa.performCSA({"a": 2.0, "b": 1.5})
+    assert len(land) == 9
+    _, best = csa.optimize({"a": 2.0, "b": 1.5})
+    assert set(best) == {"a", "b"}
+    A = dg.CoupledSimulatedAnnealing
+    for e in (3e4, -3e4, 5.0, math.inf):
+        g = A.couplingFactor(variant, [e, e + 800.0, e - 900.0], 1.0)
+        A.acceptanceProbability(variant, e, e - 1.0, g, 1.0)      # may be NaN / Inf, must not raise
+    assert A.couplingFactor("CSA-MuSA", [-3e4], 1.0) == math.inf
+    assert A.couplingFactor("CSA-MuSA", [3e4], 1.0) == 0.0
+    assert math.isnan(A.acceptanceProbability("CSA-MuSA", 3e4, 3e4, 0.0, 1.0))   # 0 / (0 + 0)
+
+
+def _gloo_csa_worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # every rank starts from its OWN random stream, as the reference's unseeded RNGs would
+        csa = dg.CoupledSimulatedAnnealing(FakeSystem(), rng=np.random.default_rng(1000 + rank))
+        csa.setGridSize(3).setStepSize(0.2).setMaxIterations(3)
+        land = csa.performCSA({"a": 2.0, "b": 1.5})
+        ok = all(abs(e - ((c["a"] - 1.0) ** 2 + (c["b"] - 0.5) ** 2)) < 1e-15 for e, c in land)
+        mismatch = None
+        try:   # ranks passing different candidate lists must be caught, not silently mis-paired
+            from dynaml_b200.optimization import sharded_energies
+            sharded_energies(FakeSystem(), [{"a": 1.0 + rank, "b": 0.0}, {"a": 0.0, "b": 1.0}])
+        except RuntimeError as ex:
+            mismatch = str(ex)
+        q.put((rank, land, ok, mismatch))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_csa_is_consistent_across_two_gloo_ranks():
+    """One process per GPU: proposals and accept draws are rank 0's on every rank, so each (energy, config) pair of
+    the landscape belongs together and all ranks end in the same state."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_csa_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1]                 # identical landscapes
+    assert res[0][2] and res[1][2]                # every energy is the energy of ITS config
+    assert res[0][3] and "different candidate lists" in res[0][3]
+
+
 # ---- 2D block-cyclic layout of the distributed Cholesky (host-only entry point of the C ABI) ----------
 @pytest.mark.parametrize("n,tile,pr,pc", [(131072, 512, 2, 4), (131072, 512, 1, 1), (10000, 256, 2, 2),
                                           (3000, 256, 1, 2), (700, 256, 2, 4)])
