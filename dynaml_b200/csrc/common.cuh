@@ -42,7 +42,7 @@ struct Ctx {
   std::map<std::tuple<int, int, int, int>, std::pair<uint32_t *, size_t>> tile_tables;
   int64_t nb = 0;     // outer Cholesky block (0 = choose from n)
   int lookahead = 1;
-  int gemm_handover = 0;  // how a DMMA warp hands a stage back to the bulk-copy engine (gemm.cu, Handover)
+  int gemm_handover = 1;  // how a DMMA warp hands a stage back to the bulk-copy engine (gemm.cu, Handover): producer-side proxy fence
   int gemm_variant = 4;  // 4 = bulk-copy / mbarrier kernel (dgemm_dmma_v4_kernel), 2 = cp.async kernel (dgemm_dmma_kernel)
   int gemm_v4_bk32_mask = 2; // layouts whose bulk-copy kernel uses 32-wide slices / two stages (NN: 34.6 vs 33.9 TFLOP/s)
   int gemm_v4_mask = 3;  // operand layouts (bit 2*a_kmajor + b_kmajor) that use the bulk-copy kernel: NT and NN (TN: 32.2 vs 33.9 for cp.async)

@@ -533,11 +533,13 @@ __global__ void __launch_bounds__(NTHREADS_B, 2) dgemm_dmma_v4_kernel(GemmArgs p
     mma_slice_v4<AK, BKM, BK, HO == HO_DEPFOLD>(acc, As + s * A_STAGE + a_off, Bs + s * B_STAGE + b_off, dep);
     __syncwarp();
     if constexpr (HO == HO_CONSFENCE) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    // An `empty` arrival hands the stage back to the bulk-copy engine (async proxy), and the arrival instruction is not
-    // ordered behind shared-memory loads that have only been *issued*: with a second CTA's global-memory epilogue
-    // backing up the load/store pipe, the refill was observed to land before queued fragment loads of the released
-    // stage had read it (rows of one warp wrong by one slice's worth).  `dep` folds every fragment register of the
-    // slice and p.zero is a run-time 0 the compiler cannot see through, so the arrival's address depends on the loads.
+    // An `empty` arrival hands the stage back to the bulk-copy engine, i.e. to the ASYNC proxy, while the fragment loads
+    // above are GENERIC-proxy reads.  mbarrier release / acquire orders them only against the producer thread's own
+    // generic accesses; the refill it then issues is an async-proxy write and needs a proxy fence in between.  Without
+    // one the refill lands before queued fragment loads have read the stage (HO_NONE: every N = 8192 factorisation
+    // wrong, scripts/handover_modes.py).  Default HO_PRODFENCE: the producer executes fence.proxy.async.shared::cta
+    // after acquiring `empty` -- the documented ordering, and free for the DMMA warps.  HO_DEPFOLD (round 1) made
+    // the arrival's address depend on every fragment register instead (16 LOP3 per slice, 1.8 % of the Cholesky).
     if constexpr (HO == HO_DEPFOLD) {
       if (lane == 0) mbar_arrive(bars + 8 * (STAGES + s) + (uint32_t)(dep & zero));
     } else {
@@ -567,25 +569,23 @@ cudaError_t opt_in() {
   e = cudaFuncSetAttribute(dgemm_dmma_kernel<AK, BKM, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)Cfg<AK, BKM, 32>::SMEM);
   if (e != cudaSuccess) return e;
-  return opt_in_v4<AK, BKM, HO_DEPFOLD>();
+  return opt_in_v4<AK, BKM, HO_PRODFENCE>();
 }
 
 template <bool AK, bool BKM>
 void launch(cudaStream_t stream, const GemmArgs &a, dim3 grid, const uint32_t *tiles, int bk, int variant) {
   if (variant == 4) {
-    // the alternative hand-over modes exist for the MN-major-A layouts the path uses (NT, NN); others keep the default
-    const int ho = AK ? HO_DEPFOLD : a.handover;
+    // the alternative hand-over modes exist for the MN-major-A layouts the path uses (NT, NN); others use the default
     auto go = [&](auto k16, auto k32) {
       if (bk == 32) k32<<<grid, NTHREADS_B, CfgB<AK, BKM, 32>::SMEM, stream>>>(a, tiles);
       else k16<<<grid, NTHREADS_B, CfgB<AK, BKM, 16>::SMEM, stream>>>(a, tiles);
     };
     if constexpr (!AK) {
-      if (ho == HO_PRODFENCE) return go(dgemm_dmma_v4_kernel<AK, BKM, 16, HO_PRODFENCE>, dgemm_dmma_v4_kernel<AK, BKM, 32, HO_PRODFENCE>);
-      if (ho == HO_CONSFENCE) return go(dgemm_dmma_v4_kernel<AK, BKM, 16, HO_CONSFENCE>, dgemm_dmma_v4_kernel<AK, BKM, 32, HO_CONSFENCE>);
-      if (ho == HO_NONE) return go(dgemm_dmma_v4_kernel<AK, BKM, 16, HO_NONE>, dgemm_dmma_v4_kernel<AK, BKM, 32, HO_NONE>);
+      if (a.handover == HO_DEPFOLD) return go(dgemm_dmma_v4_kernel<AK, BKM, 16, HO_DEPFOLD>, dgemm_dmma_v4_kernel<AK, BKM, 32, HO_DEPFOLD>);
+      if (a.handover == HO_CONSFENCE) return go(dgemm_dmma_v4_kernel<AK, BKM, 16, HO_CONSFENCE>, dgemm_dmma_v4_kernel<AK, BKM, 32, HO_CONSFENCE>);
+      if (a.handover == HO_NONE) return go(dgemm_dmma_v4_kernel<AK, BKM, 16, HO_NONE>, dgemm_dmma_v4_kernel<AK, BKM, 32, HO_NONE>);
     }
-    (void)ho;
-    go(dgemm_dmma_v4_kernel<AK, BKM, 16, HO_DEPFOLD>, dgemm_dmma_v4_kernel<AK, BKM, 32, HO_DEPFOLD>);
+    go(dgemm_dmma_v4_kernel<AK, BKM, 16, HO_PRODFENCE>, dgemm_dmma_v4_kernel<AK, BKM, 32, HO_PRODFENCE>);
   } else if (bk == 32) dgemm_dmma_kernel<AK, BKM, 32><<<grid, NTHREADS, Cfg<AK, BKM, 32>::SMEM, stream>>>(a, tiles);
   else dgemm_dmma_kernel<AK, BKM, 16><<<grid, NTHREADS, Cfg<AK, BKM, 16>::SMEM, stream>>>(a, tiles);
 }
@@ -648,8 +648,8 @@ int32_t gemm_init(Ctx *ctx) {
   DGP_CUDA_OK(ctx, (opt_in<false, true>()));
   DGP_CUDA_OK(ctx, (opt_in<true, false>()));
   DGP_CUDA_OK(ctx, (opt_in<true, true>()));
-  DGP_CUDA_OK(ctx, (opt_in_v4<false, false, HO_PRODFENCE>()));
-  DGP_CUDA_OK(ctx, (opt_in_v4<false, true, HO_PRODFENCE>()));
+  DGP_CUDA_OK(ctx, (opt_in_v4<false, false, HO_DEPFOLD>()));
+  DGP_CUDA_OK(ctx, (opt_in_v4<false, true, HO_DEPFOLD>()));
   DGP_CUDA_OK(ctx, (opt_in_v4<false, false, HO_CONSFENCE>()));
   DGP_CUDA_OK(ctx, (opt_in_v4<false, true, HO_CONSFENCE>()));
   DGP_CUDA_OK(ctx, (opt_in_v4<false, false, HO_NONE>()));
