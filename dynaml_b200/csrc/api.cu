@@ -663,7 +663,7 @@ int32_t dgp_ctx_create(int32_t device, dgp_ctx **out) {
     ok = cudaMemPoolCreate(&ctx->data_pool, &props) == cudaSuccess &&
          cudaMemPoolSetAttribute(ctx->data_pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess;
   }
-  if (ok) ok = gemm_init(ctx) == DGP_OK && potrf_init(ctx) == DGP_OK;
+  if (ok) ok = gemm_init(ctx) == DGP_OK && potrf_init(ctx) == DGP_OK && solve_init(ctx) == DGP_OK;
   if (!ok) {
     delete ctx;
     return DGP_ERR_CUDA;
@@ -742,6 +742,11 @@ int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
   } else if (!strcmp(key, "gemm_v4_mask")) {
     if (value < 0 || value > 15) return ctx->fail(DGP_ERR_ARG, "gemm_v4_mask must be in 0..15");
     ctx->gemm_v4_mask = (int)value;
+  } else if (!strcmp(key, "leaf_variant")) {
+    if (value < 0 || value > 1) return ctx->fail(DGP_ERR_ARG, "leaf_variant must be 0 or 1");
+    ctx->leaf_variant = (int)value;
+  } else if (!strcmp(key, "trsv_chained")) {
+    ctx->trsv_chained = value != 0;
   } else if (!strcmp(key, "inverse_transposed")) {
     ctx->inverse_transposed = value != 0;
   } else if (!strcmp(key, "gemm_no_prefetch")) {

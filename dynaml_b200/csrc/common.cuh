@@ -47,6 +47,9 @@ struct Ctx {
   int gemm_v4_bk32_mask = 2; // layouts whose bulk-copy kernel uses 32-wide slices / two stages (NN: 34.6 vs 33.9 TFLOP/s)
   int gemm_v4_mask = 3;  // operand layouts (bit 2*a_kmajor + b_kmajor) that use the bulk-copy kernel: NT and NN (TN: 32.2 vs 33.9 for cp.async)
   int inverse_transposed = 1;  // gradient path: K^-1 = U U^T from U = L^-T (all NT / NN products) instead of W^T W from W = L^-1
+  int leaf_variant = 1;  // 128-block leaf of the Cholesky: 1 = tile / DMMA kernel, 0 = scalar register kernel
+  int trsv_chained = 1;  // triangular solves as one chained launch per direction (0: one launch per 128-block)
+  int trsv_epoch = 0;    // flag value of the next chained solve
   int gemm_no_prefetch = 0;  // testing only: GEMMs skip the L2 prefetch of their C tile
   int gemm_bk = 32;   // K-slice of the GEMM pipeline: 16 (3-4 stages) or 32 (double buffered)
   int assembly = 0;   // 0: Gram/DMMA assembly when its error bound allows, 1: always exact differences, 2: force Gram

@@ -13,22 +13,77 @@ namespace dgp {
 namespace {
 
 constexpr int LB = 128;          // leaf block
-constexpr int LEAF_THREADS = 256;
+constexpr int LEAF_MAIN = 256;   // elimination threads (8 warps)
+constexpr int LEAF_THREADS = LEAF_MAIN + 32;  // + one pivot warp
 constexpr size_t LEAF_SMEM = 0;
+
+__device__ __forceinline__ void leaf_bar() { asm volatile("bar.sync 1, %0;\n" ::"n"(LEAF_THREADS) : "memory"); }
 
 // Cholesky + triangular inverse of one 128x128 diagonal block, register resident.
 //
-// The 256 threads form a 16x16 grid (tr, tc); thread (tr, tc) owns the elements (r, c) with
+// The 256 elimination threads form a 16x16 grid (tr, tc); thread (tr, tc) owns the elements (r, c) with
 // r = 16 i + tr, c = 16 q + tc (2D block-cyclic), i.e. an 8x8 local block of which only the local
 // lower part i >= q is live (36 FP64 values for L, 36 for W = L^-1).  Each elimination step
 // broadcasts one column of L and one row of W through double-buffered 128-entry lines in shared
-// memory and costs a single __syncthreads; all register indices are compile-time after unrolling
+// memory and costs a single barrier; all register indices are compile-time after unrolling
 // the 16-wide column blocks, so nothing spills.
+//
+// The 128 reciprocal square roots form the serial chain of the factorisation; a ninth warp runs it one column
+// AHEAD of the elimination: with column k the owners also publish a(k+1,k+1) as it stands before that column's
+// update, and the pivot warp forms l = a(k+1,k) / l_kk, d = a(k+1,k+1) - l^2 and 1 / sqrt(d) -- the same three
+// operations, in the same order and precision, that the elimination threads apply to that element -- while they
+// are busy with the rank-1 updates of step k.  No elimination thread executes an rsqrt or waits for one.
+//
+// blockIdx.x > 0: copy CTAs.  The panel below the diagonal block is multiplied by inv(L)^T right after this
+// kernel, by a GEMM whose CTAs share input rows and therefore cannot run in place; CTA b copies rows
+// [128 (b-1), 128 b) of the panel (panel_src, leading dimension lda) to the scratch operand of that product
+// (leading dimension mrows) underneath the factorisation.
+// (nine warps put three on one SM sub-partition, whose 16 K registers then allow 168 per thread: ptxas spills ~28 values)
 __global__ void __launch_bounds__(LEAF_THREADS, 1)
-leaf_potrf_inv_kernel(double *A, int64_t lda, double *Inv, int *info, int pivot_base) {
+leaf_potrf_inv_kernel(double *A, int64_t lda, double *Inv, int *info, int pivot_base, const double *panel_src,
+                      double *scratch, int64_t mrows) {
   __shared__ double colbuf[2][LB];
   __shared__ double rowbuf[2][LB];
+  __shared__ double dnext[2];  // a(k+1,k+1) at the start of step k
+  __shared__ double liv[2];    // 1 / l_kk of step k
   const int tid = threadIdx.x;
+
+  if (blockIdx.x > 0) {
+    if (tid < LEAF_MAIN) {
+      const int64_t r = (int64_t)(blockIdx.x - 1) * LB + (tid & (LB - 1));
+      const double *src = panel_src + r;
+      double *dst = scratch + r;
+#pragma unroll 8
+      for (int c = tid >> 7; c < LB; c += 2) dst[(int64_t)c * mrows] = src[(int64_t)c * lda];
+    }
+    return;
+  }
+
+  if (tid >= LEAF_MAIN) {
+    // ---- pivot warp (all lanes compute the same scalars; lane 0 publishes) ----------------------------------
+    double d = A[0];
+    if (!(d > 0.0)) {
+      if (tid == LEAF_MAIN) atomicCAS(info, 0, pivot_base + 1);
+      d = 1.0;
+    }
+    double li = rsqrt(d);
+    if (tid == LEAF_MAIN) liv[0] = li;
+    for (int k = 0; k < LB; ++k) {
+      leaf_bar();  // column k, a(k+1,k+1) and (from here) liv[k & 1] are visible
+      if (k + 1 < LB) {
+        const double l = colbuf[k & 1][k + 1] * li;      // L(k+1, k)
+        double dn = fma(-l, l, dnext[k & 1]);            // a(k+1,k+1) after the update of column k
+        if (!(dn > 0.0)) {                               // also catches NaN
+          if (tid == LEAF_MAIN) atomicCAS(info, 0, pivot_base + k + 2);
+          dn = 1.0;
+        }
+        li = rsqrt(dn);
+        if (tid == LEAF_MAIN) liv[(k + 1) & 1] = li;
+      }
+    }
+    return;
+  }
+
   const int tr = tid & 15, tc = tid >> 4;
 
   double a[8][8], w[8][8];
@@ -40,7 +95,7 @@ leaf_potrf_inv_kernel(double *A, int64_t lda, double *Inv, int *info, int pivot_
       a[i][q] = (i >= q) ? A[(i * 16 + tr) + (int64_t)(q * 16 + tc) * lda] : 0.0;
     }
 
-  // ---- factorisation and inverse, fused: one elimination step and one __syncthreads per column ----
+  // ---- factorisation and inverse, fused: one elimination step and one barrier per column ----
   // Step k: column k of the trailing matrix and row k of R = (running) L W - I travel through shared
   // memory; then  l = sqrt(a_kk), L(:,k) = a(:,k)/l, a(r,c) -= L(r,k) L(c,k)   (Cholesky)
   // and           W(k,:) = R(k,:)/l,  R(i,:) -= L(i,k) W(k,:) for i > k        (L W = I, right-looking).
@@ -58,15 +113,14 @@ leaf_potrf_inv_kernel(double *A, int64_t lda, double *Inv, int *info, int pivot_
 #pragma unroll
         for (int q = 0; q <= kc; ++q) rb[q * 16 + tc] = w[kc][q];
       }
-      __syncthreads();
-      double d = cb[k];
-      if (!(d > 0.0)) {  // also catches NaN; uniform across the CTA
-        if (tid == 0) atomicCAS(info, 0, pivot_base + k + 1);
-        d = 1.0;
+      {  // the next pivot, before this column's update, for the pivot warp
+        const int kn = (k + 1) & 15;
+        if (tr == kn && tc == kn && k + 1 < LB) dnext[k & 1] = (kk < 15) ? a[kc][kc] : a[(kc + 1) & 7][(kc + 1) & 7];
       }
-      // every thread needs 1/l: rsqrt + one multiply instead of a redundant sqrt and divide on all
-      // 256 threads (the FP64 pipe, not latency, bounds this step); l = d * rsqrt(d) is within 1 ulp
-      const double li = rsqrt(d);
+      leaf_bar();
+      double d = cb[k];
+      if (!(d > 0.0)) d = 1.0;  // the pivot warp has flagged it and used the same substitute
+      const double li = liv[k & 1];
       const double l = d * li;
       double lr[8], lc[8], wk[8];
 #pragma unroll
@@ -131,6 +185,337 @@ leaf_potrf_inv_kernel(double *A, int64_t lda, double *Inv, int *info, int pivot_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Tile leaf (the default): the same 128x128 Cholesky + inverse, blocked by 8 columns on the FP64 tensor pipe.
+//
+// The scalar leaf above issues ~200 instructions per thread and column, a tenth of them useful FMAs (ncu / SASS:
+// 64 us per block, 4.1 of the 9.1 ms of an N = 8192 factorisation).  Here L and W = L^-1 live in shared memory as
+// 136 lower 8x8 tiles each, stored in DMMA accumulator order, and one elimination step handles a whole tile column kb:
+//   1. warp 0 factors the 8x8 diagonal tile (registers, unrolled) -> L88, inv(L88);
+//   2. one thread per row scales the panel below, L(r, :) = A(r, :) inv(L88)^T, and one thread per column the
+//      8 new rows of the inverse, W(blk, c) = inv(L88) R(blk, c); both land in fragment-ordered panel buffers;
+//   3. all eight warps apply the rank-8 updates A(I,J) -= L(I,kb) L(J,kb)^T (kb < J <= I) and
+//      R(I,J) -= L(I,kb) W(kb,J) (J <= kb < I) as two chained mma.sync.m8n8k4.f64 per tile, tiles dealt round-robin.
+// 16 steps of three barriers instead of 128 steps of ~1000 clk.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int T8 = 8, NT8 = LB / T8, NTILES8 = NT8 * (NT8 + 1) / 2;  // 16 x 16 tiles, 136 on / below the diagonal
+constexpr int TL_THREADS = 256;
+constexpr int TL_OFF_A = 0;
+constexpr int TL_OFF_W = TL_OFF_A + NTILES8 * 64;
+constexpr int TL_OFF_PA = TL_OFF_W + NTILES8 * 64;   // [2][128][4]  -L(r, 4 kh + t): A operand of both updates
+constexpr int TL_OFF_PB = TL_OFF_PA + 2 * LB * 4;    // [2][128][4]   L(c, 4 kh + t): B operand of the Cholesky update
+constexpr int TL_OFF_PW = TL_OFF_PB + 2 * LB * 4;    // [2][128][4]   W(8 kb + 4 kh + t, c): B operand of the inverse update
+constexpr int TL_OFF_I88 = TL_OFF_PW + 2 * LB * 4;   // [8][8] inverse of the diagonal tile's factor (upper part zero)
+constexpr size_t TL_SMEM = (size_t)(TL_OFF_I88 + 64) * sizeof(double);
+
+// Work items of the update phase, per elimination step kb: up to four horizontally adjacent tiles of one tile row
+// (they share the A fragments).  Cholesky items first -- the very first one is the next diagonal tile, which warp 0
+// takes before it factors that tile underneath the other warps' updates -- then the items of the inverse.
+constexpr int TL_MAX_ITEMS = 1024;
+struct ItemTab {
+  unsigned int off[NT8 + 1];
+  unsigned int item[TL_MAX_ITEMS];  // inverse flag << 24 | I << 16 | J0 << 8 | count
+};
+constexpr ItemTab make_items() {
+  ItemTab t{};
+  int n = 0;
+  for (int kb = 0; kb < NT8; ++kb) {
+    t.off[kb] = (unsigned int)n;
+    for (int I = kb + 1; I < NT8; ++I)
+      for (int J0 = kb + 1; J0 <= I; J0 += 4) {
+        const int cnt = (I - J0 + 1) < 4 ? (I - J0 + 1) : 4;
+        t.item[n++] = (unsigned int)((I << 16) | (J0 << 8) | cnt);
+      }
+    for (int I = kb + 1; I < NT8; ++I)
+      for (int J0 = 0; J0 <= kb; J0 += 4) {
+        const int cnt = (kb - J0 + 1) < 4 ? (kb - J0 + 1) : 4;
+        t.item[n++] = (unsigned int)((1u << 24) | (I << 16) | (J0 << 8) | cnt);
+      }
+  }
+  t.off[NT8] = (unsigned int)n;
+  return t;
+}
+__constant__ ItemTab c_items = make_items();
+
+struct TilePos {
+  unsigned char I[NTILES8], J[NTILES8];
+};
+constexpr TilePos make_tilepos() {
+  TilePos t{};
+  int n = 0;
+  for (int I = 0; I < NT8; ++I)
+    for (int J = 0; J <= I; ++J) {
+      t.I[n] = (unsigned char)I;
+      t.J[n] = (unsigned char)J;
+      ++n;
+    }
+  return t;
+}
+__constant__ TilePos c_tilepos = make_tilepos();   // tile index I (I + 1) / 2 + J -> (I, J)
+
+__device__ __forceinline__ int tix(int I, int J) { return (I * (I + 1)) / 2 + J; }
+
+__device__ __forceinline__ void dmma884_leaf(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// 1 / sqrt(d) for a normal positive d: MUFU.RSQ64H seed (relative error 2^-22) and one Newton step with the cubic
+// term, y (1 + e/2 + 3 e^2/8), e = 1 - d y^2 (error of the iteration 5 e^3/16 ~ 2^-67): accurate to the rounding of its
+// four dependent operations, about two ulp.  The library rsqrt() adds a second step and a guarded call sequence for
+// denormals and specials (which the pivot test has excluded); FP64 latency is what the 128-pivot chain consists of.
+__device__ __forceinline__ double rsqrt_pos(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(d));
+  const double t = d * y;
+  const double e = fma(-t, y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
+}
+
+// Value of lane `src` of this lane's group of eight.  Raw shfl.sync: the calling warp is converged by construction
+// (a warp-uniform branch), which the compiler cannot see -- __shfl_sync there is wrapped in WARPSYNC / ENDCOLLECTIVE
+// pairs, tripling the instruction count of the factorisation's serial chain.
+__device__ __forceinline__ double shfl8(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  // c = ((32 - width) << 8) | 0x1f  with width 8: segments of eight lanes
+  asm volatile("shfl.sync.idx.b32 %0, %0, %2, 0x181f, 0xffffffff;\n\tshfl.sync.idx.b32 %1, %1, %2, 0x181f, 0xffffffff;\n"
+               : "+r"(lo), "+r"(hi)
+               : "r"(src));
+  return __hiloint2double(hi, lo);
+}
+
+// Cholesky factor and inverse of the 8x8 tile D (row-major, lower part read) by one warp: lane & 7 is a row of
+// the factorisation (and then a column of the inverse); the four groups of eight lanes work redundantly, group 0
+// stores.  Results: D (in place, upper part zeroed), i88 and Wtile = inv(L).  Pivots <= 0 or NaN flag `info`.
+__device__ __forceinline__ void factor_tile8(double *D, double *i88, double *Wtile, int *info, int pivot0, int lane) {
+  const int i = lane & 7;
+  double l[8], li[8];
+#pragma unroll
+  for (int b = 0; b < 8; b += 2) {
+    const double2 x = *reinterpret_cast<const double2 *>(D + i * 8 + b);
+    l[b] = x.x;
+    l[b + 1] = x.y;
+  }
+  int bad = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    double d = shfl8(l[k], k);   // a_kk, held by the lane of row k
+    const bool ok = d > 0.0;      // false for NaN too
+    bad = (!ok && bad == 0) ? k + 1 : bad;
+    d = ok ? d : 1.0;
+    // 1 / sqrt(d) as in rsqrt_pos, with the Newton correction applied to the column entry directly:
+    // l_ik = a_ik y (1 + e (1/2 + 3 e / 8)) -- one dependent operation fewer on the pivot chain than (a_ik * r)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(d));
+    const double x0 = ((i == k) ? d : l[k]) * y;
+    const double tt = d * y;
+    const double e = fma(-tt, y, 1.0);
+    const double cc = fma(0.375, e, 0.5);
+    li[k] = fma(y * e, cc, y);
+    const double lk = fma(x0 * e, cc, x0);
+    l[k] = lk;
+    // the next pivot first, from this lane's own value: its update must not wait for a shuffle
+    if (k + 1 < 8 && i == k + 1) l[k + 1] = fma(-lk, lk, l[k + 1]);
+#pragma unroll
+    for (int j = k + 1; j < 8; ++j) {
+      const double ljk = shfl8(lk, j);
+      if (i > j || (i == j && j != k + 1)) l[j] = fma(-lk, ljk, l[j]);   // rows i < j hold nothing that is used
+    }
+  }
+  if (bad != 0 && lane == 0) atomicCAS(info, 0, pivot0 + bad);
+  if (lane < 8) {
+#pragma unroll
+    for (int b = 0; b < 8; b += 2) {
+      double2 x;
+      x.x = (b <= i) ? l[b] : 0.0;
+      x.y = (b + 1 <= i) ? l[b + 1] : 0.0;
+      *reinterpret_cast<double2 *>(D + i * 8 + b) = x;
+    }
+  }
+  __syncwarp();
+  // V = L^-1, one column per lane (column k = lane & 7), right-looking so that each row costs one multiply and one
+  // independent FMA per remaining row:  v_r = -s_r / l_rr,  s_r' += l_r'r v_r  (r' > r);  v_k = 1 / l_kk, v_r = 0 above
+  const int k = i;
+  double v[8], sacc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) sacc[r] = 0.0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    v[r] = (r > k) ? -sacc[r] * li[r] : ((r == k) ? li[r] : 0.0);
+#pragma unroll
+    for (int q = r + 1; q < 8; ++q) sacc[q] = fma(D[q * 8 + r], v[r], sacc[q]);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      i88[r * 8 + k] = v[r];
+      Wtile[r * 8 + k] = v[r];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TL_THREADS, 1)
+leaf_tile_kernel(double *A, int64_t lda, double *Inv, int *info, int pivot_base, const double *panel_src,
+                 double *scratch, int64_t mrows) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x;
+  if (blockIdx.x > 0) {  // copy CTAs: the panel below the block -> scratch operand of the panel product
+    const int64_t r = (int64_t)(blockIdx.x - 1) * LB + (tid & (LB - 1));
+    const double *src = panel_src + r;
+    double *dst = scratch + r;
+#pragma unroll 8
+    for (int c = tid >> 7; c < LB; c += 2) dst[(int64_t)c * mrows] = src[(int64_t)c * lda];
+    return;
+  }
+  double *sA = sm + TL_OFF_A, *sW = sm + TL_OFF_W, *pA = sm + TL_OFF_PA, *pB = sm + TL_OFF_PB, *pW = sm + TL_OFF_PW;
+  double *i88 = sm + TL_OFF_I88;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp-uniform for the compiler as well
+  const int g = lane >> 2, t = lane & 3;
+
+  // ---- load the lower tiles, one tile per warp instruction pair: lane (g, t) fetches the two elements of its
+  //      accumulator slot (eight consecutive rows of a column are one 64-byte segment), conflict-free 16-byte
+  //      shared-memory stores; 34 independent loads in flight per lane.  Clear W. -----------------------------------
+  {
+    double2 v[NTILES8 / 8];
+#pragma unroll
+    for (int n = 0; n < NTILES8 / 8; ++n) {
+      const int ti = warp + 8 * n;
+      const int I = c_tilepos.I[ti], J = c_tilepos.J[ti];
+      const double *src = A + (I * 8 + g) + (int64_t)(J * 8 + 2 * t) * lda;
+      v[n].x = src[0];
+      v[n].y = src[lda];
+    }
+#pragma unroll
+    for (int n = 0; n < NTILES8 / 8; ++n) reinterpret_cast<double2 *>(sA + (warp + 8 * n) * 64)[lane] = v[n];
+    for (int idx = tid; idx < NTILES8 * 32; idx += TL_THREADS) reinterpret_cast<double2 *>(sW)[idx] = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  if (warp == 0) factor_tile8(sA, i88, sW, info, pivot_base, lane);
+  __syncthreads();
+
+  for (int kb = 0; kb < NT8; ++kb) {
+    // ---- panel below (threads 0..127: one row each) and the new rows of W (threads 128..255: one column) ---------
+    if (tid < LB) {
+      const int r = tid;
+      if (r >= (kb + 1) * T8) {
+        double *row = sA + tix(r >> 3, kb) * 64 + (r & 7) * 8;
+        double x[8], yv[8];
+#pragma unroll
+        for (int b = 0; b < 8; b += 2) {
+          const double2 q = *reinterpret_cast<const double2 *>(row + b);
+          x[b] = q.x;
+          x[b + 1] = q.y;
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {  // L(r, a) = sum_{b <= a} A(r, b) inv88(a, b)
+          double s = 0.0;
+#pragma unroll
+          for (int b = 0; b <= a; ++b) s = fma(x[b], i88[a * 8 + b], s);
+          yv[a] = s;
+        }
+#pragma unroll
+        for (int b = 0; b < 8; b += 2) {
+          double2 q, n;
+          q.x = yv[b];  q.y = yv[b + 1];
+          n.x = -yv[b];  n.y = -yv[b + 1];
+          *reinterpret_cast<double2 *>(row + b) = q;
+          *reinterpret_cast<double2 *>(pB + (b >> 2) * LB * 4 + r * 4 + (b & 3)) = q;
+          *reinterpret_cast<double2 *>(pA + (b >> 2) * LB * 4 + r * 4 + (b & 3)) = n;
+        }
+      }
+    } else {
+      const int c = tid - LB;
+      if (c < (kb + 1) * T8) {
+        double yv[8];
+        if (c >= kb * T8) {  // inside the block: W = inv88
+#pragma unroll
+          for (int a = 0; a < 8; ++a) yv[a] = i88[a * 8 + (c - kb * T8)];
+        } else {
+          double *col = sW + tix(kb, c >> 3) * 64 + (c & 7);
+          double x[8];
+#pragma unroll
+          for (int b = 0; b < 8; ++b) x[b] = col[b * 8];
+#pragma unroll
+          for (int a = 0; a < 8; ++a) {  // W(8 kb + a, c) = sum_{b <= a} inv88(a, b) R(8 kb + b, c)
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b <= a; ++b) s = fma(i88[a * 8 + b], x[b], s);
+            yv[a] = s;
+          }
+#pragma unroll
+          for (int a = 0; a < 8; ++a) col[a * 8] = yv[a];
+        }
+#pragma unroll
+        for (int b = 0; b < 8; b += 2) {
+          double2 q;
+          q.x = yv[b];  q.y = yv[b + 1];
+          *reinterpret_cast<double2 *>(pW + (b >> 2) * LB * 4 + c * 4 + (b & 3)) = q;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- rank-8 updates on the tensor pipe.  Warp 0 updates the next diagonal tile and factors it at once (the
+    //      128 reciprocal square roots are the serial chain of the block); warps 1..7 share the other items. --------
+    {
+      const int first = (int)c_items.off[kb], nitems = (int)c_items.off[kb + 1] - first;
+      const int q0 = warp == 0 ? 0 : warp, qstep = warp == 0 ? nitems : 7, qend = warp == 0 ? (nitems > 0 ? 1 : 0) : nitems;
+      for (int q = q0; q < qend; q += qstep) {
+        const unsigned int item = c_items.item[first + q];
+        const int I = (item >> 16) & 0xff, J0 = (item >> 8) & 0xff, cnt = item & 0xff;
+        double *base = (item >> 24) ? sW : sA;
+        const double *pb = (item >> 24) ? pW : pB;
+        const double a0 = pA[(I * 8 + g) * 4 + t], a1 = pA[LB * 4 + (I * 8 + g) * 4 + t];
+        double2 *ct = reinterpret_cast<double2 *>(base + tix(I, J0) * 64) + lane;   // tiles of a row are adjacent
+        double2 cv[4];
+        double b0[4], b1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int uu = u < cnt ? u : 0;
+          cv[u] = ct[uu * 32];
+          b0[u] = pb[((J0 + uu) * 8 + g) * 4 + t];
+          b1[u] = pb[LB * 4 + ((J0 + uu) * 8 + g) * 4 + t];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          dmma884_leaf(cv[u].x, cv[u].y, a0, b0[u]);
+          dmma884_leaf(cv[u].x, cv[u].y, a1, b1[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (u < cnt) ct[u * 32] = cv[u];
+      }
+      if (warp == 0 && kb + 1 < NT8) {
+        __syncwarp();
+        factor_tile8(sA + tix(kb + 1, kb + 1) * 64, i88, sW + tix(kb + 1, kb + 1) * 64, info, pivot_base + (kb + 1) * T8,
+                     lane);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- write back L (upper part zeroed) and W, tile by tile in accumulator order ------------------------------------
+#pragma unroll 4
+  for (int n = 0; n < NT8 * NT8 / 8; ++n) {
+    const int tp = warp + 8 * n, I = tp >> 4, J = tp & 15;
+    double2 lv = make_double2(0.0, 0.0), wv = make_double2(0.0, 0.0);
+    if (I >= J) {
+      lv = reinterpret_cast<const double2 *>(sA + tix(I, J) * 64)[lane];
+      wv = reinterpret_cast<const double2 *>(sW + tix(I, J) * 64)[lane];
+      if (I == J) {  // the strictly upper part of a diagonal tile is scratch
+        if (g < 2 * t) lv.x = wv.x = 0.0;
+        if (g < 2 * t + 1) lv.y = wv.y = 0.0;
+      }
+    }
+    double *da = A + (I * 8 + g) + (int64_t)(J * 8 + 2 * t) * lda;
+    double *di = Inv + (I * 8 + g) + (J * 8 + 2 * t) * LB;
+    da[0] = lv.x;
+    da[lda] = lv.y;
+    di[0] = wv.x;
+    di[LB] = wv.y;
+  }
+}
+
 // W diagonal tiles <- leaf inverses
 __global__ void copy_diag_blocks_kernel(const double *inv, double *W, int64_t ldw) {
   const int b = blockIdx.x;
@@ -185,16 +570,19 @@ int32_t factor_block_column(Ctx *ctx, cudaStream_t st, double *A, int64_t lda, i
       DGP_TRY(gemm(ctx, st, u));
     }
     double *invb = inv + (cs / LB) * LB * LB;
-    leaf_potrf_inv_kernel<<<1, LEAF_THREADS, LEAF_SMEM, st>>>(A + cs + cs * lda, lda, invb, info, (int)cs);
+    const int64_t rb = cs + LB, mrows = n - rb;
+    // one launch: the leaf, and (extra CTAs) the copy of the panel below it to the scratch operand of the panel
+    // product -- two CTAs of that GEMM share each 128-row strip, so it cannot run in place
+    if (ctx->leaf_variant == 1)
+      leaf_tile_kernel<<<(unsigned)(1 + mrows / LB), TL_THREADS, TL_SMEM, st>>>(
+          A + cs + cs * lda, lda, invb, info, (int)cs, A + rb + cs * lda, scratch, mrows);
+    else
+      leaf_potrf_inv_kernel<<<(unsigned)(1 + mrows / LB), LEAF_THREADS, LEAF_SMEM, st>>>(
+          A + cs + cs * lda, lda, invb, info, (int)cs, A + rb + cs * lda, scratch, mrows);
     ctx->launches++;
     DGP_CUDA_OK(ctx, cudaGetLastError());
-    const int64_t rb = cs + LB;
     if (rb >= n) break;
-    // panel: A[rb:, cs:cs+128] <- A[rb:, cs:cs+128] * inv(L_cs)^T, through a scratch copy of the
-    // panel (two CTAs share each 128-row strip, so the product cannot run in place)
-    const int64_t mrows = n - rb;
-    DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(scratch, mrows * sizeof(double), A + rb + cs * lda, lda * sizeof(double),
-                                       mrows * sizeof(double), LB, cudaMemcpyDeviceToDevice, st));
+    // panel: A[rb:, cs:cs+128] <- A[rb:, cs:cs+128] * inv(L_cs)^T
     GemmArgs g;
     g.A = scratch;            g.lda = mrows;  g.a_kmajor = 0;
     g.B = invb;               g.ldb = LB;     g.b_kmajor = 0;   // op(B)(k,n) = inv(n,k)
@@ -209,15 +597,16 @@ int32_t factor_block_column(Ctx *ctx, cudaStream_t st, double *A, int64_t lda, i
 }  // namespace
 
 int32_t potrf_init(Ctx *ctx) {
-  (void)ctx;
+  DGP_CUDA_OK(ctx, cudaFuncSetAttribute(leaf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM));
   return DGP_OK;
 }
 
-// Wider blocks amortise the per-tile prologue/epilogue of the trailing update (measured on B200,
-// scripts/tune.py: N = 32768 -> 404 / 386 / 382 ms at nb = 256 / 512 / 768), narrower ones shorten
-// the leaf -> panel -> update chain that bounds small N.
+// Wider blocks amortise the per-tile prologue/epilogue of the trailing update, narrower ones shorten the
+// leaf -> panel -> update chain that bounds small N.  Measured on B200 with the tile leaf (scripts/tune_nb2.py,
+// profiles/tune_nb_r2.txt; ms at nb = 256 / 512 / 768): N = 8192 8.35 / 8.98 / 9.66, N = 16384 46.9 / 47.4 / 47.8,
+// N = 24576 147.9 / 146.9 / 147.7, N = 32768 (round 1) 404 / 386 / 382.
 int64_t potrf_outer_block(const Ctx *ctx, int64_t n) {
-  return ctx->nb > 0 ? ctx->nb : (n >= 24576 ? 768 : (n >= 12288 ? 512 : 256));
+  return ctx->nb > 0 ? ctx->nb : (n >= 28672 ? 768 : (n >= 20480 ? 512 : 256));
 }
 
 int32_t potrf_blocked(Ctx *ctx, double *A, int64_t lda, int64_t n, double *inv, int *info) {

@@ -131,6 +131,140 @@ __global__ void __launch_bounds__(ST) trsv_bwd_step_kernel(const double *L, int6
   if (tid < SB) x[(int64_t)j * SB + tid] = w[tid];
 }
 
+// ---- chained solves: ONE launch per direction ------------------------------------------------------------------
+// One CTA per 128-row block, all in one grid.  CTA i consumes the solved segments x_j as their CTAs publish them
+// (a release store of the call's epoch to flags[j]; the consumer polls with an acquire load), so the 2 N/128
+// dependent launches of the step kernels above -- 8-15 us each, launch latency included -- become one dependent
+// flag hand-over (~1-2 us) per block, and the off-diagonal blocks of a row stream while earlier segments are
+// still being solved.  A CTA waits only for CTAs of lower blockIdx; the hardware dispatches CTAs in index order,
+// so every CTA waited for is resident or finished, whatever else occupies the GPU.
+// The arithmetic is the step kernels', operation for operation: results are bit-identical.
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr size_t CHAIN_SMEM = (size_t)(SB * SB + 2 * 8 * SB + SB) * sizeof(double);
+
+__global__ void __launch_bounds__(ST, 1) trsv_fwd_chain_kernel(const double *L, int64_t ldl, const double *inv, double *x,
+                                                               int *flags, int epoch) {
+  extern __shared__ __align__(16) double sm[];
+  double *invs = sm;                 // inverse of this block's diagonal block, staged while the row streams
+  double *part = sm + SB * SB;       // [2][8][SB]
+  double *v = part + 2 * 8 * SB;     // [SB]
+  const int tid = threadIdx.x, r = tid & 127, h = tid >> 7;
+  const int i = blockIdx.x;
+  {
+    const double *src = inv + (int64_t)i * SB * SB;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) invs[tid + u * ST] = src[tid + u * ST];
+  }
+  double xi = (h == 0) ? x[(int64_t)i * SB + r] : 0.0;
+  const double *Lrow = L + (int64_t)i * SB + r + (int64_t)(h * 16) * ldl;
+  for (int j = 0; j < i; ++j) {
+    double m[16];
+    const double *blk = Lrow + (int64_t)j * SB * ldl;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) m[u] = blk[(int64_t)u * ldl];   // in flight while the flag is polled
+    if (tid == 0)
+      while (ld_acquire_gpu(flags + j) != epoch) {}
+    __syncthreads();   // x_j is visible; the parts of block j-1 are complete
+    if (h == 0 && j > 0) {
+      const double *pp = part + ((j - 1) & 1) * 8 * SB;
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += pp[q * SB + r];
+      xi -= s;
+    }
+    const double *xj = x + (int64_t)j * SB + h * 16;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+    for (int u = 0; u < 16; u += 4) {
+      acc0 = fma(m[u + 0], __ldcg(xj + u + 0), acc0);
+      acc1 = fma(m[u + 1], __ldcg(xj + u + 1), acc1);
+      acc2 = fma(m[u + 2], __ldcg(xj + u + 2), acc2);
+      acc3 = fma(m[u + 3], __ldcg(xj + u + 3), acc3);
+    }
+    part[(j & 1) * 8 * SB + h * SB + r] = (acc0 + acc1) + (acc2 + acc3);
+  }
+  __syncthreads();
+  if (h == 0) {
+    if (i > 0) {
+      const double *pp = part + ((i - 1) & 1) * 8 * SB;
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += pp[q * SB + r];
+      xi -= s;
+    }
+    v[r] = xi;
+  }
+  __syncthreads();
+  xi = rowblock_mv(invs, SB, v, part);  // lower triangular with explicit zeros
+  if (h == 0) {
+    x[(int64_t)i * SB + r] = xi;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) st_release_gpu(flags + i, epoch);
+}
+
+__global__ void __launch_bounds__(ST, 1) trsv_bwd_chain_kernel(const double *L, int64_t ldl, const double *inv, double *x,
+                                                               int *flags, int epoch, int nblk) {
+  extern __shared__ __align__(16) double sm[];
+  double *invs = sm;
+  double *v = sm + SB * SB;   // [SB]  x_b of the block being consumed
+  double *w = v + SB;         // [SB]  this block's running right-hand side
+  const int tid = threadIdx.x;
+  const int j = nblk - 1 - (int)blockIdx.x;   // column block solved here; waits for blocks b > j = lower blockIdx
+  {
+    const double *src = inv + (int64_t)j * SB * SB;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) invs[tid + u * ST] = src[tid + u * ST];
+  }
+  if (tid < SB) w[tid] = x[(int64_t)j * SB + tid];
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int b = nblk - 1; b > j; --b) {
+    double m[4][4];
+    const double *blk = L + (int64_t)b * SB + (int64_t)j * SB * ldl;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double *col = blk + (int64_t)(warp * 4 + u) * ldl;
+      m[u][0] = col[lane];
+      m[u][1] = col[lane + 32];
+      m[u][2] = col[lane + 64];
+      m[u][3] = col[lane + 96];
+    }
+    if (tid == 0)
+      while (ld_acquire_gpu(flags + (nblk - 1 - b)) != epoch) {}
+    __syncthreads();
+    const double *xb = x + (int64_t)b * SB;
+    const double v0 = __ldcg(xb + lane), v1 = __ldcg(xb + lane + 32), v2 = __ldcg(xb + lane + 64),
+                 v3 = __ldcg(xb + lane + 96);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      double s = (m[u][0] * v0 + m[u][1] * v1) + (m[u][2] * v2 + m[u][3] * v3);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) w[warp * 4 + u] -= s;   // each warp owns its four columns of w
+    }
+  }
+  __syncthreads();
+  if (tid < SB) v[tid] = w[tid];
+  __syncthreads();
+  colblock_dot(invs, SB, v, [&](int c, double s) { w[c] = s; });
+  __syncthreads();
+  if (tid < SB) {
+    x[(int64_t)j * SB + tid] = w[tid];
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) st_release_gpu(flags + blockIdx.x, epoch);
+}
+
 __device__ __forceinline__ double block_reduce_1024(double s, double *sh) {
   const int tid = threadIdx.x;
   sh[tid] = s;
@@ -197,13 +331,40 @@ __global__ void __launch_bounds__(256) mirror_lower_kernel(double *A, int64_t ld
 
 }  // namespace
 
+// Flag words of the chained solves: one array per stream (solves on one stream are ordered, so they can share it;
+// every call uses a fresh epoch value, so the words never need resetting).
+static int32_t chain_flags(Ctx *ctx, cudaStream_t st, int nblk, int **flags, int *epoch) {
+  char name[48];
+  snprintf(name, sizeof name, "trsv_flags@%p", (void *)st);
+  const bool fresh = ctx->arena.find(name) == ctx->arena.end() || ctx->arena[name].second < (size_t)2 * nblk * sizeof(int);
+  int *f = (int *)ctx->buf(name, (size_t)2 * nblk * sizeof(int));
+  if (!f) return DGP_ERR_OOM;
+  if (fresh) DGP_CUDA_OK(ctx, cudaMemsetAsync(f, 0, (size_t)2 * nblk * sizeof(int), st));
+  *flags = f;
+  *epoch = ++ctx->trsv_epoch;
+  return DGP_OK;
+}
+
+int32_t solve_init(Ctx *ctx) {
+  DGP_CUDA_OK(ctx, cudaFuncSetAttribute(trsv_fwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM));
+  DGP_CUDA_OK(ctx, cudaFuncSetAttribute(trsv_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM));
+  return DGP_OK;
+}
+
 int32_t trsv_lower_fwd(Ctx *ctx, cudaStream_t st, const double *L, int64_t ldl, const double *inv, int64_t n,
                        double *x) {
   const int nblk = (int)(n / SB);
   if (nblk == 0) return DGP_OK;
-  trsv_fwd_step_kernel<<<1, ST, 0, st>>>(L, ldl, inv, x, -1);
-  for (int b = 0; b + 1 < nblk; ++b) trsv_fwd_step_kernel<<<nblk - 1 - b, ST, 0, st>>>(L, ldl, inv, x, b);
-  ctx->launches += nblk;
+  if (ctx->trsv_chained) {
+    int *flags = nullptr, epoch = 0;
+    DGP_TRY(chain_flags(ctx, st, nblk, &flags, &epoch));
+    trsv_fwd_chain_kernel<<<nblk, ST, CHAIN_SMEM, st>>>(L, ldl, inv, x, flags, epoch);
+    ctx->launches++;
+  } else {
+    trsv_fwd_step_kernel<<<1, ST, 0, st>>>(L, ldl, inv, x, -1);
+    for (int b = 0; b + 1 < nblk; ++b) trsv_fwd_step_kernel<<<nblk - 1 - b, ST, 0, st>>>(L, ldl, inv, x, b);
+    ctx->launches += nblk;
+  }
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
 }
@@ -212,9 +373,16 @@ int32_t trsv_lower_bwd(Ctx *ctx, cudaStream_t st, const double *L, int64_t ldl, 
                        double *x) {
   const int nblk = (int)(n / SB);
   if (nblk == 0) return DGP_OK;
-  trsv_bwd_step_kernel<<<1, ST, 0, st>>>(L, ldl, inv, x, nblk, nblk);
-  for (int b = nblk - 1; b >= 1; --b) trsv_bwd_step_kernel<<<b, ST, 0, st>>>(L, ldl, inv, x, b, nblk);
-  ctx->launches += nblk;
+  if (ctx->trsv_chained) {
+    int *flags = nullptr, epoch = 0;
+    DGP_TRY(chain_flags(ctx, st, nblk, &flags, &epoch));
+    trsv_bwd_chain_kernel<<<nblk, ST, CHAIN_SMEM, st>>>(L, ldl, inv, x, flags + nblk, epoch, nblk);
+    ctx->launches++;
+  } else {
+    trsv_bwd_step_kernel<<<1, ST, 0, st>>>(L, ldl, inv, x, nblk, nblk);
+    for (int b = nblk - 1; b >= 1; --b) trsv_bwd_step_kernel<<<b, ST, 0, st>>>(L, ldl, inv, x, b, nblk);
+    ctx->launches += nblk;
+  }
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;
 }

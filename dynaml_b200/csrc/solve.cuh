@@ -5,6 +5,8 @@
 
 namespace dgp {
 
+int32_t solve_init(Ctx *ctx);  // opt in to the dynamic shared memory of the chained solves, once per context
+
 // x <- L^-1 x (forward) using the diagonal-block inverses; n % 128 == 0.
 // recLTriagSolve, CORE/algebra/PartitionedMatrixSolvers.scala:28-63.
 int32_t trsv_lower_fwd(Ctx *ctx, cudaStream_t st, const double *L, int64_t ldl, const double *inv, int64_t n,

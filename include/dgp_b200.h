@@ -144,7 +144,9 @@ const char *dgp_version(void);
    "gemm_v4_bk32_mask" (bit 2*a_kmajor + b_kmajor per operand layout: layouts on the bulk-copy kernel, and
    those of them using 32-wide K-slices; defaults 3 and 2), "gemm_bk" (16/32, cp.async kernel),
    "gemm_handover" (stage hand-over of the bulk-copy kernel), "gemm_no_prefetch" (0/1, testing: no L2 prefetch of the C tile),
-   "inverse_transposed" (1 = K^-1 as U U^T from U = L^-T, the default; 0 = W^T W from W = L^-1).          */
+   "inverse_transposed" (1 = K^-1 as U U^T from U = L^-T, the default; 0 = W^T W from W = L^-1),
+   "trsv_chained" (1 = each triangular solve is one launch whose CTAs hand the solved segments over through
+   flags, the default; 0 = one launch per 128-row block; same results).                                     */
 int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value);
 /* Phase timings (ms, CUDA events) of the last energy/energy_grad/fit/predict call:
    [0] assemble [1] potrf [2] solves+logdet [3] inverse (trtri+lauum) [4] trace pass

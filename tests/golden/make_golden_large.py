@@ -39,22 +39,67 @@ def kernel_matrix(cov, X, noise):
     return K
 
 
-def energy_and_grad(cov, noise, X, y, want_grad=True):
+BIG = 4096   # block edge of the out-of-LAPACK path below
+
+
+def _chol_solve_inverse_blocked(K, y, want_inv):
+    """N >= 32768: SciPy's LP64 OpenBLAS crashes inside dpotrf / dpotri at this size (2^30 elements), so the
+    factorisation goes through NumPy's ILP64 LAPACK (np.linalg.cholesky -> dpotrf) and the triangular solve and
+    inverse are blocked by hand: dtrtrs on BIG x BIG diagonal blocks, dgemm for everything else.
+    Returns (L, z = L^-1 y, alpha = L^-T z, lower triangle of K^-1 or None)."""
+    n = K.shape[0]
+    L = np.linalg.cholesky(K)
+    nb = range(0, n, BIG)
+    z = y.astype(np.float64).copy()
+    for j in nb:
+        z[j:j + BIG] = sla.solve_triangular(L[j:j + BIG, j:j + BIG], z[j:j + BIG], lower=True)
+        z[j + BIG:] -= L[j + BIG:, j:j + BIG] @ z[j:j + BIG]
+    alpha = z.copy()
+    for j in reversed(nb):
+        alpha[j:j + BIG] = sla.solve_triangular(L[j:j + BIG, j:j + BIG], alpha[j:j + BIG], lower=True, trans="T")
+        alpha[:j] -= L[j:j + BIG, :j].T @ alpha[j:j + BIG]
+    if not want_inv:
+        return L, z, alpha, None
+    W = np.zeros_like(L)                       # W = L^-1, block column by block column
+    eye = np.eye(BIG)
+    for j in nb:
+        W[j:j + BIG, j:j + BIG] = sla.solve_triangular(L[j:j + BIG, j:j + BIG], eye[:min(BIG, n - j), :min(BIG, n - j)], lower=True)
+        for i in range(j + BIG, n, BIG):
+            acc = L[i:i + BIG, j:i] @ W[j:i, j:j + BIG]
+            W[i:i + BIG, j:j + BIG] = -sla.solve_triangular(L[i:i + BIG, i:i + BIG], acc, lower=True)
+    kinv = np.zeros_like(L)                    # lower blocks of W' W
+    for j in nb:
+        for i in range(j, n, BIG):
+            kinv[i:i + BIG, j:j + BIG] = W[i:, i:i + BIG].T @ W[i:, j:j + BIG]
+    return L, z, alpha, kinv
+
+
+def energy_and_grad(cov, noise, X, y, want_grad=True, blocked=None):
     n = X.shape[0]
     t0 = time.perf_counter()
     K = kernel_matrix(cov, X, noise)
-    c, info = lapack.dpotrf(K, lower=1, overwrite_a=1)
-    assert info == 0
-    del K
-    alpha = sla.solve_triangular(c, y, lower=True)
+    if blocked is None:
+        blocked = n >= 32768
+    if blocked:
+        c, z, alpha_full, kinv_b = _chol_solve_inverse_blocked(K, y, want_grad)
+        del K
+        alpha = z
+    else:
+        c, info = lapack.dpotrf(K, lower=1, overwrite_a=1)
+        assert info == 0
+        del K
+        alpha = sla.solve_triangular(c, y, lower=True)
     quad = float(alpha @ alpha)
     logdet_half = float(np.log(np.diag(c)).sum())
     e = 0.5 * (quad + logdet_half + n * math.log(2 * math.pi))
     out = {"energy": e, "quad": quad, "logdet_half": logdet_half}
     if want_grad:
-        alpha = sla.solve_triangular(c, alpha, lower=True, trans="T")
-        kinv, info = lapack.dpotri(c, lower=1, overwrite_c=1)  # lower triangle of K^-1
-        assert info == 0
+        if blocked:
+            alpha, kinv = alpha_full, kinv_b
+        else:
+            alpha = sla.solve_triangular(c, alpha, lower=True, trans="T")
+            kinv, info = lapack.dpotri(c, lower=1, overwrite_c=1)  # lower triangle of K^-1
+            assert info == 0
         names = cov.effective()
         g = {k: 0.0 for k in names}
         for i0 in range(0, n, BLOCK):
@@ -149,6 +194,15 @@ def selftest():
         scale = max(abs(v) for v in go.values())
         for k, v in go.items():
             assert abs(r["grad"][k] - v) <= 1e-9 * scale, (k, r["grad"][k], v)
+    # the hand-blocked path used at N >= 32768 against the LAPACK one
+    global BIG
+    BIG = 128
+    cov = orc.Kernel("matern", {"p": 2.0, "l": 2.0})
+    a, b = energy_and_grad(cov, 0.05, X, y, blocked=False), energy_and_grad(cov, 0.05, X, y, blocked=True)
+    assert abs(a["energy"] - b["energy"]) <= 1e-13 * abs(a["energy"])
+    for k in a["grad"]:
+        assert abs(a["grad"][k] - b["grad"][k]) <= 1e-10 * max(abs(v) for v in a["grad"].values()), k
+    BIG = 4096
     BLOCK = 1024
     print("selftest ok", flush=True)
 
