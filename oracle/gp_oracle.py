@@ -42,7 +42,7 @@ Config = Dict[str, float]
 def _sqdist(X: np.ndarray, Y: np.ndarray, w: np.ndarray | None = None) -> np.ndarray:
     """sum_c w_c (x_c - y_c)^2 for every pair; chunked to bound memory."""
     n, m = X.shape[0], Y.shape[0]
-    out = np.zeros((n, m))
+    out = np.zeros((n, m), dtype=np.result_type(X, Y))  # float64, or longdouble for oracle/extended.py
     for c in range(X.shape[1]):
         diff = X[:, c][:, None] - Y[:, c][None, :]
         out += diff * diff if w is None else w[c] * (diff * diff)  # diff.t * (bandwidth * diff)
@@ -50,7 +50,7 @@ def _sqdist(X: np.ndarray, Y: np.ndarray, w: np.ndarray | None = None) -> np.nda
 
 
 def _l1dist(X: np.ndarray, Y: np.ndarray) -> np.ndarray:
-    out = np.zeros((X.shape[0], Y.shape[0]))
+    out = np.zeros((X.shape[0], Y.shape[0]), dtype=np.result_type(X, Y))
     for c in range(X.shape[1]):
         out += np.abs(X[:, c][:, None] - Y[:, c][None, :])
     return out

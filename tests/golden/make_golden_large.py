@@ -43,13 +43,23 @@ BIG = 4096   # block edge of the out-of-LAPACK path below
 
 
 def _chol_solve_inverse_blocked(K, y, want_inv):
-    """N >= 32768: SciPy's LP64 OpenBLAS crashes inside dpotrf / dpotri at this size (2^30 elements), so the
-    factorisation goes through NumPy's ILP64 LAPACK (np.linalg.cholesky -> dpotrf) and the triangular solve and
-    inverse are blocked by hand: dtrtrs on BIG x BIG diagonal blocks, dgemm for everything else.
+    """N >= 32768: both OpenBLAS builds in this image (SciPy's LP64 and NumPy's ILP64) crash inside their threaded
+    dpotrf / dpotri at this size, so the factorisation, the triangular solves and the inverse are blocked by hand:
+    LAPACK (dpotrf, dtrtrs) on BIG x BIG diagonal blocks only, dgemm for everything else.
     Returns (L, z = L^-1 y, alpha = L^-T z, lower triangle of K^-1 or None)."""
     n = K.shape[0]
-    L = np.linalg.cholesky(K)
     nb = range(0, n, BIG)
+    # right-looking blocked Cholesky in place (lower): dpotrf on BIG x BIG diagonal blocks, dtrsm / dgemm around them
+    L = K
+    for j in nb:
+        L[j:j + BIG, j:j + BIG] = sla.cholesky(L[j:j + BIG, j:j + BIG], lower=True)
+        if j + BIG < n:
+            L[j + BIG:, j:j + BIG] = sla.solve_triangular(L[j:j + BIG, j:j + BIG], L[j + BIG:, j:j + BIG].T, lower=True).T
+            for i in range(j + BIG, n, BIG):
+                L[i:i + BIG, j + BIG:i + BIG] -= L[i:i + BIG, j:j + BIG] @ L[j + BIG:i + BIG, j:j + BIG].T
+    for j in nb:   # the strictly upper blocks still hold K: clear them
+        L[j:j + BIG, j + BIG:] = 0.0
+        L[j:j + BIG, j:j + BIG] = np.tril(L[j:j + BIG, j:j + BIG])
     z = y.astype(np.float64).copy()
     for j in nb:
         z[j:j + BIG] = sla.solve_triangular(L[j:j + BIG, j:j + BIG], z[j:j + BIG], lower=True)

@@ -187,7 +187,9 @@ def test_energy_grad_ragged_sizes_vs_oracle(n, d, noise):
     g, go = model.gradEnergy(model._current_state), orc.grad_energy(ok, noise, X, y)
     scale = max(abs(v) for v in go.values())
     for name, v in go.items():
-        assert g[name] == pytest.approx(v, rel=1e-7 if noise < 0.01 else TOL, abs=TOL * scale), name
+        # 1e-9 at the stress noise as well: tests/test_gpu_arbitration.py shows device and oracle both within
+        # ~4e-12 of the extended-precision value there
+        assert g[name] == pytest.approx(v, rel=TOL, abs=TOL * scale), name
 
 
 def test_mean_function_and_validation_set():
