@@ -368,6 +368,27 @@ def run_c5(ctx, D: Dist, rank: int, args) -> dict:
             rels.append(abs(e_dev - c["energy"]) / abs(c["energy"]))
         out["oracle_candidates"] = [c["index"] for c in gold["candidates"]]
         out["max_rel_vs_oracle"] = max(rels)
+    # -- the same landscape from ONE process driving every GPU of the run (dgp_energy_batch_multi: DynaML is a single
+    #    JVM); the other ranks have released their workspaces and wait at the barrier
+    if world > 1:
+        ctx.trim()
+        D.barrier()
+        if rank == 0:
+            try:
+                model.useDevices(list(range(world)))
+                model.energyBatch(gs.getGrid(init)[: 3 * world])          # warm-up on every device
+                gs.group = "local"                                         # no torch.distributed sharding for this leg
+                t0 = time.perf_counter()
+                land1 = [(e, c) for e, c in zip(model.energyBatch(gs.getGrid(init)), gs.getGrid(init))]
+                dt1 = time.perf_counter() - t0
+                out["single_process"] = {"what": "dgp_energy_batch_multi: one host process, one context per GPU, "
+                                                 "candidates round-robin over the GPUs", "n_gpus": world, "seconds": dt1,
+                                         "candidates_per_s": len(land1) / dt1,
+                                         "identical_to_sharded_run": [e for e, _ in land1] == [e for e, _ in land]}
+            except Exception as ex:
+                out["single_process"] = {"error": f"{type(ex).__name__}: {ex}"}
+            model.useDevices([])
+        D.barrier()
     model._drop_data()
     return out
 

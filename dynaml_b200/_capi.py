@@ -34,7 +34,7 @@ EXPORTS = [
     "dgp_predict", "dgp_dist_unique_id", "dgp_dist_init", "dgp_dist_finalize", "dgp_dist_plan", "dgp_dist_energy",
     "dgp_measure_peaks", "dgp_launch_count", "dgp_outer_block", "dgp_time_phase", "dgp_test_gemm", "dgp_test_potrf",
     "dgp_spec_grad_len", "dgp_data_set_basis", "dgp_model_set_test_basis", "dgp_model_solve", "dgp_model_cross_apply",
-    "dgp_model_set_cross_spec", "dgp_ctx_trim", "dgp_dist_info", "dgp_ctx_info",
+    "dgp_model_set_cross_spec", "dgp_ctx_trim", "dgp_dist_info", "dgp_ctx_info", "dgp_energy_batch_multi",
 ]
 
 
@@ -86,6 +86,7 @@ def load_library() -> C.CDLL:
         "dgp_model_terms": (i32, [vp, vp, _dp, _dp]),
         "dgp_energy_grad": (i32, [vp, vp, sp, _dp, _dp]),
         "dgp_energy_batch": (i32, [vp, vp, sp, i32, _dp, C.POINTER(i32)]),
+        "dgp_energy_batch_multi": (i32, [C.POINTER(vp), C.POINTER(vp), i32, sp, i32, _dp, C.POINTER(i32)]),
         "dgp_fit": (i32, [vp, vp, sp, C.POINTER(vp)]),
         "dgp_model_destroy": (i32, [vp, vp]),
         "dgp_model_energy": (i32, [vp, vp, _dp]),
@@ -331,6 +332,19 @@ class Context:
         self.check(self.lib.dgp_energy_batch(self.h, data, arr, n, _ptr(e), status.ctypes.data_as(C.POINTER(C.c_int32))))
         return e, status
 
+    @staticmethod
+    def energy_batch_multi(ctxs, datas, specs):
+        """dgp_energy_batch_multi: candidate i on ctxs[i % len(ctxs)], all GPUs concurrently, one process."""
+        n, nc = len(specs), len(ctxs)
+        arr = (KernelSpec * n)(*[s for s, _ in specs])
+        hc = (C.c_void_p * nc)(*[c.h for c in ctxs])
+        hd = (C.c_void_p * nc)(*[d for d in datas])
+        e = np.empty(n)
+        status = np.zeros(n, dtype=np.int32)
+        ctxs[0].check(ctxs[0].lib.dgp_energy_batch_multi(hc, hd, nc, arr, n, _ptr(e),
+                                                         status.ctypes.data_as(C.POINTER(C.c_int32))))
+        return e, status
+
     # -- fit / predict ----------------------------------------------------------------------
     def fit(self, data, spec):
         s, keep = spec
@@ -449,6 +463,19 @@ def dist_plan(n: int, tile: int, grid_rows: int, grid_cols: int, rank: int) -> d
         raise DgpError(st, "dgp_dist_plan: bad arguments")
     return {"tiles": out[0], "local_rows": out[1], "local_cols": out[2], "owned_lower_tiles": out[3],
             "local_bytes": out[4]}
+
+
+def device_count() -> int:
+    """GPUs visible to this process (0 without a driver)."""
+    try:
+        cudart = C.CDLL("libcudart.so")
+    except OSError:
+        try:
+            cudart = C.CDLL("libcudart.so.12")
+        except OSError:
+            return 0
+    n = C.c_int(0)
+    return int(n.value) if cudart.cudaGetDeviceCount(C.byref(n)) == 0 else 0
 
 
 _default_ctx: Context | None = None

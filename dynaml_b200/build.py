@@ -70,19 +70,22 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 def build_cpp_mirror_test(force: bool = False) -> Path:
-    """The C++ host mirror (include/dynaml_b200.hpp) compiled against the C ABI: tests/cpp/host_mirror_test.cpp."""
+    """The compiled-language side of the C ABI: tests/cpp/host_mirror_test.cpp (the C++ host mirror,
+    include/dynaml_b200.hpp) and tests/cpp/multi_gpu_batch_test.cpp (candidates over several GPUs from one process)."""
     root = ROOT.parent
-    src = root / "tests" / "cpp" / "host_mirror_test.cpp"
     out = LIBDIR / "host_mirror_test"
-    deps = [src, root / "include" / "dynaml_b200.hpp", root / "include" / "dgp_b200.h", LIB]
-    if src.exists() and (force or _stale(out, deps)):
-        cmd = ["g++", "-std=c++17", "-O2", "-I", str(root / "include"), str(src), "-o", str(out),
-               "-L", str(LIBDIR), "-ldgp_b200", "-Wl,-rpath,$ORIGIN"]
-        if ASAN:
-            cmd += ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"g++ failed for {src}:\n{r.stdout}\n{r.stderr}")
+    for name in ("host_mirror_test", "multi_gpu_batch_test"):
+        src = root / "tests" / "cpp" / f"{name}.cpp"
+        exe = LIBDIR / name
+        deps = [src, root / "include" / "dynaml_b200.hpp", root / "include" / "dgp_b200.h", LIB]
+        if src.exists() and (force or _stale(exe, deps)):
+            cmd = ["g++", "-std=c++17", "-O2", "-pthread", "-I", str(root / "include"), str(src), "-o", str(exe),
+                   "-L", str(LIBDIR), "-ldgp_b200", "-Wl,-rpath,$ORIGIN"]
+            if ASAN:
+                cmd += ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"g++ failed for {src}:\n{r.stdout}\n{r.stderr}")
     return out
 
 

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <utility>
 
 #include "assemble.cuh"
@@ -967,6 +968,49 @@ int32_t dgp_energy_batch(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec 
   }
   collect_timings(ctx, false);
   ctx->timings[9] = batch_ms;  // device time of the whole batch (first enqueue to the last read-back)
+  return DGP_OK;
+}
+
+int32_t dgp_energy_batch_multi(dgp_ctx *const *ctxs, const dgp_data *const *data, int32_t n_ctx,
+                               const dgp_kernel_spec *specs, int32_t n, double *e, int32_t *status) {
+  if (!ctxs || !data || n_ctx < 1 || !specs || !e || !status || n < 0) return DGP_ERR_ARG;
+  for (int32_t c = 0; c < n_ctx; ++c)
+    if (!ctxs[c] || !data[c]) return DGP_ERR_ARG;
+  if (n_ctx == 1) return dgp_energy_batch(ctxs[0], data[0], specs, n, e, status);
+  for (int32_t c = 0; c < n_ctx; ++c) {
+    if (data[c]->N != data[0]->N || data[c]->d != data[0]->d)
+      return ctxs[0]->fail(DGP_ERR_SHAPE, "energy_batch_multi: the data handles must hold the same training set");
+    for (int32_t b = 0; b < c; ++b)
+      if (ctxs[b] == ctxs[c]) return ctxs[0]->fail(DGP_ERR_ARG, "energy_batch_multi: a context is listed twice");
+  }
+  // Candidate i runs on context i mod n_ctx (the round-robin of SURVEY 8e).  One host thread per context: a dgp_ctx
+  // is single-threaded but distinct contexts are independent, and every entry point selects its own device, so the
+  // shards run concurrently on their GPUs; only scalars come back.
+  std::vector<std::vector<dgp_kernel_spec>> shard(n_ctx);
+  std::vector<std::vector<double>> se(n_ctx);
+  std::vector<std::vector<int32_t>> ss(n_ctx);
+  for (int32_t i = 0; i < n; ++i) shard[i % n_ctx].push_back(specs[i]);
+  std::vector<int32_t> rc(n_ctx, DGP_OK);
+  std::vector<std::thread> workers;
+  for (int32_t c = 0; c < n_ctx; ++c) {
+    se[c].resize(shard[c].size());
+    ss[c].resize(shard[c].size());
+    workers.emplace_back([&, c] {
+      rc[c] = shard[c].empty() ? DGP_OK
+                               : dgp_energy_batch(ctxs[c], data[c], shard[c].data(), (int32_t)shard[c].size(), se[c].data(),
+                                                  ss[c].data());
+    });
+  }
+  for (auto &w : workers) w.join();
+  for (int32_t c = 0; c < n_ctx; ++c)
+    if (rc[c] != DGP_OK) {
+      if (c != 0) ctxs[0]->fail(rc[c], "energy_batch_multi: context %d: %s", c, ctxs[c]->err.c_str());
+      return rc[c];
+    }
+  for (int32_t i = 0; i < n; ++i) {
+    e[i] = se[i % n_ctx][i / n_ctx];
+    status[i] = ss[i % n_ctx][i / n_ctx];
+  }
   return DGP_OK;
 }
 

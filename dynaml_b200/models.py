@@ -75,6 +75,7 @@ class CudaGPRegression:
         self._data_key = None
         self._model = None       # dgp_model handle (persisted L, alpha)
         self._train_data = None  # second resident copy without the validation set (persist / predict), made lazily
+        self._peers: List[Tuple[_capi.Context, object]] = []  # (context, data handle) on further GPUs for energyBatch
         self.caching = False
 
     # ---- reference accessors ----------------------------------------------------------------
@@ -107,8 +108,33 @@ class CudaGPRegression:
         self.current_state = {**self.covariance.state, **self.noiseModel.state}
         return self
 
+    # ---- further GPUs for the candidate loop (one process) ---------------------------
+    def useDevices(self, devices: Sequence[int]):
+        """Shard `energyBatch` (hence GridSearch / CSA sweeps) over these GPUs from this one process: the training
+        set is replicated on each, candidate i runs on devices[i % len(devices)] (dgp_energy_batch_multi).  The
+        model's own context counts as the first device; energy / gradEnergy / prediction stay on it."""
+        self._drop_peers()
+        own_seen = False
+        for dev in devices:
+            if int(dev) == self.ctx.device and not own_seen:
+                own_seen = True      # the model's own context
+                continue
+            self._peers.append((_capi.Context(int(dev)), None))   # a further context (a device may be listed twice)
+        return self
+
+    def _drop_peers(self, contexts: bool = True):
+        for i, (c, h) in enumerate(self._peers):
+            if h is not None:
+                c.data_destroy(h)
+            self._peers[i] = (c, None)
+        if contexts:
+            for c, _ in self._peers:
+                c.close()
+            self._peers = []
+
     # ---- device residency -------------------------------------------------------------------
     def _drop_data(self):
+        self._drop_peers(contexts=False)
         if self._data is not None:
             self.ctx.data_destroy(self._data)
             self._data = None
@@ -125,6 +151,7 @@ class CudaGPRegression:
         try:
             self._drop_model()
             self._drop_data()
+            self._drop_peers()
         except Exception:
             pass
 
@@ -144,6 +171,9 @@ class CudaGPRegression:
         pass
 
     def _attach_test_basis(self, model, Xs: np.ndarray) -> None:
+        pass
+
+    def _attach_basis_on(self, ctx, handle, X: np.ndarray) -> None:
         pass
 
     def _spec(self):
@@ -180,7 +210,21 @@ class CudaGPRegression:
             specs.append(self._spec())
         if not specs:
             return []
-        e, status = self.ctx.energy_batch(self._device_data(), specs)
+        if self._peers:
+            pts = self.g + self.validationSet
+            for i, (c, h) in enumerate(self._peers):
+                if h is None:
+                    X = _as_points([p[0] for p in pts])
+                    y = np.asarray([p[1] for p in pts], dtype=np.float64)
+                    m = np.asarray([self.mean(x) for x in X], dtype=np.float64)
+                    h = c.data_create(X, y, m)
+                    self._attach_basis_on(c, h, X)
+                    self._peers[i] = (c, h)
+            ctxs = [self.ctx] + [c for c, _ in self._peers]
+            datas = [self._device_data()] + [h for _, h in self._peers]
+            e, status = _capi.Context.energy_batch_multi(ctxs, datas, specs)
+        else:
+            e, status = self.ctx.energy_batch(self._device_data(), specs)
         bad = [int(s) for s in status if s not in (_capi.DGP_OK, _capi.DGP_ERR_NOT_PD)]
         if bad:
             raise _capi.DgpError(bad[0], "energy batch: a candidate could not be evaluated")
@@ -321,6 +365,9 @@ class GPBasisFuncRegression(CudaGPRegression):
 
     def _attach_basis(self, handle, X):
         self.ctx.data_set_basis(handle, self._features(X))
+
+    def _attach_basis_on(self, ctx, handle, X):
+        ctx.data_set_basis(handle, self._features(X))
 
     def _attach_test_basis(self, model, Xs):
         self.ctx.model_set_test_basis(model, self._features(Xs))

@@ -15,8 +15,10 @@
  *  - point sets X are N x d.  x_layout == DGP_ROW_MAJOR means point i occupies
  *    X[i*d .. i*d+d-1] (a packed Seq[DenseVector[Double]]); DGP_COL_MAJOR means a Breeze N x d matrix.
  *  - the caller owns every host pointer; the library copies in/out before returning (synchronous).
- *  - a dgp_ctx is bound to ONE GPU (one process per GPU) and is NOT thread-safe: the reference
- *    model mutates kernel state in setState (CORE/models/gp/AbstractGPRegressionModel.scala:117-128).
+ *  - a dgp_ctx is bound to ONE GPU and is NOT thread-safe: the reference model mutates kernel state in
+ *    setState (CORE/models/gp/AbstractGPRegressionModel.scala:117-128).  Distinct contexts are independent:
+ *    one context per host thread per GPU is a supported pattern (every entry point selects its context's
+ *    device for the calling thread), and dgp_energy_batch_multi drives several contexts from one call.
  *  - there is no CPU fallback: without a usable sm_100 device dgp_ctx_create fails with DGP_ERR_CUDA.
  */
 #ifndef DGP_B200_H
@@ -226,6 +228,14 @@ int32_t dgp_energy_grad(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spe
    without aborting the batch.  Returns DGP_OK unless the batch itself could not run.           */
 int32_t dgp_energy_batch(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *specs,
                          int32_t n, double *e, int32_t *status);
+
+/* The same loop over several GPUs from ONE process (DynaML is a single JVM): ctxs[c] is a context on its own
+   device and data[c] the same training set created on it; candidate i runs on context i mod n_ctx, the shards
+   concurrently (one internal host thread per context), and only the energies travel.  Results are bit-identical
+   to dgp_energy_batch on one context.  The caller must not use any of the listed contexts from another thread
+   during the call.  Errors of context c > 0 are reported through ctxs[0].                               */
+int32_t dgp_energy_batch_multi(dgp_ctx *const *ctxs, const dgp_data *const *data, int32_t n_ctx,
+                               const dgp_kernel_spec *specs, int32_t n, double *e, int32_t *status);
 
 /* ---- persist + predictiveDistribution + predictionWithErrorBars
         (AbstractGPRegressionModel.scala:304-413, 434-466;

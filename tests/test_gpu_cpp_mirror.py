@@ -101,3 +101,33 @@ def test_cpp_basis_function_model(result):
     assert out["basis_energy"] == pytest.approx(orc.energy(ok, 0.3, X, y, mean), rel=TOL)
     mu, _ = orc.predictive(ok, 0.3, X, y, Xs, mean, mean_s)
     assert np.abs(np.array(out["basis_mu"]) - mu).max() <= TOL * np.abs(mu).max()
+
+
+def test_candidates_over_several_gpus_from_one_process():
+    """tests/cpp/multi_gpu_batch_test.cpp: one context per host thread per GPU, and dgp_energy_batch_multi, both bit
+    for bit equal to the single-context batch (on a one-GPU box: two contexts on that GPU)."""
+    exe = ROOT / "dynaml_b200" / "lib" / "multi_gpu_batch_test"
+    assert exe.exists(), "build it with `python -m dynaml_b200.build`"
+    r = subprocess.run([str(exe), "1500"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = json.loads(r.stdout)
+    assert out["mismatches"] == 0 and out["bad_arg_checks"] == 0 and out["contexts"] >= 2
+    assert out["non_pd_status"] == 1          # DGP_ERR_NOT_PD for the NaN-bandwidth candidate, the others unaffected
+
+
+def test_model_energy_batch_over_devices():
+    """The Python mirror of the same: GPRegression.useDevices shards energyBatch / GridSearch over GPUs from this one
+    process; identical energies (here every visible GPU, or device 0 alone when there is just one)."""
+    import dynaml_b200 as dg
+    from dynaml_b200 import _capi
+    X, y, _ = orc.synthetic(900, 5, seed=4)
+    se = dg.SEKernel(2.0, 1.0)
+    model = dg.GPRegression(se, dg.DiracKernel(0.3), list(zip(X, y)))
+    gs = dg.GridSearch(model).setGridSize(3).setStepSize(0.2)
+    init = {"bandwidth": 2.5, "amplitude": 1.4, "noiseLevel": 0.6}
+    single = gs.getEnergyLandscape(init)
+    ndev = max(1, _capi.device_count())
+    model.useDevices(list(range(ndev)) if ndev > 1 else [0, 0])   # one GPU: a second context on it
+    multi = gs.getEnergyLandscape(init)
+    assert [e for e, _ in multi] == [e for e, _ in single]
+    model.useDevices([])
