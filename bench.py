@@ -377,7 +377,6 @@ def run_c5(ctx, D: Dist, rank: int, args) -> dict:
             try:
                 model.useDevices(list(range(world)))
                 model.energyBatch(gs.getGrid(init)[: 3 * world])          # warm-up on every device
-                gs.group = "local"                                         # no torch.distributed sharding for this leg
                 t0 = time.perf_counter()
                 land1 = [(e, c) for e, c in zip(model.energyBatch(gs.getGrid(init)), gs.getGrid(init))]
                 dt1 = time.perf_counter() - t0
@@ -528,7 +527,7 @@ def main():
             "phases_ms": phase,
             "peaks_measured": peaks,
             "e2e": {"value": e2e_value, "unit": UNIT, # dgp_data_create copies the centred points, the raw points and the residual vector (padded) in one transfer
-                    "h2d_bytes_per_step": int(8 * (2 * (-(-n // 128) * 128) * (-(-d // 4) * 4) + (-(-n // 128) * 128))),
+                    "h2d_bytes_per_step": int(8 * (2 * (-(-n // 128) * 128 + 128) * (-(-d // 4) * 4) + (-(-n // 128) * 128))),
                     "d2h_bytes_per_step": int(8 * (1 + len(g)))},
             "gpu_launches": int(launches),
             "clocks": clocks,

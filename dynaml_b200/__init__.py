@@ -13,6 +13,8 @@ from .kernels import (AdditiveCovariance, CauchyKernel, CompositeCovariance, Dec
                       LaplacianKernel, LocalScalarKernel, MahalanobisKernel, MultiplicativeCovariance, PeriodicKernel,
                       RationalQuadraticKernel, RBFKernel, ScaledKernel, SEKernel, SVMKernelMatrix, TStudentKernel,
                       KroneckerProductKernel, TensorCombinationKernel)
+from .kernels import SVMKernel
+from .algebra import LowerTriPartitionedMatrix, PartitionedMatrix, PartitionedPSDMatrix, PartitionedVector
 from .models import (AbstractGPRegressionModel, CudaGPRegression, GPBasisFuncRegression, GPRegression,
                      MultGaussianPRV)
 from .stp import AbstractSTPRegressionModel, MultStudentsTPRV, STPRegression
@@ -28,7 +30,8 @@ __all__ = [
     "Context", "DgpError", "NotPositiveDefinite", "default_context",
     "LocalScalarKernel", "SEKernel", "RBFKernel", "MahalanobisKernel", "GenericMaternKernel", "PeriodicKernel",
     "DiracKernel", "AdditiveCovariance", "MultiplicativeCovariance", "CompositeCovariance", "ScaledKernel",
-    "SVMKernelMatrix",
+    "SVMKernelMatrix", "SVMKernel", "PartitionedMatrix", "PartitionedPSDMatrix", "LowerTriPartitionedMatrix",
+    "PartitionedVector",
     "CauchyKernel", "LaplacianKernel", "RationalQuadraticKernel", "TStudentKernel", "PolynomialKernel", "FBMKernel",
     "GPRegression", "CudaGPRegression", "GPBasisFuncRegression", "AbstractGPRegressionModel", "MultGaussianPRV",
     "STPRegression", "AbstractSTPRegressionModel", "MultStudentsTPRV",

@@ -34,7 +34,7 @@ EXPORTS = [
     "dgp_predict", "dgp_dist_unique_id", "dgp_dist_init", "dgp_dist_finalize", "dgp_dist_plan", "dgp_dist_energy",
     "dgp_measure_peaks", "dgp_launch_count", "dgp_outer_block", "dgp_time_phase", "dgp_test_gemm", "dgp_test_potrf",
     "dgp_spec_grad_len", "dgp_data_set_basis", "dgp_model_set_test_basis", "dgp_model_solve", "dgp_model_cross_apply",
-    "dgp_model_set_cross_spec", "dgp_ctx_trim", "dgp_dist_info", "dgp_ctx_info", "dgp_energy_batch_multi",
+    "dgp_model_set_cross_spec", "dgp_ctx_trim", "dgp_dist_info", "dgp_ctx_info", "dgp_energy_batch_multi", "dgp_data_kernel_block", "dgp_kernel_grad_matrix",
 ]
 
 
@@ -81,6 +81,8 @@ def load_library() -> C.CDLL:
         "dgp_data_create": (i32, [vp, _dp, i64, i32, i32, _dp, _dp, C.POINTER(vp)]),
         "dgp_data_destroy": (i32, [vp, vp]),
         "dgp_kernel_matrix": (i32, [vp, sp, _dp, i64, _dp, i64, i32, i32, _dp, i64, i32]),
+        "dgp_data_kernel_block": (i32, [vp, vp, sp, i64, i64, i64, i64, i32, _dp, i64]),
+        "dgp_kernel_grad_matrix": (i32, [vp, sp, _dp, i64, _dp, i64, i32, i32, i32, _dp]),
         "dgp_energy": (i32, [vp, vp, sp, _dp]),
         "dgp_energy_terms": (i32, [vp, vp, sp, _dp, _dp]),
         "dgp_model_terms": (i32, [vp, vp, _dp, _dp]),
@@ -250,6 +252,30 @@ class Context:
                                             n1, 0)
         self.check(st)
         return out
+
+    def data_kernel_block(self, data, spec, row0: int, nrows: int, col0: int, ncols: int, add_noise=True):
+        """K[row0:row0+nrows, col0:col0+ncols] of the training kernel matrix of a resident data set."""
+        s, keep = spec
+        out = np.empty((nrows, ncols), order="F")
+        self.check(self.lib.dgp_data_kernel_block(self.h, data, C.byref(s), row0, nrows, col0, ncols, int(bool(add_noise)),
+                                                  _ptr(out), nrows))
+        return out
+
+    def kernel_grad_matrix(self, spec, X1, X2=None, add_noise=False):
+        """(K, [dK/dtheta ...]) in the order of energy_grad: the spec's hyper-parameters, then the noise level."""
+        s, keep = spec
+        X1 = _f64(X1)
+        n1, d = X1.shape
+        ng = int(self.lib.dgp_spec_grad_len(C.byref(s)))
+        if ng < 0:
+            raise DgpError(-ng, "malformed kernel spec")
+        X2c = None if X2 is None else _f64(X2)
+        n2 = n1 if X2c is None else X2c.shape[0]
+        out = np.empty((1 + ng, n2, n1))          # plane-major, each plane column-major n1 x n2
+        self.check(self.lib.dgp_kernel_grad_matrix(self.h, C.byref(s), _ptr(X1), n1, _ptr(X2c), n2 if X2c is not None else 0,
+                                                   d, DGP_ROW_MAJOR, int(bool(add_noise)), _ptr(out)))
+        planes = [np.asfortranarray(out[q].T) for q in range(1 + ng)]
+        return planes[0], planes[1:]
 
     # -- energies ---------------------------------------------------------------------------
     def energy(self, data, spec) -> float:

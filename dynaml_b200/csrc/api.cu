@@ -789,7 +789,8 @@ int32_t dgp_data_create(dgp_ctx *ctx, const double *X, int64_t N, int32_t d, int
   D->dp = (int)round_up(d, 4);
   // one device block [ centred X | raw X | r ] from the stream-ordered pool, filled by one copy out of a
   // pinned staging buffer: a create / destroy pair costs host packing only (cudaMalloc / cudaFree took ~2 ms each)
-  const size_t nx = (size_t)D->Np * D->dp, nr = (size_t)D->Np, total = 2 * nx + nr;
+  // (+ TILE zero rows behind each point set: dgp_data_kernel_block assembles blocks that start at any row)
+  const size_t nx = (size_t)(D->Np + TILE) * D->dp, nr = (size_t)D->Np, total = 2 * nx + nr;
   if (ctx->h_stage_bytes < total * sizeof(double)) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     ctx->h_stage = nullptr;
@@ -806,9 +807,10 @@ int32_t dgp_data_create(dgp_ctx *ctx, const double *X, int64_t N, int32_t d, int
   column_means(X, N, d, x_layout, D->center);
   D->max_sq_norm = pack_points(X, N, d, x_layout, D->Np, D->dp, hx, D->center.data());
   D->has_dup = has_duplicate_rows(hx, N, D->dp);
-  memcpy(hs, hx.data(), nx * sizeof(double));
+  memset(hs, 0, 2 * nx * sizeof(double));
+  memcpy(hs, hx.data(), hx.size() * sizeof(double));
   pack_points(X, N, d, x_layout, D->Np, D->dp, hx, nullptr);
-  memcpy(hs + nx, hx.data(), nx * sizeof(double));
+  memcpy(hs + nx, hx.data(), hx.size() * sizeof(double));
   for (int64_t i = 0; i < D->Np; ++i) hs[2 * nx + i] = i < N ? y[i] - (mean ? mean[i] : 0.0) : 0.0;
   if (cudaMallocFromPoolAsync((void **)&D->block, total * sizeof(double), ctx->data_pool, ctx->stream) != cudaSuccess) {
     cudaGetLastError();
@@ -1402,6 +1404,107 @@ int32_t dgp_kernel_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec, const doubl
     float ms;
     cudaEventElapsedTime(&ms, ctx->tev[0], ctx->tev[1]);
     ctx->timings[0] = ms;
+  }
+  return DGP_OK;
+}
+
+// ---- blocks of the training matrix from resident data (SVMKernel.buildPartitionedKernelMatrix, :181-219) ---------
+int32_t dgp_data_kernel_block(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *spec, int64_t row0, int64_t nrows,
+                              int64_t col0, int64_t ncols, int32_t add_noise, double *out, int64_t ld) {
+  if (!ctx || !D || !spec || !out) return DGP_ERR_ARG;
+  if (row0 < 0 || col0 < 0 || nrows <= 0 || ncols <= 0 || row0 + nrows > D->N || col0 + ncols > D->N || ld < nrows)
+    return ctx->fail(DGP_ERR_SHAPE, "kernel_block: rows [%lld, +%lld) x cols [%lld, +%lld) of an N = %lld set, ld = %lld",
+                     (long long)row0, (long long)nrows, (long long)col0, (long long)ncols, (long long)D->N, (long long)ld);
+  cudaSetDevice(ctx->device);
+  Spec sp;
+  DGP_TRY(parse_spec(ctx, spec, D->d, &sp));
+  cudaStream_t S = ctx->stream;
+  const int dp = D->dp;
+  const int64_t rp = round_up(nrows, TILE), cpad = round_up(ncols, TILE);
+  const bool diag = row0 == col0 && nrows == ncols;           // a diagonal block: symmetric, evaluated i >= j and mirrored
+  const bool overlap = row0 < col0 + ncols && col0 < row0 + nrows;
+  // the Dirac term fires wherever |x - y| == 0: on the diagonal, and anywhere when the set has duplicated points
+  const bool noise = add_noise && (overlap || D->has_dup);
+  const double *Xbase = spec_uses_raw_points(sp) ? D->Xraw : D->X;
+  const double *Xk = nullptr;
+  DGP_TRY(scaled_points(ctx, S, sp, Xbase, D->Np + TILE, dp, D->d, "kb_xs", &Xk));
+  CovParams cp = make_cov_params(sp, noise, D->d);
+  DGP_BUF(Kd, double, ctx, "kb_out", (size_t)rp * cpad * sizeof(double));
+  AssembleArgs a;
+  a.X1 = Xk + row0 * dp;  a.X2 = Xk + col0 * dp;  a.dp = dp;
+  a.rows = nrows;  a.cols = ncols;  a.rows_p = rp;  a.cols_p = cpad;
+  a.out = Kd;  a.ld = rp;
+  a.symmetric = diag ? 1 : 0;
+  a.lower_only = diag ? 1 : 0;
+  // the Gram formulation needs 16-byte aligned operands (dp is a multiple of 4 doubles: any row offset is) and, with a
+  // noise term, the guarantee that only i == j coincide: a diagonal block of a duplicate-free set
+  a.use_gram = (!noise || (diag && !D->has_dup)) ? pick_gram(ctx, sp, cp, dp, D->d, D->max_sq_norm) : 0;
+  a.nodup = diag ? points_stay_distinct(D->has_dup, sp, D->d) : 0;
+  DGP_TRY(assemble(ctx, S, cp, a));
+  if (diag) DGP_TRY(mirror_lower(ctx, S, Kd, rp, rp));
+  DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(out, ld * sizeof(double), Kd, rp * sizeof(double), nrows * sizeof(double), ncols,
+                                     cudaMemcpyDeviceToHost, S));
+  DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
+  return DGP_OK;
+}
+
+// ---- kernel matrix with its derivatives (SVMKernel.buildKernelGradMatrix / buildCrossKernelGradMatrix, :107-179) ---
+int32_t dgp_kernel_grad_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec, const double *X1, int64_t N1, const double *X2,
+                               int64_t N2, int32_t d, int32_t x_layout, int32_t add_noise, double *out) {
+  if (!ctx || !spec || !X1 || !out || N1 <= 0 || d <= 0) return DGP_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const bool sym = X2 == nullptr;
+  if (sym) N2 = N1;
+  if (N2 <= 0) return ctx->fail(DGP_ERR_SHAPE, "kernel_grad_matrix: bad N2");
+  Spec sp;
+  DGP_TRY(parse_spec(ctx, spec, d, &sp));
+  const int ng = dgp_spec_grad_len(spec);
+  if (ng < 0) return ctx->fail(DGP_ERR_ARG, "kernel_grad_matrix: malformed spec");
+  const size_t plane = (size_t)N1 * N2;
+  // plane 0: the kernel matrix itself (key "kernel-matrix"), through the ordinary builder
+  DGP_TRY(dgp_kernel_matrix(ctx, spec, X1, N1, sym ? nullptr : X2, N2, d, x_layout, out, N1, sym ? add_noise : 0));
+  cudaStream_t S = ctx->stream;
+  const int dp = (int)round_up(d, 4);
+  const int64_t n1p = round_up(N1, TILE), n2p = round_up(N2, TILE);
+  std::vector<double> h1, h2, ctr;
+  column_means(X1, N1, d, x_layout, ctr);
+  if (spec_uses_raw_points(sp)) ctr.assign(ctr.size(), 0.0);
+  pack_points(X1, N1, d, x_layout, n1p, dp, h1, ctr.data());
+  DGP_BUF(A1, double, ctx, "km_x1", h1.size() * sizeof(double));
+  DGP_CUDA_OK(ctx, cudaMemcpyAsync(A1, h1.data(), h1.size() * sizeof(double), cudaMemcpyHostToDevice, S));
+  double *A2 = A1;
+  if (!sym) {
+    pack_points(X2, N2, d, x_layout, n2p, dp, h2, ctr.data());
+    A2 = (double *)ctx->buf("km_x2", h2.size() * sizeof(double));
+    if (!A2) return DGP_ERR_OOM;
+    DGP_CUDA_OK(ctx, cudaMemcpyAsync(A2, h2.data(), h2.size() * sizeof(double), cudaMemcpyHostToDevice, S));
+  }
+  const double *B1 = nullptr, *B2 = nullptr;
+  DGP_TRY(scaled_points(ctx, S, sp, A1, n1p, dp, d, "km_x1s", &B1));
+  if (sym) B2 = B1;
+  else DGP_TRY(scaled_points(ctx, S, sp, A2, n2p, dp, d, "km_x2s", &B2));
+  // the derivative of the noise term exists only where the builder adds it (the symmetric training matrix)
+  Spec spn = sp;
+  if (!(sym && add_noise)) spn.noise = 0.0;
+  CovParams cp = make_cov_params(spn, sym && add_noise, d);
+  const int nsmax = cp.kind == DGP_KERNEL_COMPOSITE ? grad_partials_per_tile(cp, dp)
+                                                    : std::max(grad_partials_per_tile(cp, dp), MAX_ARD_DIM + 2);
+  // columns in chunks of at most ~64 MB of moments
+  int64_t chunk = std::max<int64_t>(1, (int64_t)(64u << 20) / (int64_t)(sizeof(double) * nsmax * N1));
+  if (chunk > N2) chunk = N2;
+  DGP_BUF(mom, double, ctx, "kg_moments", (size_t)N1 * chunk * nsmax * sizeof(double));
+  std::vector<double> hm((size_t)N1 * chunk * nsmax), g((size_t)ng + 1);
+  for (int64_t c0 = 0; c0 < N2; c0 += chunk) {
+    const int64_t nc = std::min(chunk, N2 - c0);
+    int ns = 0;
+    DGP_TRY(grad_pair_moments(ctx, S, cp, A1, B1, A2, B2, N1, c0, nc, dp, mom, &ns));
+    DGP_CUDA_OK(ctx, cudaMemcpyAsync(hm.data(), mom, (size_t)N1 * nc * ns * sizeof(double), cudaMemcpyDeviceToHost, S));
+    DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
+    for (int64_t j = 0; j < nc; ++j)
+      for (int64_t i = 0; i < N1; ++i) {
+        grad_finish(spn, d, hm.data() + ((size_t)i + (size_t)j * N1) * ns, ns, g.data());
+        for (int q = 0; q < ng; ++q) out[(size_t)(1 + q) * plane + (size_t)i + (size_t)(c0 + j) * N1] = g[q];
+      }
   }
   return DGP_OK;
 }

@@ -13,6 +13,8 @@
 
 namespace dgp {
 
+int grad_partials_per_tile(const CovParams &cp, int dp);
+
 namespace {
 
 constexpr int GT = 128;
@@ -574,7 +576,92 @@ int mode_of(const CovParams &cp) {
   }
 }
 
+// ---- per-pair moments: the gradient MATRICES (SVMKernel.buildKernelGradMatrix / buildCrossKernelGradMatrix) ----------
+// dK_ij / dtheta is what the trace pass contributes for the weight matrix M = e_i e_j', so one thread per pair runs the
+// very same accumulate<> / composite_pair<> with m = 1 into its own moment vector; grad_finish (linear in the moments)
+// then maps each pair's moments to the reference's derivatives on the host.  Not a hot path: runtime feature loop.
+constexpr int PAIR_NS_MAX = MAX_COMPOSITE_MOMENTS;
+
+__global__ void __launch_bounds__(128) pair_moments_kernel(CovParams cp, int mode, const double *X1, const double *X1s,
+                                                           const double *X2, const double *X2s, int64_t n1, int64_t c0,
+                                                           int64_t ncols, int dp, int ns, double *out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n1 * ncols) return;
+  const int64_t i = idx % n1, jl = idx / n1, j = c0 + jl;
+  double s[MAX_ARD_DIM + 2 > 8 ? MAX_ARD_DIM + 2 : 8];
+  for (int q = 0; q < ns; ++q) s[q] = 0.0;
+  const double *x = X1 + i * dp, *y = X2 + j * dp;
+  double d = 0.0, p = 0.0, sq[MAX_ARD_DIM];
+  for (int c = 0; c < MAX_ARD_DIM; ++c) sq[c] = 0.0;
+  const bool l1 = mode == M_PERIODIC || mode == M_LAPLACIAN, ard = mode == M_ARD_REF || mode == M_ARD_EXACT;
+  for (int c = 0; c < dp; ++c) {
+    const double e = x[c] - y[c];
+    if (l1) d += fabs(e);
+    else if (ard) {
+      const double f = X1s[i * dp + c] - X2s[j * dp + c];
+      d = fma(f, f, d);
+      p = fma(e, e, p);
+      if (c < MAX_ARD_DIM) sq[c] = e * e;
+    } else d = fma(e, e, d);
+  }
+  switch (mode) {
+    case M_SE: accumulate<M_SE, 0>(cp, 1.0, d, p, nullptr, s); break;
+    case M_ARD_REF: accumulate<M_ARD_REF, 0>(cp, 1.0, d, p, nullptr, s); break;
+    case M_ARD_EXACT: accumulate<M_ARD_EXACT, MAX_ARD_DIM>(cp, 1.0, d, p, sq, s); break;
+    case M_MATERN: accumulate<M_MATERN, 0>(cp, 1.0, d, p, nullptr, s); break;
+    case M_PERIODIC: accumulate<M_PERIODIC, 0>(cp, 1.0, d, p, nullptr, s); break;
+    case M_CAUCHY: accumulate<M_CAUCHY, 0>(cp, 1.0, d, p, nullptr, s); break;
+    case M_LAPLACIAN: accumulate<M_LAPLACIAN, 0>(cp, 1.0, d, p, nullptr, s); break;
+    case M_RATQUAD: accumulate<M_RATQUAD, 0>(cp, 1.0, d, p, nullptr, s); break;
+    case M_TSTUDENT: accumulate<M_TSTUDENT, 0>(cp, 1.0, d, p, nullptr, s); break;
+    default: accumulate<M_DIRAC, 0>(cp, 1.0, d, p, nullptr, s); break;
+  }
+  double *o = out + (i + jl * n1) * ns;
+  for (int q = 0; q < ns; ++q) o[q] = s[q];
+}
+
+__global__ void __launch_bounds__(64) pair_moments_composite_kernel(CompositeDev c, CompositeModes md, const double *X1,
+                                                                    const double *X2, int64_t n1, int64_t c0,
+                                                                    int64_t ncols, int dp, int ns, double *out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n1 * ncols) return;
+  const int64_t i = idx % n1, jl = idx / n1, j = c0 + jl;
+  double s[PAIR_NS_MAX];
+  for (int q = 0; q < ns; ++q) s[q] = 0.0;
+  composite_pair<0, MAXF>(c, md, X1 + i * dp, X2 + j * dp, dp, 1.0, s);
+  double *o = out + (i + jl * n1) * ns;
+  for (int q = 0; q < ns; ++q) o[q] = s[q];
+}
+
 }  // namespace
+
+int32_t grad_pair_moments(Ctx *ctx, cudaStream_t st, const CovParams &cp, const double *X1, const double *X1s,
+                          const double *X2, const double *X2s, int64_t n1, int64_t c0, int64_t ncols, int dp, double *out,
+                          int *ns_out) {
+  const int64_t pairs = n1 * ncols;
+  if (pairs <= 0) return DGP_OK;
+  if (cp.kind == DGP_KERNEL_COMPOSITE) {
+    if (!cp.comp) return ctx->fail(DGP_ERR_ARG, "grad matrix: composite kernel without an expression");
+    const CompositeDev &c = *cp.comp;
+    const int NS = c.moment_off[c.F] + 1;
+    if (NS > PAIR_NS_MAX) return ctx->fail(DGP_ERR_SHAPE, "composite gradient needs %d moments, at most %d", NS, PAIR_NS_MAX);
+    CompositeModes md;
+    for (int f = 0; f < MAXF; ++f) md.mode[f] = f < c.F ? mode_of(c.cp[f]) : M_DIRAC;
+    pair_moments_composite_kernel<<<(unsigned)((pairs + 63) / 64), 64, 0, st>>>(c, md, X1, X2, n1, c0, ncols, dp, NS, out);
+    *ns_out = NS;
+  } else {
+    const int mode = mode_of(cp);
+    if (mode == M_ARD_EXACT && dp > MAX_ARD_DIM)
+      return ctx->fail(DGP_ERR_SHAPE, "exact ARD gradients support up to %d features, got dp=%d", MAX_ARD_DIM, dp);
+    const int NS = mode == M_ARD_EXACT ? MAX_ARD_DIM + 2 : grad_partials_per_tile(cp, dp);
+    pair_moments_kernel<<<(unsigned)((pairs + 127) / 128), 128, 0, st>>>(cp, mode, X1, X1s, X2, X2s, n1, c0, ncols, dp, NS,
+                                                                         out);
+    *ns_out = NS;
+  }
+  ctx->launches++;
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  return DGP_OK;
+}
 
 int grad_partials_per_tile(const CovParams &cp, int dp) {
   if (cp.kind == DGP_KERNEL_COMPOSITE) return cp.comp ? cp.comp->moment_off[cp.comp->F] + 1 : 1;

@@ -119,6 +119,14 @@ class LocalScalarKernel:
     def buildCrossKernelMatrix(self, dataset1: Sequence, dataset2: Sequence) -> np.ndarray:
         return _capi.default_context().kernel_matrix(self._spec(), _as_points(dataset1), _as_points(dataset2))
 
+    def buildBlockedKernelMatrix(self, mappedData: Sequence, length: int):
+        """LocalScalarKernel.scala:160-161: the PartitionedPSDMatrix of blocks rowBlocking x colBlocking."""
+        return SVMKernel.buildPartitionedKernelMatrix(mappedData, length, self.rowBlocking, self.colBlocking, self)
+
+    def buildBlockedCrossKernelMatrix(self, dataset1: Sequence, dataset2: Sequence):
+        """LocalScalarKernel.scala:163-164."""
+        return SVMKernel.crossPartitonedKernelMatrix(dataset1, dataset2, self.rowBlocking, self.colBlocking, self)
+
     # ---- kernel algebra (LocalScalarKernel.scala:53-91) -------------------------------------
     # Every kernel reduces to the normal form  sum_t coef_t * prod_f leaf_f ^ e_tf  that the device
     # evaluates (DGP_KERNEL_COMPOSITE): `_leaves()` lists the base kernels in hyper-parameter order,
@@ -150,6 +158,117 @@ class LocalScalarKernel:
         return ScaledKernel(self, float(other))
 
     __rmul__ = __mul__
+
+
+class SVMKernel:
+    """The matrix builders of the SVMKernel companion object (CORE/kernels/SVMKernel.scala:71-307).  The reference
+    passes per-pair closures `eval` / `evalGrad`; here the kernel object itself is passed and the device evaluates
+    it (`noise`, optional, is the level of a DiracKernel noise model added on coincident points, i.e. the
+    `cov + noise` eval the GP model hands over; AbstractGPRegressionModel.scala:269-277)."""
+
+    @staticmethod
+    def buildSVMKernelMatrix(mappedData: Sequence, length: int, kernel: "LocalScalarKernel", noise: float | None = None):
+        X = _as_points(mappedData)
+        assert X.shape[0] == length
+        K = _capi.default_context().kernel_matrix(kernel._spec(noise=0.0 if noise is None else noise), X,
+                                                  add_noise=noise is not None)
+        return SVMKernelMatrix(K, length)
+
+    @staticmethod
+    def crossKernelMatrix(data1: Sequence, data2: Sequence, kernel: "LocalScalarKernel") -> np.ndarray:
+        return _capi.default_context().kernel_matrix(kernel._spec(), _as_points(data1), _as_points(data2))
+
+    @staticmethod
+    def buildPartitionedKernelMatrix(data: Sequence, length: int, numElementsPerRowBlock: int, numElementsPerColBlock: int,
+                                     kernel: "LocalScalarKernel", noise: float | None = None, ctx=None):
+        """:181-219.  Lower block list (block row >= block column) of the training matrix, every block cut straight
+        from the points resident on the device (dgp_data_kernel_block: no re-upload per block).  Diagonal blocks
+        require equal row and column block sizes, as every caller of the reference uses them."""
+        from .algebra import PartitionedPSDMatrix
+        ctx = ctx or _capi.default_context()
+        X = _as_points(data)
+        assert X.shape[0] == length
+        nr, nc = int(numElementsPerRowBlock), int(numElementsPerColBlock)
+        if nr != nc:
+            raise ValueError("buildPartitionedKernelMatrix: equal row and column block sizes are required "
+                             "(a PartitionedPSDMatrix has square diagonal blocks)")
+        spec = kernel._spec(noise=0.0 if noise is None else noise)
+        h = ctx.data_create(X, np.zeros(length))
+        try:
+            nb = -(-length // nr)
+            blocks = []
+            for i in range(nb):
+                for j in range(i + 1):
+                    r0, c0 = i * nr, j * nc
+                    blocks.append(((i, j), ctx.data_kernel_block(h, spec, r0, min(nr, length - r0), c0, min(nc, length - c0),
+                                                                 add_noise=noise is not None)))
+        finally:
+            ctx.data_destroy(h)
+        return PartitionedPSDMatrix(blocks, length, length, nb, nb)
+
+    @staticmethod
+    def crossPartitonedKernelMatrix(data1: Sequence, data2: Sequence, numElementsPerRowBlock: int,
+                                    numElementsPerColBlock: int, kernel: "LocalScalarKernel", ctx=None):
+        """:221-248 (the reference's spelling).  Every block is a crossKernelMatrix of the two groups."""
+        from .algebra import PartitionedMatrix
+        ctx = ctx or _capi.default_context()
+        X1, X2 = _as_points(data1), _as_points(data2)
+        nr, nc = int(numElementsPerRowBlock), int(numElementsPerColBlock)
+        rb, cb = -(-X1.shape[0] // nr), -(-X2.shape[0] // nc)
+        spec = kernel._spec()
+        blocks = [((i, j), ctx.kernel_matrix(spec, X1[i * nr:(i + 1) * nr], X2[j * nc:(j + 1) * nc]))
+                  for i in range(rb) for j in range(cb)]
+        return PartitionedMatrix(blocks, X1.shape[0], X2.shape[0], rb, cb)
+
+    @staticmethod
+    def _grad_names(kernel: "LocalScalarKernel", noise: float | None) -> List[str]:
+        names = []
+        for leaf in kernel._leaves():
+            names += list(leaf.hyper_parameters)
+        return names + ["noiseLevel"]
+
+    @staticmethod
+    def buildKernelGradMatrix(data1: Sequence, hyper_parameters: Sequence[str], kernel: "LocalScalarKernel",
+                              noise: float | None = None, ctx=None) -> Dict[str, np.ndarray]:
+        """:107-145: {"kernel-matrix": K, h: dK/dh for h in hyper_parameters} (h also "noiseLevel" with a noise model)."""
+        ctx = ctx or _capi.default_context()
+        X = _as_points(data1)
+        K, G = ctx.kernel_grad_matrix(kernel._spec(noise=0.0 if noise is None else noise), X, add_noise=noise is not None)
+        return SVMKernel._as_map(kernel, noise, K, G, hyper_parameters)
+
+    @staticmethod
+    def buildCrossKernelGradMatrix(data1: Sequence, data2: Sequence, hyper_parameters: Sequence[str],
+                                   kernel: "LocalScalarKernel", ctx=None) -> Dict[str, np.ndarray]:
+        """:147-179."""
+        ctx = ctx or _capi.default_context()
+        K, G = ctx.kernel_grad_matrix(kernel._spec(), _as_points(data1), _as_points(data2))
+        return SVMKernel._as_map(kernel, None, K, G, hyper_parameters)
+
+    @staticmethod
+    def _as_map(kernel, noise, K, G, hyper_parameters) -> Dict[str, np.ndarray]:
+        out = {"kernel-matrix": K}
+        # device order: the hyper-parameters of the kernel's leaves, then the noise level; kernels that re-parametrise a
+        # device kind translate their own derivatives (as gradEnergy does)
+        off = 0
+        by_name: Dict[str, np.ndarray] = {}
+        for leaf, cfg in zip(kernel._leaves(), kernel._leaf_configs(kernel.state)):
+            nh = len(leaf.hyper_parameters)
+            planes = G[off:off + nh]
+            if type(leaf)._fix_device_grad is not LocalScalarKernel._fix_device_grad:
+                stack = np.stack(planes)
+                fixed = np.apply_along_axis(lambda v: np.asarray(leaf._fix_device_grad(cfg, list(v))), 0, stack)
+                planes = [fixed[q] for q in range(nh)]
+            for name, pl in zip(leaf.hyper_parameters, planes):
+                by_name[name] = pl
+            off += nh
+        if noise is not None:
+            by_name["noiseLevel"] = G[off]
+        for h in hyper_parameters:
+            key = h.split("/")[-1]
+            if key not in by_name:
+                raise KeyError(f"no derivative for hyper-parameter {h!r}")
+            out[h] = by_name[key]
+        return out
 
 
 def composite_spec(parts: Sequence[tuple], noise: float = 0.0, extra_terms: Sequence[tuple] = ()):

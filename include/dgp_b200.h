@@ -171,6 +171,27 @@ int32_t dgp_kernel_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec,
                           const double *X1, int64_t N1, const double *X2, int64_t N2,
                           int32_t d, int32_t x_layout, double *out, int64_t ld, int32_t add_noise);
 
+/* ---- SVMKernel.buildPartitionedKernelMatrix (CORE/kernels/SVMKernel.scala:181-219; LocalScalarKernel.buildBlockedKernelMatrix,
+        LocalScalarKernel.scala:160-161): the training matrix block by block, straight from the resident points --------
+   out (nrows x ncols, column-major, leading dimension ld) = K[row0 : row0 + nrows, col0 : col0 + ncols] of the kernel
+   matrix of the points held by `data`; add_noise != 0 adds the Dirac term of spec->noise wherever two points coincide
+   (the diagonal; and any duplicates).  A block with equal row and column ranges is evaluated for i >= j and mirrored,
+   as buildSVMKernelMatrix does (bitwise symmetric); any other block as crossKernelMatrix does.  No re-upload per block.
+   The reference's PartitionedPSDMatrix is the list of such blocks for block row >= block column with
+   num_elements_per_row_block = num_elements_per_col_block = blockSize.                                            */
+int32_t dgp_data_kernel_block(dgp_ctx *ctx, const dgp_data *data, const dgp_kernel_spec *spec, int64_t row0,
+                              int64_t nrows, int64_t col0, int64_t ncols, int32_t add_noise, double *out, int64_t ld);
+
+/* ---- SVMKernel.buildKernelGradMatrix / buildCrossKernelGradMatrix (CORE/kernels/SVMKernel.scala:107-179) -----------
+   The kernel matrix and its derivative with respect to every hyper-parameter, per entry.  `out` receives
+   1 + dgp_spec_grad_len(spec) planes of N1 x N2 (column-major, contiguous): plane 0 the kernel matrix (the
+   reference's key "kernel-matrix"), planes 1.. the derivatives in the order of dgp_energy_grad (the spec's
+   hyper-parameters, then the noise level; NaN where the reference defines none).  X2 == NULL: the symmetric matrix
+   of X1, with the Dirac term and its derivative when add_noise != 0.  Meant for inspection and parity at moderate
+   N (the derivatives pass through the host); gradEnergy itself never materialises them.                          */
+int32_t dgp_kernel_grad_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec, const double *X1, int64_t N1,
+                               const double *X2, int64_t N2, int32_t d, int32_t x_layout, int32_t add_noise, double *out);
+
 /* ---- AbstractGPRegressionModel.energy (AbstractGPRegressionModel.scala:148-189, 516-535) ----
    E = 0.5 * ( r' K^-1 r + sum_i log L_ii + n log 2 pi ),  r = y - m(X)  (the reference's value,
    whose log-det term is half the textbook one).  Non-PD K: *e = +Inf, returns DGP_ERR_NOT_PD.   */

@@ -43,6 +43,37 @@ struct DenseMatrix {  // Breeze DenseMatrix[Double]: column-major, offset 0
   double operator()(int64_t i, int64_t j) const { return data[(size_t)(i + j * rows)]; }
 };
 
+// PartitionedPSDMatrix (CORE/algebra/PartitionedMatrix.scala:248-259): the blocks on / below the block diagonal;
+// the blocks above it are their transposes.  PartitionedMatrix: every block given.
+struct PartitionedMatrix {
+  int64_t rows = 0, cols = 0, rowBlocks = 0, colBlocks = 0;
+  bool symmetric = false;  // true: only blocks (i, j), i >= j, are stored
+  std::map<std::pair<int64_t, int64_t>, DenseMatrix> blocks;
+  DenseMatrix toDenseMatrix() const {
+    DenseMatrix out;
+    out.rows = rows;
+    out.cols = cols;
+    out.data.assign((size_t)rows * cols, 0.0);
+    std::vector<int64_t> r0(rowBlocks + 1, 0), c0(colBlocks + 1, 0);
+    for (const auto &kv : blocks) {
+      if (kv.first.second == 0) r0[kv.first.first + 1] = kv.second.rows;
+      if (kv.first.first == kv.first.second || !symmetric) c0[kv.first.second + 1] = kv.second.cols;
+    }
+    for (int64_t i = 0; i < rowBlocks; ++i) r0[i + 1] += r0[i];
+    for (int64_t j = 0; j < colBlocks; ++j) c0[j + 1] += c0[j];
+    for (const auto &kv : blocks) {
+      const DenseMatrix &b = kv.second;
+      for (int64_t c = 0; c < b.cols; ++c)
+        for (int64_t r = 0; r < b.rows; ++r) {
+          out.data[(size_t)(r0[kv.first.first] + r + (c0[kv.first.second] + c) * rows)] = b(r, c);
+          if (symmetric && kv.first.first != kv.first.second)
+            out.data[(size_t)(c0[kv.first.second] + c + (r0[kv.first.first] + r) * rows)] = b(r, c);
+        }
+    }
+    return out;
+  }
+};
+
 class DgpError : public std::runtime_error {
  public:
   DgpError(int32_t st, const std::string &m) : std::runtime_error(m), status(st) {}
@@ -121,6 +152,66 @@ class LocalScalarKernel {
   }
 
   double evaluate(const Vec &x, const Vec &y) const { return buildCrossKernelMatrix({x}, {y})(0, 0); }
+
+  // LocalScalarKernel.scala:39-44, 160-161 -> SVMKernel.buildPartitionedKernelMatrix (SVMKernel.scala:181-219): blocks of
+  // rowBlocking x colBlocking, block row >= block column, cut from the points resident on the device.
+  int64_t rowBlocking = 1000, colBlocking = 1000;
+  void setBlockSizes(int64_t r, int64_t c) { rowBlocking = r; colBlocking = c; }
+  PartitionedMatrix buildBlockedKernelMatrix(const std::vector<Vec> &data, double noise = 0.0, bool add_noise = false) const {
+    if (rowBlocking != colBlocking) throw std::invalid_argument("buildBlockedKernelMatrix: equal block sizes are required");
+    const auto ctx = Context::global();
+    Vec hyp = device_hyp();
+    dgp_kernel_spec sp{device_kind(), (int32_t)hyp.size(), grad_mode, 0, hyp.data(), noise};
+    std::vector<double> X = pack(data), y(data.size(), 0.0);
+    const int64_t n = (int64_t)data.size(), nb = (n + rowBlocking - 1) / rowBlocking;
+    dgp_data *h = nullptr;
+    ctx->check(dgp_data_create(ctx->get(), X.data(), n, (int32_t)data[0].size(), DGP_ROW_MAJOR, y.data(), nullptr, &h));
+    PartitionedMatrix P;
+    P.rows = P.cols = n;
+    P.rowBlocks = P.colBlocks = nb;
+    P.symmetric = true;
+    for (int64_t i = 0; i < nb; ++i)
+      for (int64_t j = 0; j <= i; ++j) {
+        DenseMatrix b;
+        b.rows = std::min(rowBlocking, n - i * rowBlocking);
+        b.cols = std::min(colBlocking, n - j * colBlocking);
+        b.data.resize((size_t)b.rows * b.cols);
+        const int32_t st = dgp_data_kernel_block(ctx->get(), h, &sp, i * rowBlocking, b.rows, j * colBlocking, b.cols,
+                                                 add_noise ? 1 : 0, b.data.data(), b.rows);
+        if (st != DGP_OK) {
+          dgp_data_destroy(ctx->get(), h);
+          ctx->check(st);
+        }
+        P.blocks[{i, j}] = std::move(b);
+      }
+    dgp_data_destroy(ctx->get(), h);
+    return P;
+  }
+  // SVMKernel.buildKernelGradMatrix (SVMKernel.scala:107-145): "kernel-matrix" and one matrix per hyper-parameter
+  // (device order: this kernel's hyper_parameters, then "noiseLevel" when a noise level is given).
+  std::map<std::string, DenseMatrix> buildKernelGradMatrix(const std::vector<Vec> &data, double noise = 0.0,
+                                                           bool add_noise = false) const {
+    const auto ctx = Context::global();
+    Vec hyp = device_hyp();
+    dgp_kernel_spec sp{device_kind(), (int32_t)hyp.size(), grad_mode, 0, hyp.data(), noise};
+    const int ng = dgp_spec_grad_len(&sp);
+    const int64_t n = (int64_t)data.size();
+    std::vector<double> X = pack(data), out((size_t)(1 + ng) * n * n);
+    ctx->check(dgp_kernel_grad_matrix(ctx->get(), &sp, X.data(), n, nullptr, 0, (int32_t)data[0].size(), DGP_ROW_MAJOR,
+                                      add_noise ? 1 : 0, out.data()));
+    std::vector<std::string> names = {"kernel-matrix"};
+    for (const auto &h : grad_names()) names.push_back(h);
+    names.push_back("noiseLevel");
+    std::map<std::string, DenseMatrix> res;
+    for (int q = 0; q <= ng && q < (int)names.size(); ++q) {
+      DenseMatrix m;
+      m.rows = m.cols = n;
+      m.data.assign(out.begin() + (size_t)q * n * n, out.begin() + (size_t)(q + 1) * n * n);
+      res[names[q]] = std::move(m);
+    }
+    return res;
+  }
+  virtual std::vector<std::string> grad_names() const { return hyper_parameters; }
 
   DenseMatrix buildKernelMatrix(const std::vector<Vec> &data, double noise = 0.0, bool add_noise = false) const {
     const auto ctx = Context::global();

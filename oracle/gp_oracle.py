@@ -379,6 +379,30 @@ def cross_kernel_matrix(cov: Kernel, X: np.ndarray, Y: np.ndarray) -> np.ndarray
 # blocked algebra restated block by block (used to validate that blocked == dense)
 # ------------------------------------------------------------------------------------------------
 
+def build_partitioned_kernel_matrix(cov, X: np.ndarray, rows_per_block: int, cols_per_block: int, noise=None):
+    """SVMKernel.buildPartitionedKernelMatrix (SVMKernel.scala:181-219): the points are grouped into consecutive blocks
+    of numElementsPerRowBlock; for every pair of groups with block row >= block column the block is
+    buildSVMKernelMatrix (diagonal) or crossKernelMatrix (below it).  Returns (blocks {(i, j): matrix}, rows, cols,
+    rowBlocks, colBlocks) -- the constructor arguments of the PartitionedPSDMatrix."""
+    n = X.shape[0]
+    groups = [X[s:s + rows_per_block] for s in range(0, n, rows_per_block)]   # data.grouped(numElementsPerRowBlock)
+    blocks = {}
+    for i, gi in enumerate(groups):
+        for j, gj in enumerate(groups):
+            if i >= j:
+                blocks[(i, j)] = build_kernel_matrix(cov, gi, noise) if i == j else \
+                    (cov.value(gi, gj) + (noise.value(gi, gj) if noise is not None else 0.0))
+    return blocks, n, n, math.ceil(n / rows_per_block), math.ceil(n / cols_per_block)
+
+
+def cross_partitioned_kernel_matrix(cov, X: np.ndarray, Y: np.ndarray, rows_per_block: int, cols_per_block: int):
+    """SVMKernel.crossPartitonedKernelMatrix (SVMKernel.scala:221-248)."""
+    gr = [X[s:s + rows_per_block] for s in range(0, X.shape[0], rows_per_block)]
+    gc = [Y[s:s + cols_per_block] for s in range(0, Y.shape[0], cols_per_block)]
+    blocks = {(i, j): cov.value(a, b) for i, a in enumerate(gr) for j, b in enumerate(gc)}
+    return blocks, X.shape[0], Y.shape[0], math.ceil(X.shape[0] / rows_per_block), math.ceil(Y.shape[0] / cols_per_block)
+
+
 def bcholesky(K: np.ndarray, block: int) -> np.ndarray:
     """choleskyPAcc (CORE/algebra/bcholesky.scala:85-125): L11 = chol(A11); L21 = A21 inv(L11)^T;
     recurse on A22 - L21 L21^T."""

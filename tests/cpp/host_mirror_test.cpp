@@ -54,6 +54,21 @@ int main(int argc, char **argv) {
     std::printf("\"kernelspec_se\": %.17g,\n", SEKernel(1.0, 1.0).evaluate({1.0}, {0.0}));
     std::printf("\"kernelspec_laplace\": %.17g, \"kernelspec_cauchy\": %.17g,\n",
                 LaplacianKernel(1.0).evaluate({1.0}, {0.0}), CauchyKernel(1.0).evaluate({1.0}, {1.5}));
+    // ---- KernelSpec.scala:205-229: partitioned builder, eval2 = 1 / (1 + (x - y)^2) = CauchyKernel(1) on {0, 1}, 1 per block
+    {
+      CauchyKernel ck(1.0);
+      ck.setBlockSizes(1, 1);
+      const PartitionedMatrix k4 = ck.buildBlockedKernelMatrix({{0.0}, {1.0}});
+      bool ok = k4.rows == 2 && k4.cols == 2 && k4.rowBlocks == 2 && k4.colBlocks == 2 && k4.blocks.size() == 3;
+      for (const auto &kv : k4.blocks) ok = ok && kv.second(0, 0) == (kv.first.first == kv.first.second ? 1.0 : 0.5);
+      const DenseMatrix dense = k4.toDenseMatrix();
+      ok = ok && dense(0, 1) == 0.5 && dense(1, 0) == 0.5 && dense(1, 1) == 1.0;
+      std::printf("\"kernelspec_partitioned_ok\": %s,\n", ok ? "true" : "false");
+      // SVMKernel.scala:107-145: d/dsigma of the Cauchy kernel = 2 k^2 r^2 / sigma^3 = 0.5 at r = 1, sigma = 1
+      const auto gm = ck.buildKernelGradMatrix({{0.0}, {1.0}});
+      std::printf("\"kernelspec_grad_sigma_01\": %.17g, \"kernelspec_grad_sigma_00\": %.17g,\n", gm.at("sigma")(0, 1),
+                  gm.at("sigma")(0, 0));
+    }
     // ---- block / unblock plumbing (KernelSpec.scala:12-32)
     {
       SEKernel se(1.0, 1.0);

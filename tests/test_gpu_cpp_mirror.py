@@ -46,6 +46,8 @@ def test_reference_known_answers_through_cpp(result):
     assert abs(out["kernelspec_laplace"] - 0.36787944117144233) < 1e-15
     assert abs(out["kernelspec_cauchy"] - 0.8) < 1e-15
     assert out["block_unblock_ok"] and out["missing_key_throws"]
+    assert out["kernelspec_partitioned_ok"]                                            # KernelSpec.scala:205-229
+    assert out["kernelspec_grad_sigma_01"] == pytest.approx(0.5, rel=1e-15) and out["kernelspec_grad_sigma_00"] == 0.0
 
 
 def test_cpp_model_matches_oracle(result):

@@ -310,6 +310,32 @@ def test_csa_is_consistent_across_two_gloo_ranks():
     assert res[0][3] and "different candidate lists" in res[0][3]
 
 
+# ---- blocked containers (CORE/algebra/PartitionedMatrix.scala, PartitionedVector.scala) ---------------------------------
+def test_partitioned_containers():
+    from dynaml_b200.algebra import LowerTriPartitionedMatrix, PartitionedMatrix, PartitionedPSDMatrix, PartitionedVector
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((7, 7))
+    S = A @ A.T
+    cuts = [(0, 3), (3, 6), (6, 7)]
+    lower = [((i, j), S[a:b, c:d]) for i, (a, b) in enumerate(cuts) for j, (c, d) in enumerate(cuts) if i >= j]
+    P = PartitionedPSDMatrix(lower, 7, 7, 3, 3)
+    assert (P.rows, P.cols, P.rowBlocks, P.colBlocks) == (7, 7, 3, 3)
+    assert len(P._underlyingdata) == 6 and len(P._data) == 9          # upper blocks are the transposes (:248-259)
+    assert np.array_equal(P.toBreezeMatrix(), S)
+    sub = P(range(1, 3), range(0, 2))                                 # re-indexed from 0 (:50-55)
+    assert (sub.rowBlocks, sub.colBlocks) == (2, 2) and np.array_equal(sub.toBreezeMatrix(), S[3:7, 0:6])
+    assert np.array_equal(P.t.toBreezeMatrix(), S.T)
+    L = np.linalg.cholesky(S)
+    T = LowerTriPartitionedMatrix([((i, j), L[a:b, c:d]) for i, (a, b) in enumerate(cuts) for j, (c, d) in enumerate(cuts)
+                                   if i >= j], 7, 7, 3, 3)
+    assert np.array_equal(T.toBreezeMatrix(), L) and T._blocks()[(0, 2)].shape == (3, 1)
+    M = PartitionedMatrix([((0, 0), np.ones((2, 3))), ((1, 0), 2 * np.ones((1, 3)))])
+    assert (M.rows, M.cols, M.rowBlocks, M.colBlocks) == (3, 3, 2, 1)
+    v = PartitionedVector.fromDense(np.arange(7.0), 3)
+    assert v.rowBlocks == 3 and v.rows == 7 and [x.size for _, x in v._data] == [3, 3, 1]
+    assert np.array_equal(v.toBreezeVector(), np.arange(7.0)) and np.array_equal(v(range(1, 3)).toBreezeVector(), np.arange(3.0, 7.0))
+
+
 # ---- 2D block-cyclic layout of the distributed Cholesky (host-only entry point of the C ABI) ----------
 @pytest.mark.parametrize("n,tile,pr,pc", [(131072, 512, 2, 4), (131072, 512, 1, 1), (10000, 256, 2, 2),
                                           (3000, 256, 1, 2), (700, 256, 2, 4)])

@@ -62,6 +62,33 @@ def test_kernelspec_builders_layout():
     assert K.shape == (2, 2) and np.array_equal(K, np.array([[1.0, 0.5], [0.5, 1.0]]))
     C = orc.cross_kernel_matrix(Eval2(), X, np.array([[0.0]]))
     assert C.shape == (2, 1) and np.array_equal(C[:, 0], np.array([1.0, 0.5]))
+    # KernelSpec.scala:205-229: the partitioned builders with one element per block
+    blocks, rows, cols, rb, cb = orc.build_partitioned_kernel_matrix(Eval2(), X, 1, 1)
+    assert (rows, cols, rb, cb) == (2, 2, 2, 2)                                   # k4.rows/cols/rowBlocks/colBlocks
+    assert sorted(blocks) == [(0, 0), (1, 0), (1, 1)]                             # block row >= block column only
+    assert all(np.array_equal(b, [[1.0]] if i == j else [[0.5]]) for (i, j), b in blocks.items())
+    blocks, rows, cols, rb, cb = orc.cross_partitioned_kernel_matrix(Eval2(), X, np.array([[0.0]]), 1, 1)
+    assert (rows, cols, rb, cb) == (2, 1, 2, 1)                                   # k5
+    assert all(np.array_equal(b, [[1.0]] if i == j else [[0.5]]) for (i, j), b in blocks.items())
+
+
+def test_partitioned_builder_blocks_are_slices_of_the_dense_matrix():
+    """Ragged last block, noise on the diagonal blocks only (distinct points), Dirac on duplicates across blocks."""
+    X, _, Xs = orc.synthetic(23, 3, seed=1, m=7)
+    cov, nz = orc.Kernel("matern", {"p": 2.0, "l": 1.7}), orc.dirac(0.3)
+    K = orc.build_kernel_matrix(cov, X, nz)
+    blocks, rows, cols, rb, cb = orc.build_partitioned_kernel_matrix(cov, X, 5, 5, nz)
+    assert (rows, cols, rb, cb) == (23, 23, 5, 5) and len(blocks) == 15
+    for (i, j), b in blocks.items():
+        assert np.array_equal(b, K[5 * i:5 * i + 5, 5 * j:5 * j + 5])
+    X[17] = X[2]                                   # a duplicate in another block: the Dirac term fires off the diagonal
+    blocks, *_ = orc.build_partitioned_kernel_matrix(cov, X, 5, 5, nz)
+    assert blocks[(3, 0)][2, 2] == orc.build_kernel_matrix(cov, X, nz)[17, 2] == 1.0 + 0.3
+    C = orc.cross_kernel_matrix(cov, X, Xs)
+    blocks, rows, cols, rb, cb = orc.cross_partitioned_kernel_matrix(cov, X, Xs, 10, 4)
+    assert (rows, cols, rb, cb) == (23, 7, 3, 2)
+    for (i, j), b in blocks.items():
+        assert np.array_equal(b, C[10 * i:10 * i + 10, 4 * j:4 * j + 4])
 
 
 def test_partitioned_cholesky_spec():
