@@ -243,10 +243,19 @@ class Dist:
             torch.cuda.set_device(local)
             dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
             self.pg = dist
+            # host-side barrier (sockets): ranks waiting in an NCCL barrier keep a spinning kernel on their GPU, which the
+            # driver time-slices against any other process computing on that GPU (the single-process C5 leg)
+            self.host = dist.new_group(backend="gloo")
 
     def barrier(self):
         if self.pg is not None:
             self.pg.barrier()
+
+    def host_barrier(self):
+        if self.pg is not None:
+            import torch
+            torch.cuda.synchronize()
+            self.pg.barrier(group=self.host)
 
     def max(self, x: float) -> float:
         if self.pg is None:
@@ -372,7 +381,7 @@ def run_c5(ctx, D: Dist, rank: int, args) -> dict:
     #    JVM); the other ranks have released their workspaces and wait at the barrier
     if world > 1:
         ctx.trim()
-        D.barrier()
+        D.host_barrier()
         if rank == 0:
             try:
                 model.useDevices(list(range(world)))
@@ -387,7 +396,7 @@ def run_c5(ctx, D: Dist, rank: int, args) -> dict:
             except Exception as ex:
                 out["single_process"] = {"error": f"{type(ex).__name__}: {ex}"}
             model.useDevices([])
-        D.barrier()
+        D.host_barrier()
     model._drop_data()
     return out
 

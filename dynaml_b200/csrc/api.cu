@@ -37,6 +37,7 @@ void *Ctx::buf(const char *name, size_t bytes) {
   if (it != arena.end() && it->second.second >= bytes) return it->second.first;
   if (it != arena.end()) {
     cudaDeviceSynchronize();  // any slot's streams may still be reading the old buffer
+    drop_graphs();            // captured launches hold the old address
     cudaFree(it->second.first);
     arena.erase(it);
   }
@@ -51,16 +52,24 @@ void *Ctx::buf(const char *name, size_t bytes) {
   return p;
 }
 
+void Ctx::drop_graphs() {
+  for (auto &kv : potrf_graphs)
+    if (kv.second.first) cudaGraphExecDestroy(kv.second.first);
+  potrf_graphs.clear();
+}
+
 void Ctx::release(const char *name) {
   auto it = arena.find(name);
   if (it == arena.end()) return;
   cudaDeviceSynchronize();
+  drop_graphs();
   cudaFree(it->second.first);
   arena.erase(it);
 }
 
 void Ctx::release_all() {
   cudaDeviceSynchronize();
+  drop_graphs();
   for (auto &kv : arena) cudaFree(kv.second.first);
   arena.clear();
 }
@@ -510,8 +519,13 @@ int32_t enqueue_eval(Ctx *ctx, int slot, const Data *D, const Spec &sp, bool wan
   DGP_TRY(assemble(ctx, S, cp, a));
   if (D->psi) DGP_TRY(add_basis_term(ctx, S, D->psi, np, D->psi, np, D->basis_mp, K, np, np, np, true));
   tick(ctx, slot, 1);
-  DGP_CUDA_OK(ctx, cudaMemsetAsync(d_info, 0, sizeof(int), S));
-  DGP_TRY(potrf_blocked_on(ctx, S, ctx->lookahead ? P : S, K, np, np, inv, d_info, nm[4]));
+  // The factorisation goes through a CUDA graph (one per slot and size): its status word must then sit at a fixed
+  // address, so it is per slot and copied to the candidate's word afterwards.
+  DGP_BUF(slot_info, int, ctx, "slot_info", 16 * sizeof(int));
+  int *sinfo = slot_info + slot;
+  DGP_CUDA_OK(ctx, cudaMemsetAsync(sinfo, 0, sizeof(int), S));
+  DGP_TRY(potrf_blocked_graph(ctx, S, ctx->lookahead ? P : S, K, np, np, inv, sinfo, nm[4]));
+  DGP_CUDA_OK(ctx, cudaMemcpyAsync(d_info, sinfo, sizeof(int), cudaMemcpyDeviceToDevice, S));
   tick(ctx, slot, 2);
   // The two triangular solves are a chain of 2 N/128 small dependent launches that leaves the GPU almost idle
   // (5 ms at N = 32768); with a gradient to compute they run on the panel stream underneath the triangular
@@ -643,6 +657,8 @@ int32_t dgp_ctx_create(int32_t device, dgp_ctx **out) {
   ctx->sm_count = prop.multiProcessorCount;
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  ctx->prio_lo = lo;
+  ctx->prio_hi = hi;
   bool ok = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, lo) == cudaSuccess &&
             cudaStreamCreateWithPriority(&ctx->panel, cudaStreamNonBlocking, hi) == cudaSuccess &&
             cudaEventCreate(&ctx->ev_a) == cudaSuccess && cudaEventCreate(&ctx->ev_b) == cudaSuccess;
@@ -678,6 +694,7 @@ int32_t dgp_ctx_destroy(dgp_ctx *ctx) {
   if (!ctx) return DGP_OK;
   cudaSetDevice(ctx->device);
   dist_destroy(ctx);
+  ctx->drop_graphs();
   gemm_release(ctx);
   ctx->release_all();
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -726,6 +743,9 @@ const char *dgp_last_error(const dgp_ctx *ctx) { return ctx ? ctx->err.c_str() :
 
 int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
   if (!ctx || !key) return DGP_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  ctx->drop_graphs();  // every tunable below changes what a captured factorisation would launch
   if (!strcmp(key, "nb")) {
     if (value < 0 || value % TILE) return ctx->fail(DGP_ERR_ARG, "nb must be 0 (auto) or a positive multiple of 128");
     ctx->nb = value;
@@ -743,6 +763,8 @@ int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
   } else if (!strcmp(key, "gemm_v4_mask")) {
     if (value < 0 || value > 15) return ctx->fail(DGP_ERR_ARG, "gemm_v4_mask must be in 0..15");
     ctx->gemm_v4_mask = (int)value;
+  } else if (!strcmp(key, "graphs")) {
+    ctx->use_graphs = value != 0;
   } else if (!strcmp(key, "leaf_variant")) {
     if (value < 0 || value > 1) return ctx->fail(DGP_ERR_ARG, "leaf_variant must be 0 or 1");
     ctx->leaf_variant = (int)value;

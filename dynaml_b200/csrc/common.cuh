@@ -67,6 +67,19 @@ struct Ctx {
   void *h_stage = nullptr;   // pinned, grow-only staging buffer of dgp_data_create
   size_t h_stage_bytes = 0;
   DistState *dist = nullptr;
+  // CUDA graphs of the blocked Cholesky (potrf.cu): one executable graph per (matrix, size, streams); the
+  // factorisation is ~5 launches per 128 columns, all with arguments that do not change between evaluations
+  int use_graphs = 0;  // opt-in (option "graphs"): measured 3-12 % slower than live streams on one GPU, see DESIGN.md 4.2
+  int prio_lo = 0, prio_hi = 0;  // stream priority range of the device (main streams: lo, panel streams: hi)
+  int stream_priority(cudaStream_t st) const {
+    if (st == panel) return prio_hi;
+    for (int i = 0; i < 4; ++i)
+      if (slot_P[i] && st == slot_P[i]) return prio_hi;
+    return prio_lo;
+  }
+  std::map<std::tuple<const void *, int64_t, int64_t, const void *, const void *, const void *, const void *>,
+           std::pair<cudaGraphExec_t, int>> potrf_graphs;   // exec (nullptr until the 2nd call), calls seen
+  void drop_graphs();
 
   int32_t fail(int32_t code, const char *fmt, ...);
   // Named grow-only buffer.  Returns nullptr (and sets err) on OOM.
@@ -74,6 +87,26 @@ struct Ctx {
   void release(const char *name);
   void release_all();
 };
+
+// Launch with the stream's priority attached as a launch attribute.  On a live stream this changes nothing (the stream
+// already has that priority); inside a stream capture it is what carries the priority into the graph's kernel node --
+// nodes captured from a high-priority stream otherwise run at default priority and the look-ahead panels of the
+// Cholesky queue up behind the trailing update.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_with_priority(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        int priority, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributePriority;
+  attr[0].val.priority = priority;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 #define DGP_CUDA_OK(ctx, expr)                                                               \
   do {                                                                                       \

@@ -573,12 +573,12 @@ cudaError_t opt_in() {
 }
 
 template <bool AK, bool BKM>
-void launch(cudaStream_t stream, const GemmArgs &a, dim3 grid, const uint32_t *tiles, int bk, int variant) {
+void launch(cudaStream_t stream, const GemmArgs &a, dim3 grid, const uint32_t *tiles, int bk, int variant, int prio) {
   if (variant == 4) {
     // the alternative hand-over modes exist for the MN-major-A layouts the path uses (NT, NN); others use the default
     auto go = [&](auto k16, auto k32) {
-      if (bk == 32) k32<<<grid, NTHREADS_B, CfgB<AK, BKM, 32>::SMEM, stream>>>(a, tiles);
-      else k16<<<grid, NTHREADS_B, CfgB<AK, BKM, 16>::SMEM, stream>>>(a, tiles);
+      if (bk == 32) launch_with_priority(k32, grid, dim3(NTHREADS_B), CfgB<AK, BKM, 32>::SMEM, stream, prio, a, tiles);
+      else launch_with_priority(k16, grid, dim3(NTHREADS_B), CfgB<AK, BKM, 16>::SMEM, stream, prio, a, tiles);
     };
     if constexpr (!AK) {
       if (a.handover == HO_DEPFOLD) return go(dgemm_dmma_v4_kernel<AK, BKM, 16, HO_DEPFOLD>, dgemm_dmma_v4_kernel<AK, BKM, 32, HO_DEPFOLD>);
@@ -616,6 +616,7 @@ struct TileTable {
 };
 
 void gemm_release(Ctx *ctx) {
+  ctx->drop_graphs();  // captured GEMM launches point at these tables
   for (auto &kv : ctx->tile_tables) cudaFree(kv.second.first);
   ctx->tile_tables.clear();
 }
@@ -684,10 +685,10 @@ int32_t gemm(Ctx *ctx, cudaStream_t stream, const GemmArgs &a_in) {
       (ctx->gemm_variant == 4 && v4_layout && !(a.ldc & 1) && !((uintptr_t)a.C & 15) && !(a.strideC & 1)) ? 4 : 2;
   const int layout = 2 * (a.a_kmajor ? 1 : 0) + (a.b_kmajor ? 1 : 0);
   if (variant == 4) bk = (((ctx->gemm_v4_bk32_mask >> layout) & 1) && a.K % 32 == 0) ? 32 : 16;
-  if (!a.a_kmajor && !a.b_kmajor) launch<false, false>(stream, a, grid, tt.dev, bk, variant);
-  else if (!a.a_kmajor && a.b_kmajor) launch<false, true>(stream, a, grid, tt.dev, bk, variant);
-  else if (a.a_kmajor && !a.b_kmajor) launch<true, false>(stream, a, grid, tt.dev, bk, variant);
-  else launch<true, true>(stream, a, grid, tt.dev, bk, variant);
+  if (!a.a_kmajor && !a.b_kmajor) launch<false, false>(stream, a, grid, tt.dev, bk, variant, ctx->stream_priority(stream));
+  else if (!a.a_kmajor && a.b_kmajor) launch<false, true>(stream, a, grid, tt.dev, bk, variant, ctx->stream_priority(stream));
+  else if (a.a_kmajor && !a.b_kmajor) launch<true, false>(stream, a, grid, tt.dev, bk, variant, ctx->stream_priority(stream));
+  else launch<true, true>(stream, a, grid, tt.dev, bk, variant, ctx->stream_priority(stream));
   ctx->launches++;
   DGP_CUDA_OK(ctx, cudaGetLastError());
   return DGP_OK;

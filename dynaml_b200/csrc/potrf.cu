@@ -573,12 +573,18 @@ int32_t factor_block_column(Ctx *ctx, cudaStream_t st, double *A, int64_t lda, i
     const int64_t rb = cs + LB, mrows = n - rb;
     // one launch: the leaf, and (extra CTAs) the copy of the panel below it to the scratch operand of the panel
     // product -- two CTAs of that GEMM share each 128-row strip, so it cannot run in place
-    if (ctx->leaf_variant == 1)
-      leaf_tile_kernel<<<(unsigned)(1 + mrows / LB), TL_THREADS, TL_SMEM, st>>>(
-          A + cs + cs * lda, lda, invb, info, (int)cs, A + rb + cs * lda, scratch, mrows);
-    else
-      leaf_potrf_inv_kernel<<<(unsigned)(1 + mrows / LB), LEAF_THREADS, LEAF_SMEM, st>>>(
-          A + cs + cs * lda, lda, invb, info, (int)cs, A + rb + cs * lda, scratch, mrows);
+    {
+      double *ablk = A + cs + cs * lda;
+      const double *psrc = A + rb + cs * lda;
+      const int pivot = (int)cs, prio = ctx->stream_priority(st);
+      const dim3 grid((unsigned)(1 + mrows / LB));
+      if (ctx->leaf_variant == 1)
+        launch_with_priority(leaf_tile_kernel, grid, dim3(TL_THREADS), TL_SMEM, st, prio, ablk, lda, invb, info, pivot, psrc,
+                             scratch, mrows);
+      else
+        launch_with_priority(leaf_potrf_inv_kernel, grid, dim3(LEAF_THREADS), LEAF_SMEM, st, prio, ablk, lda, invb, info,
+                             pivot, psrc, scratch, mrows);
+    }
     ctx->launches++;
     DGP_CUDA_OK(ctx, cudaGetLastError());
     if (rb >= n) break;
@@ -672,6 +678,52 @@ int32_t potrf_blocked_on(Ctx *ctx, cudaStream_t S, cudaStream_t P, double *A, in
     DGP_CUDA_OK(ctx, cudaEventRecord(e, P));
     DGP_CUDA_OK(ctx, cudaStreamWaitEvent(S, e, 0));
   }
+  return DGP_OK;
+}
+
+int32_t potrf_blocked_graph(Ctx *ctx, cudaStream_t S, cudaStream_t P, double *A, int64_t lda, int64_t n, double *inv,
+                            int *info, const char *scratch_name) {
+  if (!ctx->use_graphs) return potrf_blocked_on(ctx, S, P, A, lda, n, inv, info, scratch_name);
+  const auto key = std::make_tuple((const void *)A, lda, n, (const void *)inv, (const void *)info, (const void *)S,
+                                   (const void *)P);
+  auto &entry = ctx->potrf_graphs[key];
+  if (entry.first) {
+    DGP_CUDA_OK(ctx, cudaGraphLaunch(entry.first, S));
+    ctx->launches += (uint64_t)entry.second;
+    return DGP_OK;
+  }
+  if (entry.second == 0) {  // first sight of this problem: eager (allocations, tile tables)
+    entry.second = -1;
+    return potrf_blocked_on(ctx, S, P, A, lda, n, inv, info, scratch_name);
+  }
+  // second call: capture.  Everything potrf_blocked_on touches exists by now, so no allocation or copy is issued.
+  const uint64_t before = ctx->launches;
+  cudaGraph_t graph = nullptr;
+  DGP_CUDA_OK(ctx, cudaStreamBeginCapture(S, cudaStreamCaptureModeRelaxed));
+  const int32_t st = potrf_blocked_on(ctx, S, P, A, lda, n, inv, info, scratch_name);
+  const cudaError_t ce = cudaStreamEndCapture(S, &graph);
+  if (st != DGP_OK || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    ctx->potrf_graphs.erase(key);
+    ctx->use_graphs = 0;  // this driver / configuration cannot capture the sequence: stay eager
+    ctx->launches = before;
+    if (st != DGP_OK) return st;
+    return potrf_blocked_on(ctx, S, P, A, lda, n, inv, info, scratch_name);
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    cudaGetLastError();
+    ctx->potrf_graphs.erase(key);
+    ctx->use_graphs = 0;
+    ctx->launches = before;
+    return potrf_blocked_on(ctx, S, P, A, lda, n, inv, info, scratch_name);
+  }
+  entry.first = exec;
+  entry.second = (int)(ctx->launches - before);   // kernels inside the graph, for the launch counter
+  DGP_CUDA_OK(ctx, cudaGraphLaunch(exec, S));
   return DGP_OK;
 }
 

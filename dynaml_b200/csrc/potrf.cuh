@@ -21,6 +21,13 @@ int32_t potrf_blocked(Ctx *ctx, double *A, int64_t lda, int64_t n, double *inv, 
 int32_t potrf_blocked_on(Ctx *ctx, cudaStream_t S, cudaStream_t P, double *A, int64_t lda, int64_t n, double *inv,
                          int *info, const char *scratch_name);
 
+// potrf_blocked_on through a CUDA graph.  The first call for a given (A, lda, n, inv, info, S, P) runs eagerly (it
+// allocates the scratch panel and builds the GEMM tile tables), the second captures the same launch sequence on the
+// two streams into a graph, and from then on one cudaGraphLaunch on S replaces the ~5 launches per 128 columns.
+// Same kernels, same order, same results.  Falls back to the eager path when ctx->use_graphs == 0.
+int32_t potrf_blocked_graph(Ctx *ctx, cudaStream_t S, cudaStream_t P, double *A, int64_t lda, int64_t n, double *inv,
+                            int *info, const char *scratch_name);
+
 // W (lower) = L^-1 from L and the diagonal-block inverses; scratch is an n x n buffer (ld = lds)
 // whose lower triangle is clobbered.  Tiles of W strictly above the diagonal are not written.
 int32_t trtri_lower(Ctx *ctx, const double *L, int64_t ldl, const double *inv, int64_t n, double *W, int64_t ldw,

@@ -147,6 +147,10 @@ const char *dgp_version(void);
    those of them using 32-wide K-slices; defaults 3 and 2), "gemm_bk" (16/32, cp.async kernel),
    "gemm_handover" (stage hand-over of the bulk-copy kernel), "gemm_no_prefetch" (0/1, testing: no L2 prefetch of the C tile),
    "inverse_transposed" (1 = K^-1 as U U^T from U = L^-T, the default; 0 = W^T W from W = L^-1),
+   "graphs" (1 = the blocked Cholesky of energy / energy_grad / energy_batch is replayed from a CUDA graph after
+   its second use at a given size; 0 = launched kernel by kernel, the default -- the graph replay measured 3-12 %
+   slower on one GPU; same results either way),
+   "leaf_variant" (1 = tensor-pipe 128-block leaf, the default; 0 = scalar leaf),
    "trsv_chained" (1 = each triangular solve is one launch whose CTAs hand the solved segments over through
    flags, the default; 0 = one launch per 128-row block; same results).                                     */
 int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value);
