@@ -509,23 +509,29 @@ int32_t enqueue_eval(Ctx *ctx, int slot, const Data *D, const Spec &sp, bool wan
   CovParams cp = make_cov_params(sp, true, D->d);
 
   tick(ctx, slot, 0);
-  AssembleArgs a;
-  a.X1 = Xk;  a.X2 = Xk;  a.dp = D->dp;
-  a.rows = D->N;  a.cols = D->N;  a.rows_p = np;  a.cols_p = np;
-  a.out = K;  a.ld = np;
-  a.symmetric = 1;  a.lower_only = 1;
-  a.use_gram = pick_gram(ctx, sp, cp, D->dp, D->d, D->max_sq_norm);
-  a.nodup = points_stay_distinct(D->has_dup, sp, D->d);
-  DGP_TRY(assemble(ctx, S, cp, a));
-  if (D->psi) DGP_TRY(add_basis_term(ctx, S, D->psi, np, D->psi, np, D->basis_mp, K, np, np, np, true));
+  {
+    NvtxRange r("dgp:assemble");
+    AssembleArgs a;
+    a.X1 = Xk;  a.X2 = Xk;  a.dp = D->dp;
+    a.rows = D->N;  a.cols = D->N;  a.rows_p = np;  a.cols_p = np;
+    a.out = K;  a.ld = np;
+    a.symmetric = 1;  a.lower_only = 1;
+    a.use_gram = pick_gram(ctx, sp, cp, D->dp, D->d, D->max_sq_norm);
+    a.nodup = points_stay_distinct(D->has_dup, sp, D->d);
+    DGP_TRY(assemble(ctx, S, cp, a));
+    if (D->psi) DGP_TRY(add_basis_term(ctx, S, D->psi, np, D->psi, np, D->basis_mp, K, np, np, np, true));
+  }
   tick(ctx, slot, 1);
-  // The factorisation goes through a CUDA graph (one per slot and size): its status word must then sit at a fixed
-  // address, so it is per slot and copied to the candidate's word afterwards.
-  DGP_BUF(slot_info, int, ctx, "slot_info", 16 * sizeof(int));
-  int *sinfo = slot_info + slot;
-  DGP_CUDA_OK(ctx, cudaMemsetAsync(sinfo, 0, sizeof(int), S));
-  DGP_TRY(potrf_blocked_graph(ctx, S, ctx->lookahead ? P : S, K, np, np, inv, sinfo, nm[4]));
-  DGP_CUDA_OK(ctx, cudaMemcpyAsync(d_info, sinfo, sizeof(int), cudaMemcpyDeviceToDevice, S));
+  {
+    NvtxRange r("dgp:potrf");
+    // The factorisation may go through a CUDA graph (option "graphs"; one per slot and size): its status word must
+    // then sit at a fixed address, so it is per slot and copied to the candidate's word afterwards.
+    DGP_BUF(slot_info, int, ctx, "slot_info", 16 * sizeof(int));
+    int *sinfo = slot_info + slot;
+    DGP_CUDA_OK(ctx, cudaMemsetAsync(sinfo, 0, sizeof(int), S));
+    DGP_TRY(potrf_blocked_graph(ctx, S, ctx->lookahead ? P : S, K, np, np, inv, sinfo, nm[4]));
+    DGP_CUDA_OK(ctx, cudaMemcpyAsync(d_info, sinfo, sizeof(int), cudaMemcpyDeviceToDevice, S));
+  }
   tick(ctx, slot, 2);
   // The two triangular solves are a chain of 2 N/128 small dependent launches that leaves the GPU almost idle
   // (5 ms at N = 32768); with a gradient to compute they run on the panel stream underneath the triangular
@@ -536,21 +542,27 @@ int32_t enqueue_eval(Ctx *ctx, int slot, const Data *D, const Spec &sp, bool wan
     DGP_CUDA_OK(ctx, cudaEventRecord(e, S));
     DGP_CUDA_OK(ctx, cudaStreamWaitEvent(Z, e, 0));
   }
-  DGP_CUDA_OK(ctx, cudaMemcpyAsync(x, D->r, (size_t)np * sizeof(double), cudaMemcpyDeviceToDevice, Z));
-  DGP_TRY(trsv_lower_fwd(ctx, Z, K, np, inv, np, x));
-  DGP_TRY(trsv_lower_bwd(ctx, Z, K, np, inv, np, x));
-  DGP_TRY(dot(ctx, Z, D->r, x, np, d_scal + 0));
-  DGP_TRY(diag_log_sum(ctx, Z, K, np, np, d_scal + 1));
+  {
+    NvtxRange r("dgp:solve");
+    DGP_CUDA_OK(ctx, cudaMemcpyAsync(x, D->r, (size_t)np * sizeof(double), cudaMemcpyDeviceToDevice, Z));
+    DGP_TRY(trsv_lower_fwd(ctx, Z, K, np, inv, np, x));
+    DGP_TRY(trsv_lower_bwd(ctx, Z, K, np, inv, np, x));
+    DGP_TRY(dot(ctx, Z, D->r, x, np, d_scal + 0));
+    DGP_TRY(diag_log_sum(ctx, Z, K, np, np, d_scal + 1));
+  }
   tick(ctx, slot, 3, Z);
   if (want_grad) {
     DGP_BUF(W, double, ctx, nm[5], (size_t)np * np * sizeof(double));
     DGP_BUF(Kinv, double, ctx, "Kinv", (size_t)np * np * sizeof(double));
-    if (ctx->inverse_transposed) {  // W holds U = L^-T
-      DGP_TRY(trtri_lower_transposed_on(ctx, S, K, np, inv, np, W, np, Kinv, np));
-      DGP_TRY(lauum_upper_on(ctx, S, W, np, np, Kinv, np));
-    } else {
-      DGP_TRY(trtri_lower_on(ctx, S, K, np, inv, np, W, np, Kinv, np));
-      DGP_TRY(lauum_lower_on(ctx, S, W, np, np, Kinv, np));
+    {
+      NvtxRange r("dgp:inverse");
+      if (ctx->inverse_transposed) {  // W holds U = L^-T
+        DGP_TRY(trtri_lower_transposed_on(ctx, S, K, np, inv, np, W, np, Kinv, np));
+        DGP_TRY(lauum_upper_on(ctx, S, W, np, np, Kinv, np));
+      } else {
+        DGP_TRY(trtri_lower_on(ctx, S, K, np, inv, np, W, np, Kinv, np));
+        DGP_TRY(lauum_lower_on(ctx, S, W, np, np, Kinv, np));
+      }
     }
     tick(ctx, slot, 4);
     if (Z != S) {  // the trace pass needs alpha
@@ -565,7 +577,10 @@ int32_t enqueue_eval(Ctx *ctx, int slot, const Data *D, const Spec &sp, bool wan
     g.X = Xbase;  g.Xs = Xk;  g.alpha = x;  g.Kinv = Kinv;  g.ld = np;
     g.n = D->N;  g.np = np;  g.dp = D->dp;
     g.partials = partials;  g.sums = d_scal + 2;
-    DGP_TRY(grad_trace(ctx, S, cp, g, ns_out));
+    {
+      NvtxRange r("dgp:grad_trace");
+      DGP_TRY(grad_trace(ctx, S, cp, g, ns_out));
+    }
     tick(ctx, slot, 5);
   }
   return DGP_OK;
@@ -781,6 +796,9 @@ int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
     if (value < 0 || value > 3)
       return ctx->fail(DGP_ERR_ARG, "assembly must be 0 (auto), 1 (exact differences), 2 (Gram) or 3 (checked Gram)");
     ctx->assembly = (int)value;
+  } else if (!strcmp(key, "assembly_store")) {
+    if (value < 0 || value > 1) return ctx->fail(DGP_ERR_ARG, "assembly_store must be 0 (direct) or 1 (bulk)");
+    ctx->assembly_store = (int)value;
   } else if (!strcmp(key, "batch_streams")) {
     if (value < 1 || value > 4) return ctx->fail(DGP_ERR_ARG, "batch_streams must be in 1..4");
     ctx->batch_streams = (int)value;
@@ -1293,6 +1311,7 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
   CovParams cpx = make_cov_params(cs, false, m->d);
   const int gram = pick_gram(ctx, cs, cpx, dp, m->d, nmax);
   tick(ctx, 0, 0);
+  NvtxRange r_predict("dgp:predict");
   {
     AssembleArgs a;
     a.X1 = Xtrain;  a.X2 = Xtk;  a.dp = dp;

@@ -655,8 +655,14 @@ struct ExpTab {
   double v[64];  // amplitude * 2^(j/64), built on the host per launch
 };
 
+// Staged (bulk / TMA) store variant, option "assembly_store" = 1: each 32-column chunk of the tile is written to a
+// shared-memory staging buffer (column stride 136 doubles: conflict-free 16-byte stores, 16-byte aligned columns) and
+// one elected thread hands the 32 columns to the bulk-copy engine as 1 KB cp.async.bulk.global.shared::cta stores.
+constexpr int STG_LD = AT + 8;                       // doubles per staged column
+constexpr int STG_DOUBLES = 32 * STG_LD;             // one chunk
+
 // P3: Matern order 3 (cubic polynomial in r); orders 1 and 2 share the quadratic form.
-template <int KIND, int DP, bool P3>
+template <int KIND, int DP, bool P3, bool BULK = false>
 __global__ void __launch_bounds__(ATHREADS, 3)
     assemble_gram_lean_kernel(LeanCov f, LeanConst lc, ExpTab T, double kdiag, AssembleArgs a) {
   constexpr int LDK = lean_ldk<DP>();
@@ -666,6 +672,7 @@ __global__ void __launch_bounds__(ATHREADS, 3)
   double *Acol = Brow + AT * LDK;       // column points j (MMA M): [j][k] = -2 y
   double *nx = Acol + AT * LDK;         // |x_i|^2
   double *ny = nx + AT;                 // |y_j|^2
+  double *stg = ny + AT;                // BULK: staging buffer of one 32-column chunk
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -731,6 +738,10 @@ __global__ void __launch_bounds__(ATHREADS, 3)
   const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab) + ((unsigned)(lane & 15) << 3);  // this lane's copy
 #pragma unroll 1
   for (int chunk = 0; chunk < 4; ++chunk) {
+    if (BULK && chunk > 0) {  // the engine must have read the previous chunk out of the staging buffer
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+      __syncthreads();
+    }
     const int jbase = chunk * 32 + wm * 16;
     const double *ap = Acol + (jbase + g) * LDK + t;
     double acc[2][4][2];
@@ -761,7 +772,7 @@ __global__ void __launch_bounds__(ATHREADS, 3)
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb) {
       const int jl = jbase + mb * 8 + g;
-      double *ocol = out + (int64_t)jl * a.ld + ibase + 2 * t;
+      double *ocol = BULK ? (stg + (jl - chunk * 32) * STG_LD + ibase + 2 * t) : (out + (int64_t)jl * a.ld + ibase + 2 * t);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         double x[4], kv[4];
@@ -801,6 +812,30 @@ __global__ void __launch_bounds__(ATHREADS, 3)
         *reinterpret_cast<double2 *>(ocol + (2 * q + 1) * 8) = make_double2(kv[2], kv[3]);
       }
     }
+    if (BULK) {
+      // the diagonal of a symmetric tile is k(0) + noise: patched in the staging buffer before it leaves
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // staged generic writes -> async-proxy reads
+      __syncthreads();
+      if (diag_tile && tid < 32) stg[tid * STG_LD + chunk * 32 + tid] = kdiag;
+      if (diag_tile) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncthreads();
+      }
+      if (tid == 0) {
+        const unsigned src = (unsigned)__cvta_generic_to_shared(stg);
+        double *dst = out + (int64_t)(chunk * 32) * a.ld;
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c)
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst + (int64_t)c * a.ld),
+                       "r"(src + (unsigned)(c * STG_LD * 8)), "n"(AT * 8)
+                       : "memory");
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+      }
+    }
+  }
+  if (BULK) {
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // shared memory is released at exit
+    return;
   }
   if (diag_tile) {  // CTA-uniform; the barrier orders these stores after the tile's own
     __syncthreads();
@@ -809,7 +844,7 @@ __global__ void __launch_bounds__(ATHREADS, 3)
 }
 
 template <int KIND, int DP>
-void launch_lean(cudaStream_t st, const CovParams &cp, const AssembleArgs &a, unsigned tiles) {
+void launch_lean(cudaStream_t st, const CovParams &cp, const AssembleArgs &a, unsigned tiles, bool bulk) {
   LeanCov f;
   f.scale = (KIND == DGP_KERNEL_MATERN) ? cp.c1 : sqrt(cp.c1);
   f.m0 = f.m1 = f.m2 = f.m3 = 0.0;
@@ -828,7 +863,9 @@ void launch_lean(cudaStream_t st, const CovParams &cp, const AssembleArgs &a, un
   lc.c5 = 1.0 / 120.0;  lc.c4 = 1.0 / 24.0;  lc.c3 = 1.0 / 6.0;
   // value at distance zero plus the noise term (DiracKernel.scala:43-47 adds |sigma| where |x-y| == 0)
   const double kdiag = ((KIND == DGP_KERNEL_MATERN) ? cp.coef[cp.p] : cp.a2) + cp.noise_abs;
-  size_t smem = ((size_t)2 * AT * lean_ldk<DP>() + 2 * AT + 64 * 16) * sizeof(double);
+  // bulk stores need 16-byte aligned destination columns (ld even is already required; out from cudaMalloc)
+  bulk = bulk && ((uintptr_t)a.out % 16 == 0) && (a.ld % 2 == 0);
+  size_t smem = ((size_t)2 * AT * lean_ldk<DP>() + 2 * AT + 64 * 16 + (bulk ? STG_DOUBLES : 0)) * sizeof(double);
   auto go = [&](auto kern) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<tiles, ATHREADS, smem, st>>>(f, lc, T, kdiag, a);
@@ -839,19 +876,25 @@ void launch_lean(cudaStream_t st, const CovParams &cp, const AssembleArgs &a, un
       return;
     }
   }
+  if constexpr (KIND == DGP_KERNEL_SE && (DP == 8 || DP == 16)) {
+    if (bulk) {
+      go(assemble_gram_lean_kernel<KIND, DP, false, true>);
+      return;
+    }
+  }
   go(assemble_gram_lean_kernel<KIND, DP, false>);
 }
 
 template <int KIND>
-bool launch_lean_kind(cudaStream_t st, const CovParams &cp, const AssembleArgs &a, unsigned tiles) {
+bool launch_lean_kind(cudaStream_t st, const CovParams &cp, const AssembleArgs &a, unsigned tiles, bool bulk = false) {
   switch (a.dp) {
-    case 4: launch_lean<KIND, 4>(st, cp, a, tiles); return true;
-    case 8: launch_lean<KIND, 8>(st, cp, a, tiles); return true;
-    case 12: launch_lean<KIND, 12>(st, cp, a, tiles); return true;
-    case 16: launch_lean<KIND, 16>(st, cp, a, tiles); return true;
-    case 20: launch_lean<KIND, 20>(st, cp, a, tiles); return true;
-    case 24: launch_lean<KIND, 24>(st, cp, a, tiles); return true;
-    case 32: launch_lean<KIND, 32>(st, cp, a, tiles); return true;
+    case 4: launch_lean<KIND, 4>(st, cp, a, tiles, bulk); return true;
+    case 8: launch_lean<KIND, 8>(st, cp, a, tiles, bulk); return true;
+    case 12: launch_lean<KIND, 12>(st, cp, a, tiles, bulk); return true;
+    case 16: launch_lean<KIND, 16>(st, cp, a, tiles, bulk); return true;
+    case 20: launch_lean<KIND, 20>(st, cp, a, tiles, bulk); return true;
+    case 24: launch_lean<KIND, 24>(st, cp, a, tiles, bulk); return true;
+    case 32: launch_lean<KIND, 32>(st, cp, a, tiles, bulk); return true;
     default: return false;
   }
 }
@@ -928,7 +971,7 @@ int32_t assemble(Ctx *ctx, cudaStream_t st, const CovParams &cp, const AssembleA
     const bool lean = ctx->assembly != 3 && (cp.noise_abs == 0.0 || (a.symmetric && a.nodup)) &&
                       cp.a2 >= 1e-150 && cp.a2 <= 1e150;
     if (lean) {
-      done = se_like ? launch_lean_kind<DGP_KERNEL_SE>(st, cp, a, (unsigned)tiles)
+      done = se_like ? launch_lean_kind<DGP_KERNEL_SE>(st, cp, a, (unsigned)tiles, ctx->assembly_store == 1)
                      : launch_lean_kind<DGP_KERNEL_MATERN>(st, cp, a, (unsigned)tiles);
       const bool padded = a.rows_p != a.rows || a.cols_p != a.cols;
       if (done && padded) {  // edge pass: tiles touching the padding, with the checked epilogue

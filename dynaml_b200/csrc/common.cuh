@@ -13,6 +13,8 @@
 #include <tuple>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost a null-pointer test unless a profiler is attached
+
 #include "../../include/dgp_b200.h"
 
 namespace dgp {
@@ -53,6 +55,7 @@ struct Ctx {
   int gemm_no_prefetch = 0;  // testing only: GEMMs skip the L2 prefetch of their C tile
   int gemm_bk = 32;   // K-slice of the GEMM pipeline: 16 (3-4 stages) or 32 (double buffered)
   int assembly = 0;   // 0: Gram/DMMA assembly when its error bound allows, 1: always exact differences, 2: force Gram
+  int assembly_store = 0;  // lean SE assembly: 0 = 16-byte st.global from registers, 1 = staged chunk + bulk (TMA) stores
   int batch_streams = 3;  // dgp_energy_batch evaluates this many candidates concurrently (1..4)
   cudaStream_t slot_S[4] = {nullptr, nullptr, nullptr, nullptr};  // extra (main, panel) stream pairs, created lazily
   cudaStream_t slot_P[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -107,6 +110,15 @@ inline cudaError_t launch_with_priority(void (*kernel)(KArgs...), dim3 grid, dim
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
+
+// NVTX range over the host-side enqueue of one phase: shows up in Nsight timelines next to the kernels the
+// phase launched; free without a tool attached.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 #define DGP_CUDA_OK(ctx, expr)                                                               \
   do {                                                                                       \

@@ -528,6 +528,7 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *
   };
 
   const size_t mv_smem = ((size_t)T + 128) * sizeof(double);
+  NvtxRange r_dist("dgp:dist_cholesky");
   for (int64_t k = 0; k < g.Nt; ++k) {
     const int b = (int)(k & 1);
     const int okr = (int)(k % ds->Pr), okc = (int)(k % ds->Pc);

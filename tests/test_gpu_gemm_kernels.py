@@ -116,3 +116,58 @@ def test_transposed_inverse_equals_the_lower_one(ctx, gemm_options):
     finally:
         ctx.set_option("inverse_transposed", 1)
         ctx.data_destroy(data)
+
+
+def test_handover_modes_agree_and_the_plain_arrival_is_caught(ctx, gemm_options):
+    """Option gemm_handover: the producer-side proxy fence (default), the consumer-side fence and the
+    round-1 register fold return the cp.async kernel's result bit for bit; the plain arrival (mode 3) is the hazard
+    itself -- if it ever stops failing, this test says so (the regression test above would then prove nothing)."""
+    import dynaml_b200 as dg
+    from oracle import gp_oracle as orc
+    X, y, _ = orc.synthetic(8192, 8, seed=5)
+    data = ctx.data_create(X, y)
+    spec = dg.SEKernel(3.0, 1.0)._spec(noise=0.05)
+    try:
+        gemm_options(gemm_variant=2)
+        e_ref = ctx.energy(data, spec)
+        gemm_options(gemm_no_prefetch=1)
+        for mode in (1, 2, 0):
+            ctx.set_option("gemm_handover", mode)
+            assert all(ctx.energy(data, spec) == e_ref for _ in range(4)), mode
+        ctx.set_option("gemm_handover", 3)
+        wrong = sum(ctx.energy(data, spec) != e_ref for _ in range(4))
+        assert wrong > 0, "the unordered hand-over no longer reproduces the hazard"
+    finally:
+        ctx.set_option("gemm_handover", 1)
+        ctx.data_destroy(data)
+
+
+def test_cholesky_and_solve_variants_agree(ctx):
+    """Options of the mid-N chain: the chained triangular solves and the CUDA-graph replay of the factorisation are
+    bit-identical to the step-by-step paths; the tile leaf and the scalar leaf agree to rounding; the staged bulk-store
+    assembly writes the same entries."""
+    import dynaml_b200 as dg
+    from oracle import gp_oracle as orc
+    X, y, _ = orc.synthetic(3000, 8, seed=2)            # ragged: padded to 3072
+    data = ctx.data_create(X, y)
+    spec = dg.SEKernel(2.5, 1.1)._spec(noise=0.1)
+    try:
+        e0, g0 = ctx.energy_grad(data, spec)
+        for key, val in (("trsv_chained", 0), ("graphs", 1), ("assembly_store", 1)):
+            ctx.set_option(key, val)
+            for _ in range(3):                           # graphs: eager, capture, replay
+                e1, g1 = ctx.energy_grad(data, spec)
+                assert e1 == e0 and np.array_equal(np.asarray(g1), np.asarray(g0)), (key, val)
+            eb, st = ctx.energy_batch(data, [spec] * 5)
+            assert all(v == ctx.energy(data, spec) for v in eb) and not st.any()
+            ctx.set_option(key, 1 - val)
+        ctx.set_option("leaf_variant", 0)
+        e2, g2 = ctx.energy_grad(data, spec)
+        assert e2 == pytest.approx(e0, rel=1e-13)
+        assert np.allclose(np.asarray(g2), np.asarray(g0), rtol=1e-11, atol=1e-11 * np.abs(g0).max(), equal_nan=True)
+        eo = orc.energy(orc.Kernel("se", {"bandwidth": 2.5, "amplitude": 1.1}), 0.1, X, y)
+        assert abs(e2 - eo) <= 1e-9 * abs(eo) and abs(e0 - eo) <= 1e-9 * abs(eo)
+    finally:
+        for key, val in (("trsv_chained", 1), ("graphs", 0), ("assembly_store", 0), ("leaf_variant", 1)):
+            ctx.set_option(key, val)
+        ctx.data_destroy(data)
