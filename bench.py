@@ -294,8 +294,11 @@ def run_c4(ctx, D: Dist, rank: int, args, dmma_peak: float | None) -> dict:
     info = ctx.dist_info()
     gold = golden_large().get("c4_check", {})
     spec = dg.SEKernel(math.sqrt(8), 1.0)._spec(noise=0.1)
+    from dynaml_b200._capi import dist_plan
+    plan = dist_plan(args.c4_n, args.c4_tile, pr, pc, rank)
     out = {"config": f"C4: synthetic N={args.c4_n}, d=8, SEKernel + DiracKernel(0.1), tile {args.c4_tile}, "
                      f"{pr}x{pc} process grid", "n": args.c4_n, "tile": args.c4_tile, "grid": [pr, pc], "n_gpus": world,
+           "local_matrix_gb_rank0": plan["local_bytes"] / 1e9, "owned_lower_tiles_rank0": plan["owned_lower_tiles"],
            "library_nccl_ranks": D.gather(info["nccl_ranks"]), "nccl_version": info["nccl_version"]}
     # -- parity leg: same grid and communicator at n = 8192 against the dense one-GPU path and the committed oracle value
     nchk = int(gold.get("n", 8192))

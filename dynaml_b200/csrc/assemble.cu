@@ -43,8 +43,8 @@ __global__ void __launch_bounds__(ATHREADS) assemble_kernel(CovParams cp, Assemb
   int64_t m0 = (int64_t)ti * AT + a.row_off, n0 = (int64_t)tj * AT + a.col_off;
   const int64_t lm0 = m0, ln0 = n0;  // position inside `out`
   if (a.bc_T > 0) {
-    m0 = ((int64_t)(lm0 / a.bc_T) * a.bc_Pr + a.bc_pr) * a.bc_T + lm0 % a.bc_T;
-    n0 = ((int64_t)(ln0 / a.bc_T) * a.bc_Pc + a.bc_pc) * a.bc_T + ln0 % a.bc_T;
+    m0 = ((int64_t)(lm0 / a.bc_T + a.bc_row0) * a.bc_Pr + a.bc_pr) * a.bc_T + lm0 % a.bc_T;
+    n0 = ((int64_t)(ln0 / a.bc_T + a.bc_col0) * a.bc_Pc + a.bc_pc) * a.bc_T + ln0 % a.bc_T;
     if (n0 > m0 + AT - 1) return;  // above the global diagonal (uniform, before any barrier)
   }
 
@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(ATHREADS) assemble_composite_kernel(CompositeD
   int64_t m0 = (int64_t)ti * AT + a.row_off, n0 = (int64_t)tj * AT + a.col_off;
   const int64_t lm0 = m0, ln0 = n0;
   if (a.bc_T > 0) {
-    m0 = ((int64_t)(lm0 / a.bc_T) * a.bc_Pr + a.bc_pr) * a.bc_T + lm0 % a.bc_T;
-    n0 = ((int64_t)(ln0 / a.bc_T) * a.bc_Pc + a.bc_pc) * a.bc_T + ln0 % a.bc_T;
+    m0 = ((int64_t)(lm0 / a.bc_T + a.bc_row0) * a.bc_Pr + a.bc_pr) * a.bc_T + lm0 % a.bc_T;
+    n0 = ((int64_t)(ln0 / a.bc_T + a.bc_col0) * a.bc_Pc + a.bc_pc) * a.bc_T + ln0 % a.bc_T;
     if (n0 > m0 + AT - 1) return;
   }
   for (int i = tid; i < AT * dp; i += ATHREADS) sm[i] = a.X2[n0 * dp + i];
@@ -449,8 +449,8 @@ __global__ void __launch_bounds__(ATHREADS, 2) assemble_gram_kernel(CovParams cp
   int64_t m0 = (int64_t)ti * AT + a.row_off, n0 = (int64_t)tj * AT + a.col_off;
   const int64_t lm0 = m0, ln0 = n0;
   if (a.bc_T > 0) {
-    m0 = ((int64_t)(lm0 / a.bc_T) * a.bc_Pr + a.bc_pr) * a.bc_T + lm0 % a.bc_T;
-    n0 = ((int64_t)(ln0 / a.bc_T) * a.bc_Pc + a.bc_pc) * a.bc_T + ln0 % a.bc_T;
+    m0 = ((int64_t)(lm0 / a.bc_T + a.bc_row0) * a.bc_Pr + a.bc_pr) * a.bc_T + lm0 % a.bc_T;
+    n0 = ((int64_t)(ln0 / a.bc_T + a.bc_col0) * a.bc_Pc + a.bc_pc) * a.bc_T + ln0 % a.bc_T;
     if (n0 > m0 + AT - 1) return;
   }
   // diag_only (edge pass): just the tiles assemble_gram_lean_kernel leaves out, those touching the padding
@@ -694,8 +694,8 @@ __global__ void __launch_bounds__(ATHREADS, 3)
   int64_t m0 = (int64_t)ti * AT + a.row_off, n0 = (int64_t)tj * AT + a.col_off;
   const int64_t lm0 = m0, ln0 = n0;
   if (a.bc_T > 0) {
-    m0 = ((int64_t)(lm0 / a.bc_T) * a.bc_Pr + a.bc_pr) * a.bc_T + lm0 % a.bc_T;
-    n0 = ((int64_t)(ln0 / a.bc_T) * a.bc_Pc + a.bc_pc) * a.bc_T + ln0 % a.bc_T;
+    m0 = ((int64_t)(lm0 / a.bc_T + a.bc_row0) * a.bc_Pr + a.bc_pr) * a.bc_T + lm0 % a.bc_T;
+    n0 = ((int64_t)(ln0 / a.bc_T + a.bc_col0) * a.bc_Pc + a.bc_pc) * a.bc_T + ln0 % a.bc_T;
     if (n0 > m0 + AT - 1) return;
   }
   // tiles touching the padding are left to assemble_gram_kernel (edge pass)

@@ -23,6 +23,7 @@ struct AssembleArgs {
   // T x T tiles; local tile (li, lj) holds global tile (li*Pr + pr, lj*Pc + pc).  Tiles entirely
   // above the global diagonal are skipped.
   int bc_T = 0, bc_Pr = 1, bc_Pc = 1, bc_pr = 0, bc_pc = 0;
+  int bc_row0 = 0, bc_col0 = 0;  // local tile index (units of bc_T) of the first row / column of `out`
   // 1: Gram/DMMA distance kernel (SE, RBF, ARD-SE, Matern with dp <= 32); the caller sets it only when
   // gram_is_accurate() holds.  0: exact-difference kernel.
   int use_gram = 0;

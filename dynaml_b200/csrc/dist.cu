@@ -149,10 +149,46 @@ struct ChunkMap {  // the panel of step k in owner-major layout, passed by value
   int Pr, T;
 };
 
+// Storage of a rank's local matrix: only what lies on or below the GLOBAL diagonal is kept.  The local tile
+// columns are grouped in chunks of STORE_G; chunk c is a column-major rectangle that starts at the first local tile row
+// its first column needs (the rows above it are above the global diagonal for every column of the chunk), so it has
+// its own leading dimension.  Sum over chunks = (1/2 + STORE_G / (2 nt)) of the full mt x nt rectangle: C4 on one
+// GPU 71 GB instead of 137 GB.  A product that spans several chunks is issued chunk by chunk.
+constexpr int STORE_G = 8;
+struct Store {
+  int T = 0, G = STORE_G;
+  int64_t mt = 0, nt = 0;
+  std::vector<int64_t> r0, off, ld;  // per chunk: first stored local tile row, offset in doubles, leading dimension
+  int64_t doubles = 0;
+  void plan(int64_t mt_, int64_t nt_, int T_, int Pr, int Pc, int pr, int pc) {
+    T = T_;  mt = mt_;  nt = nt_;
+    r0.clear();  off.clear();  ld.clear();
+    doubles = 0;
+    for (int64_t c0 = 0; c0 < nt; c0 += G) {
+      const int64_t J = c0 * Pc + pc;                                   // first global tile column of the chunk
+      int64_t first = J <= pr ? 0 : (J - pr + Pr - 1) / Pr;            // first local row li with li*Pr + pr >= J
+      if (first > mt) first = mt;
+      const int64_t cols = std::min<int64_t>(G, nt - c0);
+      r0.push_back(first);
+      off.push_back(doubles);
+      ld.push_back((mt - first) * T);
+      doubles += (mt - first) * T * cols * T;
+    }
+  }
+  int chunk_of(int64_t lj) const { return (int)(lj / G); }
+  int64_t ld_of(int64_t lj) const { return ld[chunk_of(lj)]; }
+  // element (0, 0) of local tile (li, lj); li must not lie above the chunk's first stored row
+  double *tile(double *base, int64_t li, int64_t lj) const {
+    const int c = chunk_of(lj);
+    return base + off[c] + (li - r0[c]) * T + (lj - (int64_t)c * G) * T * ld[c];
+  }
+};
+
 // One grid rank's buffers.
 struct RankBuf {
   int pr = 0, pc = 0;
-  int64_t mt = 0, nt = 0, ld = 0;
+  int64_t mt = 0, nt = 0;
+  Store st;
   double *A = nullptr;
   double *Pfull[2] = {nullptr, nullptr};
   double *Pcol[2] = {nullptr, nullptr};
@@ -382,7 +418,9 @@ int32_t dgp_dist_plan(int64_t n, int32_t tile, int32_t grid_rows, int32_t grid_c
   out[1] = g.local_rows(pr);
   out[2] = g.local_cols(pc);
   out[3] = owned;
-  out[4] = g.local_rows(pr) * tile * g.local_cols(pc) * tile * (int64_t)sizeof(double);
+  Store st;
+  st.plan(g.local_rows(pr), g.local_cols(pc), tile, grid_rows, grid_cols, pr, pc);
+  out[4] = st.doubles * (int64_t)sizeof(double);
   return DGP_OK;
 }
 
@@ -440,13 +478,13 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *
     R.pc = id % ds->Pc;
     R.mt = g.local_rows(R.pr);
     R.nt = g.local_cols(R.pc);
-    R.ld = R.mt * T;
+    R.st.plan(R.mt, R.nt, T, ds->Pr, ds->Pc, R.pr, R.pc);
     char name[64];
     auto get = [&](const char *base, size_t doubles) -> double * {
       snprintf(name, sizeof name, "dist_%s_%d", base, q);
       return (double *)ctx->buf(name, (doubles ? doubles : 1) * sizeof(double));
     };
-    R.A = get("A", (size_t)R.ld * R.nt * T);
+    R.A = get("A", (size_t)R.st.doubles);
     for (int b = 0; b < 2; ++b) {
       snprintf(name, sizeof name, "pf%d", b);
       R.Pfull[b] = get(name, panel_doubles);
@@ -470,30 +508,62 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *
     DGP_CUDA_OK(ctx, cudaMemsetAsync(R.z, 0, (size_t)Ntot * sizeof(double), S));
     DGP_CUDA_OK(ctx, cudaMemsetAsync(R.scal, 0, 8 * sizeof(double), S));
     if (R.mt == 0 || R.nt == 0) continue;
-    AssembleArgs a;
-    a.X1 = Xk;  a.X2 = Xk;  a.dp = D->dp;
-    a.rows = D->N;  a.cols = D->N;
-    a.rows_p = R.mt * T;  a.cols_p = R.nt * T;
-    a.out = R.A;  a.ld = R.ld;
-    a.symmetric = 1;
-    a.bc_T = T;  a.bc_Pr = ds->Pr;  a.bc_Pc = ds->Pc;  a.bc_pr = R.pr;  a.bc_pc = R.pc;
-    a.use_gram = pick_gram_pub(ctx, sp, cp, D->dp, D->d, D->max_sq_norm);
-    a.nodup = points_stay_distinct_pub(D->has_dup, sp, D->d);
-    DGP_TRY(assemble(ctx, S, cp, a));
+    for (size_t c = 0; c < R.st.r0.size(); ++c) {
+      const int64_t c0 = (int64_t)c * R.st.G, cols = std::min<int64_t>(R.st.G, R.nt - c0), rows = R.mt - R.st.r0[c];
+      if (rows <= 0) continue;
+      AssembleArgs a;
+      a.X1 = Xk;  a.X2 = Xk;  a.dp = D->dp;
+      a.rows = D->N;  a.cols = D->N;
+      a.rows_p = rows * T;  a.cols_p = cols * T;
+      a.out = R.A + R.st.off[c];  a.ld = R.st.ld[c];
+      a.symmetric = 1;
+      a.bc_T = T;  a.bc_Pr = ds->Pr;  a.bc_Pc = ds->Pc;  a.bc_pr = R.pr;  a.bc_pc = R.pc;
+      a.bc_row0 = (int)R.st.r0[c];  a.bc_col0 = (int)c0;
+      a.use_gram = pick_gram_pub(ctx, sp, cp, D->dp, D->d, D->max_sq_norm);
+      a.nodup = points_stay_distinct_pub(D->has_dup, sp, D->d);
+      DGP_TRY(assemble(ctx, S, cp, a));
+    }
   }
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  // The trailing update of step k on rank R, as the list of GEMMs it takes: the part in the next tile column first
+  // (look-ahead), then the rest, cut at the chunk boundaries of the storage.  Used to build the tile tables ahead of
+  // the timed pipeline and to issue the products.
+  struct Piece {
+    int64_t li, lj, rows, cols;  // local tile origin and extent
+    bool next_col;               // the look-ahead part
+  };
+  auto trailing_pieces = [&](int64_t k, const RankBuf &R, std::vector<Piece> &out) {
+    out.clear();
+    const int64_t nrow = g.count_row(k, R.pr), ncol = g.count_col(k, R.pc);
+    if (nrow == 0 || ncol == 0) return;
+    const int64_t li0 = g.first_row(k, R.pr) / ds->Pr, lj0 = g.first_col(k, R.pc) / ds->Pc;
+    const bool owns_next = la && g.first_col(k, R.pc) == k + 1;
+    int64_t lj = lj0;
+    const int64_t lje = lj0 + ncol;
+    auto push = [&](int64_t a, int64_t b, bool nx) {
+      const int c = R.st.chunk_of(a);
+      const int64_t lis = std::max(li0, R.st.r0[c]);
+      if (lis < li0 + nrow && b > a) out.push_back({lis, a, li0 + nrow - lis, b - a, nx});
+    };
+    if (owns_next) {
+      push(lj, lj + 1, true);
+      ++lj;
+    }
+    while (lj < lje) {
+      const int64_t cend = std::min<int64_t>(lje, ((int64_t)R.st.chunk_of(lj) + 1) * R.st.G);
+      push(lj, cend, false);
+      lj = cend;
+    }
+  };
+  std::vector<Piece> pieces;
   // tile tables of every product of the loop, built before the timed pipeline starts (get_tiles allocates and
   // copies synchronously on first use of a shape; there are O(Nt) distinct trailing shapes)
   for (int64_t k = 0; k + 1 < g.Nt; ++k)
     for (RankBuf &R : ranks) {
-      const int64_t nrow = g.count_row(k, R.pr), ncol = g.count_col(k, R.pc);
+      const int64_t nrow = g.count_row(k, R.pr);
       if (R.pc == (int)(k % ds->Pc)) DGP_TRY(gemm_prepare(ctx, (int)(nrow * T), T, 0, 0));
-      if (nrow == 0 || ncol == 0) continue;
-      if (la && g.first_col(k, R.pc) == k + 1) {
-        DGP_TRY(gemm_prepare(ctx, (int)(nrow * T), T, 0, 0));
-        DGP_TRY(gemm_prepare(ctx, (int)(nrow * T), (int)((ncol - 1) * T), 0, 0));
-      } else {
-        DGP_TRY(gemm_prepare(ctx, (int)(nrow * T), (int)(ncol * T), 0, 0));
-      }
+      trailing_pieces(k, R, pieces);
+      for (const Piece &pz : pieces) DGP_TRY(gemm_prepare(ctx, (int)(pz.rows * T), (int)(pz.cols * T), 0, 0));
     }
   DGP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_a, S));
   size_t ev = 0;
@@ -558,11 +628,12 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *
     for (int q = 0; q < nranks; ++q) {
       RankBuf &R = ranks[q];
       if (R.pr != okr || R.pc != okc) continue;
-      double *Akk = R.A + (k / ds->Pr) * T + (k / ds->Pc) * T * R.ld;
+      double *Akk = R.st.tile(R.A, k / ds->Pr, k / ds->Pc);
+      const int64_t ldk = R.st.ld_of(k / ds->Pc);
       DGP_CUDA_OK(ctx, cudaMemsetAsync(R.info, 0, sizeof(int), P));
-      DGP_TRY(potrf_blocked_on(ctx, P, P, Akk, R.ld, T, inv, R.info, "dist_potrf_panel"));
+      DGP_TRY(potrf_blocked_on(ctx, P, P, Akk, ldk, T, inv, R.info, "dist_potrf_panel"));
       DGP_CUDA_OK(ctx, cudaMemsetAsync(R.Winv[b], 0, ((size_t)T * T + 8) * sizeof(double), P));
-      DGP_TRY(trtri_lower_on(ctx, P, Akk, R.ld, inv, T, R.Winv[b], T, tt, T));
+      DGP_TRY(trtri_lower_on(ctx, P, Akk, ldk, inv, T, R.Winv[b], T, tt, T));
       set_status_kernel<<<1, 1, 0, P>>>(R.Winv[b] + (size_t)T * T, R.info);
       ctx->launches++;
     }
@@ -581,7 +652,7 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *
       if (R.pc != okc || cm.count[R.pr] == 0) continue;
       const int64_t li0 = cm.first[R.pr] / ds->Pr;
       GemmArgs pg;
-      pg.A = R.A + li0 * T + (k / ds->Pc) * T * R.ld;  pg.lda = R.ld;  pg.a_kmajor = 0;
+      pg.A = R.st.tile(R.A, li0, k / ds->Pc);  pg.lda = R.st.ld_of(k / ds->Pc);  pg.a_kmajor = 0;
       pg.B = R.Winv[b];  pg.ldb = T;  pg.b_kmajor = 0;  // op(B)(k,n) = W(n,k)
       pg.C = R.Pfull[b] + cm.offset[R.pr];  pg.ldc = cm.count[R.pr] * T;
       pg.M = (int)(cm.count[R.pr] * T);  pg.N = T;  pg.K = T;
@@ -610,39 +681,28 @@ int32_t dgp_dist_energy(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec *
       DGP_CUDA_OK(ctx, cudaEventRecord(ev_panel, P));
       DGP_CUDA_OK(ctx, cudaStreamWaitEvent(S, ev_panel, 0));
     }
-    // 7. trailing update of the local tiles: first the next tile column, then the rest
+    // 7. trailing update of the local tiles: first the next tile column, then the rest chunk by chunk
     for (RankBuf &R : ranks) {
       const int64_t nrow = cm.count[R.pr], ncol = g.count_col(k, R.pc);
       if (nrow == 0 || ncol == 0) continue;
       const int64_t li0 = cm.first[R.pr] / ds->Pr, lj0 = g.first_col(k, R.pc) / ds->Pc;
-      GemmArgs u;
-      u.A = R.Pfull[b] + cm.offset[R.pr];  u.lda = nrow * T;  u.a_kmajor = 0;
-      u.B = R.Pcol[b];  u.ldb = ncol * T;  u.b_kmajor = 0;
-      u.C = R.A + li0 * T + lj0 * T * R.ld;  u.ldc = R.ld;
-      u.M = (int)(nrow * T);  u.K = T;
-      u.alpha = -1.0;  u.beta = 1.0;
-      u.bc_T = T;  u.bc_Pr = ds->Pr;  u.bc_Pc = ds->Pc;  u.bc_pr = R.pr;  u.bc_pc = R.pc;
-      u.bc_row0 = (int)li0;  u.bc_col0 = (int)lj0;
-      const bool owns_next = g.first_col(k, R.pc) == k + 1;
-      if (la && owns_next) {
-        GemmArgs a1 = u;
-        a1.N = T;
-        DGP_TRY(gemm(ctx, S, a1));
-        DGP_CUDA_OK(ctx, cudaEventRecord(ev_col, S));
-        col_recorded = true;
-        if (ncol > 1) {
-          GemmArgs a2 = u;
-          a2.B = u.B + T;
-          a2.C = u.C + (int64_t)T * R.ld;
-          a2.N = (int)((ncol - 1) * T);
-          a2.bc_col0 = (int)lj0 + 1;
-          DGP_TRY(gemm(ctx, S, a2));
-        }
-      } else {
-        // ranks outside the next process column never touch tile column k+1: their panel stream
-        // has nothing to wait for and joins the next broadcasts right away
-        u.N = (int)(ncol * T);
+      trailing_pieces(k, R, pieces);
+      for (const Piece &pz : pieces) {
+        GemmArgs u;
+        u.A = R.Pfull[b] + cm.offset[R.pr] + (pz.li - li0) * T;  u.lda = nrow * T;  u.a_kmajor = 0;
+        u.B = R.Pcol[b] + (pz.lj - lj0) * T;  u.ldb = ncol * T;  u.b_kmajor = 0;
+        u.C = R.st.tile(R.A, pz.li, pz.lj);  u.ldc = R.st.ld_of(pz.lj);
+        u.M = (int)(pz.rows * T);  u.N = (int)(pz.cols * T);  u.K = T;
+        u.alpha = -1.0;  u.beta = 1.0;
+        u.bc_T = T;  u.bc_Pr = ds->Pr;  u.bc_Pc = ds->Pc;  u.bc_pr = R.pr;  u.bc_pc = R.pc;
+        u.bc_row0 = (int)pz.li;  u.bc_col0 = (int)pz.lj;
         DGP_TRY(gemm(ctx, S, u));
+        if (pz.next_col) {
+          // ranks outside the next process column never touch tile column k+1: their panel stream has nothing to
+          // wait for and joins the next broadcasts right away
+          DGP_CUDA_OK(ctx, cudaEventRecord(ev_col, S));
+          col_recorded = true;
+        }
       }
     }
     if (la) {

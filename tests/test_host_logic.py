@@ -353,7 +353,17 @@ def test_block_cyclic_plan_partitions_the_lower_triangle(n, tile, pr, pc):
     assert sum(owned) == nt * (nt + 1) // 2
     for r, p in enumerate(plans):
         assert p["local_rows"] == len(range(r // pc, nt, pr)) and p["local_cols"] == len(range(r % pc, nt, pc))
-        assert p["local_bytes"] == p["local_rows"] * p["local_cols"] * tile * tile * 8
+        # packed lower storage (dist.cu, Store): chunks of 8 local tile columns, each from the first local row its first
+        # column needs; about half of the local rectangle on a large grid, never more than all of it
+        mt, ntc, prow, pcol = p["local_rows"], p["local_cols"], r // pc, r % pc
+        want = 0
+        for c0 in range(0, ntc, 8):
+            J = c0 * pc + pcol
+            first = 0 if J <= prow else min(mt, -(-(J - prow) // pr))
+            want += (mt - first) * min(8, ntc - c0)
+        assert p["local_bytes"] == want * tile * tile * 8 <= mt * ntc * tile * tile * 8
+        if nt >= 64:
+            assert p["local_bytes"] <= 0.57 * mt * ntc * tile * tile * 8
 
 
 def test_gaussian_scaling_and_regression_metrics():
