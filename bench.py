@@ -406,6 +406,9 @@ def run_c5(ctx, D: Dist, rank: int, args) -> dict:
 
 def main():
     args = parse()
+    # NCCL prints "NCCL version ..." on stdout at the first communicator unless told otherwise; stdout carries the one
+    # JSON line (an explicit NCCL_DEBUG from the caller is respected)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     if args.impl == "reference":
         run_reference(args)
         return
