@@ -558,8 +558,10 @@ cudaEvent_t get_event(Ctx *ctx, size_t i) {
 // issued a rank-128 update per sub-panel; profiles/launches_c3_step_r1.txt showed those K = 128
 // launches at half the efficiency of the K >= 256 ones).  Enqueued on `st`.
 int32_t factor_block_column(Ctx *ctx, cudaStream_t st, double *A, int64_t lda, int64_t n, int64_t c0, int64_t w,
-                            double *inv, int *info, double *scratch) {
+                            double *inv, int *info, double *scratch, cudaEvent_t rest_updated = nullptr) {
   for (int64_t cs = c0; cs < c0 + w; cs += LB) {
+    if (cs == c0 + LB && rest_updated)   // columns beyond the first 128 received the previous block column's update later
+      DGP_CUDA_OK(ctx, cudaStreamWaitEvent(st, rest_updated, 0));
     if (cs > c0) {
       GemmArgs u;  // A[cs:, cs:cs+128] -= A[cs:, c0:cs] * A[cs:cs+128, c0:cs]^T
       u.A = A + cs + c0 * lda;  u.lda = lda;  u.a_kmajor = 0;
@@ -636,9 +638,11 @@ int32_t potrf_blocked_on(Ctx *ctx, cudaStream_t S, cudaStream_t P, double *A, in
     DGP_CUDA_OK(ctx, cudaStreamWaitEvent(P, e, 0));
   }
 
+  cudaEvent_t rest_ev = nullptr;  // set when the block column about to be factored was updated in two parts
   for (int64_t c0 = 0; c0 < n; c0 += nb) {
     const int64_t w = (n - c0 < nb) ? (n - c0) : nb;
-    DGP_TRY(factor_block_column(ctx, P, A, lda, n, c0, w, inv, info, scratch));
+    DGP_TRY(factor_block_column(ctx, P, A, lda, n, c0, w, inv, info, scratch, rest_ev));
+    rest_ev = nullptr;
     const int64_t c1 = c0 + w;
     if (c1 >= n) break;
     if (la) {
@@ -647,18 +651,32 @@ int32_t potrf_blocked_on(Ctx *ctx, cudaStream_t S, cudaStream_t P, double *A, in
       DGP_CUDA_OK(ctx, cudaStreamWaitEvent(S, e, 0));
     }
     const int64_t w1 = (n - c1 < nb) ? (n - c1) : nb;
-    // (a) trailing update restricted to the next block column
+    // (a) trailing update restricted to the next block column.  With look-ahead only its first 128 columns are on
+    //     the critical chain (the next leaf and its panel need nothing else), so they go first and the panel stream
+    //     resumes as soon as they are done; the rest of the block column follows and is awaited before its own
+    //     128-wide sub-panels are touched.
+    const int64_t wa = (la && w1 > LB) ? LB : w1;
     GemmArgs a;
     a.A = A + c1 + c0 * lda;  a.lda = lda;  a.a_kmajor = 0;
     a.B = A + c1 + c0 * lda;  a.ldb = lda;  a.b_kmajor = 0;
     a.C = A + c1 + c1 * lda;  a.ldc = lda;
-    a.M = (int)(n - c1);  a.N = (int)w1;  a.K = (int)w;
+    a.M = (int)(n - c1);  a.N = (int)wa;  a.K = (int)w;
     a.alpha = -1.0;  a.beta = 1.0;
     DGP_TRY(gemm(ctx, S, a));
     if (la) {
       cudaEvent_t e = get_event(ctx, ev++);
       DGP_CUDA_OK(ctx, cudaEventRecord(e, S));
       DGP_CUDA_OK(ctx, cudaStreamWaitEvent(P, e, 0));
+    }
+    if (wa < w1) {
+      GemmArgs a2 = a;   // rows from c1 + 128: the tiles above belong to the strictly upper part of the block column
+      a2.A = A + (c1 + wa) + c0 * lda;
+      a2.B = A + (c1 + wa) + c0 * lda;
+      a2.C = A + (c1 + wa) + (c1 + wa) * lda;
+      a2.M = (int)(n - c1 - wa);  a2.N = (int)(w1 - wa);
+      DGP_TRY(gemm(ctx, S, a2));
+      rest_ev = get_event(ctx, ev++);
+      DGP_CUDA_OK(ctx, cudaEventRecord(rest_ev, S));
     }
     // (b) the rest of the trailing matrix (lower tiles), overlapped with the next panel
     const int64_t c2 = c1 + w1;
