@@ -73,6 +73,7 @@ def parse():
     ap.add_argument("--c4-tile", type=int, default=512)
     ap.add_argument("--c5-n", type=int, default=16384, help="size of the GridSearch leg (0 = skip)")
     ap.add_argument("--c5-grid", type=int, default=16, help="grid points per hyper-parameter (16 x 16 = 256 candidates)")
+    ap.add_argument("--predict-m", type=int, default=4096, help="test points of the prediction leg (0 = skip)")
     return ap.parse_args()
 
 
@@ -566,6 +567,36 @@ def main():
                     "inverse_tflops": inv_tf, "inverse_frac": inv_tf / dmma if inv_tf else None,
                     "assemble_gbs": asm_gbs, "assemble_frac_of_hbm_write": asm_gbs / peaks["hbm_write_gbs"]}
         line["roofline"] = roofline
+        # ---- the prediction half of config C3: fit, then mean + covariance + error bars of 4096 test points --------
+        if args.predict_m > 0:
+            try:
+                rngp = np.random.default_rng(7)
+                Xs = rngp.standard_normal((args.predict_m, d))
+                rec = {}
+                for _ in range(2):   # first pass warms the workspaces
+                    model = ctx.fit(data, spec)
+                    fit_ph = ctx.timings()
+                    t0 = time.perf_counter()
+                    mu, cov, lo, hi = ctx.predict(model, Xs, want_cov=True, want_bars=True, sigma=2.0)
+                    pred_wall = time.perf_counter() - t0
+                    ph = ctx.timings()
+                    ctx.model_destroy(model)
+                m_ = args.predict_m
+                dg_ = np.diag(cov)
+                rec = {"m": m_, "fit_device_ms": fit_ph["total"], "predict_device_ms": ph["total"],
+                       "predict_wall_ms_with_d2h": pred_wall * 1e3,
+                       "cross_assemble_ms": ph["cross_assemble"], "trsm_ms": ph["trsm"], "syrk_ms": ph["syrk"],
+                       "trsm_tflops": n * n * m_ / ph["trsm"] / 1e9, "trsm_frac": n * n * m_ / ph["trsm"] / 1e9 / dmma,
+                       "syrk_tflops": m_ * m_ * n / ph["syrk"] / 1e9, "syrk_frac": m_ * m_ * n / ph["syrk"] / 1e9 / dmma,
+                       "d2h_bytes": int(8 * (m_ * m_ + 3 * m_)),
+                       "checks": {"finite": bool(np.isfinite(mu).all() and np.isfinite(cov).all() and np.isfinite(lo).all()),
+                                  "variances_positive": bool((dg_ > 0).all()),
+                                  "covariance_symmetric": bool(np.array_equal(cov, cov.T)),
+                                  "bars_bracket_mean": bool((lo <= mu).all() and (mu <= hi).all()),
+                                  "bars_are_2_sigma": bool(np.allclose(hi - mu, 2.0 * np.sqrt(dg_), rtol=1e-12, atol=0))}}
+                roofline["predict"] = rec
+            except Exception as ex:
+                roofline["predict"] = {"error": f"{type(ex).__name__}: {ex}"}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_record([cpu_sample(args.workload, args.cpu_sample_n, args.cpu_sample_n3)])
         elif not args.no_cpu_baseline:

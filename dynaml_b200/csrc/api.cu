@@ -577,6 +577,9 @@ int32_t enqueue_eval(Ctx *ctx, int slot, const Data *D, const Spec &sp, bool wan
     g.X = Xbase;  g.Xs = Xk;  g.alpha = x;  g.Kinv = Kinv;  g.ld = np;
     g.n = D->N;  g.np = np;  g.dp = D->dp;
     g.partials = partials;  g.sums = d_scal + 2;
+    // same conditions as the lean assembly of the strictly-lower tiles: Gram accuracy gate, pairwise distinct points
+    g.lean = ctx->grad_lean && ctx->assembly != 3 && pick_gram(ctx, sp, cp, D->dp, D->d, D->max_sq_norm) &&
+             points_stay_distinct(D->has_dup, sp, D->d);
     {
       NvtxRange r("dgp:grad_trace");
       DGP_TRY(grad_trace(ctx, S, cp, g, ns_out));
@@ -796,6 +799,9 @@ int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
     if (value < 0 || value > 3)
       return ctx->fail(DGP_ERR_ARG, "assembly must be 0 (auto), 1 (exact differences), 2 (Gram) or 3 (checked Gram)");
     ctx->assembly = (int)value;
+  } else if (!strcmp(key, "grad_lean")) {
+    if (value < 0 || value > 1) return ctx->fail(DGP_ERR_ARG, "grad_lean must be 0 (exact differences) or 1 (lean Gram pass)");
+    ctx->grad_lean = (int)value;
   } else if (!strcmp(key, "assembly_store")) {
     if (value < 0 || value > 1) return ctx->fail(DGP_ERR_ARG, "assembly_store must be 0 (direct) or 1 (bulk)");
     ctx->assembly_store = (int)value;

@@ -55,6 +55,7 @@ struct Ctx {
   int gemm_no_prefetch = 0;  // testing only: GEMMs skip the L2 prefetch of their C tile
   int gemm_bk = 32;   // K-slice of the GEMM pipeline: 16 (3-4 stages) or 32 (double buffered)
   int assembly = 0;   // 0: Gram/DMMA assembly when its error bound allows, 1: always exact differences, 2: force Gram
+  int grad_lean = 1;       // gradient trace pass: 1 = lean Gram epilogue where the lean assembly's conditions hold, 0 = exact differences
   int assembly_store = 0;  // lean SE assembly: 0 = 16-byte st.global from registers, 1 = staged chunk + bulk (TMA) stores
   int batch_streams = 3;  // dgp_energy_batch evaluates this many candidates concurrently (1..4)
   cudaStream_t slot_S[4] = {nullptr, nullptr, nullptr, nullptr};  // extra (main, panel) stream pairs, created lazily

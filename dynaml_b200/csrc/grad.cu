@@ -10,6 +10,7 @@
 // The kernel accumulates kind-specific "moments" S_q = sum_ij M_ij * f_q(x_i, x_j); grad_finish()
 // maps them to the reference's per-hyper-parameter derivatives on the host.
 #include "grad.cuh"
+#include "lean.cuh"
 
 namespace dgp {
 
@@ -115,10 +116,19 @@ __global__ void __launch_bounds__(GTHREADS) grad_trace_kernel(CovParams cp, Grad
   const int tid = threadIdx.x;
   const int tx = tid & 63, ty = tid >> 6;
   int64_t tlin = blockIdx.x;
-  int ti = (int)((sqrt(8.0 * (double)tlin + 1.0) - 1.0) * 0.5);
-  while ((int64_t)ti * (ti + 1) / 2 > tlin) --ti;
-  while ((int64_t)(ti + 1) * (ti + 2) / 2 <= tlin) ++ti;
-  const int tj = (int)(tlin - (int64_t)ti * (ti + 1) / 2);
+  int ti, tj;
+  if (a.edge_only) {
+    // the tiles the lean pass leaves out: the mt diagonal tiles, then the rest of the last tile row (padding)
+    const int mt = (int)(a.np / GT);
+    ti = tlin < mt ? (int)tlin : mt - 1;
+    tj = tlin < mt ? (int)tlin : (int)(tlin - mt);
+    tlin = (int64_t)ti * (ti + 1) / 2 + tj;
+  } else {
+    ti = (int)((sqrt(8.0 * (double)tlin + 1.0) - 1.0) * 0.5);
+    while ((int64_t)ti * (ti + 1) / 2 > tlin) --ti;
+    while ((int64_t)(ti + 1) * (ti + 2) / 2 <= tlin) ++ti;
+    tj = (int)(tlin - (int64_t)ti * (ti + 1) / 2);
+  }
   const int64_t m0 = (int64_t)ti * GT, n0 = (int64_t)tj * GT;
 
   {
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(GTHREADS) grad_trace_kernel(CovParams cp, Grad
   if (tid < NS) {
     double v = 0.0;
     for (int wdx = 0; wdx < GTHREADS / 32; ++wdx) v += red[wdx * NS + tid];
-    a.partials[(int64_t)blockIdx.x * NS + tid] = v;
+    a.partials[tlin * NS + tid] = v;
   }
 }
 
@@ -228,6 +238,255 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *par
     __syncthreads();
   }
   if (threadIdx.x == 0) sums[q] = sh[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Lean trace pass: the strictly-lower tiles of a training set whose points are pairwise distinct (no pair at
+// distance zero, so no noise moment there) under the accuracy gate of the Gram assembly (gram_is_accurate).  Same
+// structure as assemble_gram_lean_kernel: the scaled squared distance of 32 x 16 pairs per warp and pass comes out of
+// m8n8k4 DMMAs (|x|^2 + |y|^2 - 2 x.y), exp / sqrt are the short table / rsqrt-seed sequences of lean.cuh, and the
+// entry of K^-1 arrives as a 16-byte load issued before the DMMAs.  Every pair of these tiles has weight 2
+// (symmetry), applied once to the tile's partial sums.  Two CTAs per SM: the 16 prefetched K^-1 entries and the 16
+// accumulators per thread do not fit the 80 registers of three (measured on B200, profiles/trace_lean_ab_r2.txt:
+// 2.27 ms with the spills against 1.83 ms, Matern-5/2 d = 16 N = 32768; the exact-difference pass takes 6.01 ms).
+//   SE       S0 += m e acc (acc = c1 r^2; the tile sum is divided by c1), S1 += m e
+//   ARD-SE   S0 += m e, S1 += m e |x - y|^2 of the unscaled points (reference mode, D2): a second Gram product
+//   Matern   dk/dl = exp(-rho) rho Q(rho), rho = sqrt(2 nu) r / l: the reference's diffLead * sumTerm + diffSum *
+//            leadingTerm (GenericMaternKernel.scala:70-97) collected by powers of rho on the host; its constant term
+//            is identically zero, Q has degree p
+// The diagonal tiles and the tiles touching the padding go through grad_trace_kernel (edge_only).
+struct LeanTraceCov {
+  double scale;            // operands are multiplied by this when staged
+  double q0, q1, q2, q3;   // Matern: Q(rho), right-aligned (q3 is the constant term)
+  double s0_scale;         // SE: 1 / c1
+};
+
+template <int MODE, int DP, bool P3>
+__global__ void __launch_bounds__(GTHREADS, 2)
+    grad_trace_lean_kernel(LeanTraceCov f, LeanConst lc, ExpTab T, GradArgs a) {
+  constexpr int NS = NSums<MODE, DP>::value;
+  constexpr bool ARD = (MODE == M_ARD_REF);
+  constexpr int LDK = lean_ldk<DP>();
+  extern __shared__ __align__(16) double sm_raw[];
+  double *tab = sm_raw;                    // 64 entries x 16 copies
+  double *Brow = tab + 64 * 16;            // row points i (MMA N): [i][k] = scale * x
+  double *Acol = Brow + GT * LDK;          // column points j (MMA M): [j][k] = -2 scale * y
+  double *nx = Acol + GT * LDK;            // scale^2 |x_i|^2
+  double *ny = nx + GT;
+  double *sal = ny + GT;                   // alpha of the rows, then of the columns
+  double *red = sal + 2 * GT;              // 8 x NS
+  double *Brow2 = red + 8 * NS;            // ARD: the unscaled points, same layout (8 * NS is even: 16-byte aligned)
+  double *Acol2 = Brow2 + GT * LDK;
+  double *nx2 = Acol2 + GT * LDK;
+  double *ny2 = nx2 + GT;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;
+
+  // strictly-lower tile (ti, tj), tj < ti: the triangular numbering of (ti - 1, tj)
+  const int64_t tl = blockIdx.x;
+  int tr = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
+  while ((int64_t)tr * (tr + 1) / 2 > tl) --tr;
+  while ((int64_t)(tr + 1) * (tr + 2) / 2 <= tl) ++tr;
+  const int tj = (int)(tl - (int64_t)tr * (tr + 1) / 2), ti = tr + 1;
+  const int64_t m0 = (int64_t)ti * GT, n0 = (int64_t)tj * GT;
+  if (m0 + GT > a.n) return;   // touches the padding: edge pass
+  const int64_t tlin = (int64_t)ti * (ti + 1) / 2 + tj;
+
+  {
+    const bool is_row = tid < GT;
+    const int pidx = is_row ? tid : tid - GT;
+    const int64_t pt = (is_row ? m0 : n0) + pidx;
+    const double *src = (ARD ? a.Xs : a.X) + pt * DP;
+    double *dst = (is_row ? Brow : Acol) + pidx * LDK;
+    const double sc = is_row ? 1.0 : -2.0;
+    double v[DP];
+#pragma unroll
+    for (int c = 0; c < DP / 2; ++c) {
+      const double2 q = reinterpret_cast<const double2 *>(src)[c];
+      v[2 * c] = q.x;
+      v[2 * c + 1] = q.y;
+    }
+    double nrm = 0.0;
+#pragma unroll
+    for (int c = 0; c < DP; ++c) {
+      v[c] *= f.scale;
+      nrm = fma(v[c], v[c], nrm);
+    }
+#pragma unroll
+    for (int c = 0; c < DP / 2; ++c)
+      reinterpret_cast<double2 *>(dst)[c] = make_double2(sc * v[2 * c], sc * v[2 * c + 1]);
+    (is_row ? nx : ny)[pidx] = nrm;
+    if (ARD) {
+      const double *src2 = a.X + pt * DP;
+      double *dst2 = (is_row ? Brow2 : Acol2) + pidx * LDK;
+#pragma unroll
+      for (int c = 0; c < DP / 2; ++c) {
+        const double2 q = reinterpret_cast<const double2 *>(src2)[c];
+        v[2 * c] = q.x;
+        v[2 * c + 1] = q.y;
+      }
+      nrm = 0.0;
+#pragma unroll
+      for (int c = 0; c < DP; ++c) nrm = fma(v[c], v[c], nrm);
+#pragma unroll
+      for (int c = 0; c < DP / 2; ++c)
+        reinterpret_cast<double2 *>(dst2)[c] = make_double2(sc * v[2 * c], sc * v[2 * c + 1]);
+      (is_row ? nx2 : ny2)[pidx] = nrm;
+    }
+    sal[tid] = a.alpha[pt];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) tab[tid * 4 + e] = T.v[(tid * 4 + e) >> 4];
+  }
+  __syncthreads();
+
+  const int ibase = wn * 32;
+  const double *bp = Brow + (ibase + g) * LDK + t;
+  const double *bp2 = Brow2 + (ibase + g) * LDK + t;
+  const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab) + ((unsigned)(lane & 15) << 3);
+  // this thread's rows: ibase + nb * 8 + 2 t (+1), nb = 0..3
+  double ali[4][2];
+#pragma unroll
+  for (int nb = 0; nb < 4; ++nb) {
+    const double2 q = *reinterpret_cast<const double2 *>(sal + ibase + nb * 8 + 2 * t);
+    ali[nb][0] = q.x;
+    ali[nb][1] = q.y;
+  }
+  const double *kin = a.Kinv + (m0 + ibase + 2 * t) + (n0 + g) * a.ld;
+
+  double s[NS];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) s[q] = 0.0;
+
+#pragma unroll 1
+  for (int chunk = 0; chunk < 4; ++chunk) {
+    const int jbase = chunk * 32 + wm * 16;
+    double2 kv[2][4];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb)
+        kv[mb][nb] = *reinterpret_cast<const double2 *>(kin + (int64_t)(jbase + mb * 8) * a.ld + nb * 8);
+    const double *ap = Acol + (jbase + g) * LDK + t;
+    const double *ap2 = Acol2 + (jbase + g) * LDK + t;
+    double acc[2][4][2];
+    double ac2[ARD ? 2 : 1][4][2];
+    {
+      const double y0 = ny[jbase + g], y1 = ny[jbase + 8 + g];
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) {
+        const double2 xn = *reinterpret_cast<const double2 *>(nx + ibase + nb * 8 + 2 * t);
+        acc[0][nb][0] = y0 + xn.x;  acc[0][nb][1] = y0 + xn.y;
+        acc[1][nb][0] = y1 + xn.x;  acc[1][nb][1] = y1 + xn.y;
+      }
+      if (ARD) {
+        const double z0 = ny2[jbase + g], z1 = ny2[jbase + 8 + g];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+          const double2 xn = *reinterpret_cast<const double2 *>(nx2 + ibase + nb * 8 + 2 * t);
+          ac2[0][nb][0] = z0 + xn.x;  ac2[0][nb][1] = z0 + xn.y;
+          ac2[ARD ? 1 : 0][nb][0] = z1 + xn.x;  ac2[ARD ? 1 : 0][nb][1] = z1 + xn.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < DP / 4; ++kk) {
+      double af[2], bf[4];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) af[mb] = ap[mb * 8 * LDK + kk * 4];
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) bf[nb] = bp[nb * 8 * LDK + kk * 4];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                       : "+d"(acc[mb][nb][0]), "+d"(acc[mb][nb][1])
+                       : "d"(af[mb]), "d"(bf[nb]));
+      if (ARD) {
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) af[mb] = ap2[mb * 8 * LDK + kk * 4];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) bf[nb] = bp2[nb * 8 * LDK + kk * 4];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+          for (int nb = 0; nb < 4; ++nb)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(ac2[ARD ? mb : 0][nb][0]), "+d"(ac2[ARD ? mb : 0][nb][1])
+                         : "d"(af[mb]), "d"(bf[nb]));
+      }
+    }
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+      const double alj = sal[GT + jbase + mb * 8 + g];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        double x[4], e[4], m[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int nb = 2 * q + (u >> 1);
+          const double kvu = (u & 1) ? kv[mb][nb].y : kv[mb][nb].x;
+          m[u] = fma(ali[nb][u & 1], alj, -kvu);
+        }
+        if (MODE == M_MATERN) {
+          double r[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double av = acc[mb][2 * q + (u >> 1)][u & 1];
+            const double v = __hiloint2double(max(__double2hiint(av), 0x03c00000), __double2loint(av));
+            const double y = rsqrt_seed(v);
+            double gg = v * y;
+            const double hh = 0.5 * y;
+            const double ee = fma(-gg, hh, 0.5);
+            gg = fma(gg, ee, gg);
+            const double dd = fma(-gg, gg, v);
+            r[u] = fma(dd, hh, gg);
+            x[u] = -r[u];
+          }
+          lean_exp_v<4>(x, lc, tab_s, e);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            double p = P3 ? fma(f.q0, r[u], f.q1) : f.q1;
+            p = fma(p, r[u], f.q2);
+            p = fma(p, r[u], f.q3);
+            s[0] = fma(m[u] * e[u], p * r[u], s[0]);
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) x[u] = -acc[mb][2 * q + (u >> 1)][u & 1];
+          lean_exp_v<4>(x, lc, tab_s, e);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double me = m[u] * e[u];
+            if (MODE == M_SE) {
+              s[0] = fma(me, acc[mb][2 * q + (u >> 1)][u & 1], s[0]);
+              s[1] += me;
+            } else {
+              s[0] += me;
+              s[1] = fma(me, ac2[ARD ? mb : 0][2 * q + (u >> 1)][u & 1], s[1]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (MODE == M_SE) s[0] *= f.s0_scale;
+
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    double v = 2.0 * s[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp * NS + q] = v;
+  }
+  __syncthreads();
+  if (tid < NS) {
+    double v = 0.0;
+    for (int wdx = 0; wdx < GTHREADS / 32; ++wdx) v += red[wdx * NS + tid];
+    a.partials[tlin * NS + tid] = v;
+  }
 }
 
 // Any feature count (dp > 32): same tiling, row points re-read from global/L1, column points in
@@ -542,6 +801,76 @@ int32_t launch(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArgs &a
   return DGP_OK;
 }
 
+// Lean pass over the strictly-lower tiles + exact-difference pass over the diagonal / padded tiles + reduction.
+template <int MODE, int DP>
+int32_t launch_lean_trace(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArgs &a, int64_t tiles, int *ns_out) {
+  constexpr int NS = NSums<MODE, DP>::value;
+  constexpr bool ARD = (MODE == M_ARD_REF);
+  const int64_t mt = a.np / GT;
+  LeanTraceCov f;
+  f.scale = (MODE == M_MATERN) ? cp.c1 : sqrt(cp.c1);
+  f.q0 = f.q1 = f.q2 = f.q3 = 0.0;
+  f.s0_scale = (MODE == M_SE) ? 1.0 / cp.c1 : 1.0;
+  if (MODE == M_MATERN) {
+    // with rho = c1 r and u = c2 r = kappa rho:  (c1 r sum(u) - q(u)) / c3 = rho * sum_k A_k rho^k,
+    //   A_k = (coef[p-k] kappa^k - (k+1) coef[p-k-1] kappa^(k+1)) / c3,  k = 0..p  (second term absent for k = p)
+    const double kappa = cp.c2 / cp.c1;
+    double *q[4] = {&f.q0, &f.q1, &f.q2, &f.q3};
+    for (int k = 0; k <= cp.p; ++k) {
+      double v = cp.coef[cp.p - k] * pow(kappa, (double)k);
+      if (k + 1 <= cp.p) v -= (double)(k + 1) * cp.coef[cp.p - k - 1] * pow(kappa, (double)(k + 1));
+      *q[3 - k] = v / cp.c3;
+    }
+  }
+  const ExpTab T = lean_exp_table(1.0);
+  const LeanConst lc = lean_constants();
+  const size_t lsmem = ((size_t)64 * 16 + (ARD ? 2 : 1) * (2 * GT * lean_ldk<DP>() + 2 * GT) + 2 * GT + 8 * NS + 2) * sizeof(double);
+  const size_t esmem = ((size_t)(ARD ? 2 : 1) * GT * DP + GT + (GTHREADS / 32) * NS) * sizeof(double);
+  auto go = [&](auto kern) -> int32_t {
+    if (lsmem > 48 * 1024)
+      DGP_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+    kern<<<(unsigned)(mt * (mt - 1) / 2), GTHREADS, lsmem, st>>>(f, lc, T, a);
+    return DGP_OK;
+  };
+  if (MODE == M_MATERN && cp.p == 3) DGP_TRY(go(grad_trace_lean_kernel<MODE, DP, (MODE == M_MATERN)>));
+  else DGP_TRY(go(grad_trace_lean_kernel<MODE, DP, false>));
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  GradArgs e = a;
+  e.edge_only = 1;
+  if (esmem > 48 * 1024)
+    DGP_CUDA_OK(ctx, cudaFuncSetAttribute(grad_trace_kernel<MODE, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)esmem));
+  const int64_t etiles = mt + ((a.np != a.n) ? mt - 1 : 0);
+  grad_trace_kernel<MODE, DP><<<(unsigned)etiles, GTHREADS, esmem, st>>>(cp, e);
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  reduce_partials_kernel<<<NS, 1024, 0, st>>>(a.partials, tiles, NS, a.sums);
+  ctx->launches += 3;
+  DGP_CUDA_OK(ctx, cudaGetLastError());
+  *ns_out = NS;
+  return DGP_OK;
+}
+
+template <int MODE>
+int32_t launch_lean_dp(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArgs &a, int64_t tiles, int *ns) {
+  switch (a.dp) {
+    case 4: return launch_lean_trace<MODE, 4>(ctx, st, cp, a, tiles, ns);
+    case 8: return launch_lean_trace<MODE, 8>(ctx, st, cp, a, tiles, ns);
+    case 12: return launch_lean_trace<MODE, 12>(ctx, st, cp, a, tiles, ns);
+    case 16: return launch_lean_trace<MODE, 16>(ctx, st, cp, a, tiles, ns);
+    case 20: return launch_lean_trace<MODE, 20>(ctx, st, cp, a, tiles, ns);
+    case 24: return launch_lean_trace<MODE, 24>(ctx, st, cp, a, tiles, ns);
+    case 32: return launch_lean_trace<MODE, 32>(ctx, st, cp, a, tiles, ns);
+    default: return DGP_ERR_SHAPE;   // not reached: lean_trace_ok() checks the feature count
+  }
+}
+
+bool lean_trace_ok(const CovParams &cp, const GradArgs &a, int mode) {
+  if (!a.lean || a.np < 4096 || a.np - a.n >= GT) return false;   // below ~4096 points the third launch costs more than it saves
+  if (a.dp != 4 && a.dp != 8 && a.dp != 12 && a.dp != 16 && a.dp != 20 && a.dp != 24 && a.dp != 32) return false;
+  if (mode == M_MATERN) return cp.p >= 1 && cp.p <= 3 && cp.c1 > 0.0 && std::isfinite(cp.c2 / cp.c1);
+  return (mode == M_SE || mode == M_ARD_REF) && cp.c1 > 0.0 && std::isfinite(1.0 / cp.c1) && std::isfinite(sqrt(cp.c1));
+}
+
 template <int MODE>
 int32_t launch_dp(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArgs &a, int64_t tiles, int *ns) {
   switch (a.dp) {
@@ -696,7 +1025,13 @@ int32_t grad_trace(Ctx *ctx, cudaStream_t st, const CovParams &cp, const GradArg
     *ns = NS;
     return DGP_OK;
   }
-  switch (mode_of(cp)) {
+  const int mode = mode_of(cp);
+  if (lean_trace_ok(cp, a, mode)) {
+    if (mode == M_SE) return launch_lean_dp<M_SE>(ctx, st, cp, a, tiles, ns);
+    if (mode == M_ARD_REF) return launch_lean_dp<M_ARD_REF>(ctx, st, cp, a, tiles, ns);
+    return launch_lean_dp<M_MATERN>(ctx, st, cp, a, tiles, ns);
+  }
+  switch (mode) {
     case M_SE: return launch_dp<M_SE>(ctx, st, cp, a, tiles, ns);
     case M_ARD_REF: return launch_dp<M_ARD_REF>(ctx, st, cp, a, tiles, ns);
     case M_ARD_EXACT: return launch_dp<M_ARD_EXACT>(ctx, st, cp, a, tiles, ns);

@@ -15,6 +15,8 @@ struct GradArgs {
   int dp = 0;
   double *partials = nullptr;     // tiles x ns scratch
   double *sums = nullptr;         // ns moments (device)
+  int lean = 0;                   // caller: Gram accuracy gate holds and the points are pairwise distinct
+  int edge_only = 0;              // internal: grad_trace_kernel covers only the tiles the lean pass leaves out
 };
 
 int grad_partials_per_tile(const CovParams &cp, int dp);

@@ -152,7 +152,13 @@ const char *dgp_version(void);
    slower on one GPU; same results either way),
    "leaf_variant" (1 = tensor-pipe 128-block leaf, the default; 0 = scalar leaf),
    "trsv_chained" (1 = each triangular solve is one launch whose CTAs hand the solved segments over through
-   flags, the default; 0 = one launch per 128-row block; same results).                                     */
+   flags, the default; 0 = one launch per 128-row block; same results),
+   "assembly_store" (lean SE assembly: 0 = 16-byte stores from registers, the default; 1 = staged chunk + bulk
+   stores, measured slower),
+   "grad_lean" (gradient trace pass: 1 = from 4096 points up the strictly-lower tiles take the lean Gram pass under
+   the conditions of the lean assembly -- Gram accuracy gate, pairwise distinct points; SE / RBF, ARD-SE in the
+   reference gradient mode, Matern orders 1-3 -- the default; 0 = exact differences everywhere; the two agree to
+   ~1e-13 relative).                                                                                        */
 int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value);
 /* Phase timings (ms, CUDA events) of the last energy/energy_grad/fit/predict call:
    [0] assemble [1] potrf [2] solves+logdet [3] inverse (trtri+lauum) [4] trace pass

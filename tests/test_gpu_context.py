@@ -1,0 +1,79 @@
+"""Context housekeeping through the C ABI: dgp_ctx_info, dgp_ctx_trim (handles stay valid, results unchanged),
+dgp_dist_info on an emulated grid, and the launch counter the bench reports as gpu_launches."""
+import numpy as np
+import pytest
+
+import dynaml_b200 as dg
+from oracle import gp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def ctx():
+    c = dg.Context(0)
+    yield c
+    c.close()
+
+
+def test_info_reports_the_device(ctx):
+    info = ctx.info()
+    assert info["device"] == 0
+    assert info["sm_count"] >= 100          # B200: 148
+    assert 0 < info["mem_free"] <= info["mem_total"]
+    assert info["mem_total"] > 100 * 2 ** 30
+
+
+def test_trim_keeps_handles_and_results(ctx):
+    X, y, Xs = orc.synthetic(1200, 4, seed=3, m=50)
+    k = dg.SEKernel(1.7, 1.1)
+    spec = k._spec(noise=0.2)
+    data = ctx.data_create(X, y)
+    try:
+        e0, g0 = ctx.energy_grad(data, spec)
+        model = ctx.fit(data, spec)
+        mu0, cov0, _, _ = ctx.predict(model, Xs)
+        free_before = ctx.info()["mem_free"]
+        ctx.trim()
+        assert ctx.info()["mem_free"] >= free_before       # the arena went back to the driver
+        e1, g1 = ctx.energy_grad(data, spec)                # data handle still valid, workspaces re-grow
+        mu1, cov1, _, _ = ctx.predict(model, Xs)            # model handle still valid
+        assert e1 == e0
+        assert np.array_equal(np.asarray(g1), np.asarray(g0))
+        assert np.array_equal(mu1, mu0) and np.array_equal(cov1, cov0)
+        ctx.model_destroy(model)
+    finally:
+        ctx.data_destroy(data)
+
+
+def test_launch_counter_counts_kernels(ctx):
+    X, y, _ = orc.synthetic(700, 3, seed=1)
+    data = ctx.data_create(X, y)
+    try:
+        spec = dg.SEKernel(1.5, 1.0)._spec(noise=0.3)
+        ctx.energy(data, spec)
+        a = ctx.launch_count()
+        ctx.energy(data, spec)
+        b = ctx.launch_count()
+        ctx.energy_grad(data, spec)
+        c = ctx.launch_count()
+        assert b - a >= 3                # assembly, at least one leaf, the solves
+        assert c - b > b - a             # the gradient adds the inverse and the trace pass
+    finally:
+        ctx.data_destroy(data)
+
+
+def test_dist_info_on_an_emulated_grid(ctx):
+    ctx.dist_init(None, 0, 1, 2, 2)
+    try:
+        info = ctx.dist_info()
+        assert info["grid"] == [2, 2]
+        assert info["emulated"] is True
+        assert info["nccl_ranks"] in (0, 1) and info["nccl_rank"] in (-1, 0)
+    finally:
+        ctx.dist_finalize()
+
+
+def test_dist_info_without_init_is_an_error(ctx):
+    with pytest.raises(dg.DgpError):
+        ctx.dist_info()
