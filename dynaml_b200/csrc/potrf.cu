@@ -609,10 +609,12 @@ int32_t potrf_init(Ctx *ctx) {
   return DGP_OK;
 }
 
-// Wider blocks amortise the per-tile prologue/epilogue of the trailing update, narrower ones shorten the
-// leaf -> panel -> update chain that bounds small N.  Measured on B200 with the tile leaf (scripts/tune_nb2.py,
-// profiles/tune_nb_r2.txt; ms at nb = 256 / 512 / 768): N = 8192 8.35 / 8.98 / 9.66, N = 16384 46.9 / 47.4 / 47.8,
-// N = 24576 147.9 / 146.9 / 147.7, N = 32768 (round 1) 404 / 386 / 382.
+// Outer block for a (remaining) matrix of size n.  Wider blocks amortise the per-tile prologue/epilogue of the
+// trailing update, narrower ones shorten the leaf -> panel -> update chain that bounds small sizes; the driver asks
+// again for every outer block with the size of what is left.  Measured on B200 (scripts/tune_nb2.py,
+// profiles/tune_nb_r2.txt; ms at fixed nb = 256 / 512 / 768 / this rule): N = 8192 8.28 / 9.01 / 9.63 / 8.23,
+// N = 16384 46.98 / 47.60 / 48.06 / 46.96, N = 24576 147.95 / 147.72 / 148.21 / 147.37, N = 32768 343.06 / 340.59 /
+// 340.53 / 340.13.
 int64_t potrf_outer_block(const Ctx *ctx, int64_t n) {
   return ctx->nb > 0 ? ctx->nb : (n >= 28672 ? 768 : (n >= 20480 ? 512 : 256));
 }
@@ -625,8 +627,10 @@ int32_t potrf_blocked(Ctx *ctx, double *A, int64_t lda, int64_t n, double *inv, 
 int32_t potrf_blocked_on(Ctx *ctx, cudaStream_t S, cudaStream_t P, double *A, int64_t lda, int64_t n, double *inv,
                          int *info, const char *scratch_name) {
   if (n % LB) return ctx->fail(DGP_ERR_SHAPE, "potrf: n=%lld must be a multiple of 128", (long long)n);
-  const int64_t nb = potrf_outer_block(ctx, n);
-  const bool la = (P != S) && n > nb;
+  // the outer block follows the size of what is left: the trailing matrix is a factorisation of that size in its own
+  // right, wide blocks where the trailing GEMM sets the pace, 256 where the leaf chain does (profiles/chain_timeline_r2.txt)
+  auto block_at = [&](int64_t c) { return potrf_outer_block(ctx, n - c); };
+  const bool la = (P != S) && n > block_at(0);
   if (!la) P = S;
   size_t ev = 0;
 
@@ -639,8 +643,9 @@ int32_t potrf_blocked_on(Ctx *ctx, cudaStream_t S, cudaStream_t P, double *A, in
   }
 
   cudaEvent_t rest_ev = nullptr;  // set when the block column about to be factored was updated in two parts
-  for (int64_t c0 = 0; c0 < n; c0 += nb) {
-    const int64_t w = (n - c0 < nb) ? (n - c0) : nb;
+  for (int64_t c0 = 0, w = 0; c0 < n; c0 += w) {
+    const int64_t nb = block_at(c0);
+    w = (n - c0 < nb) ? (n - c0) : nb;
     DGP_TRY(factor_block_column(ctx, P, A, lda, n, c0, w, inv, info, scratch, rest_ev));
     rest_ev = nullptr;
     const int64_t c1 = c0 + w;
@@ -650,7 +655,7 @@ int32_t potrf_blocked_on(Ctx *ctx, cudaStream_t S, cudaStream_t P, double *A, in
       DGP_CUDA_OK(ctx, cudaEventRecord(e, P));
       DGP_CUDA_OK(ctx, cudaStreamWaitEvent(S, e, 0));
     }
-    const int64_t w1 = (n - c1 < nb) ? (n - c1) : nb;
+    const int64_t nb1 = block_at(c1), w1 = (n - c1 < nb1) ? (n - c1) : nb1;
     // (a) trailing update restricted to the next block column.  With look-ahead only its first 128 columns are on
     //     the critical chain (the next leaf and its panel need nothing else), so they go first and the panel stream
     //     resumes as soon as they are done; the rest of the block column follows and is awaited before its own
