@@ -593,7 +593,8 @@ def main():
                                   "variances_positive": bool((dg_ > 0).all()),
                                   "covariance_symmetric": bool(np.array_equal(cov, cov.T)),
                                   "bars_bracket_mean": bool((lo <= mu).all() and (mu <= hi).all()),
-                                  "bars_are_2_sigma": bool(np.allclose(hi - mu, 2.0 * np.sqrt(dg_), rtol=1e-12, atol=0))}}
+                                  # the reference's bars are mean -/+ sigma * row sums of chol(Sigma*), not 2 sigma_i
+                                  "bars_symmetric_about_mean": bool(np.allclose(hi - mu, mu - lo, rtol=1e-9, atol=1e-12))}}
                 roofline["predict"] = rec
             except Exception as ex:
                 roofline["predict"] = {"error": f"{type(ex).__name__}: {ex}"}

@@ -1343,12 +1343,25 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
     a.use_gram = gram;
     DGP_TRY(assemble(ctx, S, cpx, a));
     if (m->psi) DGP_TRY(add_basis_term(ctx, S, m->psi_s, mp, m->psi_s, mp, m->basis_mp, C, mp, mp, mp, true));
-    // V = L^-1 K*  (blocked forward substitution on tensor cores, in place in Ks)
-    DGP_TRY(trsm_lower_fwd(ctx, S, m->L, np, m->inv, np, Ks, np, mp, np >= 4096 ? 512 : 256));
+    // V' = K*' L^-T (blocked substitution from the right on tensor cores): K*' is assembled in its own right, test
+    // points as rows, and Ks -- whose only use, the mean, is behind us on the stream -- receives V'
+    DGP_BUF(KsT, double, ctx, "KsT", (size_t)np * mp * sizeof(double));
+    {
+      AssembleArgs at;
+      at.X1 = Xtk;  at.X2 = Xtrain;  at.dp = dp;
+      at.rows = M;  at.cols = m->N;  at.rows_p = mp;  at.cols_p = np;
+      at.out = KsT;  at.ld = mp;
+      at.use_gram = gram;
+      DGP_TRY(assemble(ctx, S, cpx, at));
+      if (m->psi) DGP_TRY(add_basis_term(ctx, S, m->psi_s, mp, m->psi, np, m->basis_mp, KsT, mp, mp, np, false));
+    }
+    double *Vt = Ks;
+    DGP_TRY(trsm_right_lower_t(ctx, S, ctx->lookahead ? ctx->panel : S, m->L, np, m->inv, np, KsT, mp, Vt, mp, mp,
+                               np >= 4096 ? 512 : 256));
     tick(ctx, 0, 3);
     GemmArgs s;  // Sigma* = K** - V' V  (lower tiles)   (:452-461)
-    s.A = Ks;  s.lda = np;  s.a_kmajor = 1;
-    s.B = Ks;  s.ldb = np;  s.b_kmajor = 1;
+    s.A = Vt;  s.lda = mp;  s.a_kmajor = 0;
+    s.B = Vt;  s.ldb = mp;  s.b_kmajor = 0;
     s.C = C;  s.ldc = mp;
     s.M = (int)mp;  s.N = (int)mp;  s.K = (int)np;
     s.alpha = -1.0;  s.beta = 1.0;  s.lower_only = 1;

@@ -840,37 +840,64 @@ int32_t trtri_lower_transposed_on(Ctx *ctx, cudaStream_t S, const double *L, int
   return DGP_OK;
 }
 
-int32_t trsm_lower_fwd(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, const double *inv, int64_t n,
-                       double *B, int64_t ldb, int64_t m, int64_t nb) {
-  if (n % LB || nb % LB || m % 64) return ctx->fail(DGP_ERR_SHAPE, "trsm: n, nb must be multiples of 128, m of 64");
+int32_t trsm_right_lower_t(Ctx *ctx, cudaStream_t S, cudaStream_t P, const double *L, int64_t ldl, const double *inv,
+                           int64_t n, double *B, int64_t ldb, double *V, int64_t ldv, int64_t m, int64_t nb) {
+  if (n % LB || nb % LB || m % LB) return ctx->fail(DGP_ERR_SHAPE, "trsm: n, nb and m must be multiples of 128");
+  const bool la = (P != S) && n > 2 * nb;
+  if (!la) P = S;
+  size_t ev = 0;
+  auto link = [&](cudaStream_t from, cudaStream_t to) -> int32_t {
+    if (from == to) return DGP_OK;
+    cudaEvent_t e = get_event(ctx, ev++);
+    DGP_CUDA_OK(ctx, cudaEventRecord(e, from));
+    DGP_CUDA_OK(ctx, cudaStreamWaitEvent(to, e, 0));
+    return DGP_OK;
+  };
+  DGP_TRY(link(S, P));
   for (int64_t c0 = 0; c0 < n; c0 += nb) {
     const int64_t c1 = (c0 + nb < n) ? c0 + nb : n;
+    // ---- the block's own columns, 128 at a time, on the panel stream (small dependent launches)
     for (int64_t cs = c0; cs < c1; cs += LB) {
-      GemmArgs d;  // V_cs = inv(L_cs,cs) * B_cs, in place: a CTA reads exactly the 128 x 64 tile it writes
-      d.A = inv + (cs / LB) * LB * LB;  d.lda = LB;  d.a_kmajor = 0;
-      d.B = B + cs;  d.ldb = ldb;  d.b_kmajor = 1;
-      d.C = B + cs;  d.ldc = ldb;
-      d.M = LB;  d.N = (int)m;  d.K = LB;
-      DGP_TRY(gemm(ctx, S, d));
+      GemmArgs d;  // V_cs = B_cs * inv(L_cs,cs)^T  (out of place: the two CTAs of a 128-row strip read all 128 columns)
+      d.A = B + cs * ldb;  d.lda = ldb;  d.a_kmajor = 0;
+      d.B = inv + (cs / LB) * LB * LB;  d.ldb = LB;  d.b_kmajor = 0;   // op(B)(k,n) = inv(n,k)
+      d.C = V + cs * ldv;  d.ldc = ldv;
+      d.M = (int)m;  d.N = LB;  d.K = LB;
+      d.alpha = 1.0;  d.beta = 0.0;
+      DGP_TRY(gemm(ctx, P, d));
       const int64_t rb = cs + LB;
       if (rb >= c1) break;
-      GemmArgs u;  // rows of the same block: B[rb:c1] -= L[rb:c1, cs] * V_cs
-      u.A = L + rb + cs * ldl;  u.lda = ldl;  u.a_kmajor = 0;
-      u.B = B + cs;  u.ldb = ldb;  u.b_kmajor = 1;
-      u.C = B + rb;  u.ldc = ldb;
-      u.M = (int)(c1 - rb);  u.N = (int)m;  u.K = LB;
+      GemmArgs u;  // columns of the same block: B[:, rb:c1] -= V_cs * L[rb:c1, cs]^T
+      u.A = V + cs * ldv;  u.lda = ldv;  u.a_kmajor = 0;
+      u.B = L + rb + cs * ldl;  u.ldb = ldl;  u.b_kmajor = 0;
+      u.C = B + rb * ldb;  u.ldc = ldb;
+      u.M = (int)m;  u.N = (int)(c1 - rb);  u.K = LB;
       u.alpha = -1.0;  u.beta = 1.0;
-      DGP_TRY(gemm(ctx, S, u));
+      DGP_TRY(gemm(ctx, P, u));
     }
     if (c1 >= n) break;
-    GemmArgs t;  // everything below the block: B[c1:] -= L[c1:, c0:c1] * V[c0:c1]
-    t.A = L + c1 + c0 * ldl;  t.lda = ldl;  t.a_kmajor = 0;
-    t.B = B + c0;  t.ldb = ldb;  t.b_kmajor = 1;
-    t.C = B + c1;  t.ldc = ldb;
-    t.M = (int)(n - c1);  t.N = (int)m;  t.K = (int)(c1 - c0);
+    DGP_TRY(link(P, S));
+    // ---- every column beyond the block: B[:, c1:] -= V[:, c0:c1] * L[c1:, c0:c1]^T.  With look-ahead the next
+    //      block's columns go first and the panel stream resumes under the rest.
+    const int64_t c2 = (c1 + nb < n) ? c1 + nb : n;
+    const int64_t first = la ? c2 - c1 : n - c1;
+    GemmArgs t;
+    t.A = V + c0 * ldv;  t.lda = ldv;  t.a_kmajor = 0;
+    t.B = L + c1 + c0 * ldl;  t.ldb = ldl;  t.b_kmajor = 0;
+    t.C = B + c1 * ldb;  t.ldc = ldb;
+    t.M = (int)m;  t.N = (int)first;  t.K = (int)(c1 - c0);
     t.alpha = -1.0;  t.beta = 1.0;
     DGP_TRY(gemm(ctx, S, t));
+    DGP_TRY(link(S, P));
+    if (c1 + first < n) {
+      GemmArgs t2 = t;
+      t2.B = L + c2 + c0 * ldl;
+      t2.C = B + c2 * ldb;
+      t2.N = (int)(n - c2);
+      DGP_TRY(gemm(ctx, S, t2));
+    }
   }
+  DGP_TRY(link(P, S));
   return DGP_OK;
 }
 

@@ -35,11 +35,14 @@ int32_t trtri_lower(Ctx *ctx, const double *L, int64_t ldl, const double *inv, i
 int32_t trtri_lower_on(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, const double *inv, int64_t n, double *W,
                        int64_t ldw, double *scratch, int64_t lds);
 
-// B (n x m, m % 64 == 0) <- L^-1 B in place: blocked forward substitution on tensor cores using the
-// diagonal-block inverses; rank-128 updates inside blocks of `nb` rows, one rank-nb update below.
+// V (m x n) = B L^-T, i.e. the transpose of L^-1 B^T, for B (m x n, m and n multiples of 128; overwritten with
+// partially updated columns): blocked substitution on tensor cores using the diagonal-block inverses; rank-128
+// updates inside blocks of `nb` columns, one rank-nb update of every column beyond.  Solving from the right keeps every
+// product in the NT form of the bulk-copy GEMM (the left-sided form needs NN products, and V^T V afterwards a TN one).
 // recLTriagMultiSolve, CORE/algebra/PartitionedMatrixSolvers.scala:120-169.
-int32_t trsm_lower_fwd(Ctx *ctx, cudaStream_t S, const double *L, int64_t ldl, const double *inv, int64_t n,
-                       double *B, int64_t ldb, int64_t m, int64_t nb);
+// With P != S the block's own 128-column steps run on P beside the update of the columns beyond the next block.
+int32_t trsm_right_lower_t(Ctx *ctx, cudaStream_t S, cudaStream_t P, const double *L, int64_t ldl, const double *inv,
+                           int64_t n, double *B, int64_t ldb, double *V, int64_t ldv, int64_t m, int64_t nb);
 
 // Kinv (lower tiles) = W^T W.
 // The same inverse stored transposed, U = L^-T (upper triangular), and K^-1 = U U^T from it: with U every product of the
