@@ -2,7 +2,9 @@
 the exact value of the reference's formulas, not merely against another float64 evaluation.
 
   * kernel entries: <= 1e-12 relative per entry, every kernel kind of the path (SURVEY 7.1);
-  * energy and every gradient component at the stress noise sigma = 1e-3 (sigma^2 = 1e-6): <= 1e-9 relative, and the
+  * energy and every gradient component at the stress noise sigma = 1e-3 (sigma^2 = 1e-6), and with 1e-6 itself as the
+    diagonal term (the reference's DiracKernel adds |sigma|, not sigma^2: both readings of the north star's
+    "sigma^2 >= 1e-6" are covered): <= 1e-9 relative, and the
     device is no further from the extended value than ten times the float64 LAPACK oracle is (or 1e-10): the device
     is not the inaccurate side of any oracle comparison."""
 import math
@@ -49,9 +51,10 @@ def test_kernel_entries_within_1e12_of_extended(name, d):
     assert float(err.max()) <= TOL_K, float(err.max())
 
 
+@pytest.mark.parametrize("noise", [1e-3, 1e-6])   # sigma = 1e-3 (sigma^2 = 1e-6), and 1e-6 added to the diagonal itself (Q4)
 @pytest.mark.parametrize("name", ["se", "ard", "matern2"])
-def test_stress_noise_energy_and_gradient_against_extended(name):
-    n, d, noise = 512, 8, 1e-3
+def test_stress_noise_energy_and_gradient_against_extended(name, noise):
+    n, d = 512, 8
     X, y, _ = orc.synthetic(n, d, seed=n)
     k, ok = pairs(d)[name]
     model = dg.GPRegression(k, dg.DiracKernel(noise), list(zip(X, y)))
