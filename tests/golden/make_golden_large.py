@@ -192,6 +192,30 @@ def c3():
     return {"n": 32768, "d": 16, "seed": 0, "kernel": "matern", "p": 2, "l": 4.0, "noise": 0.1, **r}
 
 
+@case
+def c2_predict():
+    """Posterior at a BASELINE size: the C2 model (N = 8192, d = 8, ARD-SE, noise 0.1) at 192 fresh test points:
+    mean, covariance (diagonal, first 8 x 8 block, one far-apart pair), error bars at sigma = 2 (gp_oracle.predictive /
+    error_bars: dpotrf + dtrtrs)."""
+    X, y, Xs = orc.synthetic(8192, 8, seed=0, m=192)
+    cov = ard_kernel(8)
+    t0 = time.perf_counter()
+    K = kernel_matrix(cov, X, 0.1)
+    c, info = lapack.dpotrf(K, lower=1, overwrite_a=1)
+    assert info == 0
+    del K
+    alpha = sla.solve_triangular(c, sla.solve_triangular(c, y, lower=True), lower=True, trans="T")
+    Ks = cov.value(X, Xs)
+    v = sla.solve_triangular(c, Ks, lower=True)
+    post = cov.value(Xs, Xs) - v.T @ v
+    mu = Ks.T @ alpha
+    lo, hi = orc.error_bars(mu, post, 2.0)
+    return {"n": 8192, "d": 8, "seed": 0, "m": 192, "kernel": "ard", "noise": 0.1, "sigma": 2.0,
+            "bandwidths": [math.sqrt(8) * (1.0 + 0.05 * i) for i in range(8)], "amplitude": 1.0,
+            "mean": mu.tolist(), "var": np.diag(post).tolist(), "cov_block": post[:8, :8].tolist(),
+            "cov_far": float(post[191, 3]), "lo": lo.tolist(), "hi": hi.tolist(), "seconds": time.perf_counter() - t0}
+
+
 def selftest():
     """The blocked formulation against gp_oracle.energy / grad_energy at a size the oracle does directly."""
     global BLOCK
