@@ -439,6 +439,58 @@ cudaEvent_t misc_event(Ctx *ctx, size_t i) {
   return ctx->ev_misc[i];
 }
 
+// Device matrix (column-major, ld_src) -> host matrix in pageable memory (ld_dst).  A transfer into pageable memory
+// is staged by the driver at a few GB/s; from OUT_MIN bytes up it goes instead through two pinned 16 MB buffers on a
+// stream of its own, the DMA of one chunk overlapping the host copy of the previous one.  Waits for `ready` (an event
+// on the producing stream; nullptr: everything enqueued on S so far) and returns when the data is in `dst`; work
+// enqueued on S after `ready` keeps running underneath.
+constexpr size_t OUT_CHUNK = (size_t)16 << 20, OUT_MIN = (size_t)32 << 20;
+
+int32_t copy_out_2d(Ctx *ctx, cudaStream_t S, cudaEvent_t ready, double *dst, int64_t ld_dst, const double *src,
+                    int64_t ld_src, int64_t rows, int64_t cols) {
+  if (rows <= 0 || cols <= 0) return DGP_OK;
+  if ((size_t)rows * cols * sizeof(double) < OUT_MIN || (size_t)rows * sizeof(double) > OUT_CHUNK) {
+    if (ready) DGP_CUDA_OK(ctx, cudaStreamWaitEvent(S, ready, 0));
+    DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst, ld_dst * sizeof(double), src, ld_src * sizeof(double), rows * sizeof(double),
+                                       cols, cudaMemcpyDeviceToHost, S));
+    DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
+    return DGP_OK;
+  }
+  if (!ctx->out_stream) {
+    DGP_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      DGP_CUDA_OK(ctx, cudaMallocHost(&ctx->h_out[b], OUT_CHUNK));
+      DGP_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->out_ev[b], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t O = ctx->out_stream;
+  if (!ready) {
+    ready = misc_event(ctx, 15);
+    DGP_CUDA_OK(ctx, cudaEventRecord(ready, S));
+  }
+  DGP_CUDA_OK(ctx, cudaStreamWaitEvent(O, ready, 0));
+  const int64_t cc = (int64_t)(OUT_CHUNK / ((size_t)rows * sizeof(double)));
+  auto drain = [&](int64_t c0, int b) -> int32_t {
+    DGP_CUDA_OK(ctx, cudaEventSynchronize(ctx->out_ev[b]));
+    const int64_t n = (cols - c0 < cc) ? cols - c0 : cc;
+    for (int64_t c = 0; c < n; ++c)
+      memcpy(dst + (size_t)(c0 + c) * ld_dst, ctx->h_out[b] + (size_t)c * rows, (size_t)rows * sizeof(double));
+    return DGP_OK;
+  };
+  int64_t prev = -1;
+  int i = 0;
+  for (int64_t c0 = 0; c0 < cols; c0 += cc, ++i) {
+    const int b = i & 1;
+    const int64_t n = (cols - c0 < cc) ? cols - c0 : cc;
+    DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(ctx->h_out[b], rows * sizeof(double), src + (size_t)c0 * ld_src,
+                                       ld_src * sizeof(double), rows * sizeof(double), n, cudaMemcpyDeviceToHost, O));
+    DGP_CUDA_OK(ctx, cudaEventRecord(ctx->out_ev[b], O));
+    if (prev >= 0) DGP_TRY(drain(prev, b ^ 1));
+    prev = c0;
+  }
+  return drain(prev, (i - 1) & 1);
+}
+
 // Stream pair of an evaluation slot; slot 0 is the context's own pair.
 int32_t slot_streams(Ctx *ctx, int slot, cudaStream_t *S, cudaStream_t *P) {
   if (slot == 0) {
@@ -724,6 +776,11 @@ int32_t dgp_ctx_destroy(dgp_ctx *ctx) {
   cudaFreeHost(ctx->h_info);
   cudaFreeHost(ctx->h_scal);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->h_out[b]) cudaFreeHost(ctx->h_out[b]);
+    if (ctx->out_ev[b]) cudaEventDestroy(ctx->out_ev[b]);
+  }
+  if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
   if (ctx->data_pool) cudaMemPoolDestroy(ctx->data_pool);
   for (int i = 1; i < 4; ++i) {
     if (ctx->slot_S[i]) cudaStreamDestroy(ctx->slot_S[i]);
@@ -1369,23 +1426,27 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
     DGP_TRY(mirror_lower(ctx, S, C, mp, mp));
     tick(ctx, 0, 4);
   }
+  cudaEvent_t cov_ready = misc_event(ctx, 14);
+  DGP_CUDA_OK(ctx, cudaEventRecord(cov_ready, S));
   DGP_CUDA_OK(ctx, cudaMemcpyAsync(mean, dmean, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, S));
-  if (cov)
-    DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(cov, ldcov * sizeof(double), C, mp * sizeof(double), M * sizeof(double), M,
-                                       cudaMemcpyDeviceToHost, S));
   int32_t ret = DGP_OK;
+  std::vector<double> hbar;
   if (lo) {
-    // error bars: mean -/+ |sigma| * chol(Sigma*) . 1   (BlockedMultiVariateGaussian.scala:58-68)
+    // error bars: mean -/+ |sigma| * chol(Sigma*) . 1   (BlockedMultiVariateGaussian.scala:58-68); enqueued here,
+    // finished on the host below, so that the second Cholesky runs underneath the copy-out of Sigma*
     DGP_BUF(Lp, double, ctx, "plpost", (size_t)mp * mp * sizeof(double));
     DGP_BUF(pinv, double, ctx, "pinv", (size_t)mp * TILE * sizeof(double));
     DGP_TRY(copy_block(ctx, S, C, mp, Lp, mp, mp, mp));
     DGP_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_info, 0, sizeof(int), S));
     DGP_TRY(potrf_blocked(ctx, Lp, mp, mp, pinv, ctx->d_info));
     DGP_TRY(lower_row_sums(ctx, S, Lp, mp, mp, dbar));
-    std::vector<double> hbar((size_t)M);
+    hbar.resize((size_t)M);
     DGP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, S));
     DGP_CUDA_OK(ctx, cudaMemcpyAsync(hbar.data(), dbar, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, S));
-    DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
+  }
+  if (cov) DGP_TRY(copy_out_2d(ctx, S, cov_ready, cov, ldcov, C, mp, M, M));
+  DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
+  if (lo) {
     if (ctx->h_info[0] != 0) {
       for (int64_t i = 0; i < M; ++i) lo[i] = hi[i] = nan("");
       ret = ctx->fail(DGP_ERR_NOT_PD, "posterior covariance is not positive definite (pivot %d)", ctx->h_info[0] - 1);
@@ -1456,8 +1517,7 @@ int32_t dgp_kernel_matrix(dgp_ctx *ctx, const dgp_kernel_spec *spec, const doubl
   DGP_TRY(assemble(ctx, S, cp, a));
   if (sym) DGP_TRY(mirror_lower(ctx, S, Kd, n1p, n1p));
   tick(ctx, 0, 1);
-  DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(out, ld * sizeof(double), Kd, n1p * sizeof(double), N1 * sizeof(double), N2,
-                                     cudaMemcpyDeviceToHost, S));
+  DGP_TRY(copy_out_2d(ctx, S, nullptr, out, ld, Kd, n1p, N1, N2));
   DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
   for (int i = 0; i < 16; ++i) ctx->timings[i] = 0.0;
   if (ctx->timing) {
@@ -1502,8 +1562,7 @@ int32_t dgp_data_kernel_block(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_
   a.nodup = diag ? points_stay_distinct(D->has_dup, sp, D->d) : 0;
   DGP_TRY(assemble(ctx, S, cp, a));
   if (diag) DGP_TRY(mirror_lower(ctx, S, Kd, rp, rp));
-  DGP_CUDA_OK(ctx, cudaMemcpy2DAsync(out, ld * sizeof(double), Kd, rp * sizeof(double), nrows * sizeof(double), ncols,
-                                     cudaMemcpyDeviceToHost, S));
+  DGP_TRY(copy_out_2d(ctx, S, nullptr, out, ld, Kd, rp, nrows, ncols));
   DGP_CUDA_OK(ctx, cudaStreamSynchronize(S));
   return DGP_OK;
 }

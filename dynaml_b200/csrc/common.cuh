@@ -70,6 +70,10 @@ struct Ctx {
   cudaMemPool_t data_pool = nullptr;  // the library's own stream-ordered pool for dgp_data blocks (never trimmed at syncs)
   void *h_stage = nullptr;   // pinned, grow-only staging buffer of dgp_data_create
   size_t h_stage_bytes = 0;
+  // large results leave through two pinned staging buffers on their own stream (copy_out_2d in api.cu)
+  double *h_out[2] = {nullptr, nullptr};
+  cudaStream_t out_stream = nullptr;
+  cudaEvent_t out_ev[2] = {nullptr, nullptr};
   DistState *dist = nullptr;
   // CUDA graphs of the blocked Cholesky (potrf.cu): one executable graph per (matrix, size, streams); the
   // factorisation is ~5 launches per 128 columns, all with arguments that do not change between evaluations

@@ -77,3 +77,23 @@ def test_dist_info_on_an_emulated_grid(ctx):
 def test_dist_info_without_init_is_an_error(ctx):
     with pytest.raises(dg.DgpError):
         ctx.dist_info()
+
+
+def test_large_results_leave_through_the_staged_copy(ctx):
+    """Results of 32 MB and more are copied out through pinned staging chunks on a stream of their own (api.cu,
+    copy_out_2d): same values as the oracle, ragged sizes so that the last chunk is partial."""
+    k, ok = dg.SEKernel(1.9, 1.2), orc.Kernel("se", {"bandwidth": 1.9, "amplitude": 1.2})
+    X, y, Xs = orc.synthetic(2300, 3, seed=4, m=2101)
+    C = k.buildCrossKernelMatrix(X, Xs)                      # 2300 x 2101 doubles = 38.7 MB
+    Co = ok.value(X, Xs)
+    assert C.shape == Co.shape
+    assert float((np.abs(C - Co) / np.maximum(np.abs(Co), 1e-290)).max()) <= 1e-12
+    model = dg.GPRegression(k, dg.DiracKernel(0.3), list(zip(X[:400], y[:400])))
+    post = model.predictiveDistribution(Xs)                  # 2101 x 2101 covariance = 35.3 MB
+    mu, cv = orc.predictive(ok, 0.3, X[:400], y[:400], Xs)
+    assert float(np.abs(post.mu - mu).max()) <= 1e-9 * float(np.abs(mu).max())
+    assert float(np.abs(np.asarray(post.covariance) - cv).max()) <= 1e-9 * float(np.abs(cv).max())
+    res = model.predictionWithErrorBars(list(Xs[:40]), 2)    # bars enqueued before a (small) copy-out
+    lo_o, hi_o = orc.error_bars(*orc.predictive(ok, 0.3, X[:400], y[:400], Xs[:40]), 2.0)
+    assert np.allclose([r[2] for r in res], lo_o, rtol=0, atol=1e-8 * float(np.abs(hi_o).max()))
+    model._drop_data()
