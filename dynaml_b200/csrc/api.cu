@@ -863,7 +863,7 @@ int32_t dgp_ctx_set_option(dgp_ctx *ctx, const char *key, int64_t value) {
     if (value < 0 || value > 1) return ctx->fail(DGP_ERR_ARG, "assembly_store must be 0 (direct) or 1 (bulk)");
     ctx->assembly_store = (int)value;
   } else if (!strcmp(key, "batch_streams")) {
-    if (value < 1 || value > 4) return ctx->fail(DGP_ERR_ARG, "batch_streams must be in 1..4");
+    if (value < 0 || value > 4) return ctx->fail(DGP_ERR_ARG, "batch_streams must be in 0..4 (0 = automatic)");
     ctx->batch_streams = (int)value;
   } else if (!strcmp(key, "timing")) {
     ctx->timing = value != 0;
@@ -1019,7 +1019,10 @@ int32_t dgp_energy_batch(dgp_ctx *ctx, const dgp_data *D, const dgp_kernel_spec 
   // evaluation slots (each with its own stream pair and workspace): the GPU never waits for the
   // host between candidates, and the panel chain of one candidate overlaps the trailing updates of
   // another.
-  int nslots = ctx->batch_streams < 1 ? 1 : (ctx->batch_streams > 4 ? 4 : ctx->batch_streams);
+  // automatic choice (0): four below N = 12288 (N = 8192: 164 against 158 candidates/s with three), three above (N = 16384:
+  // no difference, and a slot holds an N x N workspace); scripts/bench_batch_nb.py
+  int nslots = ctx->batch_streams == 0 ? (D->Np <= 12288 ? 4 : 3) : ctx->batch_streams;
+  nslots = nslots < 1 ? 1 : (nslots > 4 ? 4 : nslots);
   if (n < nslots) nslots = n > 0 ? n : 1;
   double batch_ms = 0.0;
   for (int32_t base = 0; base < n; base += 4096) {

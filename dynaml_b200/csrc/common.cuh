@@ -57,7 +57,7 @@ struct Ctx {
   int assembly = 0;   // 0: Gram/DMMA assembly when its error bound allows, 1: always exact differences, 2: force Gram
   int grad_lean = 1;       // gradient trace pass: 1 = lean Gram epilogue where the lean assembly's conditions hold, 0 = exact differences
   int assembly_store = 0;  // lean SE assembly: 0 = 16-byte st.global from registers, 1 = staged chunk + bulk (TMA) stores
-  int batch_streams = 3;  // dgp_energy_batch evaluates this many candidates concurrently (1..4)
+  int batch_streams = 0;  // dgp_energy_batch evaluates this many candidates concurrently (1..4; 0 = by size: 4 up to N = 12288, else 3)
   cudaStream_t slot_S[4] = {nullptr, nullptr, nullptr, nullptr};  // extra (main, panel) stream pairs, created lazily
   cudaStream_t slot_P[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t slot_ev[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -139,7 +139,7 @@ int32_t dgp_ctx_trim(dgp_ctx *ctx);
 int32_t dgp_ctx_info(dgp_ctx *ctx, int64_t *out, int32_t n);
 const char *dgp_version(void);
 /* Tunables: "nb" (outer Cholesky block, multiple of 128; 0 = auto, the default), "lookahead"
-   (0/1), "timing" (0/1), "batch_streams" (1..4 candidates of dgp_energy_batch in flight; default 3),
+   (0/1), "timing" (0/1), "batch_streams" (1..4 candidates of dgp_energy_batch in flight; 0 = by size, the default: 4 up to N = 12288, else 3),
    "assembly" (0 = Gram/DMMA kernel when its error bound allows, 1 = exact differences, 2 = force Gram).
    GEMM kernel selection (results are bit-identical for every choice): "gemm_variant" (4 = bulk-copy /
    mbarrier kernel where "gemm_v4_mask" allows, the default; 2 = cp.async kernel everywhere), "gemm_v4_mask" and
