@@ -97,3 +97,28 @@ def test_large_results_leave_through_the_staged_copy(ctx):
     lo_o, hi_o = orc.error_bars(*orc.predictive(ok, 0.3, X[:400], y[:400], Xs[:40]), 2.0)
     assert np.allclose([r[2] for r in res], lo_o, rtol=0, atol=1e-8 * float(np.abs(hi_o).max()))
     model._drop_data()
+
+
+def test_repeated_calls_are_bitwise_reproducible(ctx):
+    """Race detection by determinism: every reduction in the library has a fixed order, so repeated evaluations must
+    agree to the last bit -- whatever the interleaving of the look-ahead streams (Cholesky panel stream, solves under
+    the inverse, triangular solve of the prediction) and of the staged copy-out."""
+    X, y, Xs = orc.synthetic(4301, 6, seed=21, m=520)
+    spec = dg.GenericMaternKernel(2.4, 2)._spec(noise=0.2)
+    data = ctx.data_create(X, y)
+    try:
+        e0, g0 = ctx.energy_grad(data, spec)
+        for _ in range(6):
+            e, g = ctx.energy_grad(data, spec)
+            assert e == e0 and np.array_equal(np.asarray(g), np.asarray(g0), equal_nan=True)
+        eb, _ = ctx.energy_batch(data, [spec] * 7)
+        assert all(v == e0 for v in eb)                       # concurrent slots: same bits as the single evaluation
+        model = ctx.fit(data, spec)
+        mu0, cov0, lo0, hi0 = ctx.predict(model, Xs, want_cov=True, want_bars=True, sigma=2.0)
+        for _ in range(3):
+            mu, cov, lo, hi = ctx.predict(model, Xs, want_cov=True, want_bars=True, sigma=2.0)
+            assert np.array_equal(mu, mu0) and np.array_equal(cov, cov0)
+            assert np.array_equal(lo, lo0) and np.array_equal(hi, hi0)
+        ctx.model_destroy(model)
+    finally:
+        ctx.data_destroy(data)
