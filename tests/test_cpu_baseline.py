@@ -48,3 +48,30 @@ def test_time_parts_and_extrapolation():
     assert cb.extrapolate(2.0, 3.0, 100, 200) == pytest.approx(2.0 * 4 + 3.0 * 8)
     assert cb.extrapolate(2.0, 3.0, 100, 400, n3_sample=200) == pytest.approx(2.0 * 16 + 3.0 * 8)
     assert cb.use_all_cores() >= 1
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the arm the driver runs beside ours) on tiny samples: one JSON line with the same
+    metric / unit / config as the GPU arm, the impl tag, a cpu_baseline record and an e2e object without copies."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample-n", "256", "--cpu-sample-n3", "512"], capture_output=True, text=True, timeout=600,
+                         cwd=str(root))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference"
+    assert line["metric"] == "GP energy+grad evals/s (N=32k FP64)" and line["unit"] == "evals/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["dtype"] == "f64"
+    assert line["config"]["N"] == 32768 and line["config"]["d"] == 16
+    assert line["value"] > 0 and line["ms_per_step"] > 0
+    cpu = line["cpu_baseline"]
+    assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["extrapolated"] is True and cpu["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0
