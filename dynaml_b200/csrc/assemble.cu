@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(ATHREADS, 3)
       reinterpret_cast<double2 *>(dst)[c] = make_double2(sc * v[2 * c], sc * v[2 * c + 1]);
     (is_row ? nx : ny)[pidx] = nrm;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) tab[tid * 4 + e] = T.v[(tid * 4 + e) >> 4];
+    for (int e = 0; e < 4; ++e) tab[e * 256 + tid] = T.v[(e * 256 + tid) >> 4];   // consecutive lanes, consecutive words
   }
   __syncthreads();
 

@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(GTHREADS, 2)
     }
     sal[tid] = a.alpha[pt];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) tab[tid * 4 + e] = T.v[(tid * 4 + e) >> 4];
+    for (int e = 0; e < 4; ++e) tab[e * 256 + tid] = T.v[(e * 256 + tid) >> 4];   // consecutive lanes, consecutive words
   }
   __syncthreads();
 
