@@ -430,6 +430,10 @@ void tick(Ctx *ctx, int slot, int i, cudaStream_t on = nullptr) {
   if (ctx->timing && slot == 0) cudaEventRecord(ctx->tev[i], on ? on : ctx->stream);
 }
 
+// misc_event slots: 2 * slot and 2 * slot + 1 (slot = 0..3) fork / join the solves of an evaluation slot
+constexpr size_t EV_COV_READY = 14;   // dgp_predict: Sigma* complete on the main stream
+constexpr size_t EV_OUT_READY = 15;   // copy_out_2d: everything enqueued so far
+
 cudaEvent_t misc_event(Ctx *ctx, size_t i) {
   while (ctx->ev_misc.size() <= i) {
     cudaEvent_t e;
@@ -465,7 +469,7 @@ int32_t copy_out_2d(Ctx *ctx, cudaStream_t S, cudaEvent_t ready, double *dst, in
   }
   cudaStream_t O = ctx->out_stream;
   if (!ready) {
-    ready = misc_event(ctx, 15);
+    ready = misc_event(ctx, EV_OUT_READY);
     DGP_CUDA_OK(ctx, cudaEventRecord(ready, S));
   }
   DGP_CUDA_OK(ctx, cudaStreamWaitEvent(O, ready, 0));
@@ -1429,7 +1433,7 @@ int32_t dgp_predict(dgp_ctx *ctx, const dgp_model *m, const double *Xs, int64_t 
     DGP_TRY(mirror_lower(ctx, S, C, mp, mp));
     tick(ctx, 0, 4);
   }
-  cudaEvent_t cov_ready = misc_event(ctx, 14);
+  cudaEvent_t cov_ready = misc_event(ctx, EV_COV_READY);
   DGP_CUDA_OK(ctx, cudaEventRecord(cov_ready, S));
   DGP_CUDA_OK(ctx, cudaMemcpyAsync(mean, dmean, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, S));
   int32_t ret = DGP_OK;
