@@ -22,7 +22,10 @@ The two sharded configurations of the north star run in the same invocation, at 
                       value (tests/golden/large.json);
   roofline.c5      -- config C5: 256 hyper-parameter candidates at N = 16384 through GridSearch.getEnergyLandscape,
                       candidates sharded round-robin over the ranks -> candidates/s, with three candidates compared
-                      against committed oracle energies.
+                      against committed oracle energies;
+  roofline.predict -- (rank 0) the prediction half of config C3: fit, then mean + covariance + error
+                      bars of 4096 test points: device times of the triangular solve and of V'V with their fractions of the
+                      DMMA peak, the wall time of dgp_predict including the copy-out, size-independent checks.
 
 Roofline: the dominant kernel is the FP64 DMMA GEMM (dgemm_dmma_v4_kernel).  `achieved` is the algorithmic flops of
 the launch the Cholesky repeats -- the first trailing update, C -= P P^T over the lower tiles with M = N - nb rows and
