@@ -138,7 +138,8 @@ int32_t dgp_ctx_trim(dgp_ctx *ctx);
 /* out[0] CUDA device ordinal, out[1] SM count, out[2] total / out[3] free device memory in bytes; n >= 4. */
 int32_t dgp_ctx_info(dgp_ctx *ctx, int64_t *out, int32_t n);
 const char *dgp_version(void);
-/* Tunables: "nb" (outer Cholesky block, multiple of 128; 0 = auto, the default), "lookahead"
+/* Tunables: "nb" (outer Cholesky block, multiple of 128; 0 = auto, the default: chosen per outer block from the size
+   of what is left to factor), "lookahead"
    (0/1), "timing" (0/1), "batch_streams" (1..4 candidates of dgp_energy_batch in flight; 0 = by size, the default: 4 up to N = 12288, else 3),
    "assembly" (0 = Gram/DMMA kernel when its error bound allows, 1 = exact differences, 2 = force Gram).
    GEMM kernel selection (results are bit-identical for every choice): "gemm_variant" (4 = bulk-copy /
